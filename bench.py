@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — train clips/sec of the TSM-MobileNetV2 MTMM step (BASELINE.json metric), 8x224^2 clips.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--dtype bf16|fp32]
+
+N>1 is launched by the driver as `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`
+(one rank per GPU, NCCL).  A "step" is one pass of the hot path over one batch of synthetic clips:
+zero-grad, forward (backbone + classifier + depth decoder), MTMM loss, backward, gradient all-reduce,
+SGD update.  Workload at N=1: BASELINE.json configs[1] — MTMM stage-1, TSM-MobileNetV2 RGB +
+pseudo-depth, batch 32/GPU, bf16 activations, 83 classes.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job clips/s with inputs resident in HBM; `e2e` = the
+same through the public call with pinned HOST buffers (H2D of every batch and a D2H loss read inside
+the timed region, next batch's copy overlapped on a side stream).
+`--impl reference`: the reference's own algorithm on the host cores (the torch-fp32 oracle port of
+the reference modules: the reference is Python and is not present on the GPU box), rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "train clips/sec TSM-MBv2 8x224^2"
+UNIT = "clips/s"
+T_SEG, SIZE, NUM_CLASS = 8, 224, 83
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--temporal", default="tsm", choices=["tsm", "action", "none"])
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period=0.1):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.max_mhz = period, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(temporal: str, clips: int, steps: int, warmup: int):
+    """clips/s of the reference MTMM step (fwd + loss + bwd + SGD) on all host cores, fp32."""
+    from oracle import ref_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.clone_state(O.build_mtmm_state(NUM_CLASS, temporal, 8, seed=0))
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.00125, momentum=0.9, weight_decay=5e-4)
+    rgb, depth, labels = O.synthetic_clip_batch(clips, T_SEG, SIZE, NUM_CLASS, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.mtmm_train_step(sd, rgb, depth, labels, T_SEG, temporal, 8, True)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return clips / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    warm = max(1, min(args.warmup, 2))
+    v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MTMM stage-1 step, {args.temporal.upper()}-MobileNetV2 RGB+pseudo-depth, "
+                               f"8x224^2, 83 classes; CPU sample = {args.cpu_clips} clips/step"},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32, "
+                                   f"{cores} threads"},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import ehgr_b200
+    from ehgr_b200 import _lib
+
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    torch.manual_seed(1)  # train_mtmm.py:43 default seed; identical initial weights on every rank
+    with quiet():
+        model = ehgr_b200.tsn_mtmm.TSN(NUM_CLASS, T_SEG, 'RGB', is_shift=(args.temporal != "none"), partial_bn=False,
+                                       base_model='mobilenetv2', shift_div=8, dropout=0.5, img_feature_dim=224,
+                                       pretrain=None, consensus_type='avg', fc_lr5=True, modal='rgb_depth',
+                                       temporal_module=("tsm" if args.temporal == "tsm" else "action"))
+    model = model.to(dev)
+    model.train()
+    step = ehgr_b200.train_step.MTMMTrainStep(model, compute_dtype=dtype)
+
+    B = args.batch
+    g = torch.Generator().manual_seed(100 + rank)
+    n_host = 2
+    host = [(torch.randn(B, T_SEG, 3, SIZE, SIZE, generator=g).pin_memory(),
+             torch.rand(B, T_SEG, 1, SIZE, SIZE, generator=g).pin_memory(),
+             torch.randint(0, NUM_CLASS, (B,), generator=g).pin_memory()) for _ in range(n_host)]
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- leg 1: inputs resident in HBM ----
+    def leg_resident(k):
+        for i in range(k):
+            step.run(*resident[i % n_host])
+
+    leg_resident(args.warmup)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    prof = _lib.KernelTimer.begin()
+    ms = timed(leg_resident, args.steps)
+    kernel_times = _lib.KernelTimer.end(prof)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+
+    # ---- leg 2: end to end from pinned host memory, next batch prefetched on a copy stream ----
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def leg_e2e(k):
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            nxt = step.stage(*host[0])
+        last = None
+        for i in range(k):
+            cur.wait_stream(copy_stream)
+            batch = nxt
+            for t in batch:
+                t.record_stream(cur)
+            if i + 1 < k:
+                with torch.cuda.stream(copy_stream):
+                    nxt = step.stage(*host[(i + 1) % n_host])
+            loss = step.run(*batch)
+            if last is not None:
+                last.item()          # D2H read of the previous step's loss (keeps one step in flight)
+            last = loss
+        last.item()
+
+    leg_e2e(2)
+    ms_e2e = timed(leg_e2e, args.steps)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        clips = B * world * args.steps
+        value = clips / (ms / 1e3)
+        e2e = clips / (ms_e2e / 1e3)
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"MTMM stage-1 step (fwd+loss+bwd+allreduce+SGD), {args.temporal.upper()}-MobileNetV2 "
+                                   f"RGB+pseudo-depth, 8x224^2, 83 classes, train-mode BN",
+                       "clips_per_gpu": B, "global_clips": B * world, "parallelism": f"dp{world}",
+                       "l2": "activations >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG),
+            "peaks": pk_kind,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1)
+            line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"3 steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32 oracle "
+                                              f"port of the reference modules, {cores} threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

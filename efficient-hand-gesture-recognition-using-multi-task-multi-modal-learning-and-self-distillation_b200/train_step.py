@@ -1,0 +1,154 @@
+"""Data-parallel training step: the unit the reference's ``train()`` loops execute
+(train_mtmm.py:205-245, train_sd.py:217-282, train.py:186-199) — H2D of the batch, forward, loss
+head, backward, gradient all-reduce, SGD step — one process per GPU.
+
+The reference is single-GPU (no DataParallel / distributed code anywhere); the
+data-parallel part is new: clips are sharded on the clip axis (a clip is never split: temporal
+mixing stays inside a clip), gradients live in ONE flat buffer that is all-reduced bucket by bucket
+with NCCL while backward is still running.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    """Flat gradient storage + overlapped bucketed all-reduce.
+
+    Every parameter's ``.grad`` is a view into one flat fp32 buffer (zeroed with a single memset per
+    step).  Parameters are split into ``n_buckets`` contiguous ranges in REVERSE registration order
+    (≈ the order backward produces them).  A post-accumulate-grad hook counts finished parameters;
+    when a bucket is complete its slice is all-reduced asynchronously on ``comm_stream`` and
+    ``finish()`` joins the streams.  With world_size == 1 (or no process group) nothing is sent.
+    """
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], n_buckets: int = 3, process_group=None,
+                 average: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBuckets needs at least one trainable parameter")
+        dev = self.params[0].device
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.average = average
+        order = list(reversed(self.params))          # backward order first -> contiguous slices per bucket
+        total = sum(p.numel() for p in order)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._slices, self._bucket_of, off = [], {}, 0
+        per_bucket = -(-total // max(1, n_buckets))
+        bounds: List[List[int]] = []
+        for p in order:
+            b = min(off // per_bucket, n_buckets - 1)
+            if len(bounds) <= b:
+                bounds.append([off, off])
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[id(p)] = b
+            off += n
+            bounds[b][1] = off
+        self.bounds = bounds
+        self._need = [0] * len(bounds)
+        for p in order:
+            self._need[self._bucket_of[id(p)]] += 1
+        self._left = list(self._need)
+        self._works = []
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] \
+            if self.world > 1 else []
+
+    # -- per step -----------------------------------------------------------------------------
+    def zero(self):
+        self.flat.zero_()
+        self._left = list(self._need)
+        self._works = []
+
+    def _launch(self, b: int):
+        lo, hi = self.bounds[b]
+        chunk = self.flat[lo:hi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                if self.average:
+                    chunk.div_(self.world)
+                self._works.append(dist.all_reduce(chunk, group=self.group, async_op=True))
+        else:  # CPU / gloo (tests)
+            if self.average:
+                chunk.div_(self.world)
+            self._works.append(dist.all_reduce(chunk, group=self.group, async_op=True))
+
+    def _on_grad(self, p):
+        b = self._bucket_of[id(p)]
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            self._launch(b)
+
+    def finish(self):
+        """Call after backward: flush buckets whose hooks did not all fire (unused parameters) and
+        make the current stream wait for the reductions."""
+        if self.world > 1:
+            for b, left in enumerate(self._left):
+                if left > 0:
+                    self._left[b] = 0
+                    self._launch(b)
+            for w in self._works:
+                w.wait()
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._works = []
+
+
+def build_sgd(model, lr: float, momentum: float = 0.9, weight_decay: float = 5e-4):
+    """SGD over the model's nine policy groups with lr_mult / decay_mult applied
+    (train_mtmm.py:576-585)."""
+    policies = [g for g in model.get_optim_policies() if len(g['params']) > 0]
+    for g in policies:
+        g['lr'] = lr * g['lr_mult']
+        g['weight_decay'] = weight_decay * g['decay_mult']
+    fused = all(p.is_cuda for g in policies for p in g['params'])
+    return torch.optim.SGD(policies, momentum=momentum, **({"fused": True} if fused else {}))
+
+
+def adjust_learning_rate(learning_rate, optimizer, epoch, lr_steps):
+    """utils.py:39-46."""
+    gamma = 0.1 ** sum(epoch >= s for s in lr_steps)
+    for g in optimizer.param_groups:
+        g['lr'] = learning_rate * gamma * g['lr_mult']
+
+
+class MTMMTrainStep:
+    """One MTMM stage-1 step (train_mtmm.py:205-245) on this rank's shard of clips.
+
+    ``run(rgb, depth, labels)`` takes DEVICE tensors; ``__call__`` takes HOST (pinned) tensors, copies
+    them and returns the loss as a Python float (one D2H read), i.e. the end-to-end user call.
+    """
+
+    def __init__(self, model, lr=0.00125, momentum=0.9, weight_decay=5e-4, compute_dtype=torch.bfloat16,
+                 n_buckets=3, process_group=None):
+        from . import fused
+        self.model = model
+        self.compute_dtype = compute_dtype
+        self.device = next(model.parameters()).device
+        self.opt = build_sgd(model, lr, momentum, weight_decay)
+        self.buckets = GradBuckets(list(model.parameters()), n_buckets, process_group)
+        self._fused = fused
+
+    def stage(self, rgb_h, depth_h, labels_h):
+        return (rgb_h.to(self.device, non_blocking=True), depth_h.to(self.device, non_blocking=True),
+                labels_h.to(self.device, non_blocking=True))
+
+    def run(self, rgb, depth, labels):
+        from .losses import mtmm_loss
+        self.buckets.zero()
+        with self._fused.compute_dtype(self.compute_dtype):
+            logits, dpred = self.model(rgb)
+            loss, _ = mtmm_loss(logits, labels, dpred, depth)
+        loss.backward()
+        self.buckets.finish()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, rgb_h, depth_h, labels_h) -> float:
+        return float(self.run(*self.stage(rgb_h, depth_h, labels_h)).item())

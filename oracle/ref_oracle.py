@@ -1,0 +1,395 @@
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.
+
+A plain PyTorch-fp32 / numpy restatement of the reference's algorithm for the training hot path
+(TSM/ACTION-MobileNetV2 forward, TSN wrapper, MTMM and SD loss heads).  It is functional code over a
+``state_dict`` (name -> tensor, the reference's parameter names) so that the same weights can be
+fed to the reference modules, to this oracle and to the CUDA implementation.  Gradients come from
+autograd over these functions.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module, and only as the checker or the reported CPU baseline — the product
+package never imports it.
+
+Parity pinning: ``tests/test_oracle_vs_reference.py`` runs this file against the live reference
+modules (``/root/reference``, present in the build container only) and
+``tests/golden/make_golden.py`` stores reference outputs as fixtures that travel to the GPU box;
+``tests/test_oracle_golden.py`` checks the oracle against those fixtures everywhere.
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+# archs/mobilenet_v2.py:75-84 — (t, c, n, s)
+MBV2_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2),
+                (6, 320, 1, 1))
+
+
+def mbv2_block_table():
+    """[(index in features, inp, oup, stride, expand_ratio)] for the 17 InvertedResidual blocks."""
+    rows, inp, idx = [], 32, 1
+    for t, c, n, s in MBV2_SETTING:
+        for i in range(n):
+            rows.append((idx, inp, c, s if i == 0 else 1, t))
+            inp, idx = c, idx + 1
+    return rows
+
+
+# --------------------------------------------------------------------------------------------
+# K1 temporal shift — models/temporal_shift.py:27-46 (dup. models/action.py:135-154)
+# --------------------------------------------------------------------------------------------
+def temporal_shift_np(x: np.ndarray, n_segment: int, fold_div: int) -> np.ndarray:
+    """numpy, any dtype (bit-exact copy semantics).  x: [nt, c, h, w]."""
+    nt, c, h, w = x.shape
+    n_batch = nt // n_segment
+    v = x.reshape(n_batch, n_segment, c, h, w)  # raises like the reference's .view on a bad nt
+    fold = c // fold_div
+    out = np.zeros_like(v)
+    out[:, :-1, :fold] = v[:, 1:, :fold]
+    out[:, 1:, fold:2 * fold] = v[:, :-1, fold:2 * fold]
+    out[:, :, 2 * fold:] = v[:, :, 2 * fold:]
+    return out.reshape(nt, c, h, w)
+
+
+def temporal_shift_bwd_np(g: np.ndarray, n_segment: int, fold_div: int) -> np.ndarray:
+    """Adjoint of temporal_shift_np (what autograd produces; equals InplaceShift.backward,
+    models/temporal_shift.py:64-76)."""
+    nt, c, h, w = g.shape
+    n_batch = nt // n_segment
+    v = g.reshape(n_batch, n_segment, c, h, w)
+    fold = c // fold_div
+    out = np.zeros_like(v)
+    out[:, 1:, :fold] = v[:, :-1, :fold]
+    out[:, :-1, fold:2 * fold] = v[:, 1:, fold:2 * fold]
+    out[:, :, 2 * fold:] = v[:, :, 2 * fold:]
+    return out.reshape(nt, c, h, w)
+
+
+def temporal_shift(x: torch.Tensor, n_segment: int, fold_div: int) -> torch.Tensor:
+    """torch, differentiable."""
+    nt, c, h, w = x.shape
+    v = x.view(nt // n_segment, n_segment, c, h, w)
+    fold = c // fold_div
+    z = torch.zeros_like(v[:, :1])
+    left = torch.cat([v[:, 1:, :fold], z[:, :, :fold]], 1)
+    right = torch.cat([z[:, :, fold:2 * fold], v[:, :-1, fold:2 * fold]], 1)
+    return torch.cat([left, right, v[:, :, 2 * fold:]], 2).reshape(nt, c, h, w)
+
+
+# --------------------------------------------------------------------------------------------
+# BatchNorm helper (nn.BatchNorm2d semantics: biased var to normalise, unbiased for running stat)
+# --------------------------------------------------------------------------------------------
+def _bn(x, sd: SD, prefix: str, training: bool, momentum: float = 0.1, eps: float = 1e-5):
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    return F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training, momentum, eps)
+
+
+# --------------------------------------------------------------------------------------------
+# ACTION — models/action.py:61-116, op for op (not the algebraic collapse)
+# --------------------------------------------------------------------------------------------
+def action_pre_net(x: torch.Tensor, sd: SD, prefix: str, n_segment: int, bn_training: bool) -> torch.Tensor:
+    """Everything in Action.forward up to (not including) ``self.net``: returns x_p1+x_p2+x_p3."""
+    nt, c, h, w = x.shape
+    n = nt // n_segment
+    T = n_segment
+    # models/action.py:65-73 — depthwise temporal conv on (n*h*w, c, T)
+    xs = x.view(n, T, c, h, w).permute(0, 3, 4, 2, 1).reshape(n * h * w, c, T)
+    xs = F.conv1d(xs, sd[prefix + ".action_shift.weight"], padding=1, groups=c)
+    xs = xs.view(n, h, w, c, T).permute(0, 4, 3, 1, 2).reshape(nt, c, h, w)
+    # :76-83 — spatio-temporal excitation
+    p1 = xs.view(n, T, c, h, w).transpose(2, 1).mean(1, keepdim=True)           # [n,1,T,h,w]
+    p1 = F.conv3d(p1, sd[prefix + ".action_p1_conv1.weight"], padding=1)
+    p1 = torch.sigmoid(p1.transpose(2, 1).reshape(nt, 1, h, w))
+    x_p1 = xs * p1 + xs
+    # :86-96 — channel excitation
+    p2 = F.adaptive_avg_pool2d(xs, 1)
+    p2 = F.conv2d(p2, sd[prefix + ".action_p2_squeeze.weight"])
+    cr = p2.shape[1]
+    p2 = p2.view(n, T, cr).transpose(2, 1)
+    p2 = F.relu(F.conv1d(p2, sd[prefix + ".action_p2_conv1.weight"], padding=1))
+    p2 = p2.transpose(2, 1).reshape(nt, cr, 1, 1)
+    p2 = torch.sigmoid(F.conv2d(p2, sd[prefix + ".action_p2_expand.weight"]))
+    x_p2 = xs * p2 + xs
+    # :99-113 — motion excitation
+    x3 = F.conv2d(xs, sd[prefix + ".action_p3_squeeze.weight"])
+    x3 = _bn(x3, sd, prefix + ".action_p3_bn1", bn_training)
+    x3_t = x3.view(n, T, cr, h, w)[:, :T - 1]
+    x3_t1 = F.conv2d(x3, sd[prefix + ".action_p3_conv1.weight"], padding=1, groups=cr)
+    x3_t1 = x3_t1.view(n, T, cr, h, w)[:, 1:]
+    p3 = F.pad(x3_t1 - x3_t, (0, 0, 0, 0, 0, 0, 0, 1))
+    p3 = F.adaptive_avg_pool2d(p3.reshape(nt, cr, h, w), 1)
+    p3 = torch.sigmoid(F.conv2d(p3, sd[prefix + ".action_p3_expand.weight"]))
+    x_p3 = xs * p3 + xs
+    return x_p1 + x_p2 + x_p3
+
+
+def action_forward(x, sd: SD, prefix: str, n_segment: int, bn_training: bool):
+    """Action wrapping a bias-free 1x1 conv ``net`` (the MobileNetV2 case, models/models.py:183-185)."""
+    return F.conv2d(action_pre_net(x, sd, prefix, n_segment, bn_training), sd[prefix + ".net.weight"])
+
+
+# --------------------------------------------------------------------------------------------
+# MobileNetV2 — archs/mobilenet_v2.py:28-66 (block), :110-114 (forward)
+# --------------------------------------------------------------------------------------------
+def inverted_residual(x, sd: SD, prefix: str, inp: int, oup: int, stride: int, expand: int,
+                      temporal: str, n_segment: int, shift_div: int, bn_training: bool):
+    """``prefix`` = 'base_model.features.{i}'.  temporal in {'none','tsm','action'} applies to conv[0]
+    of residual blocks only (models/models.py:183)."""
+    hidden = inp * expand
+    res = stride == 1 and inp == oup
+    y = x
+    k = 0
+    if expand != 1:
+        p0 = f"{prefix}.conv.0"
+        if res and temporal == "tsm":
+            y = F.conv2d(temporal_shift(y, n_segment, shift_div), sd[p0 + ".net.weight"])
+        elif res and temporal == "action":
+            y = action_forward(y, sd, p0, n_segment, bn_training)
+        else:
+            y = F.conv2d(y, sd[p0 + ".weight"])
+        y = F.relu6(_bn(y, sd, f"{prefix}.conv.1", bn_training))
+        k = 3
+    y = F.conv2d(y, sd[f"{prefix}.conv.{k}.weight"], stride=stride, padding=1, groups=hidden)
+    y = F.relu6(_bn(y, sd, f"{prefix}.conv.{k + 1}", bn_training))
+    y = F.conv2d(y, sd[f"{prefix}.conv.{k + 3}.weight"])
+    y = _bn(y, sd, f"{prefix}.conv.{k + 4}", bn_training)
+    return x + y if res else y
+
+
+def mobilenet_v2_features(x, sd: SD, temporal: str = "none", n_segment: int = 8, shift_div: int = 8,
+                          bn_training: bool = True, prefix: str = "base_model.features", taps=None):
+    """features[0..18]; ``taps`` (optional dict) receives {index: activation} for the listed indices."""
+    y = F.conv2d(x, sd[f"{prefix}.0.0.weight"], stride=2, padding=1)
+    y = F.relu6(_bn(y, sd, f"{prefix}.0.1", bn_training))
+    for idx, inp, oup, stride, t in mbv2_block_table():
+        y = inverted_residual(y, sd, f"{prefix}.{idx}", inp, oup, stride, t, temporal, n_segment, shift_div,
+                              bn_training)
+        if taps is not None and idx in taps:
+            taps[idx] = y
+    y = F.conv2d(y, sd[f"{prefix}.18.0.weight"])
+    y = F.relu6(_bn(y, sd, f"{prefix}.18.1", bn_training))
+    if taps is not None and 18 in taps:
+        taps[18] = y
+    return y
+
+
+def tsn_forward(x5: torch.Tensor, sd: SD, num_segments: int, temporal: str = "none", shift_div: int = 8,
+                bn_training: bool = True, dropout_mask: Optional[torch.Tensor] = None, taps=None):
+    """models/models.py:323-356 with base_model='mobilenetv2': fold T into the batch, backbone,
+    x.mean(3).mean(2) (archs/mobilenet_v2.py:112), Dropout (as an explicit mask*scale tensor, or
+    identity), new_fc, mean over segments.  Returns logits [N, num_class]."""
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    f = mobilenet_v2_features(x, sd, temporal, num_segments, shift_div, bn_training, taps=taps)
+    pooled = f.mean(3).mean(2)
+    if dropout_mask is not None:
+        pooled = pooled * dropout_mask
+    z = F.linear(pooled, sd["new_fc.weight"], sd["new_fc.bias"])
+    return z.view((-1, num_segments) + tuple(z.shape[1:])).mean(dim=1, keepdim=True).squeeze(1)
+
+
+# --------------------------------------------------------------------------------------------
+# Loss heads
+# --------------------------------------------------------------------------------------------
+def mtmm_loss(logits, labels, depth_pred, depth_gt5):
+    """train_mtmm.py:223-231.  depth_gt5: [N,T,1,224,224]; depth_pred: [NT,1,56,56]."""
+    gt = depth_gt5.view(-1, 1, depth_gt5.size(-2), depth_gt5.size(-1))
+    gt = F.interpolate(gt, size=(56, 56), mode="bilinear")
+    g_depth_loss = F.mse_loss(depth_pred, gt)
+    return F.cross_entropy(logits, labels) + 0.01 * g_depth_loss, g_depth_loss
+
+
+def kd_loss(output, target_soft, temperature):
+    """train_sd.py:178-188."""
+    ls = torch.log_softmax(output / temperature, dim=1)
+    return -torch.mean(torch.sum(ls * target_soft, dim=1))
+
+
+def feature_loss(fea, target_fea):
+    """train_sd.py:191-193."""
+    loss = (fea - target_fea) ** 2 * ((fea > 0) | (target_fea > 0)).float()
+    return torch.abs(loss).sum()
+
+
+def sd_loss(outputs, feats, labels, alpha=0.1, beta=1e-6, temperature=3.0):
+    """train_sd.py:227-265.  outputs = (final, mid1, mid2, mid3) logits; feats = (final, mid1, mid2,
+    mid3) pooled features.  Returns (total, dict of the ten terms)."""
+    out, m1, m2, m3 = outputs
+    f4, f1, f2, f3 = feats
+    ce = [F.cross_entropy(o, labels) for o in (out, m1, m2, m3)]
+    temp4 = torch.softmax(out / temperature, dim=1).detach()
+    kd = [kd_loss(m, temp4, temperature) * temperature ** 2 for m in (m1, m2, m3)]
+    fl = [feature_loss(f, f4.detach()) for f in (f1, f2, f3)]
+    total = (1 - alpha) * sum(ce) + alpha * sum(kd) + beta * sum(fl)
+    return total, {"ce": ce, "kd": kd, "feat": fl}
+
+
+# --------------------------------------------------------------------------------------------
+# state-dict utilities
+# --------------------------------------------------------------------------------------------
+def clone_state(sd: SD, requires_grad: bool = True, dtype=torch.float32) -> SD:
+    """Detached fp32 copy; floating-point *parameters* get requires_grad (buffers do not)."""
+    out = {}
+    for k, v in sd.items():
+        t = v.detach().clone()
+        if t.is_floating_point():
+            t = t.to(dtype)
+            if requires_grad and not (k.endswith("running_mean") or k.endswith("running_var")):
+                t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+def randomize_state(sd: SD, seed: int = 0, action_sigma: float = 0.3) -> None:
+    """In-place: give BN layers non-trivial affine/running stats and ACTION layers non-trivial
+    weights so that parity runs do not sit on the initialisation's symmetric point."""
+    g = torch.Generator().manual_seed(seed)
+    for k, v in sd.items():
+        if not v.is_floating_point():
+            continue
+        if k.endswith("running_mean"):
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+        elif k.endswith("running_var"):
+            v.copy_(torch.rand(v.shape, generator=g) * 0.5 + 0.75)
+        elif ".action_" in k and k.endswith("weight") and "bn" not in k:
+            v.add_(torch.randn(v.shape, generator=g) * action_sigma)
+        elif k.endswith("weight") and v.dim() == 1:   # BN gamma
+            v.copy_(torch.rand(v.shape, generator=g) * 0.5 + 0.75)
+        elif k.endswith("bias") and v.dim() == 1 and "fc" not in k:  # BN beta
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+
+
+# --------------------------------------------------------------------------------------------
+# deterministic, machine-independent weights and inputs (numpy RandomState, not torch RNG)
+# --------------------------------------------------------------------------------------------
+def _bn_entries(sd, prefix, c, rs):
+    sd[prefix + ".weight"] = torch.from_numpy(rs.uniform(0.75, 1.25, c).astype(np.float32))
+    sd[prefix + ".bias"] = torch.from_numpy((rs.standard_normal(c) * 0.1).astype(np.float32))
+    sd[prefix + ".running_mean"] = torch.from_numpy((rs.standard_normal(c) * 0.1).astype(np.float32))
+    sd[prefix + ".running_var"] = torch.from_numpy(rs.uniform(0.75, 1.25, c).astype(np.float32))
+    sd[prefix + ".num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+
+
+def _conv_entry(sd, name, shape, rs, std=None):
+    if std is None:  # archs/mobilenet_v2.py:118-120
+        std = math.sqrt(2.0 / (shape[2] * shape[3] * shape[0]))
+    sd[name] = torch.from_numpy((rs.standard_normal(shape) * std).astype(np.float32))
+
+
+def action_state(sd: SD, prefix: str, c: int, shift_div: int, rs, sigma: float = 0.3) -> None:
+    """Entries of one Action module (models/action.py:25-58): TSM-pattern shift weights plus noise,
+    default-scale random weights elsewhere."""
+    cr, fold = c // 16, c // shift_div
+    w = np.zeros((c, 1, 3), np.float32)
+    w[:fold, 0, 2] = 1
+    w[fold:2 * fold, 0, 0] = 1
+    w[2 * fold:, 0, 1] = 1
+    sd[prefix + ".action_shift.weight"] = torch.from_numpy(w + (rs.standard_normal(w.shape) * sigma).astype(np.float32))
+    sd[prefix + ".action_p1_conv1.weight"] = torch.from_numpy((rs.standard_normal((1, 1, 3, 3, 3)) * 0.2).astype(np.float32))
+    sd[prefix + ".action_p2_squeeze.weight"] = torch.from_numpy((rs.standard_normal((cr, c, 1, 1)) * 0.3).astype(np.float32))
+    sd[prefix + ".action_p2_conv1.weight"] = torch.from_numpy((rs.standard_normal((cr, cr, 3)) * 0.5).astype(np.float32))
+    sd[prefix + ".action_p2_expand.weight"] = torch.from_numpy((rs.standard_normal((c, cr, 1, 1)) * 0.5).astype(np.float32))
+    sd[prefix + ".action_p3_squeeze.weight"] = torch.from_numpy((rs.standard_normal((cr, c, 1, 1)) * 0.3).astype(np.float32))
+    _bn_entries(sd, prefix + ".action_p3_bn1", cr, rs)
+    sd[prefix + ".action_p3_conv1.weight"] = torch.from_numpy((rs.standard_normal((cr, 1, 3, 3)) * 0.4).astype(np.float32))
+    sd[prefix + ".action_p3_expand.weight"] = torch.from_numpy((rs.standard_normal((c, cr, 1, 1)) * 0.5).astype(np.float32))
+
+
+def build_tsn_state(num_class: int = 83, temporal: str = "none", shift_div: int = 8, seed: int = 0) -> SD:
+    """A full state_dict for TSN(base_model='mobilenetv2', dropout>0) with the REFERENCE's key names
+    (models/models.py:169-194 + archs/mobilenet_v2.py), loadable with strict=True into the reference
+    and into ehgr_b200.TSN.  Values come from numpy RandomState(seed)."""
+    rs = np.random.RandomState(seed)
+    sd: SD = {}
+    f = "base_model.features"
+    _conv_entry(sd, f"{f}.0.0.weight", (32, 3, 3, 3), rs)
+    _bn_entries(sd, f"{f}.0.1", 32, rs)
+    for idx, inp, oup, stride, t in mbv2_block_table():
+        hidden, p, k = inp * t, f"{f}.{idx}.conv", 0
+        res = stride == 1 and inp == oup
+        if t != 1:
+            if res and temporal in ("tsm", "action"):
+                _conv_entry(sd, f"{p}.0.net.weight", (hidden, inp, 1, 1), rs)
+                if temporal == "action":
+                    action_state(sd, f"{p}.0", inp, shift_div, rs)
+            else:
+                _conv_entry(sd, f"{p}.0.weight", (hidden, inp, 1, 1), rs)
+            _bn_entries(sd, f"{p}.1", hidden, rs)
+            k = 3
+        _conv_entry(sd, f"{p}.{k}.weight", (hidden, 1, 3, 3), rs)
+        _bn_entries(sd, f"{p}.{k + 1}", hidden, rs)
+        _conv_entry(sd, f"{p}.{k + 3}.weight", (oup, hidden, 1, 1), rs)
+        _bn_entries(sd, f"{p}.{k + 4}", oup, rs)
+    _conv_entry(sd, f"{f}.18.0.weight", (1280, 320, 1, 1), rs)
+    _bn_entries(sd, f"{f}.18.1", 1280, rs)
+    sd["new_fc.weight"] = torch.from_numpy((rs.standard_normal((num_class, 1280)) * 0.02).astype(np.float32))
+    sd["new_fc.bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
+    return sd
+
+
+def synthetic_clip_batch(n: int, t: int = 8, size: int = 224, num_class: int = 83, seed: int = 0):
+    """(rgb [n,t,3,size,size] ~N(0,1), depth [n,t,1,size,size] in [0,1], labels [n]) — SURVEY §8d."""
+    rs = np.random.RandomState(1000 + seed)
+    rgb = torch.from_numpy(rs.standard_normal((n, t, 3, size, size)).astype(np.float32))
+    depth = torch.from_numpy(rs.uniform(0, 1, (n, t, 1, size, size)).astype(np.float32))
+    labels = torch.from_numpy(rs.randint(0, num_class, (n,)).astype(np.int64))
+    return rgb, depth, labels
+
+
+# --------------------------------------------------------------------------------------------
+# MTMM wrapper on MobileNetV2 — models/models_MTMM.py:129-155 (global_decoder), :268-292 (forward)
+# The reference wires this for ResNet only (layer4, 2048 ch); for MobileNetV2 the tap is the
+# features[18] output (1280 ch) — builder-defined, SURVEY §8a A10.
+# --------------------------------------------------------------------------------------------
+DECODER_UNITS = ((0, 1, True), (4, 5, True), (8, 9, True), (12, 13, False))  # (conv idx, bn idx, upsample)
+
+
+def global_decoder(f, sd: SD, bn_training: bool, prefix: str = "global_decoder"):
+    y = f
+    for ci, bi, up in DECODER_UNITS:
+        y = F.conv2d(y, sd[f"{prefix}.{ci}.weight"], padding=1)
+        y = F.relu(_bn(y, sd, f"{prefix}.{bi}", bn_training))
+        if up:
+            y = F.interpolate(y, scale_factor=2, mode="nearest")
+    return torch.sigmoid(F.conv2d(y, sd[f"{prefix}.15.weight"], sd[f"{prefix}.15.bias"]))
+
+
+def mtmm_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8,
+                 bn_training: bool = True, dropout_mask=None):
+    """-> (logits [N,cls], depth [NT,1,56,56])."""
+    taps = {18: None}
+    logits = tsn_forward(x5, sd, num_segments, temporal, shift_div, bn_training, dropout_mask, taps=taps)
+    return logits, global_decoder(taps[18], sd, bn_training)
+
+
+def build_mtmm_state(num_class: int = 83, temporal: str = "tsm", shift_div: int = 8, seed: int = 0,
+                     feat: int = 1280) -> SD:
+    sd = build_tsn_state(num_class, temporal, shift_div, seed)
+    rs = np.random.RandomState(seed + 77)
+    chans = (feat, 256, 64, 32, 32)
+    for (ci, bi, _), i, o in zip(DECODER_UNITS, chans[:-1], chans[1:]):
+        sd[f"global_decoder.{ci}.weight"] = torch.from_numpy(
+            (rs.standard_normal((o, i, 3, 3)) * math.sqrt(2.0 / (9 * i))).astype(np.float32))
+        _bn_entries(sd, f"global_decoder.{bi}", o, rs)
+    sd["global_decoder.15.weight"] = torch.from_numpy((rs.standard_normal((1, 32, 1, 1)) * 0.2).astype(np.float32))
+    sd["global_decoder.15.bias"] = torch.from_numpy((rs.standard_normal(1) * 0.1).astype(np.float32))
+    return sd
+
+
+def mtmm_train_step(sd: SD, rgb, depth, labels, num_segments=8, temporal="tsm", shift_div=8, bn_training=True):
+    """One reference-equivalent MTMM step on CPU: forward, loss (train_mtmm.py:223-231), backward.
+    Returns (loss, logits, depth_pred); gradients are left in sd[*].grad."""
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    logits, dpred = mtmm_forward(rgb, sd, num_segments, temporal, shift_div, bn_training)
+    loss, _ = mtmm_loss(logits, labels, dpred, depth)
+    loss.backward()
+    return loss.detach(), logits.detach(), dpred.detach()

@@ -1,0 +1,213 @@
+"""Generate golden fixtures by running the LIVE reference (/root/reference) on CPU.
+
+    python tests/golden/make_golden.py          (build container only; /root/reference must exist)
+
+Writes small .npz files next to this script.  They travel to the GPU box, where /root/reference does
+not exist, and pin the oracle (tests/test_oracle_golden.py) and the CUDA path (tests/test_*_gpu.py).
+Weights and inputs are produced by oracle.ref_oracle.build_tsn_state / synthetic_clip_batch (numpy
+RandomState: machine independent), loaded into the reference with strict=True.
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import io
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REF = Path("/root/reference")
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REF))
+
+from oracle import ref_oracle as O  # noqa: E402
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def ref_functions(path: Path, names):
+    """Extract top-level function definitions from a reference script WITHOUT importing it (the train
+    scripts parse argv at import time) and compile them in a scratch namespace."""
+    tree = ast.parse(path.read_text())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    ns = {"torch": torch, "F": F}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), str(path), "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def grad_digest(named_grads):
+    """Per-parameter (sum, sum of |g|, g.flat[::stride] samples) — small but discriminating."""
+    out = {}
+    for k, g in named_grads.items():
+        g = g.detach().double().flatten()
+        idx = torch.linspace(0, g.numel() - 1, steps=min(16, g.numel())).long()
+        out[k] = np.concatenate([[g.sum().item(), g.abs().sum().item()], g[idx].numpy()])
+    return out
+
+
+def golden_shift():
+    from models.temporal_shift import InplaceShift, TemporalShift
+    rs = np.random.RandomState(7)
+    cases = {}
+    for name, (nt, c, h, w, T, div) in {
+        "a": (8, 16, 5, 5, 4, 8), "b": (16, 24, 7, 7, 8, 8), "c": (6, 3, 4, 4, 3, 8), "d": (8, 20, 3, 3, 8, 3),
+        "e": (16, 160, 7, 7, 8, 8), "f": (4, 8, 2, 2, 1, 4), "g": (8, 9, 3, 5, 2, 2),
+    }.items():
+        x = torch.from_numpy(rs.standard_normal((nt, c, h, w)).astype(np.float32)).requires_grad_(True)
+        y = TemporalShift.shift(x, T, fold_div=div)
+        g = torch.from_numpy(rs.standard_normal((nt, c, h, w)).astype(np.float32))
+        y.backward(g)
+        # the reference's in-place variant (unreachable via shift(); called directly) must agree
+        xin = x.detach().clone().view(nt // T, T, c, h, w)
+        yin = InplaceShift.apply(xin, c // div)
+        assert torch.equal(yin.reshape(nt, c, h, w), y.detach())
+        cases[name + "_meta"] = np.array([nt, c, h, w, T, div])
+        cases[name + "_x"] = x.detach().numpy()
+        cases[name + "_y"] = y.detach().numpy()
+        cases[name + "_g"] = g.numpy()
+        cases[name + "_gx"] = x.grad.numpy()
+    np.savez_compressed(HERE / "shift.npz", **cases)
+
+
+def golden_action():
+    from models.action import Action
+    out = {}
+    for name, (c, h, T, n, train_bn) in {"c32": (32, 6, 4, 2, True), "c24": (24, 5, 8, 1, True),
+                                        "c160": (160, 3, 8, 1, False)}.items():
+        rs = np.random.RandomState(11 + c)
+        sd = {}
+        O.action_state(sd, "m", c, 8, rs)
+        O._conv_entry(sd, "m.net.weight", (6 * c, c, 1, 1), rs)
+        with _quiet():
+            mod = Action(torch.nn.Conv2d(c, 6 * c, 1, bias=False), n_segment=T, shift_div=8)
+        mod.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        mod.train(train_bn)
+        x = torch.from_numpy(rs.standard_normal((n * T, c, h, h)).astype(np.float32)).requires_grad_(True)
+        y = mod(x)
+        g = torch.from_numpy(rs.standard_normal(tuple(y.shape)).astype(np.float32))
+        y.backward(g)
+        out[name + "_meta"] = np.array([c, h, T, n, int(train_bn)])
+        out[name + "_x"] = x.detach().numpy()
+        out[name + "_g"] = g.numpy()
+        out[name + "_y"] = y.detach().numpy()
+        out[name + "_gx"] = x.grad.numpy()
+        for k, p in mod.named_parameters():
+            out[f"{name}_grad_{k}"] = p.grad.numpy()
+        out[name + "_rm"] = mod.action_p3_bn1.running_mean.numpy()
+        out[name + "_rv"] = mod.action_p3_bn1.running_var.numpy()
+    np.savez_compressed(HERE / "action.npz", **out)
+
+
+def golden_tsn():
+    """Whole TSN-MobileNetV2 fwd+bwd at 64x64 (final map 2x2), the three temporal variants, train-BN
+    and frozen-BN (eval) modes."""
+    from models.models import TSN
+    from models.temporal_shift import TemporalShift
+    from archs.mobilenet_v2 import InvertedResidual
+    out = {}
+    for temporal in ("none", "tsm", "action"):
+        for bn_train in (True, False):
+            for dt, dtag in ((torch.float32, ""), (torch.float64, "64")):
+                with _quiet():
+                    ref = TSN(83, 8, 'RGB', base_model='mobilenetv2', pretrain=None, dropout=0.5, partial_bn=False,
+                              is_shift=(temporal == "action"), shift_div=8, consensus_type='avg', fc_lr5=True,
+                              img_feature_dim=224)
+                    if temporal == "tsm":
+                        for m in ref.base_model.modules():
+                            if isinstance(m, InvertedResidual) and len(m.conv) == 8 and m.use_res_connect:
+                                m.conv[0] = TemporalShift(m.conv[0], n_segment=8, n_div=8)
+                sd = O.build_tsn_state(83, temporal, 8, seed=5)
+                ref.load_state_dict(sd, strict=True)       # checkpoint-contract check
+                ref = ref.to(dt)
+                ref.train(bn_train)
+                for m in ref.modules():
+                    if isinstance(m, torch.nn.Dropout):
+                        m.eval()
+                rgb, _, labels = O.synthetic_clip_batch(2, 8, 64, 83, seed=3)
+                logits = ref(rgb.to(dt))
+                loss = F.cross_entropy(logits, labels)
+                loss.backward()
+                tag = f"{temporal}_{'train' if bn_train else 'eval'}"
+                out[tag + f"_logits{dtag}"] = logits.detach().numpy()
+                out[tag + f"_loss{dtag}"] = np.array(loss.item())
+                for k, v in grad_digest({k: p.grad for k, p in ref.named_parameters()}).items():
+                    out[f"{tag}_g{dtag}_{k}"] = v
+                rsd = ref.state_dict()
+                for k in ("base_model.features.0.1.running_mean", "base_model.features.9.conv.4.running_var",
+                          "base_model.features.18.1.running_var"):
+                    out[f"{tag}_rs{dtag}_{k}"] = rsd[k].numpy()
+    np.savez_compressed(HERE / "tsn_mbv2.npz", **out)
+
+
+def golden_losses():
+    kd_fn, feat_fn = ref_functions(REF / "train_sd.py", ["kd_loss_function", "feature_loss_function"])
+
+    class A:  # the argparse namespace the reference functions read
+        temperature, alpha, beta = 3, 0.1, 1e-6
+
+    rs = np.random.RandomState(21)
+    N, T, cls, fd = 4, 8, 83, 1280
+    logits = [torch.from_numpy(rs.standard_normal((N, cls)).astype(np.float32) * 2).requires_grad_(True) for _ in range(4)]
+    feats = [torch.from_numpy(rs.standard_normal((N * T, fd, 1, 1)).astype(np.float32)).requires_grad_(True) for _ in range(4)]
+    labels = torch.from_numpy(rs.randint(0, cls, (N,)).astype(np.int64))
+    crit = torch.nn.CrossEntropyLoss()
+    # train_sd.py:227-265, statement for statement
+    output, m1, m2, m3 = logits
+    final_fea, f1, f2, f3 = feats
+    loss = crit(output, labels)
+    ml = [crit(m, labels) for m in (m1, m2, m3)]
+    temp4 = torch.softmax(output / A.temperature, dim=1)
+    kd = [kd_fn(m, temp4.detach(), A) * (A.temperature ** 2) for m in (m1, m2, m3)]
+    fl = [feat_fn(f, final_fea.detach()) for f in (f1, f2, f3)]
+    total = (1 - A.alpha) * (loss + ml[0] + ml[1] + ml[2]) + A.alpha * (kd[0] + kd[1] + kd[2]) + A.beta * (fl[0] + fl[1] + fl[2])
+    total.backward()
+    out = {"sd_labels": labels.numpy(), "sd_total": np.array(total.item()),
+           "sd_terms": np.array([loss.item()] + [v.item() for v in ml] + [v.item() for v in kd] + [v.item() for v in fl])}
+    for i in range(4):
+        out[f"sd_logits{i}"] = logits[i].detach().numpy()
+        out[f"sd_feat{i}"] = feats[i].detach().numpy()
+        out[f"sd_glogits{i}"] = logits[i].grad.numpy()
+        out[f"sd_gfeat{i}"] = feats[i].grad.numpy() if feats[i].grad is not None else np.zeros_like(feats[i].detach().numpy())
+
+    # MTMM loss, train_mtmm.py:223-231
+    lg = torch.from_numpy(rs.standard_normal((N, cls)).astype(np.float32)).requires_grad_(True)
+    pred = torch.from_numpy(rs.uniform(0, 1, (N * 2, 1, 56, 56)).astype(np.float32)).requires_grad_(True)
+    n_depth = torch.from_numpy(rs.uniform(0, 1, (N, 2, 1, 224, 224)).astype(np.float32))
+    gt = F.interpolate(n_depth.view(-1, 1, n_depth.size(-2), n_depth.size(-1)), size=(56, 56), mode='bilinear')
+    g_depth_loss = torch.nn.MSELoss()(pred, gt)
+    mt = crit(lg, labels) + 0.01 * g_depth_loss
+    mt.backward()
+    out.update({"mt_logits": lg.detach().numpy(), "mt_pred": pred.detach().numpy(),
+                "mt_depth": n_depth.numpy().astype(np.float16).astype(np.float32), "mt_loss": np.array(mt.item()),
+                "mt_depth_loss": np.array(g_depth_loss.item()), "mt_glogits": lg.grad.numpy(),
+                "mt_gpred": pred.grad.numpy()})
+    # depth is stored through fp16 to keep the fixture small: recompute the reference on that input
+    n_depth = torch.from_numpy(out["mt_depth"])
+    pred2 = pred.detach().clone().requires_grad_(True)
+    lg2 = lg.detach().clone().requires_grad_(True)
+    gt = F.interpolate(n_depth.view(-1, 1, 224, 224), size=(56, 56), mode='bilinear')
+    g_depth_loss = torch.nn.MSELoss()(pred2, gt)
+    mt = crit(lg2, labels) + 0.01 * g_depth_loss
+    mt.backward()
+    out.update({"mt_loss": np.array(mt.item()), "mt_depth_loss": np.array(g_depth_loss.item()),
+                "mt_glogits": lg2.grad.numpy(), "mt_gpred": pred2.grad.numpy(),
+                "mt_depth": out["mt_depth"].astype(np.float16)})
+    np.savez_compressed(HERE / "losses.npz", **out)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    golden_shift()
+    golden_action()
+    golden_losses()
+    golden_tsn()
+    for p in sorted(HERE.glob("*.npz")):
+        print(p.name, p.stat().st_size)

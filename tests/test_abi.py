@@ -1,0 +1,46 @@
+"""The C-ABI library loads and exports every symbol include/ehgr_b200.h declares (no compute)."""
+import ctypes
+import re
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (REPO / "include" / "ehgr_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ehgr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_symbols():
+    syms = _declared_symbols()
+    assert "ehgr_temporal_shift_fwd" in syms and "ehgr_abi_version" in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import ehgr_b200
+    lib = ehgr_b200._lib.lib()
+    for s in _declared_symbols():
+        assert hasattr(lib, s), f"libehgr_b200.so does not export {s}"
+    assert lib.ehgr_abi_version() == 1
+    assert ehgr_b200._lib.lib().ehgr_status_string(-4).decode().startswith("invalid")
+
+
+def test_binding_table_covers_header():
+    import ehgr_b200
+    declared = set(_declared_symbols()) - {"ehgr_abi_version", "ehgr_status_string", "ehgr_launch_count", "ehgr_stream_t"}
+    bound = set(ehgr_b200._lib.SIGNATURES)
+    assert declared == bound, (declared - bound, bound - declared)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    import ehgr_b200
+    lib = ehgr_b200._lib.lib()
+    assert lib.ehgr_temporal_shift_fwd(None, None, 1, 8, 8, 4, 1, 0, 0, None) == -1          # null
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    assert lib.ehgr_temporal_shift_fwd(p, p + 32, 1, 8, 8, 4, 1, 7, 0, None) == -3             # dtype
+    assert lib.ehgr_temporal_shift_fwd(p, p + 32, 1, 0, 8, 4, 1, 0, 0, None) == -4             # shape
+    assert lib.ehgr_temporal_shift_fwd(p, p + 32, 1, 8, 8, 4, 5, 0, 0, None) == -4             # 2*fold > c
+    assert lib.ehgr_temporal_shift_fwd(p + 1, p + 32, 1, 8, 8, 4, 1, 0, 0, None) == -2         # alignment
+    assert lib.ehgr_temporal_shift_fwd(p, p + 32, 0, 8, 8, 4, 1, 0, 0, None) == 0              # empty batch

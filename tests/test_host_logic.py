@@ -1,0 +1,86 @@
+"""Host-side mirror of the reference interface: module tree, state_dict keys, optimiser groups,
+error behaviour.  No GPU needed (nothing is executed on a device)."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from oracle import ref_oracle as O
+
+
+def _tsn(temporal, **kw):
+    import ehgr_b200
+    with contextlib.redirect_stdout(io.StringIO()):
+        return ehgr_b200.TSN(83, 8, 'RGB', base_model='mobilenetv2', pretrain=None, dropout=0.5,
+                             partial_bn=kw.pop("partial_bn", False), is_shift=(temporal != "none"), shift_div=8,
+                             consensus_type='avg', fc_lr5=True, img_feature_dim=224,
+                             temporal_module=("tsm" if temporal == "tsm" else "action"), **kw)
+
+
+@pytest.mark.parametrize("temporal", ["none", "tsm", "action"])
+def test_state_dict_keys_are_the_reference_checkpoint_contract(temporal):
+    m = _tsn(temporal)
+    sd = O.build_tsn_state(83, temporal, 8, seed=0)   # loads strict=True into the reference (make_golden.py)
+    m.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == {"none": 2330195, "tsm": 2330195, "action": 2355455}[temporal]
+
+
+def test_action_insertion_sites_and_structure():
+    import ehgr_b200
+    m = _tsn("action")
+    sites = [i for i, f in enumerate(m.base_model.features)
+             if isinstance(f, ehgr_b200.InvertedResidual) and isinstance(f.conv[0], ehgr_b200.Action)]
+    assert sites == [3, 5, 6, 8, 9, 10, 12, 13, 15, 16]
+    a = m.base_model.features[3].conv[0]
+    assert (a.in_channels, a.out_channels, a.reduced_channels, a.fold, a.n_segment) == (24, 144, 1, 3, 8)
+    assert len(m.base_model.features[1].conv) == 5 and len(m.base_model.features[2].conv) == 8
+    assert m.base_model.last_layer_name == 'classifier' and isinstance(m.base_model.classifier, torch.nn.Dropout)
+    t = _tsn("tsm")
+    assert all(isinstance(t.base_model.features[i].conv[0], ehgr_b200.TemporalShift) for i in sites)
+    assert t.base_model.features[3].conv[0].fold_div == 8
+
+
+def test_optim_policies_group_sizes_match_reference():
+    # MBv2+ACTION -> 1 / 0 / 51 / 0 / 104 / 80 / 20 / 1 / 1
+    pol = _tsn("action").get_optim_policies()
+    assert [len(g['params']) for g in pol] == [1, 0, 51, 0, 104, 80, 20, 1, 1]
+    assert [g['lr_mult'] for g in pol] == [1, 2, 1, 2, 1, 1, 1, 5, 10]
+    assert [g['decay_mult'] for g in pol] == [1, 0, 1, 0, 0, 1, 0, 1, 0]
+    assert pol[4]['name'] == "BN scale/shift"
+
+
+def test_partial_bn_freezes_all_but_first_bn():
+    m = _tsn("action", partial_bn=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.train()
+    bns = [b for b in m.base_model.modules() if isinstance(b, torch.nn.BatchNorm2d)]
+    assert bns[0].training and not any(b.training for b in bns[1:])
+    assert not bns[5].weight.requires_grad
+
+
+def test_make_temporal_shift_rejects_unknown_backbones_like_the_reference():
+    import ehgr_b200
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(NotImplementedError):
+            ehgr_b200.make_temporal_shift(torch.nn.Sequential(), 8)
+        import torchvision
+        r = torchvision.models.resnet18()
+        ehgr_b200.make_temporal_shift(r, 8, n_div=8, place='blockres')
+        assert isinstance(r.layer1[0].conv1, ehgr_b200.TemporalShift)
+
+
+def test_no_cpu_fallback():
+    import ehgr_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ehgr_b200.TemporalShift.shift(torch.zeros(8, 8, 2, 2), 8, fold_div=8)
+    with pytest.raises(RuntimeError):   # the reference's .view error on a ragged segment count
+        ehgr_b200.TemporalShift.shift(torch.zeros(7, 8, 2, 2), 4, fold_div=8)
+
+
+def test_product_package_never_imports_the_oracle():
+    from pathlib import Path
+    import ehgr_b200
+    pkg = Path(ehgr_b200.__file__).parent
+    for f in pkg.rglob("*.py"):
+        assert "oracle" not in f.read_text().replace("no oracle", ""), f
