@@ -82,11 +82,39 @@ def ptr(t) -> int:
 
 _I, _P, _F, _D, _Z = c_int, c_void_p, c_float, c_double, c_size_t
 
+class RowOp(ctypes.Structure):
+    """struct ehgr_rowop (include/ehgr_b200.h)."""
+    _fields_ = [("mode", ctypes.c_int32), ("relu6", ctypes.c_int32), ("in1", c_void_p), ("in2", c_void_p),
+                ("scale", c_void_p), ("shift", c_void_p), ("ca", c_void_p), ("cb", c_void_p), ("cc", c_void_p),
+                ("n_segment", ctypes.c_int32), ("fold", ctypes.c_int32), ("hw", ctypes.c_int32),
+                ("shift_dir", ctypes.c_int32)]
+
+
+_L = c_longlong
+_R = ctypes.POINTER(RowOp)
+
 # name -> argtypes for every int-returning symbol of include/ehgr_b200.h
 # (tests/test_abi.py cross-checks this table against the header and the built library).
 SIGNATURES = {
     "ehgr_temporal_shift_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_temporal_shift_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_pw_gemm": [_R, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_pw_wgrad": [_R, _R, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_dw_fwd": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_dw_dgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_dw_wgrad": [_R, _R, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_stem_wgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P],
+    "ehgr_bn_bwd_reduce": [_P, _P, _P, _P, _I, _P, _L, _I, _I, _P],
+    "ehgr_bn_bwd_finalize": [_P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
+    "ehgr_row_apply": [_R, _P, _P, _L, _I, _I, _P],
+    "ehgr_pool_fwd": [_R, _P, _I, _I, _I, _I, _P],
+    "ehgr_pool_bwd": [_P, _P, _I, _I, _I, _I, _P],
+    "ehgr_fc_consensus_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ehgr_fc_consensus_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ehgr_mtmm_loss": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_sd_loss": [_P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _L, _I, _P],
 }
 
 

@@ -1,0 +1,210 @@
+// bn.cu — K14 BatchNorm2d bookkeeping around the lazily-applied normalisation, and the generic
+// "materialise a row operand" elementwise kernel (BatchNorm apply + residual add, K11).
+//
+// nn.BatchNorm2d semantics (what the reference's modules do, archs/mobilenet_v2.py:10,17,41,...):
+//   training: y = (x - mean_b) / sqrt(var_b + eps) * gamma + beta, var_b biased;
+//             running = (1-momentum)*running + momentum*{mean_b, var_b * n/(n-1)}
+//   eval    : y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
+// Backward of conv -> BN(train) -> [ReLU6]:  with dz the (masked) gradient at the BN output,
+//   d raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat)),   dgamma = sum dz*xhat,  dbeta = sum dz
+// which is written  ca*dz + cb*raw + cc  so that consumers can apply it while loading (rowop.cuh).
+#include "rowop.cuh"
+
+namespace ehgr {
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, float momentum, float eps, int training,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                                   float* __restrict__ invstd_o, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    const double m = stats[c] / count;
+    double var = stats[C + c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = static_cast<float>(m);
+    invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    if (rmean) {
+      const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * static_cast<float>(unbiased);
+    }
+  } else {
+    mean = rmean[c];
+    invstd = 1.0f / sqrtf(rvar[c] + eps);
+  }
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - mean * sc;
+  if (mean_o) mean_o[c] = mean;
+  if (invstd_o) invstd_o[c] = invstd;
+}
+
+// sums[c] += sum_m mask*g ; sums[C+c] += sum_m mask*g*raw
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const float* __restrict__ scale,
+                     const float* __restrict__ shift, int relu6, double* __restrict__ sums, long long M, int C,
+                     int iters) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float smem[];  // [2C]
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < 2 * C; i += nthreads) smem[i] = 0.f;
+  __syncthreads();
+  const int c0 = threadIdx.x * V;
+  float s[V], b[V], a1[V], a2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a1[i] = a2[i] = 0.f; s[i] = 1.f; b[i] = 1.f; }
+  if (relu6) { load_vec<float, V>(scale + c0, s); load_vec<float, V>(shift + c0, b); }
+  const long long base = static_cast<long long>(blockIdx.x) * (static_cast<long long>(blockDim.y) * iters) + threadIdx.y;
+#pragma unroll 2
+  for (int it = 0; it < iters; ++it) {
+    const long long m = base + static_cast<long long>(it) * blockDim.y;
+    if (m >= M) break;
+    float gv[V], rv[V];
+    load_vec<T, V>(g + m * C + c0, gv);
+    load_vec<T, V>(raw + m * C + c0, rv);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float gg = gv[i];
+      if (relu6) {
+        const float z = fmaf(rv[i], s[i], b[i]);
+        if (!(z > 0.f && z < 6.f)) gg = 0.f;
+      }
+      a1[i] += gg;
+      a2[i] = fmaf(gg, rv[i], a2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) { atomicAdd(&smem[c0 + i], a1[i]); atomicAdd(&smem[C + c0 + i], a2[i]); }
+  __syncthreads();
+  for (int i = tid; i < 2 * C; i += nthreads) atomicAdd(&sums[i], static_cast<double>(smem[i]));
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ mean, const float* __restrict__ invstd, int training,
+                                       float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cc,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sdz = sums[c], sdzr = sums[C + c];
+  const double mu = mean[c], is = invstd[c], g = gamma ? gamma[c] : 1.0;
+  const double sdzx = (sdzr - mu * sdz) * is;  // sum dz * xhat
+  if (dgamma) dgamma[c] = static_cast<float>(sdzx);
+  if (dbeta) dbeta[c] = static_cast<float>(sdz);
+  const double sc = g * is;
+  if (training) {
+    const double k1 = sdz / count, k2 = sdzx / count;
+    ca[c] = static_cast<float>(sc);
+    cb[c] = static_cast<float>(-sc * k2 * is);
+    cc[c] = static_cast<float>(-sc * (k1 - mu * is * k2));
+  } else {
+    ca[c] = static_cast<float>(sc);
+    cb[c] = 0.f;
+    cc[c] = 0.f;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv) {
+  constexpr int V = VecOf<T>::N;
+  const long long total = M * cv;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / cv;
+    const int c0 = static_cast<int>(i - m * cv) * V;
+    float v[V];
+    load_row<T, V>(a, m, c0, C, v);
+    if (addend) {
+      float ad[V];
+      load_vec<T, V>(addend + m * C + c0, ad);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] += ad[k];
+    }
+    store_vec<T, V>(out + m * C + c0, v);
+  }
+}
+
+}  // namespace ehgr
+
+using namespace ehgr;
+
+extern "C" int ehgr_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, float momentum, float eps, int training,
+                                float* scale, float* shift, float* mean, float* invstd, int c,
+                                ehgr_stream_t stream) {
+  if (!scale || !shift) return EHGR_E_NULL;
+  if (training && (!stats || count <= 0)) return EHGR_E_NULL;
+  if (!training && (!running_mean || !running_var)) return EHGR_E_NULL;
+  if (c <= 0) return EHGR_E_SHAPE;
+  bn_finalize_kernel<<<static_cast<unsigned>(cdiv(c, 128)), 128, 0, as_stream(stream)>>>(
+      stats, static_cast<double>(count), gamma, beta, running_mean, running_var, momentum, eps, training, scale,
+      shift, mean, invstd, c);
+  return launch_status();
+}
+
+extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* scale, const float* shift,
+                                  int relu6, double* sums, long long m, int c, int dtype, ehgr_stream_t stream) {
+  const int es = esize_of(dtype);
+  if (es == 0) return EHGR_E_DTYPE;
+  if (!g || !raw || !sums || (relu6 && (!scale || !shift))) return EHGR_E_NULL;
+  const int V = 16 / es;
+  if (m < 0 || c <= 0 || (c % V)) return EHGR_E_SHAPE;
+  if (!aligned_to(g, 16) || !aligned_to(raw, 16)) return EHGR_E_ALIGN;
+  if (c / V > 256) return EHGR_E_UNSUPPORTED;
+  if (m == 0) return EHGR_OK;
+  const int cv = c / V;
+  const dim3 block(cv, std::max(1, 256 / cv));
+  long long iters = cdiv(m, 8LL * kNumSMs * block.y);
+  iters = std::max(1LL, std::min(iters, 1024LL));
+  const long long blocks = cdiv(m, static_cast<long long>(block.y) * iters);
+  const size_t smem = static_cast<size_t>(2) * c * sizeof(float);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_F32)
+    bn_bwd_reduce_kernel<float><<<static_cast<unsigned>(blocks), block, smem, s>>>(
+        static_cast<const float*>(g), static_cast<const float*>(raw), scale, shift, relu6, sums, m, c,
+        static_cast<int>(iters));
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), block, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(raw), scale, shift, relu6, sums, m,
+        c, static_cast<int>(iters));
+  return launch_status();
+}
+
+extern "C" int ehgr_bn_bwd_finalize(const double* sums, long long count, const float* gamma, const float* mean,
+                                    const float* invstd, int training, float* ca, float* cb, float* cc,
+                                    float* dgamma, float* dbeta, int c, ehgr_stream_t stream) {
+  if (!sums || !mean || !invstd || !ca || !cb || !cc) return EHGR_E_NULL;
+  if (c <= 0 || count <= 0) return EHGR_E_SHAPE;
+  bn_bwd_finalize_kernel<<<static_cast<unsigned>(cdiv(c, 128)), 128, 0, as_stream(stream)>>>(
+      sums, static_cast<double>(count), gamma, mean, invstd, training, ca, cb, cc, dgamma, dbeta, c);
+  return launch_status();
+}
+
+extern "C" int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out, long long m, int c, int dtype,
+                              ehgr_stream_t stream) {
+  const int es = esize_of(dtype);
+  if (es == 0) return EHGR_E_DTYPE;
+  if (!out) return EHGR_E_NULL;
+  if (int st = validate_rowop(a, es)) return st;
+  const int V = 16 / es;
+  if (m < 0 || c <= 0 || (c % V)) return EHGR_E_SHAPE;
+  if (!aligned_to(out, 16) || (addend && !aligned_to(addend, 16))) return EHGR_E_ALIGN;
+  if (m == 0) return EHGR_OK;
+  const int cv = c / V;
+  const long long total = m * cv;
+  const long long blocks = std::min(cdiv(total, 256), 16LL * kNumSMs);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_F32)
+    row_apply_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, s>>>(*a, static_cast<const float*>(addend),
+                                                                         static_cast<float*>(out), m, c, cv);
+  else
+    row_apply_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+        *a, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(out), m, c, cv);
+  return launch_status();
+}

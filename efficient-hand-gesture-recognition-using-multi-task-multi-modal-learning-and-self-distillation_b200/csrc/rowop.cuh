@@ -1,0 +1,191 @@
+// rowop.cuh — the "row operand": how a kernel reads an activation row [M, C] (NHWC, M = NT*H*W).
+//
+// Activations are stored RAW (the convolution output before BatchNorm); the BatchNorm affine, the
+// ReLU6, the temporal shift and — in backward — the BatchNorm-backward combination are applied by
+// the CONSUMER kernel while it loads the row.  That removes every stand-alone BN / ReLU6 / shift pass
+// of the reference (archs/mobilenet_v2.py:40-59 = conv, BN, ReLU6 as three kernels each).
+//
+//   PLAIN  : v = in1
+//   AFFINE : v = in1*scale[c] + shift[c]; relu6 ? clamp(v,0,6)                  (lazy BN(+ReLU6))
+//   SHIFT  : v = in1 of frame t+1 (c < fold), t-1 (fold <= c < 2 fold), t (rest), zero at clip ends
+//            (TemporalShift.shift, models/temporal_shift.py:40-44)
+//   BNBWD  : v = ca[c]*mask*in1 + cb[c]*in2 + cc[c],  mask = relu6 ? (0 < in2*scale+shift < 6) : 1
+//            in1 = gradient w.r.t. the post-activation, in2 = raw forward output of that layer:
+//            this is d(loss)/d(raw) of conv->BN(->ReLU6) with batch statistics (cb, cc != 0) or frozen
+//            statistics (cb = cc = 0).
+#pragma once
+#include "common.cuh"
+
+namespace ehgr {
+
+using RowOp = ehgr_rowop;
+
+template <typename T>
+struct VecOf;  // 16-byte vector of T
+template <>
+struct VecOf<float> { static constexpr int N = 4; };
+template <>
+struct VecOf<__nv_bfloat16> { static constexpr int N = 8; };
+
+// ---- raw vector loads / stores of NV elements (NV*sizeof(T) in {8,16}) as floats ---------------
+template <typename T, int NV>
+__device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&v)[NV]);
+
+template <>
+__device__ __forceinline__ void load_vec<float, 4>(const float* __restrict__ p, float (&v)[4]) {
+  const float4 r = *reinterpret_cast<const float4*>(p);
+  v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+template <>
+__device__ __forceinline__ void load_vec<float, 8>(const float* __restrict__ p, float (&v)[8]) {
+  const float4 r0 = *reinterpret_cast<const float4*>(p);
+  const float4 r1 = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = r0.x; v[1] = r0.y; v[2] = r0.z; v[3] = r0.w;
+  v[4] = r1.x; v[5] = r1.y; v[6] = r1.z; v[7] = r1.w;
+}
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16, 4>(const __nv_bfloat16* __restrict__ p, float (&v)[4]) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16, 8>(const __nv_bfloat16* __restrict__ p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] = __low2float(a);
+    v[2 * i + 1] = __high2float(a);
+  }
+}
+
+template <typename T, int NV>
+__device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&v)[NV]);
+
+template <>
+__device__ __forceinline__ void store_vec<float, 4>(float* __restrict__ p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void store_vec<float, 8>(float* __restrict__ p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ void store_vec<__nv_bfloat16, 4>(__nv_bfloat16* __restrict__ p, const float (&v)[4]) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+template <>
+__device__ __forceinline__ void store_vec<__nv_bfloat16, 8>(__nv_bfloat16* __restrict__ p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// value as the consumer's storage type would hold it (bf16 storage rounds, fp32 does not)
+template <typename T>
+__device__ __forceinline__ float round_to(float v);
+template <>
+__device__ __forceinline__ float round_to<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---- the row operand ------------------------------------------------------------------------------
+// Loads NV consecutive channels [c0, c0+NV) of row m (C channels per row) as fp32 with the operand's
+// transformation applied.  The caller guarantees c0 % NV == 0, C % NV == 0 and 0 <= m < M.
+template <typename T, int NV>
+__device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, int C, float (&v)[NV]) {
+  const T* in1 = static_cast<const T*>(op.in1);
+  const long long off = m * C + c0;
+  if (op.mode == EHGR_ROW_PLAIN) {
+    load_vec<T, NV>(in1 + off, v);
+  } else if (op.mode == EHGR_ROW_AFFINE) {
+    load_vec<T, NV>(in1 + off, v);
+    float s[NV], b[NV];
+    load_vec<float, NV>(op.scale + c0, s);
+    load_vec<float, NV>(op.shift + c0, b);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float z = fmaf(v[i], s[i], b[i]);
+      if (op.relu6) z = fminf(fmaxf(z, 0.f), 6.f);
+      v[i] = z;
+    }
+  } else if (op.mode == EHGR_ROW_SHIFT) {
+    const long long frame = m / op.hw;
+    const int t = static_cast<int>(frame % op.n_segment);
+    const int dir = op.shift_dir < 0 ? -1 : 1;
+    const long long step = static_cast<long long>(dir) * op.hw * C;
+    const int fold = op.fold;
+    // class 0 reads frame t+dir, class 1 reads frame t-dir
+    const bool has_next = dir > 0 ? (t < op.n_segment - 1) : (t > 0);
+    const bool has_prev = dir > 0 ? (t > 0) : (t < op.n_segment - 1);
+    const int lo = c0, hi = c0 + NV - 1;
+    auto cls_of = [fold](int c) { return c < fold ? 0 : (c < 2 * fold ? 1 : 2); };
+    const int cl = cls_of(lo), ch = cls_of(hi);
+    if (cl == ch) {
+      const bool ok = cl == 2 || (cl == 0 ? has_next : has_prev);
+      if (ok) {
+        load_vec<T, NV>(in1 + off + (cl == 0 ? step : cl == 1 ? -step : 0), v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = 0.f;
+      }
+    } else {
+      float a[NV], b[NV], c[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) a[i] = b[i] = 0.f;
+      if (has_next) load_vec<T, NV>(in1 + off + step, a);
+      if (has_prev) load_vec<T, NV>(in1 + off - step, b);
+      load_vec<T, NV>(in1 + off, c);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int k = cls_of(c0 + i);
+        v[i] = k == 0 ? a[i] : (k == 1 ? b[i] : c[i]);
+      }
+    }
+  } else {  // EHGR_ROW_BNBWD
+    float g[NV], r[NV], ca[NV], cb[NV], cc[NV];
+    load_vec<T, NV>(in1 + off, g);
+    load_vec<T, NV>(static_cast<const T*>(op.in2) + off, r);
+    load_vec<float, NV>(op.ca + c0, ca);
+    load_vec<float, NV>(op.cb + c0, cb);
+    load_vec<float, NV>(op.cc + c0, cc);
+    if (op.relu6) {
+      float s[NV], b[NV];
+      load_vec<float, NV>(op.scale + c0, s);
+      load_vec<float, NV>(op.shift + c0, b);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float z = fmaf(r[i], s[i], b[i]);
+        if (!(z > 0.f && z < 6.f)) g[i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[i], g[i], fmaf(cb[i], r[i], cc[i]));
+  }
+}
+
+inline int validate_rowop(const RowOp* op, int es) {
+  if (!op || !op->in1) return EHGR_E_NULL;
+  if (!aligned_to(op->in1, 16)) return EHGR_E_ALIGN;
+  switch (op->mode) {
+    case EHGR_ROW_PLAIN: return EHGR_OK;
+    case EHGR_ROW_AFFINE: return (op->scale && op->shift) ? EHGR_OK : EHGR_E_NULL;
+    case EHGR_ROW_SHIFT:
+      return (op->n_segment > 0 && op->hw > 0 && op->fold >= 0) ? EHGR_OK : EHGR_E_SHAPE;
+    case EHGR_ROW_BNBWD:
+      if (!op->in2 || !op->ca || !op->cb || !op->cc) return EHGR_E_NULL;
+      if (op->relu6 && (!op->scale || !op->shift)) return EHGR_E_NULL;
+      return aligned_to(op->in2, 16) ? EHGR_OK : EHGR_E_ALIGN;
+    default: return EHGR_E_DTYPE;
+  }
+  (void)es;
+}
+
+}  // namespace ehgr

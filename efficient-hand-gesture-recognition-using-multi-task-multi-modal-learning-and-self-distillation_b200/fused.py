@@ -1,78 +1,558 @@
-"""Execution of the backbone modules on CUDA.
+"""Fused execution of the backbone on CUDA (sm_100a): every arithmetic op of the TSM-MobileNetV2
+chain below is a hand-written kernel of libehgr_b200.so reached through the C ABI
+(include/ehgr_b200.h).  No torch conv / BN / activation op and no CPU path is involved.
 
-BOOTSTRAP STATE (round 1, first slice): the temporal shift runs on the hand-written kernel; the
-convolution / BatchNorm / excitation arithmetic below still goes through the torch CUDA library ops
-(cuDNN/cuBLAS) while the fused sm_100a block kernels are brought up one by one.  Nothing here runs
-on the CPU: every entry point refuses non-CUDA tensors.
+Design:
+  * activations live in NHWC ("channels last") in the compute dtype (fp32 or bf16) and are stored
+    RAW, i.e. as the convolution output before BatchNorm.  Each conv kernel accumulates the batch
+    statistics of its output in its epilogue; the consumer kernel applies BatchNorm(+ReLU6) — or the
+    temporal shift — while loading ("row operand", csrc/rowop.cuh).  The reference runs conv, BN and
+    ReLU6 as three kernels with an HBM round trip each (archs/mobilenet_v2.py:40-59).
+  * backward mirrors this: a layer's gradient kernels read (grad, raw) through a BNBWD row operand
+    that evaluates the BatchNorm(+ReLU6) backward on the fly, so dz / dBN tensors never exist.
+  * one ``torch.autograd.Function`` (``_ChainFunction``) runs a whole chain of units (stem,
+    InvertedResidual blocks, final 1x1 conv); the module tree (``features.{i}.conv.{j}``) is only
+    the parameter container and the checkpoint contract.
 """
 from __future__ import annotations
 
-import torch
-import torch.nn.functional as F
-
 import contextlib
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
 
 from . import _lib
+from ._lib import RowOp
+
+_STATE = {"dtype": torch.float32, "engine": 0}
 
 
 @contextlib.contextmanager
 def compute_dtype(dtype):
-    """Activation storage dtype of the backbone inside the block (fp32 master weights either way)."""
-    if dtype == torch.float32:
-        yield
-    else:
-        with torch.autocast("cuda", dtype=dtype):
+    """Storage dtype of the activations inside the fused chain (fp32 master weights either way).
+    fp32: exact-fp32 CUDA-core GEMMs (parity mode); bf16: tcgen05 tensor-core GEMMs."""
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("compute dtype must be torch.float32 or torch.bfloat16")
+    old = _STATE["dtype"]
+    _STATE["dtype"] = dtype
+    try:
+        if dtype == torch.bfloat16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):  # library modules around the chain (decoder)
+                yield
+        else:
             yield
+    finally:
+        _STATE["dtype"] = old
 
 
+@contextlib.contextmanager
+def gemm_engine(engine: int):
+    """0 auto, 1 force fp32 SIMT, 2 force tcgen05 (tests)."""
+    old = _STATE["engine"]
+    _STATE["engine"] = engine
+    try:
+        yield
+    finally:
+        _STATE["engine"] = old
+
+
+def current_dtype():
+    return _STATE["dtype"]
+
+
+# ------------------------------------------------------------------------------------------------
+# row operands
+# ------------------------------------------------------------------------------------------------
+def op_plain(t):
+    return RowOp(mode=0, in1=t.data_ptr())
+
+
+def op_affine(raw, scale, shift, relu6):
+    return RowOp(mode=1, relu6=int(relu6), in1=raw.data_ptr(), scale=scale.data_ptr(), shift=shift.data_ptr())
+
+
+def op_shift(x, n_segment, fold, hw, direction=1):
+    return RowOp(mode=2, in1=x.data_ptr(), n_segment=n_segment, fold=fold, hw=hw, shift_dir=direction)
+
+
+def op_bnbwd(g, raw, ca, cb, cc, scale, shift, relu6):
+    return RowOp(mode=3, relu6=int(relu6), in1=g.data_ptr(), in2=raw.data_ptr(), scale=scale.data_ptr(),
+                 shift=shift.data_ptr(), ca=ca.data_ptr(), cb=cb.data_ptr(), cc=cc.data_ptr())
+
+
+def _nhwc_empty(nt, h, w, c, dtype, device):
+    """logical [NT,C,H,W] tensor with channels-last strides."""
+    return torch.empty((nt, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def _is_nhwc_dense(x):
+    nt, c, h, w = x.shape
+    return x.stride() == (h * w * c, 1, w * c, c)
+
+
+def _as_nhwc(x, dtype):
+    if x.dtype == dtype and _is_nhwc_dense(x):
+        return x
+    nt, c, h, w = x.shape
+    y = _nhwc_empty(nt, h, w, c, dtype, x.device)
+    y.copy_(x)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# chain description
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Stage:
+    kind: str                      # 'stem' | 'pw' | 'dw'
+    conv: nn.Conv2d
+    bn: nn.BatchNorm2d
+    relu6: bool
+    stride: int = 1
+    shift: Optional[Tuple[int, int]] = None   # (n_segment, fold) — TemporalShift on the input (pw only)
+
+
+@dataclass
+class Unit:
+    stages: List[Stage]
+    residual: bool = False
+    tap: bool = False              # also return this unit's output from the chain
+
+
+def _conv_bn_stage(kind, conv, bn, relu6, shift=None):
+    if conv.bias is not None:
+        raise NotImplementedError("fused chain expects bias-free convolutions followed by BatchNorm")
+    if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+        raise NotImplementedError("fused chain expects the default nn.BatchNorm2d configuration")
+    return Stage(kind, conv, bn, relu6, conv.stride[0], shift)
+
+
+def unit_of_block(block) -> Unit:
+    """InvertedResidual -> Unit (archs/mobilenet_v2.py:28-66)."""
+    from .action import Action
+    from .temporal_shift import TemporalShift
+    conv = block.conv
+    stages = []
+    k = 0
+    if len(conv) == 8:
+        first, shift = conv[0], None
+        if isinstance(first, TemporalShift):
+            shift = (first.n_segment, first.net.in_channels // first.fold_div)
+            first = first.net
+        elif isinstance(first, Action):
+            raise NotImplementedError("Action blocks run through action_forward")
+        stages.append(_conv_bn_stage('pw', first, conv[1], True, shift))
+        k = 3
+    stages.append(_conv_bn_stage('dw', conv[k], conv[k + 1], True))
+    stages.append(_conv_bn_stage('pw', conv[k + 3], conv[k + 4], False))
+    return Unit(stages, residual=block.use_res_connect)
+
+
+def units_of_backbone(model, taps: Sequence[int] = ()) -> List[Unit]:
+    """MobileNetV2.features -> chain; the stem is merged with features[1] (its only consumer) so that
+    the stem activation is never materialised."""
+    from .mobilenet_v2 import InvertedResidual
+    feats = model.features
+    units: List[Unit] = []
+    stem = _conv_bn_stage('stem', feats[0][0], feats[0][1], True)
+    first = True
+    for i in range(1, len(feats) - 1):
+        blk = feats[i]
+        if not isinstance(blk, InvertedResidual):
+            raise NotImplementedError(type(blk))
+        u = unit_of_block(blk)
+        if first:
+            if 0 in taps:
+                units.append(Unit([stem], tap=True))
+            else:
+                u.stages.insert(0, stem)
+            first = False
+        u.tap = i in taps
+        units.append(u)
+    last = feats[len(feats) - 1]
+    units.append(Unit([_conv_bn_stage('pw', last[0], last[1], True)], tap=(len(feats) - 1) in taps))
+    return units
+
+
+def _has_action(model) -> bool:
+    from .action import Action
+    return any(isinstance(m, Action) for m in model.modules())
+
+
+# ------------------------------------------------------------------------------------------------
+# the chain autograd Function
+# ------------------------------------------------------------------------------------------------
+def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None):
+    nt, h, wd, cin = a_geom
+    cout = st.conv.out_channels
+    sp = _lib.stream_ptr(dev)
+    stats_p = 0 if stats is None else stats.data_ptr()
+    code = _lib.dtype_code(out)
+    es = out.element_size()
+    if st.kind == 'stem':
+        _lib.call("ehgr_stem_fwd", x_nchw.data_ptr(), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cout,
+                  _lib.dtype_code(x_nchw), code, sp,
+                  algo_bytes=x_nchw.numel() * x_nchw.element_size() + out.numel() * es,
+                  algo_flops=2 * 27 * out.numel())
+    elif st.kind == 'pw':
+        m = nt * h * wd
+        _lib.call("ehgr_pw_gemm", ctypes.byref(a_op), w.data_ptr(), 0, out.data_ptr(), 0, stats_p, m, cin, cout,
+                  code, _STATE["engine"], sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
+                  algo_flops=2 * m * cin * cout)
+    else:
+        _lib.call("ehgr_dw_fwd", ctypes.byref(a_op), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cin,
+                  st.stride, code, sp, algo_bytes=(nt * h * wd * cin + out.numel()) * es + 36 * cin,
+                  algo_flops=18 * out.numel())
+
+
+class _ChainFunction(torch.autograd.Function):
+    """forward(units, dtype, x, *params): params = per stage (conv.weight, bn.weight, bn.bias)."""
+
+    @staticmethod
+    def forward(ctx, units: List[Unit], dt, x, *params):
+        dev = x.device
+        _lib.require_cuda(x)
+        stages = [s for u in units for s in u.stages]
+        n_stat = sum(2 * s.conv.out_channels for s in stages if s.bn.training)
+        stat_arena = torch.zeros(max(n_stat, 1), dtype=torch.float64, device=dev)
+        vec_arena = torch.empty(sum(4 * s.conv.out_channels for s in stages), dtype=torch.float32, device=dev)
+        s_off = v_off = 0
+        sp = _lib.stream_ptr(dev)
+
+        first_is_stem = stages[0].kind == 'stem'
+        if first_is_stem:
+            if x.dim() != 4 or x.shape[1] != 3:
+                raise RuntimeError(f"stem expects [NT,3,H,W], got {tuple(x.shape)}")
+            x_in = x.contiguous()                       # NCHW, read directly by the stem kernel
+            if x_in.dtype not in (torch.float32, torch.bfloat16):
+                x_in = x_in.float()
+            cur_final = None
+            geom = (x_in.shape[0], x_in.shape[2], x_in.shape[3], 3)
+        else:
+            x_in = _as_nhwc(x, dt)
+            cur_final = x_in
+            geom = (x_in.shape[0], x_in.shape[2], x_in.shape[3], x_in.shape[1])
+
+        saved_units, outputs, nbt = [], [], []
+        p_i = 0
+        for u in units:
+            unit_in, unit_geom = cur_final, geom
+            lazy = None                                  # (raw, scale, shift, relu6) of the previous stage
+            recs = []
+            for st in u.stages:
+                w, gamma, beta = params[p_i], params[p_i + 1], params[p_i + 2]
+                p_i += 3
+                nt, h, wd, cin = geom
+                cout = st.conv.out_channels
+                if st.kind == 'stem':
+                    a_op = None
+                elif lazy is None:
+                    a_op = (op_shift(cur_final, st.shift[0], st.shift[1], h * wd, 1) if st.shift is not None
+                            else op_plain(cur_final))
+                else:
+                    if st.shift is not None:
+                        raise NotImplementedError("temporal shift is defined on a block input")
+                    a_op = op_affine(*lazy)
+                ho, wo = ((h - 1) // st.stride + 1, (wd - 1) // st.stride + 1) if st.kind != 'pw' else (h, wd)
+                raw = _nhwc_empty(nt, ho, wo, cout, dt, dev)
+                tr = st.bn.training
+                stats = None
+                if tr:
+                    stats = stat_arena[s_off:s_off + 2 * cout]
+                    s_off += 2 * cout
+                _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None)
+                vec = vec_arena[v_off:v_off + 4 * cout].view(4, cout)   # scale, shift, mean, invstd
+                v_off += 4 * cout
+                _lib.call("ehgr_bn_finalize", 0 if stats is None else stats.data_ptr(), nt * ho * wo, gamma.data_ptr(),
+                          beta.data_ptr(), st.bn.running_mean.data_ptr(), st.bn.running_var.data_ptr(),
+                          float(st.bn.momentum), float(st.bn.eps), int(tr), vec[0].data_ptr(), vec[1].data_ptr(),
+                          vec[2].data_ptr(), vec[3].data_ptr(), cout, sp)
+                if tr and st.bn.num_batches_tracked is not None:
+                    nbt.append(st.bn.num_batches_tracked)
+                recs.append((raw, vec, geom, tr))
+                lazy = (raw, vec[0], vec[1], st.relu6)
+                geom = (nt, ho, wo, cout)
+            # materialise the unit output: BN(+ReLU6) (+ residual)
+            nt, h, wd, c = geom
+            out = _nhwc_empty(nt, h, wd, c, dt, dev)
+            _lib.call("ehgr_row_apply", ctypes.byref(op_affine(*lazy)), unit_in.data_ptr() if u.residual else 0,
+                      out.data_ptr(), nt * h * wd, c, _lib.dtype_code(out), sp,
+                      algo_bytes=(2 + int(u.residual)) * out.numel() * out.element_size())
+            saved_units.append((unit_in, unit_geom, recs))
+            cur_final = out
+            if u.tap:
+                outputs.append(out)
+        tap_units = [i for i, u in enumerate(units) if u.tap]
+        if not units[-1].tap:
+            outputs.append(cur_final)
+            tap_units.append(len(units) - 1)
+        if nbt:
+            torch._foreach_add_(nbt, 1)
+        ctx.units, ctx.dt, ctx.saved_units, ctx.x_in = units, dt, saved_units, x_in
+        ctx.params, ctx.tap_units = params, tap_units
+        return tuple(outputs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        units, dt, params = ctx.units, ctx.dt, ctx.params
+        dev = ctx.x_in.device
+        sp = _lib.stream_ptr(dev)
+        stages = [s for u in units for s in u.stages]
+        sizes = [p.numel() for p in params]
+        gflat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)   # every parameter gradient of the chain
+        gviews, off = [], 0
+        for p, n in zip(params, sizes):
+            gviews.append(gflat[off:off + n].view(p.shape))
+            off += n
+        sum_arena = torch.zeros(sum(2 * s.conv.out_channels for s in stages), dtype=torch.float64, device=dev)
+        coef_arena = torch.empty(sum(3 * s.conv.out_channels for s in stages), dtype=torch.float32, device=dev)
+        s_off = c_off = 0
+        gout_of = {ui: g for ui, g in zip(ctx.tap_units, gouts) if g is not None}
+        need_x_grad = ctx.needs_input_grad[2]
+
+        code = _lib.F32 if dt == torch.float32 else _lib.BF16
+        es = 4 if dt == torch.float32 else 2
+        p_end = len(params)
+        g = None                                         # gradient w.r.t. the current unit's output
+        for ui in range(len(units) - 1, -1, -1):
+            u = units[ui]
+            unit_in, unit_geom, recs = ctx.saved_units[ui]
+            gt = gout_of.get(ui)
+            if gt is not None:
+                gt = _as_nhwc(gt, dt)
+                if g is None:
+                    g = gt
+                else:
+                    tmp = torch.empty_like(g)
+                    _lib.call("ehgr_row_apply", ctypes.byref(op_plain(g)), gt.data_ptr(), tmp.data_ptr(),
+                              g.numel() // g.shape[1], g.shape[1], code, sp, algo_bytes=3 * g.numel() * es)
+                    g = tmp
+            if g is None:
+                raise RuntimeError("chain backward reached a unit without an incoming gradient")
+            g_unit_out = g
+            p_begin = p_end - 3 * len(u.stages)
+            for si in range(len(u.stages) - 1, -1, -1):
+                st = u.stages[si]
+                raw, vec, geom, tr = recs[si]
+                nt, h, wd, cin = geom
+                cout = st.conv.out_channels
+                ho, wo = raw.shape[2], raw.shape[3]
+                m_out = nt * ho * wo
+                w, gamma = params[p_begin + 3 * si], params[p_begin + 3 * si + 1]
+                gw, ggam, gbet = gviews[p_begin + 3 * si], gviews[p_begin + 3 * si + 1], gviews[p_begin + 3 * si + 2]
+                sums = sum_arena[s_off:s_off + 2 * cout]
+                s_off += 2 * cout
+                coef = coef_arena[c_off:c_off + 3 * cout].view(3, cout)
+                c_off += 3 * cout
+                _lib.call("ehgr_bn_bwd_reduce", g.data_ptr(), raw.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(),
+                          int(st.relu6), sums.data_ptr(), m_out, cout, code, sp, algo_bytes=2 * m_out * cout * es)
+                _lib.call("ehgr_bn_bwd_finalize", sums.data_ptr(), m_out, gamma.data_ptr(), vec[2].data_ptr(),
+                          vec[3].data_ptr(), int(tr), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
+                          ggam.data_ptr(), gbet.data_ptr(), cout, sp)
+                dy_op = op_bnbwd(g, raw, coef[0], coef[1], coef[2], vec[0], vec[1], st.relu6)
+                if st.kind == 'stem':
+                    _lib.call("ehgr_stem_wgrad", ctypes.byref(dy_op), ctx.x_in.data_ptr(), gw.data_ptr(), nt, h, wd,
+                              cout, _lib.dtype_code(ctx.x_in), code, sp,
+                              algo_bytes=2 * m_out * cout * es + ctx.x_in.numel() * ctx.x_in.element_size(),
+                              algo_flops=2 * 27 * m_out * cout)
+                    g = None
+                    continue
+                # forward operand of this stage, re-derived from what was saved
+                if si == 0:
+                    a_op = (op_shift(unit_in, st.shift[0], st.shift[1], h * wd, 1) if st.shift is not None
+                            else op_plain(unit_in))
+                else:
+                    a_op = op_affine(recs[si - 1][0], recs[si - 1][1][0], recs[si - 1][1][1], u.stages[si - 1].relu6)
+                m_in = nt * h * wd
+                need_dgrad = not (si == 0 and ui == 0 and not need_x_grad)
+                g_prev = None
+                if st.kind == 'pw':
+                    _lib.call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), gw.data_ptr(), m_in, cin, cout,
+                              code, _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
+                              algo_flops=2 * m_in * cin * cout)
+                    if need_dgrad:
+                        g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
+                        # residual units without a shift: fold "+ g_unit_out" into the dgrad epilogue
+                        fuse_res = si == 0 and u.residual and st.shift is None
+                        _lib.call("ehgr_pw_gemm", ctypes.byref(dy_op), w.data_ptr(), 1, g_prev.data_ptr(),
+                                  g_unit_out.data_ptr() if fuse_res else 0, 0, m_in, cout, cin, code,
+                                  _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
+                                  algo_flops=2 * m_in * cin * cout)
+                else:
+                    _lib.call("ehgr_dw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), gw.data_ptr(), nt, h, wd, cin,
+                              st.stride, code, sp, algo_bytes=(2 * m_out + m_in) * cin * es,
+                              algo_flops=18 * m_out * cin)
+                    if need_dgrad:
+                        g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
+                        _lib.call("ehgr_dw_dgrad", ctypes.byref(dy_op), w.data_ptr(), g_prev.data_ptr(), nt, h, wd, cin,
+                                  st.stride, code, sp, algo_bytes=(2 * m_out + m_in) * cin * es,
+                                  algo_flops=18 * m_in * cin)
+                g = g_prev
+            # gradient w.r.t. the unit input: undo the shift, add the residual branch
+            st0 = u.stages[0]
+            if g is not None and st0.kind != 'stem':
+                nt, h, wd, cin = unit_geom
+                if st0.shift is not None:
+                    gx = torch.empty_like(g)
+                    _lib.call("ehgr_row_apply", ctypes.byref(op_shift(g, st0.shift[0], st0.shift[1], h * wd, -1)),
+                              g_unit_out.data_ptr() if u.residual else 0, gx.data_ptr(), nt * h * wd, cin, code, sp,
+                              algo_bytes=(2 + int(u.residual)) * g.numel() * es)
+                    g = gx
+                elif u.residual and st0.kind != 'pw':
+                    gx = torch.empty_like(g)
+                    _lib.call("ehgr_row_apply", ctypes.byref(op_plain(g)), g_unit_out.data_ptr(), gx.data_ptr(),
+                              nt * h * wd, cin, code, sp, algo_bytes=3 * g.numel() * es)
+                    g = gx
+            p_end = p_begin
+        gx = None
+        if need_x_grad and g is not None:
+            gx = g if g.dtype == ctx.x_in.dtype else g.to(ctx.x_in.dtype)
+        pg = [gv if p.requires_grad else None for gv, p in zip(gviews, params)]
+        return (None, None, gx, *pg)
+
+
+def _chain_params(units):
+    ps = []
+    for u in units:
+        for s in u.stages:
+            ps += [s.conv.weight, s.bn.weight, s.bn.bias]
+    return ps
+
+
+def run_chain(units: List[Unit], x):
+    return _ChainFunction.apply(units, _STATE["dtype"], x, *_chain_params(units))
+
+
+# ------------------------------------------------------------------------------------------------
+# module entry points
+# ------------------------------------------------------------------------------------------------
 def inverted_residual(m, x):
+    """InvertedResidual.forward (archs/mobilenet_v2.py:62-66) as a one-unit chain."""
     _lib.require_cuda(x)
-    y = m.conv(x)
-    return x + y if m.use_res_connect else y
+    from .action import Action
+    if len(m.conv) == 8 and isinstance(m.conv[0], Action):
+        return _inverted_residual_library(m, x)
+    return run_chain([unit_of_block(m)], x)[0]
 
 
-def mobilenet_v2_features(model, x):
-    """features[0..18] -> [NT, 1280, H/32, W/32]."""
+def mobilenet_v2_features(model, x, taps: Sequence[int] = ()):
+    """features[0..18] -> [NT, 1280, H/32, W/32] (NHWC strides).  With ``taps`` returns a tuple: the
+    outputs of the listed feature indices (ascending) followed by the final map."""
     _lib.require_cuda(x)
-    return model.features(x)
+    if _has_action(model):
+        return _features_library(model, x, taps)
+    outs = run_chain(units_of_backbone(model, taps), x)
+    return outs[0] if not taps else outs
 
 
 def mobilenet_v2_forward(model, x):
-    x = mobilenet_v2_features(model, x)
-    x = x.mean(3).mean(2)
-    return model.classifier(x)
+    f = mobilenet_v2_features(model, x)
+    return model.classifier(global_avg_pool(f))
+
+
+class _PoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        nt, c, h, w = x.shape
+        ctx.shape, ctx.dtype = (nt, c, h, w), x.dtype
+        pooled = torch.empty((nt, c), dtype=torch.float32, device=x.device)
+        _lib.call("ehgr_pool_fwd", ctypes.byref(op_plain(x)), pooled.data_ptr(), nt, h * w, c, _lib.dtype_code(x),
+                  _lib.stream_ptr(x.device), algo_bytes=x.numel() * x.element_size())
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        nt, c, h, w = ctx.shape
+        da = _nhwc_empty(nt, h, w, c, ctx.dtype, g.device)
+        g = g.contiguous().float()
+        _lib.call("ehgr_pool_bwd", g.data_ptr(), da.data_ptr(), nt, h * w, c, _lib.dtype_code(da),
+                  _lib.stream_ptr(g.device), algo_bytes=da.numel() * da.element_size())
+        return da
+
+
+def global_avg_pool(x):
+    """x.mean(3).mean(2) (archs/mobilenet_v2.py:112) -> fp32 [NT, C]."""
+    _lib.require_cuda(x)
+    dt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    return _PoolFunction.apply(_as_nhwc(x, dt))
+
+
+class _FcConsensusFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, weight, bias, n_segment):
+        nt, f = feat.shape
+        n, k = nt // n_segment, weight.shape[0]
+        feat = feat.contiguous().float()
+        w = weight.contiguous().float()
+        b = bias.contiguous().float() if bias is not None else None
+        meanfeat = torch.empty((n, f), dtype=torch.float32, device=feat.device)
+        logits = torch.empty((n, k), dtype=torch.float32, device=feat.device)
+        _lib.call("ehgr_fc_consensus_fwd", feat.data_ptr(), w.data_ptr(), _lib.ptr(b), meanfeat.data_ptr(),
+                  logits.data_ptr(), n, n_segment, f, k, _lib.stream_ptr(feat.device))
+        ctx.save_for_backward(meanfeat, w)
+        ctx.meta = (n, n_segment, f, k, bias is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        meanfeat, w = ctx.saved_tensors
+        n, T, f, k, has_bias = ctx.meta
+        g = g.contiguous().float()
+        dfeat = torch.empty((n * T, f), dtype=torch.float32, device=g.device)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(k, dtype=torch.float32, device=g.device) if has_bias else None
+        _lib.call("ehgr_fc_consensus_bwd", g.data_ptr(), meanfeat.data_ptr(), w.data_ptr(), dfeat.data_ptr(),
+                  dw.data_ptr(), _lib.ptr(db), n, T, f, k, _lib.stream_ptr(g.device))
+        return dfeat, dw, db, None
+
+
+def fc_consensus(feat, linear: nn.Linear, n_segment: int):
+    """new_fc followed by the 'avg' segment consensus: [N*T, F] -> [N, K]."""
+    if feat.shape[0] % n_segment:
+        raise RuntimeError(f"shape '[-1, {n_segment}, ...]' is invalid for input with {feat.shape[0]} rows")
+    return _FcConsensusFunction.apply(feat, linear.weight, linear.bias, n_segment)
 
 
 def classifier_head(tsn, fmap):
     """global average pool -> Dropout -> new_fc -> mean over segments (models/models.py:341-356)."""
-    pooled = fmap.mean(3).mean(2)
+    pooled = global_avg_pool(fmap)
     drop = getattr(tsn.base_model, tsn.base_model.last_layer_name)
-    z = tsn.new_fc(drop(pooled))
+    if isinstance(drop, nn.Dropout):
+        pooled = drop(pooled)                       # mask-and-scale on the tiny [NT, F] tensor
+        if tsn.consensus_type == 'avg' and tsn.new_fc is not None and tsn.before_softmax:
+            return fc_consensus(pooled, tsn.new_fc, tsn.num_segments)
+        z = tsn.new_fc(pooled)
+    else:                                           # dropout == 0: the Linear sits in the backbone
+        z = drop(pooled)
+    if not tsn.before_softmax:
+        z = tsn.softmax(z)
     z = z.view((-1, tsn.num_segments) + z.size()[1:])
     return tsn.consensus(z).squeeze(1)
 
 
+# ------------------------------------------------------------------------------------------------
+# ACTION (bring-up state: excitation arithmetic on library ops; fused kernels pending)
+# ------------------------------------------------------------------------------------------------
 def action_forward(m, x):
     """out = net(x_shift * (3 + g_STE + g_CE + g_ME)) — reference models/action.py:61-116."""
+    import torch.nn.functional as F
     _lib.require_cuda(x)
     nt, c, h, w = x.shape
     T = m.n_segment
     n = nt // T
     x5 = x.reshape(n, T, c, h, w)
-    # per-channel 3-tap temporal FIR (zero padded)
     wt = m.action_shift.weight.view(c, 3)
     xp = F.pad(x5, (0, 0, 0, 0, 0, 0, 1, 1))
     xs = (xp[:, :-2] * wt[:, 0].view(1, 1, c, 1, 1) + xp[:, 1:-1] * wt[:, 1].view(1, 1, c, 1, 1)
           + xp[:, 2:] * wt[:, 2].view(1, 1, c, 1, 1))
-    # STE
-    g1 = torch.sigmoid(m.action_p1_conv1(xs.mean(2, keepdim=True).transpose(1, 2)))  # [n,1,T,h,w]
-    g1 = g1.transpose(1, 2)                                                          # [n,T,1,h,w]
-    # CE
-    p = xs.mean((3, 4))                                                              # [n,T,c]
+    g1 = torch.sigmoid(m.action_p1_conv1(xs.mean(2, keepdim=True).transpose(1, 2))).transpose(1, 2)
+    p = xs.mean((3, 4))
     s = F.conv2d(p.reshape(nt, c, 1, 1), m.action_p2_squeeze.weight).view(n, T, -1).transpose(1, 2)
     s = F.relu(m.action_p2_conv1(s)).transpose(1, 2).reshape(nt, -1, 1, 1)
     g2 = torch.sigmoid(F.conv2d(s, m.action_p2_expand.weight)).view(n, T, c, 1, 1)
-    # ME
     x3 = m.action_p3_bn1(m.action_p3_squeeze(xs.reshape(nt, c, h, w)))
     cr = x3.shape[1]
     c3 = m.action_p3_conv1(x3).view(n, T, cr, h, w)
@@ -81,3 +561,24 @@ def action_forward(m, x):
     g3 = torch.sigmoid(F.conv2d(d.mean((3, 4)).reshape(nt, cr, 1, 1), m.action_p3_expand.weight)).view(n, T, c, 1, 1)
     y = xs * (3.0 + g1 + g2 + g3)
     return m.net(y.reshape(nt, c, h, w))
+
+
+def _inverted_residual_library(m, x):
+    y = m.conv(x)
+    return x + y if m.use_res_connect else y
+
+
+def _features_library(model, x, taps):
+    from .action import Action
+    outs = []
+    last = len(model.features) - 1
+    for i, f in enumerate(model.features):
+        if i == 0 or i == last:
+            x = f(x)
+        elif len(f.conv) == 8 and isinstance(f.conv[0], Action):
+            x = _inverted_residual_library(f, x)
+        else:
+            x = f(x)
+        if i in taps:
+            outs.append(x)
+    return x if not taps else tuple(outs + ([] if last in taps else [x]))

@@ -1,37 +1,101 @@
-"""Loss heads of the two training stages.
+"""Loss heads of the two training stages — one fused forward+backward kernel each (csrc/loss.cu).
 
 * ``mtmm_loss``  — train_mtmm.py:223-231: CE(logits, labels) + 0.01 * MSE(depth_pred,
   bilinear56(depth_gt)).  The 224->56 bilinear resize with align_corners=False is exactly the mean of
-  the 2x2 pixels at rows/cols 4i+1, 4i+2, which is what the fused kernel reads.
+  the 2x2 pixels at rows/cols 4i+1, 4i+2, which is what the kernel reads directly.
 * ``sd_loss``    — train_sd.py:178-193,227-265: 4 CE + 3 temperature-KL (x T^2) + 3 masked-L2 feature
   terms, weights (1-alpha), alpha, beta.
+
+Both return device scalars (no .item() synchronisation: the reference syncs 4 / 17 times per step).
+The gradients w.r.t. logits / depth prediction / features are produced by the same launch and
+handed to autograd in ``backward`` (scaled by the incoming gradient of the loss).
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 
 
+class _MTMMLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, pred, labels, depth_gt, depth_weight):
+        _lib.require_cuda(logits, pred, labels, depth_gt)
+        n, k = logits.shape
+        ph, pw = pred.shape[-2:]
+        frames = pred.numel() // (ph * pw)
+        if depth_gt.shape[-2] != 4 * ph or depth_gt.shape[-1] != 4 * pw or depth_gt.numel() != frames * 16 * ph * pw:
+            raise RuntimeError("mtmm_loss expects depth_gt of 4x the spatial size of depth_pred and the same frame count")
+        lg = logits.contiguous().float()
+        pr = pred.contiguous()
+        if pr.dtype not in (torch.float32, torch.bfloat16):
+            pr = pr.float()
+        gt = depth_gt.contiguous().float()
+        lab = labels.contiguous().long()
+        out = torch.zeros(3, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(lg)
+        dpred = torch.empty(pr.shape, dtype=torch.float32, device=pr.device)
+        _lib.call("ehgr_mtmm_loss", lg.data_ptr(), lab.data_ptr(), pr.data_ptr(), gt.data_ptr(), float(depth_weight),
+                  out.data_ptr(), dlogits.data_ptr(), dpred.data_ptr(), n, k, frames, ph, pw, _lib.dtype_code(pr),
+                  _lib.stream_ptr(logits.device), algo_bytes=gt.numel() * 2 + pr.numel() * (pr.element_size() + 4))
+        ctx.save_for_backward(dlogits, dpred)
+        ctx.dtypes = (logits.dtype, pred.dtype)
+        return out                                  # [total, CE, MSE]; only out[0] carries gradient
+
+    @staticmethod
+    def backward(ctx, g_out):
+        dlogits, dpred = ctx.saved_tensors
+        g_total = g_out[0]
+        return (dlogits * g_total).to(ctx.dtypes[0]), (dpred * g_total).to(ctx.dtypes[1]), None, None, None
+
+
 def mtmm_loss(logits, labels, depth_pred, depth_gt, depth_weight: float = 0.01):
-    """Returns (loss, depth_mse).  depth_gt: [N,T,1,224,224] (any leading shape, HxW = 4x depth_pred)."""
-    _lib.require_cuda(logits, depth_pred, depth_gt)
-    gt = depth_gt.reshape(-1, 1, depth_gt.size(-2), depth_gt.size(-1)).float()
-    gt = F.interpolate(gt, size=tuple(depth_pred.shape[-2:]), mode='bilinear')
-    depth_mse = F.mse_loss(depth_pred.float(), gt)
-    return F.cross_entropy(logits.float(), labels) + depth_weight * depth_mse, depth_mse
+    """Returns (loss, depth_mse) as device scalars.  depth_gt: [..., 4*ph, 4*pw] fp32 in [0,1]."""
+    out = _MTMMLossFunction.apply(logits, depth_pred, labels, depth_gt, depth_weight)
+    return out[0], out[2].detach()
+
+
+class _SDLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, alpha, beta, temperature, *tensors):
+        logits, feats = tensors[:4], tensors[4:]
+        _lib.require_cuda(*tensors)
+        n, k = logits[0].shape
+        lg = [t.contiguous().float() for t in logits]
+        ft = [t.contiguous().float().reshape(t.shape[0], -1) for t in feats]
+        rows, f = ft[0].shape
+        if any(t.shape != (rows, f) for t in ft) or any(t.shape != (n, k) for t in lg):
+            raise RuntimeError("sd_loss: the four logits / four feature tensors must have equal shapes")
+        lab = labels.contiguous().long()
+        terms = torch.zeros(11, dtype=torch.float32, device=lab.device)
+        dl = [torch.empty_like(t) for t in lg]
+        df = [torch.empty_like(t) for t in ft[1:]]
+        P4, P3 = ctypes.c_void_p * 4, ctypes.c_void_p * 3
+        _lib.call("ehgr_sd_loss", P4(*[t.data_ptr() for t in lg]), P4(*[t.data_ptr() for t in ft]), lab.data_ptr(),
+                  float(alpha), float(beta), float(temperature), terms.data_ptr(), P4(*[t.data_ptr() for t in dl]),
+                  P3(*[t.data_ptr() for t in df]), n, k, rows, f, _lib.stream_ptr(lab.device),
+                  algo_bytes=7 * rows * f * 4)
+        ctx.save_for_backward(*dl, *df)
+        ctx.meta = ([t.dtype for t in logits], [t.dtype for t in feats], [t.shape for t in feats])
+        return terms                                # [total, 4 CE, 3 KD, 3 feature]; only terms[0] carries gradient
+
+    @staticmethod
+    def backward(ctx, g_terms):
+        saved = ctx.saved_tensors
+        g_total = g_terms[0]
+        dl, df = saved[:4], saved[4:]
+        ldt, fdt, fshape = ctx.meta
+        gl = [(d * g_total).to(t) for d, t in zip(dl, ldt)]
+        gf = [None] + [(d * g_total).to(t).reshape(s) for d, t, s in zip(df, fdt[1:], fshape[1:])]
+        return (None, None, None, None, *gl, *gf)
 
 
 def sd_loss(outputs, feats, labels, alpha: float = 0.1, beta: float = 1e-6, temperature: float = 3.0):
-    """outputs = (final, mid1, mid2, mid3) logits [N,cls]; feats = (final, mid1, mid2, mid3) pooled
-    features.  Returns (total, terms[10]) with terms = 4 CE, 3 KD (already x T^2), 3 feature sums."""
-    _lib.require_cuda(*outputs, *feats)
-    out = [o.float() for o in outputs]
-    ce = [F.cross_entropy(o, labels) for o in out]
-    soft = torch.softmax(out[0] / temperature, dim=1).detach()
-    kd = [-(torch.log_softmax(o / temperature, dim=1) * soft).sum(1).mean() * temperature ** 2 for o in out[1:]]
-    f4 = feats[0].detach().float()
-    fl = [(((f.float() - f4) ** 2) * ((f > 0) | (f4 > 0)).float()).sum() for f in feats[1:]]
-    total = (1 - alpha) * sum(ce) + alpha * sum(kd) + beta * sum(fl)
-    return total, torch.stack(ce + kd + fl)
+    """outputs = (final, mid1, mid2, mid3) logits [N,cls]; feats = (final, mid1, mid2, mid3) pooled features
+    (any trailing shape).  Returns (total, terms[10]): 4 CE, 3 KD (already x T^2), 3 feature sums."""
+    if len(outputs) != 4 or len(feats) != 4:
+        raise ValueError("sd_loss expects four logits and four feature tensors (final first)")
+    terms = _SDLossFunction.apply(labels, alpha, beta, temperature, *outputs, *feats)
+    return terms[0], terms[1:].detach()

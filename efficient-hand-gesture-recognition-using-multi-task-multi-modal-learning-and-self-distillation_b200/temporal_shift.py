@@ -37,6 +37,8 @@ def _run_shift(x: torch.Tensor, n_segment: int, fold: int, backward: bool) -> to
     nt, c, h, w = x.shape
     x, layout = _layout_of(x)
     out = torch.empty_like(x)  # preserves the memory format
+    if x.numel() == 0:
+        return out
     name = "ehgr_temporal_shift_bwd" if backward else "ehgr_temporal_shift_fwd"
     with torch.cuda.device(x.device):
         _lib.call(name, x.data_ptr(), out.data_ptr(), nt // n_segment, n_segment, c, h * w, fold,

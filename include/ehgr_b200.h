@@ -69,6 +69,143 @@ int ehgr_temporal_shift_fwd(const void* x, void* out, int n_batch, int n_segment
 int ehgr_temporal_shift_bwd(const void* grad_out, void* grad_in, int n_batch, int n_segment, int c,
                             int hw, int fold, int dtype, int layout, ehgr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row operand — how a fused kernel READS an NHWC activation [M, C] (M = NT*H*W rows).
+ * Activations are stored raw (conv output before BatchNorm); BatchNorm(+ReLU6), the temporal shift
+ * and the BatchNorm-backward combination are applied while loading (csrc/rowop.cuh).  HOST struct,
+ * copied into the kernel's parameters; all pointers inside are device pointers.
+ * ------------------------------------------------------------------------------------------- */
+enum { EHGR_ROW_PLAIN = 0, EHGR_ROW_AFFINE = 1, EHGR_ROW_SHIFT = 2, EHGR_ROW_BNBWD = 3 };
+
+typedef struct ehgr_rowop {
+  int32_t mode;        /* EHGR_ROW_* */
+  int32_t relu6;       /* AFFINE: clamp to [0,6];  BNBWD: mask in1 where !(0 < in2*scale+shift < 6) */
+  const void* in1;     /* [M, C] activation (or, for BNBWD, gradient w.r.t. the post-activation) */
+  const void* in2;     /* BNBWD: raw forward output of the layer, [M, C] */
+  const float* scale;  /* [C] BatchNorm scale  gamma*invstd       (AFFINE; BNBWD when relu6) */
+  const float* shift;  /* [C] BatchNorm shift  beta - mean*scale  (AFFINE; BNBWD when relu6) */
+  const float* ca;     /* [C] BNBWD: v = ca*mask*in1 + cb*in2 + cc */
+  const float* cb;
+  const float* cc;
+  int32_t n_segment;   /* SHIFT: frames per clip T */
+  int32_t fold;        /* SHIFT: shifted channels per direction */
+  int32_t hw;          /* SHIFT: rows per frame (H*W) */
+  int32_t shift_dir;   /* SHIFT: +1 forward shift, -1 its adjoint */
+} ehgr_rowop;
+
+enum { EHGR_ENGINE_AUTO = 0, EHGR_ENGINE_SIMT = 1, EHGR_ENGINE_TCGEN05 = 2 };
+
+/* ---------------------------------------------------------------------------------------------
+ * K8/K11  pointwise (1x1) convolution as a GEMM over NHWC rows — replaces the nn.Conv2d 1x1 layers of
+ *   InvertedResidual / conv_1x1_bn (archs/mobilenet_v2.py:15-20,44-45,50-52,58-59) and, with
+ *   w_is_kn=1, their input-gradient (autograd's conv dgrad).
+ *     out[M,N] = rowop(a)[M,K] * B[K,N] (+ addend[M,N])
+ *     B[k][n] = w[n*K + k]  (w_is_kn = 0: w is the conv weight [N_out, K_in], forward)
+ *             = w[k*N + n]  (w_is_kn = 1: w is the conv weight [K, N] read as is: dgrad)
+ *   w is fp32 (master weights); out/addend have `dtype`.  stats (nullable) = double[2N]:
+ *   stats[n] += sum_m out[m,n], stats[N+n] += sum_m out[m,n]^2 (BatchNorm batch statistics, K14),
+ *   accumulated from the fp32 accumulators.  K % 8 == 0 and N % 8 == 0 required.
+ *   engine: AUTO picks the tcgen05/TMEM tensor-core kernel for bf16 when the shape is supported and
+ *   the fp32 SIMT kernel otherwise; SIMT / TCGEN05 force one (TCGEN05 -> EHGR_E_UNSUPPORTED if not).
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_pw_gemm(const ehgr_rowop* a, const float* w, int w_is_kn, void* out, const void* addend,
+                 double* stats, long long M, int K, int N, int dtype, int engine, ehgr_stream_t stream);
+
+/* weight gradient of the same layer: dw[N,K] += sum_m rowop(dy)[m,n] * rowop(a)[m,k]   (fp32, atomics;
+ * the caller zeroes dw).  dy is normally a BNBWD operand, a the layer's forward operand. */
+int ehgr_pw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, long long M, int K, int N,
+                  int dtype, int engine, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K7  depthwise 3x3 convolution, pad 1, stride 1|2 (archs/mobilenet_v2.py:40,54), NHWC.
+ *   fwd   : out[nt,ho,wo,c] = sum_{kh,kw} rowop(a)[nt, ho*s+kh-1, wo*s+kw-1, c] * w[c,kh,kw]
+ *           (taps outside the image contribute 0 — the padding is applied AFTER the row operand).
+ *           stats as in ehgr_pw_gemm (double[2C], nullable).
+ *   dgrad : da[nt,h,w,c] = sum over taps of rowop(dy)[...] * w   (gradient w.r.t. rowop(a))
+ *   wgrad : dw[c,kh,kw] += sum rowop(dy)[q] * rowop(a)[p(q,kh,kw)]   (fp32 atomics, caller zeroes)
+ *   w: fp32 [C,1,3,3] contiguous.  C % 8 == 0.  Ho = (H-1)/s + 1.
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, double* stats, int nt, int h, int wd, int c,
+                int stride, int dtype, ehgr_stream_t stream);
+int ehgr_dw_dgrad(const ehgr_rowop* dy, const float* w, void* da, int nt, int h, int wd, int c, int stride,
+                  int dtype, ehgr_stream_t stream);
+int ehgr_dw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, int nt, int h, int wd, int c,
+                  int stride, int dtype, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9  stem: dense 3x3 stride-2 pad-1 convolution 3 -> cout from the NCHW network input
+ *   (archs/mobilenet_v2.py:7-12,90) to an NHWC raw output + batch statistics; and its weight
+ *   gradient (the network input needs no gradient).  x: [nt,3,h,w] of x_dtype; w: fp32 [cout,3,3,3].
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_stem_fwd(const void* x, const float* w, void* out, double* stats, int nt, int h, int wd, int cout,
+                  int x_dtype, int dtype, ehgr_stream_t stream);
+int ehgr_stem_wgrad(const ehgr_rowop* dy, const void* x, float* dw, int nt, int h, int wd, int cout,
+                    int x_dtype, int dtype, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K14  BatchNorm2d bookkeeping (nn.BatchNorm2d semantics: biased variance normalises, unbiased
+ *   variance feeds running_var, momentum update; eval mode uses the running statistics).
+ *   finalize     : stats (double[2C]: sum, sum of squares over `count` elements per channel) ->
+ *                  scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (all fp32 [C]);
+ *                  training != 0 also updates running_mean/var in place.  training == 0 ignores
+ *                  stats/count and uses running_mean/var.
+ *   bwd_reduce   : sums[c] += sum_m mask*g[m,c];  sums[C+c] += sum_m mask*g[m,c]*raw[m,c]
+ *                  mask = relu6 ? (0 < raw*scale+shift < 6) : 1          (double[2C], caller zeroes)
+ *   bwd_finalize : sums -> (ca, cb, cc) of the BNBWD row operand and dgamma, dbeta.
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, int training,
+                     float* scale, float* shift, float* mean, float* invstd, int c, ehgr_stream_t stream);
+int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* scale, const float* shift, int relu6,
+                       double* sums, long long m, int c, int dtype, ehgr_stream_t stream);
+int ehgr_bn_bwd_finalize(const double* sums, long long count, const float* gamma, const float* mean,
+                         const float* invstd, int training, float* ca, float* cb, float* cc, float* dgamma,
+                         float* dbeta, int c, ehgr_stream_t stream);
+
+/* out[M,C] = rowop(a) (+ addend): materialises a lazy activation — BatchNorm(+ReLU6)(+residual add,
+ * InvertedResidual.forward archs/mobilenet_v2.py:62-66) — or, with a SHIFT operand of shift_dir=-1,
+ * the input gradient of a shifted block plus the residual gradient. */
+int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out, long long m, int c, int dtype,
+                   ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K10  classifier head: x.mean(3).mean(2) (archs/mobilenet_v2.py:112), new_fc and the segment
+ *   consensus (models/models.py:341-356, models/basic_ops.py:9-37).
+ *   pool_fwd : pooled[nt,c] (fp32) = mean over hw rows of rowop(a)
+ *   pool_bwd : da[nt*hw, c] = dpooled[nt,c] / hw
+ *   fc_consensus_fwd : meanfeat[n,f] = mean_t feat[n*T+t, f];  logits[n,k] = bias[k] + sum_f W[k,f]*meanfeat[n,f]
+ *   fc_consensus_bwd : dfeat[n*T+t,f] = (1/T) sum_k dlogits[n,k] W[k,f];
+ *                      dW[k,f] += sum_n dlogits[n,k] meanfeat[n,f];  db[k] += sum_n dlogits[n,k]
+ *                      (fp32 atomics; the caller zeroes dW, db)
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_pool_fwd(const ehgr_rowop* a, float* pooled, int nt, int hw, int c, int dtype, ehgr_stream_t stream);
+int ehgr_pool_bwd(const float* dpooled, void* da, int nt, int hw, int c, int dtype, ehgr_stream_t stream);
+int ehgr_fc_consensus_fwd(const float* feat, const float* w, const float* bias, float* meanfeat, float* logits,
+                          int n, int n_segment, int f, int k, ehgr_stream_t stream);
+int ehgr_fc_consensus_bwd(const float* dlogits, const float* meanfeat, const float* w, float* dfeat, float* dw,
+                          float* dbias, int n, int n_segment, int f, int k, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K12  MTMM loss, forward and backward in one launch (train_mtmm.py:223-231):
+ *   loss = CE(logits, labels) + depth_weight * MSE(pred, bilinear_{gh x gw -> ph x pw}(depth_gt))
+ *   with gh = 4*ph, gw = 4*pw (align_corners=False => mean of the 2x2 centre pixels of each 4x4 cell).
+ *   logits fp32 [n,k]; labels int64 [n]; pred `dtype` [frames,ph,pw]; depth_gt fp32 [frames,gh,gw].
+ *   out: loss_out[0] = total, loss_out[1] = CE, loss_out[2] = MSE (fp32, caller zeroes);
+ *        dlogits fp32 [n,k]; dpred fp32 [frames,ph,pw]   (gradients of `total`).
+ * K13  self-distillation loss (train_sd.py:178-193,227-265), forward+backward in one launch:
+ *   logits: HOST array of 4 device pointers fp32 [n,k] (final, mid1..3); feats: HOST array of 4 device
+ *   pointers fp32 [rows,f] (final, mid1..3).
+ *   terms_out fp32[11] = total, 4 CE, 3 KD (x T^2), 3 feature sums (caller zeroes);
+ *   dlogits: HOST array of 4 device pointers [n,k]; dfeats: HOST array of 3 device pointers [rows,f]
+ *   (mid1..3; the final feature is detached).
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_mtmm_loss(const float* logits, const long long* labels, const void* pred, const float* depth_gt,
+                   float depth_weight, float* loss_out, float* dlogits, float* dpred, int n, int k,
+                   int frames, int ph, int pw, int dtype, ehgr_stream_t stream);
+int ehgr_sd_loss(const float* const* logits, const float* const* feats, const long long* labels, float alpha,
+                 float beta, float temperature, float* terms_out, float* const* dlogits, float* const* dfeats,
+                 int n, int k, long long rows, int f, ehgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

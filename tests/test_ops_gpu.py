@@ -1,0 +1,298 @@
+"""Per-kernel parity: each C-ABI entry point against a plain PyTorch restatement of the same op
+evaluated in fp64 on the CPU (fp32 kernels: 1e-5 relative; bf16 storage: 2e-2)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+
+
+def _E():
+    import ehgr_b200
+    return ehgr_b200
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+def _rows(x_nchw):
+    """[NT,C,H,W] -> [M, C] rows (NHWC order)."""
+    return x_nchw.permute(0, 2, 3, 1).reshape(-1, x_nchw.shape[1])
+
+
+def _dev_rows(t, dtype):
+    return t.to(dtype).cuda().contiguous()
+
+
+def _call(name, *args):
+    _E()._lib.call(name, *args)
+
+
+def _sp():
+    return _E()._lib.stream_ptr(torch.device("cuda"))
+
+
+# ---------------------------------------------------------------------------------------------
+# row operand semantics, through ehgr_row_apply
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_row_apply_modes(dtype):
+    E = _E()
+    f = E.fused
+    M, C, T, hw = 2 * 4 * 6, 24, 4, 6
+    x = _rand((M, C), 1).to(dtype)
+    xr = x.double()
+    scale, shift = _rand((C,), 2).abs() + 0.5, _rand((C,), 3)
+    add = _rand((M, C), 4).to(dtype)
+    xd, ad = x.cuda(), add.cuda()
+    sd_, sh_ = scale.cuda(), shift.cuda()
+    code = E._lib.dtype_code(xd)
+
+    def run(op, addend=None):
+        out = torch.empty_like(xd)
+        _call("ehgr_row_apply", ctypes.byref(op), 0 if addend is None else addend.data_ptr(), out.data_ptr(), M, C, code, _sp())
+        return out.cpu().double()
+
+    assert rel_err(run(f.op_plain(xd), ad), xr + add.double()) < TOL[dtype]
+    want = torch.clamp(xr * scale.double() + shift.double(), 0, 6)
+    assert rel_err(run(f.op_affine(xd, sd_, sh_, True)), want) < TOL[dtype]
+    want = xr * scale.double() + shift.double() + add.double()
+    assert rel_err(run(f.op_affine(xd, sd_, sh_, False), ad), want) < TOL[dtype]
+    # shift (NHWC rows) == reference shift on the NCHW view, exactly
+    from oracle import ref_oracle as O
+    x4 = x.view(2 * T, 2, 3, C).permute(0, 3, 1, 2).contiguous()          # [NT, C, 2, 3]
+    for fold in (3, 8, 0, 12):
+        want = torch.from_numpy(O.temporal_shift_np(x4.float().numpy(), T, C // fold if fold else 10 ** 6)) if fold else x4.float()
+        if fold:
+            # oracle takes fold_div; emulate an absolute fold by picking c//fold_div == fold
+            div = C // fold
+            assert C // div == fold
+            want = torch.from_numpy(O.temporal_shift_np(x4.float().numpy(), T, div))
+        got = run(f.op_shift(xd, T, fold, hw, 1)).float().view(2 * T, 2, 3, C).permute(0, 3, 1, 2)
+        assert torch.equal(got, want.float()), fold
+        if fold:
+            wantb = torch.from_numpy(O.temporal_shift_bwd_np(x4.float().numpy(), T, div))
+            gotb = run(f.op_shift(xd, T, fold, hw, -1)).float().view(2 * T, 2, 3, C).permute(0, 3, 1, 2)
+            assert torch.equal(gotb, wantb.float())
+    # BNBWD
+    raw = _rand((M, C), 5).to(dtype)
+    ca, cb, cc = _rand((C,), 6), _rand((C,), 7) * 0.1, _rand((C,), 8) * 0.1
+    z = raw.double() * scale.double() + shift.double()
+    mask = ((z > 0) & (z < 6)).double()
+    want = ca.double() * mask * xr + cb.double() * raw.double() + cc.double()
+    got = run(f.op_bnbwd(xd, raw.cuda(), ca.cuda(), cb.cuda(), cc.cuda(), sd_, sh_, True))
+    assert rel_err(got, want) < TOL[dtype]
+
+
+# ---------------------------------------------------------------------------------------------
+# pointwise GEMM (SIMT engine) fwd / dgrad / wgrad
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,N", [(200, 16, 96), (333, 24, 144), (128, 144, 24), (50, 960, 320), (1000, 32, 192), (64, 320, 1280)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pw_gemm_simt(M, K, N, dtype):
+    E = _E()
+    f = E.fused
+    a = _rand((M, K), 10).to(dtype)
+    w = _rand((N, K), 11, (2.0 / K) ** 0.5)
+    add = _rand((M, N), 12).to(dtype)
+    scale, shift = _rand((K,), 13).abs() + 0.5, _rand((K,), 14)
+    ad, wd, addd = a.cuda(), w.cuda(), add.cuda()
+    code = E._lib.dtype_code(ad)
+    # forward with lazy BN+ReLU6 prologue, stats
+    out = torch.empty((M, N), dtype=dtype, device="cuda")
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)), wd.data_ptr(), 0, out.data_ptr(), 0,
+          stats.data_ptr(), M, K, N, code, 1, _sp())
+    aa = torch.clamp(a.double() * scale.double() + shift.double(), 0, 6)
+    want = aa @ w.double().t()
+    assert rel_err(out.cpu(), want) < TOL[dtype]
+    assert rel_err(stats[:N].cpu(), want.sum(0)) < 1e-4 and rel_err(stats[N:].cpu(), (want ** 2).sum(0)) < 1e-4
+    # "dgrad" form: out[M,K] = g[M,N] @ W[N,K] + addend
+    g = _rand((M, N), 15).to(dtype)
+    out2 = torch.empty((M, K), dtype=dtype, device="cuda")
+    add2 = _rand((M, K), 16).to(dtype)
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_plain(g.cuda())), wd.data_ptr(), 1, out2.data_ptr(), add2.cuda().data_ptr(), 0,
+          M, N, K, code, 1, _sp())
+    assert rel_err(out2.cpu(), g.double() @ w.double() + add2.double()) < TOL[dtype]
+    # wgrad: dW[N,K] = g^T a'
+    dw = torch.zeros((N, K), dtype=torch.float32, device="cuda")
+    _call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(g.cuda())), ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)),
+          dw.data_ptr(), M, K, N, code, 1, _sp())
+    assert rel_err(dw.cpu(), g.double().t() @ aa) < max(TOL[dtype], 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# depthwise 3x3
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nt,h,w,c,stride", [(3, 9, 7, 32, 1), (2, 8, 8, 96, 2), (2, 7, 7, 960, 1), (2, 14, 14, 144, 2), (1, 1, 1, 16, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dw_fwd_bwd(nt, h, w, c, stride, dtype):
+    E = _E()
+    f = E.fused
+    x = _rand((nt, c, h, w), 20).to(dtype)
+    wt = _rand((c, 1, 3, 3), 21, 0.4)
+    scale, shift = _rand((c,), 22).abs() + 0.5, _rand((c,), 23)
+    xr = _rows(x).contiguous().cuda()
+    code = E._lib.dtype_code(xr)
+    a64 = torch.clamp(x.double() * scale.double().view(1, c, 1, 1) + shift.double().view(1, c, 1, 1), 0, 6).requires_grad_(True)
+    w64 = wt.double().requires_grad_(True)
+    y64 = F.conv2d(a64, w64, stride=stride, padding=1, groups=c)
+    ho, wo = y64.shape[2:]
+    a_op = f.op_affine(xr, scale.cuda(), shift.cuda(), True)
+    out = torch.empty((nt * ho * wo, c), dtype=dtype, device="cuda")
+    stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+    _call("ehgr_dw_fwd", ctypes.byref(a_op), wt.cuda().data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, c, stride, code, _sp())
+    assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
+    assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < 1e-4
+    assert rel_err(stats[c:].cpu(), (y64 ** 2).sum((0, 2, 3))) < 1e-4
+    g = _rand(tuple(y64.shape), 24).to(dtype)
+    y64.backward(g.double())
+    gr = _rows(g).contiguous().cuda()
+    da = torch.empty((nt * h * w, c), dtype=dtype, device="cuda")
+    _call("ehgr_dw_dgrad", ctypes.byref(f.op_plain(gr)), wt.cuda().data_ptr(), da.data_ptr(), nt, h, w, c, stride, code, _sp())
+    assert rel_err(da.cpu(), _rows(a64.grad)) < TOL[dtype]
+    dw = torch.zeros((c, 9), dtype=torch.float32, device="cuda")
+    _call("ehgr_dw_wgrad", ctypes.byref(f.op_plain(gr)), ctypes.byref(a_op), dw.data_ptr(), nt, h, w, c, stride, code, _sp())
+    assert rel_err(dw.cpu(), w64.grad.view(c, 9)) < max(TOL[dtype], 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# stem
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw", [(32, 32), (17, 23)])
+def test_stem(dtype, hw):
+    E = _E()
+    f = E.fused
+    h, w = hw
+    nt, cout = 3, 32
+    x = _rand((nt, 3, h, w), 30)
+    wt = _rand((cout, 3, 3, 3), 31, 0.3)
+    x64, w64 = x.double(), wt.double().requires_grad_(True)
+    y64 = F.conv2d(x64, w64, stride=2, padding=1)
+    ho, wo = y64.shape[2:]
+    out = torch.empty((nt * ho * wo, cout), dtype=dtype, device="cuda")
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    xd = x.cuda()
+    code = E._lib.dtype_code(out)
+    _call("ehgr_stem_fwd", xd.data_ptr(), wt.cuda().data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, cout, 0, code, _sp())
+    assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
+    assert rel_err(stats[:cout].cpu(), y64.sum((0, 2, 3))) < 1e-4
+    g = _rand(tuple(y64.shape), 32).to(dtype)
+    y64.backward(g.double())
+    dw = torch.zeros((cout, 27), dtype=torch.float32, device="cuda")
+    _call("ehgr_stem_wgrad", ctypes.byref(f.op_plain(_rows(g).contiguous().cuda())), xd.data_ptr(), dw.data_ptr(), nt, h, w, cout, 0,
+          code, _sp())
+    assert rel_err(dw.cpu(), w64.grad.view(cout, 27)) < max(TOL[dtype], 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm bookkeeping against nn.BatchNorm2d semantics
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_forward_backward_against_torch(training):
+    E = _E()
+    f = E.fused
+    M, C = 5 * 6 * 7, 40
+    x = _rand((5, C, 6, 7), 40) * 2 + 0.5
+    bn = torch.nn.BatchNorm2d(C).double()
+    bn.weight.data = _rand((C,), 41).double().abs() + 0.5
+    bn.bias.data = _rand((C,), 42).double()
+    bn.running_mean.data = _rand((C,), 43).double() * 0.2
+    bn.running_var.data = _rand((C,), 44).double().abs() + 0.5
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    bn.train(training)
+    x64 = x.double().requires_grad_(True)
+    y = F.relu6(bn(x64))
+    g = _rand(tuple(y.shape), 45)
+    y.backward(g.double())
+
+    xr = _rows(x).contiguous().cuda()
+    stats = torch.stack([xr.double().sum(0), (xr.double() ** 2).sum(0)]).reshape(-1).contiguous()
+    gamma, beta = bn.weight.data.float().cuda(), bn.bias.data.float().cuda()
+    rm, rv = rm0.float().cuda(), rv0.float().cuda()
+    vec = torch.empty((4, C), dtype=torch.float32, device="cuda")
+    _call("ehgr_bn_finalize", stats.data_ptr(), M, gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5,
+          int(training), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), C, _sp())
+    out = torch.empty_like(xr)
+    _call("ehgr_row_apply", ctypes.byref(f.op_affine(xr, vec[0], vec[1], True)), 0, out.data_ptr(), M, C, 0, _sp())
+    assert rel_err(out.cpu(), _rows(y)) < 1e-5
+    assert rel_err(rm.cpu(), bn.running_mean) < 1e-6 and rel_err(rv.cpu(), bn.running_var) < 1e-6
+    # backward
+    gr = _rows(g).contiguous().cuda()
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    _call("ehgr_bn_bwd_reduce", gr.data_ptr(), xr.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(), 1, sums.data_ptr(), M, C, 0, _sp())
+    coef = torch.empty((3, C), dtype=torch.float32, device="cuda")
+    dgb = torch.empty((2, C), dtype=torch.float32, device="cuda")
+    _call("ehgr_bn_bwd_finalize", sums.data_ptr(), M, gamma.data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), int(training),
+          coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), C, _sp())
+    dx = torch.empty_like(xr)
+    _call("ehgr_row_apply", ctypes.byref(f.op_bnbwd(gr, xr, coef[0], coef[1], coef[2], vec[0], vec[1], True)), 0, dx.data_ptr(),
+          M, C, 0, _sp())
+    assert rel_err(dx.cpu(), _rows(x64.grad)) < 1e-5
+    assert rel_err(dgb[0].cpu(), bn.weight.grad) < 1e-5 and rel_err(dgb[1].cpu(), bn.bias.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# classifier head
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pool_and_fc_consensus(dtype):
+    E = _E()
+    nt, c, h, w, T, K = 16, 1280, 7, 7, 8, 83
+    x = _rand((nt, c, h, w), 50).to(dtype)
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    lin = torch.nn.Linear(c, K).cuda()
+    pooled = E.fused.global_avg_pool(xd)
+    logits = E.fused.fc_consensus(pooled, lin, T)
+    x64 = x.double().requires_grad_(True)
+    w64, b64 = lin.weight.detach().cpu().double().requires_grad_(True), lin.bias.detach().cpu().double().requires_grad_(True)
+    p64 = x64.mean(3).mean(2)
+    l64 = F.linear(p64, w64, b64).view(-1, T, K).mean(1)
+    assert rel_err(pooled.detach().cpu(), p64) < TOL[dtype]
+    assert rel_err(logits.detach().cpu(), l64) < TOL[dtype]
+    g = _rand(tuple(l64.shape), 51)
+    logits.backward(g.cuda())
+    l64.backward(g.double())
+    assert rel_err(xd.grad.cpu(), x64.grad) < TOL[dtype]
+    assert rel_err(lin.weight.grad.cpu(), w64.grad) < max(TOL[dtype], 1e-5)
+    assert rel_err(lin.bias.grad.cpu(), b64.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# loss heads: oracle + reference golden fixtures
+# ---------------------------------------------------------------------------------------------
+def test_losses_match_reference_fixtures():
+    from conftest import GOLDEN
+    E = _E()
+    z = np.load(GOLDEN / "losses.npz")
+    labels = torch.from_numpy(z["sd_labels"]).cuda()
+    logits = [torch.from_numpy(z[f"sd_logits{i}"]).cuda().requires_grad_(True) for i in range(4)]
+    feats = [torch.from_numpy(z[f"sd_feat{i}"]).cuda().requires_grad_(True) for i in range(4)]
+    total, terms = E.losses.sd_loss(logits, feats, labels, 0.1, 1e-6, 3.0)
+    assert abs(total.item() - float(z["sd_total"])) < 2e-5 * abs(float(z["sd_total"]))
+    assert np.allclose(terms.cpu().numpy(), z["sd_terms"], rtol=2e-5)
+    total.backward()
+    for i in range(4):
+        assert rel_err(logits[i].grad.cpu(), torch.from_numpy(z[f"sd_glogits{i}"])) < 1e-5
+        if i > 0:
+            assert rel_err(feats[i].grad.cpu(), torch.from_numpy(z[f"sd_gfeat{i}"])) < 1e-5
+    assert feats[0].grad is None
+
+    lg = torch.from_numpy(z["mt_logits"]).cuda().requires_grad_(True)
+    pred = torch.from_numpy(z["mt_pred"]).cuda().requires_grad_(True)
+    depth = torch.from_numpy(z["mt_depth"].astype(np.float32)).cuda()
+    loss, dl = E.losses.mtmm_loss(lg, labels, pred, depth)
+    assert abs(loss.item() - float(z["mt_loss"])) < 2e-6 and abs(dl.item() - float(z["mt_depth_loss"])) < 1e-6
+    (loss * 2.0).backward()     # exercises the incoming-gradient scaling
+    assert rel_err(lg.grad.cpu() / 2, torch.from_numpy(z["mt_glogits"])) < 1e-5
+    assert rel_err(pred.grad.cpu() / 2, torch.from_numpy(z["mt_gpred"])) < 1e-5
