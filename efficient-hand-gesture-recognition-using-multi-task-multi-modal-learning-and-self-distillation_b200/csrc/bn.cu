@@ -43,44 +43,44 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
   if (invstd_o) invstd_o[c] = invstd;
 }
 
-// sums[c] += sum_m mask*g ; sums[C+c] += sum_m mask*g*raw
+// sums[c] += sum_m mask*g ; sums[C+c] += sum_m mask*g*raw.  block = (bx channel vectors, P rows),
+// persistent grid-stride over rows; a thread keeps its channel vector(s) for its whole life.
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const float* __restrict__ scale,
-                     const float* __restrict__ shift, int relu6, double* __restrict__ sums, long long M, int C,
-                     int iters) {
+                     const float* __restrict__ shift, int relu6, double* __restrict__ sums, long long M, int C) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ float smem[];  // [2C]
   const int nthreads = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   for (int i = tid; i < 2 * C; i += nthreads) smem[i] = 0.f;
   __syncthreads();
-  const int c0 = threadIdx.x * V;
-  float s[V], b[V], a1[V], a2[V];
+  const long long row_stride = static_cast<long long>(gridDim.x) * blockDim.y;
+  for (int cv = threadIdx.x; cv < C / V; cv += blockDim.x) {
+    const int c0 = cv * V;
+    float s[V], b[V], a1[V], a2[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) { a1[i] = a2[i] = 0.f; s[i] = 1.f; b[i] = 1.f; }
-  if (relu6) { load_vec<float, V>(scale + c0, s); load_vec<float, V>(shift + c0, b); }
-  const long long base = static_cast<long long>(blockIdx.x) * (static_cast<long long>(blockDim.y) * iters) + threadIdx.y;
+    for (int i = 0; i < V; ++i) { a1[i] = a2[i] = 0.f; s[i] = 1.f; b[i] = 1.f; }
+    if (relu6) { load_vec<float, V>(scale + c0, s); load_vec<float, V>(shift + c0, b); }
 #pragma unroll 2
-  for (int it = 0; it < iters; ++it) {
-    const long long m = base + static_cast<long long>(it) * blockDim.y;
-    if (m >= M) break;
-    float gv[V], rv[V];
-    load_vec<T, V>(g + m * C + c0, gv);
-    load_vec<T, V>(raw + m * C + c0, rv);
+    for (long long m = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; m < M; m += row_stride) {
+      float gv[V], rv[V];
+      load_vec<T, V>(g + m * C + c0, gv);
+      load_vec<T, V>(raw + m * C + c0, rv);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float gg = gv[i];
-      if (relu6) {
-        const float z = fmaf(rv[i], s[i], b[i]);
-        if (!(z > 0.f && z < 6.f)) gg = 0.f;
+      for (int i = 0; i < V; ++i) {
+        float gg = gv[i];
+        if (relu6) {
+          const float z = fmaf(rv[i], s[i], b[i]);
+          if (!(z > 0.f && z < 6.f)) gg = 0.f;
+        }
+        a1[i] += gg;
+        a2[i] = fmaf(gg, rv[i], a2[i]);
       }
-      a1[i] += gg;
-      a2[i] = fmaf(gg, rv[i], a2[i]);
     }
-  }
 #pragma unroll
-  for (int i = 0; i < V; ++i) { atomicAdd(&smem[c0 + i], a1[i]); atomicAdd(&smem[C + c0 + i], a2[i]); }
+    for (int i = 0; i < V; ++i) { atomicAdd(&smem[c0 + i], a1[i]); atomicAdd(&smem[C + c0 + i], a2[i]); }
+  }
   __syncthreads();
   for (int i = tid; i < 2 * C; i += nthreads) atomicAdd(&sums[i], static_cast<double>(smem[i]));
 }
@@ -156,23 +156,20 @@ extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* s
   const int V = 16 / es;
   if (m < 0 || c <= 0 || (c % V)) return EHGR_E_SHAPE;
   if (!aligned_to(g, 16) || !aligned_to(raw, 16)) return EHGR_E_ALIGN;
-  if (c / V > 256) return EHGR_E_UNSUPPORTED;
   if (m == 0) return EHGR_OK;
   const int cv = c / V;
-  const dim3 block(cv, std::max(1, 256 / cv));
-  long long iters = cdiv(m, 8LL * kNumSMs * block.y);
-  iters = std::max(1LL, std::min(iters, 1024LL));
-  const long long blocks = cdiv(m, static_cast<long long>(block.y) * iters);
+  int bx = cv;
+  while (bx > 256) bx = (bx + 1) / 2;
+  const dim3 block(bx, std::max(1, 256 / bx));
+  const long long blocks = std::max(1LL, std::min(cdiv(m, block.y), 8LL * kNumSMs));
   const size_t smem = static_cast<size_t>(2) * c * sizeof(float);
   cudaStream_t s = as_stream(stream);
   if (dtype == EHGR_F32)
     bn_bwd_reduce_kernel<float><<<static_cast<unsigned>(blocks), block, smem, s>>>(
-        static_cast<const float*>(g), static_cast<const float*>(raw), scale, shift, relu6, sums, m, c,
-        static_cast<int>(iters));
+        static_cast<const float*>(g), static_cast<const float*>(raw), scale, shift, relu6, sums, m, c);
   else
     bn_bwd_reduce_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), block, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(raw), scale, shift, relu6, sums, m,
-        c, static_cast<int>(iters));
+        static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(raw), scale, shift, relu6, sums, m, c);
   return launch_status();
 }
 

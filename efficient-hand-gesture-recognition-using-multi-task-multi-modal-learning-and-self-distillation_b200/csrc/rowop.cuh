@@ -171,6 +171,61 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
   }
 }
 
+// Same operand, for threads that read MANY rows of the SAME channel vector (depthwise taps, reductions,
+// GEMM operand staging): the per-channel coefficients are fetched once into registers by init() and
+// load() only touches the activation tensors.
+template <typename T, int NV>
+struct RowLoader {
+  float s[NV], b[NV], ca[NV], cb[NV], cc[NV];
+  int c0, C;
+
+  __device__ __forceinline__ void init(const RowOp& op, int c0_, int C_) {
+    c0 = c0_;
+    C = C_;
+    if (op.mode == EHGR_ROW_AFFINE || (op.mode == EHGR_ROW_BNBWD && op.relu6)) {
+      load_vec<float, NV>(op.scale + c0, s);
+      load_vec<float, NV>(op.shift + c0, b);
+    }
+    if (op.mode == EHGR_ROW_BNBWD) {
+      load_vec<float, NV>(op.ca + c0, ca);
+      load_vec<float, NV>(op.cb + c0, cb);
+      load_vec<float, NV>(op.cc + c0, cc);
+    }
+  }
+
+  __device__ __forceinline__ void load(const RowOp& op, long long m, float (&v)[NV]) const {
+    const T* in1 = static_cast<const T*>(op.in1);
+    const long long off = m * C + c0;
+    if (op.mode == EHGR_ROW_PLAIN) {
+      load_vec<T, NV>(in1 + off, v);
+    } else if (op.mode == EHGR_ROW_AFFINE) {
+      load_vec<T, NV>(in1 + off, v);
+      if (op.relu6) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(fmaf(v[i], s[i], b[i]), 0.f), 6.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
+      }
+    } else if (op.mode == EHGR_ROW_BNBWD) {
+      float g[NV], r[NV];
+      load_vec<T, NV>(in1 + off, g);
+      load_vec<T, NV>(static_cast<const T*>(op.in2) + off, r);
+      if (op.relu6) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float z = fmaf(r[i], s[i], b[i]);
+          if (!(z > 0.f && z < 6.f)) g[i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[i], g[i], fmaf(cb[i], r[i], cc[i]));
+    } else {
+      load_row<T, NV>(op, m, c0, C, v);  // SHIFT: no per-channel coefficients
+    }
+  }
+};
+
 inline int validate_rowop(const RowOp* op, int es) {
   if (!op || !op->in1) return EHGR_E_NULL;
   if (!aligned_to(op->in1, 16)) return EHGR_E_ALIGN;

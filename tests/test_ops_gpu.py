@@ -131,6 +131,81 @@ def test_pw_gemm_simt(M, K, N, dtype):
 
 
 # ---------------------------------------------------------------------------------------------
+# pointwise GEMM, tcgen05 engine (bf16): every MobileNetV2 (K, N) pair class, ragged M, padded K / N
+# ---------------------------------------------------------------------------------------------
+TC_SHAPES = [(300, 16, 96), (1000, 24, 144), (257, 96, 24), (128, 144, 32), (5000, 32, 192), (130, 192, 64),
+             (700, 64, 384), (260, 384, 96), (400, 576, 160), (140, 160, 960), (98, 960, 320), (392, 320, 1280),
+             (64, 1280, 320), (20000, 32, 16), (1, 16, 16)]
+
+
+@pytest.mark.parametrize("M,K,N", TC_SHAPES)
+def test_pw_gemm_tcgen05_forward(M, K, N):
+    E = _E()
+    f = E.fused
+    dtype = torch.bfloat16
+    a = _rand((M, K), 60).to(dtype)
+    w = _rand((N, K), 61, (2.0 / K) ** 0.5)
+    scale, shift = _rand((K,), 62).abs() + 0.5, _rand((K,), 63)
+    ad, wd = a.cuda(), w.cuda()
+    out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)), wd.data_ptr(), 0, out.data_ptr(), 0,
+          stats.data_ptr(), M, K, N, 1, 2, _sp())
+    torch.cuda.synchronize()
+    aa = torch.clamp(a.double() * scale.double() + shift.double(), 0, 6).to(dtype).double()   # operand is rounded to bf16
+    want = aa @ w.to(dtype).double().t()
+    assert rel_err(out.cpu(), want) < 1e-2
+    assert rel_err(stats[:N].cpu(), want.sum(0)) < 2e-3 and rel_err(stats[N:].cpu(), (want ** 2).sum(0)) < 2e-3
+    # same call on the SIMT engine must agree to bf16 rounding
+    out_s = torch.empty_like(out)
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)), wd.data_ptr(), 0, out_s.data_ptr(), 0, 0,
+          M, K, N, 1, 1, _sp())
+    assert rel_err(out.cpu(), out_s.cpu().double()) < 2e-2
+
+
+@pytest.mark.parametrize("M,K,N", TC_SHAPES)
+def test_pw_gemm_tcgen05_dgrad_form(M, K, N):
+    """out[M,K] = rowop(g)[M,N] @ W[N,K] + addend: the conv weight read as an MN-major B operand."""
+    E = _E()
+    f = E.fused
+    dtype = torch.bfloat16
+    g = _rand((M, N), 64).to(dtype)
+    raw = _rand((M, N), 65).to(dtype)
+    w = _rand((N, K), 66, (2.0 / K) ** 0.5)
+    add = _rand((M, K), 67).to(dtype)
+    ca, cb, cc = _rand((N,), 68), _rand((N,), 69) * 0.1, _rand((N,), 70) * 0.1
+    scale, shift = _rand((N,), 71).abs() + 0.5, _rand((N,), 72)
+    out = torch.full((M, K), float("nan"), dtype=dtype, device="cuda")
+    op = f.op_bnbwd(g.cuda(), raw.cuda(), ca.cuda(), cb.cuda(), cc.cuda(), scale.cuda(), shift.cuda(), True)
+    keep = (g, raw)
+    _call("ehgr_pw_gemm", ctypes.byref(op), w.cuda().data_ptr(), 1, out.data_ptr(), add.cuda().data_ptr(), 0, M, N, K, 1, 2, _sp())
+    torch.cuda.synchronize()
+    z = raw.double() * scale.double() + shift.double()
+    mask = ((z > 0) & (z < 6)).double()
+    dy = (ca.double() * mask * g.double() + cb.double() * raw.double() + cc.double()).to(dtype).double()
+    want = dy @ w.to(dtype).double() + add.double()
+    assert rel_err(out.cpu(), want) < 1e-2
+
+
+def test_pw_gemm_tcgen05_shift_prologue_full_size():
+    """BASELINE config #2 size of the largest shifted layer (24->144 at 56x56, 256 frames): the shift
+    fused into the GEMM A-load equals shift-then-GEMM."""
+    E = _E()
+    f = E.fused
+    nt, hw, K, N, T = 256, 56 * 56, 24, 144, 8
+    M = nt * hw
+    gcuda = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((M, K), device="cuda", generator=gcuda).to(torch.bfloat16)
+    w = torch.randn((N, K), device="cuda", generator=gcuda) * 0.3
+    out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_shift(x, T, K // 8, hw, 1)), w.data_ptr(), 0, out.data_ptr(), 0, 0, M, K, N, 1, 2, _sp())
+    xs = torch.empty_like(x)
+    _call("ehgr_row_apply", ctypes.byref(f.op_shift(x, T, K // 8, hw, 1)), 0, xs.data_ptr(), M, K, 1, _sp())
+    want = xs.float() @ w.to(torch.bfloat16).float().t()
+    assert rel_err(out.float().cpu(), want.cpu()) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------
 # depthwise 3x3
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("nt,h,w,c,stride", [(3, 9, 7, 32, 1), (2, 8, 8, 96, 2), (2, 7, 7, 960, 1), (2, 14, 14, 144, 2), (1, 1, 1, 16, 1)])
