@@ -89,7 +89,8 @@ def test_row_apply_modes(dtype):
     z = raw.double() * scale.double() + shift.double()
     mask = ((z > 0) & (z < 6)).double()
     want = ca.double() * mask * xr + cb.double() * raw.double() + cc.double()
-    got = run(f.op_bnbwd(xd, raw.cuda(), ca.cuda(), cb.cuda(), cc.cuda(), sd_, sh_, True))
+    dev = [t.cuda() for t in (raw, ca, cb, cc)]
+    got = run(f.op_bnbwd(xd, *dev, sd_, sh_, True))
     assert rel_err(got, want) < TOL[dtype]
 
 
@@ -106,11 +107,12 @@ def test_pw_gemm_simt(M, K, N, dtype):
     add = _rand((M, N), 12).to(dtype)
     scale, shift = _rand((K,), 13).abs() + 0.5, _rand((K,), 14)
     ad, wd, addd = a.cuda(), w.cuda(), add.cuda()
+    sc_d, sh_d = scale.cuda(), shift.cuda()      # device tensors stay referenced until the kernels have run
     code = E._lib.dtype_code(ad)
     # forward with lazy BN+ReLU6 prologue, stats
     out = torch.empty((M, N), dtype=dtype, device="cuda")
     stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
-    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)), wd.data_ptr(), 0, out.data_ptr(), 0,
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, sc_d, sh_d, True)), wd.data_ptr(), 0, out.data_ptr(), 0,
           stats.data_ptr(), M, K, N, code, 1, _sp())
     aa = torch.clamp(a.double() * scale.double() + shift.double(), 0, 6)
     want = aa @ w.double().t()
@@ -120,12 +122,13 @@ def test_pw_gemm_simt(M, K, N, dtype):
     g = _rand((M, N), 15).to(dtype)
     out2 = torch.empty((M, K), dtype=dtype, device="cuda")
     add2 = _rand((M, K), 16).to(dtype)
-    _call("ehgr_pw_gemm", ctypes.byref(f.op_plain(g.cuda())), wd.data_ptr(), 1, out2.data_ptr(), add2.cuda().data_ptr(), 0,
+    gd, add2d = g.cuda(), add2.cuda()
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_plain(gd)), wd.data_ptr(), 1, out2.data_ptr(), add2d.data_ptr(), 0,
           M, N, K, code, 1, _sp())
     assert rel_err(out2.cpu(), g.double() @ w.double() + add2.double()) < TOL[dtype]
     # wgrad: dW[N,K] = g^T a'
     dw = torch.zeros((N, K), dtype=torch.float32, device="cuda")
-    _call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(g.cuda())), ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)),
+    _call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(gd)), ctypes.byref(f.op_affine(ad, sc_d, sh_d, True)),
           dw.data_ptr(), M, K, N, code, 1, _sp())
     assert rel_err(dw.cpu(), g.double().t() @ aa) < max(TOL[dtype], 2e-5)
 
@@ -146,10 +149,10 @@ def test_pw_gemm_tcgen05_forward(M, K, N):
     a = _rand((M, K), 60).to(dtype)
     w = _rand((N, K), 61, (2.0 / K) ** 0.5)
     scale, shift = _rand((K,), 62).abs() + 0.5, _rand((K,), 63)
-    ad, wd = a.cuda(), w.cuda()
+    ad, wd, sc_d, sh_d = a.cuda(), w.cuda(), scale.cuda(), shift.cuda()
     out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
     stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
-    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)), wd.data_ptr(), 0, out.data_ptr(), 0,
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, sc_d, sh_d, True)), wd.data_ptr(), 0, out.data_ptr(), 0,
           stats.data_ptr(), M, K, N, 1, 2, _sp())
     torch.cuda.synchronize()
     aa = torch.clamp(a.double() * scale.double() + shift.double(), 0, 6).to(dtype).double()   # operand is rounded to bf16
@@ -158,7 +161,7 @@ def test_pw_gemm_tcgen05_forward(M, K, N):
     assert rel_err(stats[:N].cpu(), want.sum(0)) < 2e-3 and rel_err(stats[N:].cpu(), (want ** 2).sum(0)) < 2e-3
     # same call on the SIMT engine must agree to bf16 rounding
     out_s = torch.empty_like(out)
-    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, scale.cuda(), shift.cuda(), True)), wd.data_ptr(), 0, out_s.data_ptr(), 0, 0,
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, sc_d, sh_d, True)), wd.data_ptr(), 0, out_s.data_ptr(), 0, 0,
           M, K, N, 1, 1, _sp())
     assert rel_err(out.cpu(), out_s.cpu().double()) < 2e-2
 
@@ -176,9 +179,9 @@ def test_pw_gemm_tcgen05_dgrad_form(M, K, N):
     ca, cb, cc = _rand((N,), 68), _rand((N,), 69) * 0.1, _rand((N,), 70) * 0.1
     scale, shift = _rand((N,), 71).abs() + 0.5, _rand((N,), 72)
     out = torch.full((M, K), float("nan"), dtype=dtype, device="cuda")
-    op = f.op_bnbwd(g.cuda(), raw.cuda(), ca.cuda(), cb.cuda(), cc.cuda(), scale.cuda(), shift.cuda(), True)
-    keep = (g, raw)
-    _call("ehgr_pw_gemm", ctypes.byref(op), w.cuda().data_ptr(), 1, out.data_ptr(), add.cuda().data_ptr(), 0, M, N, K, 1, 2, _sp())
+    dev = [t.cuda() for t in (g, raw, ca, cb, cc, scale, shift, w, add)]
+    op = f.op_bnbwd(*dev[:7], True)
+    _call("ehgr_pw_gemm", ctypes.byref(op), dev[7].data_ptr(), 1, out.data_ptr(), dev[8].data_ptr(), 0, M, N, K, 1, 2, _sp())
     torch.cuda.synchronize()
     z = raw.double() * scale.double() + shift.double()
     mask = ((z > 0) & (z < 6)).double()
@@ -222,10 +225,11 @@ def test_dw_fwd_bwd(nt, h, w, c, stride, dtype):
     w64 = wt.double().requires_grad_(True)
     y64 = F.conv2d(a64, w64, stride=stride, padding=1, groups=c)
     ho, wo = y64.shape[2:]
-    a_op = f.op_affine(xr, scale.cuda(), shift.cuda(), True)
+    sc_d, sh_d, wt_d = scale.cuda(), shift.cuda(), wt.cuda()
+    a_op = f.op_affine(xr, sc_d, sh_d, True)
     out = torch.empty((nt * ho * wo, c), dtype=dtype, device="cuda")
     stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
-    _call("ehgr_dw_fwd", ctypes.byref(a_op), wt.cuda().data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, c, stride, code, _sp())
+    _call("ehgr_dw_fwd", ctypes.byref(a_op), wt_d.data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, c, stride, code, _sp())
     assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
     assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < 1e-4
     assert rel_err(stats[c:].cpu(), (y64 ** 2).sum((0, 2, 3))) < 1e-4
@@ -233,7 +237,7 @@ def test_dw_fwd_bwd(nt, h, w, c, stride, dtype):
     y64.backward(g.double())
     gr = _rows(g).contiguous().cuda()
     da = torch.empty((nt * h * w, c), dtype=dtype, device="cuda")
-    _call("ehgr_dw_dgrad", ctypes.byref(f.op_plain(gr)), wt.cuda().data_ptr(), da.data_ptr(), nt, h, w, c, stride, code, _sp())
+    _call("ehgr_dw_dgrad", ctypes.byref(f.op_plain(gr)), wt_d.data_ptr(), da.data_ptr(), nt, h, w, c, stride, code, _sp())
     assert rel_err(da.cpu(), _rows(a64.grad)) < TOL[dtype]
     dw = torch.zeros((c, 9), dtype=torch.float32, device="cuda")
     _call("ehgr_dw_wgrad", ctypes.byref(f.op_plain(gr)), ctypes.byref(a_op), dw.data_ptr(), nt, h, w, c, stride, code, _sp())
@@ -257,15 +261,16 @@ def test_stem(dtype, hw):
     ho, wo = y64.shape[2:]
     out = torch.empty((nt * ho * wo, cout), dtype=dtype, device="cuda")
     stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
-    xd = x.cuda()
+    xd, wt_d = x.cuda(), wt.cuda()
     code = E._lib.dtype_code(out)
-    _call("ehgr_stem_fwd", xd.data_ptr(), wt.cuda().data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, cout, 0, code, _sp())
+    _call("ehgr_stem_fwd", xd.data_ptr(), wt_d.data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, cout, 0, code, _sp())
     assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
     assert rel_err(stats[:cout].cpu(), y64.sum((0, 2, 3))) < 1e-4
     g = _rand(tuple(y64.shape), 32).to(dtype)
     y64.backward(g.double())
     dw = torch.zeros((cout, 27), dtype=torch.float32, device="cuda")
-    _call("ehgr_stem_wgrad", ctypes.byref(f.op_plain(_rows(g).contiguous().cuda())), xd.data_ptr(), dw.data_ptr(), nt, h, w, cout, 0,
+    g_d = _rows(g).contiguous().cuda()
+    _call("ehgr_stem_wgrad", ctypes.byref(f.op_plain(g_d)), xd.data_ptr(), dw.data_ptr(), nt, h, w, cout, 0,
           code, _sp())
     assert rel_err(dw.cpu(), w64.grad.view(cout, 27)) < max(TOL[dtype], 2e-5)
 
