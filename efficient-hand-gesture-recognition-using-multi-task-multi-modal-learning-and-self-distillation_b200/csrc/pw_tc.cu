@@ -31,8 +31,10 @@ namespace tc {
 
 constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int BK = 64;             // reduction elements per ring stage
-constexpr int kStages = 3;
-constexpr int kThreads = 288;      // 4 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int kStages = 4;
+constexpr int kProducerGroups = 2;  // x 4 warps each; groups take ring stages round-robin
+constexpr int kProducerWarps = 4 * kProducerGroups;
+constexpr int kThreads = (kProducerWarps + 1 + 4) * 32;   // producers + 1 MMA warp + 4 epilogue warps
 constexpr int kABytes = BM * BK * 2;                 // 16 KB
 constexpr uint32_t kSpinLimit = 1u << 28;            // bounded waits: trap instead of hanging the GPU
 
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
     }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(p.tmem_cols));
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(p.tmem_cols));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -203,62 +205,112 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
   const int k_stages = (p.K + BK - 1) / BK;
   const int Kp = (p.K + 15) & ~15;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ===================== PRODUCERS =====================
-    const int tid = threadIdx.x;  // 0..127
+    // kProducerGroups groups of 128 threads take ring stages round-robin: each group has its own
+    // registers, so that many stages' global loads are in flight per SM.  Within a stage a thread
+    // first FETCHES all its vectors (loads only), then converts and stores them.
+    const int tid = threadIdx.x & 127;
+    const int group = warp >> 2;
+    const int r = tid & 7, t8 = tid >> 3;          // row inside an 8-row core matrix, 16 vector slots
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const long long m0 = static_cast<long long>(tile / p.n_chunks) * BM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
+        if (static_cast<int>(it % kProducerGroups) != group) continue;
         const int s = it % kStages;
         const uint32_t round = it / kStages;
-        mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1);
         uint8_t* a_dst = smem + s * stage_bytes;
         uint8_t* b_dst = a_dst + kABytes;
         const int k_base = ks * BK;
         const int kvalid = min(BK, Kp - k_base);     // multiple of 16
-        const int kv = kvalid >> 3;                    // 16-byte vectors per row in this stage
-        // ---- A: [128 rows][kvalid]  ->  K-major core matrices: (row/8)*1024 + k8*128 + (row%8)*16
-        for (int v = tid; v < BM * kv; v += 128) {
-          const int r = v & 7, k8 = (v >> 3) % kv, rg = (v >> 3) / kv;
-          const int row = rg * 8 + r, k = k_base + k8 * 8;
-          const long long m = m0 + row;
-          float f[8];
+        const int kv = kvalid >> 3;                    // 16-byte vectors per row in this stage: 2, 4, 6 or 8
+        bool waited = false;
+        // ---- A: [128 rows][kvalid] -> K-major core matrices: (row/8)*1024 + k8*128 + (row%8)*16
+        if ((16 % kv) == 0) {
+          // thread owns channel vector k8 and kv row groups (rg0, rg0 + 16/kv, ...)
+          const int k8 = t8 % kv, rg0 = t8 / kv, rg_step = 16 / kv;
+          const int k = k_base + k8 * 8;
+          RowLoader<__nv_bfloat16, 8> ld;
+          if (k < p.K) ld.init(p.a, k, p.K);
+#pragma unroll 1
+          for (int j0 = 0; j0 < kv; j0 += 4) {
+            RowLoader<__nv_bfloat16, 8>::Raw raw[4];
+            bool live[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = 0.f;
-          if (m < p.M && k < p.K) load_row<__nv_bfloat16, 8>(p.a, m, k, p.K, f);
-          *reinterpret_cast<uint4*>(a_dst + rg * 1024 + k8 * 128 + r * 16) = pack8(f);
-        }
-        // ---- B
-        if (!p.w_is_kn) {
-          // B[k][n] = w[n*K + k]: K-major, same core-matrix layout with n in place of row
-          for (int v = tid; v < p.BN * kv; v += 128) {
-            const int r = v & 7, k8 = (v >> 3) % kv, ng = (v >> 3) / kv;
-            const int n = n0 + ng * 8 + r, k = k_base + k8 * 8;
-            float f[8];
+            for (int j = 0; j < 4; ++j) {
+              const long long m = m0 + (rg0 + (j0 + j) * rg_step) * 8 + r;
+              live[j] = (j0 + j) < kv && m < p.M && k < p.K;
+              if (live[j]) raw[j] = ld.fetch(p.a, m);
+            }
+            if (!waited) { mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1); waited = true; }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = 0.f;
-            if (n < p.N && k < p.K) load_vec<float, 8>(p.w + static_cast<size_t>(n) * p.K + k, f);
-            *reinterpret_cast<uint4*>(b_dst + ng * 1024 + k8 * 128 + r * 16) = pack8(f);
+            for (int j = 0; j < 4; ++j) {
+              if ((j0 + j) < kv) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = 0.f;
+                if (live[j]) ld.finish(p.a, raw[j], f);
+                *reinterpret_cast<uint4*>(a_dst + (rg0 + (j0 + j) * rg_step) * 1024 + k8 * 128 + r * 16) = pack8(f);
+              }
+            }
           }
         } else {
-          // B[k][n] = w[k*N + n]: MN-major core matrices: (n/8)*1024 + (k/8)*128 + (k%8)*16, 8 n per vector
-          const int ngroups = p.BN >> 3;
-          for (int v = tid; v < ngroups * kvalid; v += 128) {
-            const int kr = v & 7, kg = (v >> 3) % kv, ng = (v >> 3) / kv;
-            const int k = k_base + kg * 8 + kr, n = n0 + ng * 8;
+          mbar_wait(bar_empty + 8 * s, (round & 1) ^ 1);
+          waited = true;
+          for (int v = tid; v < BM * kv; v += 128) {
+            const int k8 = (v >> 3) % kv, rg = (v >> 3) / kv;
+            const int k = k_base + k8 * 8;
+            const long long m = m0 + rg * 8 + r;
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = 0.f;
-            if (k < p.K && n < p.N) load_vec<float, 8>(p.w + static_cast<size_t>(k) * p.N + n, f);
-            *reinterpret_cast<uint4*>(b_dst + ng * 1024 + kg * 128 + kr * 16) = pack8(f);
+            if (m < p.M && k < p.K) load_row<__nv_bfloat16, 8>(p.a, m, k, p.K, f);
+            *reinterpret_cast<uint4*>(a_dst + rg * 1024 + k8 * 128 + r * 16) = pack8(f);
+          }
+        }
+        // ---- B (fp32 weights, L2 resident): batches of 4 vectors = 8 x 16-byte loads in flight
+        const int nvec = (p.BN >> 3) * kvalid;       // (BN/8 groups) x (kv vectors) x 8
+#pragma unroll 1
+        for (int v0 = tid; v0 < nvec; v0 += 4 * 128) {
+          float4 lo[4], hi[4];
+          int dst[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int v = v0 + j * 128;
+            lo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hi[j] = lo[j];
+            dst[j] = -1;
+            if (v < nvec) {
+              const int x = v & 7, kg = (v >> 3) % kv, ng = (v >> 3) / kv;
+              dst[j] = ng * 1024 + kg * 128 + x * 16;
+              const float* src = nullptr;
+              if (!p.w_is_kn) {   // B[k][n] = w[n*K + k]: K-major, x = n % 8, vector = 8 consecutive k
+                const int n = n0 + ng * 8 + x, k = k_base + kg * 8;
+                if (n < p.N && k < p.K) src = p.w + static_cast<size_t>(n) * p.K + k;
+              } else {            // B[k][n] = w[k*N + n]: MN-major, x = k % 8, vector = 8 consecutive n
+                const int k = k_base + kg * 8 + x, n = n0 + ng * 8;
+                if (k < p.K && n < p.N) src = p.w + static_cast<size_t>(k) * p.N + n;
+              }
+              if (src) {
+                lo[j] = __ldg(reinterpret_cast<const float4*>(src));
+                hi[j] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (dst[j] >= 0) {
+              const float f[8] = {lo[j].x, lo[j].y, lo[j].z, lo[j].w, hi[j].x, hi[j].y, hi[j].z, hi[j].w};
+              *reinterpret_cast<uint4*>(b_dst + dst[j]) = pack8(f);
+            }
           }
         }
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kProducerWarps) {
     // ===================== MMA ISSUER =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, p.BN, 0, p.w_is_kn ? 1 : 0);
@@ -353,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 4) {
+  if (warp == kProducerWarps) {
     __syncwarp();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
@@ -366,6 +418,179 @@ static int pick_bn(int N) {
   int bn = (Np / chunks + 15) & ~15;
   while (bn * chunks < Np) bn += 16;
   return bn;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight gradient:  dw[N,K] += sum_m dy[m,n] * a[m,k]
+//   D[128 n x BKc k] (TMEM, fp32) accumulates over ALL row tiles a CTA owns: no per-tile epilogue.
+//   Both operands are MN-major (the reduction index is the row m): a thread's 16-byte vector of 8
+//   consecutive channels of row m lands at (m%8)*16 + (m/8)*128 + (channel/8)*2048 — plain vector
+//   stores, no transposition anywhere.  grid = (n_tiles*k_tiles) x splits; each split strides over
+//   the row tiles; the epilogue adds the partial tile to dw with fp32 atomics.
+//   5 warps: 0-3 produce (and run the epilogue at the end), 4 issues the MMAs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWgStages = 2;
+constexpr int kWgThreads = 288;   // 2 producer groups x 4 warps + 1 MMA warp
+constexpr int kWgDyBytes = 128 * 128 * 2;   // [128 n][128 m] bf16
+
+struct WgradArgs {
+  RowOp dy, a;
+  float* dw;
+  long long M;
+  int K, N;
+  int BKc;        // k columns per output tile (multiple of 16, <= 256)
+  int k_tiles, n_tiles, m_tiles, splits;
+  int tmem_cols;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int a_bytes = p.BKc * 128 * 2;
+  const int stage_bytes = kWgDyBytes + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWgStages), bar_done = smem_u32(bars + 2 * kWgStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(bar_full + 8 * s, 128);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  // zero the operand ring once: padded channel groups are never written again
+  for (int i = threadIdx.x; i < kWgStages * stage_bytes / 16; i += kWgThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(p.tmem_cols));
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles = p.n_tiles * p.k_tiles;
+  const int tile = blockIdx.x % tiles, split = blockIdx.x / tiles;
+  const int n0 = (tile / p.k_tiles) * 128, k0 = (tile % p.k_tiles) * p.BKc;
+  const int n_valid = min(128, p.N - n0), k_valid = min(p.BKc, p.K - k0);   // multiples of 8
+  const int ng = n_valid >> 3, kg = k_valid >> 3;
+  int my_tiles = 0;
+  for (int mt = split; mt < p.m_tiles; mt += p.splits) ++my_tiles;
+
+  if (warp < 8) {
+    // two producer groups (128 threads each) alternate ring stages; per stage a thread fetches its
+    // vectors in batches of four (loads only), then applies the row operand and stores.
+    const int tid = threadIdx.x & 127, group = warp >> 2;
+    const int r = tid & 7;
+    using Ld = RowLoader<__nv_bfloat16, 8>;
+    uint32_t it = 0;
+    for (int mt = split; mt < p.m_tiles; mt += p.splits, ++it) {
+      if (static_cast<int>(it & 1) != group) continue;
+      const int s = it % kWgStages;
+      uint8_t* dy_dst = smem + s * stage_bytes;
+      uint8_t* a_dst = dy_dst + kWgDyBytes;
+      const long long m0 = static_cast<long long>(mt) * 128;
+      bool waited = false;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const RowOp& op = pass ? p.a : p.dy;
+        const int groups = pass ? kg : ng, c_base = pass ? k0 : n0, C = pass ? p.K : p.N;
+        uint8_t* dst = pass ? a_dst : dy_dst;
+#pragma unroll 1
+        for (int v0 = tid; v0 < 128 * groups; v0 += 4 * 128) {
+          Ld::Raw raw[4];
+          bool live[4];
+          int off[4], c0[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int v = v0 + j * 128;
+            off[j] = -1;
+            live[j] = false;
+            if (v < 128 * groups) {
+              const int g = (v >> 3) % groups, mg = (v >> 3) / groups;
+              const long long m = m0 + mg * 8 + r;
+              off[j] = g * 2048 + mg * 128 + r * 16;
+              c0[j] = c_base + g * 8;
+              live[j] = m < p.M;
+              if (live[j]) {
+                Ld ld;
+                ld.c0 = c0[j];
+                ld.C = C;
+                raw[j] = ld.fetch(op, m);
+              }
+            }
+          }
+          if (!waited) { mbar_wait(bar_empty + 8 * s, ((it / kWgStages) & 1) ^ 1); waited = true; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (off[j] >= 0) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = 0.f;
+              if (live[j]) {
+                Ld ld;
+                ld.init(op, c0[j], C);
+                ld.finish(op, raw[j], f);
+              }
+              *reinterpret_cast<uint4*>(dst + off[j]) = pack8(f);
+            }
+          }
+        }
+      }
+      if (!waited) mbar_wait(bar_empty + 8 * s, ((it / kWgStages) & 1) ^ 1);
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * s);
+    }
+  }
+  if (warp < 4) {
+    // ---- epilogue (same warps): TMEM -> fp32 atomics into dw[N,K]
+    if (my_tiles > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int n = n0 + q * 32 + lane;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int cc = 0; cc * 16 < k_valid; ++cc) {
+        float v[16];
+        tmem_ld16(t_base + cc * 16, v);
+        if (n < p.N) {
+          float* dst = p.dw + static_cast<size_t>(n) * p.K + k0 + cc * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (cc * 16 + i < k_valid) atomicAdd(dst + i, v[i]);
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == 8 && lane == 0 && my_tiles > 0) {
+    const uint32_t idesc = make_idesc(128, p.BKc, 1, 1);     // both operands MN-major
+    uint32_t it = 0;
+    for (int mt = split; mt < p.m_tiles; mt += p.splits, ++it) {
+      const int s = it % kWgStages;
+      mbar_wait(bar_full + 8 * s, (it / kWgStages) & 1);
+      tc_fence_after();
+      const uint32_t dy_addr = smem_base + s * stage_bytes;
+      const uint32_t a_addr = dy_addr + kWgDyBytes;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        // 16 rows of m = two 8-row core matrices = 256 bytes; LBO (k groups) = 128, SBO (channel groups) = 2048
+        const uint64_t da = make_desc(dy_addr + kk * 256, 128, 2048);
+        const uint64_t db = make_desc(a_addr + kk * 256, 128, 2048);
+        umma_bf16(tmem_base, da, db, idesc, (it | kk) ? 1u : 0u);
+      }
+      umma_commit(bar_empty + 8 * s);
+    }
+    umma_commit(bar_done);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
 }
 
 }  // namespace tc
@@ -402,7 +627,31 @@ int pw_gemm_tc(const RowOp& a, const float* w, int w_is_kn, void* out, const voi
   return launch_status();
 }
 
-bool pw_wgrad_tc_supported(const RowOp&, const RowOp&, long long, int, int, int) { return false; }
-int pw_wgrad_tc(const RowOp&, const RowOp&, float*, long long, int, int, cudaStream_t) { return EHGR_E_UNSUPPORTED; }
+bool pw_wgrad_tc_supported(const RowOp& dy, const RowOp& a, long long M, int K, int N, int dtype) {
+  (void)dy; (void)a;
+  if (dtype != EHGR_BF16) return false;
+  if (K % 8 || N % 8 || K < 8 || N < 8) return false;
+  if (M < 1 || M / 128 > 0x3fffffff) return false;
+  return true;
+}
+
+int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, int N, cudaStream_t s) {
+  tc::WgradArgs p;
+  p.dy = dy; p.a = a; p.dw = dw;
+  p.M = M; p.K = K; p.N = N;
+  p.BKc = tc::pick_bn(K);
+  p.k_tiles = (K + p.BKc - 1) / p.BKc;
+  p.n_tiles = (N + 127) / 128;
+  p.m_tiles = static_cast<int>(cdiv(M, 128));
+  const int tiles = p.n_tiles * p.k_tiles;
+  p.splits = std::max(1, std::min(p.m_tiles, kNumSMs / tiles));
+  int cols = 32;
+  while (cols < p.BKc) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = static_cast<size_t>(tc::kWgStages) * (tc::kWgDyBytes + p.BKc * 256) + 128;
+  cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  tc::pw_wgrad_tc_kernel<<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
+  return launch_status();
+}
 
 }  // namespace ehgr

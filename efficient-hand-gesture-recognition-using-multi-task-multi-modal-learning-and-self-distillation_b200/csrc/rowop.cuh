@@ -174,9 +174,11 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
 // Same operand, for threads that read MANY rows of the SAME channel vector (depthwise taps, reductions,
 // GEMM operand staging): the per-channel coefficients are fetched once into registers by init() and
 // load() only touches the activation tensors.
-template <typename T, int NV>
+// kTwo = false compiles the two-tensor BNBWD mode out (fewer registers) for kernels whose operand is
+// known to be PLAIN / AFFINE / SHIFT; the host checks the mode before choosing such an instantiation.
+template <typename T, int NV, bool kTwo = true>
 struct RowLoader {
-  float s[NV], b[NV], ca[NV], cb[NV], cc[NV];
+  float s[NV], b[NV], ca[kTwo ? NV : 1], cb[kTwo ? NV : 1], cc[kTwo ? NV : 1];
   int c0, C;
 
   __device__ __forceinline__ void init(const RowOp& op, int c0_, int C_) {
@@ -186,10 +188,12 @@ struct RowLoader {
       load_vec<float, NV>(op.scale + c0, s);
       load_vec<float, NV>(op.shift + c0, b);
     }
-    if (op.mode == EHGR_ROW_BNBWD) {
-      load_vec<float, NV>(op.ca + c0, ca);
-      load_vec<float, NV>(op.cb + c0, cb);
-      load_vec<float, NV>(op.cc + c0, cc);
+    if constexpr (kTwo) {
+      if (op.mode == EHGR_ROW_BNBWD) {
+        load_vec<float, NV>(op.ca + c0, ca);
+        load_vec<float, NV>(op.cb + c0, cb);
+        load_vec<float, NV>(op.cc + c0, cc);
+      }
     }
   }
 
@@ -207,7 +211,7 @@ struct RowLoader {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
       }
-    } else if (op.mode == EHGR_ROW_BNBWD) {
+    } else if (kTwo && op.mode == EHGR_ROW_BNBWD) {
       float g[NV], r[NV];
       load_vec<T, NV>(in1 + off, g);
       load_vec<T, NV>(static_cast<const T*>(op.in2) + off, r);
@@ -219,9 +223,76 @@ struct RowLoader {
         }
       }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[i], g[i], fmaf(cb[i], r[i], cc[i]));
+      for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[kTwo ? i : 0], g[i], fmaf(cb[kTwo ? i : 0], r[i], cc[kTwo ? i : 0]));
     } else {
       load_row<T, NV>(op, m, c0, C, v);  // SHIFT: no per-channel coefficients
+    }
+  }
+
+  // Split form for memory-level parallelism: fetch() only ISSUES the 16-byte loads of a row (no
+  // instruction depends on the data), finish() does the arithmetic.  Kernels fetch a batch of rows
+  // (all nine depthwise taps, several GEMM operand vectors) before finishing the first one, so a thread
+  // has many loads in flight instead of one round trip per row.  Requires NV == VecOf<T>::N.
+  struct Raw { uint4 a; uint4 b[kTwo ? 1 : 0 + 1]; };
+
+  __device__ __forceinline__ Raw fetch(const RowOp& op, long long m) const {
+    static_assert(NV == VecOf<T>::N, "fetch/finish work on full 16-byte vectors");
+    Raw r;
+    r.a = make_uint4(0, 0, 0, 0);
+    r.b[0] = r.a;
+    const long long off = m * C + c0;
+    const T* in1 = static_cast<const T*>(op.in1);
+    if (op.mode == EHGR_ROW_SHIFT) {
+      const long long frame = m / op.hw;
+      const int t = static_cast<int>(frame % op.n_segment);
+      const int dir = op.shift_dir < 0 ? -1 : 1;
+      const long long step = static_cast<long long>(dir) * op.hw * C;
+      const int fold = op.fold;
+      auto cls_of = [fold](int c) { return c < fold ? 0 : (c < 2 * fold ? 1 : 2); };
+      const int cl = cls_of(c0), ch = cls_of(c0 + NV - 1);
+      if (cl == ch) {
+        const bool has_next = dir > 0 ? (t < op.n_segment - 1) : (t > 0);
+        const bool has_prev = dir > 0 ? (t > 0) : (t < op.n_segment - 1);
+        const bool ok = cl == 2 || (cl == 0 ? has_next : has_prev);
+        if (ok) r.a = *reinterpret_cast<const uint4*>(in1 + off + (cl == 0 ? step : cl == 1 ? -step : 0));
+      } else {  // straddles a fold boundary (C = 24, 32, 96, 160: one vector per row): assemble now
+        float v[NV];
+        load_row<T, NV>(op, m, c0, C, v);
+        T tmp[NV];
+        store_vec<T, NV>(tmp, v);
+        r.a = *reinterpret_cast<const uint4*>(tmp);
+      }
+    } else {
+      r.a = *reinterpret_cast<const uint4*>(in1 + off);
+      if constexpr (kTwo) {
+        if (op.mode == EHGR_ROW_BNBWD) r.b[0] = *reinterpret_cast<const uint4*>(static_cast<const T*>(op.in2) + off);
+      }
+    }
+    return r;
+  }
+
+  __device__ __forceinline__ void finish(const RowOp& op, const Raw& r, float (&v)[NV]) const {
+    load_vec<T, NV>(reinterpret_cast<const T*>(&r.a), v);
+    if (op.mode == EHGR_ROW_AFFINE) {
+      if (op.relu6) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(fmaf(v[i], s[i], b[i]), 0.f), 6.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
+      }
+    } else if (kTwo && op.mode == EHGR_ROW_BNBWD) {
+      float raw[NV];
+      load_vec<T, NV>(reinterpret_cast<const T*>(&r.b[0]), raw);
+      if (op.relu6) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float z = fmaf(raw[i], s[i], b[i]);
+          if (!(z > 0.f && z < 6.f)) v[i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[kTwo ? i : 0], v[i], fmaf(cb[kTwo ? i : 0], raw[i], cc[kTwo ? i : 0]));
     }
   }
 };

@@ -190,6 +190,35 @@ def test_pw_gemm_tcgen05_dgrad_form(M, K, N):
     assert rel_err(out.cpu(), want) < 1e-2
 
 
+@pytest.mark.parametrize("M,K,N", TC_SHAPES)
+def test_pw_wgrad_tcgen05(M, K, N):
+    """dW[N,K] = rowop(dy)^T rowop(a): both operands MN-major, accumulation over row tiles in TMEM."""
+    E = _E()
+    f = E.fused
+    dtype = torch.bfloat16
+    g = _rand((M, N), 80).to(dtype)
+    raw = _rand((M, N), 81).to(dtype)
+    a = _rand((M, K), 82).to(dtype)
+    ca, cb, cc = _rand((N,), 83), _rand((N,), 84) * 0.1, _rand((N,), 85) * 0.1
+    s_o, b_o = _rand((N,), 86).abs() + 0.5, _rand((N,), 87)
+    s_a, b_a = _rand((K,), 88).abs() + 0.5, _rand((K,), 89)
+    dev = [t.cuda() for t in (g, raw, ca, cb, cc, s_o, b_o, a, s_a, b_a)]
+    dy_op = f.op_bnbwd(*dev[:7], True)
+    a_op = f.op_affine(dev[7], dev[8], dev[9], True)
+    dw = torch.zeros((N, K), dtype=torch.float32, device="cuda")
+    _call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), dw.data_ptr(), M, K, N, 1, 2, _sp())
+    torch.cuda.synchronize()
+    z = raw.double() * s_o.double() + b_o.double()
+    mask = ((z > 0) & (z < 6)).double()
+    dy = (ca.double() * mask * g.double() + cb.double() * raw.double() + cc.double()).to(dtype).double()
+    aa = torch.clamp(a.double() * s_a.double() + b_a.double(), 0, 6).to(dtype).double()
+    want = dy.t() @ aa
+    assert rel_err(dw.cpu(), want) < 5e-3
+    dw_s = torch.zeros_like(dw)
+    _call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), dw_s.data_ptr(), M, K, N, 1, 1, _sp())
+    assert rel_err(dw.cpu(), dw_s.cpu().double()) < 2e-2
+
+
 def test_pw_gemm_tcgen05_shift_prologue_full_size():
     """BASELINE config #2 size of the largest shifted layer (24->144 at 56x56, 256 frames): the shift
     fused into the GEMM A-load equals shift-then-GEMM."""
