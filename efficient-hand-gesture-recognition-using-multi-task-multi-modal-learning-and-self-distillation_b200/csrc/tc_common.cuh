@@ -1,0 +1,138 @@
+// tc_common.cuh — tcgen05 / TMEM / mbarrier plumbing shared by the tensor-core kernels (sm_100a).
+// Inline PTX only; descriptor encodings follow cute::UMMA::SmemDescriptor / InstrDescriptor.
+#pragma once
+#include "rowop.cuh"
+
+namespace ehgr {
+namespace tc {
+
+constexpr uint32_t kSpinLimit = 1u << 28;            // bounded waits: trap instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start address, leading
+// byte offset (stride between core matrices along K), stride byte offset (stride between core
+// matrices along M/N), all in 16-byte units; version 1 at bit 46.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, major-ness, N>>3, M>>4.
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                  // c_format = F32
+  d |= 1u << 7;                                  // a_format = BF16
+  d |= 1u << 10;                                 // b_format = BF16
+  d |= static_cast<uint32_t>(a_mn_major) << 15;
+  d |= static_cast<uint32_t>(b_mn_major) << 16;
+  d |= static_cast<uint32_t>(n >> 3) << 17;
+  d |= static_cast<uint32_t>(m >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// transpose-reduce 16 columns held by the 32 lanes of a warp: returns, in every lane, the sum over
+// the 32 lanes of column ((lane >> 1) & 15).
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float a[8];
+  const bool u4 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = u4 ? v[8 + i] : v[i], send = u4 ? v[i] : v[8 + i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float b[4];
+  const bool u3 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = u3 ? a[4 + i] : a[i], send = u3 ? a[i] : a[4 + i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c[2];
+  const bool u2 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = u2 ? b[2 + i] : b[i], send = u2 ? b[i] : b[2 + i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const bool u1 = lane & 2;
+  const float keep = u1 ? c[1] : c[0], send = u1 ? c[0] : c[1];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+inline int pick_bn(int N) {
+  // output columns per tile: a multiple of 16 (UMMA N for M=128), <= 256, as few chunks as possible
+  const int Np = (N + 15) & ~15;
+  const int chunks = (Np + 255) / 256;
+  int bn = (Np / chunks + 15) & ~15;
+  while (bn * chunks < Np) bn += 16;
+  return bn;
+}
+
+
+}  // namespace tc
+}  // namespace ehgr

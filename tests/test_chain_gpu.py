@@ -154,7 +154,7 @@ def test_mtmm_step_against_oracle(dtype, tol):
         sdy = O.clone_state(sd0)
         yloss, ylogits, ydpred = O.mtmm_train_step(sdy, rgb, depth, labels, 8, "tsm", 8, True)
     else:
-        sdy = {k: (v.float().cuda().requires_grad_(v.requires_grad) if v.is_floating_point() else v.cuda())
+        sdy = {k: (v.detach().float().cuda().requires_grad_(v.requires_grad) if v.is_floating_point() else v.cuda())
                for k, v in O.clone_state(sd0).items()}
         with torch.autocast("cuda", dtype=torch.bfloat16):
             yloss, ylogits, ydpred = O.mtmm_train_step(sdy, rgb.cuda(), depth.cuda(), labels.cuda(), 8, "tsm", 8, True)
