@@ -39,6 +39,8 @@ constexpr int kProducerWarps = 7;   // 12 warps = 384 threads: up to 168 registe
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kThreads = (kProducerWarps + 1 + 4) * 32;   // 384
 constexpr int kMaxStages = 12;
+constexpr int kBarBytes = 256;                 // mbarriers + TMEM slot
+constexpr int kTailBytes = kBarBytes + 4 * 512 * 4;   // + per-epilogue-warp statistics accumulators
 
 struct GemmArgs {
   RowOp a;
@@ -140,16 +142,21 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
 
   const int total_tiles = p.m_tiles * p.n_chunks;
   const int k_stages = (p.K + BK - 1) / BK;
-  const int a_sbo = p.a_bytes >> 4;                 // row-group stride of an A stage = min(Kp,64)*16 bytes
+  const int a_sbo = p.a_bytes >> 4;                 // BYTES between 8-row groups of an A stage = min(Kp,64)*16
 
   if (warp < kProducerWarps) {
     // ===================== PRODUCERS (one warp per ring stage) =====================
     const int r = lane & 7, slot = lane >> 3;
+    const int pw = p.n_stages < kProducerWarps ? p.n_stages : kProducerWarps;   // active producer warps
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x) {
       const long long m0 = static_cast<long long>(tile / p.n_chunks) * BM;
       for (int ks = 0; ks < k_stages; ++ks, ++it) {
-        if (static_cast<int>(it % kProducerWarps) != warp) continue;
+        // Stage i belongs to warp i % pw.  The empty-slot wait only tracks phase PARITY, so a producer
+        // must never get two ring rounds ahead of the MMA warp: either pw == n_stages (a slot is only
+        // ever filled by one warp, whose stages are sequential) or pw < n_stages (a warp's previous
+        // stage was at most pw < n_stages stages back, and it waited for that slot's previous round).
+        if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
         const int s = it % p.n_stages;
         const uint32_t parity = ((it / p.n_stages) & 1) ^ 1;
         uint8_t* a_dst = ring + s * p.stage_bytes;
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = 0.f;
                 if (live[j]) ld.finish(p.a, raw[j], v);
-                *reinterpret_cast<uint4*>(a_dst + rg * (a_sbo << 4) + k8 * 128 + r * 16) = pack8(v);
+                *reinterpret_cast<uint4*>(a_dst + rg * a_sbo + k8 * 128 + r * 16) = pack8(v);
               }
             }
           }
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           const int ksteps = min(BK, Kp - ks * BK) >> 4;
           for (int kk = 0; kk < ksteps; ++kk) {
             // one K=16 step = two 8-element core matrices along K = 256 bytes
-            const uint64_t da = make_desc(a_addr + kk * 256, 128, static_cast<uint32_t>(a_sbo) << 4);
+            const uint64_t da = make_desc(a_addr + kk * 256, 128, static_cast<uint32_t>(a_sbo));
             const uint64_t db = p.b_resident
                                     ? make_desc(bres_addr + (ks * 8 + kk * 2) * 128, 128, static_cast<uint32_t>(Kp) * 16)
                                     : make_desc(a_addr + p.a_bytes + kk * 256, 128, 1024);
@@ -230,9 +237,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
     // ===================== EPILOGUE =====================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int n_cc = p.BN >> 4;                     // 16-column chunks
-    float ssum[16], ssq[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) ssum[i] = ssq[i] = 0.f;
+    // per-warp statistics accumulators live in shared memory (column index is dynamic); the chunk loop
+    // is deliberately NOT unrolled: the kernel must stay small enough for the instruction cache
+    float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + q * 512;
+    float* s_sq = s_sum + 256;
+    const int col = (lane >> 1) & 15;
+    if (p.stats) {
+      for (int i = lane; i < 512; i += 32) s_sum[i] = 0.f;
+      __syncwarp();
+    }
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const uint32_t buf = tl & 1;
@@ -240,17 +253,20 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
       mbar_wait(bar_tfull + 8 * buf, (tl >> 1) & 1);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * static_cast<uint32_t>(p.BN);
-#pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        if (cc < n_cc) {
+#pragma unroll 1
+      for (int cc = 0; cc < n_cc; ++cc) {
+        {
           float v[16];
           tmem_ld16(t_base + cc * 16, v);
           if (p.stats) {
             float sq[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-            ssum[cc] += warp_colsum16(v, lane);
-            ssq[cc] += warp_colsum16(sq, lane);
+            const float cs = warp_colsum16(v, lane), cq = warp_colsum16(sq, lane);
+            if (!(lane & 1)) {                      // lanes 2c and 2c+1 hold the same column: one writes
+              s_sum[cc * 16 + col] += cs;
+              s_sq[cc * 16 + col] += cq;
+            }
           }
           const int n = n0 + cc * 16;
           if (m < p.M && n < p.N) {
@@ -278,14 +294,13 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * buf);
     }
-    if (p.stats && !(lane & 1)) {
-      const int col = (lane >> 1) & 15;
-#pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        const int n = n0 + cc * 16 + col;
-        if (cc < n_cc && n < p.N) {
-          atomicAdd(&p.stats[n], static_cast<double>(ssum[cc]));
-          atomicAdd(&p.stats[p.N + n], static_cast<double>(ssq[cc]));
+    if (p.stats) {
+      __syncwarp();
+      for (int c = lane; c < p.BN; c += 32) {
+        const int n = n0 + c;
+        if (n < p.N) {
+          atomicAdd(&p.stats[n], static_cast<double>(s_sum[c]));
+          atomicAdd(&p.stats[p.N + n], static_cast<double>(s_sq[c]));
         }
       }
     }
@@ -325,7 +340,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, int w_is_kn, void* out, const voi
   p.tmem_cols = cols;
   const int Kp = (K + 15) & ~15;
   constexpr int kBudget = 200 * 1024;
-  const int bar_bytes = (2 * tc::kMaxStages + 4) * 8 + 16;
+  const int bar_bytes = tc::kTailBytes;
   p.a_bytes = tc::BM * std::min(Kp, tc::BK) * 2;
   const int b_res = p.BN * Kp * 2;
   // weights resident when that still leaves >= 6 A stages (the large-M layers all qualify)

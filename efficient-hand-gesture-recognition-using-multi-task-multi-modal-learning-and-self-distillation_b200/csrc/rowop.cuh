@@ -171,6 +171,17 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
   }
 }
 
+// SHIFT vector that straddles a fold boundary, assembled and re-packed to its 16 raw bytes.  Kept out
+// of line: it is the rare path and would otherwise be inlined into every unrolled fetch.
+template <typename T, int NV>
+__device__ __noinline__ uint4 shift_straddle_raw(const RowOp& op, long long m, int c0, int C) {
+  float v[NV];
+  load_row<T, NV>(op, m, c0, C, v);
+  uint4 out;
+  store_vec<T, NV>(reinterpret_cast<T*>(&out), v);
+  return out;
+}
+
 // Same operand, for threads that read MANY rows of the SAME channel vector (depthwise taps, reductions,
 // GEMM operand staging): the per-channel coefficients are fetched once into registers by init() and
 // load() only touches the activation tensors.
@@ -256,11 +267,7 @@ struct RowLoader {
         const bool ok = cl == 2 || (cl == 0 ? has_next : has_prev);
         if (ok) r.a = *reinterpret_cast<const uint4*>(in1 + off + (cl == 0 ? step : cl == 1 ? -step : 0));
       } else {  // straddles a fold boundary (C = 24, 32, 96, 160: one vector per row): assemble now
-        float v[NV];
-        load_row<T, NV>(op, m, c0, C, v);
-        T tmp[NV];
-        store_vec<T, NV>(tmp, v);
-        r.a = *reinterpret_cast<const uint4*>(tmp);
+        r.a = shift_straddle_raw<T, NV>(op, m, c0, C);
       }
     } else {
       r.a = *reinterpret_cast<const uint4*>(in1 + off);
