@@ -39,6 +39,7 @@ constexpr int kProducerWarps = 7;   // 12 warps = 384 threads: up to 168 registe
 constexpr int kMmaWarp = kProducerWarps;
 constexpr int kThreads = (kProducerWarps + 1 + 4) * 32;   // 384
 constexpr int kMaxStages = 12;
+constexpr int kBatch = 4;                      // vectors a producer lane fetches before it converts any
 constexpr int kBarBytes = 256;                 // mbarriers + TMEM slot
 constexpr int kTailBytes = kBarBytes + 4 * 512 * 4;   // + per-epilogue-warp statistics accumulators
 
@@ -174,11 +175,11 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           RowLoader<__nv_bfloat16, 8> ld;
           if (kin) ld.init(p.a, k, p.K);
 #pragma unroll 1
-          for (int j0 = 0; j0 * f < 16; j0 += 8) {
-            RowLoader<__nv_bfloat16, 8>::Raw raw[8];
-            bool live[8];
+          for (int j0 = 0; j0 * f < 16; j0 += kBatch) {
+            RowLoader<__nv_bfloat16, 8>::Raw raw[kBatch];
+            bool live[kBatch];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kBatch; ++j) {
               const int rg = (j0 + j) * f + slot / kvp;
               const long long m = m0 + rg * 8 + r;
               live[j] = kin && rg < 16 && m < p.M;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
             }
             if (!waited) { mbar_wait(bar_empty + 8 * s, parity); waited = true; }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kBatch; ++j) {
               const int rg = (j0 + j) * f + slot / kvp;
               if (k8 < kv && rg < 16) {
                 float v[8];
