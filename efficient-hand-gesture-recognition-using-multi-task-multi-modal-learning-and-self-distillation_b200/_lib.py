@@ -103,6 +103,7 @@ SIGNATURES = {
     "ehgr_dw_fwd": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_dw_dgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_dw_wgrad": [_R, _R, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_dw_bwd": [_R, _R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_stem_wgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P],

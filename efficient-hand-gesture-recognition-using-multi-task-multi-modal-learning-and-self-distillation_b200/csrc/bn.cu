@@ -113,20 +113,46 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv) {
   constexpr int V = VecOf<T>::N;
+  constexpr int U = 4;  // vectors in flight per thread
+  using Ld = RowLoader<T, V>;
   const long long total = M * cv;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cv;
-    const int c0 = static_cast<int>(i - m * cv) * V;
-    float v[V];
-    load_row<T, V>(a, m, c0, C, v);
-    if (addend) {
-      float ad[V];
-      load_vec<T, V>(addend + m * C + c0, ad);
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    typename Ld::Raw raw[U];
+    uint4 ad[U];
+    long long off[U];
+    int c0[U];
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] += ad[k];
+    for (int j = 0; j < U; ++j) {
+      const long long i = i0 + j * stride;
+      off[j] = -1;
+      if (i < total) {
+        const long long m = i / cv;
+        c0[j] = static_cast<int>(i - m * cv) * V;
+        off[j] = m * C + c0[j];
+        Ld ld;
+        ld.c0 = c0[j];
+        ld.C = C;
+        raw[j] = ld.fetch(a, m);
+        if (addend) ad[j] = *reinterpret_cast<const uint4*>(addend + off[j]);
+      }
     }
-    store_vec<T, V>(out + m * C + c0, v);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (off[j] >= 0) {
+        Ld ld;
+        ld.init(a, c0[j], C);
+        float v[V];
+        ld.finish(a, raw[j], v);
+        if (addend) {
+          float av[V];
+          load_vec<T, V>(reinterpret_cast<const T*>(&ad[j]), av);
+#pragma unroll
+          for (int k = 0; k < V; ++k) v[k] += av[k];
+        }
+        store_vec<T, V>(out + off[j], v);
+      }
+    }
   }
 }
 

@@ -278,6 +278,10 @@ static int dw_wgrad_launch(const RowOp& dy, const RowOp& a, float* dw, const DwG
 
 }  // namespace ehgr
 
+namespace ehgr {
+int dw_fwd_tiled(const RowOp& a, const float* w, void* out, double* stats, int nt, int h, int wd, int c, int stride,
+                 int dtype, cudaStream_t s);
+}
 using namespace ehgr;
 
 extern "C" int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, double* stats, int nt, int h, int wd,
@@ -289,8 +293,7 @@ extern "C" int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, doubl
   if (!aligned_to(out, 16)) return EHGR_E_ALIGN;
   if (g.n_out == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);
-  return dtype == EHGR_F32 ? dw_fwd_launch<float>(*a, w, out, stats, g, s)
-                           : dw_fwd_launch<__nv_bfloat16>(*a, w, out, stats, g, s);
+  return dw_fwd_tiled(*a, w, out, stats, nt, h, wd, c, stride, dtype, s);   // shared-memory-tiled kernel (dw_tiled.cu)
 }
 
 extern "C" int ehgr_dw_dgrad(const ehgr_rowop* dy, const float* w, void* da, int nt, int h, int wd, int c,

@@ -382,14 +382,12 @@ class _ChainFunction(torch.autograd.Function):
                                   _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
                                   algo_flops=2 * m_in * cin * cout)
                 else:
-                    _lib.call("ehgr_dw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), gw.data_ptr(), nt, h, wd, cin,
-                              st.stride, code, sp, algo_bytes=(2 * m_out + m_in) * cin * es,
-                              algo_flops=18 * m_out * cin)
-                    if need_dgrad:
-                        g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
-                        _lib.call("ehgr_dw_dgrad", ctypes.byref(dy_op), w.data_ptr(), g_prev.data_ptr(), nt, h, wd, cin,
-                                  st.stride, code, sp, algo_bytes=(2 * m_out + m_in) * cin * es,
-                                  algo_flops=18 * m_in * cin)
+                    # fused backward: one shared-memory staging of rowop(dy) and rowop(a) per tile gives
+                    # both the input gradient and the weight gradient
+                    g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
+                    _lib.call("ehgr_dw_bwd", ctypes.byref(dy_op), ctypes.byref(a_op), w.data_ptr(), g_prev.data_ptr(),
+                              gw.data_ptr(), nt, h, wd, cin, st.stride, code, sp,
+                              algo_bytes=(2 * m_out + 2 * m_in) * cin * es, algo_flops=18 * (m_out + m_in) * cin)
                 g = g_prev
             # gradient w.r.t. the unit input: undo the shift, add the residual branch
             st0 = u.stages[0]

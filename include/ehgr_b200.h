@@ -131,6 +131,10 @@ int ehgr_dw_dgrad(const ehgr_rowop* dy, const float* w, void* da, int nt, int h,
                   int dtype, ehgr_stream_t stream);
 int ehgr_dw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, int nt, int h, int wd, int c,
                   int stride, int dtype, ehgr_stream_t stream);
+/* fused backward: da (as ehgr_dw_dgrad) and dw (as ehgr_dw_wgrad) from ONE shared-memory staging of
+ * rowop(dy) and rowop(a) per tile — the training path uses this; dgrad/wgrad above are the separable form. */
+int ehgr_dw_bwd(const ehgr_rowop* dy, const ehgr_rowop* a, const float* w, void* da, float* dw, int nt, int h,
+                int wd, int c, int stride, int dtype, ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K9  stem: dense 3x3 stride-2 pad-1 convolution 3 -> cout from the NCHW network input

@@ -271,6 +271,43 @@ def test_dw_fwd_bwd(nt, h, w, c, stride, dtype):
     dw = torch.zeros((c, 9), dtype=torch.float32, device="cuda")
     _call("ehgr_dw_wgrad", ctypes.byref(f.op_plain(gr)), ctypes.byref(a_op), dw.data_ptr(), nt, h, w, c, stride, code, _sp())
     assert rel_err(dw.cpu(), w64.grad.view(c, 9)) < max(TOL[dtype], 2e-5)
+    # fused backward (shared-memory tiled): same two results from one kernel
+    da2 = torch.full((nt * h * w, c), float("nan"), dtype=dtype, device="cuda")
+    dw2 = torch.zeros((c, 9), dtype=torch.float32, device="cuda")
+    _call("ehgr_dw_bwd", ctypes.byref(f.op_plain(gr)), ctypes.byref(a_op), wt_d.data_ptr(), da2.data_ptr(), dw2.data_ptr(),
+          nt, h, w, c, stride, code, _sp())
+    assert rel_err(da2.cpu(), _rows(a64.grad)) < TOL[dtype]
+    assert rel_err(dw2.cpu(), w64.grad.view(c, 9)) < max(TOL[dtype], 2e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dw_tiled_ragged_tiles(dtype):
+    """Spatial sizes that do not divide the tile (partial tiles, odd sizes under stride 2)."""
+    E = _E()
+    f = E.fused
+    for (nt, h, w, c, stride) in [(2, 17, 23, 48, 1), (2, 17, 23, 48, 2), (1, 30, 9, 96, 2), (3, 15, 15, 24, 1)]:
+        x = _rand((nt, c, h, w), 25).to(dtype)
+        wt = _rand((c, 1, 3, 3), 26, 0.4)
+        a64 = x.double().requires_grad_(True)
+        w64 = wt.double().requires_grad_(True)
+        y64 = F.conv2d(a64, w64, stride=stride, padding=1, groups=c)
+        ho, wo = y64.shape[2:]
+        xr, wt_d = _rows(x).contiguous().cuda(), wt.cuda()
+        code = E._lib.dtype_code(xr)
+        out = torch.full((nt * ho * wo, c), float("nan"), dtype=dtype, device="cuda")
+        stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+        _call("ehgr_dw_fwd", ctypes.byref(f.op_plain(xr)), wt_d.data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, c, stride, code, _sp())
+        assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
+        assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < 1e-3
+        g = _rand(tuple(y64.shape), 27).to(dtype)
+        y64.backward(g.double())
+        gr = _rows(g).contiguous().cuda()
+        da = torch.full((nt * h * w, c), float("nan"), dtype=dtype, device="cuda")
+        dw = torch.zeros((c, 9), dtype=torch.float32, device="cuda")
+        _call("ehgr_dw_bwd", ctypes.byref(f.op_plain(gr)), ctypes.byref(f.op_plain(xr)), wt_d.data_ptr(), da.data_ptr(), dw.data_ptr(),
+              nt, h, w, c, stride, code, _sp())
+        assert rel_err(da.cpu(), _rows(a64.grad)) < TOL[dtype], (h, w, stride)
+        assert rel_err(dw.cpu(), w64.grad.view(c, 9)) < max(TOL[dtype], 2e-5), (h, w, stride)
 
 
 # ---------------------------------------------------------------------------------------------

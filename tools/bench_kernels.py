@@ -121,6 +121,10 @@ def main():
             "dw_wgrad": (lambda: _lib.call("ehgr_dw_wgrad", ctypes.byref(f.op_bnbwd(g2, raw2, ca2, cb2, cc2, s2, b2, True)),
                                            ctypes.byref(f.op_affine(raw1, s1, b1, True)), dwg.data_ptr(), nt, h, h, hid, stride, 1, sp),
                          f"dw wgrad {hid} @{h} s{stride}", (2 * m_out + m_in) * hid * es, 18 * m_out * hid),
+            "dw_bwd": (lambda: _lib.call("ehgr_dw_bwd", ctypes.byref(f.op_bnbwd(g2, raw2, ca2, cb2, cc2, s2, b2, True)),
+                                         ctypes.byref(f.op_affine(raw1, s1, b1, True)), w2.data_ptr(), g1.data_ptr(), dwg.data_ptr(),
+                                         nt, h, h, hid, stride, 1, sp),
+                       f"dw fused bwd {hid} @{h} s{stride}", (2 * m_out + 2 * m_in) * hid * es, 18 * (m_in + m_out) * hid),
             "pw_dgrad1": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_bnbwd(g1, raw1, ca1, cb1, cc1, s1, b1, True)), w1.data_ptr(), 1,
                                             gx.data_ptr(), 0, 0, m_in, hid, cin, 1, args.engine, sp), f"dgrad {hid}->{cin} @{h}",
                           m_in * (2 * hid + cin) * es, 2 * m_in * hid * cin),
