@@ -260,8 +260,9 @@ def test_dw_fwd_bwd(nt, h, w, c, stride, dtype):
     stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
     _call("ehgr_dw_fwd", ctypes.byref(a_op), wt_d.data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, c, stride, code, _sp())
     assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
-    assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < 1e-4
-    assert rel_err(stats[c:].cpu(), (y64 ** 2).sum((0, 2, 3))) < 1e-4
+    stol = 1e-4 if dtype == torch.float32 else 1e-2   # bf16: staged activations and weights are rounded
+    assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < stol
+    assert rel_err(stats[c:].cpu(), (y64 ** 2).sum((0, 2, 3))) < stol
     g = _rand(tuple(y64.shape), 24).to(dtype)
     y64.backward(g.double())
     gr = _rows(g).contiguous().cuda()
@@ -298,7 +299,7 @@ def test_dw_tiled_ragged_tiles(dtype):
         stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
         _call("ehgr_dw_fwd", ctypes.byref(f.op_plain(xr)), wt_d.data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, c, stride, code, _sp())
         assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
-        assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < 1e-3
+        assert rel_err(stats[:c].cpu(), y64.sum((0, 2, 3))) < (1e-3 if dtype == torch.float32 else 1e-2)
         g = _rand(tuple(y64.shape), 27).to(dtype)
         y64.backward(g.double())
         gr = _rows(g).contiguous().cuda()
