@@ -2,17 +2,30 @@
 recogniser: hand-written CUDA behind the reference's own operator API.
 
 Import as ``import ehgr_b200`` (alias module at the repo root) — the directory name carries the
-reference's full title and is not a Python identifier.
+reference's full title and is not a Python identifier.  Sub-modules are exposed as attributes with a
+``_module`` suffix where a re-exported function has the same name (``temporal_shift``).
 """
+import importlib as _importlib
+
 from . import _lib  # noqa: F401
-from .temporal_shift import (InplaceShift, TemporalPool, TemporalShift, make_temporal_pool,  # noqa: F401
+
+temporal_shift_module = _importlib.import_module(__name__ + ".temporal_shift")
+mobilenet_v2_module = _importlib.import_module(__name__ + ".mobilenet_v2")
+action = _importlib.import_module(__name__ + ".action")
+basic_ops = _importlib.import_module(__name__ + ".basic_ops")
+fused = _importlib.import_module(__name__ + ".fused")
+tsn = _importlib.import_module(__name__ + ".tsn")
+losses = _importlib.import_module(__name__ + ".losses")
+train_step = _importlib.import_module(__name__ + ".train_step")
+tsn_mtmm = _importlib.import_module(__name__ + ".tsn_mtmm")
+tsn_sd = _importlib.import_module(__name__ + ".tsn_sd")
+
+from .temporal_shift import (InplaceShift, TemporalPool, TemporalShift, make_temporal_pool,  # noqa: E402,F401
                              make_temporal_shift, temporal_shift)
-from .action import Action  # noqa: F401
-from .basic_ops import ConsensusModule, SegmentConsensus  # noqa: F401
-from .mobilenet_v2 import InvertedResidual, MobileNetV2, mobilenet_v2  # noqa: F401
-from .tsn import TSN  # noqa: F401
-from . import losses, train_step, tsn_mtmm  # noqa: F401
-from . import action, basic_ops, fused, mobilenet_v2 as mobilenet_v2_module, temporal_shift as temporal_shift_module, tsn  # noqa: F401,E501
+from .action import Action  # noqa: E402,F401
+from .basic_ops import ConsensusModule, SegmentConsensus  # noqa: E402,F401
+from .mobilenet_v2 import InvertedResidual, MobileNetV2, mobilenet_v2  # noqa: E402,F401
+from .tsn import TSN  # noqa: E402,F401
 
 __all__ = [
     "TemporalShift", "InplaceShift", "TemporalPool", "make_temporal_shift", "make_temporal_pool",

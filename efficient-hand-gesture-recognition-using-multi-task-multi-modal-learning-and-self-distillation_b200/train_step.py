@@ -152,3 +152,33 @@ class MTMMTrainStep:
 
     def __call__(self, rgb_h, depth_h, labels_h) -> float:
         return float(self.run(*self.stage(rgb_h, depth_h, labels_h)).item())
+
+
+class SDTrainStep(MTMMTrainStep):
+    """One self-distillation step (train_sd.py:217-282): forward with the three exit heads, the fused
+    SD loss (4 CE + 3 KD + 3 feature terms), backward, gradient all-reduce, SGD.
+
+    The feature term is a SUM over the local batch (train_sd.py:191-193): with gradient averaging over
+    `world` ranks its weight would shrink by 1/world relative to a single-process global batch, so
+    beta is multiplied by world here (DDP loss scaling)."""
+
+    def __init__(self, model, alpha=0.1, beta=1e-6, temperature=3.0, **kw):
+        super().__init__(model, **kw)
+        self.alpha, self.beta, self.temperature = alpha, beta * self.buckets.world, temperature
+
+    def stage(self, rgb_h, labels_h):
+        return rgb_h.to(self.device, non_blocking=True), labels_h.to(self.device, non_blocking=True)
+
+    def run(self, rgb, labels):
+        from .losses import sd_loss
+        self.buckets.zero()
+        with self._fused.compute_dtype(self.compute_dtype):
+            outs = self.model(rgb)
+            total, _terms = sd_loss(outs[:4], outs[4:], labels, self.alpha, self.beta, self.temperature)
+        total.backward()
+        self.buckets.finish()
+        self.opt.step()
+        return total.detach()
+
+    def __call__(self, rgb_h, labels_h) -> float:
+        return float(self.run(*self.stage(rgb_h, labels_h)).item())

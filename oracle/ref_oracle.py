@@ -393,3 +393,72 @@ def mtmm_train_step(sd: SD, rgb, depth, labels, num_segments=8, temporal="tsm", 
     loss, _ = mtmm_loss(logits, labels, dpred, depth)
     loss.backward()
     return loss.detach(), logits.detach(), dpred.detach()
+
+
+# --------------------------------------------------------------------------------------------
+# SD wrapper on MobileNetV2 — exit heads models/models_SD.py:81-101 (SepConv), :214-253 (scala1-3,
+# middle_fc1-3), forward :364-431.  The reference wires ResNet stages; the MobileNetV2 taps
+# (features[3], [6], [13]; 24/32/96 channels) are builder-defined.
+# --------------------------------------------------------------------------------------------
+def sepconv(x, sd: SD, prefix: str, bn_training: bool):
+    c = x.shape[1]
+    y = F.conv2d(x, sd[f"{prefix}.op.0.weight"], stride=2, padding=1, groups=c)
+    y = F.conv2d(y, sd[f"{prefix}.op.1.weight"])
+    y = F.relu(_bn(y, sd, f"{prefix}.op.2", bn_training))
+    y = F.conv2d(y, sd[f"{prefix}.op.4.weight"], stride=1, padding=1, groups=c)
+    y = F.conv2d(y, sd[f"{prefix}.op.5.weight"])
+    return F.relu(_bn(y, sd, f"{prefix}.op.6", bn_training))
+
+
+SD_TAPS = (3, 6, 13)
+SD_HEADS = (("scala1", (24, 32, 96, 1280)), ("scala2", (32, 96, 1280)), ("scala3", (96, 1280)))
+
+
+def sd_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8, bn_training: bool = True):
+    """-> (output, mid1, mid2, mid3, final_fea, fea1, fea2, fea3) as models/models_SD.py:431."""
+    taps = {i: None for i in SD_TAPS + (18,)}
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    mobilenet_v2_features(x, sd, temporal, num_segments, shift_div, bn_training, taps=taps)
+    mids, feas = [], []
+    for (name, chans), tap, fc in zip(SD_HEADS, SD_TAPS, ("middle_fc1", "middle_fc2", "middle_fc3")):
+        y = taps[tap]
+        for j in range(len(chans) - 1):
+            y = sepconv(y, sd, f"{name}.{j}", bn_training)
+        fea = F.adaptive_avg_pool2d(y, 1)
+        z = F.linear(torch.flatten(fea, 1), sd[fc + ".weight"], sd[fc + ".bias"])
+        mids.append(z.view((-1, num_segments) + tuple(z.shape[1:])).mean(1))
+        feas.append(fea)
+    final_fea = F.adaptive_avg_pool2d(taps[18], 1)
+    z = F.linear(torch.flatten(final_fea, 1), sd["new_fc.weight"], sd["new_fc.bias"])
+    out = z.view((-1, num_segments) + tuple(z.shape[1:])).mean(1)
+    return (out, *mids, final_fea, *feas)
+
+
+def build_sd_state(num_class: int = 83, temporal: str = "tsm", shift_div: int = 8, seed: int = 0) -> SD:
+    sd = build_tsn_state(num_class, temporal, shift_div, seed)
+    rs = np.random.RandomState(seed + 991)
+    for name, chans in SD_HEADS:
+        for j, (ci, co) in enumerate(zip(chans[:-1], chans[1:])):
+            p = f"{name}.{j}.op"
+            _conv_entry(sd, f"{p}.0.weight", (ci, 1, 3, 3), rs, std=0.3)
+            _conv_entry(sd, f"{p}.1.weight", (ci, ci, 1, 1), rs, std=math.sqrt(2.0 / ci))
+            _bn_entries(sd, f"{p}.2", ci, rs)
+            _conv_entry(sd, f"{p}.4.weight", (ci, 1, 3, 3), rs, std=0.3)
+            _conv_entry(sd, f"{p}.5.weight", (co, ci, 1, 1), rs, std=math.sqrt(2.0 / ci))
+            _bn_entries(sd, f"{p}.6", co, rs)
+    for fc in ("middle_fc1", "middle_fc2", "middle_fc3"):
+        sd[fc + ".weight"] = torch.from_numpy((rs.standard_normal((num_class, 1280)) * 0.02).astype(np.float32))
+        sd[fc + ".bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
+    return sd
+
+
+def sd_train_step(sd: SD, rgb, labels, num_segments=8, temporal="tsm", shift_div=8, bn_training=True,
+                  alpha=0.1, beta=1e-6, temperature=3.0):
+    """One reference-equivalent SD step (train_sd.py:217-282) on the oracle: returns (total, terms)."""
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    outs = sd_forward(rgb, sd, num_segments, temporal, shift_div, bn_training)
+    total, terms = sd_loss(outs[:4], outs[4:], labels, alpha, beta, temperature)
+    total.backward()
+    return total.detach(), terms

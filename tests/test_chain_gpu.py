@@ -171,3 +171,52 @@ def test_mtmm_step_against_oracle(dtype, tol):
            "grad": grad_err((k, v.grad) for k, v in sdy.items() if v.is_floating_point() and v.grad is not None)}
     for k in ours:
         assert ours[k] <= max(3.0 * ref[k], tol), (k, ours, ref)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_sd_step_against_oracle(dtype, tol):
+    """SD stage-2 step (train_sd.py:217-282) on TSM-MobileNetV2 with the three exit heads: fused chain
+    with taps + fused SD loss kernel, against the oracle; yardstick = the oracle at the same precision."""
+    import ehgr_b200 as E
+    sd0 = O.build_sd_state(83, "tsm", 8, seed=6)
+    with _quiet():
+        model = E.tsn_sd.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                             dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                             temporal_module='tsm')
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    for d in model.modules():
+        if isinstance(d, torch.nn.Dropout):
+            d.eval()
+    rgb, _, labels = O.synthetic_clip_batch(1, 8, 224, 83, seed=7)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False      # the exit heads still run on library convolutions
+    try:
+        with E.fused.compute_dtype(dtype):
+            outs = model(rgb.cuda())
+            total, terms = E.losses.sd_loss(outs[:4], outs[4:], labels.cuda(), 0.1, 1e-6, 3.0)
+        total.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert [tuple(o.shape) for o in outs] == [(1, 83)] * 4 + [(8, 1280, 1, 1)] * 4
+    sd = O.clone_state(sd0, dtype=torch.float64)
+    ototal, oterms = O.sd_train_step(sd, rgb.double(), labels)
+    if dtype == torch.float32:
+        sdy = O.clone_state(sd0)
+        ytotal, _ = O.sd_train_step(sdy, rgb, labels)
+    else:
+        sdy = {k: (v.detach().float().cuda().requires_grad_(v.requires_grad) if v.is_floating_point() else v.cuda())
+               for k, v in O.clone_state(sd0).items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ytotal, _ = O.sd_train_step(sdy, rgb.cuda(), labels.cuda())
+    gmax = max(v.grad.abs().max().item() for v in sd.values() if v.grad is not None)
+
+    def grad_err(named):
+        return max(((g.detach().cpu().double() - sd[k].grad).abs().max().item() / gmax) for k, g in named)
+
+    ours = {"loss": abs(total.item() - ototal.item()) / abs(ototal.item()),
+            "grad": grad_err((k, p.grad) for k, p in model.named_parameters())}
+    ref = {"loss": abs(float(ytotal) - ototal.item()) / abs(ototal.item()),
+           "grad": grad_err((k, v.grad) for k, v in sdy.items() if v.is_floating_point() and v.grad is not None)}
+    for k in ours:
+        assert ours[k] <= max(3.0 * ref[k], tol), (k, ours, ref)

@@ -1,0 +1,74 @@
+"""Data-parallel host logic on CPU: world_size-2 gloo run of the bucketed gradient all-reduce
+(ehgr_b200.train_step.GradBuckets).  No GPU, no kernels: gradients are written by hand."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ehgr_b200
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((7, 3), (5,), (2, 2, 2), (11,), (1,))]
+    gb = ehgr_b200.train_step.GradBuckets(params, n_buckets=3)
+    assert gb.world == world and 2 <= len(gb.bounds) <= 3
+    assert sum(hi - lo for lo, hi in gb.bounds) == sum(p.numel() for p in params)
+    for step in range(2):
+        gb.zero()
+        # a fake backward in reverse parameter order: every rank contributes (rank+1) * (index+1)
+        for i, p in reversed(list(enumerate(params))):
+            loss = (p * float((rank + 1) * (i + 1) + step)).sum()
+            loss.backward()
+        gb.finish()
+        want = sum((r + 1) for r in range(world)) / world
+        for i, p in enumerate(params):
+            expect = ((want * (i + 1)) + step)
+            assert torch.allclose(p.grad, torch.full_like(p, expect)), (rank, i, p.grad.flatten()[:3], expect)
+            assert p.grad.data_ptr() >= gb.flat.data_ptr()          # grads are views of the flat buffer
+    # unused parameter: its bucket is flushed by finish()
+    gb.zero()
+    (params[0] * 2.0).sum().backward()
+    gb.finish()
+    assert torch.allclose(params[0].grad, torch.full_like(params[0], 2.0))
+    assert float(params[3].grad.abs().sum()) == 0.0
+    if rank == 0:
+        out.put("ok")
+    dist.destroy_process_group()
+
+
+def test_grad_buckets_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == "ok"
+
+
+def test_sgd_groups_follow_reference_multipliers():
+    import contextlib, io
+    import ehgr_b200
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ehgr_b200.TSN(10, 8, 'RGB', base_model='mobilenetv2', pretrain=None, dropout=0.5, partial_bn=False,
+                          is_shift=True, fc_lr5=True, temporal_module='tsm')
+    opt = ehgr_b200.train_step.build_sgd(m, lr=0.01, momentum=0.9, weight_decay=5e-4)
+    by_name = {g['name']: g for g in opt.param_groups}
+    assert abs(by_name['lr5_weight']['lr'] - 0.05) < 1e-12 and abs(by_name['lr10_bias']['lr'] - 0.1) < 1e-12
+    assert by_name['BN scale/shift']['weight_decay'] == 0 and abs(by_name['normal_weight']['weight_decay'] - 5e-4) < 1e-12
+    ehgr_b200.train_step.adjust_learning_rate(0.01, opt, epoch=25, lr_steps=[20, 40])
+    assert abs(by_name['normal_weight']['lr'] - 0.001) < 1e-12 and abs(by_name['lr5_weight']['lr'] - 0.005) < 1e-12
