@@ -1,21 +1,26 @@
 // pw_tc_wgrad.cu — weight gradient of the pointwise convolution on tcgen05 tensor cores.
+//
+//   dw[N,K] += sum_m rowop(dy)[m,n] * rowop(a)[m,k]
+//
+//   D[128 n x BKc k] (TMEM, fp32) accumulates over ALL row tiles a CTA owns: no per-tile epilogue.
+//   Both operands are MN-major (the reduction index is the row m): a lane's 16-byte vector of 8
+//   consecutive channels of row m lands at (m%8)*16 + (m/8)*128 + (channel/8)*gs — plain vector stores,
+//   no transposition anywhere; the same bytes a forward GEMM would stage, read through a different
+//   descriptor.  A ring stage holds kMS = 32 rows (two K=16 MMA steps); grid = (n_tiles*k_tiles) x
+//   splits, each split strides over the row chunks; the epilogue adds the partial tile to dw with fp32
+//   atomics.  Warps: 0-6 producers (one ring stage each, lane = row, batched fetch), 7 MMA issuer,
+//   0-3 double as the epilogue at the end.
 #include "tc_common.cuh"
 
 namespace ehgr {
 namespace tc {
 
-// ---------------------------------------------------------------------------------------------------
-// weight gradient:  dw[N,K] += sum_m dy[m,n] * a[m,k]
-//   D[128 n x BKc k] (TMEM, fp32) accumulates over ALL row tiles a CTA owns: no per-tile epilogue.
-//   Both operands are MN-major (the reduction index is the row m): a thread's 16-byte vector of 8
-//   consecutive channels of row m lands at (m%8)*16 + (m/8)*128 + (channel/8)*2048 — plain vector
-//   stores, no transposition anywhere.  grid = (n_tiles*k_tiles) x splits; each split strides over
-//   the row tiles; the epilogue adds the partial tile to dw with fp32 atomics.
-//   5 warps: 0-3 produce (and run the epilogue at the end), 4 issues the MMAs.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kWgStages = 2;
-constexpr int kWgThreads = 288;   // 2 producer groups x 4 warps + 1 MMA warp
-constexpr int kWgDyBytes = 128 * 128 * 2;   // [128 n][128 m] bf16
+constexpr int kMS = 32;                 // rows (reduction elements) per ring stage
+constexpr int kWgProducers = 7;
+constexpr int kWgMmaWarp = 7;
+constexpr int kWgThreads = 256;
+constexpr int kWgMaxStages = 12;
+constexpr int kWgBarBytes = 256;
 
 struct WgradArgs {
   RowOp dy, a;
@@ -23,32 +28,34 @@ struct WgradArgs {
   long long M;
   int K, N;
   int BKc;        // k columns per output tile (multiple of 16, <= 256)
-  int k_tiles, n_tiles, m_tiles, splits;
+  int k_tiles, n_tiles, splits;
+  long long m_chunks;   // ceil(M / kMS)
   int tmem_cols;
+  int n_stages, stage_bytes;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int a_bytes = p.BKc * 128 * 2;
-  const int stage_bytes = kWgDyBytes + a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * stage_bytes);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWgStages), bar_done = smem_u32(bars + 2 * kWgStages);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  const int gs = kMS * 16;                              // bytes between channel groups inside a stage
+  const int dy_bytes = 16 * gs;                         // 128 n = 16 groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * p.stage_bytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWgMaxStages), bar_done = smem_u32(bars + 2 * kWgMaxStages);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) {
-      mbar_init(bar_full + 8 * s, 128);
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 32);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
     fence_mbar_init();
   }
   // zero the operand ring once: padded channel groups are never written again
-  for (int i = threadIdx.x; i < kWgStages * stage_bytes / 16; i += kWgThreads)
+  for (int i = threadIdx.x; i < p.n_stages * p.stage_bytes / 16; i += kWgThreads)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(p.tmem_cols));
+  if (warp == kWgMmaWarp) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(p.tmem_cols));
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -60,118 +67,104 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
   const int n0 = (tile / p.k_tiles) * 128, k0 = (tile % p.k_tiles) * p.BKc;
   const int n_valid = min(128, p.N - n0), k_valid = min(p.BKc, p.K - k0);   // multiples of 8
   const int ng = n_valid >> 3, kg = k_valid >> 3;
-  int my_tiles = 0;
-  for (int mt = split; mt < p.m_tiles; mt += p.splits) ++my_tiles;
+  long long my_chunks = 0;
+  if (split < p.m_chunks) my_chunks = (p.m_chunks - split + p.splits - 1) / p.splits;
+  const int pw = p.n_stages < kWgProducers ? p.n_stages : kWgProducers;   // see pw_tc.cu: parity aliasing
 
-  if (warp < 8) {
-    // two producer groups (128 threads each) alternate ring stages; per stage a thread fetches its
-    // vectors in batches of four (loads only), then applies the row operand and stores.
-    const int tid = threadIdx.x & 127, group = warp >> 2;
-    const int r = tid & 7;
+  if (warp < pw) {
     using Ld = RowLoader<__nv_bfloat16, 8>;
     uint32_t it = 0;
-    for (int mt = split; mt < p.m_tiles; mt += p.splits, ++it) {
-      if (static_cast<int>(it & 1) != group) continue;
-      const int s = it % kWgStages;
-      uint8_t* dy_dst = smem + s * stage_bytes;
-      uint8_t* a_dst = dy_dst + kWgDyBytes;
-      const long long m0 = static_cast<long long>(mt) * 128;
+    for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
+      if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
+      const int s = it % p.n_stages;
+      uint8_t* dy_dst = smem + s * p.stage_bytes;
+      uint8_t* a_dst = dy_dst + dy_bytes;
+      const long long m = mc * kMS + lane;               // lane = row of the stage
+      const bool row_ok = m < p.M;
+      const int row_off = (lane >> 3) * 128 + (lane & 7) * 16;
       bool waited = false;
+      const int total = ng + kg;                          // channel groups of dy, then of a
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const RowOp& op = pass ? p.a : p.dy;
-        const int groups = pass ? kg : ng, c_base = pass ? k0 : n0, C = pass ? p.K : p.N;
-        uint8_t* dst = pass ? a_dst : dy_dst;
-#pragma unroll 1
-        for (int v0 = tid; v0 < 128 * groups; v0 += 4 * 128) {
-          Ld::Raw raw[4];
-          bool live[4];
-          int off[4], c0[4];
+      for (int g0 = 0; g0 < total; g0 += 4) {
+        Ld::Raw raw[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int v = v0 + j * 128;
-            off[j] = -1;
-            live[j] = false;
-            if (v < 128 * groups) {
-              const int g = (v >> 3) % groups, mg = (v >> 3) / groups;
-              const long long m = m0 + mg * 8 + r;
-              off[j] = g * 2048 + mg * 128 + r * 16;
-              c0[j] = c_base + g * 8;
-              live[j] = m < p.M;
-              if (live[j]) {
-                Ld ld;
-                ld.c0 = c0[j];
-                ld.C = C;
-                raw[j] = ld.fetch(op, m);
-              }
-            }
+        for (int j = 0; j < 4; ++j) {
+          const int g = g0 + j;
+          if (g < total && row_ok) {
+            Ld ld;
+            const bool is_a = g >= ng;
+            ld.c0 = is_a ? k0 + (g - ng) * 8 : n0 + g * 8;
+            ld.C = is_a ? p.K : p.N;
+            raw[j] = ld.fetch(is_a ? p.a : p.dy, m);
           }
-          if (!waited) { mbar_wait(bar_empty + 8 * s, ((it / kWgStages) & 1) ^ 1); waited = true; }
+        }
+        if (!waited) { mbar_wait(bar_empty + 8 * s, ((it / p.n_stages) & 1) ^ 1); waited = true; }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (off[j] >= 0) {
-              float f[8];
+        for (int j = 0; j < 4; ++j) {
+          const int g = g0 + j;
+          if (g < total) {
+            const bool is_a = g >= ng;
+            float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = 0.f;
-              if (live[j]) {
-                Ld ld;
-                ld.init(op, c0[j], C);
-                ld.finish(op, raw[j], f);
-              }
-              *reinterpret_cast<uint4*>(dst + off[j]) = pack8(f);
+            for (int i = 0; i < 8; ++i) f[i] = 0.f;
+            if (row_ok) {
+              Ld ld;
+              const RowOp& op = is_a ? p.a : p.dy;
+              ld.init(op, is_a ? k0 + (g - ng) * 8 : n0 + g * 8, is_a ? p.K : p.N);
+              ld.finish(op, raw[j], f);
             }
+            uint8_t* dst = is_a ? a_dst + (g - ng) * gs : dy_dst + g * gs;
+            *reinterpret_cast<uint4*>(dst + row_off) = pack8(f);
           }
         }
       }
-      if (!waited) mbar_wait(bar_empty + 8 * s, ((it / kWgStages) & 1) ^ 1);
       fence_proxy_async();
       mbar_arrive(bar_full + 8 * s);
     }
-  }
-  if (warp < 4) {
-    // ---- epilogue (same warps): TMEM -> fp32 atomics into dw[N,K]
-    if (my_tiles > 0) {
-      mbar_wait(bar_done, 0);
-      tc_fence_after();
-      const int q = warp & 3;
-      const int n = n0 + q * 32 + lane;
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      for (int cc = 0; cc * 16 < k_valid; ++cc) {
-        float v[16];
-        tmem_ld16(t_base + cc * 16, v);
-        if (n < p.N) {
-          float* dst = p.dw + static_cast<size_t>(n) * p.K + k0 + cc * 16;
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (cc * 16 + i < k_valid) atomicAdd(dst + i, v[i]);
-        }
-      }
-      tc_fence_before();
-    }
-  } else if (warp == 8 && lane == 0 && my_tiles > 0) {
+  } else if (warp == kWgMmaWarp && lane == 0 && my_chunks > 0) {
     const uint32_t idesc = make_idesc(128, p.BKc, 1, 1);     // both operands MN-major
     uint32_t it = 0;
-    for (int mt = split; mt < p.m_tiles; mt += p.splits, ++it) {
-      const int s = it % kWgStages;
-      mbar_wait(bar_full + 8 * s, (it / kWgStages) & 1);
+    for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
+      const int s = it % p.n_stages;
+      mbar_wait(bar_full + 8 * s, (it / p.n_stages) & 1);
       tc_fence_after();
-      const uint32_t dy_addr = smem_base + s * stage_bytes;
-      const uint32_t a_addr = dy_addr + kWgDyBytes;
+      const uint32_t dy_addr = smem_base + s * p.stage_bytes;
+      const uint32_t a_addr = dy_addr + dy_bytes;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        // 16 rows of m = two 8-row core matrices = 256 bytes; LBO (k groups) = 128, SBO (channel groups) = 2048
-        const uint64_t da = make_desc(dy_addr + kk * 256, 128, 2048);
-        const uint64_t db = make_desc(a_addr + kk * 256, 128, 2048);
+      for (int kk = 0; kk < kMS / 16; ++kk) {
+        // 16 rows of m = two 8-row core matrices = 256 bytes; LBO (m groups) = 128, SBO (channel groups) = gs
+        const uint64_t da = make_desc(dy_addr + kk * 256, 128, gs);
+        const uint64_t db = make_desc(a_addr + kk * 256, 128, gs);
         umma_bf16(tmem_base, da, db, idesc, (it | kk) ? 1u : 0u);
       }
       umma_commit(bar_empty + 8 * s);
     }
     umma_commit(bar_done);
   }
+  // ---- epilogue (warps 0-3 once their production is done): TMEM -> fp32 atomics into dw[N,K]
+  if (warp < 4 && my_chunks > 0) {
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int cc = 0; cc * 16 < k_valid; ++cc) {
+      float v[16];
+      tmem_ld16(t_base + cc * 16, v);
+      if (n < p.N) {
+        float* dst = p.dw + static_cast<size_t>(n) * p.K + k0 + cc * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (cc * 16 + i < k_valid) atomicAdd(dst + i, v[i]);
+      }
+    }
+    tc_fence_before();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) {
+  if (warp == kWgMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
@@ -183,7 +176,7 @@ bool pw_wgrad_tc_supported(const RowOp& dy, const RowOp& a, long long M, int K, 
   (void)dy; (void)a;
   if (dtype != EHGR_BF16) return false;
   if (K % 8 || N % 8 || K < 8 || N < 8) return false;
-  if (M < 1 || M / 128 > 0x3fffffff) return false;
+  if (M < 1) return false;
   return true;
 }
 
@@ -194,14 +187,17 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   p.BKc = tc::pick_bn(K);
   p.k_tiles = (K + p.BKc - 1) / p.BKc;
   p.n_tiles = (N + 127) / 128;
-  p.m_tiles = static_cast<int>(cdiv(M, 128));
+  p.m_chunks = cdiv(M, tc::kMS);
   const int tiles = p.n_tiles * p.k_tiles;
-  p.splits = std::max(1, std::min(p.m_tiles, kNumSMs / tiles));
+  p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>(p.m_chunks, kNumSMs / tiles)));
   int cols = 32;
   while (cols < p.BKc) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = static_cast<size_t>(tc::kWgStages) * (tc::kWgDyBytes + p.BKc * 256) + 128;
-  cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  constexpr int kBudget = 200 * 1024;
+  p.stage_bytes = (128 + p.BKc) * tc::kMS * 2;
+  p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes) / p.stage_bytes));
+  const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes;
+  cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
   tc::pw_wgrad_tc_kernel<<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
   return launch_status();
 }
