@@ -109,48 +109,44 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
   }
 }
 
+// out = rowop(a) (+ addend).  block = (bx channel vectors, P rows): a thread keeps ONE channel vector
+// (operand coefficients in registers) and strides over rows, four rows fetched per batch.
 template <typename T>
 __global__ void __launch_bounds__(256)
-row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv) {
+row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv_total) {
   constexpr int V = VecOf<T>::N;
-  constexpr int U = 4;  // vectors in flight per thread
+  constexpr int U = 4;
   using Ld = RowLoader<T, V>;
-  const long long total = M * cv;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
-    typename Ld::Raw raw[U];
-    uint4 ad[U];
-    long long off[U];
-    int c0[U];
+  const long long row_stride = static_cast<long long>(gridDim.x) * blockDim.y;
+  for (int cv = threadIdx.x; cv < cv_total; cv += blockDim.x) {
+    const int c0 = cv * V;
+    Ld ld;
+    ld.init(a, c0, C);
+    for (long long m0 = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; m0 < M; m0 += U * row_stride) {
+      typename Ld::Raw raw[U];
+      uint4 ad[U];
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const long long i = i0 + j * stride;
-      off[j] = -1;
-      if (i < total) {
-        const long long m = i / cv;
-        c0[j] = static_cast<int>(i - m * cv) * V;
-        off[j] = m * C + c0[j];
-        Ld ld;
-        ld.c0 = c0[j];
-        ld.C = C;
-        raw[j] = ld.fetch(a, m);
-        if (addend) ad[j] = *reinterpret_cast<const uint4*>(addend + off[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      if (off[j] >= 0) {
-        Ld ld;
-        ld.init(a, c0[j], C);
-        float v[V];
-        ld.finish(a, raw[j], v);
-        if (addend) {
-          float av[V];
-          load_vec<T, V>(reinterpret_cast<const T*>(&ad[j]), av);
-#pragma unroll
-          for (int k = 0; k < V; ++k) v[k] += av[k];
+      for (int j = 0; j < U; ++j) {
+        const long long m = m0 + j * row_stride;
+        if (m < M) {
+          raw[j] = ld.fetch(a, m);
+          if (addend) ad[j] = *reinterpret_cast<const uint4*>(addend + m * C + c0);
         }
-        store_vec<T, V>(out + off[j], v);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const long long m = m0 + j * row_stride;
+        if (m < M) {
+          float v[V];
+          ld.finish(a, raw[j], v);
+          if (addend) {
+            float av[V];
+            load_vec<T, V>(reinterpret_cast<const T*>(&ad[j]), av);
+#pragma unroll
+            for (int k = 0; k < V; ++k) v[k] += av[k];
+          }
+          store_vec<T, V>(out + m * C + c0, v);
+        }
       }
     }
   }
@@ -220,14 +216,16 @@ extern "C" int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out
   if (!aligned_to(out, 16) || (addend && !aligned_to(addend, 16))) return EHGR_E_ALIGN;
   if (m == 0) return EHGR_OK;
   const int cv = c / V;
-  const long long total = m * cv;
-  const long long blocks = std::min(cdiv(total, 256), 16LL * kNumSMs);
+  int bx = cv;
+  while (bx > 256) bx = (bx + 1) / 2;
+  const dim3 block(bx, std::max(1, 256 / bx));
+  const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), 8LL * kNumSMs));
   cudaStream_t s = as_stream(stream);
   if (dtype == EHGR_F32)
-    row_apply_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, s>>>(*a, static_cast<const float*>(addend),
-                                                                         static_cast<float*>(out), m, c, cv);
+    row_apply_kernel<float><<<static_cast<unsigned>(blocks), block, 0, s>>>(*a, static_cast<const float*>(addend),
+                                                                           static_cast<float*>(out), m, c, cv);
   else
-    row_apply_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+    row_apply_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), block, 0, s>>>(
         *a, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(out), m, c, cv);
   return launch_status();
 }

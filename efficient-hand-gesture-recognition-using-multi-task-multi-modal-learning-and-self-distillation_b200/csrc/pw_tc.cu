@@ -190,11 +190,17 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
             for (int j = 0; j < kBatch; ++j) {
               const int rg = (j0 + j) * f + slot / kvp;
               if (k8 < kv && rg < 16) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                if (live[j]) ld.finish(p.a, raw[j], v);
-                *reinterpret_cast<uint4*>(a_dst + rg * a_sbo + k8 * 128 + r * 16) = pack8(v);
+                uint4 packed = make_uint4(0, 0, 0, 0);
+                if (live[j]) {
+                  if (p.a.mode == EHGR_ROW_PLAIN) {
+                    packed = raw[j].a;                      // already bf16: a straight 16-byte copy
+                  } else {
+                    float v[8];
+                    ld.finish(p.a, raw[j], v);
+                    packed = pack8(v);
+                  }
+                }
+                *reinterpret_cast<uint4*>(a_dst + rg * a_sbo + k8 * 128 + r * 16) = packed;
               }
             }
           }

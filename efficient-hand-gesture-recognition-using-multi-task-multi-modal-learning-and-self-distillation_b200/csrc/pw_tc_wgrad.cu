@@ -104,17 +104,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
           const int g = g0 + j;
           if (g < total) {
             const bool is_a = g >= ng;
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = 0.f;
+            uint4 packed = make_uint4(0, 0, 0, 0);
             if (row_ok) {
-              Ld ld;
               const RowOp& op = is_a ? p.a : p.dy;
-              ld.init(op, is_a ? k0 + (g - ng) * 8 : n0 + g * 8, is_a ? p.K : p.N);
-              ld.finish(op, raw[j], f);
+              if (op.mode == EHGR_ROW_PLAIN) {
+                packed = raw[j].a;                        // already bf16: a straight 16-byte copy
+              } else {
+                Ld ld;
+                float f[8];
+                ld.init(op, is_a ? k0 + (g - ng) * 8 : n0 + g * 8, is_a ? p.K : p.N);
+                ld.finish(op, raw[j], f);
+                packed = pack8(f);
+              }
             }
             uint8_t* dst = is_a ? a_dst + (g - ng) * gs : dy_dst + g * gs;
-            *reinterpret_cast<uint4*>(dst + row_off) = pack8(f);
+            *reinterpret_cast<uint4*>(dst + row_off) = packed;
           }
         }
       }

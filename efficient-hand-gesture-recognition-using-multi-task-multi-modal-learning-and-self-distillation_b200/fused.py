@@ -369,6 +369,13 @@ class _ChainFunction(torch.autograd.Function):
                 m_in = nt * h * wd
                 need_dgrad = not (si == 0 and ui == 0 and not need_x_grad)
                 g_prev = None
+                if st.kind == 'pw' and need_dgrad:
+                    # dgrad AND wgrad both consume d(raw): evaluate the BN-backward operand once (one
+                    # streaming pass at full occupancy) so the tensor-core producers only copy bf16 rows
+                    draw = torch.empty_like(raw)
+                    _lib.call("ehgr_row_apply", ctypes.byref(dy_op), 0, draw.data_ptr(), m_out, cout, code, sp,
+                              algo_bytes=3 * m_out * cout * es)
+                    dy_op = op_plain(draw)
                 if st.kind == 'pw':
                     _lib.call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), gw.data_ptr(), m_in, cin, cout,
                               code, _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
