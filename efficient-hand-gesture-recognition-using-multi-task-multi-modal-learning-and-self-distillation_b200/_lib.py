@@ -90,8 +90,21 @@ class RowOp(ctypes.Structure):
                 ("shift_dir", ctypes.c_int32)]
 
 
+class ActionArgs(ctypes.Structure):
+    """struct ehgr_action (include/ehgr_b200.h)."""
+    _fields_ = ([(k, ctypes.c_int32) for k in ("n", "t", "h", "w", "c", "cr")] +
+                [(k, c_void_p) for k in (
+                    "shift_w", "p1_w", "p2_squeeze", "p2_conv1", "p2_expand", "p3_squeeze", "p3_conv1", "p3_expand",
+                    "bn3_scale", "bn3_shift",
+                    "mrow", "pool", "q", "qstats", "g1", "g2", "g3", "s", "u", "pi",
+                    "dg1", "dgc", "dm", "dpool", "dd", "bn3_sums", "bn3_ca", "bn3_cb", "bn3_cc",
+                    "d_shift_w", "d_p1_w", "d_p2_squeeze", "d_p2_conv1", "d_p2_expand", "d_p3_squeeze", "d_p3_conv1",
+                    "d_p3_expand")])
+
+
 _L = c_longlong
 _R = ctypes.POINTER(RowOp)
+_A = ctypes.POINTER(ActionArgs)
 
 # name -> argtypes for every int-returning symbol of include/ehgr_b200.h
 # (tests/test_abi.py cross-checks this table against the header and the built library).
@@ -114,6 +127,12 @@ SIGNATURES = {
     "ehgr_pool_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "ehgr_fc_consensus_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ehgr_fc_consensus_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ehgr_action_xs": [_A, _P, _P, _I, _P],
+    "ehgr_action_gates": [_A, _P],
+    "ehgr_action_bwd_reduce": [_A, _P, _P, _I, _P],
+    "ehgr_action_bwd_small": [_A, _P],
+    "ehgr_action_bwd_dxs": [_A, _P, _P, _P, _I, _P],
+    "ehgr_action_fir_bwd": [_A, _P, _P, _P, _P, _I, _P],
     "ehgr_mtmm_loss": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_sd_loss": [_P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _L, _I, _P],
 }

@@ -1,0 +1,658 @@
+// action.cu — K2-K6: the ACTION module (models/action.py:61-116) as fused kernels, forward and backward.
+//
+//   xs  = per-channel 3-tap temporal FIR of x (zero padded)                            (:65-73)
+//   g1  = sigmoid(conv3d_3x3x3(mean_c xs))                       [N,T,H,W]   STE      (:77-83)
+//   g2  = sigmoid(W_ex relu(conv1d_T(W_sq mean_hw xs)))          [N,T,C]     CE       (:86-96)
+//   g3  = sigmoid(W_ex3 mean_hw( dw3x3(x3)[t+1] - x3[t] )),  x3 = BN(W_sq3 xs), g3[T-1] from 0   ME (:99-113)
+//   out = net( xs * (3 + g1 + g2 + g3) )                                               (:83,96,113,115)
+//
+// The reference materialises ~25 full-size temporaries (two permute+contiguous, three x*g+x, ...).
+// Here ONE pass over x writes xs and, in the same pass, every reduction the three excitations need
+// (channel mean per pixel, spatial sum per channel, the C->C/16 squeeze q and its BatchNorm statistics),
+// one small kernel per clip turns them into the gates, and the gating itself is a row operand (GATE,
+// rowop.cuh) applied inside the A-load of the wrapped 1x1 convolution's GEMM.  Backward mirrors it:
+// one reduction pass, one per-clip kernel, one pass producing d(xs), one FIR-adjoint pass.
+// Row reductions use shared-memory staging per 16-byte channel vector and warp shuffles.
+#include "rowop.cuh"
+
+namespace ehgr {
+
+using Act = ehgr_action;
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// forward pass 1: block = one frame; thread = (channel vector cv, row lane py)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float smem[];
+  const int C = a.c, Cr = a.cr, HW = a.h * a.w, CV = C / V, P = blockDim.x / CV;
+  float* s_sq3 = smem;                         // [Cr][C]
+  float* s_row = s_sq3 + Cr * C;               // [P][Cr+1]
+  float* s_pool = s_row + P * (Cr + 1);        // [C]
+  float* s_qs = s_pool + C;                    // [2*Cr]
+  for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) s_sq3[i] = a.p3_squeeze[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_pool[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) s_qs[i] = 0.f;
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  const bool active = py < P;
+  const int c0 = cv * V;
+  const long long nt = blockIdx.x;
+  const int t = static_cast<int>(nt % a.t);
+  const bool has_prev = t > 0, has_next = t < a.t - 1;
+  float w0[V], w1[V], w2[V], pool_acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    w0[i] = a.shift_w[(c0 + i) * 3 + 0];
+    w1[i] = a.shift_w[(c0 + i) * 3 + 1];
+    w2[i] = a.shift_w[(c0 + i) * 3 + 2];
+    pool_acc[i] = 0.f;
+  }
+  float qs_sum = 0.f, qs_sq = 0.f;             // used by threads that finalise q (cv < Cr)
+  const long long frame_elems = static_cast<long long>(HW) * C;
+  for (int r0 = 0; r0 < HW; r0 += P) {
+    const int row = r0 + py;
+    const bool live = active && row < HW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * (Cr + 1); i += blockDim.x) s_row[i] = 0.f;
+    __syncthreads();
+    const long long m = nt * HW + row;
+    if (live) {
+      const T* px = x + m * C + c0;
+      float cur[V], prv[V], nxt[V], v[V];
+      load_vec<T, V>(px, cur);
+#pragma unroll
+      for (int i = 0; i < V; ++i) prv[i] = nxt[i] = 0.f;
+      if (has_prev) load_vec<T, V>(px - frame_elems, prv);
+      if (has_next) load_vec<T, V>(px + frame_elems, nxt);
+      float s8 = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        v[i] = fmaf(w0[i], prv[i], fmaf(w1[i], cur[i], w2[i] * nxt[i]));
+        s8 += v[i];
+        pool_acc[i] += v[i];
+      }
+      store_vec<T, V>(xs + m * C + c0, v);
+      atomicAdd(&s_row[py * (Cr + 1)], s8);
+      for (int j = 0; j < Cr; ++j) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < V; ++i) d = fmaf(s_sq3[j * C + c0 + i], v[i], d);
+        atomicAdd(&s_row[py * (Cr + 1) + 1 + j], d);
+      }
+    }
+    __syncthreads();
+    if (live) {
+      if (cv == 0) a.mrow[m] = s_row[py * (Cr + 1)] / static_cast<float>(C);
+      for (int j = cv; j < Cr; j += CV) {        // the row's cv threads share the Cr outputs
+        const float qv = s_row[py * (Cr + 1) + 1 + j];
+        a.q[m * Cr + j] = qv;
+        atomicAdd(&s_qs[j], qv);
+        atomicAdd(&s_qs[Cr + j], qv * qv);
+      }
+    }
+  }
+  (void)qs_sum; (void)qs_sq;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) atomicAdd(&s_pool[c0 + i], pool_acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) a.pool[nt * C + i] = s_pool[i];       // spatial SUM
+  for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) atomicAdd(&a.qstats[i], static_cast<double>(s_qs[i]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward pass 2: block = one clip: the three gates from the small reductions
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) action_gates_kernel(Act a) {
+  extern __shared__ float smem[];
+  const int C = a.c, Cr = a.cr, T = a.t, H = a.h, W = a.w, HW = H * W;
+  float* pm = smem;                 // [T][C] spatial mean
+  float* s = pm + T * C;            // [T][Cr]
+  float* r = s + T * Cr;            // [T][Cr] relu(u)
+  float* pi = r + T * Cr;           // [T][Cr]
+  const long long n = blockIdx.x;
+  const long long f0 = n * T, m0 = f0 * HW;
+  const float inv_hw = 1.f / static_cast<float>(HW);
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) pm[i] = a.pool[f0 * C + i] * inv_hw;
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) pi[i] = 0.f;
+  __syncthreads();
+  // ---- STE: 3x3x3 conv over (t,h,w) of the channel mean
+  for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
+    const int t = i / HW, p = i - t * HW, h = p / W, w = p - h * W;
+    float acc = 0.f;
+    for (int dt = -1; dt <= 1; ++dt) {
+      const int tt = t + dt;
+      if (tt < 0 || tt >= T) continue;
+      for (int dh = -1; dh <= 1; ++dh) {
+        const int hh = h + dh;
+        if (hh < 0 || hh >= H) continue;
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int ww = w + dw;
+          if (ww < 0 || ww >= W) continue;
+          acc = fmaf(a.p1_w[(dt + 1) * 9 + (dh + 1) * 3 + dw + 1], a.mrow[m0 + static_cast<long long>(tt) * HW + hh * W + ww], acc);
+        }
+      }
+    }
+    a.g1[m0 + i] = sigmoidf(acc);
+  }
+  // ---- CE: squeeze
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
+    const int t = i / Cr, j = i - t * Cr;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(a.p2_squeeze[j * C + c], pm[t * C + c], acc);
+    s[i] = acc;
+    a.s[f0 * Cr + i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
+    const int t = i / Cr, j = i - t * Cr;
+    float acc = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const int tt = t + k - 1;
+      if (tt < 0 || tt >= T) continue;
+      for (int j2 = 0; j2 < Cr; ++j2) acc = fmaf(a.p2_conv1[(j * Cr + j2) * 3 + k], s[tt * Cr + j2], acc);
+    }
+    a.u[f0 * Cr + i] = acc;
+    r[i] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  // ---- ME: pi[t][j] = mean_p( dw3x3(x3[t+1])[p] - x3[t][p] ), t < T-1  (per-lane shared atomics: any HW)
+  for (int i = threadIdx.x; i < (T - 1) * Cr * HW; i += blockDim.x) {
+    const int p = i % HW, tj = i / HW, j = tj % Cr, t = tj / Cr;
+    const int h = p / W, w = p - h * W;
+    const float sc = a.bn3_scale[j], sh = a.bn3_shift[j];
+    const float* q1 = a.q + (m0 + static_cast<long long>(t + 1) * HW) * Cr + j;
+    float acc = 0.f;
+    for (int dh = -1; dh <= 1; ++dh) {
+      const int hh = h + dh;
+      if (hh < 0 || hh >= H) continue;
+      for (int dw = -1; dw <= 1; ++dw) {
+        const int ww = w + dw;
+        if (ww < 0 || ww >= W) continue;
+        acc = fmaf(a.p3_conv1[j * 9 + (dh + 1) * 3 + dw + 1], fmaf(q1[static_cast<long long>(hh * W + ww) * Cr], sc, sh), acc);
+      }
+    }
+    acc -= fmaf(a.q[(m0 + static_cast<long long>(t) * HW + p) * Cr + j], sc, sh);
+    atomicAdd(&pi[t * Cr + j], acc * inv_hw);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) a.pi[f0 * Cr + i] = pi[i];
+  // ---- expand + sigmoid
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    float e2 = 0.f, e3 = 0.f;
+    for (int j = 0; j < Cr; ++j) {
+      e2 = fmaf(a.p2_expand[c * Cr + j], r[t * Cr + j], e2);
+      e3 = fmaf(a.p3_expand[c * Cr + j], pi[t * Cr + j], e3);
+    }
+    a.g2[f0 * C + i] = sigmoidf(e2);
+    a.g3[f0 * C + i] = sigmoidf(e3);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 1: dG = gy * xs reduced over channels (-> dg1[m]) and over pixels (-> dgc[frame][c])
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+action_bwd_reduce_kernel(Act a, const T* __restrict__ gy, const T* __restrict__ xs) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float smem[];
+  const int C = a.c, HW = a.h * a.w, CV = C / V, P = blockDim.x / CV;
+  float* s_row = smem;          // [P]
+  float* s_c = smem + P;        // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_c[i] = 0.f;
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  const bool active = py < P;
+  const int c0 = cv * V;
+  const long long nt = blockIdx.x;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  for (int r0 = 0; r0 < HW; r0 += P) {
+    const int row = r0 + py;
+    const bool live = active && row < HW;
+    __syncthreads();
+    if (threadIdx.x < P) s_row[threadIdx.x] = 0.f;
+    __syncthreads();
+    const long long m = nt * HW + row;
+    if (live) {
+      float g[V], v[V];
+      load_vec<T, V>(gy + m * C + c0, g);
+      load_vec<T, V>(xs + m * C + c0, v);
+      float s8 = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { const float d = g[i] * v[i]; s8 += d; acc[i] += d; }
+      atomicAdd(&s_row[py], s8);
+    }
+    __syncthreads();
+    if (live && cv == 0) a.dg1[m] = s_row[py];
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) atomicAdd(&s_c[c0 + i], acc[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) a.dgc[nt * C + i] = s_c[i];
+}
+
+// border-aware sum of the depthwise weights whose transposed tap lands inside the image at (h,w):
+//   d/d x3[t][h,w] of sum_p dw3x3(x3[t])[p]  =  sum over (kh,kw) with output (h-kh+1, w-kw+1) inside
+__device__ __forceinline__ float border_wsum(const float* w9, int h, int w, int H, int W) {
+  float s = 0.f;
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ho = h - kh + 1;
+    if (ho < 0 || ho >= H) continue;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int wo = w - kw + 1;
+      if (wo < 0 || wo >= W) continue;
+      s += w9[kh * 3 + kw];
+    }
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 2: block = one clip: gate backward, small parameter gradients, dm / dpool / dd,
+// BatchNorm-backward sums of the motion branch
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) action_bwd_small_kernel(Act a) {
+  extern __shared__ float smem[];
+  const int C = a.c, Cr = a.cr, T = a.t, H = a.h, W = a.w, HW = H * W;
+  float* pm = smem;                  // [T][C]
+  float* de2 = pm + T * C;           // [T][C]
+  float* de3 = de2 + T * C;          // [T][C]
+  float* sv = de3 + T * C;           // [T][Cr] squeeze output
+  float* rv = sv + T * Cr;           // [T][Cr] relu(u)
+  float* du = rv + T * Cr;           // [T][Cr]
+  float* ds = du + T * Cr;           // [T][Cr]
+  float* dd = ds + T * Cr;           // [T][Cr]
+  float* acc27 = dd + T * Cr;        // [27]
+  float* acc9 = acc27 + 27;          // [Cr][9]
+  float* bsum = acc9 + Cr * 9;       // [2*Cr]
+  const long long n = blockIdx.x;
+  const long long f0 = n * T, m0 = f0 * HW;
+  const float inv_hw = 1.f / static_cast<float>(HW);
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    pm[i] = a.pool[f0 * C + i] * inv_hw;
+    const float g2 = a.g2[f0 * C + i], g3 = a.g3[f0 * C + i], d = a.dgc[f0 * C + i];
+    de2[i] = d * g2 * (1.f - g2);
+    de3[i] = d * g3 * (1.f - g3);
+  }
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
+    sv[i] = a.s[f0 * Cr + i];
+    rv[i] = fmaxf(a.u[f0 * Cr + i], 0.f);
+  }
+  for (int i = threadIdx.x; i < 27 + Cr * 9 + 2 * Cr; i += blockDim.x) acc27[i] = 0.f;
+  __syncthreads();
+  // ---- STE: da1 = dg1 * g1 (1 - g1) (in place in dg1), then dm = conv3d^T(da1), dW_p1 = corr(mrow, da1)
+  for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
+    const float g = a.g1[m0 + i];
+    a.dg1[m0 + i] *= g * (1.f - g);
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
+    const int t = i / HW, p = i - t * HW, h = p / W, w = p - h * W;
+    float acc = 0.f;
+    for (int dt = -1; dt <= 1; ++dt) {
+      const int tt = t - dt;                       // output position that used this input with tap dt
+      if (tt < 0 || tt >= T) continue;
+      for (int dh = -1; dh <= 1; ++dh) {
+        const int hh = h - dh;
+        if (hh < 0 || hh >= H) continue;
+        for (int dw = -1; dw <= 1; ++dw) {
+          const int ww = w - dw;
+          if (ww < 0 || ww >= W) continue;
+          acc = fmaf(a.p1_w[(dt + 1) * 9 + (dh + 1) * 3 + dw + 1], a.dg1[m0 + static_cast<long long>(tt) * HW + hh * W + ww], acc);
+        }
+      }
+    }
+    a.dm[m0 + i] = acc;
+  }
+  for (int tap = 0; tap < 27; ++tap) {
+    const int dt = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
+      const int t = i / HW, p = i - t * HW, h = p / W, w = p - h * W;
+      const int tt = t + dt, hh = h + dh, ww = w + dw;
+      if (tt < 0 || tt >= T || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      acc = fmaf(a.dg1[m0 + i], a.mrow[m0 + static_cast<long long>(tt) * HW + hh * W + ww], acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&acc27[tap], acc);
+  }
+  // ---- CE backward
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
+    const int t = i / Cr, j = i - t * Cr;
+    float dr = 0.f;
+    for (int c = 0; c < C; ++c) dr = fmaf(a.p2_expand[c * Cr + j], de2[t * C + c], dr);
+    du[i] = a.u[f0 * Cr + i] > 0.f ? dr : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
+    const int t = i / Cr, j2 = i - t * Cr;          // ds[t][j2] = sum_{j,k} w[j][j2][k] du[t-k+1][j]
+    float acc = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const int tt = t - k + 1;
+      if (tt < 0 || tt >= T) continue;
+      for (int j = 0; j < Cr; ++j) acc = fmaf(a.p2_conv1[(j * Cr + j2) * 3 + k], du[tt * Cr + j], acc);
+    }
+    ds[i] = acc;
+  }
+  // ---- ME: d pi, dd
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
+    const int t = i / Cr, j = i - t * Cr;
+    float dpi = 0.f;
+    if (t < T - 1)
+      for (int c = 0; c < C; ++c) dpi = fmaf(a.p3_expand[c * Cr + j], de3[t * C + c], dpi);
+    dd[i] = dpi * inv_hw;
+    a.dd[f0 * Cr + i] = dd[i];
+  }
+  __syncthreads();
+  // parameter gradients of the tiny layers (one atomic per element per clip)
+  for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {
+    const int c = i / Cr, j = i - c * Cr;
+    float g2 = 0.f, g3 = 0.f, gs = 0.f;
+    for (int t = 0; t < T; ++t) {
+      g2 = fmaf(de2[t * C + c], rv[t * Cr + j], g2);
+      g3 = fmaf(de3[t * C + c], a.pi[(f0 + t) * Cr + j], g3);
+      gs = fmaf(ds[t * Cr + j], pm[t * C + c], gs);
+    }
+    atomicAdd(&a.d_p2_expand[c * Cr + j], g2);
+    atomicAdd(&a.d_p3_expand[c * Cr + j], g3);
+    atomicAdd(&a.d_p2_squeeze[j * C + c], gs);
+  }
+  for (int i = threadIdx.x; i < Cr * Cr * 3; i += blockDim.x) {
+    const int k = i % 3, j2 = (i / 3) % Cr, j = i / (3 * Cr);
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int tt = t + k - 1;
+      if (tt < 0 || tt >= T) continue;
+      acc = fmaf(du[t * Cr + j], sv[tt * Cr + j2], acc);
+    }
+    atomicAdd(&a.d_p2_conv1[i], acc);
+  }
+  // dpool[t][c] = sum_j W_sq[j][c] ds[t][j]   (gradient w.r.t. the spatial MEAN)
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    float acc = 0.f;
+    for (int j = 0; j < Cr; ++j) acc = fmaf(a.p2_squeeze[j * C + c], ds[t * Cr + j], acc);
+    a.dpool[f0 * C + i] = acc;
+  }
+  // ---- ME: depthwise-conv weight gradient and the BatchNorm-backward sums of x3's gradient
+  //   dx3[t][p][j] = -dd[t][j] + dd[t-1][j] * border_wsum(p)      (dd[-1] = dd[T-1] = 0)
+  for (int i = threadIdx.x; i < T * Cr * HW; i += blockDim.x) {
+    const int p = i % HW, tj = i / HW, j = tj % Cr, t = tj / Cr;
+    const int h = p / W, w = p - h * W;
+    const float qv = a.q[(m0 + static_cast<long long>(t) * HW + p) * Cr + j];
+    const float ddp = t > 0 ? dd[(t - 1) * Cr + j] : 0.f;
+    const float dx3 = -dd[t * Cr + j] + ddp * border_wsum(a.p3_conv1 + j * 9, h, w, H, W);
+    atomicAdd(&bsum[j], dx3);
+    atomicAdd(&bsum[Cr + j], dx3 * qv);
+    if (t > 0 && ddp != 0.f) {
+      // dW3[j][kh][kw] += dd[t-1][j] * x3[t][h+kh-1, w+kw-1] summed over output positions p=(h,w)
+      const float sc = a.bn3_scale[j], sh = a.bn3_shift[j];
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        if (hh < 0 || hh >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = w + kw - 1;
+          if (ww < 0 || ww >= W) continue;
+          const float x3 = fmaf(a.q[(m0 + static_cast<long long>(t) * HW + hh * W + ww) * Cr + j], sc, sh);
+          atomicAdd(&acc9[j * 9 + kh * 3 + kw], ddp * x3);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27; i += blockDim.x) atomicAdd(&a.d_p1_w[i], acc27[i]);
+  for (int i = threadIdx.x; i < Cr * 9; i += blockDim.x) atomicAdd(&a.d_p3_conv1[i], acc9[i]);
+  for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) atomicAdd(&a.bn3_sums[i], static_cast<double>(bsum[i]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 3: dxs = gy*G + dm/C + dpool/HW + W_sq3^T dq,  dq = BN3-backward(dx3);  dW_sq3 += dq xs^T
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CRMAX>
+__global__ void __launch_bounds__(256)
+action_bwd_dxs_kernel(Act a, const T* __restrict__ gy, const T* __restrict__ xs, T* __restrict__ dxs) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float smem[];
+  const int C = a.c, Cr = a.cr, H = a.h, W = a.w, HW = H * W, CV = C / V, P = blockDim.x / CV;
+  float* s_sq3 = smem;                 // [Cr][C]
+  float* s_dsq = s_sq3 + Cr * C;       // [Cr][C]
+  float* s_dq = s_dsq + Cr * C;        // [P][Cr]
+  for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) { s_sq3[i] = a.p3_squeeze[i]; s_dsq[i] = 0.f; }
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  const bool active = py < P;
+  const int c0 = cv * V;
+  const long long nt = blockIdx.x;
+  const int t = static_cast<int>(nt % a.t);
+  const float inv_c = 1.f / static_cast<float>(C), inv_hw = 1.f / static_cast<float>(HW);
+  float g23[V], dpl[V], dacc[CRMAX][V];
+  if (active) {
+    float g2[V], g3[V];
+    load_vec<float, V>(a.g2 + nt * C + c0, g2);
+    load_vec<float, V>(a.g3 + nt * C + c0, g3);
+    load_vec<float, V>(a.dpool + nt * C + c0, dpl);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { g23[i] = 3.f + g2[i] + g3[i]; dpl[i] *= inv_hw; }
+  }
+#pragma unroll
+  for (int j = 0; j < CRMAX; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) dacc[j][i] = 0.f;
+  for (int r0 = 0; r0 < HW; r0 += P) {
+    const int row = r0 + py;
+    const bool live = active && row < HW;
+    const long long m = nt * HW + row;
+    __syncthreads();
+    // dq for the P rows of this iteration (threads cv < Cr of each row)
+    if (live) {
+      const int h = row / W, w = row - h * W;
+      for (int j = cv; j < Cr; j += CV) {
+        const float ddc = a.dd[nt * Cr + j];
+        const float ddp = t > 0 ? a.dd[(nt - 1) * Cr + j] : 0.f;
+        const float dx3 = -ddc + ddp * border_wsum(a.p3_conv1 + j * 9, h, w, H, W);
+        s_dq[py * Cr + j] = fmaf(a.bn3_ca[j], dx3, fmaf(a.bn3_cb[j], a.q[m * Cr + j], a.bn3_cc[j]));
+      }
+    }
+    __syncthreads();
+    if (live) {
+      float g[V], v[V], o[V];
+      load_vec<T, V>(gy + m * C + c0, g);
+      load_vec<T, V>(xs + m * C + c0, v);
+      const float g1 = a.g1[m], dmv = a.dm[m] * inv_c;
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = fmaf(g[i], g23[i] + g1, dmv + dpl[i]);
+#pragma unroll
+      for (int j = 0; j < CRMAX; ++j) {
+        if (j < Cr) {
+          const float dq = s_dq[py * Cr + j];
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            o[i] = fmaf(dq, s_sq3[j * C + c0 + i], o[i]);
+            dacc[j][i] = fmaf(dq, v[i], dacc[j][i]);
+          }
+        }
+      }
+      store_vec<T, V>(dxs + m * C + c0, o);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < CRMAX; ++j)
+      if (j < Cr)
+#pragma unroll
+        for (int i = 0; i < V; ++i) atomicAdd(&s_dsq[j * C + c0 + i], dacc[j][i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) atomicAdd(&a.d_p3_squeeze[i], s_dsq[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 4: adjoint of the temporal FIR (+ residual gradient) and its weight gradient
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+action_fir_bwd_kernel(Act a, const T* __restrict__ dxs, const T* __restrict__ x, const T* __restrict__ addend,
+                      T* __restrict__ dx) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float smem[];   // [C][3]
+  const int C = a.c, HW = a.h * a.w, CV = C / V, P = blockDim.x / CV;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) smem[i] = 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x % CV, py = threadIdx.x / CV;
+  const bool active = py < P;
+  const int c0 = cv * V;
+  const long long nt = blockIdx.x;
+  const int t = static_cast<int>(nt % a.t);
+  const bool has_prev = t > 0, has_next = t < a.t - 1;
+  float w0[V], w1[V], w2[V], a0[V], a1[V], a2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    w0[i] = a.shift_w[(c0 + i) * 3 + 0];
+    w1[i] = a.shift_w[(c0 + i) * 3 + 1];
+    w2[i] = a.shift_w[(c0 + i) * 3 + 2];
+    a0[i] = a1[i] = a2[i] = 0.f;
+  }
+  const long long fe = static_cast<long long>(HW) * C;
+  if (active) {
+    for (int row = py; row < HW; row += P) {
+      const long long off = (nt * HW + row) * C + c0;
+      float dc[V], dp[V], dn[V], xc[V], xp[V], xn[V], o[V];
+      load_vec<T, V>(dxs + off, dc);
+      load_vec<T, V>(x + off, xc);
+#pragma unroll
+      for (int i = 0; i < V; ++i) dp[i] = dn[i] = xp[i] = xn[i] = 0.f;
+      if (has_prev) { load_vec<T, V>(dxs + off - fe, dp); load_vec<T, V>(x + off - fe, xp); }
+      if (has_next) { load_vec<T, V>(dxs + off + fe, dn); load_vec<T, V>(x + off + fe, xn); }
+      // xs[t] = w0 x[t-1] + w1 x[t] + w2 x[t+1]  =>  dx[t] = w0 dxs[t+1] + w1 dxs[t] + w2 dxs[t-1]
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        o[i] = fmaf(w0[i], dn[i], fmaf(w1[i], dc[i], w2[i] * dp[i]));
+        a0[i] = fmaf(dc[i], xp[i], a0[i]);
+        a1[i] = fmaf(dc[i], xc[i], a1[i]);
+        a2[i] = fmaf(dc[i], xn[i], a2[i]);
+      }
+      if (addend) {
+        float ad[V];
+        load_vec<T, V>(addend + off, ad);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] += ad[i];
+      }
+      store_vec<T, V>(dx + off, o);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      atomicAdd(&smem[(c0 + i) * 3 + 0], a0[i]);
+      atomicAdd(&smem[(c0 + i) * 3 + 1], a1[i]);
+      atomicAdd(&smem[(c0 + i) * 3 + 2], a2[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(&a.d_shift_w[i], smem[i]);
+}
+
+static int act_check(const Act* a, int dtype) {
+  const int es = esize_of(dtype);
+  if (es == 0) return EHGR_E_DTYPE;
+  if (!a) return EHGR_E_NULL;
+  const int V = 16 / es;
+  if (a->n <= 0 || a->t <= 0 || a->h <= 0 || a->w <= 0 || a->c <= 0 || a->cr <= 0 || (a->c % V)) return EHGR_E_SHAPE;
+  if (a->c / V > 256 || a->cr > 16) return EHGR_E_UNSUPPORTED;
+  return EHGR_OK;
+}
+
+}  // namespace ehgr
+
+using namespace ehgr;
+
+extern "C" int ehgr_action_xs(const ehgr_action* a, const void* x, void* xs, int dtype, ehgr_stream_t stream) {
+  if (int st = act_check(a, dtype)) return st;
+  if (!x || !xs || !a->shift_w || !a->p3_squeeze || !a->mrow || !a->pool || !a->q || !a->qstats) return EHGR_E_NULL;
+  const int V = 16 / esize_of(dtype), CV = a->c / V, P = 256 / CV;
+  const size_t smem = (static_cast<size_t>(a->cr) * a->c + static_cast<size_t>(P) * (a->cr + 1) + a->c + 2 * a->cr) * sizeof(float);
+  const unsigned grid = static_cast<unsigned>(a->n) * a->t;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_F32) action_xs_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(x), static_cast<float*>(xs));
+  else action_xs_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xs));
+  return launch_status();
+}
+
+extern "C" int ehgr_action_gates(const ehgr_action* a, ehgr_stream_t stream) {
+  if (int st = act_check(a, EHGR_F32)) return st;
+  if (!a->mrow || !a->pool || !a->q || !a->bn3_scale || !a->bn3_shift || !a->g1 || !a->g2 || !a->g3 || !a->s || !a->u || !a->pi)
+    return EHGR_E_NULL;
+  const size_t smem = (static_cast<size_t>(a->t) * a->c + 3 * static_cast<size_t>(a->t) * a->cr) * sizeof(float);
+  action_gates_kernel<<<a->n, 256, smem, as_stream(stream)>>>(*a);
+  return launch_status();
+}
+
+extern "C" int ehgr_action_bwd_reduce(const ehgr_action* a, const void* gy, const void* xs, int dtype,
+                                      ehgr_stream_t stream) {
+  if (int st = act_check(a, dtype)) return st;
+  if (!gy || !xs || !a->dg1 || !a->dgc) return EHGR_E_NULL;
+  const int V = 16 / esize_of(dtype), CV = a->c / V, P = 256 / CV;
+  const size_t smem = (static_cast<size_t>(P) + a->c) * sizeof(float);
+  const unsigned grid = static_cast<unsigned>(a->n) * a->t;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_F32)
+    action_bwd_reduce_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(gy), static_cast<const float*>(xs));
+  else
+    action_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(gy),
+                                                                    static_cast<const __nv_bfloat16*>(xs));
+  return launch_status();
+}
+
+extern "C" int ehgr_action_bwd_small(const ehgr_action* a, ehgr_stream_t stream) {
+  if (int st = act_check(a, EHGR_F32)) return st;
+  if (!a->dg1 || !a->dgc || !a->dm || !a->dpool || !a->dd || !a->bn3_sums || !a->d_p1_w || !a->d_p2_squeeze ||
+      !a->d_p2_conv1 || !a->d_p2_expand || !a->d_p3_conv1 || !a->d_p3_expand)
+    return EHGR_E_NULL;
+  const size_t smem = (3 * static_cast<size_t>(a->t) * a->c + 5 * static_cast<size_t>(a->t) * a->cr + 27 + 11 * a->cr) * sizeof(float);
+  action_bwd_small_kernel<<<a->n, 256, smem, as_stream(stream)>>>(*a);
+  return launch_status();
+}
+
+extern "C" int ehgr_action_bwd_dxs(const ehgr_action* a, const void* gy, const void* xs, void* dxs, int dtype,
+                                   ehgr_stream_t stream) {
+  if (int st = act_check(a, dtype)) return st;
+  if (!gy || !xs || !dxs || !a->bn3_ca || !a->bn3_cb || !a->bn3_cc || !a->d_p3_squeeze) return EHGR_E_NULL;
+  const int V = 16 / esize_of(dtype), CV = a->c / V, P = 256 / CV;
+  const size_t smem = (2 * static_cast<size_t>(a->cr) * a->c + static_cast<size_t>(P) * a->cr) * sizeof(float);
+  const unsigned grid = static_cast<unsigned>(a->n) * a->t;
+  cudaStream_t s = as_stream(stream);
+#define EHGR_DXS(TT, CRM) action_bwd_dxs_kernel<TT, CRM><<<grid, 256, smem, s>>>(*a, static_cast<const TT*>(gy), static_cast<const TT*>(xs), static_cast<TT*>(dxs))
+  if (dtype == EHGR_F32) {
+    if (a->cr <= 4) EHGR_DXS(float, 4); else if (a->cr <= 10) EHGR_DXS(float, 10); else EHGR_DXS(float, 16);
+  } else {
+    if (a->cr <= 4) EHGR_DXS(__nv_bfloat16, 4); else if (a->cr <= 10) EHGR_DXS(__nv_bfloat16, 10); else EHGR_DXS(__nv_bfloat16, 16);
+  }
+#undef EHGR_DXS
+  return launch_status();
+}
+
+extern "C" int ehgr_action_fir_bwd(const ehgr_action* a, const void* dxs, const void* x, const void* addend, void* dx,
+                                   int dtype, ehgr_stream_t stream) {
+  if (int st = act_check(a, dtype)) return st;
+  if (!dxs || !x || !dx || !a->d_shift_w) return EHGR_E_NULL;
+  const size_t smem = 3 * static_cast<size_t>(a->c) * sizeof(float);
+  const unsigned grid = static_cast<unsigned>(a->n) * a->t;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_F32)
+    action_fir_bwd_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(dxs), static_cast<const float*>(x),
+                                                         static_cast<const float*>(addend), static_cast<float*>(dx));
+  else
+    action_fir_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(dxs),
+                                                                 static_cast<const __nv_bfloat16*>(x),
+                                                                 static_cast<const __nv_bfloat16*>(addend),
+                                                                 static_cast<__nv_bfloat16*>(dx));
+  return launch_status();
+}

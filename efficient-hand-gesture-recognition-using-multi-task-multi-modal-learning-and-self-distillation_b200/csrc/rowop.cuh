@@ -149,6 +149,15 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
         v[i] = k == 0 ? a[i] : (k == 1 ? b[i] : c[i]);
       }
     }
+  } else if (op.mode == EHGR_ROW_GATE) {
+    load_vec<T, NV>(in1 + off, v);
+    const long long f = m / op.hw;
+    const float g1 = static_cast<const float*>(op.in2)[m];
+    float g2[NV], g3[NV];
+    load_vec<float, NV>(op.scale + f * C + c0, g2);
+    load_vec<float, NV>(op.shift + f * C + c0, g3);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] *= (3.f + g1) + (g2[i] + g3[i]);
   } else {  // EHGR_ROW_BNBWD
     float g[NV], r[NV], ca[NV], cb[NV], cc[NV];
     load_vec<T, NV>(in1 + off, g);
@@ -236,7 +245,7 @@ struct RowLoader {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[kTwo ? i : 0], g[i], fmaf(cb[kTwo ? i : 0], r[i], cc[kTwo ? i : 0]));
     } else {
-      load_row<T, NV>(op, m, c0, C, v);  // SHIFT: no per-channel coefficients
+      load_row<T, NV>(op, m, c0, C, v);  // SHIFT / GATE: no per-channel coefficients held in registers
     }
   }
 
@@ -271,6 +280,10 @@ struct RowLoader {
       }
     } else {
       r.a = *reinterpret_cast<const uint4*>(in1 + off);
+      if (op.mode == EHGR_ROW_GATE) {   // finish() needs the row index for the per-row / per-frame gates
+        r.b[0].x = static_cast<uint32_t>(m & 0xffffffffLL);
+        r.b[0].y = static_cast<uint32_t>(m >> 32);
+      }
       if constexpr (kTwo) {
         if (op.mode == EHGR_ROW_BNBWD) r.b[0] = *reinterpret_cast<const uint4*>(static_cast<const T*>(op.in2) + off);
       }
@@ -288,6 +301,15 @@ struct RowLoader {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
       }
+    } else if (op.mode == EHGR_ROW_GATE) {
+      const long long m = static_cast<long long>(r.b[0].x) | (static_cast<long long>(r.b[0].y) << 32);
+      const long long f = m / op.hw;
+      const float g1 = static_cast<const float*>(op.in2)[m];
+      float g2[NV], g3[NV];
+      load_vec<float, NV>(op.scale + f * C + c0, g2);
+      load_vec<float, NV>(op.shift + f * C + c0, g3);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] *= (3.f + g1) + (g2[i] + g3[i]);
     } else if (kTwo && op.mode == EHGR_ROW_BNBWD) {
       float raw[NV];
       load_vec<T, NV>(reinterpret_cast<const T*>(&r.b[0]), raw);
@@ -312,6 +334,8 @@ inline int validate_rowop(const RowOp* op, int es) {
     case EHGR_ROW_AFFINE: return (op->scale && op->shift) ? EHGR_OK : EHGR_E_NULL;
     case EHGR_ROW_SHIFT:
       return (op->n_segment > 0 && op->hw > 0 && op->fold >= 0) ? EHGR_OK : EHGR_E_SHAPE;
+    case EHGR_ROW_GATE:
+      return (op->in2 && op->scale && op->shift && op->hw > 0) ? EHGR_OK : EHGR_E_NULL;
     case EHGR_ROW_BNBWD:
       if (!op->in2 || !op->ca || !op->cb || !op->cc) return EHGR_E_NULL;
       if (op->relu6 && (!op->scale || !op->shift)) return EHGR_E_NULL;

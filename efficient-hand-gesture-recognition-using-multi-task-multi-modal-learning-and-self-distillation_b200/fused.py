@@ -24,7 +24,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, action_ops
 from ._lib import RowOp
 
 _STATE = {"dtype": torch.float32, "engine": 0}
@@ -113,6 +113,10 @@ class Stage:
     relu6: bool
     stride: int = 1
     shift: Optional[Tuple[int, int]] = None   # (n_segment, fold) — TemporalShift on the input (pw only)
+    action: Optional[nn.Module] = None        # Action module wrapping this conv (pw only, first stage of a unit)
+
+    def n_params(self) -> int:
+        return 3 + (10 if self.action is not None else 0)
 
 
 @dataclass
@@ -142,9 +146,11 @@ def unit_of_block(block) -> Unit:
         if isinstance(first, TemporalShift):
             shift = (first.n_segment, first.net.in_channels // first.fold_div)
             first = first.net
-        elif isinstance(first, Action):
-            raise NotImplementedError("Action blocks run through action_forward")
+        action = None
+        if isinstance(first, Action):
+            action, first = first, first.net
         stages.append(_conv_bn_stage('pw', first, conv[1], True, shift))
+        stages[-1].action = action
         k = 3
     stages.append(_conv_bn_stage('dw', conv[k], conv[k + 1], True))
     stages.append(_conv_bn_stage('pw', conv[k + 3], conv[k + 4], False))
@@ -244,11 +250,17 @@ class _ChainFunction(torch.autograd.Function):
             recs = []
             for st in u.stages:
                 w, gamma, beta = params[p_i], params[p_i + 1], params[p_i + 2]
-                p_i += 3
+                act_params = params[p_i + 3:p_i + st.n_params()]
+                p_i += st.n_params()
                 nt, h, wd, cin = geom
                 cout = st.conv.out_channels
+                act_state = None
                 if st.kind == 'stem':
                     a_op = None
+                elif st.action is not None:
+                    if lazy is not None:
+                        raise NotImplementedError("Action is defined on a block input")
+                    act_state, a_op = action_ops.forward_gates(st.action, cur_final, act_params, dt)
                 elif lazy is None:
                     a_op = (op_shift(cur_final, st.shift[0], st.shift[1], h * wd, 1) if st.shift is not None
                             else op_plain(cur_final))
@@ -272,7 +284,7 @@ class _ChainFunction(torch.autograd.Function):
                           vec[2].data_ptr(), vec[3].data_ptr(), cout, sp)
                 if tr and st.bn.num_batches_tracked is not None:
                     nbt.append(st.bn.num_batches_tracked)
-                recs.append((raw, vec, geom, tr))
+                recs.append((raw, vec, geom, tr, act_state))
                 lazy = (raw, vec[0], vec[1], st.relu6)
                 geom = (nt, ho, wo, cout)
             # materialise the unit output: BN(+ReLU6) (+ residual)
@@ -333,16 +345,21 @@ class _ChainFunction(torch.autograd.Function):
             if g is None:
                 raise RuntimeError("chain backward reached a unit without an incoming gradient")
             g_unit_out = g
-            p_begin = p_end - 3 * len(u.stages)
+            p_begin = p_end - sum(st_.n_params() for st_ in u.stages)
+            p_off = [p_begin]
+            for st_ in u.stages[:-1]:
+                p_off.append(p_off[-1] + st_.n_params())
+            unit_grad_done = False
             for si in range(len(u.stages) - 1, -1, -1):
                 st = u.stages[si]
-                raw, vec, geom, tr = recs[si]
+                raw, vec, geom, tr, act_state = recs[si]
                 nt, h, wd, cin = geom
                 cout = st.conv.out_channels
                 ho, wo = raw.shape[2], raw.shape[3]
                 m_out = nt * ho * wo
-                w, gamma = params[p_begin + 3 * si], params[p_begin + 3 * si + 1]
-                gw, ggam, gbet = gviews[p_begin + 3 * si], gviews[p_begin + 3 * si + 1], gviews[p_begin + 3 * si + 2]
+                pb = p_off[si]
+                w, gamma = params[pb], params[pb + 1]
+                gw, ggam, gbet = gviews[pb], gviews[pb + 1], gviews[pb + 2]
                 sums = sum_arena[s_off:s_off + 2 * cout]
                 s_off += 2 * cout
                 coef = coef_arena[c_off:c_off + 3 * cout].view(3, cout)
@@ -361,7 +378,9 @@ class _ChainFunction(torch.autograd.Function):
                     g = None
                     continue
                 # forward operand of this stage, re-derived from what was saved
-                if si == 0:
+                if act_state is not None:
+                    a_op = action_ops.gate_op(act_state)
+                elif si == 0:
                     a_op = (op_shift(unit_in, st.shift[0], st.shift[1], h * wd, 1) if st.shift is not None
                             else op_plain(unit_in))
                 else:
@@ -383,7 +402,7 @@ class _ChainFunction(torch.autograd.Function):
                     if need_dgrad:
                         g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
                         # residual units without a shift: fold "+ g_unit_out" into the dgrad epilogue
-                        fuse_res = si == 0 and u.residual and st.shift is None
+                        fuse_res = si == 0 and u.residual and st.shift is None and act_state is None
                         _lib.call("ehgr_pw_gemm", ctypes.byref(dy_op), w.data_ptr(), 1, g_prev.data_ptr(),
                                   g_unit_out.data_ptr() if fuse_res else 0, 0, m_in, cout, cin, code,
                                   _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
@@ -396,9 +415,14 @@ class _ChainFunction(torch.autograd.Function):
                               gw.data_ptr(), nt, h, wd, cin, st.stride, code, sp,
                               algo_bytes=(2 * m_out + 2 * m_in) * cin * es, algo_flops=18 * (m_out + m_in) * cin)
                 g = g_prev
+                if act_state is not None and g is not None:
+                    # g is d(loss)/d(gated input): run the ACTION backward (adds the residual gradient)
+                    g = action_ops.backward(act_state, params[pb + 3:pb + 13], gviews[pb + 3:pb + 13], g, unit_in,
+                                            g_unit_out if u.residual else None)
+                    unit_grad_done = True
             # gradient w.r.t. the unit input: undo the shift, add the residual branch
             st0 = u.stages[0]
-            if g is not None and st0.kind != 'stem':
+            if g is not None and st0.kind != 'stem' and not unit_grad_done:
                 nt, h, wd, cin = unit_geom
                 if st0.shift is not None:
                     gx = torch.empty_like(g)
@@ -424,6 +448,8 @@ def _chain_params(units):
     for u in units:
         for s in u.stages:
             ps += [s.conv.weight, s.bn.weight, s.bn.bias]
+            if s.action is not None:
+                ps += action_ops.action_params(s.action)
     return ps
 
 
@@ -437,9 +463,6 @@ def run_chain(units: List[Unit], x):
 def inverted_residual(m, x):
     """InvertedResidual.forward (archs/mobilenet_v2.py:62-66) as a one-unit chain."""
     _lib.require_cuda(x)
-    from .action import Action
-    if len(m.conv) == 8 and isinstance(m.conv[0], Action):
-        return _inverted_residual_library(m, x)
     return run_chain([unit_of_block(m)], x)[0]
 
 
@@ -447,8 +470,6 @@ def mobilenet_v2_features(model, x, taps: Sequence[int] = ()):
     """features[0..18] -> [NT, 1280, H/32, W/32] (NHWC strides).  With ``taps`` returns a tuple: the
     outputs of the listed feature indices (ascending) followed by the final map."""
     _lib.require_cuda(x)
-    if _has_action(model):
-        return _features_library(model, x, taps)
     outs = run_chain(units_of_backbone(model, taps), x)
     return outs[0] if not taps else outs
 
@@ -539,51 +560,14 @@ def classifier_head(tsn, fmap):
 
 
 # ------------------------------------------------------------------------------------------------
-# ACTION (bring-up state: excitation arithmetic on library ops; fused kernels pending)
+# stand-alone ACTION module (inside an InvertedResidual the chain fuses the gating into the GEMM A-load)
 # ------------------------------------------------------------------------------------------------
 def action_forward(m, x):
-    """out = net(x_shift * (3 + g_STE + g_CE + g_ME)) — reference models/action.py:61-116."""
-    import torch.nn.functional as F
+    """out = net(x_shift * (3 + g_STE + g_CE + g_ME)) — reference models/action.py:61-116.  The gated tensor
+    comes from the fused kernels (csrc/action.cu); ``m.net`` is whatever module was wrapped."""
     _lib.require_cuda(x)
-    nt, c, h, w = x.shape
-    T = m.n_segment
-    n = nt // T
-    x5 = x.reshape(n, T, c, h, w)
-    wt = m.action_shift.weight.view(c, 3)
-    xp = F.pad(x5, (0, 0, 0, 0, 0, 0, 1, 1))
-    xs = (xp[:, :-2] * wt[:, 0].view(1, 1, c, 1, 1) + xp[:, 1:-1] * wt[:, 1].view(1, 1, c, 1, 1)
-          + xp[:, 2:] * wt[:, 2].view(1, 1, c, 1, 1))
-    g1 = torch.sigmoid(m.action_p1_conv1(xs.mean(2, keepdim=True).transpose(1, 2))).transpose(1, 2)
-    p = xs.mean((3, 4))
-    s = F.conv2d(p.reshape(nt, c, 1, 1), m.action_p2_squeeze.weight).view(n, T, -1).transpose(1, 2)
-    s = F.relu(m.action_p2_conv1(s)).transpose(1, 2).reshape(nt, -1, 1, 1)
-    g2 = torch.sigmoid(F.conv2d(s, m.action_p2_expand.weight)).view(n, T, c, 1, 1)
-    x3 = m.action_p3_bn1(m.action_p3_squeeze(xs.reshape(nt, c, h, w)))
-    cr = x3.shape[1]
-    c3 = m.action_p3_conv1(x3).view(n, T, cr, h, w)
-    x3 = x3.view(n, T, cr, h, w)
-    d = F.pad(c3[:, 1:] - x3[:, :-1], (0, 0, 0, 0, 0, 0, 0, 1))
-    g3 = torch.sigmoid(F.conv2d(d.mean((3, 4)).reshape(nt, cr, 1, 1), m.action_p3_expand.weight)).view(n, T, c, 1, 1)
-    y = xs * (3.0 + g1 + g2 + g3)
-    return m.net(y.reshape(nt, c, h, w))
-
-
-def _inverted_residual_library(m, x):
-    y = m.conv(x)
-    return x + y if m.use_res_connect else y
-
-
-def _features_library(model, x, taps):
-    from .action import Action
-    outs = []
-    last = len(model.features) - 1
-    for i, f in enumerate(model.features):
-        if i == 0 or i == last:
-            x = f(x)
-        elif len(f.conv) == 8 and isinstance(f.conv[0], Action):
-            x = _inverted_residual_library(f, x)
-        else:
-            x = f(x)
-        if i in taps:
-            outs.append(x)
-    return x if not taps else tuple(outs + ([] if last in taps else [x]))
+    dt = _STATE["dtype"]
+    y = action_ops.gated(m, x, dt)
+    if y.dtype != x.dtype and not torch.is_autocast_enabled():
+        y = y.to(x.dtype)
+    return m.net(y)

@@ -75,7 +75,7 @@ int ehgr_temporal_shift_bwd(const void* grad_out, void* grad_in, int n_batch, in
  * and the BatchNorm-backward combination are applied while loading (csrc/rowop.cuh).  HOST struct,
  * copied into the kernel's parameters; all pointers inside are device pointers.
  * ------------------------------------------------------------------------------------------- */
-enum { EHGR_ROW_PLAIN = 0, EHGR_ROW_AFFINE = 1, EHGR_ROW_SHIFT = 2, EHGR_ROW_BNBWD = 3 };
+enum { EHGR_ROW_PLAIN = 0, EHGR_ROW_AFFINE = 1, EHGR_ROW_SHIFT = 2, EHGR_ROW_BNBWD = 3, EHGR_ROW_GATE = 4 };
 
 typedef struct ehgr_rowop {
   int32_t mode;        /* EHGR_ROW_* */
@@ -91,6 +91,8 @@ typedef struct ehgr_rowop {
   int32_t fold;        /* SHIFT: shifted channels per direction */
   int32_t hw;          /* SHIFT: rows per frame (H*W) */
   int32_t shift_dir;   /* SHIFT: +1 forward shift, -1 its adjoint */
+  /* GATE (ACTION, models/action.py:83,96,113,115): v = in1 * (3 + g1[m] + g2[m/hw, c] + g3[m/hw, c]) with
+   * in2 = g1 (fp32 [M]), scale = g2, shift = g3 (fp32 [frames, C]) and hw = rows per frame. */
 } ehgr_rowop;
 
 enum { EHGR_ENGINE_AUTO = 0, EHGR_ENGINE_SIMT = 1, EHGR_ENGINE_TCGEN05 = 2 };
@@ -209,6 +211,71 @@ int ehgr_mtmm_loss(const float* logits, const long long* labels, const void* pre
 int ehgr_sd_loss(const float* const* logits, const float* const* feats, const long long* labels, float alpha,
                  float beta, float temperature, float* terms_out, float* const* dlogits, float* const* dfeats,
                  int n, int k, long long rows, int f, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2-K6  ACTION module (models/action.py:8-116): temporal FIR + spatio-temporal / channel / motion
+ *   excitation around a 1x1 convolution.  All small tensors are fp32; x / xs / gy / dxs / dx have `dtype`
+ *   and are NHWC rows [n*t*h*w, c].  The struct is a HOST struct of device pointers (copied into the
+ *   kernel parameters); the caller owns every buffer and zeroes the accumulators marked (+=).
+ *   forward :  ehgr_action_xs -> ehgr_bn_finalize(qstats -> bn3_scale/shift) -> ehgr_action_gates ->
+ *              ehgr_pw_gemm with a GATE row operand (in1 = xs, in2 = g1, scale = g2, shift = g3)
+ *   backward:  gy = dgrad of that GEMM;  ehgr_action_bwd_reduce -> ehgr_action_bwd_small ->
+ *              ehgr_bn_bwd_finalize(bn3_sums -> bn3_ca/cb/cc, dgamma, dbeta) -> ehgr_action_bwd_dxs ->
+ *              ehgr_action_fir_bwd (adds the residual gradient `addend`, nullable)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ehgr_action {
+  int32_t n, t, h, w, c, cr;      /* clips, segments, spatial size, channels, reduced channels c/16 */
+  /* parameters (fp32, the reference's module names) */
+  const float* shift_w;     /* action_shift.weight      [c,1,3]    */
+  const float* p1_w;        /* action_p1_conv1.weight   [1,1,3,3,3] */
+  const float* p2_squeeze;  /* action_p2_squeeze.weight [cr,c]     */
+  const float* p2_conv1;    /* action_p2_conv1.weight   [cr,cr,3]  */
+  const float* p2_expand;   /* action_p2_expand.weight  [c,cr]     */
+  const float* p3_squeeze;  /* action_p3_squeeze.weight [cr,c]     */
+  const float* p3_conv1;    /* action_p3_conv1.weight   [cr,1,3,3] */
+  const float* p3_expand;   /* action_p3_expand.weight  [c,cr]     */
+  const float* bn3_scale;   /* action_p3_bn1 as scale/shift [cr] (ehgr_bn_finalize) */
+  const float* bn3_shift;
+  /* forward products, saved for backward */
+  float* mrow;              /* [M]      mean over channels of xs */
+  float* pool;              /* [n*t, c] spatial SUM of xs */
+  float* q;                 /* [M, cr]  p3_squeeze(xs), before BatchNorm */
+  double* qstats;           /* [2*cr]   (+=) sum q, sum q^2 */
+  float* g1;                /* [M]      spatio-temporal gate */
+  float* g2;                /* [n*t, c] channel gate */
+  float* g3;                /* [n*t, c] motion gate */
+  float* s;                 /* [n*t, cr] p2_squeeze output */
+  float* u;                 /* [n*t, cr] p2_conv1 output (pre-ReLU) */
+  float* pi;                /* [n*t, cr] pooled motion feature */
+  /* backward workspaces */
+  float* dg1;               /* [M]      sum_c gy*xs, overwritten with d(a1) */
+  float* dgc;               /* [n*t, c] sum_hw gy*xs */
+  float* dm;                /* [M]      gradient w.r.t. mrow */
+  float* dpool;             /* [n*t, c] gradient w.r.t. the spatial mean */
+  float* dd;                /* [n*t, cr] gradient w.r.t. the motion difference map (spatially constant) */
+  double* bn3_sums;         /* [2*cr]   (+=) sum dx3, sum dx3*q */
+  const float* bn3_ca;      /* [cr] BatchNorm-backward coefficients of action_p3_bn1 */
+  const float* bn3_cb;
+  const float* bn3_cc;
+  /* parameter gradients (+=) */
+  float* d_shift_w;
+  float* d_p1_w;
+  float* d_p2_squeeze;
+  float* d_p2_conv1;
+  float* d_p2_expand;
+  float* d_p3_squeeze;
+  float* d_p3_conv1;
+  float* d_p3_expand;
+} ehgr_action;
+
+int ehgr_action_xs(const ehgr_action* a, const void* x, void* xs, int dtype, ehgr_stream_t stream);
+int ehgr_action_gates(const ehgr_action* a, ehgr_stream_t stream);
+int ehgr_action_bwd_reduce(const ehgr_action* a, const void* gy, const void* xs, int dtype, ehgr_stream_t stream);
+int ehgr_action_bwd_small(const ehgr_action* a, ehgr_stream_t stream);
+int ehgr_action_bwd_dxs(const ehgr_action* a, const void* gy, const void* xs, void* dxs, int dtype,
+                        ehgr_stream_t stream);
+int ehgr_action_fir_bwd(const ehgr_action* a, const void* dxs, const void* x, const void* addend, void* dx, int dtype,
+                        ehgr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,8 @@ def _randomize(module, seed):
 
 
 @pytest.mark.parametrize("inp,oup,stride,t,temporal", [(24, 24, 1, 6, "none"), (24, 24, 1, 6, "tsm"), (32, 64, 2, 6, "none"),
-                                                      (32, 16, 1, 1, "none"), (160, 160, 1, 6, "tsm"), (64, 96, 1, 6, "none")])
+                                                      (32, 16, 1, 1, "none"), (160, 160, 1, 6, "tsm"), (64, 96, 1, 6, "none"),
+                                                      (32, 32, 1, 6, "action"), (96, 96, 1, 6, "action")])
 @pytest.mark.parametrize("bn_train", [True, False])
 def test_inverted_residual_block(inp, oup, stride, t, temporal, bn_train):
     import ehgr_b200 as E
@@ -38,6 +39,13 @@ def test_inverted_residual_block(inp, oup, stride, t, temporal, bn_train):
         blk = E.InvertedResidual(inp, oup, stride, t)
         if temporal == "tsm":
             blk.conv[0] = E.TemporalShift(blk.conv[0], n_segment=4, n_div=8)
+        if temporal == "action":
+            blk.conv[0] = E.Action(blk.conv[0], n_segment=4, shift_div=8)
+            with torch.no_grad():
+                g0 = torch.Generator().manual_seed(9)
+                for k, p in blk.conv[0].named_parameters():
+                    if k.startswith("action_") and "bn" not in k:
+                        p.add_(torch.randn(p.shape, generator=g0) * 0.3)
     _randomize(blk, 3)
     sd0 = {"f." + k: v.clone() for k, v in blk.state_dict().items()}
     nt, hw = 8, 9
@@ -68,6 +76,43 @@ def test_inverted_residual_block(inp, oup, stride, t, temporal, bn_train):
                 assert int(new[k]) == 1
 
 
+@pytest.mark.parametrize("name", ["c32", "c24", "c160"])
+def test_action_module_against_reference_fixture(name):
+    """Stand-alone Action (fused xs / gates / backward kernels + library `net`) against the outputs and
+    gradients of the reference module (tests/golden/action.npz)."""
+    import ehgr_b200 as E
+    z = np.load(GOLDEN / "action.npz")
+    c, h, T, n, train_bn = (int(v) for v in z[name + "_meta"])
+    rs = np.random.RandomState(11 + c)
+    sd = {}
+    O.action_state(sd, "m", c, 8, rs)
+    O._conv_entry(sd, "m.net.weight", (6 * c, c, 1, 1), rs)
+    with _quiet():
+        mod = E.Action(torch.nn.Conv2d(c, 6 * c, 1, bias=False), n_segment=T, shift_div=8)
+    mod.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+    mod = mod.cuda().train(bool(train_bn))
+    x = torch.from_numpy(z[name + "_x"]).cuda().requires_grad_(True)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y = mod(x)
+        y.backward(torch.from_numpy(z[name + "_g"]).cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert rel_err(y, torch.from_numpy(z[name + "_y"])) < 1e-5
+    assert rel_err(x.grad, torch.from_numpy(z[name + "_gx"])) < 2e-5
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith(name + "_grad_"))
+    for k in z.files:
+        if k.startswith(name + "_grad_"):
+            pk = k[len(name + "_grad_"):]
+            got = dict(mod.named_parameters())[pk].grad.cpu().double()
+            ref = torch.from_numpy(z[k]).double()
+            assert (got - ref).abs().max().item() <= 3e-5 * max(ref.abs().max().item(), 1e-3 * gmax), pk
+    if train_bn:
+        assert rel_err(mod.action_p3_bn1.running_mean, torch.from_numpy(z[name + "_rm"])) < 1e-5
+        assert rel_err(mod.action_p3_bn1.running_var, torch.from_numpy(z[name + "_rv"])) < 1e-5
+
+
 def _digest(g):
     g = g.detach().double().flatten().cpu()
     idx = torch.linspace(0, g.numel() - 1, steps=min(16, g.numel())).long()
@@ -82,7 +127,7 @@ def _tsn(temporal):
                      temporal_module=("tsm" if temporal == "tsm" else "action"))
 
 
-@pytest.mark.parametrize("temporal", ["none", "tsm"])
+@pytest.mark.parametrize("temporal", ["none", "tsm", "action"])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_tsn_against_reference_fixture(temporal, mode):
     """Whole network, fp32 kernels, against the live-reference fixture.  The arbiter is the reference's
