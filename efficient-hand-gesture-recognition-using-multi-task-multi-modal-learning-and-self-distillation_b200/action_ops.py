@@ -30,6 +30,11 @@ def action_params(mod):
             mod.action_p3_conv1.weight, mod.action_p3_expand.weight]
 
 
+def _pad(n_: int) -> int:
+    """Sub-buffers of one allocation start on 32-byte boundaries (vector loads of the per-channel gates)."""
+    return (n_ + 7) // 8 * 8
+
+
 class ActionState:
     """Everything the backward needs from one forward call."""
     __slots__ = ("n", "t", "h", "w", "c", "cr", "xs", "small", "views", "bn3_vec", "bn3_training", "dtype")
@@ -63,11 +68,11 @@ def forward_gates(mod, x, params, dt):
     M, cr = nt * h * w, st.cr
     sizes = {"mrow": M, "pool": nt * c, "q": M * cr, "g1": M, "g2": nt * c, "g3": nt * c, "s": nt * cr, "u": nt * cr,
              "pi": nt * cr}
-    st.small = torch.empty(sum(sizes.values()), dtype=torch.float32, device=dev)
+    st.small = torch.empty(sum(_pad(v) for v in sizes.values()), dtype=torch.float32, device=dev)
     st.views, off = {}, 0
     for k, n_ in sizes.items():
         st.views[k] = st.small[off:off + n_]
-        off += n_
+        off += _pad(n_)
     qstats = torch.zeros(2 * cr, dtype=torch.float64, device=dev)
     st.views["qstats"] = qstats
     st.bn3_vec = torch.empty((4, cr), dtype=torch.float32, device=dev)
@@ -101,12 +106,12 @@ def backward(st: ActionState, params, grads, gy, x, addend):
     dev = gy.device
     nt, c, cr = st.n * st.t, st.c, st.cr
     M = nt * st.h * st.w
-    ws = torch.empty(2 * M + 2 * nt * c + nt * cr, dtype=torch.float32, device=dev)
+    ws = torch.empty(2 * _pad(M) + 2 * _pad(nt * c) + _pad(nt * cr), dtype=torch.float32, device=dev)
     o = [0]
 
     def take(n_):
         v = ws[o[0]:o[0] + n_]
-        o[0] += n_
+        o[0] += _pad(n_)
         return v
     extra = {"dg1": take(M), "dm": take(M), "dgc": take(nt * c), "dpool": take(nt * c), "dd": take(nt * cr)}
     sums = torch.zeros(2 * cr, dtype=torch.float64, device=dev)

@@ -314,11 +314,12 @@ class _ChainFunction(torch.autograd.Function):
         sp = _lib.stream_ptr(dev)
         stages = [s for u in units for s in u.stages]
         sizes = [p.numel() for p in params]
-        gflat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)   # every parameter gradient of the chain
+        # every parameter gradient of the chain, each on a 32-byte boundary (vector stores / atomics)
+        gflat = torch.zeros(sum((n + 7) // 8 * 8 for n in sizes), dtype=torch.float32, device=dev)
         gviews, off = [], 0
         for p, n in zip(params, sizes):
             gviews.append(gflat[off:off + n].view(p.shape))
-            off += n
+            off += (n + 7) // 8 * 8
         sum_arena = torch.zeros(sum(2 * s.conv.out_channels for s in stages), dtype=torch.float64, device=dev)
         coef_arena = torch.empty(sum(3 * s.conv.out_channels for s in stages), dtype=torch.float32, device=dev)
         s_off = c_off = 0
