@@ -8,6 +8,8 @@
 // Backward of conv -> BN(train) -> [ReLU6]:  with dz the (masked) gradient at the BN output,
 //   d raw = scale * (dz - mean(dz) - xhat * mean(dz*xhat)),   dgamma = sum dz*xhat,  dbeta = sum dz
 // which is written  ca*dz + cb*raw + cc  so that consumers can apply it while loading (rowop.cuh).
+#include <type_traits>
+
 #include "rowop.cuh"
 
 namespace ehgr {
@@ -111,12 +113,12 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
 
 // out = rowop(a) (+ addend).  block = (bx channel vectors, P rows): a thread keeps ONE channel vector
 // (operand coefficients in registers) and strides over rows, four rows fetched per batch.
-template <typename T>
+template <typename T, bool kGate>
 __global__ void __launch_bounds__(256)
 row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv_total) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;
-  using Ld = RowLoader<T, V>;
+  using Ld = RowLoader<T, V, true, kGate>;
   const long long row_stride = static_cast<long long>(gridDim.x) * blockDim.y;
   for (int cv = threadIdx.x; cv < cv_total; cv += blockDim.x) {
     const int c0 = cv * V;
@@ -221,11 +223,16 @@ extern "C" int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out
   const dim3 block(bx, std::max(1, 256 / bx));
   const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), 8LL * kNumSMs));
   cudaStream_t s = as_stream(stream);
-  if (dtype == EHGR_F32)
-    row_apply_kernel<float><<<static_cast<unsigned>(blocks), block, 0, s>>>(*a, static_cast<const float*>(addend),
-                                                                           static_cast<float*>(out), m, c, cv);
-  else
-    row_apply_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), block, 0, s>>>(
-        *a, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(out), m, c, cv);
+  const bool gate = a->mode == EHGR_ROW_GATE;
+  auto launch = [&](auto tag, auto gate_tag) {
+    using T = decltype(tag);
+    row_apply_kernel<T, decltype(gate_tag)::value><<<static_cast<unsigned>(blocks), block, 0, s>>>(
+        *a, static_cast<const T*>(addend), static_cast<T*>(out), m, c, cv);
+  };
+  if (dtype == EHGR_F32) {
+    if (gate) launch(float{}, std::true_type{}); else launch(float{}, std::false_type{});
+  } else {
+    if (gate) launch(__nv_bfloat16{}, std::true_type{}); else launch(__nv_bfloat16{}, std::false_type{});
+  }
   return launch_status();
 }

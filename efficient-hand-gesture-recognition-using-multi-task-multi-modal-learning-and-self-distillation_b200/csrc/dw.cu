@@ -289,7 +289,7 @@ extern "C" int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, doubl
   DwGeom g;
   if (int st = dw_geom(g, nt, h, wd, c, stride, dtype)) return st;
   if (!w || !out) return EHGR_E_NULL;
-  if (int st = validate_rowop(a, esize_of(dtype))) return st;
+  if (int st = validate_rowop_nogate(a, esize_of(dtype))) return st;
   if (!aligned_to(out, 16)) return EHGR_E_ALIGN;
   if (g.n_out == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);
@@ -301,7 +301,7 @@ extern "C" int ehgr_dw_dgrad(const ehgr_rowop* dy, const float* w, void* da, int
   DwGeom g;
   if (int st = dw_geom(g, nt, h, wd, c, stride, dtype)) return st;
   if (!w || !da) return EHGR_E_NULL;
-  if (int st = validate_rowop(dy, esize_of(dtype))) return st;
+  if (int st = validate_rowop_nogate(dy, esize_of(dtype))) return st;
   if (!aligned_to(da, 16)) return EHGR_E_ALIGN;
   if (g.n_in == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);
@@ -314,8 +314,8 @@ extern "C" int ehgr_dw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* d
   DwGeom g;
   if (int st = dw_geom(g, nt, h, wd, c, stride, dtype)) return st;
   if (!dw) return EHGR_E_NULL;
-  if (int st = validate_rowop(dy, esize_of(dtype))) return st;
-  if (int st = validate_rowop(a, esize_of(dtype))) return st;
+  if (int st = validate_rowop_nogate(dy, esize_of(dtype))) return st;
+  if (int st = validate_rowop_nogate(a, esize_of(dtype))) return st;
   if (a->mode == EHGR_ROW_BNBWD) return EHGR_E_UNSUPPORTED;  // the forward operand is never a BN-backward operand
   if (g.n_out == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);

@@ -370,8 +370,8 @@ extern "C" int ehgr_dw_bwd(const ehgr_rowop* dy, const ehgr_rowop* a, const floa
   DwTile g;
   if (int st = dw_tile_geom(g, nt, h, wd, c, stride, dtype)) return st;
   if (!w || !da || !dw) return EHGR_E_NULL;
-  if (int st = validate_rowop(dy, esize_of(dtype))) return st;
-  if (int st = validate_rowop(a, esize_of(dtype))) return st;
+  if (int st = validate_rowop_nogate(dy, esize_of(dtype))) return st;
+  if (int st = validate_rowop_nogate(a, esize_of(dtype))) return st;
   if (a->mode == EHGR_ROW_BNBWD) return EHGR_E_UNSUPPORTED;
   if (!aligned_to(da, 16)) return EHGR_E_ALIGN;
   if (g.items == 0) return EHGR_OK;

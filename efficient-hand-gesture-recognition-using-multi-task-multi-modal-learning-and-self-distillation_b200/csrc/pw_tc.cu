@@ -172,11 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           const int k8 = pass * 4 + (slot % kvp);
           const int k = k_base + k8 * 8;
           const bool kin = k8 < kv && k < p.K;
-          RowLoader<__nv_bfloat16, 8> ld;
+          RowLoader<__nv_bfloat16, 8, true, true> ld;
           if (kin) ld.init(p.a, k, p.K);
 #pragma unroll 1
           for (int j0 = 0; j0 * f < 16; j0 += kBatch) {
-            RowLoader<__nv_bfloat16, 8>::Raw raw[kBatch];
+            RowLoader<__nv_bfloat16, 8, true, true>::Raw raw[kBatch];
             bool live[kBatch];
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {

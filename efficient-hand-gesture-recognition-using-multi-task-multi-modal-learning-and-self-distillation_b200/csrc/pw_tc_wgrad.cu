@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
   const int pw = p.n_stages < kWgProducers ? p.n_stages : kWgProducers;   // see pw_tc.cu: parity aliasing
 
   if (warp < pw) {
-    using Ld = RowLoader<__nv_bfloat16, 8>;
+    using Ld = RowLoader<__nv_bfloat16, 8, true, true>;
     uint32_t it = 0;
     for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
       if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;

@@ -99,7 +99,8 @@ __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfl
 // ---- the row operand ------------------------------------------------------------------------------
 // Loads NV consecutive channels [c0, c0+NV) of row m (C channels per row) as fp32 with the operand's
 // transformation applied.  The caller guarantees c0 % NV == 0, C % NV == 0 and 0 <= m < M.
-template <typename T, int NV>
+// kGate = false compiles the GATE mode out (kernels that never take a gated operand).
+template <typename T, int NV, bool kGate = true>
 __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, int C, float (&v)[NV]) {
   const T* in1 = static_cast<const T*>(op.in1);
   const long long off = m * C + c0;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
         v[i] = k == 0 ? a[i] : (k == 1 ? b[i] : c[i]);
       }
     }
-  } else if (op.mode == EHGR_ROW_GATE) {
+  } else if (kGate && op.mode == EHGR_ROW_GATE) {
     load_vec<T, NV>(in1 + off, v);
     const long long f = m / op.hw;
     const float g1 = static_cast<const float*>(op.in2)[m];
@@ -185,7 +186,7 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
 template <typename T, int NV>
 __device__ __noinline__ uint4 shift_straddle_raw(const RowOp& op, long long m, int c0, int C) {
   float v[NV];
-  load_row<T, NV>(op, m, c0, C, v);
+  load_row<T, NV, false>(op, m, c0, C, v);
   uint4 out;
   store_vec<T, NV>(reinterpret_cast<T*>(&out), v);
   return out;
@@ -196,7 +197,8 @@ __device__ __noinline__ uint4 shift_straddle_raw(const RowOp& op, long long m, i
 // load() only touches the activation tensors.
 // kTwo = false compiles the two-tensor BNBWD mode out (fewer registers) for kernels whose operand is
 // known to be PLAIN / AFFINE / SHIFT; the host checks the mode before choosing such an instantiation.
-template <typename T, int NV, bool kTwo = true>
+// kGate = true compiles the GATE mode in (pointwise GEMM operands and row_apply only).
+template <typename T, int NV, bool kTwo = true, bool kGate = false>
 struct RowLoader {
   float s[NV], b[NV], ca[kTwo ? NV : 1], cb[kTwo ? NV : 1], cc[kTwo ? NV : 1];
   int c0, C;
@@ -245,7 +247,7 @@ struct RowLoader {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = fmaf(ca[kTwo ? i : 0], g[i], fmaf(cb[kTwo ? i : 0], r[i], cc[kTwo ? i : 0]));
     } else {
-      load_row<T, NV>(op, m, c0, C, v);  // SHIFT / GATE: no per-channel coefficients held in registers
+      load_row<T, NV, kGate>(op, m, c0, C, v);  // SHIFT / GATE: no per-channel coefficients held in registers
     }
   }
 
@@ -253,7 +255,7 @@ struct RowLoader {
   // instruction depends on the data), finish() does the arithmetic.  Kernels fetch a batch of rows
   // (all nine depthwise taps, several GEMM operand vectors) before finishing the first one, so a thread
   // has many loads in flight instead of one round trip per row.  Requires NV == VecOf<T>::N.
-  struct Raw { uint4 a; uint4 b[kTwo ? 1 : 0 + 1]; };
+  struct Raw { uint4 a; uint4 b[1]; };   // b: second tensor (BNBWD) or the row index (GATE); dead otherwise
 
   __device__ __forceinline__ Raw fetch(const RowOp& op, long long m) const {
     static_assert(NV == VecOf<T>::N, "fetch/finish work on full 16-byte vectors");
@@ -280,9 +282,11 @@ struct RowLoader {
       }
     } else {
       r.a = *reinterpret_cast<const uint4*>(in1 + off);
-      if (op.mode == EHGR_ROW_GATE) {   // finish() needs the row index for the per-row / per-frame gates
-        r.b[0].x = static_cast<uint32_t>(m & 0xffffffffLL);
-        r.b[0].y = static_cast<uint32_t>(m >> 32);
+      if constexpr (kGate) {
+        if (op.mode == EHGR_ROW_GATE) {   // finish() needs the row index for the per-row / per-frame gates
+          r.b[0].x = static_cast<uint32_t>(m & 0xffffffffLL);
+          r.b[0].y = static_cast<uint32_t>(m >> 32);
+        }
       }
       if constexpr (kTwo) {
         if (op.mode == EHGR_ROW_BNBWD) r.b[0] = *reinterpret_cast<const uint4*>(static_cast<const T*>(op.in2) + off);
@@ -301,7 +305,7 @@ struct RowLoader {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
       }
-    } else if (op.mode == EHGR_ROW_GATE) {
+    } else if (kGate && op.mode == EHGR_ROW_GATE) {
       const long long m = static_cast<long long>(r.b[0].x) | (static_cast<long long>(r.b[0].y) << 32);
       const long long f = m / op.hw;
       const float g1 = static_cast<const float*>(op.in2)[m];
@@ -343,6 +347,12 @@ inline int validate_rowop(const RowOp* op, int es) {
     default: return EHGR_E_DTYPE;
   }
   (void)es;
+}
+
+// for kernels compiled without the GATE mode (depthwise family)
+inline int validate_rowop_nogate(const RowOp* op, int es) {
+  if (op && op->mode == EHGR_ROW_GATE) return EHGR_E_UNSUPPORTED;
+  return validate_rowop(op, es);
 }
 
 }  // namespace ehgr
