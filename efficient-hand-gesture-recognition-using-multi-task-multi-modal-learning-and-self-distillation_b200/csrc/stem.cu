@@ -136,6 +136,235 @@ stem_wgrad_kernel(RowOp dy, const X* __restrict__ x, float* __restrict__ dwgt, S
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path for Cout == 32 (every MobileNetV2 the reference builds: width_mult = 1).
+//
+// A CTA works on a band of R output rows of one frame.  The 2R+1 input rows of the three colour planes
+// are staged into shared memory de-interleaved by column parity,
+//     E[ci][r][j] = x[ci][hi0+r][2j]      O[ci][r][j] = x[ci][hi0+r][2j-1]   (zero outside the image)
+// so that the stride-2 taps of neighbouring output columns are stride-1 (conflict-free) reads:
+//     kw = 0 -> O[wo], kw = 1 -> E[wo], kw = 2 -> O[wo+1].
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemC = 32;
+
+template <typename X>
+__device__ __forceinline__ void stem_stage_band(const X* __restrict__ x, float* __restrict__ planes, long long nt,
+                                                int hi0, int nrows, int h, int w, int wp, int tid, int nthreads) {
+  // planes: [3][nrows][2][wp] (E then O per row); index c2 in [0, 2wp): col = c2 - 1, c2 even -> O[c2/2], odd -> E[c2/2]
+  const int per_row = 2 * wp;
+  const int total = 3 * nrows * per_row;
+  const size_t plane = static_cast<size_t>(h) * w;
+#pragma unroll 4
+  for (int i = tid; i < total; i += nthreads) {
+    const int c2 = i % per_row;
+    const int rr = i / per_row;          // ci * nrows + r
+    const int ci = rr / nrows, r = rr - ci * nrows;
+    const int hi = hi0 + r, col = c2 - 1;
+    float v = 0.f;
+    if (hi >= 0 && hi < h && col >= 0 && col < w) v = ld_x<X>(x + (static_cast<size_t>(nt) * 3 + ci) * plane + static_cast<size_t>(hi) * w + col);
+    planes[(rr * 2 + ((c2 & 1) ? 0 : 1)) * wp + (c2 >> 1)] = v;
+  }
+}
+
+// 32 values per lane -> lane L receives the warp-wide sum of element L (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <typename T>
+__device__ __forceinline__ void stem_store32(T* __restrict__ p, const float (&a)[32]);
+template <>
+__device__ __forceinline__ void stem_store32<float>(float* __restrict__ p, const float (&a)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+}
+template <>
+__device__ __forceinline__ void stem_store32<__nv_bfloat16>(__nv_bfloat16* __restrict__ p, const float (&a)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    reinterpret_cast<uint4*>(p)[i] = make_uint4(pack_bf16x2(a[8 * i], a[8 * i + 1]), pack_bf16x2(a[8 * i + 2], a[8 * i + 3]),
+                                                pack_bf16x2(a[8 * i + 4], a[8 * i + 5]), pack_bf16x2(a[8 * i + 6], a[8 * i + 7]));
+}
+
+// thread = one output column, two vertically adjacent output pixels x 32 channels in registers; the
+// 27 x 32 weights are broadcast reads from shared memory, shared by the two pixels.
+template <typename X, typename T>
+__global__ void __launch_bounds__(128)
+stem_fwd32_kernel(const X* __restrict__ x, const float* __restrict__ wgt, T* __restrict__ out,
+                  double* __restrict__ stats, StemGeom g, int R, int bands, int wp) {
+  extern __shared__ __align__(16) float smem[];
+  float* ws = smem;                      // [27][32]
+  float* s_stat = ws + 27 * kStemC;      // [64]
+  float* planes = s_stat + 2 * kStemC;   // [3][2R+1][2][wp]
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 27 * kStemC; i += blockDim.x) {
+    const int tap = i / kStemC, co = i - tap * kStemC;
+    ws[i] = wgt[co * 27 + tap];
+  }
+  if (tid < 2 * kStemC) s_stat[tid] = 0.f;
+  float st_sum = 0.f, st_sq = 0.f;       // this lane's channel (= lane)
+  const int nrows = 2 * R + 1;
+  const long long items = static_cast<long long>(g.nt) * bands;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long nt = item / bands;
+    const int ho0 = static_cast<int>(item - nt * bands) * R;
+    __syncthreads();
+    stem_stage_band<X>(x, planes, nt, 2 * ho0 - 1, nrows, g.h, g.w, wp, tid, blockDim.x);
+    __syncthreads();
+    const int rmax = min(R, g.ho - ho0);
+    const int wo_end = (g.wo + 31) / 32 * 32;          // whole warps run the shuffles
+    for (int wo = tid; wo < wo_end; wo += blockDim.x) {
+      const bool col_ok = wo < g.wo;
+      const int wc = col_ok ? wo : 0;
+      for (int oh = 0; oh < rmax; oh += 2) {
+        const bool two = oh + 1 < rmax;
+        float a0[32], a1[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a0[i] = a1[i] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const float* row0 = planes + ((ci * nrows + 2 * oh + kh) * 2) * wp;   // E row, O row = +wp
+            const float* row1 = row0 + 4 * wp;                                      // two input rows further down
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int off = (kw == 1 ? 0 : wp) + wc + (kw == 2 ? 1 : 0);
+              const float x0 = row0[off];
+              const float x1 = two ? row1[off] : 0.f;
+              const float4* wv = reinterpret_cast<const float4*>(ws + (ci * 9 + kh * 3 + kw) * kStemC);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 w4 = wv[q4];
+                a0[4 * q4 + 0] = fmaf(x0, w4.x, a0[4 * q4 + 0]); a1[4 * q4 + 0] = fmaf(x1, w4.x, a1[4 * q4 + 0]);
+                a0[4 * q4 + 1] = fmaf(x0, w4.y, a0[4 * q4 + 1]); a1[4 * q4 + 1] = fmaf(x1, w4.y, a1[4 * q4 + 1]);
+                a0[4 * q4 + 2] = fmaf(x0, w4.z, a0[4 * q4 + 2]); a1[4 * q4 + 2] = fmaf(x1, w4.z, a1[4 * q4 + 2]);
+                a0[4 * q4 + 3] = fmaf(x0, w4.w, a0[4 * q4 + 3]); a1[4 * q4 + 3] = fmaf(x1, w4.w, a1[4 * q4 + 3]);
+              }
+            }
+          }
+        }
+        if (col_ok) {
+          const long long q0 = (nt * g.ho + ho0 + oh) * g.wo + wo;
+          stem_store32<T>(out + q0 * kStemC, a0);
+          if (two) stem_store32<T>(out + (q0 + g.wo) * kStemC, a1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a0[i] = a1[i] = 0.f;
+        }
+        if (stats) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { sq[i] = fmaf(a0[i], a0[i], a1[i] * a1[i]); a0[i] += a1[i]; }
+          st_sum += warp_transpose_sum32(a0, lane);
+          st_sq += warp_transpose_sum32(sq, lane);
+        }
+      }
+    }
+  }
+  if (stats) {
+    atomicAdd(&s_stat[lane], st_sum);
+    atomicAdd(&s_stat[kStemC + lane], st_sq);
+    __syncthreads();
+    if (tid < 2 * kStemC) atomicAdd(&stats[tid], static_cast<double>(s_stat[tid]));
+  }
+}
+
+// Weight gradient.  12 warps = 4 channel groups (8 output channels) x 3 input planes; a warp keeps its
+// 9 taps x 8 channels in registers over every band the CTA visits, lanes = output pixels of the band.
+// rowop(dy) is evaluated once per element while the band is staged (as fp32, [quad][pixel][4]).
+template <typename X, typename T>
+__global__ void __launch_bounds__(384)
+stem_wgrad32_kernel(RowOp dy, const X* __restrict__ x, float* __restrict__ dwgt, StemGeom g, int R, int bands, int wp) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int QV = V / 4;                    // quads per vector
+  extern __shared__ __align__(16) float smem[];
+  const int nrows = 2 * R + 1;
+  const int npix = R * g.wo;
+  float* dtile = smem;                                       // [8][npix][4]  (16-byte aligned: float4 accesses)
+  float* planes = dtile + 8 * npix * 4;                      // [3][nrows][2][wp]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cog = warp & 3, ci = warp >> 2;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  const int vec_per_row = kStemC / V;
+  const int cv = tid % vec_per_row;            // blockDim % vec_per_row == 0: fixed channel vector per thread
+  const long long items = static_cast<long long>(g.nt) * bands;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long nt = item / bands;
+    const int ho0 = static_cast<int>(item - nt * bands) * R;
+    const int rmax = min(R, g.ho - ho0);
+    const int np = rmax * g.wo;
+    __syncthreads();
+    stem_stage_band<X>(x, planes, nt, 2 * ho0 - 1, nrows, g.h, g.w, wp, tid, blockDim.x);
+    {
+      RowLoader<T, V> ld;            // coefficients live only while staging (the tap loop needs the registers)
+      ld.init(dy, cv * V, kStemC);
+      const long long q0 = (nt * g.ho + ho0) * g.wo;
+      const int step = blockDim.x / vec_per_row;
+#pragma unroll 1
+      for (int p0 = tid / vec_per_row; p0 < np; p0 += 2 * step) {
+        typename RowLoader<T, V>::Raw raw[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) if (p0 + j * step < np) raw[j] = ld.fetch(dy, q0 + p0 + j * step);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int p = p0 + j * step;
+          if (p < np) {
+            float v[V];
+            ld.finish(dy, raw[j], v);
+#pragma unroll
+            for (int qd = 0; qd < QV; ++qd)
+              *reinterpret_cast<float4*>(dtile + (static_cast<size_t>(cv * QV + qd) * npix + p) * 4) =
+                  make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int oh = 0; oh < rmax; ++oh) {
+      for (int wo = lane; wo < g.wo; wo += 32) {
+        const int p = oh * g.wo + wo;
+        const float4 d0 = *reinterpret_cast<const float4*>(dtile + (static_cast<size_t>(cog * 2) * npix + p) * 4);
+        const float4 d1 = *reinterpret_cast<const float4*>(dtile + (static_cast<size_t>(cog * 2 + 1) * npix + p) * 4);
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float* row = planes + ((ci * nrows + 2 * oh + kh) * 2) * wp;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float xv = row[(kw == 1 ? 0 : wp) + wo + (kw == 2 ? 1 : 0)];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(d[i], xv, acc[kh * 3 + kw][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[t][i];
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) atomicAdd(&dwgt[(cog * 8 + i) * 27 + ci * 9 + t], v);
+    }
+}
+
 static int stem_geom(StemGeom& g, int nt, int h, int w, int cout) {
   if (nt < 0 || h <= 0 || w <= 0 || cout <= 0 || (cout % 8) || cout > 256) return EHGR_E_SHAPE;
   g.nt = nt; g.h = h; g.w = w; g.cout = cout;
@@ -145,9 +374,37 @@ static int stem_geom(StemGeom& g, int nt, int h, int w, int cout) {
   return EHGR_OK;
 }
 
+template <typename X, typename T>
+static void stem_fwd32_go(const void* x, const float* w, void* out, double* stats, const StemGeom& g, cudaStream_t s) {
+  const int R = 4, bands = static_cast<int>(cdiv(g.ho, R)), wp = g.wo + 1;
+  const size_t smem = (static_cast<size_t>(29) * kStemC + 3 * (2 * R + 1) * 2 * wp) * sizeof(float);
+  cudaFuncSetAttribute(stem_fwd32_kernel<X, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const long long items = static_cast<long long>(g.nt) * bands;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 4LL * kNumSMs));
+  stem_fwd32_kernel<X, T><<<grid, 128, smem, s>>>(static_cast<const X*>(x), w, static_cast<T*>(out), stats, g, R, bands, wp);
+}
+
+template <typename X, typename T>
+static void stem_wgrad32_go(const RowOp& dy, const void* x, float* dw, const StemGeom& g, cudaStream_t s) {
+  const int R = 2, bands = static_cast<int>(cdiv(g.ho, R)), wp = g.wo + 1;
+  const size_t smem = (static_cast<size_t>(3) * (2 * R + 1) * 2 * wp + static_cast<size_t>(8) * R * g.wo * 4) * sizeof(float);
+  cudaFuncSetAttribute(stem_wgrad32_kernel<X, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const long long items = static_cast<long long>(g.nt) * bands;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 1LL * kNumSMs));
+  stem_wgrad32_kernel<X, T><<<grid, 384, smem, s>>>(dy, static_cast<const X*>(x), dw, g, R, bands, wp);
+}
+
+// shared-memory budget of the banded kernels (image width bound)
+static bool stem32_fits(const StemGeom& g) { return g.cout == kStemC && g.wo <= 1024; }
+
 template <typename X>
 static int stem_fwd_launch(const void* x, const float* w, void* out, double* stats, const StemGeom& g, int dtype,
                            cudaStream_t s) {
+  if (stem32_fits(g)) {
+    if (dtype == EHGR_F32) stem_fwd32_go<X, float>(x, w, out, stats, g, s);
+    else stem_fwd32_go<X, __nv_bfloat16>(x, w, out, stats, g, s);
+    return launch_status();
+  }
   const size_t smem = static_cast<size_t>(29) * g.cout * sizeof(float);
   if (dtype == EHGR_F32) {
     const dim3 block(g.cout / 4, std::max(1, 256 / (g.cout / 4)));
@@ -166,6 +423,11 @@ static int stem_fwd_launch(const void* x, const float* w, void* out, double* sta
 template <typename X>
 static int stem_wgrad_launch(const RowOp& dy, const void* x, float* dw, const StemGeom& g, int dtype,
                              cudaStream_t s) {
+  if (stem32_fits(g) && dy.mode != EHGR_ROW_GATE) {
+    if (dtype == EHGR_F32) stem_wgrad32_go<X, float>(dy, x, dw, g, s);
+    else stem_wgrad32_go<X, __nv_bfloat16>(dy, x, dw, g, s);
+    return launch_status();
+  }
   const dim3 block(g.cout / 4, std::max(1, 256 / (g.cout / 4)));
   long long iters = cdiv(g.n_out, 4LL * kNumSMs * block.y);
   iters = std::max(1LL, std::min(iters, 4096LL));

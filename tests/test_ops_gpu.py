@@ -315,12 +315,13 @@ def test_dw_tiled_ragged_tiles(dtype):
 # stem
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("hw", [(32, 32), (17, 23)])
-def test_stem(dtype, hw):
+@pytest.mark.parametrize("hw,cout", [((32, 32), 32), ((17, 23), 32), ((50, 46), 32), ((224, 224), 32), ((20, 18), 16)])
+def test_stem(dtype, hw, cout):
+    """cout = 32 takes the banded shared-memory kernels, anything else the generic ones."""
     E = _E()
     f = E.fused
     h, w = hw
-    nt, cout = 3, 32
+    nt = 3
     x = _rand((nt, 3, h, w), 30)
     wt = _rand((cout, 3, 3, 3), 31, 0.3)
     x64, w64 = x.double(), wt.double().requires_grad_(True)
@@ -333,6 +334,7 @@ def test_stem(dtype, hw):
     _call("ehgr_stem_fwd", xd.data_ptr(), wt_d.data_ptr(), out.data_ptr(), stats.data_ptr(), nt, h, w, cout, 0, code, _sp())
     assert rel_err(out.cpu(), _rows(y64)) < TOL[dtype]
     assert rel_err(stats[:cout].cpu(), y64.sum((0, 2, 3))) < 1e-4
+    assert rel_err(stats[cout:].cpu(), (y64 * y64).sum((0, 2, 3))) < 1e-4
     g = _rand(tuple(y64.shape), 32).to(dtype)
     y64.backward(g.double())
     dw = torch.zeros((cout, 27), dtype=torch.float32, device="cuda")
