@@ -106,6 +106,13 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
   }
 }
 
+// kAsync = true : operand modes PLAIN / AFFINE / SHIFT / GATE.  A producer warp fills its ring stage with
+//                  16-byte cp.async copies straight into the core-matrix layout (a whole 16 KB stage in
+//                  flight per warp, no registers held), waits, and — for AFFINE / GATE — transforms the
+//                  stage IN PLACE (each lane re-reads exactly the chunks it copied).  SHIFT is a pure gather:
+//                  the copy's source is the neighbouring frame or a zero fill.
+// kAsync = false: register path (batched fetch -> rowop -> store) for the two-tensor BNBWD operand.
+template <bool kAsync>
 __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Kp = (p.K + 15) & ~15;
@@ -166,6 +173,82 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
         const int kv = kvalid >> 3;                    // 2, 4, 6 or 8 channel vectors per row
         const int kvp = kv < 4 ? kv : 4;               // channel vectors handled per pass by the 4 lane slots
         const int f = 4 / kvp;                         // spare slots interleave row groups (kv == 2)
+        if constexpr (kAsync) {
+          mbar_wait(bar_empty + 8 * s, parity);
+          const int mode = p.a.mode;
+          const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(p.a.in1);
+          const uint32_t a_dst32 = smem_u32(a_dst);
+          // SHIFT: frame / segment index of the tile's first row (rows advance by < 128 inside a stage)
+          int t0 = 0, rem0 = 0;
+          if (mode == EHGR_ROW_SHIFT) {
+            const long long f0 = m0 / p.a.hw;
+            rem0 = static_cast<int>(m0 - f0 * p.a.hw);
+            t0 = static_cast<int>(f0 % p.a.n_segment);
+          }
+#pragma unroll 1
+          for (int pass = 0; pass * 4 < kv; ++pass) {
+            const int k8 = pass * 4 + (slot % kvp);
+            const int k = k_base + k8 * 8;
+            const bool kin = k8 < kv && k < p.K;
+            int cls = 2;               // SHIFT: 0 reads frame t+dir, 1 reads t-dir, 2 reads t, 3 straddles a fold boundary
+            if (mode == EHGR_ROW_SHIFT && kin) {
+              const int fold = p.a.fold;
+              const int cl = k < fold ? 0 : (k < 2 * fold ? 1 : 2);
+              const int ch = k + 7 < fold ? 0 : (k + 7 < 2 * fold ? 1 : 2);
+              cls = cl == ch ? cl : 3;
+            }
+            const int dir = p.a.shift_dir < 0 ? -1 : 1;
+            const long long step = static_cast<long long>(dir) * p.a.hw * p.K;
+#pragma unroll 4
+            for (int j = 0; j * f < 16; ++j) {
+              const int rg = j * f + slot / kvp;
+              if (!(k8 < kv && rg < 16)) continue;
+              const int d = rg * 8 + r;
+              const long long m = m0 + d;
+              bool live = kin && m < p.M;
+              const uint32_t dst = a_dst32 + rg * a_sbo + k8 * 128 + r * 16;
+              const __nv_bfloat16* src = in1 + m * p.K + k;
+              if (mode == EHGR_ROW_SHIFT && cls != 2 && live) {
+                if (cls == 3) {
+                  sts128(dst, shift_straddle_raw<__nv_bfloat16, 8>(p.a, m, k, p.K));
+                  continue;
+                }
+                int rem = rem0 + d, t = t0;
+                while (rem >= p.a.hw) { rem -= p.a.hw; t = t + 1 == p.a.n_segment ? 0 : t + 1; }
+                const int tt = cls == 0 ? t + dir : t - dir;       // frame the data comes from
+                live = tt >= 0 && tt < p.a.n_segment;
+                src += cls == 0 ? step : -step;
+              }
+              cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+            }
+          }
+          cp_async_wait_all();
+          if (mode == EHGR_ROW_AFFINE || mode == EHGR_ROW_GATE) {
+#pragma unroll 1
+            for (int pass = 0; pass * 4 < kv; ++pass) {
+              const int k8 = pass * 4 + (slot % kvp);
+              const int k = k_base + k8 * 8;
+              if (!(k8 < kv && k < p.K)) continue;
+              RowLoader<__nv_bfloat16, 8, false, true> ld;
+              ld.init(p.a, k, p.K);
+#pragma unroll 4
+              for (int j = 0; j * f < 16; ++j) {
+                const int rg = j * f + slot / kvp;
+                const long long m = m0 + rg * 8 + r;
+                if (rg < 16 && m < p.M) {
+                  const uint32_t dst = a_dst32 + rg * a_sbo + k8 * 128 + r * 16;
+                  RowLoader<__nv_bfloat16, 8, false, true>::Raw raw;
+                  raw.a = lds128(dst);
+                  raw.b[0].x = static_cast<uint32_t>(m & 0xffffffffLL);
+                  raw.b[0].y = static_cast<uint32_t>(m >> 32);
+                  float v[8];
+                  ld.finish(p.a, raw, v);
+                  sts128(dst, pack8(v));
+                }
+              }
+            }
+          }
+        } else {
         bool waited = false;
 #pragma unroll 1
         for (int pass = 0; pass * 4 < kv; ++pass) {
@@ -204,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
               }
             }
           }
+        }
         }
         if (!p.b_resident) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
         fence_proxy_async();
@@ -360,8 +444,13 @@ int pw_gemm_tc(const RowOp& a, const float* w, int w_is_kn, void* out, const voi
   long long grid = std::min<long long>(tiles, kNumSMs);
   grid = std::max<long long>(p.n_chunks, grid / p.n_chunks * p.n_chunks);
   const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes;
-  cudaFuncSetAttribute(tc::pw_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
-  tc::pw_gemm_tc_kernel<<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
+  if (a.mode == EHGR_ROW_BNBWD) {
+    cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    tc::pw_gemm_tc_kernel<false><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
+  } else {
+    cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    tc::pw_gemm_tc_kernel<true><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
+  }
   return launch_status();
 }
 

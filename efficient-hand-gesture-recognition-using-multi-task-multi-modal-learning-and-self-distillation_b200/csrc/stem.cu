@@ -152,17 +152,21 @@ __device__ __forceinline__ void stem_stage_band(const X* __restrict__ x, float* 
                                                 int hi0, int nrows, int h, int w, int wp, int tid, int nthreads) {
   // planes: [3][nrows][2][wp] (E then O per row); index c2 in [0, 2wp): col = c2 - 1, c2 even -> O[c2/2], odd -> E[c2/2]
   const int per_row = 2 * wp;
-  const int total = 3 * nrows * per_row;
   const size_t plane = static_cast<size_t>(h) * w;
-#pragma unroll 4
-  for (int i = tid; i < total; i += nthreads) {
-    const int c2 = i % per_row;
-    const int rr = i / per_row;          // ci * nrows + r
+  const int nwarps = nthreads >> 5, warp = tid >> 5, lane = tid & 31;
+  for (int rr = warp; rr < 3 * nrows; rr += nwarps) {      // one warp per (plane, row): no per-element divisions
     const int ci = rr / nrows, r = rr - ci * nrows;
-    const int hi = hi0 + r, col = c2 - 1;
-    float v = 0.f;
-    if (hi >= 0 && hi < h && col >= 0 && col < w) v = ld_x<X>(x + (static_cast<size_t>(nt) * 3 + ci) * plane + static_cast<size_t>(hi) * w + col);
-    planes[(rr * 2 + ((c2 & 1) ? 0 : 1)) * wp + (c2 >> 1)] = v;
+    const int hi = hi0 + r;
+    const bool row_ok = hi >= 0 && hi < h;
+    const X* src = x + (static_cast<size_t>(nt) * 3 + ci) * plane + static_cast<size_t>(row_ok ? hi : 0) * w;
+    float* dst = planes + static_cast<size_t>(rr) * per_row;
+#pragma unroll 4
+    for (int c2 = lane; c2 < per_row; c2 += 32) {
+      const int col = c2 - 1;
+      float v = 0.f;
+      if (row_ok && col >= 0 && col < w) v = ld_x<X>(src + col);
+      dst[((c2 & 1) ? 0 : wp) + (c2 >> 1)] = v;
+    }
   }
 }
 
