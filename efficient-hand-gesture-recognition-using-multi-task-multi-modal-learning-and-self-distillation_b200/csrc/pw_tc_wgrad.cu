@@ -34,6 +34,88 @@ struct WgradArgs {
   int n_stages, stage_bytes;
 };
 
+// Asynchronous staging of one operand of a ring stage (32 rows x `groups` 8-channel groups): lane owns a
+// fixed channel group g = lane % G (G = power of two >= groups) and the rows rsub, rsub + 32/G, ...;
+// every 16-byte chunk is one cp.async straight into the MN-major core-matrix layout.  SHIFT is a gather
+// (neighbouring frame or zero fill); AFFINE is applied in place afterwards by the lane that copied the
+// chunk (coefficients of its fixed group live in registers for the whole kernel).
+struct WgLane {
+  int g, rsub, rstep;     // channel group, first row, row step
+  int cls;                // SHIFT class of the group: 0 -> frame t+dir, 1 -> t-dir, 2 -> same frame, 3 -> straddles
+  bool on;                // g < groups
+};
+
+__device__ __forceinline__ WgLane wg_lane(const RowOp& op, int c_base, int groups, int lane) {
+  WgLane w;
+  int lg = 0;
+  while ((1 << lg) < groups) ++lg;
+  w.g = lane & ((1 << lg) - 1);
+  w.rsub = lane >> lg;
+  w.rstep = 32 >> lg;
+  w.on = w.g < groups;
+  w.cls = 2;
+  if (op.mode == EHGR_ROW_SHIFT && w.on) {
+    const int c = c_base + w.g * 8, fold = op.fold;
+    const int cl = c < fold ? 0 : (c < 2 * fold ? 1 : 2);
+    const int ch = c + 7 < fold ? 0 : (c + 7 < 2 * fold ? 1 : 2);
+    w.cls = cl == ch ? cl : 3;
+  }
+  return w;
+}
+
+__device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_base, int C, uint32_t dst_base, int gs,
+                                        long long m_base, long long M) {
+  if (!w.on) return;
+  const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(op.in1);
+  const int c = c_base + w.g * 8;
+  int t0 = 0, rem0 = 0;
+  const int dir = op.shift_dir < 0 ? -1 : 1;
+  if (op.mode == EHGR_ROW_SHIFT && w.cls != 2) {
+    const long long f0 = m_base / op.hw;
+    rem0 = static_cast<int>(m_base - f0 * op.hw);
+    t0 = static_cast<int>(f0 % op.n_segment);
+  }
+  const long long step = static_cast<long long>(dir) * op.hw * C;
+#pragma unroll 4
+  for (int row = w.rsub; row < kMS; row += w.rstep) {
+    const long long m = m_base + row;
+    bool live = m < M;
+    const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
+    const __nv_bfloat16* src = in1 + m * C + c;
+    if (op.mode == EHGR_ROW_SHIFT && w.cls != 2 && live) {
+      if (w.cls == 3) {
+        sts128(dst, shift_straddle_raw<__nv_bfloat16, 8>(op, m, c, C));
+        continue;
+      }
+      int rem = rem0 + row, t = t0;
+      while (rem >= op.hw) { rem -= op.hw; t = t + 1 == op.n_segment ? 0 : t + 1; }
+      const int tt = w.cls == 0 ? t + dir : t - dir;
+      live = tt >= 0 && tt < op.n_segment;
+      src += w.cls == 0 ? step : -step;
+    }
+    cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+  }
+}
+
+__device__ __forceinline__ void wg_affine_inplace(const RowOp& op, const WgLane& w,
+                                                  const RowLoader<__nv_bfloat16, 8, false, false>& ld, uint32_t dst_base,
+                                                  int gs, long long m_base, long long M) {
+  if (!w.on) return;
+#pragma unroll 4
+  for (int row = w.rsub; row < kMS; row += w.rstep) {
+    if (m_base + row < M) {
+      const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
+      RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
+      raw.a = lds128(dst);
+      float v[8];
+      ld.finish(op, raw, v);
+      sts128(dst, pack8(v));
+    }
+  }
+}
+
+// kAsync: dy is PLAIN and a is PLAIN / AFFINE / SHIFT (what the fused chain issues); otherwise the register path.
+template <bool kAsync>
 __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int gs = kMS * 16;                              // bytes between channel groups inside a stage
@@ -72,58 +154,77 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
   const int pw = p.n_stages < kWgProducers ? p.n_stages : kWgProducers;   // see pw_tc.cu: parity aliasing
 
   if (warp < pw) {
-    using Ld = RowLoader<__nv_bfloat16, 8, true, true>;
-    uint32_t it = 0;
-    for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
-      if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
-      const int s = it % p.n_stages;
-      uint8_t* dy_dst = smem + s * p.stage_bytes;
-      uint8_t* a_dst = dy_dst + dy_bytes;
-      const long long m = mc * kMS + lane;               // lane = row of the stage
-      const bool row_ok = m < p.M;
-      const int row_off = (lane >> 3) * 128 + (lane & 7) * 16;
-      bool waited = false;
-      const int total = ng + kg;                          // channel groups of dy, then of a
-#pragma unroll 1
-      for (int g0 = 0; g0 < total; g0 += 4) {
-        Ld::Raw raw[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int g = g0 + j;
-          if (g < total && row_ok) {
-            Ld ld;
-            const bool is_a = g >= ng;
-            ld.c0 = is_a ? k0 + (g - ng) * 8 : n0 + g * 8;
-            ld.C = is_a ? p.K : p.N;
-            raw[j] = ld.fetch(is_a ? p.a : p.dy, m);
-          }
-        }
-        if (!waited) { mbar_wait(bar_empty + 8 * s, ((it / p.n_stages) & 1) ^ 1); waited = true; }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int g = g0 + j;
-          if (g < total) {
-            const bool is_a = g >= ng;
-            uint4 packed = make_uint4(0, 0, 0, 0);
-            if (row_ok) {
-              const RowOp& op = is_a ? p.a : p.dy;
-              if (op.mode == EHGR_ROW_PLAIN) {
-                packed = raw[j].a;                        // already bf16: a straight 16-byte copy
-              } else {
-                Ld ld;
-                float f[8];
-                ld.init(op, is_a ? k0 + (g - ng) * 8 : n0 + g * 8, is_a ? p.K : p.N);
-                ld.finish(op, raw[j], f);
-                packed = pack8(f);
-              }
-            }
-            uint8_t* dst = is_a ? a_dst + (g - ng) * gs : dy_dst + g * gs;
-            *reinterpret_cast<uint4*>(dst + row_off) = packed;
-          }
-        }
+    if constexpr (kAsync) {
+      const WgLane wl_dy = wg_lane(p.dy, n0, ng, lane), wl_a = wg_lane(p.a, k0, kg, lane);
+      RowLoader<__nv_bfloat16, 8, false, false> ld_a;
+      if (p.a.mode == EHGR_ROW_AFFINE && wl_a.on) ld_a.init(p.a, k0 + wl_a.g * 8, p.K);
+      uint32_t it = 0;
+      for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
+        if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
+        const int s = it % p.n_stages;
+        const uint32_t dy_dst = smem_base + s * p.stage_bytes, a_dst = dy_dst + dy_bytes;
+        mbar_wait(bar_empty + 8 * s, ((it / p.n_stages) & 1) ^ 1);
+        wg_copy(p.dy, wl_dy, n0, p.N, dy_dst, gs, mc * kMS, p.M);
+        wg_copy(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M);
+        cp_async_wait_all();
+        if (p.a.mode == EHGR_ROW_AFFINE) wg_affine_inplace(p.a, wl_a, ld_a, a_dst, gs, mc * kMS, p.M);
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
       }
-      fence_proxy_async();
-      mbar_arrive(bar_full + 8 * s);
+    } else {
+    using Ld = RowLoader<__nv_bfloat16, 8, true, true>;
+      uint32_t it = 0;
+      for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
+        if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
+        const int s = it % p.n_stages;
+        uint8_t* dy_dst = smem + s * p.stage_bytes;
+        uint8_t* a_dst = dy_dst + dy_bytes;
+        const long long m = mc * kMS + lane;               // lane = row of the stage
+        const bool row_ok = m < p.M;
+        const int row_off = (lane >> 3) * 128 + (lane & 7) * 16;
+        bool waited = false;
+        const int total = ng + kg;                          // channel groups of dy, then of a
+  #pragma unroll 1
+        for (int g0 = 0; g0 < total; g0 += 4) {
+          Ld::Raw raw[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int g = g0 + j;
+            if (g < total && row_ok) {
+              Ld ld;
+              const bool is_a = g >= ng;
+              ld.c0 = is_a ? k0 + (g - ng) * 8 : n0 + g * 8;
+              ld.C = is_a ? p.K : p.N;
+              raw[j] = ld.fetch(is_a ? p.a : p.dy, m);
+            }
+          }
+          if (!waited) { mbar_wait(bar_empty + 8 * s, ((it / p.n_stages) & 1) ^ 1); waited = true; }
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int g = g0 + j;
+            if (g < total) {
+              const bool is_a = g >= ng;
+              uint4 packed = make_uint4(0, 0, 0, 0);
+              if (row_ok) {
+                const RowOp& op = is_a ? p.a : p.dy;
+                if (op.mode == EHGR_ROW_PLAIN) {
+                  packed = raw[j].a;                        // already bf16: a straight 16-byte copy
+                } else {
+                  Ld ld;
+                  float f[8];
+                  ld.init(op, is_a ? k0 + (g - ng) * 8 : n0 + g * 8, is_a ? p.K : p.N);
+                  ld.finish(op, raw[j], f);
+                  packed = pack8(f);
+                }
+              }
+              uint8_t* dst = is_a ? a_dst + (g - ng) * gs : dy_dst + g * gs;
+              *reinterpret_cast<uint4*>(dst + row_off) = packed;
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * s);
+      }
     }
   } else if (warp == kWgMmaWarp && lane == 0 && my_chunks > 0) {
     const uint32_t idesc = make_idesc(128, p.BKc, 1, 1);     // both operands MN-major
@@ -201,8 +302,15 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   p.stage_bytes = (128 + p.BKc) * tc::kMS * 2;
   p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes) / p.stage_bytes));
   const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes;
-  cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
-  tc::pw_wgrad_tc_kernel<<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
+  const bool async = dy.mode == EHGR_ROW_PLAIN &&
+                     (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_SHIFT);
+  if (async) {
+    cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    tc::pw_wgrad_tc_kernel<true><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
+  } else {
+    cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    tc::pw_wgrad_tc_kernel<false><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
+  }
   return launch_status();
 }
 

@@ -219,6 +219,67 @@ def test_pw_wgrad_tcgen05(M, K, N):
     assert rel_err(dw.cpu(), dw_s.cpu().double()) < 2e-2
 
 
+@pytest.mark.parametrize("K,N", [(16, 96), (24, 144), (64, 384), (160, 960), (96, 24), (576, 160)])
+@pytest.mark.parametrize("a_mode", ["plain", "affine", "shift"])
+def test_pw_wgrad_tcgen05_async_operands(K, N, a_mode):
+    """The operand combinations the fused chain issues (dy materialised, a plain / lazily normalised / shifted):
+    staged with cp.async straight into the MN-major core-matrix layout."""
+    E = _E()
+    f = E.fused
+    dtype = torch.bfloat16
+    T, hw, clips = 4, 49, 3
+    M = clips * T * hw
+    g = _rand((M, N), 90).to(dtype)
+    a = _rand((M, K), 91).to(dtype)
+    s_a, b_a = _rand((K,), 92).abs() + 0.5, _rand((K,), 93)
+    gd, ad, sd_, bd = g.cuda(), a.cuda(), s_a.cuda(), b_a.cuda()
+    if a_mode == "plain":
+        a_op, aa = f.op_plain(ad), a.double()
+    elif a_mode == "affine":
+        a_op = f.op_affine(ad, sd_, bd, True)
+        aa = torch.clamp(a.double() * s_a.double() + b_a.double(), 0, 6).to(dtype).double()
+    else:
+        fold = K // 8
+        a_op = f.op_shift(ad, T, fold, hw)
+        x5 = a.double().view(clips, T, hw, K)
+        sh = torch.zeros_like(x5)
+        sh[:, :-1, :, :fold] = x5[:, 1:, :, :fold]
+        sh[:, 1:, :, fold:2 * fold] = x5[:, :-1, :, fold:2 * fold]
+        sh[:, :, :, 2 * fold:] = x5[:, :, :, 2 * fold:]
+        aa = sh.view(M, K)
+    dw = torch.zeros((N, K), dtype=torch.float32, device="cuda")
+    _call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(gd)), ctypes.byref(a_op), dw.data_ptr(), M, K, N, 1, 2, _sp())
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu(), g.double().t() @ aa) < 5e-3
+
+
+@pytest.mark.parametrize("K,N", [(16, 96), (24, 144), (32, 192), (64, 384), (160, 960), (96, 24)])
+def test_pw_gemm_tcgen05_shift_operand(K, N):
+    """SHIFT as a cp.async gather (incl. channel vectors that straddle a fold boundary), ragged last tile."""
+    E = _E()
+    f = E.fused
+    dtype = torch.bfloat16
+    T, hw, clips = 8, 49, 2
+    M = clips * T * hw
+    a = _rand((M, K), 94).to(dtype)
+    w = _rand((N, K), 95, (2.0 / K) ** 0.5)
+    ad, wd = a.cuda(), w.cuda()
+    fold = K // 8
+    x5 = a.double().view(clips, T, hw, K)
+    sh = torch.zeros_like(x5)
+    sh[:, :-1, :, :fold] = x5[:, 1:, :, :fold]
+    sh[:, 1:, :, fold:2 * fold] = x5[:, :-1, :, fold:2 * fold]
+    sh[:, :, :, 2 * fold:] = x5[:, :, :, 2 * fold:]
+    out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    _call("ehgr_pw_gemm", ctypes.byref(f.op_shift(ad, T, fold, hw)), wd.data_ptr(), 0, out.data_ptr(), 0, stats.data_ptr(),
+          M, K, N, 1, 2, _sp())
+    torch.cuda.synchronize()
+    want = sh.view(M, K) @ w.to(dtype).double().t()
+    assert rel_err(out.cpu(), want) < 1e-2
+    assert rel_err(stats[:N].cpu(), want.sum(0)) < 2e-3
+
+
 def test_pw_gemm_tcgen05_shift_prologue_full_size():
     """BASELINE config #2 size of the largest shifted layer (24->144 at 56x56, 256 frames): the shift
     fused into the GEMM A-load equals shift-then-GEMM."""
