@@ -57,11 +57,16 @@ __device__ __forceinline__ void stage_tile(const RowOp& op, const RowLoader<T, V
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (idx[j] < np) {
-        float v[V];
+        T* dst = smem + (static_cast<size_t>(idx[j]) * CV + cv) * V;
+        if constexpr (sizeof(T) == 2) {
+          *reinterpret_cast<uint4*>(dst) = in_img[j] ? ld.finish_packed(op, raw[j]) : make_uint4(0, 0, 0, 0);
+        } else {
+          float v[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) v[i] = 0.f;
-        if (in_img[j]) ld.finish(op, raw[j], v);
-        st_smem_vec<T>(smem + (static_cast<size_t>(idx[j]) * CV + cv) * V, v);
+          for (int i = 0; i < V; ++i) v[i] = 0.f;
+          if (in_img[j]) ld.finish(op, raw[j], v);
+          st_smem_vec<T>(dst, v);
+        }
       }
     }
   }
@@ -352,8 +357,15 @@ static int dw_bwd_tiled_launch(const RowOp& dy, const RowOp& a, const float* w, 
   return launch_status();
 }
 
+int dw_fwd_sw(const RowOp& a, const float* w, void* out, double* stats, int nt, int h, int wd, int c, int stride,
+              cudaStream_t s);
+
 int dw_fwd_tiled(const RowOp& a, const float* w, void* out, double* stats, int nt, int h, int wd, int c, int stride,
                  int dtype, cudaStream_t s) {
+  if (dtype == EHGR_BF16 && nt > 0) {   // bf16: asynchronous sliding-window kernels (dw_sw.cu)
+    const int st = dw_fwd_sw(a, w, out, stats, nt, h, wd, c, stride, s);
+    if (st != EHGR_E_UNSUPPORTED) return st;
+  }
   DwTile g;
   if (int st = dw_tile_geom(g, nt, h, wd, c, stride, dtype)) return st;
   if (g.items == 0) return EHGR_OK;

@@ -241,9 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
                   raw.a = lds128(dst);
                   raw.b[0].x = static_cast<uint32_t>(m & 0xffffffffLL);
                   raw.b[0].y = static_cast<uint32_t>(m >> 32);
-                  float v[8];
-                  ld.finish(p.a, raw, v);
-                  sts128(dst, pack8(v));
+                  sts128(dst, ld.finish_packed(p.a, raw));
                 }
               }
             }

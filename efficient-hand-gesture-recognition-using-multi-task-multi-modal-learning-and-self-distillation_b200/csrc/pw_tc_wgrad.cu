@@ -107,9 +107,7 @@ __device__ __forceinline__ void wg_affine_inplace(const RowOp& op, const WgLane&
       const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
       RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
       raw.a = lds128(dst);
-      float v[8];
-      ld.finish(op, raw, v);
-      sts128(dst, pack8(v));
+      sts128(dst, ld.finish_packed(op, raw));
     }
   }
 }

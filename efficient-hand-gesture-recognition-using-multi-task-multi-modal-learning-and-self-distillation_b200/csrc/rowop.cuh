@@ -78,6 +78,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// ---- packed helpers: a bf16x2 word <-> a float2 (Blackwell FFMA2 / FADD2 operate on register pairs) ----
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+// round-to-nearest pack with the negative half clamped to zero (ReLU folded into the conversion)
+__device__ __forceinline__ uint32_t f2_to_bf2_relu(float2 v) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_min6(uint32_t w) {
+  uint32_t d;
+  asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(w), "r"(0x40C040C0u));   // 6.0 is exact in bf16
+  return d;
+}
+
 template <>
 __device__ __forceinline__ void store_vec<__nv_bfloat16, 4>(__nv_bfloat16* __restrict__ p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
@@ -293,6 +309,47 @@ struct RowLoader {
       }
     }
     return r;
+  }
+
+  // finish() for bf16 storage with the result re-packed to its 16 bytes (shared-memory staging): packed
+  // FFMA2 arithmetic, ReLU folded into the conversion, min(.,6) on the packed halves.  Bit-identical to
+  // pack(finish()): rounding is monotonic and 6 is representable.
+  __device__ __forceinline__ uint4 finish_packed(const RowOp& op, const Raw& r) const {
+    static_assert(sizeof(T) == 2 && NV == 8, "finish_packed: bf16 storage only");
+    if (op.mode == EHGR_ROW_PLAIN || op.mode == EHGR_ROW_SHIFT) return r.a;
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+    uint32_t o[4];
+    if (op.mode == EHGR_ROW_AFFINE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 z = __ffma2_rn(bf2_to_f2(w[i]), make_float2(s[2 * i], s[2 * i + 1]), make_float2(b[2 * i], b[2 * i + 1]));
+        o[i] = op.relu6 ? bf2_min6(f2_to_bf2_relu(z)) : pack_bf16x2(z.x, z.y);
+      }
+      return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (kTwo && op.mode == EHGR_ROW_BNBWD) {
+      const uint32_t rw[4] = {r.b[0].x, r.b[0].y, r.b[0].z, r.b[0].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 g = bf2_to_f2(w[i]);
+        const float2 raw = bf2_to_f2(rw[i]);
+        if (op.relu6) {
+          const float2 z = __ffma2_rn(raw, make_float2(s[2 * i], s[2 * i + 1]), make_float2(b[2 * i], b[2 * i + 1]));
+          if (!(z.x > 0.f && z.x < 6.f)) g.x = 0.f;
+          if (!(z.y > 0.f && z.y < 6.f)) g.y = 0.f;
+        }
+        const int j = kTwo ? 2 * i : 0;
+        const float2 t = __ffma2_rn(make_float2(cb[j], cb[kTwo ? j + 1 : 0]), raw, make_float2(cc[j], cc[kTwo ? j + 1 : 0]));
+        const float2 v = __ffma2_rn(make_float2(ca[j], ca[kTwo ? j + 1 : 0]), g, t);
+        o[i] = pack_bf16x2(v.x, v.y);
+      }
+      return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    float v[NV];
+    finish(op, r, v);
+    uint4 out;
+    store_vec<T, NV>(reinterpret_cast<T*>(&out), v);
+    return out;
   }
 
   __device__ __forceinline__ void finish(const RowOp& op, const Raw& r, float (&v)[NV]) const {

@@ -98,6 +98,8 @@ def main():
         dw1 = torch.zeros(hid * cin, dtype=torch.float32, device="cuda")
         dw3 = torch.zeros(hid * cout, dtype=torch.float32, device="cuda")
         gx = torch.empty(m_in, cin, device="cuda", dtype=dt)
+        d1 = torch.randn(m_in, hid, device="cuda").to(dt)
+        d3 = torch.randn(m_out, cout, device="cuda").to(dt)
         es = 2
         tests = {
             "pw_fwd": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_plain(x)), w1.data_ptr(), 0, raw1.data_ptr(), 0, st1.data_ptr(),
@@ -107,12 +109,16 @@ def main():
             "pw_proj": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_affine(raw2, s2, b2, True)), w3.data_ptr(), 0, raw3.data_ptr(), 0,
                                           st3.data_ptr(), m_out, hid, cout, 1, args.engine, sp), f"project {hid}->{cout} @{ho}", m_out * (hid + cout) * es,
                         2 * m_out * hid * cout),
-            "pw_dgrad3": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_bnbwd(g3, raw3, ca3, cb3, cc3, s3, b3, False)), w3.data_ptr(), 1,
+            # backward of a pointwise layer as the chain issues it: d(raw) materialised once (row_apply),
+            # then dgrad and wgrad read it as a PLAIN operand
+            "draw3": (lambda: _lib.call("ehgr_row_apply", ctypes.byref(f.op_bnbwd(g3, raw3, ca3, cb3, cc3, s3, b3, False)), 0,
+                                        d3.data_ptr(), m_out, cout, 1, sp), f"d(raw) {cout} @{ho}", 3 * m_out * cout * es, 0),
+            "pw_dgrad3": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_plain(d3)), w3.data_ptr(), 1,
                                             g2.data_ptr(), 0, 0, m_out, cout, hid, 1, args.engine, sp), f"dgrad {cout}->{hid} @{ho}",
-                          m_out * (2 * cout + hid) * es, 2 * m_out * hid * cout),
-            "pw_wgrad3": (lambda: _lib.call("ehgr_pw_wgrad", ctypes.byref(f.op_bnbwd(g3, raw3, ca3, cb3, cc3, s3, b3, False)),
+                          m_out * (cout + hid) * es, 2 * m_out * hid * cout),
+            "pw_wgrad3": (lambda: _lib.call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(d3)),
                                             ctypes.byref(f.op_affine(raw2, s2, b2, True)), dw3.data_ptr(), m_out, hid, cout, 1, args.engine, sp),
-                          f"wgrad {cout}x{hid} @{ho}", m_out * (2 * cout + hid) * es, 2 * m_out * hid * cout),
+                          f"wgrad {cout}x{hid} @{ho}", m_out * (cout + hid) * es, 2 * m_out * hid * cout),
             "bn_reduce": (lambda: _lib.call("ehgr_bn_bwd_reduce", g2.data_ptr(), raw2.data_ptr(), s2.data_ptr(), b2.data_ptr(), 1,
                                             st1.data_ptr(), m_out, hid, 1, sp), f"bn-bwd reduce {hid} @{ho}", 2 * m_out * hid * es, 0),
             "dw_dgrad": (lambda: _lib.call("ehgr_dw_dgrad", ctypes.byref(f.op_bnbwd(g2, raw2, ca2, cb2, cc2, s2, b2, True)), w2.data_ptr(),
@@ -125,12 +131,14 @@ def main():
                                          ctypes.byref(f.op_affine(raw1, s1, b1, True)), w2.data_ptr(), g1.data_ptr(), dwg.data_ptr(),
                                          nt, h, h, hid, stride, 1, sp),
                        f"dw fused bwd {hid} @{h} s{stride}", (2 * m_out + 2 * m_in) * hid * es, 18 * (m_in + m_out) * hid),
-            "pw_dgrad1": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_bnbwd(g1, raw1, ca1, cb1, cc1, s1, b1, True)), w1.data_ptr(), 1,
+            "draw1": (lambda: _lib.call("ehgr_row_apply", ctypes.byref(f.op_bnbwd(g1, raw1, ca1, cb1, cc1, s1, b1, True)), 0,
+                                        d1.data_ptr(), m_in, hid, 1, sp), f"d(raw) {hid} @{h}", 3 * m_in * hid * es, 0),
+            "pw_dgrad1": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_plain(d1)), w1.data_ptr(), 1,
                                             gx.data_ptr(), 0, 0, m_in, hid, cin, 1, args.engine, sp), f"dgrad {hid}->{cin} @{h}",
-                          m_in * (2 * hid + cin) * es, 2 * m_in * hid * cin),
-            "pw_wgrad1": (lambda: _lib.call("ehgr_pw_wgrad", ctypes.byref(f.op_bnbwd(g1, raw1, ca1, cb1, cc1, s1, b1, True)),
+                          m_in * (hid + cin) * es, 2 * m_in * hid * cin),
+            "pw_wgrad1": (lambda: _lib.call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(d1)),
                                             ctypes.byref(f.op_plain(x)), dw1.data_ptr(), m_in, cin, hid, 1, args.engine, sp),
-                          f"wgrad {hid}x{cin} @{h}", m_in * (2 * hid + cin) * es, 2 * m_in * hid * cin),
+                          f"wgrad {hid}x{cin} @{h}", m_in * (hid + cin) * es, 2 * m_in * hid * cin),
             "row_apply": (lambda: _lib.call("ehgr_row_apply", ctypes.byref(f.op_affine(raw3, s3, b3, False)), g3.data_ptr(), raw3.data_ptr(),
                                             m_out, cout, 1, sp), f"bn-apply+res {cout} @{ho}", 3 * m_out * cout * es, 0),
         }
