@@ -236,6 +236,183 @@ dw_fwd_sw_kernel(RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused backward: d(a) and d(w) from ONE staging of rowop(dy) and rowop(a).
+//   stride 1: A tile and DY tile both (TH+2) x (TW+2) with origin (-1,-1); d(a) = conv_sweep over the DY tile
+//             with flipped taps.
+//   stride 2: A tile (2TH+1) x (2TW+1) origin (2ho0-1, 2wo0-1); DY tile (TH+1) x (TW+1) origin (ho0, wo0);
+//             thread (cv, ox) produces the input columns 2ox, 2ox+1 of the 2TH input rows the tile owns.
+//   d(w)   : generic sweep, acc9[kh*3+kw] += dy[oy][ox] * a[oy*S+kh][ox*S+kw], accumulated in registers over
+//            every tile the CTA visits.
+// ------------------------------------------------------------------------------------------------
+template <int STRIDE, int CVN, int IW, int IH, int TH, int DWID, int DOFF>
+__device__ __forceinline__ void wgrad_sweep(uint32_t a_tile, uint32_t d_tile, int cv, int ox, float2 (&acc9)[9][4]) {
+  float2 dsl[3][4];
+  const uint32_t abase = a_tile + static_cast<uint32_t>((ox * STRIDE * CVN + cv) * 16);
+  const uint32_t dbase = d_tile + static_cast<uint32_t>((((DOFF * DWID) + ox + DOFF) * CVN + cv) * 16);
+#pragma unroll
+  for (int iy = 0; iy < IH; ++iy) {
+    if (iy % STRIDE == 0 && iy / STRIDE < TH)
+      unpack8(lds128(dbase + static_cast<uint32_t>(((iy / STRIDE) * DWID * CVN) * 16)), dsl[(iy / STRIDE) % 3]);
+    float2 xa[3][4];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) unpack8(lds128(abase + static_cast<uint32_t>(((iy * IW + kw) * CVN) * 16)), xa[kw]);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int t = iy - kh;
+      if (t < 0 || (t % STRIDE) != 0 || t / STRIDE >= TH) continue;
+      const int slot = (t / STRIDE) % 3;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc9[kh * 3 + kw][i] = __ffma2_rn(dsl[slot][i], xa[kw][i], acc9[kh * 3 + kw][i]);
+    }
+  }
+}
+
+template <int STRIDE, int CVN, int TW, int TH>
+__global__ void __launch_bounds__(128, 2)
+dw_bwd_sw_kernel(RowOp dy, RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ da,
+                 float* __restrict__ dwgt, DwSw g) {
+  using Cfg = DwCfg<STRIDE, CVN, TW, TH>;
+  constexpr int DOFF = STRIDE == 1 ? 1 : 0;
+  constexpr int DH = TH + 1 + DOFF, DWID = TW + 1 + DOFF;          // dy tile
+  constexpr int DT_BYTES = DH * DWID * CVN * 16;
+  constexpr int CC = Cfg::CC;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t a_tile = smem_u32(smem), g_tile = a_tile + Cfg::TILE_BYTES, r_tile = g_tile + DT_BYTES;
+  float* s_w = reinterpret_cast<float*>(smem + Cfg::TILE_BYTES + 2 * DT_BYTES);   // [9][CC] taps (storage-rounded)
+  float* s_acc = s_w + 9 * CC;                                                     // [9][CC]
+  const int tid = threadIdx.x, cv = tid % CVN, col = tid / CVN;
+  const int chunk = blockIdx.x % g.n_chunks;
+  const int c_base = chunk * CC;
+  const int c0 = c_base + cv * 8;
+  const bool cv_on = c0 < g.c;
+  for (int i = tid; i < 9 * CC; i += 128) {
+    const int t = i / CC, c = i - t * CC;
+    s_w[i] = c_base + c < g.c ? round_to<__nv_bfloat16>(wgt[(c_base + c) * 9 + t]) : 0.f;
+    s_acc[i] = 0.f;
+  }
+  float2 acc9[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc9[t][i] = make_float2(0.f, 0.f);
+
+  const __nv_bfloat16* a_in = static_cast<const __nv_bfloat16*>(a.in1);
+  const __nv_bfloat16* g_in = static_cast<const __nv_bfloat16*>(dy.in1);
+  const __nv_bfloat16* r_in = static_cast<const __nv_bfloat16*>(dy.in2);
+  const bool two = dy.mode == EHGR_ROW_BNBWD;
+  const long long item_stride = gridDim.x / g.n_chunks;
+  for (long long item = blockIdx.x / g.n_chunks; item < g.items; item += item_stride) {
+    const int tx = static_cast<int>(item % g.tiles_x);
+    const long long r = item / g.tiles_x;
+    const int ho0 = static_cast<int>(r % g.tiles_y) * TH, wo0 = tx * TW;
+    const long long nt = r / g.tiles_y;
+    __syncthreads();                       // previous item's sweeps are done with the tiles
+    if (cv_on) {
+      tile_copy<Cfg::IH, Cfg::IW, CVN>(a_in, a_tile, nt, g.h, g.w, g.c, c0, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
+      tile_copy<DH, DWID, CVN>(g_in, g_tile, nt, g.ho, g.wo, g.c, c0, ho0 - DOFF, wo0 - DOFF, cv, col);
+      if (two) tile_copy<DH, DWID, CVN>(r_in, r_tile, nt, g.ho, g.wo, g.c, c0, ho0 - DOFF, wo0 - DOFF, cv, col);
+      tc::cp_async_wait_all();
+      if (a.mode != EHGR_ROW_PLAIN) {
+        RowLoader<__nv_bfloat16, 8, false, false> ld;
+        ld.init(a, c0, g.c);
+        tile_transform<Cfg::IH, Cfg::IW, CVN>(a, ld, a_tile, a_tile, g.h, g.w, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
+      }
+      if (two) {
+        RowLoader<__nv_bfloat16, 8, true, false> ld;
+        ld.init(dy, c0, g.c);
+        tile_transform<DH, DWID, CVN>(dy, ld, g_tile, r_tile, g.ho, g.wo, ho0 - DOFF, wo0 - DOFF, cv, col);
+      }
+    }
+    __syncthreads();
+    if (col < TW) {
+      // ---- weight gradient
+      wgrad_sweep<STRIDE, CVN, Cfg::IW, Cfg::IH, TH, DWID, DOFF>(a_tile, g_tile, cv, col, acc9);
+      // ---- input gradient
+      if constexpr (STRIDE == 1) {
+        float2 wf[9][4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 lo = *reinterpret_cast<const float4*>(s_w + (8 - t) * CC + cv * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(s_w + (8 - t) * CC + cv * 8 + 4);
+          wf[t][0] = make_float2(lo.x, lo.y); wf[t][1] = make_float2(lo.z, lo.w);
+          wf[t][2] = make_float2(hi.x, hi.y); wf[t][3] = make_float2(hi.z, hi.w);
+        }
+        const int wi = wo0 + col;
+        const bool st_ok = cv_on && wi < g.w;
+        __nv_bfloat16* orow = da + ((nt * g.h + ho0) * g.w + wi) * g.c + c0;
+        conv_sweep<1, CVN, DWID, DH, TH>(g_tile, cv, col, wf, [&](int oy, const float2 (&acc)[4]) {
+          if (st_ok && ho0 + oy < g.h) *reinterpret_cast<uint4*>(orow + static_cast<long long>(oy) * g.w * g.c) = pack8f2(acc);
+        });
+      } else {
+        float2 wt[9][4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 lo = *reinterpret_cast<const float4*>(s_w + t * CC + cv * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(s_w + t * CC + cv * 8 + 4);
+          wt[t][0] = make_float2(lo.x, lo.y); wt[t][1] = make_float2(lo.z, lo.w);
+          wt[t][2] = make_float2(hi.x, hi.y); wt[t][3] = make_float2(hi.z, hi.w);
+        }
+        const int wi = (wo0 + col) * 2;
+        const bool c0_ok = cv_on && wi < g.w, c1_ok = cv_on && wi + 1 < g.w;
+        __nv_bfloat16* orow = da + ((nt * g.h + ho0 * 2) * g.w + wi) * g.c + c0;
+        const long long rstride = static_cast<long long>(g.w) * g.c;
+        const uint32_t dbase = g_tile + static_cast<uint32_t>((col * CVN + cv) * 16);
+        float2 o0[4], o1[4];                 // the odd input row in flight (columns 2ox, 2ox+1)
+#pragma unroll
+        for (int j = 0; j < DH; ++j) {
+          float2 d0[4], d1[4];
+          unpack8(lds128(dbase + static_cast<uint32_t>((j * DWID * CVN) * 16)), d0);
+          unpack8(lds128(dbase + static_cast<uint32_t>(((j * DWID + 1) * CVN) * 16)), d1);
+          if (j >= 1) {                      // kh = 0 taps complete the odd row 2(j-1)+1
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              o0[i] = __ffma2_rn(d0[i], wt[1][i], o0[i]);
+              o1[i] = __ffma2_rn(d1[i], wt[0][i], __ffma2_rn(d0[i], wt[2][i], o1[i]));
+            }
+            const int hi = ho0 * 2 + 2 * (j - 1) + 1;
+            if (hi < g.h) {
+              if (c0_ok) *reinterpret_cast<uint4*>(orow + (2 * (j - 1) + 1) * rstride) = pack8f2(o0);
+              if (c1_ok) *reinterpret_cast<uint4*>(orow + (2 * (j - 1) + 1) * rstride + g.c) = pack8f2(o1);
+            }
+          }
+          if (j < TH) {
+            float2 e0[4], e1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              e0[i] = __fmul2_rn(d0[i], wt[4][i]);                                       // even row: kh = 1
+              e1[i] = __ffma2_rn(d1[i], wt[3][i], __fmul2_rn(d0[i], wt[5][i]));
+              o0[i] = __fmul2_rn(d0[i], wt[7][i]);                                       // odd row: kh = 2 now
+              o1[i] = __ffma2_rn(d1[i], wt[6][i], __fmul2_rn(d0[i], wt[8][i]));
+            }
+            const int hi = ho0 * 2 + 2 * j;
+            if (hi < g.h) {
+              if (c0_ok) *reinterpret_cast<uint4*>(orow + (2 * j) * rstride) = pack8f2(e0);
+              if (c1_ok) *reinterpret_cast<uint4*>(orow + (2 * j) * rstride + g.c) = pack8f2(e1);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (cv_on && col < TW) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(&s_acc[t * CC + cv * 8 + 2 * i], acc9[t][i].x);
+        atomicAdd(&s_acc[t * CC + cv * 8 + 2 * i + 1], acc9[t][i].y);
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * CC; i += 128) {
+    const int t = i / CC, c = i - t * CC;
+    if (c_base + c < g.c) atomicAdd(&dwgt[(c_base + c) * 9 + t], s_acc[i]);
+  }
+}
+
 template <int STRIDE, int CVN, int TW, int TH>
 static void dw_sw_geom(DwSw& g, int nt, int h, int w, int c) {
   g.nt = nt; g.h = h; g.w = w; g.c = c;
@@ -278,6 +455,36 @@ int dw_fwd_sw(const RowOp& a, const float* w, void* out, double* stats, int nt, 
   }
   if (wo <= 7) return dw_fwd_sw_go<2, 16, 7, 4>(a, w, out, stats, nt, h, wd, c, s);
   return dw_fwd_sw_go<2, 8, 14, 4>(a, w, out, stats, nt, h, wd, c, s);
+}
+
+template <int STRIDE, int CVN, int TW, int TH>
+static int dw_bwd_sw_go(const RowOp& dy, const RowOp& a, const float* w, void* da, float* dw, int nt, int h, int wd, int c,
+                        cudaStream_t s) {
+  using Cfg = DwCfg<STRIDE, CVN, TW, TH>;
+  constexpr int DOFF = STRIDE == 1 ? 1 : 0;
+  constexpr int DT_BYTES = (TH + 1 + DOFF) * (TW + 1 + DOFF) * CVN * 16;
+  DwSw g;
+  dw_sw_geom<STRIDE, CVN, TW, TH>(g, nt, h, wd, c);
+  const size_t smem = Cfg::TILE_BYTES + 2 * DT_BYTES + 18 * Cfg::CC * sizeof(float);
+  auto kern = dw_bwd_sw_kernel<STRIDE, CVN, TW, TH>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const int per_sm = std::max(1, std::min(2, static_cast<int>((220 * 1024) / (smem + 1024))));
+  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(dy, a, w, static_cast<__nv_bfloat16*>(da), dw, g);
+  return launch_status();
+}
+
+// bf16 fused backward; EHGR_E_UNSUPPORTED when an operand mode is outside {PLAIN, AFFINE} x {PLAIN, BNBWD}
+int dw_bwd_sw(const RowOp& dy, const RowOp& a, const float* w, void* da, float* dw, int nt, int h, int wd, int c,
+              int stride, cudaStream_t s) {
+  if (a.mode != EHGR_ROW_PLAIN && a.mode != EHGR_ROW_AFFINE) return EHGR_E_UNSUPPORTED;
+  if (dy.mode != EHGR_ROW_PLAIN && dy.mode != EHGR_ROW_BNBWD) return EHGR_E_UNSUPPORTED;
+  const int wo = (wd - 1) / stride + 1;
+  if (stride == 1) {
+    if (wo <= 7) return dw_bwd_sw_go<1, 16, 7, 7>(dy, a, w, da, dw, nt, h, wd, c, s);
+    return dw_bwd_sw_go<1, 8, 14, 14>(dy, a, w, da, dw, nt, h, wd, c, s);
+  }
+  if (wo <= 7) return dw_bwd_sw_go<2, 16, 7, 4>(dy, a, w, da, dw, nt, h, wd, c, s);
+  return dw_bwd_sw_go<2, 8, 14, 4>(dy, a, w, da, dw, nt, h, wd, c, s);
 }
 
 }  // namespace ehgr

@@ -360,6 +360,9 @@ static int dw_bwd_tiled_launch(const RowOp& dy, const RowOp& a, const float* w, 
 int dw_fwd_sw(const RowOp& a, const float* w, void* out, double* stats, int nt, int h, int wd, int c, int stride,
               cudaStream_t s);
 
+int dw_bwd_sw(const RowOp& dy, const RowOp& a, const float* w, void* da, float* dw, int nt, int h, int wd, int c,
+              int stride, cudaStream_t s);
+
 int dw_fwd_tiled(const RowOp& a, const float* w, void* out, double* stats, int nt, int h, int wd, int c, int stride,
                  int dtype, cudaStream_t s) {
   if (dtype == EHGR_BF16 && nt > 0) {   // bf16: asynchronous sliding-window kernels (dw_sw.cu)
@@ -388,6 +391,10 @@ extern "C" int ehgr_dw_bwd(const ehgr_rowop* dy, const ehgr_rowop* a, const floa
   if (!aligned_to(da, 16)) return EHGR_E_ALIGN;
   if (g.items == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_BF16) {   // bf16: asynchronous sliding-window kernel (dw_sw.cu)
+    const int st = dw_bwd_sw(*dy, *a, w, da, dw, nt, h, wd, c, stride, s);
+    if (st != EHGR_E_UNSUPPORTED) return st;
+  }
   return dtype == EHGR_F32 ? dw_bwd_tiled_launch<float>(*dy, *a, w, da, dw, g, s)
                            : dw_bwd_tiled_launch<__nv_bfloat16>(*dy, *a, w, da, dw, g, s);
 }
