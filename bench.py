@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--temporal", default="tsm", choices=["tsm", "action", "none"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     return ap.parse_args()
 
 
@@ -178,7 +179,7 @@ def run_ours(args):
                                        temporal_module=("tsm" if args.temporal == "tsm" else "action"))
     model = model.to(dev)
     model.train()
-    step = ehgr_b200.train_step.MTMMTrainStep(model, compute_dtype=dtype)
+    step = ehgr_b200.train_step.MTMMTrainStep(model, compute_dtype=dtype, use_graph=not args.no_graph)
 
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
@@ -194,12 +195,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    host_ms = {}
+
+    def timed(fn, steps, tag=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         fn(steps)
         e1.record()
+        if tag:
+            host_ms[tag] = (time.perf_counter() - t0) * 1e3 / steps    # host time to ENQUEUE a step
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -215,11 +221,18 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
-    prof = _lib.KernelTimer.begin()
-    ms = timed(leg_resident, args.steps)
-    kernel_times = _lib.KernelTimer.end(prof)
+    ms = timed(leg_resident, args.steps, "resident")
     launches = _lib.launch_count() - l0
+    if step.use_graph:      # replayed launches never pass through the host entry points: count what was captured
+        launches = step.launches_per_step * args.steps
     clocks = sampler.stop()
+    # the same K steps once more with a CUDA-event pair around every library kernel (per-kernel durations
+    # for the roofline object; kept out of the timed region above because 2 events per launch perturb it)
+    graph_mode, step.use_graph = step.use_graph, False       # per-kernel events need eager launches
+    prof = _lib.KernelTimer.begin()
+    ms_prof = timed(leg_resident, args.steps)
+    kernel_times = _lib.KernelTimer.end(prof)
+    step.use_graph = graph_mode
 
     # ---- leg 2: end to end from pinned host memory, next batch prefetched on a copy stream ----
     copy_stream = torch.cuda.Stream(device=dev)
@@ -258,12 +271,15 @@ def run_ours(args):
             "config": {"workload": f"MTMM stage-1 step (fwd+loss+bwd+allreduce+SGD), {args.temporal.upper()}-MobileNetV2 "
                                    f"RGB+pseudo-depth, 8x224^2, 83 classes, train-mode BN",
                        "clips_per_gpu": B, "global_clips": B * world, "parallelism": f"dp{world}",
+                       "launch": "one CUDA graph per step" if step.use_graph else "eager",
                        "l2": "activations >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG),
             "peaks": pk_kind,
+            "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
+            "ms_per_step_with_kernel_events": round(ms_prof / args.steps, 3),
         }
         if not args.no_cpu_baseline and world == 1:
             v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1)

@@ -1,8 +1,20 @@
 // api.cu — library-level entry points of libehgr_b200.so (version, status text, launch counter).
 #include "common.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace ehgr {
 std::atomic<long long> g_launches{0};
+
+void ensure_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> have;
+  std::lock_guard<std::mutex> lock(mu);
+  int& cur = have[func];
+  if (cur >= bytes) return;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess) cur = bytes;
+}
 }
 
 extern "C" int ehgr_abi_version(void) { return EHGR_ABI_VERSION; }

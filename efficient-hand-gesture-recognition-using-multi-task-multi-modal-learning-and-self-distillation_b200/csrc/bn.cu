@@ -64,20 +64,34 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const f
 #pragma unroll
     for (int i = 0; i < V; ++i) { a1[i] = a2[i] = 0.f; s[i] = 1.f; b[i] = 1.f; }
     if (relu6) { load_vec<float, V>(scale + c0, s); load_vec<float, V>(shift + c0, b); }
-#pragma unroll 2
-    for (long long m = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; m < M; m += row_stride) {
-      float gv[V], rv[V];
-      load_vec<T, V>(g + m * C + c0, gv);
-      load_vec<T, V>(raw + m * C + c0, rv);
+    constexpr int U = 4;                       // rows fetched per batch: 2U 16-byte loads in flight per thread
+#pragma unroll 1
+    for (long long m0 = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y; m0 < M; m0 += U * row_stride) {
+      uint4 gq[U], rq[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float gg = gv[i];
-        if (relu6) {
-          const float z = fmaf(rv[i], s[i], b[i]);
-          if (!(z > 0.f && z < 6.f)) gg = 0.f;
+      for (int j = 0; j < U; ++j) {
+        const long long m = m0 + j * row_stride;
+        gq[j] = rq[j] = make_uint4(0, 0, 0, 0);
+        if (m < M) {
+          gq[j] = *reinterpret_cast<const uint4*>(g + m * C + c0);
+          rq[j] = *reinterpret_cast<const uint4*>(raw + m * C + c0);
         }
-        a1[i] += gg;
-        a2[i] = fmaf(gg, rv[i], a2[i]);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        float gv[V], rv[V];
+        load_vec<T, V>(reinterpret_cast<const T*>(&gq[j]), gv);
+        load_vec<T, V>(reinterpret_cast<const T*>(&rq[j]), rv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float gg = gv[i];
+          if (relu6) {
+            const float z = fmaf(rv[i], s[i], b[i]);
+            if (!(z > 0.f && z < 6.f)) gg = 0.f;
+          }
+          a1[i] += gg;
+          a2[i] = fmaf(gg, rv[i], a2[i]);
+        }
       }
     }
 #pragma unroll
@@ -114,7 +128,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
 // out = rowop(a) (+ addend).  block = (bx channel vectors, P rows): a thread keeps ONE channel vector
 // (operand coefficients in registers) and strides over rows, four rows fetched per batch.
 template <typename T, bool kGate>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv_total) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;
@@ -185,7 +199,9 @@ extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* s
   int bx = cv;
   while (bx > 256) bx = (bx + 1) / 2;
   const dim3 block(bx, std::max(1, 256 / bx));
-  const long long blocks = std::max(1LL, std::min(cdiv(m, block.y), 8LL * kNumSMs));
+  // every CTA ends with 2C double atomics: cap the CTA count for wide layers (they have few rows anyway)
+  const long long cap = std::max<long long>(kNumSMs, std::min<long long>(8LL * kNumSMs, 300000LL / (2 * c)));
+  const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), cap));
   const size_t smem = static_cast<size_t>(2) * c * sizeof(float);
   cudaStream_t s = as_stream(stream);
   if (dtype == EHGR_F32)

@@ -19,6 +19,12 @@ inline int launch_status() {
   return e == cudaSuccess ? EHGR_OK : static_cast<int>(e);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per kernel (not on every launch: the call costs
+// host time and must not sit inside a CUDA-graph capture more often than needed); grows monotonically.
+void ensure_dyn_smem(const void* func, int bytes);
+template <typename K>
+inline void ensure_smem(K kernel, size_t bytes) { ensure_dyn_smem(reinterpret_cast<const void*>(kernel), static_cast<int>(bytes)); }
+
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 inline int esize_of(int dtype) { return dtype == EHGR_F32 ? 4 : dtype == EHGR_BF16 ? 2 : 0; }
 inline cudaStream_t as_stream(ehgr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

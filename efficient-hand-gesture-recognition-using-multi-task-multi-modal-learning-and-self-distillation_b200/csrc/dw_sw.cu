@@ -438,7 +438,7 @@ static int dw_fwd_sw_go(const RowOp& a, const float* w, void* out, double* stats
   dw_sw_geom<STRIDE, CVN, TW, TH>(g, nt, h, wd, c);
   const size_t smem = 2 * Cfg::TILE_BYTES + 2 * Cfg::CC * sizeof(float);
   auto kern = dw_fwd_sw_kernel<STRIDE, CVN, TW, TH>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  ensure_smem(kern, static_cast<int>(smem));
   const int per_sm = std::max(1, std::min(3, static_cast<int>((220 * 1024) / (smem + 1024))));
   kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(a, w, static_cast<__nv_bfloat16*>(out), stats, g);
   return launch_status();
@@ -467,7 +467,7 @@ static int dw_bwd_sw_go(const RowOp& dy, const RowOp& a, const float* w, void* d
   dw_sw_geom<STRIDE, CVN, TW, TH>(g, nt, h, wd, c);
   const size_t smem = Cfg::TILE_BYTES + 2 * DT_BYTES + 18 * Cfg::CC * sizeof(float);
   auto kern = dw_bwd_sw_kernel<STRIDE, CVN, TW, TH>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  ensure_smem(kern, static_cast<int>(smem));
   const int per_sm = std::max(1, std::min(2, static_cast<int>((220 * 1024) / (smem + 1024))));
   kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(dy, a, w, static_cast<__nv_bfloat16*>(da), dw, g);
   return launch_status();

@@ -321,10 +321,10 @@ static int dw_fwd_tiled_launch(const RowOp& a, const float* w, void* out, double
   const size_t smem = static_cast<size_t>(ih) * iw * g.cc * sizeof(T) + 2 * g.cc * sizeof(float);
   const unsigned grid = dw_tile_grid(g, 4);
   if (a.mode == EHGR_ROW_BNBWD) {
-    cudaFuncSetAttribute(dw_fwd_tiled_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    ensure_smem(dw_fwd_tiled_kernel<T, true>, 160 * 1024);
     dw_fwd_tiled_kernel<T, true><<<grid, 128, smem, s>>>(a, w, static_cast<T*>(out), stats, g);
   } else {
-    cudaFuncSetAttribute(dw_fwd_tiled_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    ensure_smem(dw_fwd_tiled_kernel<T, false>, 160 * 1024);
     dw_fwd_tiled_kernel<T, false><<<grid, 128, smem, s>>>(a, w, static_cast<T*>(out), stats, g);
   }
   return launch_status();
@@ -333,7 +333,7 @@ static int dw_fwd_tiled_launch(const RowOp& a, const float* w, void* out, double
 template <typename T, bool kTwo, int STRIDE>
 static void dw_bwd_tiled_go(const RowOp& dy, const RowOp& a, const float* w, void* da, float* dw, const DwTile& g,
                             unsigned grid, size_t smem, cudaStream_t s) {
-  cudaFuncSetAttribute(dw_bwd_tiled_kernel<T, kTwo, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  ensure_smem(dw_bwd_tiled_kernel<T, kTwo, STRIDE>, 200 * 1024);
   dw_bwd_tiled_kernel<T, kTwo, STRIDE><<<grid, 128, smem, s>>>(dy, a, w, static_cast<T*>(da), dw, g);
 }
 

@@ -443,10 +443,10 @@ int pw_gemm_tc(const RowOp& a, const float* w, int w_is_kn, void* out, const voi
   grid = std::max<long long>(p.n_chunks, grid / p.n_chunks * p.n_chunks);
   const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes;
   if (a.mode == EHGR_ROW_BNBWD) {
-    cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    ensure_smem(tc::pw_gemm_tc_kernel<false>, kBudget);
     tc::pw_gemm_tc_kernel<false><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
   } else {
-    cudaFuncSetAttribute(tc::pw_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    ensure_smem(tc::pw_gemm_tc_kernel<true>, kBudget);
     tc::pw_gemm_tc_kernel<true><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
   }
   return launch_status();

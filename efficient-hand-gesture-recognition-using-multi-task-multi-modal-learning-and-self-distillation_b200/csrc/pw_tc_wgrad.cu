@@ -303,10 +303,10 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   const bool async = dy.mode == EHGR_ROW_PLAIN &&
                      (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_SHIFT);
   if (async) {
-    cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    ensure_smem(tc::pw_wgrad_tc_kernel<true>, kBudget);
     tc::pw_wgrad_tc_kernel<true><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
   } else {
-    cudaFuncSetAttribute(tc::pw_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
+    ensure_smem(tc::pw_wgrad_tc_kernel<false>, kBudget);
     tc::pw_wgrad_tc_kernel<false><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
   }
   return launch_status();

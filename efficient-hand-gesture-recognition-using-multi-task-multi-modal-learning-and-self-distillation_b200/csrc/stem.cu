@@ -382,7 +382,7 @@ template <typename X, typename T>
 static void stem_fwd32_go(const void* x, const float* w, void* out, double* stats, const StemGeom& g, cudaStream_t s) {
   const int R = 4, bands = static_cast<int>(cdiv(g.ho, R)), wp = g.wo + 1;
   const size_t smem = (static_cast<size_t>(29) * kStemC + 3 * (2 * R + 1) * 2 * wp) * sizeof(float);
-  cudaFuncSetAttribute(stem_fwd32_kernel<X, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  ensure_smem(stem_fwd32_kernel<X, T>, 200 * 1024);
   const long long items = static_cast<long long>(g.nt) * bands;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 4LL * kNumSMs));
   stem_fwd32_kernel<X, T><<<grid, 128, smem, s>>>(static_cast<const X*>(x), w, static_cast<T*>(out), stats, g, R, bands, wp);
@@ -392,7 +392,7 @@ template <typename X, typename T>
 static void stem_wgrad32_go(const RowOp& dy, const void* x, float* dw, const StemGeom& g, cudaStream_t s) {
   const int R = 2, bands = static_cast<int>(cdiv(g.ho, R)), wp = g.wo + 1;
   const size_t smem = (static_cast<size_t>(3) * (2 * R + 1) * 2 * wp + static_cast<size_t>(8) * R * g.wo * 4) * sizeof(float);
-  cudaFuncSetAttribute(stem_wgrad32_kernel<X, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  ensure_smem(stem_wgrad32_kernel<X, T>, 200 * 1024);
   const long long items = static_cast<long long>(g.nt) * bands;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 1LL * kNumSMs));
   stem_wgrad32_kernel<X, T><<<grid, 384, smem, s>>>(dy, static_cast<const X*>(x), dw, g, R, bands, wp);

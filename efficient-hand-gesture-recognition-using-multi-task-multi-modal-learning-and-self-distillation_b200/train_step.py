@@ -112,7 +112,7 @@ def build_sgd(model, lr: float, momentum: float = 0.9, weight_decay: float = 5e-
 
 
 def adjust_learning_rate(learning_rate, optimizer, epoch, lr_steps):
-    """utils.py:39-46."""
+    """utils.py:39-46.  (A train step running in CUDA-graph mode must be told: ``invalidate_graph()``.)"""
     gamma = 0.1 ** sum(epoch >= s for s in lr_steps)
     for g in optimizer.param_groups:
         g['lr'] = learning_rate * gamma * g['lr_mult']
@@ -126,7 +126,7 @@ class MTMMTrainStep:
     """
 
     def __init__(self, model, lr=0.00125, momentum=0.9, weight_decay=5e-4, compute_dtype=torch.bfloat16,
-                 n_buckets=3, process_group=None):
+                 n_buckets=3, process_group=None, use_graph=False, graph_warmup=2):
         from . import fused
         self.model = model
         self.compute_dtype = compute_dtype
@@ -134,12 +134,23 @@ class MTMMTrainStep:
         self.opt = build_sgd(model, lr, momentum, weight_decay)
         self.buckets = GradBuckets(list(model.parameters()), n_buckets, process_group)
         self._fused = fused
+        # CUDA-graph mode: the step launches ~3600 small kernels; replaying one captured graph removes the
+        # host launch cost.  The first `graph_warmup` calls run eagerly (lazy state: momentum buffers, cuDNN
+        # plans, the allocator), the next call is captured with ITS batch in the static input buffers and
+        # replayed, so no training step is spent on warm-up data.
+        self.use_graph = bool(use_graph) and self.device.type == "cuda"
+        self.graph_warmup = graph_warmup
+        self._graph = None
+        self._static_in = None
+        self._static_loss = None
+        self._eager_calls = 0
+        self.launches_per_step = None      # libehgr_b200 kernel launches of one step (counted while capturing)
 
     def stage(self, rgb_h, depth_h, labels_h):
         return (rgb_h.to(self.device, non_blocking=True), depth_h.to(self.device, non_blocking=True),
                 labels_h.to(self.device, non_blocking=True))
 
-    def run(self, rgb, depth, labels):
+    def _step(self, rgb, depth, labels):
         from .losses import mtmm_loss
         self.buckets.zero()
         with self._fused.compute_dtype(self.compute_dtype):
@@ -149,6 +160,40 @@ class MTMMTrainStep:
         self.buckets.finish()
         self.opt.step()
         return loss.detach()
+
+    def invalidate_graph(self):
+        """Call after anything the captured graph has baked in changes (learning rate, train/eval mode,
+        frozen parameters, input shapes)."""
+        self._graph = None
+        self._static_in = None
+        self._static_loss = None
+
+    def run(self, *batch):
+        if not self.use_graph:
+            return self._step(*batch)
+        if self._graph is not None and any(a.shape != b.shape or a.dtype != b.dtype
+                                           for a, b in zip(batch, self._static_in)):
+            self.invalidate_graph()
+        if self._graph is None:
+            if self._eager_calls < self.graph_warmup:
+                self._eager_calls += 1
+                return self._step(*batch)
+            from . import _lib
+            self._static_in = [torch.empty_like(t) for t in batch]
+            for dst, src in zip(self._static_in, batch):
+                dst.copy_(src)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                self._static_loss = self._step(*self._static_in)
+            self.launches_per_step = _lib.launch_count() - l0
+            self._graph = graph
+        else:
+            for dst, src in zip(self._static_in, batch):
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
 
     def __call__(self, rgb_h, depth_h, labels_h) -> float:
         return float(self.run(*self.stage(rgb_h, depth_h, labels_h)).item())
@@ -169,7 +214,7 @@ class SDTrainStep(MTMMTrainStep):
     def stage(self, rgb_h, labels_h):
         return rgb_h.to(self.device, non_blocking=True), labels_h.to(self.device, non_blocking=True)
 
-    def run(self, rgb, labels):
+    def _step(self, rgb, labels):
         from .losses import sd_loss
         self.buckets.zero()
         with self._fused.compute_dtype(self.compute_dtype):

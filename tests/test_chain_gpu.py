@@ -265,3 +265,42 @@ def test_sd_step_against_oracle(dtype, tol):
            "grad": grad_err((k, v.grad) for k, v in sdy.items() if v.is_floating_point() and v.grad is not None)}
     for k in ours:
         assert ours[k] <= max(3.0 * ref[k], tol), (k, ours, ref)
+
+
+def test_train_step_cuda_graph_matches_eager():
+    """MTMMTrainStep in CUDA-graph mode (two eager warm-up calls, capture, replays) walks exactly the same
+    trajectory as the eager step: same losses, same parameters, same BatchNorm running statistics."""
+    import ehgr_b200 as E
+
+    def make():
+        sd0 = O.build_mtmm_state(83, "tsm", 8, seed=6)
+        with _quiet():
+            model = E.tsn_mtmm.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                                   dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                                   modal='rgb_depth', temporal_module='tsm')
+        model.load_state_dict(sd0, strict=True)
+        model = model.cuda().train()
+        for d in model.modules():
+            if isinstance(d, torch.nn.Dropout):
+                d.eval()
+        return model
+
+    batches = [tuple(t.cuda() for t in O.synthetic_clip_batch(2, 8, 64, 83, seed=20 + i)) for i in range(5)]
+    losses = {}
+    models = {}
+    for mode in (False, True):
+        model = make()
+        step = E.train_step.MTMMTrainStep(model, lr=0.01, compute_dtype=torch.bfloat16, use_graph=mode)
+        losses[mode] = [float(step.run(*b).item()) for b in batches]
+        models[mode] = model
+        if mode:
+            assert step._graph is not None and step.launches_per_step > 100
+    # atomics make the reductions order-dependent: equal to a few bf16 ulps of the trajectory, not bitwise
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-2 * abs(a), (losses[False], losses[True])
+    sd_e, sd_g = models[False].state_dict(), models[True].state_dict()
+    for k in sd_e:
+        if sd_e[k].is_floating_point():
+            assert rel_err(sd_g[k], sd_e[k]) < 5e-2, k
+        else:
+            assert torch.equal(sd_g[k], sd_e[k]), k
