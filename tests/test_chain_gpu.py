@@ -268,8 +268,10 @@ def test_sd_step_against_oracle(dtype, tol):
 
 
 def test_train_step_cuda_graph_matches_eager():
-    """MTMMTrainStep in CUDA-graph mode (two eager warm-up calls, capture, replays) walks exactly the same
-    trajectory as the eager step: same losses, same parameters, same BatchNorm running statistics."""
+    """MTMMTrainStep in CUDA-graph mode (two eager warm-up calls, capture, replays) walks the same trajectory
+    as the eager step.  Atomics make every run order-dependent and this random-weight problem amplifies
+    that, so the yardstick is a SECOND eager run: graph-vs-eager may not exceed eager-vs-eager by more than
+    a small factor.  fp32 storage keeps the noise floor low."""
     import ehgr_b200 as E
 
     def make():
@@ -286,21 +288,31 @@ def test_train_step_cuda_graph_matches_eager():
         return model
 
     batches = [tuple(t.cuda() for t in O.synthetic_clip_batch(2, 8, 64, 83, seed=20 + i)) for i in range(5)]
-    losses = {}
-    models = {}
-    for mode in (False, True):
-        model = make()
-        step = E.train_step.MTMMTrainStep(model, lr=0.01, compute_dtype=torch.bfloat16, use_graph=mode)
-        losses[mode] = [float(step.run(*b).item()) for b in batches]
-        models[mode] = model
-        if mode:
-            assert step._graph is not None and step.launches_per_step > 100
-    # atomics make the reductions order-dependent: equal to a few bf16 ulps of the trajectory, not bitwise
-    for a, b in zip(losses[False], losses[True]):
-        assert abs(a - b) <= 2e-2 * abs(a), (losses[False], losses[True])
-    sd_e, sd_g = models[False].state_dict(), models[True].state_dict()
-    for k in sd_e:
-        if sd_e[k].is_floating_point():
-            assert rel_err(sd_g[k], sd_e[k]) < 5e-2, k
-        else:
-            assert torch.equal(sd_g[k], sd_e[k]), k
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        runs = {}
+        for mode in ("eager", "eager2", "graph"):
+            model = make()
+            step = E.train_step.MTMMTrainStep(model, lr=1e-4, compute_dtype=torch.float32, use_graph=(mode == "graph"))
+            losses = [float(step.run(*b).item()) for b in batches]
+            runs[mode] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()})
+            if mode == "graph":
+                assert step._graph is not None and step.launches_per_step > 100
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+    def dist_to_eager(mode):
+        la, lb = runs["eager"][0], runs[mode][0]
+        dl = max(abs(a - b) / abs(a) for a, b in zip(la, lb))
+        sa, sb = runs["eager"][1], runs[mode][1]
+        for k in sa:
+            if not sa[k].is_floating_point():
+                assert torch.equal(sa[k], sb[k]), k
+        dp = max(rel_err(sb[k], sa[k]) for k in sa if sa[k].is_floating_point())
+        return dl, dp
+
+    noise_l, noise_p = dist_to_eager("eager2")
+    dl, dp = dist_to_eager("graph")
+    assert dl <= 10 * noise_l + 1e-5, (dl, noise_l)
+    assert dp <= 10 * noise_p + 1e-4, (dp, noise_p)
