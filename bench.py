@@ -288,7 +288,19 @@ def run_ours(args):
                                               f"port of the reference modules, {cores} threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A captured graph holds NCCL kernels: drop it and drain the device before the communicator goes
+        # away, then leave without the (occasionally hanging) communicator teardown.  The timer bounds
+        # whatever part of this still blocks.
+        sys.stdout.flush()
+        wd = threading.Timer(30.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        step.invalidate_graph()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
