@@ -112,6 +112,7 @@ SIGNATURES = {
     "ehgr_temporal_shift_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_temporal_shift_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_pw_gemm": [_R, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_pw_gemm_w16": [_R, _P, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_pw_wgrad": [_R, _R, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_dw_fwd": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_dw_dgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],

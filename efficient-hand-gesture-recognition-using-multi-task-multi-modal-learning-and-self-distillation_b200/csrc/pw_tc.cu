@@ -46,6 +46,7 @@ constexpr int kTailBytes = kBarBytes + 4 * 512 * 4;   // + per-epilogue-warp sta
 struct GemmArgs {
   RowOp a;
   const float* w;
+  const __nv_bfloat16* w16;   // optional bf16 mirror of w (same layout): B staged with cp.async
   int w_is_kn;
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
@@ -69,6 +70,23 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
                                         int tid, int nthreads) {
   const int kv = kvalid >> 3;
   const int nvec = (p.BN >> 3) * kvalid;
+  if (p.w16) {   // bf16 mirror: every 16-byte chunk is one asynchronous copy (the caller waits for them)
+    const uint32_t dst32 = smem_u32(dst);
+#pragma unroll 4
+    for (int v = tid; v < nvec; v += nthreads) {
+      const int x = v & 7, kg = (v >> 3) % kv, ng = (v >> 3) / kv;
+      const __nv_bfloat16* src = nullptr;
+      if (!p.w_is_kn) {
+        const int n = n0 + ng * 8 + x, k = k_base + kg * 8;
+        if (n < p.N && k < p.K) src = p.w16 + static_cast<size_t>(n) * p.K + k;
+      } else {
+        const int k = k_base + kg * 8 + x, n = n0 + ng * 8;
+        if (k < p.K && n < p.N) src = p.w16 + static_cast<size_t>(k) * p.N + n;
+      }
+      cp_async16(dst32 + ng * gs + kg * 128 + x * 16, src ? src : p.w16, src ? 16u : 0u);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int v0 = tid; v0 < nvec; v0 += 4 * nthreads) {
     float4 lo[4], hi[4];
@@ -141,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(p.tmem_cols));
   if (p.b_resident) {
     stage_b(p, smem, Kp * 16, n0, 0, Kp, threadIdx.x, kThreads);
+    cp_async_wait_all();
     fence_proxy_async();
   }
   tc_fence_before();
@@ -222,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
               cp_async16(dst, live ? src : in1, live ? 16u : 0u);
             }
           }
+          if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
           cp_async_wait_all();
           if (mode == EHGR_ROW_AFFINE || mode == EHGR_ROW_GATE) {
 #pragma unroll 1
@@ -287,7 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           }
         }
         }
-        if (!p.b_resident) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+        if (!p.b_resident && !(kAsync && p.w16)) {
+          stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+          cp_async_wait_all();
+        }
         fence_proxy_async();
         mbar_arrive(bar_full + 8 * s);
       }
@@ -413,10 +436,11 @@ bool pw_gemm_tc_supported(const RowOp& a, int w_is_kn, long long M, int K, int N
   return true;
 }
 
-int pw_gemm_tc(const RowOp& a, const float* w, int w_is_kn, void* out, const void* addend, double* stats,
-               long long M, int K, int N, cudaStream_t s) {
+int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, void* out, const void* addend,
+               double* stats, long long M, int K, int N, cudaStream_t s) {
   tc::GemmArgs p;
   p.a = a; p.w = w; p.w_is_kn = w_is_kn;
+  p.w16 = static_cast<const __nv_bfloat16*>(w16);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
   p.stats = stats;

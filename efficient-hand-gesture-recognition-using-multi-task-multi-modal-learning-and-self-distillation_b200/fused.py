@@ -66,6 +66,14 @@ def current_dtype():
 # ------------------------------------------------------------------------------------------------
 # row operands
 # ------------------------------------------------------------------------------------------------
+def _bf16_mirror(w, storage_dtype):
+    """bf16 copy of a pointwise-conv weight for the tensor-core engine's asynchronous B staging
+    (None for fp32 storage / the SIMT engine, which read the fp32 master weights)."""
+    if storage_dtype != torch.bfloat16 or _STATE["engine"] == 1:
+        return None
+    return w.detach().to(torch.bfloat16)
+
+
 def op_plain(t):
     return RowOp(mode=0, in1=t.data_ptr())
 
@@ -205,8 +213,9 @@ def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None):
                   algo_flops=2 * 27 * out.numel())
     elif st.kind == 'pw':
         m = nt * h * wd
-        _lib.call("ehgr_pw_gemm", ctypes.byref(a_op), w.data_ptr(), 0, out.data_ptr(), 0, stats_p, m, cin, cout,
-                  code, _STATE["engine"], sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
+        w16 = _bf16_mirror(w, out.dtype)
+        _lib.call("ehgr_pw_gemm_w16", ctypes.byref(a_op), w.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
+                  cin, cout, code, _STATE["engine"], sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
                   algo_flops=2 * m * cin * cout)
     else:
         _lib.call("ehgr_dw_fwd", ctypes.byref(a_op), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cin,
@@ -404,7 +413,8 @@ class _ChainFunction(torch.autograd.Function):
                         g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
                         # residual units without a shift: fold "+ g_unit_out" into the dgrad epilogue
                         fuse_res = si == 0 and u.residual and st.shift is None and act_state is None
-                        _lib.call("ehgr_pw_gemm", ctypes.byref(dy_op), w.data_ptr(), 1, g_prev.data_ptr(),
+                        w16 = _bf16_mirror(w, dt)
+                        _lib.call("ehgr_pw_gemm_w16", ctypes.byref(dy_op), w.data_ptr(), _lib.ptr(w16), 1, g_prev.data_ptr(),
                                   g_unit_out.data_ptr() if fuse_res else 0, 0, m_in, cout, cin, code,
                                   _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
                                   algo_flops=2 * m_in * cin * cout)

@@ -112,6 +112,13 @@ enum { EHGR_ENGINE_AUTO = 0, EHGR_ENGINE_SIMT = 1, EHGR_ENGINE_TCGEN05 = 2 };
  * ------------------------------------------------------------------------------------------- */
 int ehgr_pw_gemm(const ehgr_rowop* a, const float* w, int w_is_kn, void* out, const void* addend,
                  double* stats, long long M, int K, int N, int dtype, int engine, ehgr_stream_t stream);
+/* Same contract with the weights ALSO supplied as a bf16 mirror `w16` (same [N,K] / [K,N] layout as `w`,
+ * 16-byte aligned; the caller refreshes it after every optimiser step).  The tensor-core engine then
+ * stages the B operand with 16-byte asynchronous copies instead of converting fp32 -> bf16 in every CTA.
+ * The SIMT engine (fp32 storage) ignores w16.  w16 == NULL is exactly ehgr_pw_gemm. */
+int ehgr_pw_gemm_w16(const ehgr_rowop* a, const float* w, const void* w16, int w_is_kn, void* out,
+                     const void* addend, double* stats, long long M, int K, int N, int dtype, int engine,
+                     ehgr_stream_t stream);
 
 /* weight gradient of the same layer: dw[N,K] += sum_m rowop(dy)[m,n] * rowop(a)[m,k]   (fp32, atomics;
  * the caller zeroes dw).  dy is normally a BNBWD operand, a the layer's forward operand. */

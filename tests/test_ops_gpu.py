@@ -280,6 +280,29 @@ def test_pw_gemm_tcgen05_shift_operand(K, N):
     assert rel_err(stats[:N].cpu(), want.sum(0)) < 2e-3
 
 
+@pytest.mark.parametrize("M,K,N", [(300, 16, 96), (257, 96, 24), (400, 576, 160), (98, 960, 320), (392, 320, 1280), (64, 1280, 320)])
+@pytest.mark.parametrize("kn", [0, 1])
+def test_pw_gemm_w16_matches_fp32_weight_path(M, K, N, kn):
+    """ehgr_pw_gemm_w16 (bf16 weight mirror staged with cp.async; resident and streamed B) gives bit-identical
+    results to ehgr_pw_gemm (fp32 weights converted in the kernel): both round the weights to bf16 once."""
+    E = _E()
+    f = E.fused
+    dtype = torch.bfloat16
+    a = _rand((M, K), 96).to(dtype).cuda()
+    w = (_rand((N, K), 97, (2.0 / K) ** 0.5) if not kn else _rand((K, N), 97, (2.0 / K) ** 0.5)).cuda()
+    w16 = w.to(dtype)
+    scale, shift = (_rand((K,), 98).abs() + 0.5).cuda(), _rand((K,), 99).cuda()
+    outs = []
+    for mirror in (0, w16.data_ptr()):
+        out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
+        _call("ehgr_pw_gemm_w16", ctypes.byref(f.op_affine(a, scale, shift, True)), w.data_ptr(), mirror, kn, out.data_ptr(), 0, 0,
+              M, K, N, 1, 2, _sp())
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.isfinite(outs[1].float()).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_pw_gemm_tcgen05_shift_prologue_full_size():
     """BASELINE config #2 size of the largest shifted layer (24->144 at 56x56, 256 frames): the shift
     fused into the GEMM A-load equals shift-then-GEMM."""
