@@ -17,6 +17,10 @@ void ensure_dyn_smem(const void* func, int bytes) {
 }
 }
 
+namespace ehgr { int g_debug_flags = 0; }
+// undocumented bring-up switch (timing experiments only; results are wrong when set)
+extern "C" void ehgr_debug_set(int flags) { ehgr::g_debug_flags = flags; }
+
 extern "C" int ehgr_abi_version(void) { return EHGR_ABI_VERSION; }
 
 extern "C" long long ehgr_launch_count(void) { return ehgr::g_launches.load(std::memory_order_relaxed); }

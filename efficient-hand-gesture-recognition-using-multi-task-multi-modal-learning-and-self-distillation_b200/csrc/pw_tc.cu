@@ -37,11 +37,13 @@ constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int BK = 64;             // reduction elements per ring stage
 constexpr int kProducerWarps = 7;   // 12 warps = 384 threads: up to 168 registers per thread
 constexpr int kMmaWarp = kProducerWarps;
-constexpr int kThreads = (kProducerWarps + 1 + 4) * 32;   // 384
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, alternating 16-column chunks
+constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps) * 32;   // 512: up to 128 registers per thread
 constexpr int kMaxStages = 12;
 constexpr int kBatch = 4;                      // vectors a producer lane fetches before it converts any
-constexpr int kBarBytes = 256;                 // mbarriers + TMEM slot
-constexpr int kTailBytes = kBarBytes + 4 * 512 * 4;   // + per-epilogue-warp statistics accumulators
+constexpr int kMaxBufs = 8;                    // TMEM accumulator buffers (n_bufs * BN <= 512 columns)
+constexpr int kBarBytes = 512;                 // mbarriers + TMEM slot
+constexpr int kTailBytes = kBarBytes + kEpiWarps * 512 * 4;   // + per-epilogue-warp statistics accumulators
 
 struct GemmArgs {
   RowOp a;
@@ -56,11 +58,13 @@ struct GemmArgs {
   int BN;          // output columns per tile (multiple of 16, <= 256)
   int n_chunks;    // ceil(N / BN)
   int m_tiles;
-  int tmem_cols;   // power of two >= 2*BN
+  int tmem_cols;   // power of two >= n_bufs*BN
+  int n_bufs;      // accumulator buffers in TMEM: the tile hand-shake latency is spread over n_bufs tiles
   int b_resident;  // 1: whole [BN x Kp] B staged once; 0: a [BN x 64] slice per stage
   int n_stages;    // ring depth
   int a_bytes;     // bytes of the A part of a stage = 128 * min(Kp,64) * 2
   int stage_bytes; // a_bytes (+ BN*128 when B is streamed)
+  int dbg;
 };
 
 // B tile -> shared memory in core-matrix layout: group stride `gs` bytes, k-group stride 128.
@@ -139,20 +143,20 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
   // bars: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2]
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
-  const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + 2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + kMaxBufs);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks;
   const int n0 = chunk * p.BN;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(bar_full + 8 * s, 32);
+      mbar_init(bar_full + 8 * s, 1);          // one arrival per producer warp (lane 0, after __syncwarp)
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < p.n_bufs; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 128);
+      mbar_init(bar_tempty + 8 * b, kEpiWarps);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -175,17 +179,23 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
     // ===================== PRODUCERS (one warp per ring stage) =====================
     const int r = lane & 7, slot = lane >> 3;
     const int pw = p.n_stages < kProducerWarps ? p.n_stages : kProducerWarps;   // active producer warps
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x) {
-      const long long m0 = static_cast<long long>(tile / p.n_chunks) * BM;
-      for (int ks = 0; ks < k_stages; ++ks, ++it) {
+    // ring position kept with counters (no integer division in the per-stage path): s = it % n_stages,
+    // ph = (it / n_stages) & 1, turn = it % pw
+    int s = 0, turn = 0;
+    uint32_t ph = 0;
+    const int tile_step = gridDim.x / p.n_chunks;            // grid is a multiple of n_chunks
+    int m_tile = blockIdx.x / p.n_chunks;
+    for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x, m_tile += tile_step) {
+      const long long m0 = static_cast<long long>(m_tile) * BM;
+      for (int ks = 0; ks < k_stages; ++ks, ++turn, ++s) {
+        if (turn == pw) turn = 0;
+        if (s == p.n_stages) { s = 0; ph ^= 1; }
         // Stage i belongs to warp i % pw.  The empty-slot wait only tracks phase PARITY, so a producer
         // must never get two ring rounds ahead of the MMA warp: either pw == n_stages (a slot is only
         // ever filled by one warp, whose stages are sequential) or pw < n_stages (a warp's previous
         // stage was at most pw < n_stages stages back, and it waited for that slot's previous round).
-        if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
-        const int s = it % p.n_stages;
-        const uint32_t parity = ((it / p.n_stages) & 1) ^ 1;
+        if (turn != warp) continue;
+        const uint32_t parity = ph ^ 1;
         uint8_t* a_dst = ring + s * p.stage_bytes;
         const int k_base = ks * BK;
         const int kvalid = min(BK, Kp - k_base);     // multiple of 16
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
             t0 = static_cast<int>(f0 % p.a.n_segment);
           }
 #pragma unroll 1
-          for (int pass = 0; pass * 4 < kv; ++pass) {
+          for (int pass = 0; pass * 4 < kv && !(p.dbg & 8); ++pass) {
             const int k8 = pass * 4 + (slot % kvp);
             const int k = k_base + k8 * 8;
             const bool kin = k8 < kv && k < p.K;
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
                 live = tt >= 0 && tt < p.a.n_segment;
                 src += cls == 0 ? step : -step;
               }
-              cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+              if (!(p.dbg & 2)) cp_async16(dst, live ? src : in1, live ? 16u : 0u);
             }
           }
           if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
@@ -311,62 +321,76 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
           cp_async_wait_all();
         }
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * s);
+        if (!(p.dbg & 1)) fence_proxy_async();
+        __syncwarp();                                // every lane's writes are fenced before the single arrival
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA ISSUER =====================
     if (lane == 0) {
+      // The single issuing thread is the serial resource of the whole pipeline (its per-stage instruction
+      // count bounds the stage rate), so everything that does not change is hoisted: descriptor high words,
+      // the ring's start-address field per stage (incremental), K-steps of the last stage.
       const uint32_t idesc = make_idesc(BM, p.BN, 0, p.w_is_kn ? 1 : 0);
-      const uint32_t ring_addr = smem_u32(ring), bres_addr = smem_u32(smem);
-      uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t buf = tl & 1;
-        mbar_wait(bar_tempty + 8 * buf, ((tl >> 1) & 1) ^ 1);
+      const uint32_t hi_a = ((static_cast<uint32_t>(a_sbo) >> 4) & 0x3FFF) | (1u << 14);      // SBO | version
+      const uint32_t hi_b = ((p.b_resident ? static_cast<uint32_t>(Kp) : 64u) & 0x3FFF) | (1u << 14);   // SBO = Kp*16 or 1024 bytes
+      const uint32_t lbo = (128u >> 4) << 16;
+      const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFF) >> 4) | lbo, bres_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | lbo;
+      const uint32_t stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4, abytes16 = static_cast<uint32_t>(p.a_bytes) >> 4;
+      const int last_ksteps = (Kp - (k_stages - 1) * BK) >> 4;
+      auto desc = [](uint32_t lo, uint32_t hi) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      uint32_t ph = 0, a_lo = ring_lo, buf = 0, bph = 0;
+      int s = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++buf) {
+        if (buf == static_cast<uint32_t>(p.n_bufs)) { buf = 0; bph ^= 1; }
+        mbar_wait(bar_tempty + 8 * buf, bph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * static_cast<uint32_t>(p.BN);
-        for (int ks = 0; ks < k_stages; ++ks, ++it) {
-          const int s = it % p.n_stages;
-          mbar_wait(bar_full + 8 * s, (it / p.n_stages) & 1);
+        for (int ks = 0; ks < k_stages; ++ks, ++s, a_lo += stage16) {
+          if (s == p.n_stages) { s = 0; ph ^= 1; a_lo = ring_lo; }
+          mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t a_addr = ring_addr + s * p.stage_bytes;
-          const int ksteps = min(BK, Kp - ks * BK) >> 4;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            // one K=16 step = two 8-element core matrices along K = 256 bytes
-            const uint64_t da = make_desc(a_addr + kk * 256, 128, static_cast<uint32_t>(a_sbo));
-            const uint64_t db = p.b_resident
-                                    ? make_desc(bres_addr + (ks * 8 + kk * 2) * 128, 128, static_cast<uint32_t>(Kp) * 16)
-                                    : make_desc(a_addr + p.a_bytes + kk * 256, 128, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (ks | kk) ? 1u : 0u);
-          }
+          const int ksteps = ks == k_stages - 1 ? last_ksteps : BK / 16;
+          // one K=16 step = two 8-element core matrices along K = 256 bytes = 16 address units
+          const uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(ks) * 64u : a_lo + abytes16;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk)
+            if (kk < ksteps && !(p.dbg & 4))
+              umma_bf16(d_tmem, desc(a_lo + kk * 16, hi_a), desc(b_lo + kk * 16, hi_b), idesc, (ks | kk) ? 1u : 0u);
+          if (p.dbg & 32) mbar_arrive(bar_empty + 8 * s); else
           umma_commit(bar_empty + 8 * s);          // ring slot free once these MMAs have read it
         }
+        if (p.dbg & 32) mbar_arrive(bar_tfull + 8 * buf); else
         umma_commit(bar_tfull + 8 * buf);          // accumulator complete
       }
     }
   } else {
     // ===================== EPILOGUE =====================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int ew = warp - (kMmaWarp + 1);           // epilogue warp index 0..7
+    const int half = ew >> 2;                       // which of the quarter's two warps: chunks cc = half, half+2, ...
     const int n_cc = p.BN >> 4;                     // 16-column chunks
     // per-warp statistics accumulators live in shared memory (column index is dynamic); the chunk loop
     // is deliberately NOT unrolled: the kernel must stay small enough for the instruction cache
-    float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + q * 512;
+    float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + ew * 512;
     float* s_sq = s_sum + 256;
     const int col = (lane >> 1) & 15;
     if (p.stats) {
       for (int i = lane; i < 512; i += 32) s_sum[i] = 0.f;
       __syncwarp();
     }
-    uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const uint32_t buf = tl & 1;
-      const long long m = static_cast<long long>(tile / p.n_chunks) * BM + q * 32 + lane;
-      mbar_wait(bar_tfull + 8 * buf, (tl >> 1) & 1);
+    uint32_t buf = 0, bph = 0;
+    const int tile_step = gridDim.x / p.n_chunks;
+    int m_tile = blockIdx.x / p.n_chunks;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++buf, m_tile += tile_step) {
+      if (buf == static_cast<uint32_t>(p.n_bufs)) { buf = 0; bph ^= 1; }
+      const long long m = static_cast<long long>(m_tile) * BM + q * 32 + lane;
+      mbar_wait(bar_tfull + 8 * buf, bph);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * static_cast<uint32_t>(p.BN);
 #pragma unroll 1
-      for (int cc = 0; cc < n_cc; ++cc) {
+      for (int cc = half; cc < n_cc && !(p.dbg & 16); cc += 2) {
         {
           float v[16];
           tmem_ld16(t_base + cc * 16, v);
@@ -404,13 +428,14 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
     if (p.stats) {
       __syncwarp();
       for (int c = lane; c < p.BN; c += 32) {
         const int n = n0 + c;
-        if (n < p.N) {
+        if (n < p.N && ((c >> 4) & 1) == half) {
           atomicAdd(&p.stats[n], static_cast<double>(s_sum[c]));
           atomicAdd(&p.stats[p.N + n], static_cast<double>(s_sq[c]));
         }
@@ -441,6 +466,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   tc::GemmArgs p;
   p.a = a; p.w = w; p.w_is_kn = w_is_kn;
   p.w16 = static_cast<const __nv_bfloat16*>(w16);
+  p.dbg = g_debug_flags;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
   p.stats = stats;
@@ -448,8 +474,10 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   p.BN = tc::pick_bn(N);
   p.n_chunks = (N + p.BN - 1) / p.BN;
   p.m_tiles = static_cast<int>(cdiv(M, tc::BM));
+  p.n_bufs = 2;   // more buffers bought nothing (the hand-shake is not the bound) and a 512-column allocation
+                  // makes the next kernel's CTAs wait for TMEM
   int cols = 32;
-  while (cols < 2 * p.BN) cols <<= 1;
+  while (cols < p.n_bufs * p.BN) cols <<= 1;
   p.tmem_cols = cols;
   const int Kp = (K + 15) & ~15;
   constexpr int kBudget = 200 * 1024;

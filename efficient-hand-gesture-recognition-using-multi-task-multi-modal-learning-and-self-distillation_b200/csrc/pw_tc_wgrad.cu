@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(bar_full + 8 * s, 32);
+      mbar_init(bar_full + 8 * s, 1);          // one arrival per producer warp (lane 0, after __syncwarp)
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
@@ -156,18 +156,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
       const WgLane wl_dy = wg_lane(p.dy, n0, ng, lane), wl_a = wg_lane(p.a, k0, kg, lane);
       RowLoader<__nv_bfloat16, 8, false, false> ld_a;
       if (p.a.mode == EHGR_ROW_AFFINE && wl_a.on) ld_a.init(p.a, k0 + wl_a.g * 8, p.K);
-      uint32_t it = 0;
-      for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
-        if (static_cast<int>(it % static_cast<uint32_t>(pw)) != warp) continue;
-        const int s = it % p.n_stages;
+      int s = 0, turn = 0;
+      uint32_t ph = 0;
+      for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++s, ++turn) {
+        if (turn == pw) turn = 0;
+        if (s == p.n_stages) { s = 0; ph ^= 1; }
+        if (turn != warp) continue;
         const uint32_t dy_dst = smem_base + s * p.stage_bytes, a_dst = dy_dst + dy_bytes;
-        mbar_wait(bar_empty + 8 * s, ((it / p.n_stages) & 1) ^ 1);
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
         wg_copy(p.dy, wl_dy, n0, p.N, dy_dst, gs, mc * kMS, p.M);
         wg_copy(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M);
         cp_async_wait_all();
         if (p.a.mode == EHGR_ROW_AFFINE) wg_affine_inplace(p.a, wl_a, ld_a, a_dst, gs, mc * kMS, p.M);
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
     } else {
     using Ld = RowLoader<__nv_bfloat16, 8, true, true>;
@@ -221,15 +224,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
           }
         }
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
     }
   } else if (warp == kWgMmaWarp && lane == 0 && my_chunks > 0) {
     const uint32_t idesc = make_idesc(128, p.BKc, 1, 1);     // both operands MN-major
-    uint32_t it = 0;
-    for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it) {
-      const int s = it % p.n_stages;
-      mbar_wait(bar_full + 8 * s, (it / p.n_stages) & 1);
+    uint32_t it = 0, ph = 0;
+    int s = 0;
+    for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++it, ++s) {
+      if (s == p.n_stages) { s = 0; ph ^= 1; }
+      mbar_wait(bar_full + 8 * s, ph);
       tc_fence_after();
       const uint32_t dy_addr = smem_base + s * p.stage_bytes;
       const uint32_t a_addr = dy_addr + dy_bytes;

@@ -6,6 +6,7 @@
 namespace ehgr {
 namespace tc {
 
+constexpr uint32_t kSuspendHintNs = 0x989680u;       // let the hardware park a waiting warp (it then takes no issue slots)
 constexpr uint32_t kSpinLimit = 1u << 28;            // bounded waits: trap instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -21,7 +22,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
+        : "memory");
+    if (spin > kSpinLimit) __trap();
+  }
+}
+// warp-collective wait: lane 0 polls, the other 31 lanes wait at the warp barrier (32x fewer shared-memory
+// polls competing with the arrivals for the same pipeline).  Call from warp-uniform code only.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+// busy-polling wait (mbarrier.test_wait never parks the thread): for the single MMA-issuing thread, whose
+// wake-up latency is on the critical path of every ring stage
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity)

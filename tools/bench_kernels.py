@@ -56,7 +56,10 @@ def main():
     ap.add_argument("--blocks", default="")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--dbg", type=int, default=0)
     args = ap.parse_args()
+    if args.dbg:
+        _lib.lib().ehgr_debug_set(args.dbg)
     only = set(filter(None, args.only.split(",")))
     blocks = set(filter(None, args.blocks.split(",")))
     nt = args.frames
@@ -88,6 +91,7 @@ def main():
         w1 = torch.randn(hid, cin, device="cuda") * 0.2
         w2 = torch.randn(hid, 9, device="cuda") * 0.3
         w3 = torch.randn(cout, hid, device="cuda") * 0.05
+        w1h, w3h = w1.to(dt), w3.to(dt)     # bf16 mirrors, as the fused chain passes them
         s1, b1, s2, b2, s3, b3 = vec(hid), vec(hid, -.2, .2), vec(hid), vec(hid, -.2, .2), vec(cout), vec(cout, -.2, .2)
         ca1, cb1, cc1 = vec(hid), vec(hid, -.1, .1), vec(hid, -.1, .1)
         ca2, cb2, cc2 = vec(hid), vec(hid, -.1, .1), vec(hid, -.1, .1)
@@ -102,18 +106,18 @@ def main():
         d3 = torch.randn(m_out, cout, device="cuda").to(dt)
         es = 2
         tests = {
-            "pw_fwd": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_plain(x)), w1.data_ptr(), 0, raw1.data_ptr(), 0, st1.data_ptr(),
+            "pw_fwd": (lambda: _lib.call("ehgr_pw_gemm_w16", ctypes.byref(f.op_plain(x)), w1.data_ptr(), w1h.data_ptr(), 0, raw1.data_ptr(), 0, st1.data_ptr(),
                                          m_in, cin, hid, 1, args.engine, sp), f"expand {cin}->{hid} @{h}", m_in * (cin + hid) * es, 2 * m_in * cin * hid),
             "dw_fwd": (lambda: _lib.call("ehgr_dw_fwd", ctypes.byref(f.op_affine(raw1, s1, b1, True)), w2.data_ptr(), raw2.data_ptr(),
                                          st1.data_ptr(), nt, h, h, hid, stride, 1, sp), f"dw {hid} @{h} s{stride}", (m_in + m_out) * hid * es, 18 * m_out * hid),
-            "pw_proj": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_affine(raw2, s2, b2, True)), w3.data_ptr(), 0, raw3.data_ptr(), 0,
+            "pw_proj": (lambda: _lib.call("ehgr_pw_gemm_w16", ctypes.byref(f.op_affine(raw2, s2, b2, True)), w3.data_ptr(), w3h.data_ptr(), 0, raw3.data_ptr(), 0,
                                           st3.data_ptr(), m_out, hid, cout, 1, args.engine, sp), f"project {hid}->{cout} @{ho}", m_out * (hid + cout) * es,
                         2 * m_out * hid * cout),
             # backward of a pointwise layer as the chain issues it: d(raw) materialised once (row_apply),
             # then dgrad and wgrad read it as a PLAIN operand
             "draw3": (lambda: _lib.call("ehgr_row_apply", ctypes.byref(f.op_bnbwd(g3, raw3, ca3, cb3, cc3, s3, b3, False)), 0,
                                         d3.data_ptr(), m_out, cout, 1, sp), f"d(raw) {cout} @{ho}", 3 * m_out * cout * es, 0),
-            "pw_dgrad3": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_plain(d3)), w3.data_ptr(), 1,
+            "pw_dgrad3": (lambda: _lib.call("ehgr_pw_gemm_w16", ctypes.byref(f.op_plain(d3)), w3.data_ptr(), w3h.data_ptr(), 1,
                                             g2.data_ptr(), 0, 0, m_out, cout, hid, 1, args.engine, sp), f"dgrad {cout}->{hid} @{ho}",
                           m_out * (cout + hid) * es, 2 * m_out * hid * cout),
             "pw_wgrad3": (lambda: _lib.call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(d3)),
@@ -133,7 +137,7 @@ def main():
                        f"dw fused bwd {hid} @{h} s{stride}", (2 * m_out + 2 * m_in) * hid * es, 18 * (m_in + m_out) * hid),
             "draw1": (lambda: _lib.call("ehgr_row_apply", ctypes.byref(f.op_bnbwd(g1, raw1, ca1, cb1, cc1, s1, b1, True)), 0,
                                         d1.data_ptr(), m_in, hid, 1, sp), f"d(raw) {hid} @{h}", 3 * m_in * hid * es, 0),
-            "pw_dgrad1": (lambda: _lib.call("ehgr_pw_gemm", ctypes.byref(f.op_plain(d1)), w1.data_ptr(), 1,
+            "pw_dgrad1": (lambda: _lib.call("ehgr_pw_gemm_w16", ctypes.byref(f.op_plain(d1)), w1.data_ptr(), w1h.data_ptr(), 1,
                                             gx.data_ptr(), 0, 0, m_in, hid, cin, 1, args.engine, sp), f"dgrad {hid}->{cin} @{h}",
                           m_in * (hid + cin) * es, 2 * m_in * hid * cin),
             "pw_wgrad1": (lambda: _lib.call("ehgr_pw_wgrad", ctypes.byref(f.op_plain(d1)),
