@@ -226,6 +226,30 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
               const int ch = k + 7 < fold ? 0 : (k + 7 < 2 * fold ? 1 : 2);
               cls = cl == ch ? cl : 3;
             }
+            if (mode != EHGR_ROW_SHIFT || cls == 2) {
+              // plain copy: destination / source / live-row count advance by constants (no per-chunk index math)
+              if (k8 < kv) {
+                const int rg0 = slot / kvp;
+                const long long mrow = m0 + rg0 * 8 + r;
+                uint32_t dst = a_dst32 + rg0 * a_sbo + k8 * 128 + r * 16;
+                const __nv_bfloat16* src = in1 + mrow * p.K + k;
+                const long long left64 = kin ? p.M - mrow : 0;
+                int left = left64 > 4096 ? 4096 : static_cast<int>(left64);    // > 0: row exists
+                const uint32_t dst_step = static_cast<uint32_t>(f * a_sbo);
+                const long long src_step = 8LL * f * p.K;
+                if (!(p.dbg & 2)) {
+#pragma unroll 4
+                  for (int rg = rg0; rg < 16; rg += f) {
+                    const bool live = left > 0;
+                    cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+                    dst += dst_step;
+                    src += src_step;
+                    left -= 8 * f;
+                  }
+                }
+              }
+              continue;
+            }
             const int dir = p.a.shift_dir < 0 ? -1 : 1;
             const long long step = static_cast<long long>(dir) * p.a.hw * p.K;
 #pragma unroll 4

@@ -262,9 +262,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
       tmem_ld16(t_base + cc * 16, v);
       if (n < p.N) {
         float* dst = p.dw + static_cast<size_t>(n) * p.K + k0 + cc * 16;
+        // k_valid is a multiple of 8: whole 16-byte groups, one vector reduction each (4x fewer L2 atomics)
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (cc * 16 + i < k_valid) atomicAdd(dst + i, v[i]);
+        for (int i = 0; i < 16; i += 4)
+          if (cc * 16 + i < k_valid)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                         "f"(v[i + 2]), "f"(v[i + 3])
+                         : "memory");
       }
     }
     tc_fence_before();
