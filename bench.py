@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--temporal", default="tsm", choices=["tsm", "action", "none"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-input", choices=["uint8", "float32"], default="uint8",
+                    help="host batch format of the end-to-end leg: uint8 frames normalised on the device, or fp32")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
     return ap.parse_args()
 
@@ -188,7 +190,16 @@ def run_ours(args):
              torch.rand(B, T_SEG, 1, SIZE, SIZE, generator=g).pin_memory(),
              torch.randint(0, NUM_CLASS, (B,), generator=g).pin_memory()) for _ in range(n_host)]
     resident = [tuple(t.to(dev) for t in h) for h in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    # end-to-end leg: the host batch is what a video loader holds before ToTorchFormatTensor / GroupNormalize —
+    # uint8 frames (RGB) and uint8 pseudo-depth maps; the normalisation runs on the device (ehgr_normalize_u8).
+    # --e2e-input float32 ships the already-normalised fp32 tensors instead (4x the bytes).
+    if args.e2e_input == "uint8":
+        host_e2e = [(torch.randint(0, 256, (B, T_SEG, 3, SIZE, SIZE), dtype=torch.uint8, generator=g).pin_memory(),
+                     torch.randint(0, 256, (B, T_SEG, 1, SIZE, SIZE), dtype=torch.uint8, generator=g).pin_memory(),
+                     h[2]) for h in host]
+    else:
+        host_e2e = host
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_e2e[0])
 
     def barrier():
         if world > 1:
@@ -240,7 +251,7 @@ def run_ours(args):
     def leg_e2e(k):
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
-            nxt = step.stage(*host[0])
+            nxt = step.stage(*host_e2e[0])
         last = None
         for i in range(k):
             cur.wait_stream(copy_stream)
@@ -249,14 +260,14 @@ def run_ours(args):
                 t.record_stream(cur)
             if i + 1 < k:
                 with torch.cuda.stream(copy_stream):
-                    nxt = step.stage(*host[(i + 1) % n_host])
+                    nxt = step.stage(*host_e2e[(i + 1) % n_host])
             loss = step.run(*batch)
             if last is not None:
                 last.item()          # D2H read of the previous step's loss (keeps one step in flight)
             last = loss
         last.item()
 
-    leg_e2e(2)
+    leg_e2e(max(args.warmup, 5))     # new input format: eager warm-up calls + graph capture happen here, untimed
     ms_e2e = timed(leg_e2e, args.steps)
 
     if rank == 0:
@@ -273,7 +284,9 @@ def run_ours(args):
                        "clips_per_gpu": B, "global_clips": B * world, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if step.use_graph else "eager",
                        "l2": "activations >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
-            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "host_batch": ("uint8 frames + uint8 depth maps, normalised on the device" if args.e2e_input == "uint8"
+                                   else "normalised fp32 tensors")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG),

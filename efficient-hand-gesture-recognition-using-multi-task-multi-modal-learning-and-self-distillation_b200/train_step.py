@@ -118,6 +118,35 @@ def adjust_learning_rate(learning_rate, optimizer, epoch, lr_steps):
         g['lr'] = learning_rate * gamma * g['lr_mult']
 
 
+def normalize_u8(frames: torch.Tensor, mean=None, std=None, out_dtype=torch.float32) -> torch.Tensor:
+    """uint8 frames [..., C, H, W] on the GPU -> (x / 255 - mean[c]) / std[c], the device end of the
+    reference's ToTorchFormatTensor(div=True) + GroupNormalize (models/spatial_transforms.py:66-80,489-503);
+    bit-identical to those CPU ops for fp32 output.  mean / std: sequences of C floats or None (x / 255 only)."""
+    from . import _lib
+    _lib.require_cuda(frames)
+    if frames.dtype != torch.uint8:
+        raise TypeError("normalize_u8 expects uint8 frames")
+    frames = frames.contiguous()
+    c, h, w = frames.shape[-3:]
+    out = torch.empty(frames.shape, dtype=out_dtype, device=frames.device)
+    m = torch.tensor(list(mean), dtype=torch.float32, device=frames.device) if mean is not None else None
+    sd = torch.tensor(list(std), dtype=torch.float32, device=frames.device) if std is not None else None
+    _lib.call("ehgr_normalize_u8", frames.data_ptr(), out.data_ptr(), frames.numel() // (h * w), c, h * w, _lib.ptr(m),
+              _lib.ptr(sd), 255.0, _lib.dtype_code(out), _lib.stream_ptr(frames.device),
+              algo_bytes=frames.numel() * (1 + out.element_size()))
+    return out
+
+
+def _normalize_with(frames, mean_t, std_t):
+    from . import _lib
+    frames = frames.contiguous()
+    c, h, w = frames.shape[-3:]
+    out = torch.empty(frames.shape, dtype=torch.float32, device=frames.device)
+    _lib.call("ehgr_normalize_u8", frames.data_ptr(), out.data_ptr(), frames.numel() // (h * w), c, h * w, _lib.ptr(mean_t),
+              _lib.ptr(std_t), 255.0, _lib.F32, _lib.stream_ptr(frames.device), algo_bytes=frames.numel() * 5)
+    return out
+
+
 class MTMMTrainStep:
     """One MTMM stage-1 step (train_mtmm.py:205-245) on this rank's shard of clips.
 
@@ -144,14 +173,27 @@ class MTMMTrainStep:
         self._static_in = None
         self._static_loss = None
         self._eager_calls = 0
+        self._mean_std = None
+        if self.device.type == "cuda" and hasattr(model, "input_mean"):
+            self._mean_std = (torch.tensor(model.input_mean, dtype=torch.float32, device=self.device),
+                              torch.tensor(model.input_std, dtype=torch.float32, device=self.device))
         self.launches_per_step = None      # libehgr_b200 kernel launches of one step (counted while capturing)
 
     def stage(self, rgb_h, depth_h, labels_h):
         return (rgb_h.to(self.device, non_blocking=True), depth_h.to(self.device, non_blocking=True),
                 labels_h.to(self.device, non_blocking=True))
 
+    def _prepare(self, rgb, depth=None):
+        """uint8 frames (the loader's native format) are normalised on the device; float input passes through."""
+        if rgb.dtype == torch.uint8:
+            rgb = _normalize_with(rgb, *self._mean_std)
+        if depth is not None and depth.dtype == torch.uint8:
+            depth = _normalize_with(depth, None, None)
+        return rgb, depth
+
     def _step(self, rgb, depth, labels):
         from .losses import mtmm_loss
+        rgb, depth = self._prepare(rgb, depth)
         self.buckets.zero()
         with self._fused.compute_dtype(self.compute_dtype):
             logits, dpred = self.model(rgb)
@@ -174,6 +216,7 @@ class MTMMTrainStep:
         if self._graph is not None and any(a.shape != b.shape or a.dtype != b.dtype
                                            for a, b in zip(batch, self._static_in)):
             self.invalidate_graph()
+            self._eager_calls = 0          # new shapes / dtypes: warm up eagerly again before re-capturing
         if self._graph is None:
             if self._eager_calls < self.graph_warmup:
                 self._eager_calls += 1
@@ -216,6 +259,7 @@ class SDTrainStep(MTMMTrainStep):
 
     def _step(self, rgb, labels):
         from .losses import sd_loss
+        rgb, _ = self._prepare(rgb)
         self.buckets.zero()
         with self._fused.compute_dtype(self.compute_dtype):
             outs = self.model(rgb)

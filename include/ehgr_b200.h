@@ -182,6 +182,17 @@ int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out, long long
                    ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N4  device-side end of the input pipeline: uint8 frames -> normalised float planes.
+ *   dst[p][i] = (float(src[p][i]) / div - mean[c]) / std[c],  c = p % channels, evaluated in fp32 in
+ *   exactly the order ToTorchFormatTensor(div=True) + GroupNormalize use on the CPU
+ *   (models/spatial_transforms.py:66-80,489-503), so an fp32 dst is bit-identical to the reference's
+ *   CPU tensors.  src: [n_planes, plane] uint8 (NCHW frames: n_planes = frames*channels, plane = H*W),
+ *   dst: same shape, fp32 or bf16.  mean/std: device float[channels], NULL = 0 / 1 (depth maps: div only).
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_normalize_u8(const void* src, void* dst, long long n_planes, int channels, long long plane,
+                      const float* mean, const float* stdv, float div, int dst_dtype, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K10  classifier head: x.mean(3).mean(2) (archs/mobilenet_v2.py:112), new_fc and the segment
  *   consensus (models/models.py:341-356, models/basic_ops.py:9-37).
  *   pool_fwd : pooled[nt,c] (fp32) = mean over hw rows of rowop(a)

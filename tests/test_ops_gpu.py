@@ -529,3 +529,23 @@ def test_losses_match_reference_fixtures():
     (loss * 2.0).backward()     # exercises the incoming-gradient scaling
     assert rel_err(lg.grad.cpu() / 2, torch.from_numpy(z["mt_glogits"])) < 1e-5
     assert rel_err(pred.grad.cpu() / 2, torch.from_numpy(z["mt_gpred"])) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# N4: uint8 frames normalised on the device == the reference's CPU ToTorchFormatTensor + GroupNormalize
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 4, 3, 32, 32), (1, 2, 3, 17, 20), (3, 1, 1, 56, 56)])
+def test_normalize_u8_bit_exact(shape):
+    E = _E()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 256, shape, dtype=torch.uint8, generator=g)
+    c = shape[2]
+    mean, std = ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]) if c == 3 else (None, None)
+    want = x.float().div(255)                                  # ToTorchFormatTensor(div=True)
+    if mean is not None:                                        # GroupNormalize: t.sub_(m).div_(s) per channel
+        for ci in range(c):
+            want[:, :, ci].sub_(mean[ci]).div_(std[ci])
+    got = E.train_step.normalize_u8(x.cuda(), mean, std)
+    assert torch.equal(got.cpu(), want)
+    got16 = E.train_step.normalize_u8(x.cuda(), mean, std, out_dtype=torch.bfloat16)
+    assert torch.equal(got16.cpu(), want.to(torch.bfloat16))
