@@ -108,6 +108,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of each library kernel, from the committed ncu capture of this same workload
+    (profiles/r1_traffic.json; produced by the command named inside it) — never measured under the timer."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)["bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def quiet():
     return contextlib.redirect_stdout(io.StringIO())
 
@@ -289,7 +300,7 @@ def run_ours(args):
                                    else "normalised fp32 tensors")},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG),
+            "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG, ncu_traffic()),
             "peaks": pk_kind,
             "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
             "ms_per_step_with_kernel_events": round(ms_prof / args.steps, 3),

@@ -189,7 +189,7 @@ def call(name: str, *args, algo_bytes: int = 0, algo_flops: int = 0) -> None:
     r["flops"] += int(algo_flops)
 
 
-def roofline_entry(kernel_times: dict, peaks: dict, peaks_kind: str, frames: int):
+def roofline_entry(kernel_times: dict, peaks: dict, peaks_kind: str, frames: int, traffic: dict = None):
     """bench.py `roofline` object for the dominant (largest total time) kernel of this library."""
     if not kernel_times:
         return None
@@ -205,7 +205,7 @@ def roofline_entry(kernel_times: dict, peaks: dict, peaks_kind: str, frames: int
         "achieved": round(tfl if tensor_bound else hbm, 2),
         "peak": peaks["bf16_tflops_sustained"] if tensor_bound else peaks["hbm_gbs"],
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
-        "traffic": None, "peak_source": peaks_kind,
+        "traffic": (traffic or {}).get(name), "peak_source": peaks_kind,
         "launches": r["launches"], "avg_us": round(r["ms"] * 1e3 / max(1, r["launches"]), 2),
         "share_of_library_kernel_time": round(r["ms"] / total_ms, 4) if total_ms > 0 else None,
         "algo_bytes_per_launch": r["bytes"] // max(1, r["launches"]),

@@ -27,7 +27,22 @@ import torch.nn as nn
 from . import _lib, action_ops
 from ._lib import RowOp
 
-_STATE = {"dtype": torch.float32, "engine": 0}
+_STATE = {"dtype": torch.float32, "engine": 0, "grad_sink": None}
+
+
+@contextlib.contextmanager
+def grad_sink(sink):
+    """While active, chain backward writes parameter gradients straight into ``sink``'s buffers
+    (``sink.view_for(p)`` -> zero-initialised fp32 tensor shaped like p, or None) instead of returning
+    them to autograd, and reports finished parameters with ``sink.mark_done(params)``.  Used by
+    train_step.GradBuckets: no per-parameter accumulate kernels, no second gradient buffer.  Every chain
+    parameter may be used once per backward while a sink is active (BatchNorm gradients are stored, not added)."""
+    old = _STATE["grad_sink"]
+    _STATE["grad_sink"] = sink
+    try:
+        yield
+    finally:
+        _STATE["grad_sink"] = old
 
 
 @contextlib.contextmanager
@@ -324,9 +339,14 @@ class _ChainFunction(torch.autograd.Function):
         stages = [s for u in units for s in u.stages]
         sizes = [p.numel() for p in params]
         # every parameter gradient of the chain, each on a 32-byte boundary (vector stores / atomics)
-        gflat = torch.zeros(sum((n + 7) // 8 * 8 for n in sizes), dtype=torch.float32, device=dev)
+        sink = _STATE["grad_sink"]
+        sunk = [sink.view_for(p) if sink is not None else None for p in params]
+        gflat = torch.zeros(sum((n + 7) // 8 * 8 for n, sv in zip(sizes, sunk) if sv is None), dtype=torch.float32, device=dev)
         gviews, off = [], 0
-        for p, n in zip(params, sizes):
+        for p, n, sv in zip(params, sizes, sunk):
+            if sv is not None:
+                gviews.append(sv)
+                continue
             gviews.append(gflat[off:off + n].view(p.shape))
             off += (n + 7) // 8 * 8
         sum_arena = torch.zeros(sum(2 * s.conv.out_channels for s in stages), dtype=torch.float64, device=dev)
@@ -407,7 +427,8 @@ class _ChainFunction(torch.autograd.Function):
                     dy_op = op_plain(draw)
                 if st.kind == 'pw':
                     _lib.call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), gw.data_ptr(), m_in, cin, cout,
-                              code, _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
+                              code, _STATE["engine"], sp,
+                              algo_bytes=((1 if dy_op.mode == 0 else 2) * cout + cin) * m_in * es + cin * cout * 4,
                               algo_flops=2 * m_in * cin * cout)
                     if need_dgrad:
                         g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
@@ -416,7 +437,8 @@ class _ChainFunction(torch.autograd.Function):
                         w16 = _bf16_mirror(w, dt)
                         _lib.call("ehgr_pw_gemm_w16", ctypes.byref(dy_op), w.data_ptr(), _lib.ptr(w16), 1, g_prev.data_ptr(),
                                   g_unit_out.data_ptr() if fuse_res else 0, 0, m_in, cout, cin, code,
-                                  _STATE["engine"], sp, algo_bytes=(2 * cout + cin) * m_in * es,
+                                  _STATE["engine"], sp,
+                                  algo_bytes=((1 if dy_op.mode == 0 else 2) * cout + cin * (2 if fuse_res else 1)) * m_in * es,
                                   algo_flops=2 * m_in * cin * cout)
                 else:
                     # fused backward: one shared-memory staging of rowop(dy) and rowop(a) per tile gives
@@ -446,11 +468,13 @@ class _ChainFunction(torch.autograd.Function):
                     _lib.call("ehgr_row_apply", ctypes.byref(op_plain(g)), g_unit_out.data_ptr(), gx.data_ptr(),
                               nt * h * wd, cin, code, sp, algo_bytes=3 * g.numel() * es)
                     g = gx
+            if sink is not None:   # this unit's parameter gradients are complete (stream order): buckets may go
+                sink.mark_done([p for p, sv in zip(params[p_begin:p_end], sunk[p_begin:p_end]) if sv is not None])
             p_end = p_begin
         gx = None
         if need_x_grad and g is not None:
             gx = g if g.dtype == ctx.x_in.dtype else g.to(ctx.x_in.dtype)
-        pg = [gv if p.requires_grad else None for gv, p in zip(gviews, params)]
+        pg = [gv if (p.requires_grad and sv is None) else None for gv, p, sv in zip(gviews, params, sunk)]
         return (None, None, gx, *pg)
 
 

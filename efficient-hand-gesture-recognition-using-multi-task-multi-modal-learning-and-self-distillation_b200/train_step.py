@@ -35,7 +35,11 @@ class GradBuckets:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.average = average
         order = list(reversed(self.params))          # backward order first -> contiguous slices per bucket
-        total = sum(p.numel() for p in order)
+
+        def pad(n):                                   # every slice on a 32-byte boundary: the chain's kernels
+            return (n + 7) // 8 * 8                   # write their weight gradients straight into it
+
+        total = sum(pad(p.numel()) for p in order)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self._slices, self._bucket_of, off = [], {}, 0
         per_bucket = -(-total // max(1, n_buckets))
@@ -47,7 +51,7 @@ class GradBuckets:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             self._bucket_of[id(p)] = b
-            off += n
+            off += pad(n)
             bounds[b][1] = off
         self.bounds = bounds
         self._need = [0] * len(bounds)
@@ -82,8 +86,23 @@ class GradBuckets:
     def _on_grad(self, p):
         b = self._bucket_of[id(p)]
         self._left[b] -= 1
-        if self._left[b] == 0:
+        if self._left[b] == 0 and self.world > 1:
             self._launch(b)
+
+    # -- gradient sink protocol (fused.grad_sink): the fused chain writes into the flat buffer itself ------
+    def view_for(self, p):
+        """The zeroed flat-buffer slice for parameter p, or None if p is not managed here."""
+        if id(p) not in self._bucket_of or p.grad is None:
+            return None
+        g = p.grad
+        lo = self.flat.data_ptr()
+        if g.dtype != torch.float32 or not (lo <= g.data_ptr() < lo + self.flat.numel() * 4) or not g.is_contiguous():
+            return None                      # someone replaced .grad: fall back to autograd accumulation
+        return g
+
+    def mark_done(self, params):
+        for p in params:
+            self._on_grad(p)
 
     def finish(self):
         """Call after backward: flush buckets whose hooks did not all fire (unused parameters) and
@@ -198,7 +217,8 @@ class MTMMTrainStep:
         with self._fused.compute_dtype(self.compute_dtype):
             logits, dpred = self.model(rgb)
             loss, _ = mtmm_loss(logits, labels, dpred, depth)
-        loss.backward()
+        with self._fused.grad_sink(self.buckets):
+            loss.backward()
         self.buckets.finish()
         self.opt.step()
         return loss.detach()
@@ -264,7 +284,8 @@ class SDTrainStep(MTMMTrainStep):
         with self._fused.compute_dtype(self.compute_dtype):
             outs = self.model(rgb)
             total, _terms = sd_loss(outs[:4], outs[4:], labels, self.alpha, self.beta, self.temperature)
-        total.backward()
+        with self._fused.grad_sink(self.buckets):
+            total.backward()
         self.buckets.finish()
         self.opt.step()
         return total.detach()

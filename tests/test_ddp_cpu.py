@@ -23,7 +23,9 @@ def _worker(rank, world, port, out):
     params = [torch.nn.Parameter(torch.randn(s)) for s in ((7, 3), (5,), (2, 2, 2), (11,), (1,))]
     gb = ehgr_b200.train_step.GradBuckets(params, n_buckets=3)
     assert gb.world == world and 2 <= len(gb.bounds) <= 3
-    assert sum(hi - lo for lo, hi in gb.bounds) == sum(p.numel() for p in params)
+    # slices are padded to 8 floats (32-byte boundaries: the fused chain writes weight gradients in place)
+    assert sum(hi - lo for lo, hi in gb.bounds) == sum((p.numel() + 7) // 8 * 8 for p in params)
+    assert all(lo % 8 == 0 for lo, _ in gb.bounds)
     for step in range(2):
         gb.zero()
         # a fake backward in reverse parameter order: every rank contributes (rank+1) * (index+1)
@@ -36,6 +38,18 @@ def _worker(rank, world, port, out):
             expect = ((want * (i + 1)) + step)
             assert torch.allclose(p.grad, torch.full_like(p, expect)), (rank, i, p.grad.flatten()[:3], expect)
             assert p.grad.data_ptr() >= gb.flat.data_ptr()          # grads are views of the flat buffer
+    # gradient-sink protocol (fused.grad_sink): a producer writes into the flat slices itself and reports
+    # finished parameters; autograd never sees those gradients
+    gb.zero()
+    for i, p in reversed(list(enumerate(params))):
+        v = gb.view_for(p)
+        assert v is not None and v.data_ptr() == p.grad.data_ptr() and float(v.abs().sum()) == 0.0
+        v.add_(float((rank + 1) * (i + 1)))
+        gb.mark_done([p])
+    gb.finish()
+    for i, p in enumerate(params):
+        assert torch.allclose(p.grad, torch.full_like(p, want * (i + 1))), (rank, i)
+    assert gb.view_for(torch.nn.Parameter(torch.zeros(3))) is None
     # unused parameter: its bucket is flushed by finish()
     gb.zero()
     (params[0] * 2.0).sum().backward()

@@ -24,7 +24,7 @@ batches = [tuple(t.cuda() for t in O.synthetic_clip_batch(2, 8, 64, 83, seed=20 
 traj = {}
 for mode in ("eager", "eager2", "graph"):
     model = make()
-    step = E.train_step.MTMMTrainStep(model, lr=0.01, compute_dtype=torch.bfloat16, use_graph=(mode == "graph"))
+    step = E.train_step.MTMMTrainStep(model, lr=1e-4, compute_dtype=torch.float32, use_graph=(mode == "graph"))
     rec = []
     for b in batches:
         loss = float(step.run(*b).item())
