@@ -75,19 +75,35 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
   const int kv = kvalid >> 3;
   const int nvec = (p.BN >> 3) * kvalid;
   if (p.w16) {   // bf16 mirror: every 16-byte chunk is one asynchronous copy (the caller waits for them)
+    // Lanes run along the CONTIGUOUS direction of the weight array (k-chunks of one row n for the K-major
+    // form, n-chunks of one row k for the MN-major form): coalesced 128-byte reads, no per-chunk division.
     const uint32_t dst32 = smem_u32(dst);
+    if (!p.w_is_kn) {
+      const int kg = tid & 7, step = nthreads >> 3;
+      const int k = k_base + kg * 8;
+      const bool k_ok = kg < kv && k < p.K;
+      if (kg < kv) {
 #pragma unroll 4
-    for (int v = tid; v < nvec; v += nthreads) {
-      const int x = v & 7, kg = (v >> 3) % kv, ng = (v >> 3) / kv;
-      const __nv_bfloat16* src = nullptr;
-      if (!p.w_is_kn) {
-        const int n = n0 + ng * 8 + x, k = k_base + kg * 8;
-        if (n < p.N && k < p.K) src = p.w16 + static_cast<size_t>(n) * p.K + k;
-      } else {
-        const int k = k_base + kg * 8 + x, n = n0 + ng * 8;
-        if (k < p.K && n < p.N) src = p.w16 + static_cast<size_t>(k) * p.N + n;
+        for (int nl = tid >> 3; nl < p.BN; nl += step) {
+          const int n = n0 + nl;
+          const bool ok = k_ok && n < p.N;
+          cp_async16(dst32 + (nl >> 3) * gs + kg * 128 + (nl & 7) * 16, ok ? p.w16 + static_cast<size_t>(n) * p.K + k : p.w16,
+                     ok ? 16u : 0u);
+        }
       }
-      cp_async16(dst32 + ng * gs + kg * 128 + x * 16, src ? src : p.w16, src ? 16u : 0u);
+    } else {
+      const int ng = tid & 31, step = nthreads >> 5;
+      const int n = n0 + ng * 8;
+      const bool n_ok = n < p.N;
+      if (ng < (p.BN >> 3)) {
+#pragma unroll 4
+        for (int kl = tid >> 5; kl < kvalid; kl += step) {
+          const int k = k_base + kl;
+          const bool ok = n_ok && k < p.K;
+          cp_async16(dst32 + ng * gs + (kl >> 3) * 128 + (kl & 7) * 16, ok ? p.w16 + static_cast<size_t>(k) * p.N + n : p.w16,
+                     ok ? 16u : 0u);
+        }
+      }
     }
     return;
   }
