@@ -1,6 +1,8 @@
 // api.cu — library-level entry points of libehgr_b200.so (version, status text, launch counter).
 #include "common.cuh"
 
+#include <cuda.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -20,6 +22,40 @@ void ensure_dyn_smem(const void* func, int bytes) {
 namespace ehgr { int g_debug_flags = 0; }
 // undocumented bring-up switch (timing experiments only; results are wrong when set)
 extern "C" void ehgr_debug_set(int flags) { ehgr::g_debug_flags = flags; }
+
+namespace ehgr {
+namespace tma {
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int make_nhwc_bf16_map(CUtensorMap* out, const void* base, int nt, int h, int w, int c, int box_c, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return EHGR_E_UNSUPPORTED;
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                              static_cast<cuuint64_t>(nt)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
+                                 static_cast<cuuint64_t>(h) * w * c * 2};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EHGR_OK : EHGR_E_UNSUPPORTED;
+}
+}  // namespace tma
+}  // namespace ehgr
 
 extern "C" int ehgr_abi_version(void) { return EHGR_ABI_VERSION; }
 

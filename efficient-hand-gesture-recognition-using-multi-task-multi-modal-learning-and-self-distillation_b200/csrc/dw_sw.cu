@@ -15,11 +15,15 @@
 //
 //   CVN = 8  (64 channels / chunk), 16 columns of threads, output tile 14 wide   (maps >= 14 wide)
 //   CVN = 16 (128 channels / chunk), 8 columns of threads, output tile  7 wide   (7x7 maps, 14 -> 7)
-#include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace ehgr {
 
 using tc::cp_async16;
+using tc::fence_mbar_init;
+using tc::fence_proxy_async;
+using tc::mbar_init;
+using tc::mbar_wait;
 using tc::lds128;
 using tc::smem_u32;
 using tc::sts128;
@@ -137,12 +141,20 @@ __device__ __forceinline__ void conv_sweep(uint32_t tile, int cv, int ox, const 
 
 template <int STRIDE, int CVN, int TW, int TH>
 __global__ void __launch_bounds__(128, 3)
-dw_fwd_sw_kernel(RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ out, double* __restrict__ stats, DwSw g) {
+dw_fwd_sw_kernel(RowOp a, const __grid_constant__ CUtensorMap tm_a, const float* __restrict__ wgt,
+                 __nv_bfloat16* __restrict__ out, double* __restrict__ stats, DwSw g) {
   using Cfg = DwCfg<STRIDE, CVN, TW, TH>;
   using Ld = RowLoader<__nv_bfloat16, 8, false, false>;
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_stat = reinterpret_cast<float*>(smem + 2 * Cfg::TILE_BYTES);   // [2][CC]
   const uint32_t tile0 = smem_u32(smem);
+  const uint32_t bar0 = smem_u32(s_stat + 2 * Cfg::CC);                    // two mbarriers: one per tile buffer
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+    tma::prefetch_map(&tm_a);
+  }
   const int tid = threadIdx.x, cv = tid % CVN, col = tid / CVN;
   const int chunk = blockIdx.x % g.n_chunks;
   const int c0 = chunk * Cfg::CC + cv * 8;
@@ -165,9 +177,15 @@ dw_fwd_sw_kernel(RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restri
 #pragma unroll
   for (int i = 0; i < 4; ++i) tsum[i] = tsq[i] = make_float2(0.f, 0.f);
 
-  const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(a.in1);
+  const int c_base = chunk * Cfg::CC;
   const long long item_stride = gridDim.x / g.n_chunks;
   const long long first = blockIdx.x / g.n_chunks;
+  // One TMA box = the whole input tile (+halo) of this channel chunk: [IH][IW][CC] bf16 lands exactly in the
+  // layout the sweeps read; coordinates outside the image and channels beyond C are zero-filled.
+  auto issue = [&](uint32_t dst, uint32_t bar, long long nt, int ho0, int wo0) {
+    tma::expect_tx(bar, Cfg::TILE_BYTES);
+    tma::load_4d(dst, &tm_a, bar, c_base, wo0 * STRIDE - 1, ho0 * STRIDE - 1, static_cast<int>(nt));
+  };
   auto origin = [&](long long item, long long& nt, int& ho0, int& wo0) {
     const int tx = static_cast<int>(item % g.tiles_x);
     const long long r = item / g.tiles_x;
@@ -175,25 +193,25 @@ dw_fwd_sw_kernel(RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restri
     wo0 = tx * TW;
     nt = r / g.tiles_y;
   };
-  if (first < g.items && cv_on) {
+  __syncthreads();                                       // barriers initialised
+  if (first < g.items && tid == 0) {
     long long nt; int ho0, wo0;
     origin(first, nt, ho0, wo0);
-    tile_copy<Cfg::IH, Cfg::IW, CVN>(in1, tile0, nt, g.h, g.w, g.c, c0, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
+    issue(tile0, bar0, nt, ho0, wo0);
   }
-  cp_async_commit();
   int buf = 0;
+  uint32_t phase[2] = {0, 0};
   for (long long item = first; item < g.items; item += item_stride, buf ^= 1) {
     long long nt; int ho0, wo0;
     origin(item, nt, ho0, wo0);
     const uint32_t tile = tile0 + buf * Cfg::TILE_BYTES;
-    if (item + item_stride < g.items && cv_on) {        // prefetch the next tile into the other buffer
+    if (item + item_stride < g.items && tid == 0) {      // prefetch the next tile into the other buffer
       long long nt2; int ho2, wo2;
       origin(item + item_stride, nt2, ho2, wo2);
-      tile_copy<Cfg::IH, Cfg::IW, CVN>(in1, tile0 + (buf ^ 1) * Cfg::TILE_BYTES, nt2, g.h, g.w, g.c, c0, ho2 * STRIDE - 1,
-                                       wo2 * STRIDE - 1, cv, col);
+      issue(tile0 + (buf ^ 1) * Cfg::TILE_BYTES, bar0 + 8 * (buf ^ 1), nt2, ho2, wo2);
     }
-    cp_async_commit();
-    cp_async_wait_group<1>();                          // this tile's copies have landed (the next one's may not)
+    mbar_wait(bar0 + 8 * buf, phase[buf]);               // this tile has landed (the next one may still be in flight)
+    phase[buf] ^= 1;
     if (cv_on && a.mode != EHGR_ROW_PLAIN)
       tile_transform<Cfg::IH, Cfg::IW, CVN, Ld>(a, ld, tile, tile, g.h, g.w, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
     __syncthreads();
@@ -212,9 +230,9 @@ dw_fwd_sw_kernel(RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restri
         }
       });
     }
+    fence_proxy_async();                                // generic-proxy accesses of this buffer precede the next TMA write
     __syncthreads();                                    // the buffer is free for the prefetch after next
   }
-  cp_async_wait_group<0>();
   if (stats) {
     if (cv_on && col < TW) {
 #pragma unroll
@@ -436,11 +454,13 @@ static int dw_fwd_sw_go(const RowOp& a, const float* w, void* out, double* stats
   using Cfg = DwCfg<STRIDE, CVN, TW, TH>;
   DwSw g;
   dw_sw_geom<STRIDE, CVN, TW, TH>(g, nt, h, wd, c);
-  const size_t smem = 2 * Cfg::TILE_BYTES + 2 * Cfg::CC * sizeof(float);
+  const size_t smem = 2 * Cfg::TILE_BYTES + 2 * Cfg::CC * sizeof(float) + 16;
+  CUtensorMap tm_a;
+  if (int st = tma::make_nhwc_bf16_map(&tm_a, a.in1, nt, h, wd, c, Cfg::CC, Cfg::IW, Cfg::IH)) return st;
   auto kern = dw_fwd_sw_kernel<STRIDE, CVN, TW, TH>;
   ensure_smem(kern, static_cast<int>(smem));
   const int per_sm = std::max(1, std::min(3, static_cast<int>((220 * 1024) / (smem + 1024))));
-  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(a, w, static_cast<__nv_bfloat16*>(out), stats, g);
+  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(a, tm_a, w, static_cast<__nv_bfloat16*>(out), stats, g);
   return launch_status();
 }
 

@@ -1,0 +1,32 @@
+// tma.cuh — Tensor Memory Accelerator plumbing: host-side tensor maps (cuTensorMapEncodeTiled, resolved
+// through the runtime's driver entry point so that libcuda is not a link dependency) and the device-side
+// bulk tensor copy.  The maps describe NHWC bf16 activations [NT, H, W, C]; a box is one spatial tile of
+// one channel chunk, out-of-image coordinates (the conv halo, ragged channel chunks) are zero-filled by
+// the hardware.
+#pragma once
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace ehgr {
+namespace tma {
+
+// 0 on success.  box = (box_c channels, box_w, box_h, 1 frame); innermost box bytes must be a multiple of 16.
+int make_nhwc_bf16_map(CUtensorMap* out, const void* base, int nt, int h, int w, int c, int box_c, int box_w, int box_h);
+
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// coordinates innermost first: channel, x, y, frame
+__device__ __forceinline__ void load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int x, int y, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+}  // namespace tma
+}  // namespace ehgr
