@@ -290,7 +290,8 @@ __device__ __forceinline__ void wgrad_sweep(uint32_t a_tile, uint32_t d_tile, in
 
 template <int STRIDE, int CVN, int TW, int TH>
 __global__ void __launch_bounds__(128, 2)
-dw_bwd_sw_kernel(RowOp dy, RowOp a, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ da,
+dw_bwd_sw_kernel(RowOp dy, RowOp a, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_g,
+                 const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ da,
                  float* __restrict__ dwgt, DwSw g) {
   using Cfg = DwCfg<STRIDE, CVN, TW, TH>;
   constexpr int DOFF = STRIDE == 1 ? 1 : 0;
@@ -301,6 +302,13 @@ dw_bwd_sw_kernel(RowOp dy, RowOp a, const float* __restrict__ wgt, __nv_bfloat16
   const uint32_t a_tile = smem_u32(smem), g_tile = a_tile + Cfg::TILE_BYTES, r_tile = g_tile + DT_BYTES;
   float* s_w = reinterpret_cast<float*>(smem + Cfg::TILE_BYTES + 2 * DT_BYTES);   // [9][CC] taps (storage-rounded)
   float* s_acc = s_w + 9 * CC;                                                     // [9][CC]
+  const uint32_t bar = smem_u32(s_acc + 9 * CC);                                   // one mbarrier: the tiles of an item
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    tma::prefetch_map(&tm_a);
+    tma::prefetch_map(&tm_g);
+  }
   const int tid = threadIdx.x, cv = tid % CVN, col = tid / CVN;
   const int chunk = blockIdx.x % g.n_chunks;
   const int c_base = chunk * CC;
@@ -317,22 +325,25 @@ dw_bwd_sw_kernel(RowOp dy, RowOp a, const float* __restrict__ wgt, __nv_bfloat16
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc9[t][i] = make_float2(0.f, 0.f);
 
-  const __nv_bfloat16* a_in = static_cast<const __nv_bfloat16*>(a.in1);
-  const __nv_bfloat16* g_in = static_cast<const __nv_bfloat16*>(dy.in1);
-  const __nv_bfloat16* r_in = static_cast<const __nv_bfloat16*>(dy.in2);
   const bool two = dy.mode == EHGR_ROW_BNBWD;
   const long long item_stride = gridDim.x / g.n_chunks;
+  uint32_t phase = 0;
   for (long long item = blockIdx.x / g.n_chunks; item < g.items; item += item_stride) {
     const int tx = static_cast<int>(item % g.tiles_x);
     const long long r = item / g.tiles_x;
     const int ho0 = static_cast<int>(r % g.tiles_y) * TH, wo0 = tx * TW;
     const long long nt = r / g.tiles_y;
-    __syncthreads();                       // previous item's sweeps are done with the tiles
+    fence_proxy_async();                   // generic-proxy accesses of the tiles precede the next TMA writes
+    __syncthreads();                       // previous item's sweeps are done with the tiles (and the barrier is initialised)
+    if (tid == 0) {                        // one TMA box per tensor: tile + halo of this channel chunk, zero-filled outside
+      tma::expect_tx(bar, Cfg::TILE_BYTES + (two ? 2 : 1) * DT_BYTES);
+      tma::load_4d(a_tile, &tm_a, bar, c_base, wo0 * STRIDE - 1, ho0 * STRIDE - 1, static_cast<int>(nt));
+      tma::load_4d(g_tile, &tm_g, bar, c_base, wo0 - DOFF, ho0 - DOFF, static_cast<int>(nt));
+      if (two) tma::load_4d(r_tile, &tm_r, bar, c_base, wo0 - DOFF, ho0 - DOFF, static_cast<int>(nt));
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
     if (cv_on) {
-      tile_copy<Cfg::IH, Cfg::IW, CVN>(a_in, a_tile, nt, g.h, g.w, g.c, c0, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
-      tile_copy<DH, DWID, CVN>(g_in, g_tile, nt, g.ho, g.wo, g.c, c0, ho0 - DOFF, wo0 - DOFF, cv, col);
-      if (two) tile_copy<DH, DWID, CVN>(r_in, r_tile, nt, g.ho, g.wo, g.c, c0, ho0 - DOFF, wo0 - DOFF, cv, col);
-      tc::cp_async_wait_all();
       if (a.mode != EHGR_ROW_PLAIN) {
         RowLoader<__nv_bfloat16, 8, false, false> ld;
         ld.init(a, c0, g.c);
@@ -485,11 +496,18 @@ static int dw_bwd_sw_go(const RowOp& dy, const RowOp& a, const float* w, void* d
   constexpr int DT_BYTES = (TH + 1 + DOFF) * (TW + 1 + DOFF) * CVN * 16;
   DwSw g;
   dw_sw_geom<STRIDE, CVN, TW, TH>(g, nt, h, wd, c);
-  const size_t smem = Cfg::TILE_BYTES + 2 * DT_BYTES + 18 * Cfg::CC * sizeof(float);
+  const size_t smem = Cfg::TILE_BYTES + 2 * DT_BYTES + 18 * Cfg::CC * sizeof(float) + 16;
+  const int ho = (h - 1) / STRIDE + 1, wo = (wd - 1) / STRIDE + 1;
+  CUtensorMap tm_a, tm_g, tm_r;
+  if (int st = tma::make_nhwc_bf16_map(&tm_a, a.in1, nt, h, wd, c, Cfg::CC, Cfg::IW, Cfg::IH)) return st;
+  if (int st = tma::make_nhwc_bf16_map(&tm_g, dy.in1, nt, ho, wo, c, Cfg::CC, TW + 1 + DOFF, TH + 1 + DOFF)) return st;
+  tm_r = tm_g;
+  if (dy.mode == EHGR_ROW_BNBWD)
+    if (int st = tma::make_nhwc_bf16_map(&tm_r, dy.in2, nt, ho, wo, c, Cfg::CC, TW + 1 + DOFF, TH + 1 + DOFF)) return st;
   auto kern = dw_bwd_sw_kernel<STRIDE, CVN, TW, TH>;
   ensure_smem(kern, static_cast<int>(smem));
   const int per_sm = std::max(1, std::min(2, static_cast<int>((220 * 1024) / (smem + 1024))));
-  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(dy, a, w, static_cast<__nv_bfloat16*>(da), dw, g);
+  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(dy, a, tm_a, tm_g, tm_r, w, static_cast<__nv_bfloat16*>(da), dw, g);
   return launch_status();
 }
 
