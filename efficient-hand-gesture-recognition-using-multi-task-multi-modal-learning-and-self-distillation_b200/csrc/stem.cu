@@ -2,7 +2,7 @@
 // input the caller supplies (models/models.py:336: input.view(-1, 3, H, W)) and writing the NHWC raw
 // activation + batch statistics the fused chain works on; and its weight gradient.
 // Reference: conv_bn(3, 32, 2), archs/mobilenet_v2.py:7-12,90.
-#include "rowop.cuh"
+#include "tma.cuh"
 
 namespace ehgr {
 
@@ -284,6 +284,129 @@ stem_fwd32_kernel(const X* __restrict__ x, const float* __restrict__ wgt, T* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA variant of the banded forward kernel (row pitch and base 16-byte aligned, W + 2 <= 256): the band
+// [3 planes][2R+1 rows][W+2 columns] is one 4-D TMA box (halo rows / columns zero-filled by hardware),
+// double-buffered so that the next band is in flight while this one is computed; FP32 math on register
+// pairs (FFMA2).  Shared-memory reads of the stride-2 taps are 2-way bank conflicted, which is noise
+// next to the 8 weight vectors read per tap.
+// ------------------------------------------------------------------------------------------------
+template <typename X>
+__device__ __forceinline__ float lds_x(const X* p);
+template <>
+__device__ __forceinline__ float lds_x<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float lds_x<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename X, typename T, int R>
+__global__ void __launch_bounds__(128, 2)
+stem_fwd32_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ wgt, T* __restrict__ out,
+                      double* __restrict__ stats, StemGeom g, int bands, int bw, int tile_bytes) {
+  constexpr int NR = 2 * R + 1;
+  constexpr int kPad = 16 / static_cast<int>(sizeof(X));      // elements in 16 bytes
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  float* ws = reinterpret_cast<float*>(smem_raw + 2 * tile_bytes);   // [27][32]
+  float* s_stat = ws + 27 * kStemC;                                   // [64]
+  const uint32_t bar0 = tc::smem_u32(s_stat + 2 * kStemC);
+  const uint32_t tile0 = tc::smem_u32(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    tc::mbar_init(bar0, 1);
+    tc::mbar_init(bar0 + 8, 1);
+    tc::fence_mbar_init();
+    tma::prefetch_map(&tm_x);
+  }
+  for (int i = tid; i < 27 * kStemC; i += blockDim.x) {
+    const int tap = i / kStemC, co = i - tap * kStemC;
+    ws[i] = wgt[co * 27 + tap];
+  }
+  if (tid < 2 * kStemC) s_stat[tid] = 0.f;
+  float st_sum = 0.f, st_sq = 0.f;
+  const long long items = static_cast<long long>(g.nt) * bands;
+  auto issue = [&](int buf, long long item) {
+    const long long nt = item / bands;
+    const int ho0 = static_cast<int>(item - nt * bands) * R;
+    tma::expect_tx(bar0 + 8 * buf, static_cast<uint32_t>(3 * NR * bw * sizeof(X)));
+    // the box starts one 16-byte unit left of the image (innermost TMA coordinates stay 16-byte aligned);
+    // column -1 of the image is element kPad-1 of a tile row
+    tma::load_4d(tile0 + buf * tile_bytes, &tm_x, bar0 + 8 * buf, -kPad, 2 * ho0 - 1, 0, static_cast<int>(nt));
+  };
+  __syncthreads();
+  if (tid == 0 && blockIdx.x < items) issue(0, blockIdx.x);
+  int buf = 0;
+  uint32_t phase[2] = {0, 0};
+  for (long long item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
+    const long long nt = item / bands;
+    const int ho0 = static_cast<int>(item - nt * bands) * R;
+    if (tid == 0 && item + gridDim.x < items) issue(buf ^ 1, item + gridDim.x);
+    tc::mbar_wait(bar0 + 8 * buf, phase[buf]);
+    phase[buf] ^= 1;
+    const X* tile = reinterpret_cast<const X*>(smem_raw + buf * tile_bytes);
+    const int rmax = min(R, g.ho - ho0);
+    const int wo_end = (g.wo + 31) / 32 * 32;          // whole warps run the shuffles
+    for (int wo = tid; wo < wo_end; wo += blockDim.x) {
+      const bool col_ok = wo < g.wo;
+      const int wc = col_ok ? wo : 0;
+      for (int oh = 0; oh < rmax; oh += 2) {
+        const bool two = oh + 1 < rmax;
+        float2 a0[16], a1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a0[i] = a1[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const X* row0 = tile + (ci * NR + 2 * oh + kh) * bw + 2 * wc + (kPad - 1);   // box origin is column -kPad
+            const X* row1 = row0 + 2 * bw;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float x0 = lds_x<X>(row0 + kw);
+              const float x1 = two ? lds_x<X>(row1 + kw) : 0.f;
+              const float2 xx0 = make_float2(x0, x0), xx1 = make_float2(x1, x1);
+              const float4* wv = reinterpret_cast<const float4*>(ws + (ci * 9 + kh * 3 + kw) * kStemC);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 w4 = wv[q4];
+                const float2 wlo = make_float2(w4.x, w4.y), whi = make_float2(w4.z, w4.w);
+                a0[2 * q4] = __ffma2_rn(xx0, wlo, a0[2 * q4]);
+                a0[2 * q4 + 1] = __ffma2_rn(xx0, whi, a0[2 * q4 + 1]);
+                a1[2 * q4] = __ffma2_rn(xx1, wlo, a1[2 * q4]);
+                a1[2 * q4 + 1] = __ffma2_rn(xx1, whi, a1[2 * q4 + 1]);
+              }
+            }
+          }
+        }
+        float f0[32], f1[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          f0[2 * i] = col_ok ? a0[i].x : 0.f; f0[2 * i + 1] = col_ok ? a0[i].y : 0.f;
+          f1[2 * i] = col_ok ? a1[i].x : 0.f; f1[2 * i + 1] = col_ok ? a1[i].y : 0.f;
+        }
+        if (col_ok) {
+          const long long q0 = (nt * g.ho + ho0 + oh) * g.wo + wo;
+          stem_store32<T>(out + q0 * kStemC, f0);
+          if (two) stem_store32<T>(out + (q0 + g.wo) * kStemC, f1);
+        }
+        if (stats) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { sq[i] = fmaf(f0[i], f0[i], f1[i] * f1[i]); f0[i] += f1[i]; }
+          st_sum += warp_transpose_sum32(f0, lane);
+          st_sq += warp_transpose_sum32(sq, lane);
+        }
+      }
+    }
+    tc::fence_proxy_async();
+    __syncthreads();                                    // band consumed: its buffer may be refilled
+  }
+  if (stats) {
+    atomicAdd(&s_stat[lane], st_sum);
+    atomicAdd(&s_stat[kStemC + lane], st_sq);
+    __syncthreads();
+    if (tid < 2 * kStemC) atomicAdd(&stats[tid], static_cast<double>(s_stat[tid]));
+  }
+}
+
 // Weight gradient.  12 warps = 4 channel groups (8 output channels) x 3 input planes; a warp keeps its
 // 9 taps x 8 channels in registers over every band the CTA visits, lanes = output pixels of the band.
 // rowop(dy) is evaluated once per element while the band is staged (as fp32, [quad][pixel][4]).
@@ -398,6 +521,37 @@ static void stem_wgrad32_go(const RowOp& dy, const void* x, float* dw, const Ste
   stem_wgrad32_kernel<X, T><<<grid, 384, smem, s>>>(dy, static_cast<const X*>(x), dw, g, R, bands, wp);
 }
 
+// x: [NT, 3, H, W] -> 4-D map (W, H, 3, NT); box = (bw columns from -1, 2R+1 rows, 3 planes, 1 frame)
+template <typename X>
+static bool stem_tma_map(CUtensorMap* tm, const void* x, const StemGeom& g, int nrows, int* bw_out) {
+  const int es = static_cast<int>(sizeof(X));
+  const int bw = (g.w + 1 + 2 * (16 / es) - 1) / (16 / es) * (16 / es);   // columns -16/es .. w, rounded to 16 bytes
+  if (bw > 256 || (static_cast<long long>(g.w) * es) % 16 != 0 || !aligned_to(x, 16)) return false;
+  const unsigned long long dims[4] = {static_cast<unsigned long long>(g.w), static_cast<unsigned long long>(g.h), 3ULL,
+                                      static_cast<unsigned long long>(g.nt)};
+  const unsigned long long strides[3] = {static_cast<unsigned long long>(g.w) * es, static_cast<unsigned long long>(g.h) * g.w * es,
+                                         3ULL * g.h * g.w * es};
+  const unsigned box[4] = {static_cast<unsigned>(bw), static_cast<unsigned>(nrows), 3u, 1u};
+  *bw_out = bw;
+  return tma::make_map_4d(tm, es, x, dims, strides, box) == EHGR_OK;
+}
+
+template <typename X, typename T>
+static bool stem_fwd32_tma_go(const void* x, const float* w, void* out, double* stats, const StemGeom& g, cudaStream_t s) {
+  constexpr int R = 4;
+  CUtensorMap tm;
+  int bw = 0;
+  if (!stem_tma_map<X>(&tm, x, g, 2 * R + 1, &bw)) return false;
+  const int bands = static_cast<int>(cdiv(g.ho, R));
+  const int tile_bytes = static_cast<int>((3 * (2 * R + 1) * bw * sizeof(X) + 127) / 128 * 128);
+  const size_t smem = 2 * static_cast<size_t>(tile_bytes) + (29 * kStemC) * sizeof(float) + 16;
+  ensure_smem(stem_fwd32_tma_kernel<X, T, R>, smem);
+  const long long items = static_cast<long long>(g.nt) * bands;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 3LL * kNumSMs));
+  stem_fwd32_tma_kernel<X, T, R><<<grid, 128, smem, s>>>(tm, w, static_cast<T*>(out), stats, g, bands, bw, tile_bytes);
+  return true;
+}
+
 // shared-memory budget of the banded kernels (image width bound)
 static bool stem32_fits(const StemGeom& g) { return g.cout == kStemC && g.wo <= 1024; }
 
@@ -405,8 +559,11 @@ template <typename X>
 static int stem_fwd_launch(const void* x, const float* w, void* out, double* stats, const StemGeom& g, int dtype,
                            cudaStream_t s) {
   if (stem32_fits(g)) {
-    if (dtype == EHGR_F32) stem_fwd32_go<X, float>(x, w, out, stats, g, s);
-    else stem_fwd32_go<X, __nv_bfloat16>(x, w, out, stats, g, s);
+    if (dtype == EHGR_F32) {
+      if (!stem_fwd32_tma_go<X, float>(x, w, out, stats, g, s)) stem_fwd32_go<X, float>(x, w, out, stats, g, s);
+    } else {
+      if (!stem_fwd32_tma_go<X, __nv_bfloat16>(x, w, out, stats, g, s)) stem_fwd32_go<X, __nv_bfloat16>(x, w, out, stats, g, s);
+    }
     return launch_status();
   }
   const size_t smem = static_cast<size_t>(29) * g.cout * sizeof(float);

@@ -14,6 +14,10 @@ namespace tma {
 // 0 on success.  box = (box_c channels, box_w, box_h, 1 frame); innermost box bytes must be a multiple of 16.
 int make_nhwc_bf16_map(CUtensorMap* out, const void* base, int nt, int h, int w, int c, int box_c, int box_w, int box_h);
 
+// generic 4-D map (dims / box innermost first, strides of dims 1..3 in bytes), bf16 (elem_bytes 2) or fp32 (4)
+int make_map_4d(CUtensorMap* out, int elem_bytes, const void* base, const unsigned long long (&dims)[4],
+                const unsigned long long (&strides_bytes)[3], const unsigned (&box)[4]);
+
 __device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
