@@ -492,6 +492,106 @@ stem_wgrad32_kernel(RowOp dy, const X* __restrict__ x, float* __restrict__ dwgt,
     }
 }
 
+// TMA variant of the weight-gradient kernel: the input band arrives as one TMA box while the CTA stages
+// rowop(dy); the tap loop runs on register pairs (FFMA2).  Same warp roles as above.
+template <typename X, typename T, int R>
+__global__ void __launch_bounds__(384)
+stem_wgrad32_tma_kernel(RowOp dy, const __grid_constant__ CUtensorMap tm_x, float* __restrict__ dwgt, StemGeom g, int bands,
+                        int bw, int tile_bytes) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int QV = V / 4;
+  constexpr int NR = 2 * R + 1;
+  constexpr int kPad = 16 / static_cast<int>(sizeof(X));
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int npix = R * g.wo;
+  const X* tile = reinterpret_cast<const X*>(smem_raw);
+  float* dtile = reinterpret_cast<float*>(smem_raw + tile_bytes);            // [8][npix][4]
+  const uint32_t bar = tc::smem_u32(dtile + 8 * npix * 4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cog = warp & 3, ci = warp >> 2;
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_mbar_init();
+    tma::prefetch_map(&tm_x);
+  }
+  float2 acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[t][i] = make_float2(0.f, 0.f);
+  const int vec_per_row = kStemC / V;
+  const int cv = tid % vec_per_row;
+  const long long items = static_cast<long long>(g.nt) * bands;
+  uint32_t phase = 0;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long nt = item / bands;
+    const int ho0 = static_cast<int>(item - nt * bands) * R;
+    const int rmax = min(R, g.ho - ho0);
+    const int np = rmax * g.wo;
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tma::expect_tx(bar, static_cast<uint32_t>(3 * NR * bw * sizeof(X)));
+      tma::load_4d(tc::smem_u32(smem_raw), &tm_x, bar, -kPad, 2 * ho0 - 1, 0, static_cast<int>(nt));
+    }
+    {
+      RowLoader<T, V> ld;
+      ld.init(dy, cv * V, kStemC);
+      const long long q0 = (nt * g.ho + ho0) * g.wo;
+      const int step = blockDim.x / vec_per_row;
+#pragma unroll 1
+      for (int p0 = tid / vec_per_row; p0 < np; p0 += 2 * step) {
+        typename RowLoader<T, V>::Raw raw[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) if (p0 + j * step < np) raw[j] = ld.fetch(dy, q0 + p0 + j * step);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int p = p0 + j * step;
+          if (p < np) {
+            float v[V];
+            ld.finish(dy, raw[j], v);
+#pragma unroll
+            for (int qd = 0; qd < QV; ++qd)
+              *reinterpret_cast<float4*>(dtile + (static_cast<size_t>(cv * QV + qd) * npix + p) * 4) =
+                  make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+          }
+        }
+      }
+    }
+    tc::mbar_wait(bar, phase);
+    phase ^= 1;
+    __syncthreads();
+    for (int oh = 0; oh < rmax; ++oh) {
+      for (int wo = lane; wo < g.wo; wo += 32) {
+        const int p = oh * g.wo + wo;
+        const float4 d0 = *reinterpret_cast<const float4*>(dtile + (static_cast<size_t>(cog * 2) * npix + p) * 4);
+        const float4 d1 = *reinterpret_cast<const float4*>(dtile + (static_cast<size_t>(cog * 2 + 1) * npix + p) * 4);
+        const float2 d[4] = {make_float2(d0.x, d0.y), make_float2(d0.z, d0.w), make_float2(d1.x, d1.y), make_float2(d1.z, d1.w)};
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const X* row = tile + (ci * NR + 2 * oh + kh) * bw + 2 * wo + (kPad - 1);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float xv = lds_x<X>(row + kw);
+            const float2 xx = make_float2(xv, xv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[kh * 3 + kw][i] = __ffma2_rn(d[i], xx, acc[kh * 3 + kw][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = (i & 1) ? acc[t][i >> 1].y : acc[t][i >> 1].x;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) atomicAdd(&dwgt[(cog * 8 + i) * 27 + ci * 9 + t], v);
+    }
+}
+
 static int stem_geom(StemGeom& g, int nt, int h, int w, int cout) {
   if (nt < 0 || h <= 0 || w <= 0 || cout <= 0 || (cout % 8) || cout > 256) return EHGR_E_SHAPE;
   g.nt = nt; g.h = h; g.w = w; g.cout = cout;
@@ -552,6 +652,23 @@ static bool stem_fwd32_tma_go(const void* x, const float* w, void* out, double* 
   return true;
 }
 
+template <typename X, typename T>
+static bool stem_wgrad32_tma_go(const RowOp& dy, const void* x, float* dw, const StemGeom& g, cudaStream_t s) {
+  constexpr int R = 2;
+  CUtensorMap tm;
+  int bw = 0;
+  if (!stem_tma_map<X>(&tm, x, g, 2 * R + 1, &bw)) return false;
+  const int bands = static_cast<int>(cdiv(g.ho, R));
+  const int tile_bytes = static_cast<int>((3 * (2 * R + 1) * bw * sizeof(X) + 127) / 128 * 128);
+  const size_t smem = static_cast<size_t>(tile_bytes) + static_cast<size_t>(8) * R * g.wo * 4 * sizeof(float) + 16;
+  if (smem > 200 * 1024) return false;
+  ensure_smem(stem_wgrad32_tma_kernel<X, T, R>, smem);
+  const long long items = static_cast<long long>(g.nt) * bands;
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 1LL * kNumSMs));
+  stem_wgrad32_tma_kernel<X, T, R><<<grid, 384, smem, s>>>(dy, tm, dw, g, bands, bw, tile_bytes);
+  return true;
+}
+
 // shared-memory budget of the banded kernels (image width bound)
 static bool stem32_fits(const StemGeom& g) { return g.cout == kStemC && g.wo <= 1024; }
 
@@ -585,8 +702,11 @@ template <typename X>
 static int stem_wgrad_launch(const RowOp& dy, const void* x, float* dw, const StemGeom& g, int dtype,
                              cudaStream_t s) {
   if (stem32_fits(g) && dy.mode != EHGR_ROW_GATE) {
-    if (dtype == EHGR_F32) stem_wgrad32_go<X, float>(dy, x, dw, g, s);
-    else stem_wgrad32_go<X, __nv_bfloat16>(dy, x, dw, g, s);
+    if (dtype == EHGR_F32) {
+      if (!stem_wgrad32_tma_go<X, float>(dy, x, dw, g, s)) stem_wgrad32_go<X, float>(dy, x, dw, g, s);
+    } else {
+      if (!stem_wgrad32_tma_go<X, __nv_bfloat16>(dy, x, dw, g, s)) stem_wgrad32_go<X, __nv_bfloat16>(dy, x, dw, g, s);
+    }
     return launch_status();
   }
   const dim3 block(g.cout / 4, std::max(1, 256 / (g.cout / 4)));
