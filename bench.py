@@ -235,9 +235,11 @@ def run_ours(args):
         return ms.item()
 
     # ---- leg 1: inputs resident in HBM ----
+    last_loss = {}
+
     def leg_resident(k):
         for i in range(k):
-            step.run(*resident[i % n_host])
+            last_loss["v"] = step.run(*resident[i % n_host])
 
     leg_resident(args.warmup)
     sampler = ClockSampler(local)
@@ -281,6 +283,9 @@ def run_ours(args):
     leg_e2e(max(args.warmup, 5))     # new input format: eager warm-up calls + graph capture happen here, untimed
     ms_e2e = timed(leg_e2e, args.steps)
 
+    loss_value = float(last_loss["v"].item())
+    if not (loss_value == loss_value and abs(loss_value) < 1e6):        # NaN / inf: the number would be meaningless
+        raise RuntimeError(f"training loss is not finite ({loss_value}); refusing to report a throughput")
     if rank == 0:
         pk, pk_kind = peaks()
         clips = B * world * args.steps
@@ -302,6 +307,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG, ncu_traffic()),
             "peaks": pk_kind,
+            "final_loss": round(loss_value, 5),
             "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
             "ms_per_step_with_kernel_events": round(ms_prof / args.steps, 3),
         }

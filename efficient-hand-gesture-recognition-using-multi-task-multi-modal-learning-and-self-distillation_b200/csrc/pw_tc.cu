@@ -79,10 +79,10 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
     // form, n-chunks of one row k for the MN-major form): coalesced 128-byte reads, no per-chunk division.
     const uint32_t dst32 = smem_u32(dst);
     if (!p.w_is_kn) {
-      const int kg = tid & 7, step = nthreads >> 3;
-      const int k = k_base + kg * 8;
-      const bool k_ok = kg < kv && k < p.K;
-      if (kg < kv) {
+      const int step = nthreads >> 3;
+      for (int kg = tid & 7; kg < kv; kg += 8) {        // kv > 8 only for the resident form (whole K at once)
+        const int k = k_base + kg * 8;
+        const bool k_ok = k < p.K;
 #pragma unroll 4
         for (int nl = tid >> 3; nl < p.BN; nl += step) {
           const int n = n0 + nl;

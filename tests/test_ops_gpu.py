@@ -292,15 +292,25 @@ def test_pw_gemm_w16_matches_fp32_weight_path(M, K, N, kn):
     w = (_rand((N, K), 97, (2.0 / K) ** 0.5) if not kn else _rand((K, N), 97, (2.0 / K) ** 0.5)).cuda()
     w16 = w.to(dtype)
     scale, shift = (_rand((K,), 98).abs() + 0.5).cuda(), _rand((K,), 99).cuda()
-    outs = []
-    for mirror in (0, w16.data_ptr()):
+    outs = {}
+    # the mirror path runs first, and a different GEMM in between overwrites the shared memory both paths
+    # stage their weights into: a chunk one path forgets to write cannot be inherited from the other
+    other_a, other_w = _rand((256, 64), 100).to(dtype).cuda(), _rand((64, 64), 101).cuda()
+    other_out = torch.empty((256, 64), dtype=dtype, device="cuda")
+    for mirror in (w16.data_ptr(), 0):
         out = torch.full((M, N), float("nan"), dtype=dtype, device="cuda")
         _call("ehgr_pw_gemm_w16", ctypes.byref(f.op_affine(a, scale, shift, True)), w.data_ptr(), mirror, kn, out.data_ptr(), 0, 0,
               M, K, N, 1, 2, _sp())
+        for _ in range(3):
+            _call("ehgr_pw_gemm", ctypes.byref(f.op_plain(other_a)), other_w.data_ptr(), 0, other_out.data_ptr(), 0, 0,
+                  256, 64, 64, 1, 2, _sp())
         torch.cuda.synchronize()
-        outs.append(out)
-    assert torch.isfinite(outs[1].float()).all()
-    assert torch.equal(outs[0], outs[1])
+        outs[mirror != 0] = out
+    assert torch.isfinite(outs[True].float()).all()
+    assert torch.equal(outs[False], outs[True])
+    aa = torch.clamp(a.double() * scale.double() + shift.double(), 0, 6).to(dtype).double()
+    want = aa @ (w16.double().t() if not kn else w16.double())
+    assert rel_err(outs[True].cpu(), want.cpu()) < 1e-2
 
 
 def test_pw_gemm_tcgen05_shift_prologue_full_size():
