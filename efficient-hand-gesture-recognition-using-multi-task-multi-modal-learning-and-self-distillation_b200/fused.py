@@ -81,12 +81,19 @@ def current_dtype():
 # ------------------------------------------------------------------------------------------------
 # row operands
 # ------------------------------------------------------------------------------------------------
-def _bf16_mirror(w, storage_dtype):
+def _bf16_mirror(w, storage_dtype, cache=None):
     """bf16 copy of a pointwise-conv weight for the tensor-core engine's asynchronous B staging
-    (None for fp32 storage / the SIMT engine, which read the fp32 master weights)."""
+    (None for fp32 storage / the SIMT engine, which read the fp32 master weights).  `cache` is the
+    per-forward dictionary that backward reuses (one cast per weight per step); there is deliberately no
+    cross-step cache: CUDA-graph replays update weights without touching their version counters."""
     if storage_dtype != torch.bfloat16 or _STATE["engine"] == 1:
         return None
-    return w.detach().to(torch.bfloat16)
+    if cache is not None and id(w) in cache:
+        return cache[id(w)]
+    m = w.detach().to(torch.bfloat16)
+    if cache is not None:
+        cache[id(w)] = m
+    return m
 
 
 def op_plain(t):
@@ -214,7 +221,7 @@ def _has_action(model) -> bool:
 # ------------------------------------------------------------------------------------------------
 # the chain autograd Function
 # ------------------------------------------------------------------------------------------------
-def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None):
+def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None, mirrors=None):
     nt, h, wd, cin = a_geom
     cout = st.conv.out_channels
     sp = _lib.stream_ptr(dev)
@@ -228,7 +235,7 @@ def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None):
                   algo_flops=2 * 27 * out.numel())
     elif st.kind == 'pw':
         m = nt * h * wd
-        w16 = _bf16_mirror(w, out.dtype)
+        w16 = _bf16_mirror(w, out.dtype, mirrors)
         _lib.call("ehgr_pw_gemm_w16", ctypes.byref(a_op), w.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
                   cin, cout, code, _STATE["engine"], sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
                   algo_flops=2 * m * cin * cout)
@@ -252,6 +259,7 @@ class _ChainFunction(torch.autograd.Function):
         s_off = v_off = 0
         sp = _lib.stream_ptr(dev)
 
+        mirrors = {}                                     # id(weight) -> bf16 mirror, reused by backward
         first_is_stem = stages[0].kind == 'stem'
         if first_is_stem:
             if x.dim() != 4 or x.shape[1] != 3:
@@ -299,7 +307,8 @@ class _ChainFunction(torch.autograd.Function):
                 if tr:
                     stats = stat_arena[s_off:s_off + 2 * cout]
                     s_off += 2 * cout
-                _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None)
+                _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None,
+                                 mirrors=mirrors)
                 vec = vec_arena[v_off:v_off + 4 * cout].view(4, cout)   # scale, shift, mean, invstd
                 v_off += 4 * cout
                 _lib.call("ehgr_bn_finalize", 0 if stats is None else stats.data_ptr(), nt * ho * wo, gamma.data_ptr(),
@@ -328,6 +337,7 @@ class _ChainFunction(torch.autograd.Function):
         if nbt:
             torch._foreach_add_(nbt, 1)
         ctx.units, ctx.dt, ctx.saved_units, ctx.x_in = units, dt, saved_units, x_in
+        ctx.mirrors = mirrors
         ctx.params, ctx.tap_units = params, tap_units
         return tuple(outputs)
 
@@ -434,7 +444,7 @@ class _ChainFunction(torch.autograd.Function):
                         g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
                         # residual units without a shift: fold "+ g_unit_out" into the dgrad epilogue
                         fuse_res = si == 0 and u.residual and st.shift is None and act_state is None
-                        w16 = _bf16_mirror(w, dt)
+                        w16 = _bf16_mirror(w, dt, ctx.mirrors)
                         _lib.call("ehgr_pw_gemm_w16", ctypes.byref(dy_op), w.data_ptr(), _lib.ptr(w16), 1, g_prev.data_ptr(),
                                   g_unit_out.data_ptr() if fuse_res else 0, 0, m_in, cout, cin, code,
                                   _STATE["engine"], sp,
