@@ -28,7 +28,7 @@
 // The two TMEM buffers let the epilogue of tile i overlap the loads and MMAs of tile i+1.
 // w_is_kn selects the B operand's major-ness: forward reads the conv weight [N,K] as a K-major B,
 // dgrad reads the same array [K,N] as an MN-major B — no transposed weight copy exists.
-#include "tma.cuh"
+#include "tc_common.cuh"
 
 namespace ehgr {
 namespace tc {
@@ -64,7 +64,6 @@ struct GemmArgs {
   int n_stages;    // ring depth
   int a_bytes;     // bytes of the A part of a stage = 128 * min(Kp,64) * 2
   int stage_bytes; // a_bytes (+ BN*128 when B is streamed)
-  int use_tma;     // PLAIN operand, M % 8 == 0: A stages are single TMA boxes (tm_a)
   int dbg;
 };
 
@@ -152,7 +151,7 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
 //                  the copy's source is the neighbouring frame or a zero fill.
 // kAsync = false: register path (batched fetch -> rowop -> store) for the two-tensor BNBWD operand.
 template <bool kAsync>
-__global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p, const __grid_constant__ CUtensorMap tm_a) {
+__global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Kp = (p.K + 15) & ~15;
   const int b_res_bytes = p.b_resident ? p.BN * Kp * 2 : 0;
@@ -221,22 +220,6 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p, con
         const int f = 4 / kvp;                         // spare slots interleave row groups (kv == 2)
         if constexpr (kAsync) {
           mbar_wait(bar_empty + 8 * s, parity);
-          if (p.use_tma) {
-            // PLAIN operand: the whole 128-row x 64-channel stage is ONE TMA box of the [M/8][K/8][8][8] view of A,
-            // which lands exactly in the core-matrix layout (rows beyond M and channels beyond K zero-filled).
-            // The weight slice (if streamed) still goes through cp.async; the single arrival carries the byte count.
-            if (!p.b_resident) {
-              stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
-              cp_async_wait_all();
-              fence_proxy_async();
-            }
-            __syncwarp();
-            if (lane == 0) {
-              tma::expect_tx(bar_full + 8 * s, static_cast<uint32_t>(p.a_bytes));
-              tma::load_4d(smem_u32(a_dst), &tm_a, bar_full + 8 * s, 0, 0, ks * (BK / 8), static_cast<int>(m0 >> 3));
-            }
-            continue;
-          }
           const int mode = p.a.mode;
           const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(p.a.in1);
           const uint32_t a_dst32 = smem_u32(a_dst);
@@ -551,25 +534,12 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   long long grid = std::min<long long>(tiles, kNumSMs);
   grid = std::max<long long>(p.n_chunks, grid / p.n_chunks * p.n_chunks);
   const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes;
-  CUtensorMap tm_a{};
-  p.use_tma = 0;
-  // Measured on B200: the box's 16-byte inner extent makes this path 5-15 % SLOWER than the cp.async producers
-  // on the large-M layers (dgrad 96->16 @112x112: 285 us vs 255 us) and equal on the small ones, so it is only
-  // taken when asked for (ehgr_debug_set(512)); a SWIZZLE_128B operand layout is the way to make TMA pay here.
-  if ((g_debug_flags & 512) && a.mode == EHGR_ROW_PLAIN && (M % 8) == 0 && w16 != nullptr) {
-    // A viewed as [M/8 row groups][K/8 chunks][8 rows][8 elements]; box = 16 row groups x kv chunks x 8 x 8
-    const int kv_box = std::min(Kp, tc::BK) / 8;
-    const unsigned long long dims[4] = {8ULL, 8ULL, static_cast<unsigned long long>(K / 8), static_cast<unsigned long long>(M / 8)};
-    const unsigned long long strides[3] = {static_cast<unsigned long long>(K) * 2, 16ULL, static_cast<unsigned long long>(K) * 16};
-    const unsigned box[4] = {8u, 8u, static_cast<unsigned>(kv_box), 16u};
-    if (tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box) == EHGR_OK) p.use_tma = 1;
-  }
   if (a.mode == EHGR_ROW_BNBWD) {
     ensure_smem(tc::pw_gemm_tc_kernel<false>, kBudget);
-    tc::pw_gemm_tc_kernel<false><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p, tm_a);
+    tc::pw_gemm_tc_kernel<false><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
   } else {
     ensure_smem(tc::pw_gemm_tc_kernel<true>, kBudget);
-    tc::pw_gemm_tc_kernel<true><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p, tm_a);
+    tc::pw_gemm_tc_kernel<true><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
   }
   return launch_status();
 }
