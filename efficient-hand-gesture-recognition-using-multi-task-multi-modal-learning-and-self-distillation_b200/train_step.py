@@ -192,6 +192,7 @@ class MTMMTrainStep:
         self._static_in = None
         self._static_loss = None
         self._eager_calls = 0
+        self._side = None
         self._mean_std = None
         if self.device.type == "cuda" and hasattr(model, "input_mean"):
             self._mean_std = (torch.tensor(model.input_mean, dtype=torch.float32, device=self.device),
@@ -238,17 +239,29 @@ class MTMMTrainStep:
             self.invalidate_graph()
             self._eager_calls = 0          # new shapes / dtypes: warm up eagerly again before re-capturing
         if self._graph is None:
+            # Warm-up calls and the capture run on ONE side stream (the documented whole-network recipe):
+            # autograd ties gradient accumulation of a leaf to the stream its accumulator was first used on,
+            # which must be the capturing stream, not the caller's.
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
             if self._eager_calls < self.graph_warmup:
                 self._eager_calls += 1
-                return self._step(*batch)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    loss = self._step(*batch)
+                for t in batch:
+                    t.record_stream(self._side)
+                cur.wait_stream(self._side)
+                return loss
             from . import _lib
             self._static_in = [torch.empty_like(t) for t in batch]
             for dst, src in zip(self._static_in, batch):
                 dst.copy_(src)
-            torch.cuda.current_stream().synchronize()
+            cur.synchronize()
             graph = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._side):
                 self._static_loss = self._step(*self._static_in)
             self.launches_per_step = _lib.launch_count() - l0
             self._graph = graph

@@ -320,3 +320,26 @@ def test_train_step_cuda_graph_matches_eager():
     # update would show up far above these bounds
     assert dl <= max(10 * noise_l, 3e-3), (dl, noise_l)
     assert dp <= max(10 * noise_p, 2e-2), (dp, noise_p)
+
+
+def test_sd_train_step_runs_in_graph_mode():
+    """SDTrainStep (three exit heads + fused SD loss) captured in a CUDA graph: finite, changing losses and
+    moving parameters over replays with different batches."""
+    import ehgr_b200 as E
+    sd0 = O.build_sd_state(83, "tsm", 8, seed=3)
+    with _quiet():
+        model = E.tsn_sd.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                             dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                             temporal_module='tsm')
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    step = E.train_step.SDTrainStep(model, lr=1e-3, compute_dtype=torch.bfloat16, use_graph=True)
+    w0 = model.base_model.features[1].conv[0].weight.detach().clone()
+    losses = []
+    for i in range(5):
+        rgb, _depth, labels = O.synthetic_clip_batch(2, 8, 64, 83, seed=40 + i)
+        losses.append(float(step.run(rgb.cuda(), labels.cuda()).item()))
+    assert step._graph is not None and step.launches_per_step > 100
+    assert all(l == l and abs(l) < 1e4 for l in losses), losses
+    assert len({round(l, 4) for l in losses}) > 1
+    assert not torch.equal(w0, model.base_model.features[1].conv[0].weight)
