@@ -258,10 +258,11 @@ __device__ __forceinline__ float border_wsum(const float* w9, int h, int w, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward pass 2: block = one clip: gate backward, small parameter gradients, dm / dpool / dd,
-// BatchNorm-backward sums of the motion branch
+// backward pass 2a: block = one clip: the clip-level part of the gate backward (channel and motion
+// excitation through their tiny temporal layers): small parameter gradients, dpool, dd.
+// The per-frame spatial work is pass 2b (action_bwd_frame_kernel), which reads dd.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) action_bwd_small_kernel(Act a) {
+__global__ void __launch_bounds__(256) action_bwd_clip_kernel(Act a) {
   extern __shared__ float smem[];
   const int C = a.c, Cr = a.cr, T = a.t, H = a.h, W = a.w, HW = H * W;
   float* pm = smem;                  // [T][C]
@@ -290,43 +291,6 @@ __global__ void __launch_bounds__(256) action_bwd_small_kernel(Act a) {
   }
   for (int i = threadIdx.x; i < 27 + Cr * 9 + 2 * Cr; i += blockDim.x) acc27[i] = 0.f;
   __syncthreads();
-  // ---- STE: da1 = dg1 * g1 (1 - g1) (in place in dg1), then dm = conv3d^T(da1), dW_p1 = corr(mrow, da1)
-  for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
-    const float g = a.g1[m0 + i];
-    a.dg1[m0 + i] *= g * (1.f - g);
-  }
-  __threadfence_block();
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
-    const int t = i / HW, p = i - t * HW, h = p / W, w = p - h * W;
-    float acc = 0.f;
-    for (int dt = -1; dt <= 1; ++dt) {
-      const int tt = t - dt;                       // output position that used this input with tap dt
-      if (tt < 0 || tt >= T) continue;
-      for (int dh = -1; dh <= 1; ++dh) {
-        const int hh = h - dh;
-        if (hh < 0 || hh >= H) continue;
-        for (int dw = -1; dw <= 1; ++dw) {
-          const int ww = w - dw;
-          if (ww < 0 || ww >= W) continue;
-          acc = fmaf(a.p1_w[(dt + 1) * 9 + (dh + 1) * 3 + dw + 1], a.dg1[m0 + static_cast<long long>(tt) * HW + hh * W + ww], acc);
-        }
-      }
-    }
-    a.dm[m0 + i] = acc;
-  }
-  for (int tap = 0; tap < 27; ++tap) {
-    const int dt = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
-      const int t = i / HW, p = i - t * HW, h = p / W, w = p - h * W;
-      const int tt = t + dt, hh = h + dh, ww = w + dw;
-      if (tt < 0 || tt >= T || hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-      acc = fmaf(a.dg1[m0 + i], a.mrow[m0 + static_cast<long long>(tt) * HW + hh * W + ww], acc);
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&acc27[tap], acc);
-  }
   // ---- CE backward
   for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
     const int t = i / Cr, j = i - t * Cr;
@@ -385,35 +349,120 @@ __global__ void __launch_bounds__(256) action_bwd_small_kernel(Act a) {
     for (int j = 0; j < Cr; ++j) acc = fmaf(a.p2_squeeze[j * C + c], ds[t * Cr + j], acc);
     a.dpool[f0 * C + i] = acc;
   }
-  // ---- ME: depthwise-conv weight gradient and the BatchNorm-backward sums of x3's gradient
-  //   dx3[t][p][j] = -dd[t][j] + dd[t-1][j] * border_wsum(p)      (dd[-1] = dd[T-1] = 0)
-  for (int i = threadIdx.x; i < T * Cr * HW; i += blockDim.x) {
-    const int p = i % HW, tj = i / HW, j = tj % Cr, t = tj / Cr;
-    const int h = p / W, w = p - h * W;
-    const float qv = a.q[(m0 + static_cast<long long>(t) * HW + p) * Cr + j];
-    const float ddp = t > 0 ? dd[(t - 1) * Cr + j] : 0.f;
-    const float dx3 = -dd[t * Cr + j] + ddp * border_wsum(a.p3_conv1 + j * 9, h, w, H, W);
-    atomicAdd(&bsum[j], dx3);
-    atomicAdd(&bsum[Cr + j], dx3 * qv);
-    if (t > 0 && ddp != 0.f) {
-      // dW3[j][kh][kw] += dd[t-1][j] * x3[t][h+kh-1, w+kw-1] summed over output positions p=(h,w)
-      const float sc = a.bn3_scale[j], sh = a.bn3_shift[j];
-      for (int kh = 0; kh < 3; ++kh) {
-        const int hh = h + kh - 1;
-        if (hh < 0 || hh >= H) continue;
-        for (int kw = 0; kw < 3; ++kw) {
-          const int ww = w + kw - 1;
-          if (ww < 0 || ww >= W) continue;
-          const float x3 = fmaf(a.q[(m0 + static_cast<long long>(t) * HW + hh * W + ww) * Cr + j], sc, sh);
-          atomicAdd(&acc9[j * 9 + kh * 3 + kw], ddp * x3);
-        }
-      }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 2b: block = one FRAME (n*T blocks instead of n): everything that runs over pixels.
+//   STE : da1 = dg1 * g1 (1 - g1) of frames t-1, t, t+1 and mrow of the same frames staged in shared memory;
+//         dm[t] = conv3d^T(da1), dW_p1 += corr(mrow, da1[t])        (27 register accumulators per thread)
+//   ME  : dx3[t][p][j] = -dd[t][j] + dd[t-1][j] * border_wsum_j(p);  the BatchNorm-backward sums and the
+//         depthwise weight gradient only need seven per-(frame, j) reductions over pixels
+//         (sum b, sum q, sum b*q, first/last row and column sums of q): no per-element atomics.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) action_bwd_frame_kernel(Act a) {
+  extern __shared__ float smem[];
+  const int Cr = a.cr, T = a.t, H = a.h, W = a.w, HW = H * W;
+  float* da = smem;             // [3][HW]
+  float* mr = da + 3 * HW;      // [3][HW]
+  float* red = mr + 3 * HW;     // [27 + 7]
+  const long long f = blockIdx.x;
+  const int t = static_cast<int>(f % T);
+  const long long m_t = f * HW;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 3 * HW; i += blockDim.x) {
+    const int fr = i / HW, p = i - fr * HW, tt = t + fr - 1;
+    float d = 0.f, m = 0.f;
+    if (tt >= 0 && tt < T) {
+      const long long idx = m_t + static_cast<long long>(fr - 1) * HW + p;
+      const float g = a.g1[idx];
+      d = a.dg1[idx] * g * (1.f - g);
+      m = a.mrow[idx];
+    }
+    da[i] = d;
+    mr[i] = m;
+  }
+  if (tid < 34) red[tid] = 0.f;
+  __syncthreads();
+  {
+    float w27[27], acc27[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) { w27[k] = a.p1_w[k]; acc27[k] = 0.f; }
+    for (int p = tid; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      const float ac = da[HW + p];
+      float accm = 0.f;
+#pragma unroll
+      for (int dt = -1; dt <= 1; ++dt)
+#pragma unroll
+        for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+          for (int dw = -1; dw <= 1; ++dw) {
+            const int tap = (dt + 1) * 9 + (dh + 1) * 3 + dw + 1;
+            const int hs = h - dh, ws = w - dw;            // transposed conv: the output position that used this input
+            if (hs >= 0 && hs < H && ws >= 0 && ws < W) accm = fmaf(w27[tap], da[(1 - dt) * HW + hs * W + ws], accm);
+            const int h2 = h + dh, w2 = w + dw;
+            if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) acc27[tap] = fmaf(ac, mr[(1 + dt) * HW + h2 * W + w2], acc27[tap]);
+          }
+      a.dm[m_t + p] = accm;
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float v = warp_sum(acc27[k]);
+      if (lane == 0 && v != 0.f) atomicAdd(&red[k], v);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 27; i += blockDim.x) atomicAdd(&a.d_p1_w[i], acc27[i]);
-  for (int i = threadIdx.x; i < Cr * 9; i += blockDim.x) atomicAdd(&a.d_p3_conv1[i], acc9[i]);
-  for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) atomicAdd(&a.bn3_sums[i], static_cast<double>(bsum[i]));
+  if (tid < 27) atomicAdd(&a.d_p1_w[tid], red[tid]);
+  // ---- motion branch
+  float* r7 = red + 27;
+  for (int j = 0; j < Cr; ++j) {
+    const float* w9 = a.p3_conv1 + j * 9;
+    float sb = 0.f, sq = 0.f, sbq = 0.f, r0 = 0.f, rl = 0.f, c0 = 0.f, cl = 0.f;
+    for (int p = tid; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      const float q = a.q[(m_t + p) * Cr + j];
+      const float b = border_wsum(w9, h, w, H, W);
+      sb += b; sq += q; sbq = fmaf(b, q, sbq);
+      if (h == 0) r0 += q;
+      if (h == H - 1) rl += q;
+      if (w == 0) c0 += q;
+      if (w == W - 1) cl += q;
+    }
+    sb = warp_sum(sb); sq = warp_sum(sq); sbq = warp_sum(sbq);
+    r0 = warp_sum(r0); rl = warp_sum(rl); c0 = warp_sum(c0); cl = warp_sum(cl);
+    if (lane == 0) {
+      atomicAdd(&r7[0], sb); atomicAdd(&r7[1], sq); atomicAdd(&r7[2], sbq);
+      atomicAdd(&r7[3], r0); atomicAdd(&r7[4], rl); atomicAdd(&r7[5], c0); atomicAdd(&r7[6], cl);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float dd_t = a.dd[f * Cr + j];
+      const float ddp = t > 0 ? a.dd[(f - 1) * Cr + j] : 0.f;
+      atomicAdd(&a.bn3_sums[j], static_cast<double>(fmaf(ddp, r7[0], -static_cast<float>(HW) * dd_t)));
+      atomicAdd(&a.bn3_sums[Cr + j], static_cast<double>(fmaf(ddp, r7[2], -dd_t * r7[1])));
+      if (t > 0 && ddp != 0.f) {
+        // dW3[j][kh][kw] += dd[t-1][j] * sum over output positions of x3[t][h+kh-1, w+kw-1], x3 = q*sc + sh:
+        // the visited inputs form the image minus one border row / column (inclusion-exclusion on q's sums)
+        const float sc = a.bn3_scale[j], sh = a.bn3_shift[j];
+        const float* qf = a.q + m_t * Cr + j;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const float ex_row = kh == 0 ? r7[4] : (kh == 2 ? r7[3] : 0.f);
+            const float ex_col = kw == 0 ? r7[6] : (kw == 2 ? r7[5] : 0.f);
+            float corner = 0.f;
+            if (kh != 1 && kw != 1)
+              corner = qf[(static_cast<long long>(kh == 0 ? H - 1 : 0) * W + (kw == 0 ? W - 1 : 0)) * Cr];
+            const float rsum = r7[1] - ex_row - ex_col + corner;
+            const int nrows = H - (kh != 1 ? 1 : 0), ncols = W - (kw != 1 ? 1 : 0);
+            const float cnt = static_cast<float>((nrows > 0 ? nrows : 0) * (ncols > 0 ? ncols : 0));
+            atomicAdd(&a.d_p3_conv1[j * 9 + kh * 3 + kw], ddp * fmaf(sc, rsum, sh * cnt));
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) r7[k] = 0.f;
+    }
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -617,7 +666,12 @@ extern "C" int ehgr_action_bwd_small(const ehgr_action* a, ehgr_stream_t stream)
       !a->d_p2_conv1 || !a->d_p2_expand || !a->d_p3_conv1 || !a->d_p3_expand)
     return EHGR_E_NULL;
   const size_t smem = (3 * static_cast<size_t>(a->t) * a->c + 5 * static_cast<size_t>(a->t) * a->cr + 27 + 11 * a->cr) * sizeof(float);
-  action_bwd_small_kernel<<<a->n, 256, smem, as_stream(stream)>>>(*a);
+  action_bwd_clip_kernel<<<a->n, 256, smem, as_stream(stream)>>>(*a);
+  if (int st = launch_status()) return st;
+  const size_t smem_f = (6 * static_cast<size_t>(a->h) * a->w + 40) * sizeof(float);
+  if (smem_f > 200 * 1024) return EHGR_E_UNSUPPORTED;
+  ensure_smem(action_bwd_frame_kernel, smem_f);
+  action_bwd_frame_kernel<<<static_cast<unsigned>(a->n) * a->t, 256, smem_f, as_stream(stream)>>>(*a);
   return launch_status();
 }
 
