@@ -106,7 +106,106 @@ action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward pass 2: block = one clip: the three gates from the small reductions
+// forward pass 2a: block = one FRAME: the spatio-temporal gate g1 = sigmoid(conv3d 3x3x3 of the channel
+// mean) with the three frames it needs staged in shared memory, and the motion squeeze
+//   pi[t][j] = mean_p( dw3x3(x3[t+1])[p] - x3[t][p] ),  x3 = BN(q),  t < T-1,
+// which only needs per-frame sums of q (total, first / last row and column, corners): the sum over output
+// positions of a zero-padded 3x3 conv is a weighted sum of nine rectangle sums of its input.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_rect_term(const float* w9, const float (&sm)[5], const float* qf, int Cr, int H, int W,
+                                                 float sc, float sh) {
+  // sum_p dw3x3(x3)[p] for x3 = q*sc + sh; sm = {total, row0, rowL, col0, colL} of q over the frame
+  float acc = 0.f;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const float ex_row = kh == 0 ? sm[2] : (kh == 2 ? sm[1] : 0.f);
+      const float ex_col = kw == 0 ? sm[4] : (kw == 2 ? sm[3] : 0.f);
+      float corner = 0.f;
+      if (kh != 1 && kw != 1) corner = qf[(static_cast<long long>(kh == 0 ? H - 1 : 0) * W + (kw == 0 ? W - 1 : 0)) * Cr];
+      const int nrows = H - (kh != 1 ? 1 : 0), ncols = W - (kw != 1 ? 1 : 0);
+      const float cnt = static_cast<float>((nrows > 0 ? nrows : 0) * (ncols > 0 ? ncols : 0));
+      acc = fmaf(w9[kh * 3 + kw], fmaf(sc, sm[0] - ex_row - ex_col + corner, sh * cnt), acc);
+    }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) action_gates_frame_kernel(Act a) {
+  extern __shared__ float smem[];
+  const int Cr = a.cr, T = a.t, H = a.h, W = a.w, HW = H * W;
+  float* mr = smem;            // [3][HW] channel mean of frames t-1, t, t+1 (zero outside the clip)
+  float* red = mr + 3 * HW;    // [6]
+  const long long f = blockIdx.x;
+  const int t = static_cast<int>(f % T);
+  const long long m_t = f * HW;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 3 * HW; i += blockDim.x) {
+    const int fr = i / HW, p = i - fr * HW, tt = t + fr - 1;
+    mr[i] = (tt >= 0 && tt < T) ? a.mrow[m_t + static_cast<long long>(fr - 1) * HW + p] : 0.f;
+  }
+  if (tid < 6) red[tid] = 0.f;
+  __syncthreads();
+  {
+    float w27[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) w27[k] = a.p1_w[k];
+    for (int p = tid; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      float acc = 0.f;
+#pragma unroll
+      for (int dt = -1; dt <= 1; ++dt)
+#pragma unroll
+        for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+          for (int dw = -1; dw <= 1; ++dw) {
+            const int hh = h + dh, ww = w + dw;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+              acc = fmaf(w27[(dt + 1) * 9 + (dh + 1) * 3 + dw + 1], mr[(1 + dt) * HW + hh * W + ww], acc);
+          }
+      a.g1[m_t + p] = sigmoidf(acc);
+    }
+  }
+  // ---- motion squeeze
+  const float inv_hw = 1.f / static_cast<float>(HW);
+  for (int j = 0; j < Cr; ++j) {
+    if (t == T - 1) {                         // the last frame has no successor: pi = 0 (models/action.py:103-105 pads)
+      if (tid == 0) a.pi[f * Cr + j] = 0.f;
+      continue;
+    }
+    const float* q0 = a.q + m_t * Cr + j;                                     // frame t
+    const float* q1 = a.q + (m_t + HW) * Cr + j;                              // frame t+1
+    float s0 = 0.f, tot = 0.f, r0 = 0.f, rl = 0.f, c0 = 0.f, cl = 0.f;
+    for (int p = tid; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      s0 += q0[static_cast<long long>(p) * Cr];
+      const float q = q1[static_cast<long long>(p) * Cr];
+      tot += q;
+      if (h == 0) r0 += q;
+      if (h == H - 1) rl += q;
+      if (w == 0) c0 += q;
+      if (w == W - 1) cl += q;
+    }
+    s0 = warp_sum(s0); tot = warp_sum(tot); r0 = warp_sum(r0); rl = warp_sum(rl); c0 = warp_sum(c0); cl = warp_sum(cl);
+    if (lane == 0) {
+      atomicAdd(&red[0], s0); atomicAdd(&red[1], tot); atomicAdd(&red[2], r0);
+      atomicAdd(&red[3], rl); atomicAdd(&red[4], c0); atomicAdd(&red[5], cl);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float sc = a.bn3_scale[j], sh = a.bn3_shift[j];
+      const float sm[5] = {red[1], red[2], red[3], red[4], red[5]};
+      const float conv_sum = block_rect_term(a.p3_conv1 + j * 9, sm, q1, Cr, H, W, sc, sh);
+      const float self_sum = fmaf(sc, red[0], sh * static_cast<float>(HW));
+      a.pi[f * Cr + j] = (conv_sum - self_sum) * inv_hw;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) red[k] = 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward pass 2b: block = one clip: channel gate g2 and motion gate g3 from the per-frame reductions
+// (pass 2a, action_gates_frame_kernel, has already written g1 and pi)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) action_gates_kernel(Act a) {
   extern __shared__ float smem[];
@@ -119,27 +218,8 @@ __global__ void __launch_bounds__(256) action_gates_kernel(Act a) {
   const long long f0 = n * T, m0 = f0 * HW;
   const float inv_hw = 1.f / static_cast<float>(HW);
   for (int i = threadIdx.x; i < T * C; i += blockDim.x) pm[i] = a.pool[f0 * C + i] * inv_hw;
-  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) pi[i] = 0.f;
+  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) pi[i] = a.pi[f0 * Cr + i];   // written by the frame kernel
   __syncthreads();
-  // ---- STE: 3x3x3 conv over (t,h,w) of the channel mean
-  for (int i = threadIdx.x; i < T * HW; i += blockDim.x) {
-    const int t = i / HW, p = i - t * HW, h = p / W, w = p - h * W;
-    float acc = 0.f;
-    for (int dt = -1; dt <= 1; ++dt) {
-      const int tt = t + dt;
-      if (tt < 0 || tt >= T) continue;
-      for (int dh = -1; dh <= 1; ++dh) {
-        const int hh = h + dh;
-        if (hh < 0 || hh >= H) continue;
-        for (int dw = -1; dw <= 1; ++dw) {
-          const int ww = w + dw;
-          if (ww < 0 || ww >= W) continue;
-          acc = fmaf(a.p1_w[(dt + 1) * 9 + (dh + 1) * 3 + dw + 1], a.mrow[m0 + static_cast<long long>(tt) * HW + hh * W + ww], acc);
-        }
-      }
-    }
-    a.g1[m0 + i] = sigmoidf(acc);
-  }
   // ---- CE: squeeze
   for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) {
     const int t = i / Cr, j = i - t * Cr;
@@ -161,27 +241,6 @@ __global__ void __launch_bounds__(256) action_gates_kernel(Act a) {
     r[i] = fmaxf(acc, 0.f);
   }
   __syncthreads();
-  // ---- ME: pi[t][j] = mean_p( dw3x3(x3[t+1])[p] - x3[t][p] ), t < T-1  (per-lane shared atomics: any HW)
-  for (int i = threadIdx.x; i < (T - 1) * Cr * HW; i += blockDim.x) {
-    const int p = i % HW, tj = i / HW, j = tj % Cr, t = tj / Cr;
-    const int h = p / W, w = p - h * W;
-    const float sc = a.bn3_scale[j], sh = a.bn3_shift[j];
-    const float* q1 = a.q + (m0 + static_cast<long long>(t + 1) * HW) * Cr + j;
-    float acc = 0.f;
-    for (int dh = -1; dh <= 1; ++dh) {
-      const int hh = h + dh;
-      if (hh < 0 || hh >= H) continue;
-      for (int dw = -1; dw <= 1; ++dw) {
-        const int ww = w + dw;
-        if (ww < 0 || ww >= W) continue;
-        acc = fmaf(a.p3_conv1[j * 9 + (dh + 1) * 3 + dw + 1], fmaf(q1[static_cast<long long>(hh * W + ww) * Cr], sc, sh), acc);
-      }
-    }
-    acc -= fmaf(a.q[(m0 + static_cast<long long>(t) * HW + p) * Cr + j], sc, sh);
-    atomicAdd(&pi[t * Cr + j], acc * inv_hw);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * Cr; i += blockDim.x) a.pi[f0 * Cr + i] = pi[i];
   // ---- expand + sigmoid
   for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
     const int t = i / C, c = i - t * C;
@@ -640,6 +699,11 @@ extern "C" int ehgr_action_gates(const ehgr_action* a, ehgr_stream_t stream) {
   if (!a->mrow || !a->pool || !a->q || !a->bn3_scale || !a->bn3_shift || !a->g1 || !a->g2 || !a->g3 || !a->s || !a->u || !a->pi)
     return EHGR_E_NULL;
   const size_t smem = (static_cast<size_t>(a->t) * a->c + 3 * static_cast<size_t>(a->t) * a->cr) * sizeof(float);
+  const size_t smem_f = (3 * static_cast<size_t>(a->h) * a->w + 8) * sizeof(float);
+  if (smem_f > 200 * 1024) return EHGR_E_UNSUPPORTED;
+  ensure_smem(action_gates_frame_kernel, smem_f);
+  action_gates_frame_kernel<<<static_cast<unsigned>(a->n) * a->t, 256, smem_f, as_stream(stream)>>>(*a);
+  if (int st = launch_status()) return st;
   action_gates_kernel<<<a->n, 256, smem, as_stream(stream)>>>(*a);
   return launch_status();
 }
