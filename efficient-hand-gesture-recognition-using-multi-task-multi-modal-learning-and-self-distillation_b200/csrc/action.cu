@@ -22,7 +22,8 @@ using Act = ehgr_action;
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------
-// forward pass 1: block = one frame; thread = (channel vector cv, row lane py)
+// forward pass 1: block = (frame, row split); thread = (channel vector cv, row lane py).  The spatial sums
+// (pool) are accumulated with global atomics: the caller zeroes `pool`.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -53,9 +54,11 @@ action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
   }
   float qs_sum = 0.f, qs_sq = 0.f;             // used by threads that finalise q (cv < Cr)
   const long long frame_elems = static_cast<long long>(HW) * C;
-  for (int r0 = 0; r0 < HW; r0 += P) {
+  const int rows_per_split = ((HW + gridDim.y - 1) / gridDim.y + P - 1) / P * P;
+  const int r_begin = blockIdx.y * rows_per_split, r_end = min(HW, r_begin + rows_per_split);
+  for (int r0 = r_begin; r0 < r_end; r0 += P) {
     const int row = r0 + py;
-    const bool live = active && row < HW;
+    const bool live = active && row < r_end;
     __syncthreads();
     for (int i = threadIdx.x; i < P * (Cr + 1); i += blockDim.x) s_row[i] = 0.f;
     __syncthreads();
@@ -101,7 +104,7 @@ action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
     for (int i = 0; i < V; ++i) atomicAdd(&s_pool[c0 + i], pool_acc[i]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) a.pool[nt * C + i] = s_pool[i];       // spatial SUM
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&a.pool[nt * C + i], s_pool[i]);   // spatial SUM (row splits add up)
   for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) atomicAdd(&a.qstats[i], static_cast<double>(s_qs[i]));
 }
 
@@ -687,8 +690,13 @@ extern "C" int ehgr_action_xs(const ehgr_action* a, const void* x, void* xs, int
   if (!x || !xs || !a->shift_w || !a->p3_squeeze || !a->mrow || !a->pool || !a->q || !a->qstats) return EHGR_E_NULL;
   const int V = 16 / esize_of(dtype), CV = a->c / V, P = 256 / CV;
   const size_t smem = (static_cast<size_t>(a->cr) * a->c + static_cast<size_t>(P) * (a->cr + 1) + a->c + 2 * a->cr) * sizeof(float);
-  const unsigned grid = static_cast<unsigned>(a->n) * a->t;
+  const unsigned frames = static_cast<unsigned>(a->n) * a->t;
+  const int hw = a->h * a->w;
+  int splits = static_cast<int>((4 * kNumSMs + frames - 1) / std::max(1u, frames));      // ~4 CTAs per SM in total
+  splits = std::max(1, std::min(std::min(splits, 16), (hw + P - 1) / P));
+  const dim3 grid(frames, splits);
   cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(a->pool, 0, static_cast<size_t>(frames) * a->c * sizeof(float), s);      // pool is accumulated by atomics
   if (dtype == EHGR_F32) action_xs_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(x), static_cast<float*>(xs));
   else action_xs_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xs));
   return launch_status();
