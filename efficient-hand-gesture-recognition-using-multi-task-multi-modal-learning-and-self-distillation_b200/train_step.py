@@ -41,7 +41,7 @@ class GradBuckets:
 
         total = sum(pad(p.numel()) for p in order)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self._slices, self._bucket_of, off = [], {}, 0
+        self._slices, self._bucket_of, self._offset_of, off = [], {}, {}, 0
         per_bucket = -(-total // max(1, n_buckets))
         bounds: List[List[int]] = []
         for p in order:
@@ -51,6 +51,7 @@ class GradBuckets:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             self._bucket_of[id(p)] = b
+            self._offset_of[id(p)] = off
             off += pad(n)
             bounds[b][1] = off
         self.bounds = bounds
@@ -130,9 +131,69 @@ def build_sgd(model, lr: float, momentum: float = 0.9, weight_decay: float = 5e-
     return torch.optim.SGD(policies, momentum=momentum, **({"fused": True} if fused else {}))
 
 
+class FlatSGD:
+    """torch.optim.SGD(momentum, weight_decay) over the policy groups of ``get_optim_policies``
+    (train_mtmm.py:576-585) as ONE kernel (csrc/optim.cu) over flat buffers laid out like ``GradBuckets.flat``:
+    every parameter's storage is moved into ``flat_p`` (``p.data`` becomes a view), the momentum lives in
+    ``flat_m`` (zero-initialised = torch's first-step rule).  The base learning rate is a DEVICE scalar:
+    ``set_base_lr`` (or ``adjust_learning_rate``) rewrites it without invalidating a captured CUDA graph."""
+
+    def __init__(self, policies, buckets: "GradBuckets", lr: float, momentum: float = 0.9, weight_decay: float = 5e-4):
+        self.buckets = buckets
+        self.momentum, self.weight_decay = float(momentum), float(weight_decay)
+        dev = buckets.flat.device
+        groups = [g for g in policies if len(g['params']) > 0]
+        if len(groups) > 64:
+            raise ValueError("FlatSGD supports at most 64 parameter groups")
+        self.param_groups = [{'params': list(g['params']), 'lr_mult': float(g.get('lr_mult', 1.0)),
+                              'decay_mult': float(g.get('decay_mult', 1.0)), 'name': g.get('name', ''),
+                              'lr': lr * float(g.get('lr_mult', 1.0))} for g in groups]
+        self.flat_p = torch.zeros_like(buckets.flat)
+        self.flat_m = torch.zeros_like(buckets.flat)
+        code = torch.full((buckets.flat.numel(),), 255, dtype=torch.uint8)
+        with torch.no_grad():
+            for k, g in enumerate(self.param_groups):
+                for p in g['params']:
+                    off = buckets._offset_of.get(id(p))
+                    if off is None:              # frozen parameter: not managed, never updated
+                        continue
+                    n = p.numel()
+                    self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                    p.data = self.flat_p[off:off + n].view_as(p)
+                    code[off:off + n] = k
+        self.code = code.to(dev)
+        self.lr_mult = torch.tensor([g['lr_mult'] for g in self.param_groups], dtype=torch.float32, device=dev)
+        self.decay_mult = torch.tensor([g['decay_mult'] for g in self.param_groups], dtype=torch.float32, device=dev)
+        self.lr_dev = torch.tensor([float(lr)], dtype=torch.float32, device=dev)
+        self._host_lr = torch.empty(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
+
+    def set_base_lr(self, lr: float):
+        for g in self.param_groups:
+            g['lr'] = lr * g['lr_mult']
+        if self._host_lr is not None:
+            self._host_lr[0] = float(lr)
+            self.lr_dev.copy_(self._host_lr, non_blocking=True)
+        else:
+            self.lr_dev.fill_(float(lr))
+
+    def step(self):
+        from . import _lib
+        f = self.buckets.flat
+        _lib.call("ehgr_sgd_step", self.flat_p.data_ptr(), f.data_ptr(), self.flat_m.data_ptr(), self.code.data_ptr(),
+                  self.lr_mult.data_ptr(), self.decay_mult.data_ptr(), len(self.param_groups), self.lr_dev.data_ptr(),
+                  self.momentum, self.weight_decay, f.numel(), _lib.stream_ptr(f.device), algo_bytes=f.numel() * 21)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.buckets.zero()
+
+
 def adjust_learning_rate(learning_rate, optimizer, epoch, lr_steps):
-    """utils.py:39-46.  (A train step running in CUDA-graph mode must be told: ``invalidate_graph()``.)"""
+    """utils.py:39-46.  With ``FlatSGD`` the new rate is written to its device scalar (a captured CUDA graph stays
+    valid); with a torch optimiser a train step running in CUDA-graph mode must be told: ``invalidate_graph()``."""
     gamma = 0.1 ** sum(epoch >= s for s in lr_steps)
+    if hasattr(optimizer, "set_base_lr"):
+        optimizer.set_base_lr(learning_rate * gamma)
+        return
     for g in optimizer.param_groups:
         g['lr'] = learning_rate * gamma * g['lr_mult']
 
@@ -179,8 +240,11 @@ class MTMMTrainStep:
         self.model = model
         self.compute_dtype = compute_dtype
         self.device = next(model.parameters()).device
-        self.opt = build_sgd(model, lr, momentum, weight_decay)
         self.buckets = GradBuckets(list(model.parameters()), n_buckets, process_group)
+        if self.device.type == "cuda":   # one fused kernel over flat parameter / gradient / momentum buffers
+            self.opt = FlatSGD(model.get_optim_policies(), self.buckets, lr, momentum, weight_decay)
+        else:
+            self.opt = build_sgd(model, lr, momentum, weight_decay)
         self._fused = fused
         # CUDA-graph mode: the step launches ~3600 small kernels; replaying one captured graph removes the
         # host launch cost.  The first `graph_warmup` calls run eagerly (lazy state: momentum buffers, cuDNN

@@ -193,6 +193,18 @@ int ehgr_normalize_u8(const void* src, void* dst, long long n_planes, int channe
                       const float* mean, const float* stdv, float div, int dst_dtype, ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N1  optimiser step: torch.optim.SGD (momentum, weight decay, dampening 0, no Nesterov) over the policy
+ *   groups of get_optim_policies (train_mtmm.py:576-585; lr_mult / decay_mult per group) as one kernel
+ *   over flat fp32 buffers:  d = g + wd*decay_mult[k]*p;  buf = momentum*buf + d;  p -= lr*lr_mult[k]*buf.
+ *   code: one byte per element = its group k (255 = padding, untouched); n % 4 == 0; buf starts at zero
+ *   (reproduces torch's first step).  lr is read from DEVICE memory (float[1]): a learning-rate schedule
+ *   (utils.py:39-46) only rewrites that scalar and never invalidates a captured CUDA graph.
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_sgd_step(float* p, const float* g, float* buf, const void* code, const float* lr_mult,
+                  const float* decay_mult, int n_groups, const float* lr_dev, float momentum, float weight_decay,
+                  long long n, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K10  classifier head: x.mean(3).mean(2) (archs/mobilenet_v2.py:112), new_fc and the segment
  *   consensus (models/models.py:341-356, models/basic_ops.py:9-37).
  *   pool_fwd : pooled[nt,c] (fp32) = mean over hw rows of rowop(a)

@@ -343,3 +343,41 @@ def test_sd_train_step_runs_in_graph_mode():
     assert all(l == l and abs(l) < 1e4 for l in losses), losses
     assert len({round(l, 4) for l in losses}) > 1
     assert not torch.equal(w0, model.base_model.features[1].conv[0].weight)
+
+
+def test_flat_sgd_matches_torch_sgd():
+    """FlatSGD (one kernel over flat buffers, device-side learning rate) against torch.optim.SGD with the same
+    policy groups over several steps, including a learning-rate change."""
+    import ehgr_b200 as E
+    torch.manual_seed(0)
+
+    def make():
+        ps = [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(i)).cuda())
+              for i, s in enumerate([(7, 3), (5,), (2, 2, 2), (11,), (1,), (33, 9)])]
+        pol = [{'params': [ps[0], ps[5]], 'lr_mult': 1, 'decay_mult': 1, 'name': 'w'},
+               {'params': [ps[1], ps[3]], 'lr_mult': 2, 'decay_mult': 0, 'name': 'b'},
+               {'params': [ps[2], ps[4]], 'lr_mult': 5, 'decay_mult': 1, 'name': 'fc'},
+               {'params': [], 'lr_mult': 1, 'decay_mult': 1, 'name': 'empty'}]
+        return ps, pol
+
+    ps_a, pol_a = make()
+    ps_b, pol_b = make()
+    gb = E.train_step.GradBuckets(ps_a, n_buckets=2)
+    opt_a = E.train_step.FlatSGD(pol_a, gb, lr=0.1, momentum=0.9, weight_decay=5e-4)
+    groups = [dict(params=g['params'], lr=0.1 * g['lr_mult'], weight_decay=5e-4 * g['decay_mult']) for g in pol_b if g['params']]
+    opt_b = torch.optim.SGD(groups, momentum=0.9)
+    for step in range(5):
+        if step == 3:
+            E.train_step.adjust_learning_rate(0.1, opt_a, 1, [1])      # gamma 0.1 from epoch 1 on
+            for g, pg in zip(opt_b.param_groups, [p for p in pol_b if p['params']]):
+                g['lr'] = 0.1 * 0.1 * pg['lr_mult']
+        gb.zero()
+        for i, (pa, pb) in enumerate(zip(ps_a, ps_b)):
+            gr = torch.randn(pa.shape, generator=torch.Generator().manual_seed(100 * step + i)).cuda()
+            pa.grad.copy_(gr)
+            pb.grad = gr.clone()
+        opt_a.step()
+        opt_b.step()
+        for pa, pb in zip(ps_a, ps_b):
+            assert rel_err(pa.detach(), pb.detach()) < 1e-6, step
+    assert all(p.data_ptr() >= opt_a.flat_p.data_ptr() for p in ps_a)
