@@ -381,3 +381,25 @@ def test_flat_sgd_matches_torch_sgd():
         for pa, pb in zip(ps_a, ps_b):
             assert rel_err(pa.detach(), pb.detach()) < 1e-6, step
     assert all(p.data_ptr() >= opt_a.flat_p.data_ptr() for p in ps_a)
+
+
+def test_training_reduces_the_loss():
+    """End-to-end sanity of the whole step (fused forward/backward, gradient sink, FlatSGD, CUDA graph): a few
+    dozen steps on one small fixed batch must drive the MTMM loss down substantially."""
+    import ehgr_b200 as E
+    sd0 = O.build_mtmm_state(83, "tsm", 8, seed=9)
+    with _quiet():
+        model = E.tsn_mtmm.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                               dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                               modal='rgb_depth', temporal_module='tsm')
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    for d in model.modules():
+        if isinstance(d, torch.nn.Dropout):
+            d.eval()
+    step = E.train_step.MTMMTrainStep(model, lr=2e-3, compute_dtype=torch.bfloat16, use_graph=True)
+    batch = tuple(t.cuda() for t in O.synthetic_clip_batch(4, 8, 64, 83, seed=77))
+    losses = [float(step.run(*batch).item()) for _ in range(40)]
+    assert all(l == l for l in losses), losses
+    first, last = sum(losses[:3]) / 3, sum(losses[-3:]) / 3
+    assert last < 0.6 * first, (first, last, losses[::5])
