@@ -403,3 +403,32 @@ def test_training_reduces_the_loss():
     assert all(l == l for l in losses), losses
     first, last = sum(losses[:3]) / 3, sum(losses[-3:]) / 3
     assert last < 0.6 * first, (first, last, losses[::5])
+
+
+def test_train_step_uint8_batch_equals_normalised_float_batch():
+    """The uint8 entry of the train step (frames normalised on the device) computes the same loss as feeding the
+    tensors the reference's CPU transforms would have produced."""
+    import ehgr_b200 as E
+    g = torch.Generator().manual_seed(3)
+    rgb8 = torch.randint(0, 256, (2, 8, 3, 64, 64), dtype=torch.uint8, generator=g)
+    dep8 = torch.randint(0, 256, (2, 8, 1, 64, 64), dtype=torch.uint8, generator=g)
+    labels = torch.randint(0, 83, (2,), generator=g)
+    rgbf = rgb8.float().div(255)
+    for ci, (m, s) in enumerate(zip([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])):
+        rgbf[:, :, ci].sub_(m).div_(s)
+    depf = dep8.float().div(255)
+    losses = []
+    for batch in ((rgb8, dep8, labels), (rgbf, depf, labels)):
+        sd0 = O.build_mtmm_state(83, "tsm", 8, seed=12)
+        with _quiet():
+            model = E.tsn_mtmm.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                                   dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                                   modal='rgb_depth', temporal_module='tsm')
+        model.load_state_dict(sd0, strict=True)
+        model = model.cuda().train()
+        for d in model.modules():
+            if isinstance(d, torch.nn.Dropout):
+                d.eval()
+        step = E.train_step.MTMMTrainStep(model, lr=1e-4, compute_dtype=torch.float32)
+        losses.append(float(step.run(*(t.cuda() for t in batch)).item()))
+    assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[1]), losses
