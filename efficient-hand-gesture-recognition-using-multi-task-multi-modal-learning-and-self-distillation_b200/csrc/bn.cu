@@ -79,6 +79,25 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const f
       }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
+        if constexpr (sizeof(T) == 2) {
+          // bf16: register-pair arithmetic (FFMA2 / FADD2), accumulators indexed [2k], [2k+1]
+          const uint32_t gw[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w}, rw[4] = {rq[j].x, rq[j].y, rq[j].z, rq[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float2 gg = bf2_to_f2(gw[k]);
+            const float2 rr = bf2_to_f2(rw[k]);
+            if (relu6) {
+              const float2 z = __ffma2_rn(rr, make_float2(s[2 * k], s[2 * k + 1]), make_float2(b[2 * k], b[2 * k + 1]));
+              if (!(z.x > 0.f && z.x < 6.f)) gg.x = 0.f;
+              if (!(z.y > 0.f && z.y < 6.f)) gg.y = 0.f;
+            }
+            const float2 n1 = __fadd2_rn(make_float2(a1[2 * k], a1[2 * k + 1]), gg);
+            const float2 n2 = __ffma2_rn(gg, rr, make_float2(a2[2 * k], a2[2 * k + 1]));
+            a1[2 * k] = n1.x; a1[2 * k + 1] = n1.y;
+            a2[2 * k] = n2.x; a2[2 * k + 1] = n2.y;
+          }
+          continue;
+        }
         float gv[V], rv[V];
         load_vec<T, V>(reinterpret_cast<const T*>(&gq[j]), gv);
         load_vec<T, V>(reinterpret_cast<const T*>(&rq[j]), rv);
@@ -153,6 +172,12 @@ row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, lon
       for (int j = 0; j < U; ++j) {
         const long long m = m0 + j * row_stride;
         if (m < M) {
+          if constexpr (sizeof(T) == 2) {
+            if (!addend) {                       // packed path: FFMA2 arithmetic, result re-packed directly
+              *reinterpret_cast<uint4*>(out + m * C + c0) = ld.finish_packed(a, raw[j]);
+              continue;
+            }
+          }
           float v[V];
           ld.finish(a, raw[j], v);
           if (addend) {
