@@ -47,10 +47,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 
 // sums[c] += sum_m mask*g ; sums[C+c] += sum_m mask*g*raw.  block = (bx channel vectors, P rows),
 // persistent grid-stride over rows; a thread keeps its channel vector(s) for its whole life.
-template <typename T>
+template <typename T, bool relu6>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const float* __restrict__ scale,
-                     const float* __restrict__ shift, int relu6, double* __restrict__ sums, long long M, int C) {
+                     const float* __restrict__ shift, double* __restrict__ sums, long long M, int C) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ float smem[];  // [2C]
   const int nthreads = blockDim.x * blockDim.y;
@@ -146,12 +146,16 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
 
 // out = rowop(a) (+ addend).  block = (bx channel vectors, P rows): a thread keeps ONE channel vector
 // (operand coefficients in registers) and strides over rows, four rows fetched per batch.
-template <typename T, bool kGate>
+// kMode: the operand mode as a compile-time constant (the host dispatches on it): the row loader's other
+// branches and their registers disappear, which is what bounds the occupancy of this streaming kernel.
+template <typename T, int kMode>
 __global__ void __launch_bounds__(256, 2)
-row_apply_kernel(RowOp a, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv_total) {
+row_apply_kernel(RowOp a_in, const T* __restrict__ addend, T* __restrict__ out, long long M, int C, int cv_total) {
   constexpr int V = VecOf<T>::N;
   constexpr int U = 4;
-  using Ld = RowLoader<T, V, true, kGate>;
+  using Ld = RowLoader<T, V, kMode == EHGR_ROW_BNBWD, kMode == EHGR_ROW_GATE>;
+  RowOp a = a_in;
+  a.mode = kMode;
   const long long row_stride = static_cast<long long>(gridDim.x) * blockDim.y;
   for (int cv = threadIdx.x; cv < cv_total; cv += blockDim.x) {
     const int c0 = cv * V;
@@ -229,12 +233,16 @@ extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* s
   const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), cap));
   const size_t smem = static_cast<size_t>(2) * c * sizeof(float);
   cudaStream_t s = as_stream(stream);
-  if (dtype == EHGR_F32)
-    bn_bwd_reduce_kernel<float><<<static_cast<unsigned>(blocks), block, smem, s>>>(
-        static_cast<const float*>(g), static_cast<const float*>(raw), scale, shift, relu6, sums, m, c);
-  else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), block, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(raw), scale, shift, relu6, sums, m, c);
+  auto go = [&](auto tag, auto rtag) {
+    using T = decltype(tag);
+    bn_bwd_reduce_kernel<T, decltype(rtag)::value><<<static_cast<unsigned>(blocks), block, smem, s>>>(
+        static_cast<const T*>(g), static_cast<const T*>(raw), scale, shift, sums, m, c);
+  };
+  if (dtype == EHGR_F32) {
+    if (relu6) go(float{}, std::true_type{}); else go(float{}, std::false_type{});
+  } else {
+    if (relu6) go(__nv_bfloat16{}, std::true_type{}); else go(__nv_bfloat16{}, std::false_type{});
+  }
   return launch_status();
 }
 
@@ -264,16 +272,20 @@ extern "C" int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out
   const dim3 block(bx, std::max(1, 256 / bx));
   const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), 8LL * kNumSMs));
   cudaStream_t s = as_stream(stream);
-  const bool gate = a->mode == EHGR_ROW_GATE;
-  auto launch = [&](auto tag, auto gate_tag) {
+  auto launch = [&](auto tag, auto mode_tag) {
     using T = decltype(tag);
-    row_apply_kernel<T, decltype(gate_tag)::value><<<static_cast<unsigned>(blocks), block, 0, s>>>(
+    row_apply_kernel<T, decltype(mode_tag)::value><<<static_cast<unsigned>(blocks), block, 0, s>>>(
         *a, static_cast<const T*>(addend), static_cast<T*>(out), m, c, cv);
   };
-  if (dtype == EHGR_F32) {
-    if (gate) launch(float{}, std::true_type{}); else launch(float{}, std::false_type{});
-  } else {
-    if (gate) launch(__nv_bfloat16{}, std::true_type{}); else launch(__nv_bfloat16{}, std::false_type{});
-  }
+  auto by_mode = [&](auto tag) {
+    switch (a->mode) {
+      case EHGR_ROW_PLAIN: launch(tag, std::integral_constant<int, EHGR_ROW_PLAIN>{}); break;
+      case EHGR_ROW_AFFINE: launch(tag, std::integral_constant<int, EHGR_ROW_AFFINE>{}); break;
+      case EHGR_ROW_SHIFT: launch(tag, std::integral_constant<int, EHGR_ROW_SHIFT>{}); break;
+      case EHGR_ROW_BNBWD: launch(tag, std::integral_constant<int, EHGR_ROW_BNBWD>{}); break;
+      default: launch(tag, std::integral_constant<int, EHGR_ROW_GATE>{}); break;
+    }
+  };
+  if (dtype == EHGR_F32) by_mode(float{}); else by_mode(__nv_bfloat16{});
   return launch_status();
 }
