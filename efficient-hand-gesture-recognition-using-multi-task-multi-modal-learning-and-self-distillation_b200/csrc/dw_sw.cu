@@ -173,7 +173,11 @@ dw_fwd_sw_kernel(RowOp a, const __grid_constant__ CUtensorMap tm_a, const float*
       w2[t][i] = make_float2(w0, w1);
     }
   Ld ld;
-  if (cv_on) ld.init(a, c0, g.c);
+  if (cv_on && a.mode == EHGR_ROW_AFFINE) {
+    RowOp ac = a;
+    ac.mode = EHGR_ROW_AFFINE;
+    ld.init(ac, c0, g.c);
+  }
   float2 tsum[4], tsq[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) tsum[i] = tsq[i] = make_float2(0.f, 0.f);
@@ -213,8 +217,11 @@ dw_fwd_sw_kernel(RowOp a, const __grid_constant__ CUtensorMap tm_a, const float*
     }
     mbar_wait(bar0 + 8 * buf, phase[buf]);               // this tile has landed (the next one may still be in flight)
     phase[buf] ^= 1;
-    if (cv_on && a.mode != EHGR_ROW_PLAIN)
-      tile_transform<Cfg::IH, Cfg::IW, CVN, Ld>(a, ld, tile, tile, g.h, g.w, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
+    if (cv_on && a.mode != EHGR_ROW_PLAIN) {
+      RowOp ac = a;
+      ac.mode = EHGR_ROW_AFFINE;        // the only other mode the host lets through: a compile-time constant for the loader
+      tile_transform<Cfg::IH, Cfg::IW, CVN, Ld>(ac, ld, tile, tile, g.h, g.w, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
+    }
     __syncthreads();
     if (col < TW) {
       const int wo = wo0 + col;
@@ -346,14 +353,18 @@ dw_bwd_sw_kernel(RowOp dy, RowOp a, const __grid_constant__ CUtensorMap tm_a, co
     phase ^= 1;
     if (cv_on && !(g.dbg & 256)) {
       if (a.mode != EHGR_ROW_PLAIN) {
+        RowOp ac = a;
+        ac.mode = EHGR_ROW_AFFINE;      // compile-time constants for the loaders (the host admits only these modes)
         RowLoader<__nv_bfloat16, 8, false, false> ld;
-        ld.init(a, c0, g.c);
-        tile_transform<Cfg::IH, Cfg::IW, CVN>(a, ld, a_tile, a_tile, g.h, g.w, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
+        ld.init(ac, c0, g.c);
+        tile_transform<Cfg::IH, Cfg::IW, CVN>(ac, ld, a_tile, a_tile, g.h, g.w, ho0 * STRIDE - 1, wo0 * STRIDE - 1, cv, col);
       }
       if (two) {
+        RowOp dc = dy;
+        dc.mode = EHGR_ROW_BNBWD;
         RowLoader<__nv_bfloat16, 8, true, false> ld;
-        ld.init(dy, c0, g.c);
-        tile_transform<DH, DWID, CVN>(dy, ld, g_tile, r_tile, g.ho, g.wo, ho0 - DOFF, wo0 - DOFF, cv, col);
+        ld.init(dc, c0, g.c);
+        tile_transform<DH, DWID, CVN>(dc, ld, g_tile, r_tile, g.ho, g.wo, ho0 - DOFF, wo0 - DOFF, cv, col);
       }
     }
     __syncthreads();

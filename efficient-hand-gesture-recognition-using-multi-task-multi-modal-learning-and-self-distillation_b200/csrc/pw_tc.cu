@@ -293,7 +293,29 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           }
           if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
           cp_async_wait_all();
-          if (mode == EHGR_ROW_AFFINE || mode == EHGR_ROW_GATE) {
+          if (mode == EHGR_ROW_AFFINE) {            // the hot one: constant mode, no GATE code in the loop
+            RowOp ac = p.a;
+            ac.mode = EHGR_ROW_AFFINE;
+#pragma unroll 1
+            for (int pass = 0; pass * 4 < kv; ++pass) {
+              const int k8 = pass * 4 + (slot % kvp);
+              const int k = k_base + k8 * 8;
+              if (!(k8 < kv && k < p.K)) continue;
+              RowLoader<__nv_bfloat16, 8, false, false> ld;
+              ld.init(ac, k, p.K);
+#pragma unroll 4
+              for (int j = 0; j * f < 16; ++j) {
+                const int rg = j * f + slot / kvp;
+                const long long m = m0 + rg * 8 + r;
+                if (rg < 16 && m < p.M) {
+                  const uint32_t dst = a_dst32 + rg * a_sbo + k8 * 128 + r * 16;
+                  RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
+                  raw.a = lds128(dst);
+                  sts128(dst, ld.finish_packed(ac, raw));
+                }
+              }
+            }
+          } else if (mode == EHGR_ROW_GATE) {
 #pragma unroll 1
             for (int pass = 0; pass * 4 < kv; ++pass) {
               const int k8 = pass * 4 + (slot % kvp);

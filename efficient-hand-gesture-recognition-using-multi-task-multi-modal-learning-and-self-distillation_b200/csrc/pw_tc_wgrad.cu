@@ -107,7 +107,9 @@ __device__ __forceinline__ void wg_affine_inplace(const RowOp& op, const WgLane&
       const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
       RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
       raw.a = lds128(dst);
-      sts128(dst, ld.finish_packed(op, raw));
+      RowOp oc = op;
+      oc.mode = EHGR_ROW_AFFINE;          // only called for AFFINE: a constant for the loader
+      sts128(dst, ld.finish_packed(oc, raw));
     }
   }
 }
