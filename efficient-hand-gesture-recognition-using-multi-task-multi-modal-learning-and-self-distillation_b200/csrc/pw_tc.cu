@@ -28,6 +28,8 @@
 // The two TMEM buffers let the epilogue of tile i overlap the loads and MMAs of tile i+1.
 // w_is_kn selects the B operand's major-ness: forward reads the conv weight [N,K] as a K-major B,
 // dgrad reads the same array [K,N] as an MN-major B — no transposed weight copy exists.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace ehgr {
@@ -144,14 +146,15 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
   }
 }
 
-// kAsync = true : operand modes PLAIN / AFFINE / SHIFT / GATE.  A producer warp fills its ring stage with
+// kMode != BNBWD (kAsync): operand modes PLAIN / AFFINE / SHIFT / GATE.  A producer warp fills its ring stage with
 //                  16-byte cp.async copies straight into the core-matrix layout (a whole 16 KB stage in
 //                  flight per warp, no registers held), waits, and — for AFFINE / GATE — transforms the
 //                  stage IN PLACE (each lane re-reads exactly the chunks it copied).  SHIFT is a pure gather:
 //                  the copy's source is the neighbouring frame or a zero fill.
 // kAsync = false: register path (batched fetch -> rowop -> store) for the two-tensor BNBWD operand.
-template <bool kAsync>
+template <int kMode>
 __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
+  constexpr bool kAsync = kMode != EHGR_ROW_BNBWD;     // the operand mode is a compile-time constant: one kernel per mode
   extern __shared__ __align__(128) uint8_t smem[];
   const int Kp = (p.K + 15) & ~15;
   const int b_res_bytes = p.b_resident ? p.BN * Kp * 2 : 0;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
         const int f = 4 / kvp;                         // spare slots interleave row groups (kv == 2)
         if constexpr (kAsync) {
           mbar_wait(bar_empty + 8 * s, parity);
-          const int mode = p.a.mode;
+          constexpr int mode = kMode;
           const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(p.a.in1);
           const uint32_t a_dst32 = smem_u32(a_dst);
           // SHIFT: frame / segment index of the tile's first row (rows advance by < 128 inside a stage)
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
               if (k8 < kv && rg < 16) {
                 uint4 packed = make_uint4(0, 0, 0, 0);
                 if (live[j]) {
-                  if (p.a.mode == EHGR_ROW_PLAIN) {
+                  if (kMode == EHGR_ROW_PLAIN) {
                     packed = raw[j].a;                      // already bf16: a straight 16-byte copy
                   } else {
                     float v[8];
@@ -556,12 +559,17 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   long long grid = std::min<long long>(tiles, kNumSMs);
   grid = std::max<long long>(p.n_chunks, grid / p.n_chunks * p.n_chunks);
   const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes;
-  if (a.mode == EHGR_ROW_BNBWD) {
-    ensure_smem(tc::pw_gemm_tc_kernel<false>, kBudget);
-    tc::pw_gemm_tc_kernel<false><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
-  } else {
-    ensure_smem(tc::pw_gemm_tc_kernel<true>, kBudget);
-    tc::pw_gemm_tc_kernel<true><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
+  auto go = [&](auto mode_tag) {
+    constexpr int kMode = decltype(mode_tag)::value;
+    ensure_smem(tc::pw_gemm_tc_kernel<kMode>, kBudget);
+    tc::pw_gemm_tc_kernel<kMode><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
+  };
+  switch (a.mode) {
+    case EHGR_ROW_PLAIN: go(std::integral_constant<int, EHGR_ROW_PLAIN>{}); break;
+    case EHGR_ROW_AFFINE: go(std::integral_constant<int, EHGR_ROW_AFFINE>{}); break;
+    case EHGR_ROW_SHIFT: go(std::integral_constant<int, EHGR_ROW_SHIFT>{}); break;
+    case EHGR_ROW_GATE: go(std::integral_constant<int, EHGR_ROW_GATE>{}); break;
+    default: go(std::integral_constant<int, EHGR_ROW_BNBWD>{}); break;
   }
   return launch_status();
 }
