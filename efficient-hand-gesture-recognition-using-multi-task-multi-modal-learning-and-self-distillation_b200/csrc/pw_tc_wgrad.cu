@@ -10,6 +10,8 @@
 //   splits, each split strides over the row chunks; the epilogue adds the partial tile to dw with fp32
 //   atomics.  Warps: 0-6 producers (one ring stage each, lane = row, batched fetch), 7 MMA issuer,
 //   0-3 double as the epilogue at the end.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace ehgr {
@@ -45,6 +47,7 @@ struct WgLane {
   bool on;                // g < groups
 };
 
+template <int kMode>
 __device__ __forceinline__ WgLane wg_lane(const RowOp& op, int c_base, int groups, int lane) {
   WgLane w;
   int lg = 0;
@@ -54,7 +57,7 @@ __device__ __forceinline__ WgLane wg_lane(const RowOp& op, int c_base, int group
   w.rstep = 32 >> lg;
   w.on = w.g < groups;
   w.cls = 2;
-  if (op.mode == EHGR_ROW_SHIFT && w.on) {
+  if (kMode == EHGR_ROW_SHIFT && w.on) {
     const int c = c_base + w.g * 8, fold = op.fold;
     const int cl = c < fold ? 0 : (c < 2 * fold ? 1 : 2);
     const int ch = c + 7 < fold ? 0 : (c + 7 < 2 * fold ? 1 : 2);
@@ -63,6 +66,7 @@ __device__ __forceinline__ WgLane wg_lane(const RowOp& op, int c_base, int group
   return w;
 }
 
+template <int kMode>
 __device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_base, int C, uint32_t dst_base, int gs,
                                         long long m_base, long long M) {
   if (!w.on) return;
@@ -70,7 +74,7 @@ __device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_
   const int c = c_base + w.g * 8;
   int t0 = 0, rem0 = 0;
   const int dir = op.shift_dir < 0 ? -1 : 1;
-  if (op.mode == EHGR_ROW_SHIFT && w.cls != 2) {
+  if (kMode == EHGR_ROW_SHIFT && w.cls != 2) {
     const long long f0 = m_base / op.hw;
     rem0 = static_cast<int>(m_base - f0 * op.hw);
     t0 = static_cast<int>(f0 % op.n_segment);
@@ -82,7 +86,7 @@ __device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_
     bool live = m < M;
     const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
     const __nv_bfloat16* src = in1 + m * C + c;
-    if (op.mode == EHGR_ROW_SHIFT && w.cls != 2 && live) {
+    if (kMode == EHGR_ROW_SHIFT && w.cls != 2 && live) {
       if (w.cls == 3) {
         sts128(dst, shift_straddle_raw<__nv_bfloat16, 8>(op, m, c, C));
         continue;
@@ -115,8 +119,11 @@ __device__ __forceinline__ void wg_affine_inplace(const RowOp& op, const WgLane&
 }
 
 // kAsync: dy is PLAIN and a is PLAIN / AFFINE / SHIFT (what the fused chain issues); otherwise the register path.
-template <bool kAsync>
+// kAMode: mode of operand a as a compile-time constant (PLAIN / AFFINE / SHIFT: asynchronous path, dy PLAIN);
+// -1: the generic register path.
+template <int kAMode>
 __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p) {
+  constexpr bool kAsync = kAMode >= 0;
   extern __shared__ __align__(128) uint8_t smem[];
   const int gs = kMS * 16;                              // bytes between channel groups inside a stage
   const int dy_bytes = 16 * gs;                         // 128 n = 16 groups
@@ -155,9 +162,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
 
   if (warp < pw) {
     if constexpr (kAsync) {
-      const WgLane wl_dy = wg_lane(p.dy, n0, ng, lane), wl_a = wg_lane(p.a, k0, kg, lane);
+      const WgLane wl_dy = wg_lane<EHGR_ROW_PLAIN>(p.dy, n0, ng, lane), wl_a = wg_lane<kAMode>(p.a, k0, kg, lane);
       RowLoader<__nv_bfloat16, 8, false, false> ld_a;
-      if (p.a.mode == EHGR_ROW_AFFINE && wl_a.on) ld_a.init(p.a, k0 + wl_a.g * 8, p.K);
+      if (kAMode == EHGR_ROW_AFFINE && wl_a.on) {
+        RowOp ac = p.a;
+        ac.mode = EHGR_ROW_AFFINE;
+        ld_a.init(ac, k0 + wl_a.g * 8, p.K);
+      }
       int s = 0, turn = 0;
       uint32_t ph = 0;
       for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++s, ++turn) {
@@ -166,10 +177,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
         if (turn != warp) continue;
         const uint32_t dy_dst = smem_base + s * p.stage_bytes, a_dst = dy_dst + dy_bytes;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        wg_copy(p.dy, wl_dy, n0, p.N, dy_dst, gs, mc * kMS, p.M);
-        wg_copy(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M);
+        wg_copy<EHGR_ROW_PLAIN>(p.dy, wl_dy, n0, p.N, dy_dst, gs, mc * kMS, p.M);
+        wg_copy<kAMode>(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M);
         cp_async_wait_all();
-        if (p.a.mode == EHGR_ROW_AFFINE) wg_affine_inplace(p.a, wl_a, ld_a, a_dst, gs, mc * kMS, p.M);
+        if (kAMode == EHGR_ROW_AFFINE) wg_affine_inplace(p.a, wl_a, ld_a, a_dst, gs, mc * kMS, p.M);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -313,13 +324,15 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes;
   const bool async = dy.mode == EHGR_ROW_PLAIN &&
                      (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_SHIFT);
-  if (async) {
-    ensure_smem(tc::pw_wgrad_tc_kernel<true>, kBudget);
-    tc::pw_wgrad_tc_kernel<true><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
-  } else {
-    ensure_smem(tc::pw_wgrad_tc_kernel<false>, kBudget);
-    tc::pw_wgrad_tc_kernel<false><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
-  }
+  auto go = [&](auto mode_tag) {
+    constexpr int kAMode = decltype(mode_tag)::value;
+    ensure_smem(tc::pw_wgrad_tc_kernel<kAMode>, kBudget);
+    tc::pw_wgrad_tc_kernel<kAMode><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
+  };
+  if (!async) go(std::integral_constant<int, -1>{});
+  else if (a.mode == EHGR_ROW_PLAIN) go(std::integral_constant<int, EHGR_ROW_PLAIN>{});
+  else if (a.mode == EHGR_ROW_AFFINE) go(std::integral_constant<int, EHGR_ROW_AFFINE>{});
+  else go(std::integral_constant<int, EHGR_ROW_SHIFT>{});
   return launch_status();
 }
 
