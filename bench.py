@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--temporal", default="tsm", choices=["tsm", "action", "none"])
+    ap.add_argument("--workload", default="mtmm", choices=["mtmm", "sd"],
+                    help="mtmm: BASELINE configs[1] (the headline); sd: the stage-2 self-distillation step (configs[2]), "
+                         "reported for the record (its reference arm / CPU baseline are not wired)")
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-input", choices=["uint8", "float32"], default="uint8",
@@ -185,14 +188,25 @@ def run_ours(args):
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(1)  # train_mtmm.py:43 default seed; identical initial weights on every rank
+    sd_mode = args.workload == "sd"
     with quiet():
-        model = ehgr_b200.tsn_mtmm.TSN(NUM_CLASS, T_SEG, 'RGB', is_shift=(args.temporal != "none"), partial_bn=False,
-                                       base_model='mobilenetv2', shift_div=8, dropout=0.5, img_feature_dim=224,
-                                       pretrain=None, consensus_type='avg', fc_lr5=True, modal='rgb_depth',
-                                       temporal_module=("tsm" if args.temporal == "tsm" else "action"))
+        if sd_mode:
+            model = ehgr_b200.tsn_sd.TSN(NUM_CLASS, T_SEG, 'RGB', is_shift=(args.temporal != "none"), partial_bn=False,
+                                         base_model='mobilenetv2', shift_div=8, dropout=0.5, img_feature_dim=224,
+                                         pretrain=None, consensus_type='avg', fc_lr5=True,
+                                         temporal_module=("tsm" if args.temporal == "tsm" else "action"))
+        else:
+            model = ehgr_b200.tsn_mtmm.TSN(NUM_CLASS, T_SEG, 'RGB', is_shift=(args.temporal != "none"), partial_bn=False,
+                                           base_model='mobilenetv2', shift_div=8, dropout=0.5, img_feature_dim=224,
+                                           pretrain=None, consensus_type='avg', fc_lr5=True, modal='rgb_depth',
+                                           temporal_module=("tsm" if args.temporal == "tsm" else "action"))
     model = model.to(dev)
     model.train()
-    step = ehgr_b200.train_step.MTMMTrainStep(model, compute_dtype=dtype, use_graph=not args.no_graph)
+    step_cls = ehgr_b200.train_step.SDTrainStep if sd_mode else ehgr_b200.train_step.MTMMTrainStep
+    step = step_cls(model, compute_dtype=dtype, use_graph=not args.no_graph)
+
+    def pick(batch):          # the SD step takes (rgb, labels); the MTMM step (rgb, depth, labels)
+        return (batch[0], batch[2]) if sd_mode else batch
 
     B = args.batch
     g = torch.Generator().manual_seed(100 + rank)
@@ -210,7 +224,7 @@ def run_ours(args):
                      h[2]) for h in host]
     else:
         host_e2e = host
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host_e2e[0])
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pick(host_e2e[0]))
 
     def barrier():
         if world > 1:
@@ -239,7 +253,7 @@ def run_ours(args):
 
     def leg_resident(k):
         for i in range(k):
-            last_loss["v"] = step.run(*resident[i % n_host])
+            last_loss["v"] = step.run(*pick(resident[i % n_host]))
 
     leg_resident(args.warmup)
     sampler = ClockSampler(local)
@@ -264,7 +278,7 @@ def run_ours(args):
     def leg_e2e(k):
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
-            nxt = step.stage(*host_e2e[0])
+            nxt = step.stage(*pick(host_e2e[0]))
         last = None
         for i in range(k):
             cur.wait_stream(copy_stream)
@@ -273,7 +287,7 @@ def run_ours(args):
                 t.record_stream(cur)
             if i + 1 < k:
                 with torch.cuda.stream(copy_stream):
-                    nxt = step.stage(*host_e2e[(i + 1) % n_host])
+                    nxt = step.stage(*pick(host_e2e[(i + 1) % n_host]))
             loss = step.run(*batch)
             if last is not None:
                 last.item()          # D2H read of the previous step's loss (keeps one step in flight)
@@ -295,8 +309,10 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"MTMM stage-1 step (fwd+loss+bwd+allreduce+SGD), {args.temporal.upper()}-MobileNetV2 "
-                                   f"RGB+pseudo-depth, 8x224^2, 83 classes, train-mode BN",
+            "config": {"workload": (f"SD stage-2 step (fwd with 3 exit heads + SD loss + bwd + allreduce + SGD), "
+                                    f"{args.temporal.upper()}-MobileNetV2 RGB, 8x224^2, 83 classes, train-mode BN" if sd_mode else
+                                    f"MTMM stage-1 step (fwd+loss+bwd+allreduce+SGD), {args.temporal.upper()}-MobileNetV2 "
+                                    f"RGB+pseudo-depth, 8x224^2, 83 classes, train-mode BN"),
                        "clips_per_gpu": B, "global_clips": B * world, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if step.use_graph else "eager",
                        "l2": "activations >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
@@ -311,7 +327,7 @@ def run_ours(args):
             "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
             "ms_per_step_with_kernel_events": round(ms_prof / args.steps, 3),
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not sd_mode:
             v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"3 steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32 oracle "
