@@ -69,6 +69,14 @@ class GradBuckets:
         self.flat.zero_()
         self._left = list(self._need)
         self._works = []
+        # a caller's ``optimizer.zero_grad(set_to_none=True)`` or a replaced ``.grad`` would silently detach a
+        # parameter from the flat buffer (the fused optimiser and the all-reduce only see the buffer): re-attach
+        base = self.flat.data_ptr()
+        for p in self.params:
+            g = p.grad
+            if g is None or g.data_ptr() != base + 4 * self._offset_of[id(p)]:
+                off = self._offset_of[id(p)]
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
 
     def _launch(self, b: int):
         lo, hi = self.bounds[b]

@@ -50,6 +50,14 @@ def _worker(rank, world, port, out):
     for i, p in enumerate(params):
         assert torch.allclose(p.grad, torch.full_like(p, want * (i + 1))), (rank, i)
     assert gb.view_for(torch.nn.Parameter(torch.zeros(3))) is None
+    # a gradient detached by the caller (set_to_none / replaced tensor) is re-attached by the next zero()
+    params[1].grad = None
+    params[2].grad = torch.ones_like(params[2])
+    gb.zero()
+    assert params[1].grad is not None and params[1].grad.data_ptr() == gb.flat.data_ptr() + 4 * gb._offset_of[id(params[1])]
+    assert params[2].grad.data_ptr() == gb.flat.data_ptr() + 4 * gb._offset_of[id(params[2])]
+    assert float(params[2].grad.abs().sum()) == 0.0
+    gb.finish()
     # unused parameter: its bucket is flushed by finish()
     gb.zero()
     (params[0] * 2.0).sum().backward()
