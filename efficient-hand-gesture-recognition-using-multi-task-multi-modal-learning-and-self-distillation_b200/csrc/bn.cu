@@ -229,7 +229,7 @@ extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* s
   while (bx > 256) bx = (bx + 1) / 2;
   const dim3 block(bx, std::max(1, 256 / bx));
   // every CTA ends with 2C double atomics: cap the CTA count for wide layers (they have few rows anyway)
-  const long long cap = std::max<long long>(kNumSMs, std::min<long long>(8LL * kNumSMs, 300000LL / (2 * c)));
+  const long long cap = std::max<long long>(kNumSMs, std::min<long long>(4LL * kNumSMs, 300000LL / (2 * c)));   // one resident wave
   const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), cap));
   const size_t smem = static_cast<size_t>(2) * c * sizeof(float);
   cudaStream_t s = as_stream(stream);
@@ -270,7 +270,7 @@ extern "C" int ehgr_row_apply(const ehgr_rowop* a, const void* addend, void* out
   int bx = cv;
   while (bx > 256) bx = (bx + 1) / 2;
   const dim3 block(bx, std::max(1, 256 / bx));
-  const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), 8LL * kNumSMs));
+  const long long blocks = std::max(1LL, std::min(cdiv(m, 4LL * block.y), 4LL * kNumSMs));
   cudaStream_t s = as_stream(stream);
   auto launch = [&](auto tag, auto mode_tag) {
     using T = decltype(tag);
