@@ -44,3 +44,24 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.ehgr_temporal_shift_fwd(p, p + 32, 1, 8, 8, 4, 5, 0, 0, None) == -4             # 2*fold > c
     assert lib.ehgr_temporal_shift_fwd(p + 1, p + 32, 1, 8, 8, 4, 1, 0, 0, None) == -2         # alignment
     assert lib.ehgr_temporal_shift_fwd(p, p + 32, 0, 8, 8, 4, 1, 0, 0, None) == 0              # empty batch
+
+
+def test_built_objects_contain_the_blackwell_instructions():
+    """SASS evidence (no GPU needed): the GEMMs issue tcgen05 MMAs (UTCHMMA) fed by cp.async (LDGSTS), the depthwise
+    and stem kernels load their tiles with TMA (UTMALDG), and the FP32 inner loops use packed FFMA2."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    if shutil.which("cuobjdump") is None:
+        import pytest
+        pytest.skip("cuobjdump not available")
+    import ehgr_b200
+    build = Path(ehgr_b200._lib.LIB_PATH).parent / "build"
+    if not (build / "pw_tc.o").exists():
+        ehgr_b200.build.build()
+    want = {"pw_tc.o": ("UTCHMMA", "LDGSTS", "UTCBAR"), "pw_tc_wgrad.o": ("UTCHMMA", "LDGSTS"),
+            "dw_sw.o": ("UTMALDG", "FFMA2"), "stem.o": ("UTMALDG", "FFMA2"), "bn.o": ("FFMA2",)}
+    for obj, mnemonics in want.items():
+        sass = subprocess.run(["cuobjdump", "-sass", str(build / obj)], capture_output=True, text=True, timeout=300).stdout
+        for m in mnemonics:
+            assert m in sass, (obj, m)
