@@ -104,3 +104,12 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["config"]["workload"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_normalize_u8_refuses_cpu_tensors_and_wrong_dtypes():
+    """No CPU fallback anywhere in the product: the device-side input normalisation says so instead of computing."""
+    import pytest
+    import torch
+    import ehgr_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ehgr_b200.train_step.normalize_u8(torch.zeros((1, 3, 4, 4), dtype=torch.uint8))
