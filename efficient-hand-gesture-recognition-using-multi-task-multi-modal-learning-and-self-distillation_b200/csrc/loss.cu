@@ -61,12 +61,16 @@ mtmm_loss_kernel(const float* __restrict__ logits, const long long* __restrict__
     const int n = blockIdx.x;
     const float* z = logits + static_cast<size_t>(n) * K;
     const float lse = block_lse(z, K, 1.f, scratch);
-    const int y = static_cast<int>(labels[n]);
+    const long long y64 = labels[n];
+    // A label outside [0, K) never indexes memory: the row's loss and gradient become NaN (the reference's
+    // nn.CrossEntropyLoss raises a device assert there).  ignore_index is not supported.
+    const bool bad = y64 < 0 || y64 >= K;
+    const int y = bad ? 0 : static_cast<int>(y64);
     const float inv_n = 1.f / static_cast<float>(N);
     for (int j = threadIdx.x; j < K; j += blockDim.x)
-      dlogits[static_cast<size_t>(n) * K + j] = (expf(z[j] - lse) - (j == y ? 1.f : 0.f)) * inv_n;
+      dlogits[static_cast<size_t>(n) * K + j] = bad ? NAN : (expf(z[j] - lse) - (j == y ? 1.f : 0.f)) * inv_n;
     if (threadIdx.x == 0) {
-      const float ce = (lse - z[y]) * inv_n;
+      const float ce = bad ? NAN : (lse - z[y]) * inv_n;
       atomicAdd(&loss_out[1], ce);
       atomicAdd(&loss_out[0], ce);
     }
@@ -115,8 +119,10 @@ sd_loss_kernel(SdPtrs p, const long long* __restrict__ labels, float alpha, floa
   __shared__ float scratch[32];
   if (static_cast<int>(blockIdx.x) < row_blocks) {
     const int n = blockIdx.x;
-    const int y = static_cast<int>(labels[n]);
-    const float inv_n = 1.f / static_cast<float>(N), inv_t = 1.f / temp;
+    const long long y64 = labels[n];
+    const bool bad = y64 < 0 || y64 >= K;           // out-of-range label: NaN loss / gradient, no out-of-bounds read
+    const int y = bad ? 0 : static_cast<int>(y64);
+    const float inv_n = bad ? NAN : 1.f / static_cast<float>(N), inv_t = 1.f / temp;
     const float* z0 = p.logits[0] + static_cast<size_t>(n) * K;
     const float lse0 = block_lse(z0, K, 1.f, scratch);
     const float lse0t = block_lse(z0, K, inv_t, scratch);

@@ -45,9 +45,11 @@ class GradBuckets:
         per_bucket = -(-total // max(1, n_buckets))
         bounds: List[List[int]] = []
         for p in order:
-            b = min(off // per_bucket, n_buckets - 1)
-            if len(bounds) <= b:
+            # buckets are opened one after the other: a new one only when the current one is full (a single
+            # parameter larger than a bucket's share simply fills its bucket; no bucket index is ever skipped)
+            if not bounds or (bounds[-1][1] - bounds[-1][0] >= per_bucket and len(bounds) < n_buckets):
                 bounds.append([off, off])
+            b = len(bounds) - 1
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             self._bucket_of[id(p)] = b
@@ -270,6 +272,65 @@ class MTMMTrainStep:
             self._mean_std = (torch.tensor(model.input_mean, dtype=torch.float32, device=self.device),
                               torch.tensor(model.input_std, dtype=torch.float32, device=self.device))
         self.launches_per_step = None      # libehgr_b200 kernel launches of one step (counted while capturing)
+        self.group = process_group
+        if self.buckets.world > 1:
+            self.sync_initial_state()
+
+    # -- replica consistency ----------------------------------------------------------------------
+    def _src(self):
+        return dist.get_global_rank(self.group, 0) if self.group is not None else 0
+
+    def sync_initial_state(self):
+        """Every rank starts from rank 0's parameters, momentum and buffers (BatchNorm running statistics,
+        num_batches_tracked): ranks that seeded differently or loaded different checkpoints would otherwise
+        average gradients taken at different weights and drift apart silently.  One broadcast of the flat
+        parameter / momentum buffers (FlatSGD has already moved every trainable parameter into them) plus one
+        per unmanaged tensor."""
+        with torch.no_grad():
+            if isinstance(self.opt, FlatSGD):
+                dist.broadcast(self.opt.flat_p, self._src(), group=self.group)
+                dist.broadcast(self.opt.flat_m, self._src(), group=self.group)
+                managed = {id(p) for p in self.buckets.params}
+                rest = [p.data for p in self.model.parameters() if id(p) not in managed]
+            else:
+                rest = [p.data for p in self.model.parameters()]
+            for t in rest + [b.data for b in self.model.buffers()]:
+                dist.broadcast(t, self._src(), group=self.group)
+
+    def sync_bn_buffers(self):
+        """BatchNorm batch statistics are per rank while training (the reference has no SyncBN and is
+        single-GPU); the running statistics therefore differ slightly between ranks.  Call this before saving a
+        checkpoint / evaluating: floating-point buffers are averaged over the ranks, integer ones
+        (num_batches_tracked) are taken from rank 0."""
+        if self.buckets.world <= 1:
+            return
+        with torch.no_grad():
+            for b in self.model.buffers():
+                if b.is_floating_point():
+                    dist.all_reduce(b.data, group=self.group)
+                    b.data.div_(self.buckets.world)
+                else:
+                    dist.broadcast(b.data, self._src(), group=self.group)
+
+    def param_checksum(self) -> torch.Tensor:
+        """[sum, sum of squares] of all parameters in fp64 — equal on every rank iff the replicas are in sync."""
+        with torch.no_grad():
+            ps = [self.opt.flat_p] if isinstance(self.opt, FlatSGD) else [p.data for p in self.model.parameters()]
+            s = torch.zeros(2, dtype=torch.float64, device=self.device)
+            for p in ps:
+                d = p.double()
+                s[0] += d.sum()
+                s[1] += (d * d).sum()
+        return s
+
+    def ranks_in_sync(self) -> bool:
+        """All-gather the parameter checksum; True iff every rank holds bit-identical sums."""
+        if self.buckets.world <= 1:
+            return True
+        mine = self.param_checksum()
+        allc = [torch.empty_like(mine) for _ in range(self.buckets.world)]
+        dist.all_gather(allc, mine, group=self.group)
+        return all(torch.equal(c, allc[0]) for c in allc)
 
     def stage(self, rgb_h, depth_h, labels_h):
         return (rgb_h.to(self.device, non_blocking=True), depth_h.to(self.device, non_blocking=True),

@@ -64,6 +64,31 @@ def _worker(rank, world, port, out):
     gb.finish()
     assert torch.allclose(params[0].grad, torch.full_like(params[0], 2.0))
     assert float(params[3].grad.abs().sum()) == 0.0
+    # replicas that were seeded differently are brought to rank 0's state by the train step's constructor
+    import contextlib, io
+    torch.manual_seed(100 + rank)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ehgr_b200.tsn_mtmm.TSN(5, 8, 'RGB', base_model='mobilenetv2', pretrain=None, dropout=0.5, partial_bn=False,
+                                   is_shift=True, fc_lr5=True, temporal_module='tsm', modal='rgb_depth')
+    for b in m.buffers():
+        if b.is_floating_point():
+            b.add_(float(rank))
+    w_before = m.new_fc.weight.detach().clone()
+    gathered = [torch.empty_like(w_before) for _ in range(world)]
+    dist.all_gather(gathered, w_before)
+    assert not torch.equal(gathered[0], gathered[1])              # the seeds really differed
+    step = ehgr_b200.train_step.MTMMTrainStep(m, compute_dtype=torch.float32)
+    assert step.ranks_in_sync()
+    assert torch.equal(m.new_fc.weight.detach(), gathered[0])
+    rm = m.base_model.features[0][1].running_mean
+    assert float(rm.abs().max()) == 0.0                            # rank 0's buffers (rank 1 had +1)
+    rm.add_(float(rank))                                           # per-rank running statistics drift apart ...
+    step.sync_bn_buffers()                                         # ... and are averaged before a checkpoint
+    assert torch.allclose(rm, torch.full_like(rm, (world - 1) / 2))
+    with torch.no_grad():
+        if rank == 1:
+            m.new_fc.weight.add_(1e-3)
+    assert not step.ranks_in_sync()                                # the checksum notices a diverged replica
     if rank == 0:
         out.put("ok")
     dist.destroy_process_group()
@@ -80,6 +105,23 @@ def test_grad_buckets_gloo_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == "ok"
+
+
+def test_bucket_assignment_with_one_dominant_parameter():
+    """a parameter larger than a bucket's share must not make the assignment skip a bucket index."""
+    import ehgr_b200
+    for sizes in ((100, 100, 3_000_000, 100), (3_000_000,), (8, 8, 8, 8, 8, 8, 8, 8, 8), (5, 1_000_000, 5, 1_000_000, 5)):
+        for nb in (1, 2, 3, 8):
+            params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+            gb = ehgr_b200.train_step.GradBuckets(params, n_buckets=nb)
+            assert 1 <= len(gb.bounds) <= nb
+            assert gb.bounds[0][0] == 0 and gb.bounds[-1][1] == gb.flat.numel()
+            assert all(a[1] == b[0] for a, b in zip(gb.bounds, gb.bounds[1:]))       # contiguous, no gaps
+            assert all(hi > lo for lo, hi in gb.bounds)
+            assert sum(gb._need) == len(params)
+            for p in params:
+                lo, hi = gb.bounds[gb._bucket_of[id(p)]]
+                assert lo <= gb._offset_of[id(p)] and gb._offset_of[id(p)] + p.numel() <= hi
 
 
 def test_sgd_groups_follow_reference_multipliers():
