@@ -10,10 +10,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / `
 legs may import this module, and only as the checker or the reported CPU baseline — the product
 package never imports it.
 
-Parity pinning: ``tests/test_oracle_vs_reference.py`` runs this file against the live reference
-modules (``/root/reference``, present in the build container only) and
-``tests/golden/make_golden.py`` stores reference outputs as fixtures that travel to the GPU box;
-``tests/test_oracle_golden.py`` checks the oracle against those fixtures everywhere.
+Parity pinning: ``tests/golden/make_golden.py`` runs the live reference modules (``/root/reference``,
+present in the build container only), asserts there that this file agrees with them, and stores the
+reference outputs as fixtures that travel to the GPU box; ``tests/test_oracle_golden.py`` checks the
+oracle against those fixtures everywhere.  Pinned that way: shift, Action, the whole TSN-MobileNetV2
+(none / TSM / ACTION x train / eval BN), both loss heads, the MTMM ``global_decoder``, ``SepConv``, the
+MTMM+SD decoders and combined loss, ``EMAWrapper`` and ``TemporalPool``.
 
 Each function cites the reference lines it restates (paths relative to /root/reference).
 """
@@ -369,17 +371,21 @@ def mtmm_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div
     return logits, global_decoder(taps[18], sd, bn_training)
 
 
+def decoder_state(sd: SD, rs, feat: int = 1280, prefix: str = "global_decoder") -> None:
+    """Entries of the MTMM depth decoder (models/models_MTMM.py:129-155) for `feat` input channels."""
+    chans = (feat, 256, 64, 32, 32)
+    for (ci, bi, _), i, o in zip(DECODER_UNITS, chans[:-1], chans[1:]):
+        sd[f"{prefix}.{ci}.weight"] = torch.from_numpy(
+            (rs.standard_normal((o, i, 3, 3)) * math.sqrt(2.0 / (9 * i))).astype(np.float32))
+        _bn_entries(sd, f"{prefix}.{bi}", o, rs)
+    sd[f"{prefix}.15.weight"] = torch.from_numpy((rs.standard_normal((1, 32, 1, 1)) * 0.2).astype(np.float32))
+    sd[f"{prefix}.15.bias"] = torch.from_numpy((rs.standard_normal(1) * 0.1).astype(np.float32))
+
+
 def build_mtmm_state(num_class: int = 83, temporal: str = "tsm", shift_div: int = 8, seed: int = 0,
                      feat: int = 1280) -> SD:
     sd = build_tsn_state(num_class, temporal, shift_div, seed)
-    rs = np.random.RandomState(seed + 77)
-    chans = (feat, 256, 64, 32, 32)
-    for (ci, bi, _), i, o in zip(DECODER_UNITS, chans[:-1], chans[1:]):
-        sd[f"global_decoder.{ci}.weight"] = torch.from_numpy(
-            (rs.standard_normal((o, i, 3, 3)) * math.sqrt(2.0 / (9 * i))).astype(np.float32))
-        _bn_entries(sd, f"global_decoder.{bi}", o, rs)
-    sd["global_decoder.15.weight"] = torch.from_numpy((rs.standard_normal((1, 32, 1, 1)) * 0.2).astype(np.float32))
-    sd["global_decoder.15.bias"] = torch.from_numpy((rs.standard_normal(1) * 0.1).astype(np.float32))
+    decoder_state(sd, np.random.RandomState(seed + 77), feat)
     return sd
 
 
@@ -434,21 +440,29 @@ def sd_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: 
     return (out, *mids, final_fea, *feas)
 
 
-def build_sd_state(num_class: int = 83, temporal: str = "tsm", shift_div: int = 8, seed: int = 0) -> SD:
-    sd = build_tsn_state(num_class, temporal, shift_div, seed)
-    rs = np.random.RandomState(seed + 991)
+def sepconv_state(sd: SD, prefix: str, ci: int, co: int, rs) -> None:
+    """Entries of one SepConv (models/models_SD.py:81-101): `prefix`.op.{0,1,2,4,5,6}."""
+    p = f"{prefix}.op"
+    _conv_entry(sd, f"{p}.0.weight", (ci, 1, 3, 3), rs, std=0.3)
+    _conv_entry(sd, f"{p}.1.weight", (ci, ci, 1, 1), rs, std=math.sqrt(2.0 / ci))
+    _bn_entries(sd, f"{p}.2", ci, rs)
+    _conv_entry(sd, f"{p}.4.weight", (ci, 1, 3, 3), rs, std=0.3)
+    _conv_entry(sd, f"{p}.5.weight", (co, ci, 1, 1), rs, std=math.sqrt(2.0 / ci))
+    _bn_entries(sd, f"{p}.6", co, rs)
+
+
+def sd_heads_state(sd: SD, rs, num_class: int) -> None:
     for name, chans in SD_HEADS:
         for j, (ci, co) in enumerate(zip(chans[:-1], chans[1:])):
-            p = f"{name}.{j}.op"
-            _conv_entry(sd, f"{p}.0.weight", (ci, 1, 3, 3), rs, std=0.3)
-            _conv_entry(sd, f"{p}.1.weight", (ci, ci, 1, 1), rs, std=math.sqrt(2.0 / ci))
-            _bn_entries(sd, f"{p}.2", ci, rs)
-            _conv_entry(sd, f"{p}.4.weight", (ci, 1, 3, 3), rs, std=0.3)
-            _conv_entry(sd, f"{p}.5.weight", (co, ci, 1, 1), rs, std=math.sqrt(2.0 / ci))
-            _bn_entries(sd, f"{p}.6", co, rs)
+            sepconv_state(sd, f"{name}.{j}", ci, co, rs)
     for fc in ("middle_fc1", "middle_fc2", "middle_fc3"):
         sd[fc + ".weight"] = torch.from_numpy((rs.standard_normal((num_class, 1280)) * 0.02).astype(np.float32))
         sd[fc + ".bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
+
+
+def build_sd_state(num_class: int = 83, temporal: str = "tsm", shift_div: int = 8, seed: int = 0) -> SD:
+    sd = build_tsn_state(num_class, temporal, shift_div, seed)
+    sd_heads_state(sd, np.random.RandomState(seed + 991), num_class)
     return sd
 
 
@@ -462,3 +476,120 @@ def sd_train_step(sd: SD, rgb, labels, num_segments=8, temporal="tsm", shift_div
     total, terms = sd_loss(outs[:4], outs[4:], labels, alpha, beta, temperature)
     total.backward()
     return total.detach(), terms
+
+
+# --------------------------------------------------------------------------------------------
+# MTMM+SD combined wrapper — models/models_MTMM_SD.py:226-249 (ConvTranspose decoders), :431-532
+# (forward), loss train_mtmm_sd.py:240-293.  ResNet-only in the reference; on MobileNetV2 the
+# `maxpool` tap (64 ch @56^2) becomes the features[3] output (24 ch @56^2, the first SD tap) and
+# `layer4` the features[18] output (1280 ch @7^2) — builder-defined like A10 / A13.
+# --------------------------------------------------------------------------------------------
+def convt_decoder(f, sd: SD, prefix: str, n_conv: int, bn_training: bool):
+    """nn.Sequential(ConvTranspose2d(k4,s2,p1), BatchNorm2d, ..., ConvTranspose2d, Sigmoid): `n_conv`
+    transposed convolutions (with bias), a BatchNorm after each but the last, NO activation in between
+    (models/models_MTMM_SD.py:227-249)."""
+    y = f
+    for j in range(n_conv):
+        y = F.conv_transpose2d(y, sd[f"{prefix}.{2 * j}.weight"], sd[f"{prefix}.{2 * j}.bias"], stride=2, padding=1)
+        if j + 1 < n_conv:
+            y = _bn(y, sd, f"{prefix}.{2 * j + 1}", bn_training)
+    return torch.sigmoid(y)
+
+
+def convt_decoder_state(sd: SD, prefix: str, chans, rs) -> None:
+    n = len(chans) - 1
+    for j, (ci, co) in enumerate(zip(chans[:-1], chans[1:])):
+        sd[f"{prefix}.{2 * j}.weight"] = torch.from_numpy(
+            (rs.standard_normal((ci, co, 4, 4)) * math.sqrt(1.0 / (4 * ci))).astype(np.float32))
+        sd[f"{prefix}.{2 * j}.bias"] = torch.from_numpy((rs.standard_normal(co) * 0.1).astype(np.float32))
+        if j + 1 < n:
+            _bn_entries(sd, f"{prefix}.{2 * j + 1}", co, rs)
+
+
+MTMM_SD_LOCAL = (24, 32, 1)            # local_decoder channels on MobileNetV2 (reference: 64, 32, 1)
+MTMM_SD_GLOBAL = (1280, 256, 32, 1)    # global_decoder channels (reference: 2048, 256, 32, 1)
+
+
+def build_mtmm_sd_state(num_class: int = 83, temporal: str = "tsm", shift_div: int = 8, seed: int = 0) -> SD:
+    sd = build_sd_state(num_class, temporal, shift_div, seed)
+    rs = np.random.RandomState(seed + 313)
+    convt_decoder_state(sd, "local_decoder", MTMM_SD_LOCAL, rs)
+    convt_decoder_state(sd, "global_decoder", MTMM_SD_GLOBAL, rs)
+    return sd
+
+
+def mtmm_sd_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8, bn_training: bool = True):
+    """-> the ten tensors of modal='rgb_depth' (models/models_MTMM_SD.py:522-523): output, mid1-3, final_fea,
+    fea1-3, local_depth_out [NT,1,224,224], global_depth_out [NT,1,56,56]."""
+    taps = {i: None for i in SD_TAPS + (18,)}
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    mobilenet_v2_features(x, sd, temporal, num_segments, shift_div, bn_training, taps=taps)
+    mids, feas = [], []
+    for (name, chans), tap, fc in zip(SD_HEADS, SD_TAPS, ("middle_fc1", "middle_fc2", "middle_fc3")):
+        y = taps[tap]
+        for j in range(len(chans) - 1):
+            y = sepconv(y, sd, f"{name}.{j}", bn_training)
+        fea = F.adaptive_avg_pool2d(y, 1)
+        z = F.linear(torch.flatten(fea, 1), sd[fc + ".weight"], sd[fc + ".bias"])
+        mids.append(z.view((-1, num_segments) + tuple(z.shape[1:])).mean(1))
+        feas.append(fea)
+    final_fea = F.adaptive_avg_pool2d(taps[18], 1)
+    z = F.linear(torch.flatten(final_fea, 1), sd["new_fc.weight"], sd["new_fc.bias"])
+    out = z.view((-1, num_segments) + tuple(z.shape[1:])).mean(1)
+    local_depth = convt_decoder(taps[SD_TAPS[0]], sd, "local_decoder", len(MTMM_SD_LOCAL) - 1, bn_training)
+    global_depth = convt_decoder(taps[18], sd, "global_decoder", len(MTMM_SD_GLOBAL) - 1, bn_training)
+    return (out, *mids, final_fea, *feas, local_depth, global_depth)
+
+
+def mtmm_sd_loss(outputs, feats, global_depth_out, depth_gt5, labels, alpha=0.1, beta=1e-6, temperature=3.0):
+    """train_mtmm_sd.py:240-293: `loss` = CE(output) + 0.01 * MSE(g_depth_out, bilinear56(depth)); the SD
+    terms as train_sd.py; total = (1-a)(loss + 3 CE) + a * 3 KD + b * 3 feature.  Returns (total, loss)."""
+    out, m1, m2, m3 = outputs
+    f4, f1, f2, f3 = feats
+    gt = depth_gt5.view(-1, 1, depth_gt5.size(-2), depth_gt5.size(-1))
+    gt = F.interpolate(gt, size=(56, 56), mode="bilinear")
+    loss = F.cross_entropy(out, labels) + 0.01 * F.mse_loss(global_depth_out, gt)
+    ce = [F.cross_entropy(o, labels) for o in (m1, m2, m3)]
+    temp4 = torch.softmax(out / temperature, dim=1).detach()
+    kd = [kd_loss(m, temp4, temperature) * temperature ** 2 for m in (m1, m2, m3)]
+    fl = [feature_loss(f, f4.detach()) for f in (f1, f2, f3)]
+    total = (1 - alpha) * (loss + sum(ce)) + alpha * sum(kd) + beta * sum(fl)
+    return total, loss
+
+
+def mtmm_sd_train_step(sd: SD, rgb, depth, labels, num_segments=8, temporal="tsm", shift_div=8, bn_training=True,
+                       alpha=0.1, beta=1e-6, temperature=3.0):
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    outs = mtmm_sd_forward(rgb, sd, num_segments, temporal, shift_div, bn_training)
+    total, loss = mtmm_sd_loss(outs[:4], outs[4:8], outs[9], depth, labels, alpha, beta, temperature)
+    total.backward()           # the reference script calls loss.backward() (train_mtmm_sd.py:310, a bug noted in
+    return total.detach(), loss.detach(), outs   # SURVEY section 4); the quantity it logs and means to train is total_loss
+
+
+# --------------------------------------------------------------------------------------------
+# EMA of the model state — train_mtmm.py:110-128 (EMAWrapper._update / update), called every step (:245)
+# --------------------------------------------------------------------------------------------
+def ema_update(ema_sd: SD, model_sd: SD, decay: float = 0.9999) -> None:
+    """In place over EVERY state_dict entry, buffers and integer counters included: the reference computes
+    ``decay * e + (1 - decay) * m`` with python-float scalars (so in the tensor's dtype for floating entries and in
+    the default float32 for the int64 ``num_batches_tracked``) and ``copy_``s the result back (truncation)."""
+    with torch.no_grad():
+        for k, e in ema_sd.items():
+            m = model_sd[k]
+            e.copy_(decay * e + (1. - decay) * m)
+
+
+# --------------------------------------------------------------------------------------------
+# TemporalPool — models/temporal_shift.py:89-98: max over frames {2t-1, 2t, 2t+1} (clipped), stride 2
+# --------------------------------------------------------------------------------------------
+def temporal_pool_np(x: np.ndarray, n_segment: int) -> np.ndarray:
+    nt, c, h, w = x.shape
+    v = x.reshape(nt // n_segment, n_segment, c, h, w)
+    t_out = (n_segment + 2 - 3) // 2 + 1
+    out = np.empty((v.shape[0], t_out, c, h, w), x.dtype)
+    for t in range(t_out):
+        lo, hi = max(2 * t - 1, 0), min(2 * t + 1, n_segment - 1)
+        out[:, t] = v[:, lo:hi + 1].max(axis=1)
+    return out.reshape(-1, c, h, w)

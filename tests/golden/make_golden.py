@@ -33,11 +33,12 @@ def _quiet():
 
 
 def ref_functions(path: Path, names):
-    """Extract top-level function definitions from a reference script WITHOUT importing it (the train
+    """Extract top-level function / class definitions from a reference script WITHOUT importing it (the train
     scripts parse argv at import time) and compile them in a scratch namespace."""
+    from copy import deepcopy
     tree = ast.parse(path.read_text())
-    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
-    ns = {"torch": torch, "F": F}
+    keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    ns = {"torch": torch, "F": F, "deepcopy": deepcopy}
     exec(compile(ast.Module(body=keep, type_ignores=[]), str(path), "exec"), ns)
     return [ns[n] for n in names]
 
@@ -202,12 +203,214 @@ def golden_losses():
     np.savez_compressed(HERE / "losses.npz", **out)
 
 
+def _fwd_bwd(mod, x, rs):
+    x = x.clone().requires_grad_(True)
+    y = mod(x)
+    g = torch.from_numpy(rs.standard_normal(tuple(y.shape)).astype(np.float32))
+    y.backward(g)
+    return x, y, g
+
+
+def golden_heads():
+    """Pieces either side of the backbone that round 1 left unpinned: SepConv (models/models_SD.py:81-101), the MTMM
+    depth decoder (models/models_MTMM.py:129-155, taken from a live models_MTMM.TSN), the MTMM+SD ConvTranspose
+    decoders (models/models_MTMM_SD.py:226-249) and the combined loss (train_mtmm_sd.py:240-293).  Every case also
+    ASSERTS here that the oracle restatement agrees with the live reference."""
+    from models.models_SD import SepConv
+    out = {}
+
+    def check(a, b, tol=2e-5, what=""):
+        err = (a.detach().double() - b.detach().double()).abs().max().item() / max(b.detach().abs().max().item(), 1e-30)
+        assert err < tol, (what, err)
+
+    # ---- SepConv --------------------------------------------------------------------------
+    for name, (ci, co, h, n, train_bn) in {"sep_a": (24, 32, 9, 4, True), "sep_b": (96, 160, 6, 2, True),
+                                           "sep_c": (32, 96, 7, 2, False)}.items():
+        rs = np.random.RandomState(501 + ci)
+        sd = {}
+        O.sepconv_state(sd, "m", ci, co, rs)
+        mod = SepConv(ci, co)
+        mod.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        mod.train(train_bn)
+        x0 = torch.from_numpy(rs.standard_normal((n, ci, h, h)).astype(np.float32))
+        x, y, g = _fwd_bwd(mod, x0, rs)
+        osd = O.clone_state(sd)
+        xo = x0.clone().requires_grad_(True)
+        yo = O.sepconv(xo, osd, "m", train_bn)
+        yo.backward(g)
+        check(yo, y, what=name)
+        check(xo.grad, x.grad, what=name + " gx")
+        out[name + "_meta"] = np.array([ci, co, h, n, int(train_bn)])
+        out[name + "_x"], out[name + "_g"], out[name + "_y"], out[name + "_gx"] = (x0.numpy(), g.numpy(), y.detach().numpy(),
+                                                                               x.grad.numpy())
+        for k, p_ in mod.named_parameters():
+            check(osd["m." + k].grad, p_.grad, what=name + k)
+            out[f"{name}_grad_{k}"] = p_.grad.numpy()
+        for k, b in mod.named_buffers():
+            if "running" in k:
+                out[f"{name}_buf_{k}"] = b.numpy().copy()
+
+    # ---- MTMM global_decoder: the module of a live models_MTMM.TSN (ResNet-50: 2048 input channels) --------
+    from models.models_MTMM import TSN as TSN_MTMM
+    with _quiet():
+        ref = TSN_MTMM(83, 8, 'RGB', base_model='resnet50', pretrain=None, dropout=0.5, partial_bn=False, is_shift=True,
+                       shift_div=8, consensus_type='avg', fc_lr5=True, img_feature_dim=224, modal='rgb_depth')
+    dec = ref.global_decoder
+    for name, (h, n, train_bn) in {"dec_a": (3, 2, True), "dec_b": (2, 3, False)}.items():
+        rs = np.random.RandomState(601 + h)
+        sd = {}
+        O.decoder_state(sd, rs, feat=2048, prefix="d")
+        dec.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        dec.train(train_bn)
+        dec.zero_grad()
+        x0 = torch.from_numpy(rs.standard_normal((n, 2048, h, h)).astype(np.float32))
+        x, y, g = _fwd_bwd(dec, x0, rs)
+        osd = O.clone_state(sd)
+        xo = x0.clone().requires_grad_(True)
+        yo = O.global_decoder(xo, osd, train_bn, prefix="d")
+        yo.backward(g)
+        check(yo, y, what=name)
+        check(xo.grad, x.grad, what=name + " gx")
+        out[name + "_meta"] = np.array([h, n, int(train_bn)])
+        out[name + "_x"], out[name + "_g"], out[name + "_y"], out[name + "_gx"] = (x0.numpy().astype(np.float16), g.numpy(),
+                                                                               None, None)
+        # x is stored through fp16 (fixture size): recompute the reference on the rounded input
+        x0 = torch.from_numpy(out[name + "_x"].astype(np.float32))
+        dec.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        dec.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        y = dec(x)
+        y.backward(g)
+        out[name + "_y"], out[name + "_gx"] = y.detach().numpy(), x.grad.numpy()
+        for k, p_ in dec.named_parameters():
+            gk = p_.grad.detach().double().flatten()
+            idx = torch.linspace(0, gk.numel() - 1, steps=min(64, gk.numel())).long()
+            out[f"{name}_gdig_{k}"] = np.concatenate([[gk.sum().item(), gk.abs().sum().item()], gk[idx].numpy()])
+        out[name + "_rv13"] = dec[13].running_var.numpy().copy()
+    del ref
+
+    # ---- MTMM+SD ConvTranspose decoders from a live models_MTMM_SD.TSN ------------------------------------
+    from models.models_MTMM_SD import TSN as TSN_MS
+    with _quiet():
+        ref = TSN_MS(83, 8, 'RGB', base_model='resnet50', pretrain=None, dropout=0.5, partial_bn=False, is_shift=True,
+                     shift_div=8, consensus_type='avg', fc_lr5=True, img_feature_dim=224, modal='rgb_depth')
+    for name, (mod, chans, h, n, train_bn) in {"ctl": (ref.local_decoder, (64, 32, 1), 5, 2, True),
+                                               "ctg": (ref.global_decoder, (2048, 256, 32, 1), 2, 2, True),
+                                               "cte": (ref.local_decoder, (64, 32, 1), 4, 3, False)}.items():
+        rs = np.random.RandomState(701 + h)
+        sd = {}
+        O.convt_decoder_state(sd, "d", chans, rs)
+        mod.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        mod.train(train_bn)
+        mod.zero_grad()
+        x0 = torch.from_numpy(rs.standard_normal((n, chans[0], h, h)).astype(np.float16).astype(np.float32))
+        x, y, g = _fwd_bwd(mod, x0, rs)
+        osd = O.clone_state(sd)
+        xo = x0.clone().requires_grad_(True)
+        yo = O.convt_decoder(xo, osd, "d", len(chans) - 1, train_bn)
+        yo.backward(g)
+        check(yo, y, what=name)
+        check(xo.grad, x.grad, what=name + " gx")
+        out[name + "_meta"] = np.array(list(chans) + [h, n, int(train_bn)])
+        out[name + "_x"], out[name + "_g"], out[name + "_y"], out[name + "_gx"] = (x0.numpy().astype(np.float16), g.numpy(),
+                                                                               y.detach().numpy(), x.grad.numpy())
+        for k, p_ in mod.named_parameters():
+            check(osd["d." + k].grad, p_.grad, what=name + k)
+            gk = p_.grad.detach().double().flatten()
+            idx = torch.linspace(0, gk.numel() - 1, steps=min(64, gk.numel())).long()
+            out[f"{name}_gdig_{k}"] = np.concatenate([[gk.sum().item(), gk.abs().sum().item()], gk[idx].numpy()])
+    del ref
+
+    # ---- combined MTMM+SD loss, train_mtmm_sd.py:240-293 statement for statement ---------------------------
+    kd_fn, feat_fn = ref_functions(REF / "train_mtmm_sd.py", ["kd_loss_function", "feature_loss_function"])
+
+    class A:
+        temperature, alpha, beta = 3, 0.1, 1e-6
+
+    rs = np.random.RandomState(33)
+    N, T, cls, fd = 3, 2, 83, 1280
+    lg = [torch.from_numpy(rs.standard_normal((N, cls)).astype(np.float32) * 2).requires_grad_(True) for _ in range(4)]
+    ft = [torch.from_numpy(rs.standard_normal((N * T, fd, 1, 1)).astype(np.float32)).requires_grad_(True) for _ in range(4)]
+    labels = torch.from_numpy(rs.randint(0, cls, (N,)).astype(np.int64))
+    g_depth_out = torch.from_numpy(rs.uniform(0, 1, (N * T, 1, 56, 56)).astype(np.float32)).requires_grad_(True)
+    depth = torch.from_numpy(rs.uniform(0, 1, (N, T, 1, 224, 224)).astype(np.float16).astype(np.float32))
+    criterion, mse_loss = torch.nn.CrossEntropyLoss(), torch.nn.MSELoss()
+    output, middle_output1, middle_output2, middle_output3 = lg
+    final_fea, middle1_fea, middle2_fea, middle3_fea = ft
+    l_depth_gt = depth.view(-1, 1, depth.size(-2), depth.size(-1))
+    g_depth_gt = F.interpolate(l_depth_gt, size=(56, 56), mode='bilinear')
+    g_depth_loss = mse_loss(g_depth_out, g_depth_gt)
+    loss = criterion(output, labels) + 0.01 * g_depth_loss
+    middle1_loss = criterion(middle_output1, labels)
+    middle2_loss = criterion(middle_output2, labels)
+    middle3_loss = criterion(middle_output3, labels)
+    temp4 = torch.softmax(output / A.temperature, dim=1)
+    loss1by4 = kd_fn(middle_output1, temp4.detach(), A) * (A.temperature ** 2)
+    loss2by4 = kd_fn(middle_output2, temp4.detach(), A) * (A.temperature ** 2)
+    loss3by4 = kd_fn(middle_output3, temp4.detach(), A) * (A.temperature ** 2)
+    feature_loss_1 = feat_fn(middle1_fea, final_fea.detach())
+    feature_loss_2 = feat_fn(middle2_fea, final_fea.detach())
+    feature_loss_3 = feat_fn(middle3_fea, final_fea.detach())
+    total_loss = (1 - A.alpha) * (loss + middle1_loss + middle2_loss + middle3_loss) + \
+        A.alpha * (loss1by4 + loss2by4 + loss3by4) + A.beta * (feature_loss_1 + feature_loss_2 + feature_loss_3)
+    total_loss.backward()
+    ot, ol = O.mtmm_sd_loss([t.detach() for t in lg], [t.detach() for t in ft], g_depth_out.detach(), depth, labels)
+    assert abs(ot.item() - total_loss.item()) < 1e-5 and abs(ol.item() - loss.item()) < 1e-6
+    out.update({"ms_labels": labels.numpy(), "ms_total": np.array(total_loss.item()), "ms_loss": np.array(loss.item()),
+                "ms_depth": depth.numpy().astype(np.float16), "ms_gpred_in": g_depth_out.detach().numpy(),
+                "ms_gpred": g_depth_out.grad.numpy()})
+    for i in range(4):
+        out[f"ms_logits{i}"], out[f"ms_feat{i}"] = lg[i].detach().numpy(), ft[i].detach().numpy()
+        out[f"ms_glogits{i}"] = lg[i].grad.numpy()
+        out[f"ms_gfeat{i}"] = ft[i].grad.numpy() if ft[i].grad is not None else np.zeros_like(ft[i].detach().numpy())
+
+    np.savez_compressed(HERE / "heads.npz", **out)
+
+
+def golden_ema_and_pool():
+    """Separate small file: EMAWrapper replay (initial state stored explicitly) and TemporalPool."""
+    from models.temporal_shift import TemporalPool
+    (EMAWrapper,) = ref_functions(REF / "train_mtmm.py", ["EMAWrapper"])
+    out = {}
+    rs = np.random.RandomState(44)
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, bias=False), torch.nn.BatchNorm2d(4), torch.nn.Linear(4, 2))
+    for k, v in net.state_dict().items():
+        out["ema_init_" + k] = v.clone().numpy()
+    ema = EMAWrapper(net, decay=0.9)
+    oema = {k: v.clone() for k, v in net.state_dict().items()}
+    for step in range(3):
+        with torch.no_grad():
+            for k, v in net.state_dict().items():
+                if v.is_floating_point():
+                    v.add_(torch.from_numpy(rs.standard_normal(tuple(v.shape)).astype(np.float32)))
+                else:
+                    v.add_(7 * (step + 1))
+        for k, v in net.state_dict().items():
+            out[f"ema_model{step}_{k}"] = v.clone().numpy()
+        ema.update(net)
+        O.ema_update(oema, net.state_dict(), 0.9)
+    for k, v in ema.state_dict().items():
+        assert torch.equal(v, oema[k]), k
+        out["ema_final_" + k] = v.numpy()
+    for name, (nt, c, h, T) in {"tp_a": (8, 5, 3, 8), "tp_b": (12, 4, 2, 4), "tp_c": (6, 3, 2, 6)}.items():
+        x = torch.from_numpy(rs.standard_normal((nt, c, h, h)).astype(np.float32))
+        y = TemporalPool.temporal_pool(x, T)
+        assert np.array_equal(O.temporal_pool_np(x.numpy(), T), y.numpy())
+        xg = x.clone().requires_grad_(True)
+        TemporalPool.temporal_pool(xg, T).backward(torch.ones_like(y) * 0.5 + y.detach())
+        out[name + "_meta"] = np.array([nt, c, h, T])
+        out[name + "_x"], out[name + "_y"], out[name + "_gx"] = x.numpy(), y.numpy(), xg.grad.numpy()
+    np.savez_compressed(HERE / "ema_pool.npz", **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    golden_shift()
-    golden_action()
-    golden_losses()
-    golden_tsn()
+    only = set(sys.argv[1:])
+    for name, fn in (("shift", golden_shift), ("action", golden_action), ("losses", golden_losses), ("tsn", golden_tsn),
+                     ("heads", golden_heads), ("ema_pool", golden_ema_and_pool)):
+        if not only or name in only:
+            fn()
     for p in sorted(HERE.glob("*.npz")):
         print(p.name, p.stat().st_size)

@@ -127,3 +127,111 @@ def test_loss_oracles_match_reference():
     loss.backward()
     assert rel_err(lg.grad, torch.from_numpy(z["mt_glogits"])) < 1e-6
     assert rel_err(pred.grad, torch.from_numpy(z["mt_gpred"])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the pieces either side of the backbone (tests/golden/heads.npz, ema_pool.npz)
+# ------------------------------------------------------------------------------------------------
+def _digest64(g):
+    g = g.detach().double().flatten()
+    idx = torch.linspace(0, g.numel() - 1, steps=min(64, g.numel())).long()
+    return np.concatenate([[g.sum().item(), g.abs().sum().item()], g[idx].numpy()])
+
+
+@pytest.mark.parametrize("name", ["sep_a", "sep_b", "sep_c"])
+def test_sepconv_oracle_matches_reference(name):
+    """models/models_SD.py:81-101, fixture from the live reference SepConv."""
+    z = np.load(GOLDEN / "heads.npz")
+    ci, co, h, n, train_bn = (int(v) for v in z[name + "_meta"])
+    sd = {}
+    O.sepconv_state(sd, "m", ci, co, np.random.RandomState(501 + ci))
+    sd = O.clone_state(sd)
+    x = torch.from_numpy(z[name + "_x"]).requires_grad_(True)
+    y = O.sepconv(x, sd, "m", bool(train_bn))
+    assert rel_err(y, torch.from_numpy(z[name + "_y"])) < 2e-6
+    y.backward(torch.from_numpy(z[name + "_g"]))
+    assert rel_err(x.grad, torch.from_numpy(z[name + "_gx"])) < 1e-5
+    for k in z.files:
+        if k.startswith(name + "_grad_"):
+            assert rel_err(sd["m." + k[len(name + "_grad_"):]].grad, torch.from_numpy(z[k])) < 2e-5, k
+        if k.startswith(name + "_buf_") and train_bn:
+            assert rel_err(sd["m." + k[len(name + "_buf_"):]], torch.from_numpy(z[k])) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["dec_a", "dec_b"])
+def test_global_decoder_oracle_matches_reference(name):
+    """models/models_MTMM.py:129-155, fixture from the global_decoder of a live models_MTMM.TSN (ResNet-50)."""
+    z = np.load(GOLDEN / "heads.npz")
+    h, n, train_bn = (int(v) for v in z[name + "_meta"])
+    sd = {}
+    O.decoder_state(sd, np.random.RandomState(601 + h), feat=2048, prefix="d")
+    sd = O.clone_state(sd)
+    x = torch.from_numpy(z[name + "_x"].astype(np.float32)).requires_grad_(True)
+    y = O.global_decoder(x, sd, bool(train_bn), prefix="d")
+    assert tuple(y.shape) == (n, 1, 8 * h, 8 * h)
+    assert rel_err(y, torch.from_numpy(z[name + "_y"])) < 2e-6
+    y.backward(torch.from_numpy(z[name + "_g"]))
+    assert rel_err(x.grad, torch.from_numpy(z[name + "_gx"])) < 2e-5
+    for k in z.files:
+        if k.startswith(name + "_gdig_"):
+            got, ref = _digest64(sd["d." + k[len(name + "_gdig_"):]].grad), z[k]
+            assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref[2:]).max(), 1e-6) + 1e-4 * abs(ref[1]) * 1e-3, k
+    if train_bn:
+        assert rel_err(sd["d.13.running_var"], torch.from_numpy(z[name + "_rv13"])) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["ctl", "ctg", "cte"])
+def test_convt_decoder_oracle_matches_reference(name):
+    """models/models_MTMM_SD.py:226-249: local / global ConvTranspose decoders of a live models_MTMM_SD.TSN."""
+    z = np.load(GOLDEN / "heads.npz")
+    meta = [int(v) for v in z[name + "_meta"]]
+    chans, (h, n, train_bn) = meta[:-3], meta[-3:]
+    sd = {}
+    O.convt_decoder_state(sd, "d", chans, np.random.RandomState(701 + h))
+    sd = O.clone_state(sd)
+    x = torch.from_numpy(z[name + "_x"].astype(np.float32)).requires_grad_(True)
+    y = O.convt_decoder(x, sd, "d", len(chans) - 1, bool(train_bn))
+    assert rel_err(y, torch.from_numpy(z[name + "_y"])) < 2e-6
+    y.backward(torch.from_numpy(z[name + "_g"]))
+    assert rel_err(x.grad, torch.from_numpy(z[name + "_gx"])) < 2e-5
+    for k in z.files:
+        if k.startswith(name + "_gdig_"):
+            got, ref = _digest64(sd["d." + k[len(name + "_gdig_"):]].grad), z[k]
+            assert np.abs(got[2:] - ref[2:]).max() <= 3e-5 * max(np.abs(ref[2:]).max(), 1e-6), k
+
+
+def test_mtmm_sd_loss_oracle_matches_reference():
+    """train_mtmm_sd.py:240-293 (fixture = the reference statements with its own kd / feature functions)."""
+    z = np.load(GOLDEN / "heads.npz")
+    lg = [torch.from_numpy(z[f"ms_logits{i}"]).requires_grad_(True) for i in range(4)]
+    ft = [torch.from_numpy(z[f"ms_feat{i}"]).requires_grad_(True) for i in range(4)]
+    pred = torch.from_numpy(z["ms_gpred_in"]).requires_grad_(True)
+    depth = torch.from_numpy(z["ms_depth"].astype(np.float32))
+    total, loss = O.mtmm_sd_loss(lg, ft, pred, depth, torch.from_numpy(z["ms_labels"]))
+    assert abs(total.item() - float(z["ms_total"])) < 1e-5 and abs(loss.item() - float(z["ms_loss"])) < 1e-6
+    total.backward()
+    for i in range(4):
+        assert rel_err(lg[i].grad, torch.from_numpy(z[f"ms_glogits{i}"])) < 1e-5
+        if i:
+            assert rel_err(ft[i].grad, torch.from_numpy(z[f"ms_gfeat{i}"])) < 1e-5
+    assert ft[0].grad is None or float(ft[0].grad.abs().max()) == 0.0
+    assert rel_err(pred.grad, torch.from_numpy(z["ms_gpred"])) < 1e-5
+
+
+def test_ema_oracle_matches_reference_bit_exact():
+    """train_mtmm.py:110-128: three updates of the reference EMAWrapper (decay 0.9), replayed on the oracle."""
+    z = np.load(GOLDEN / "ema_pool.npz")
+    keys = [k[len("ema_init_"):] for k in z.files if k.startswith("ema_init_")]
+    ema = {k: torch.from_numpy(z["ema_init_" + k].copy()) for k in keys}
+    for step in range(3):
+        O.ema_update(ema, {k: torch.from_numpy(z[f"ema_model{step}_{k}"]) for k in keys}, 0.9)
+    for k in keys:
+        assert torch.equal(ema[k], torch.from_numpy(z["ema_final_" + k])), k
+    assert ema["1.num_batches_tracked"].dtype == torch.int64
+
+
+@pytest.mark.parametrize("name", ["tp_a", "tp_b", "tp_c"])
+def test_temporal_pool_oracle_matches_reference_bit_exact(name):
+    z = np.load(GOLDEN / "ema_pool.npz")
+    nt, c, h, T = (int(v) for v in z[name + "_meta"])
+    assert np.array_equal(O.temporal_pool_np(z[name + "_x"], T), z[name + "_y"])
