@@ -1,0 +1,247 @@
+"""Parity at the configuration bench.py measures (BASELINE.json configs[1]): 32 clips x 8 frames x 224x224, bf16
+storage, train-mode BatchNorm, TSM and ACTION.
+
+The arbiter is the oracle (oracle/ref_oracle.py, pinned to the live reference in fp64) run ON THE GPU IN FP32:
+  * per block: every unit output of our chain (19 taps) is compared with the oracle block fed the SAME
+    bf16-rounded unit input, so rounding does not compound through the 19 stages — bound 2e-2 per block
+    (north_star's bf16 tolerance; the error norm is max|a-b| / max|b| as everywhere in this suite);
+  * end to end: logits, loss and the gradient of every parameter group against the fp32 oracle started
+    from the same fp32 input, with the bounds stated below (the whole-network error compounds through the 19
+    stages; the bounds were fixed after measuring both the fused chain and PyTorch's own bf16 autocast run
+    of the oracle on this case).
+The multi-tile / multi-wave paths of the persistent kernels (148 CTAs x hundreds of tiles, TMEM buffer
+wrap-around, ring phase flips over thousands of stages) are what this size exercises.
+"""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from oracle import ref_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CLIPS = 32
+BF16_BLOCK_TOL = 2e-2
+
+
+def _quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def _err(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _rms_err(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30)).item()
+
+
+def _model(temporal, sd0):
+    import ehgr_b200 as E
+    with _quiet():
+        model = E.tsn_mtmm.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                               dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                               modal='rgb_depth', temporal_module=temporal)
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    for d in model.modules():
+        if isinstance(d, torch.nn.Dropout):
+            d.eval()
+    return model
+
+
+def _cuda_state(sd0, grad=False):
+    out = {}
+    for k, v in sd0.items():
+        t = v.detach().clone().cuda()
+        if grad and t.is_floating_point() and not ("running_" in k):
+            t.requires_grad_(True)
+        out[k] = t
+    return out
+
+
+@pytest.mark.parametrize("temporal", ["tsm", "action"])
+def test_every_block_at_bench_size_bf16(temporal):
+    import ehgr_b200 as E
+    sd0 = O.build_mtmm_state(83, temporal, 8, seed=21)
+    model = _model(temporal, sd0)
+    rgb, _, _ = O.synthetic_clip_batch(CLIPS, 8, 224, 83, seed=5)
+    x = rgb.view(-1, 3, 224, 224).cuda()
+    with torch.no_grad(), E.fused.compute_dtype(torch.bfloat16):
+        outs = E.fused.mobilenet_v2_features(model.base_model, x, taps=list(range(19)))
+    assert len(outs) == 19                                      # features[0..18]; the last tap is the final map
+    taps = outs
+    assert all(t.dtype == torch.bfloat16 for t in taps)
+    sd = _cuda_state(sd0)
+    worst = {}
+    with torch.no_grad():
+        # features[0]: stem from the fp32 input
+        f = "base_model.features"
+        y = torch.nn.functional.conv2d(x, sd[f"{f}.0.0.weight"], stride=2, padding=1)
+        y = torch.nn.functional.relu6(O._bn(y, sd, f"{f}.0.1", True))
+        worst[0] = _err(taps[0], y)
+        for idx, inp, oup, stride, t in O.mbv2_block_table():
+            xin = taps[idx - 1].float().contiguous()            # the SAME bf16-rounded input our block consumed
+            y = O.inverted_residual(xin, sd, f"{f}.{idx}", inp, oup, stride, t, temporal, 8, 8, True)
+            worst[idx] = _err(taps[idx], y)
+        xin = taps[17].float().contiguous()
+        y = torch.nn.functional.conv2d(xin, sd[f"{f}.18.0.weight"])
+        y = torch.nn.functional.relu6(O._bn(y, sd, f"{f}.18.1", True))
+        worst[18] = _err(taps[18], y)
+    print("per-block max-norm relative error (bf16 storage, B=%d): %s" % (CLIPS, {k: round(v, 5) for k, v in worst.items()}))
+    bad = {k: v for k, v in worst.items() if not v < BF16_BLOCK_TOL}
+    assert not bad, bad
+
+
+# end-to-end bounds at this size: max-norm relative for the logits, relative for the loss and for the norm of the
+# whole gradient, and ||g - g_ref|| / ||g_ref|| over the concatenation of all parameter gradients.  Individual
+# BatchNorm scale/shift gradients are sums with heavy cancellation (the loss is nearly invariant to them under the
+# next train-mode BatchNorm); with bf16 activations they carry O(1) relative noise in ANY implementation (PyTorch's
+# autocast run of the oracle is printed beside ours), so they are bounded through the whole-vector norm, not one by one.
+E2E_LOGITS, E2E_LOSS, E2E_GRAD_NORM = 6e-2, 5e-3, 6e-2
+
+
+@pytest.mark.parametrize("temporal", ["tsm", "action"])
+def test_step_at_bench_size_bf16_against_fp32_oracle(temporal):
+    import ehgr_b200 as E
+    sd0 = O.build_mtmm_state(83, temporal, 8, seed=22)
+    model = _model(temporal, sd0)
+    rgb, depth, labels = O.synthetic_clip_batch(CLIPS, 8, 224, 83, seed=6)
+    rgb, depth, labels = rgb.cuda(), depth.cuda(), labels.cuda()
+    with E.fused.compute_dtype(torch.bfloat16):
+        logits, dpred = model(rgb)
+        loss, _ = E.losses.mtmm_loss(logits, labels, dpred, depth)
+    loss.backward()
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = _cuda_state(sd0, grad=True)
+        oloss, ologits, odpred = O.mtmm_train_step(sd, rgb, depth, labels, 8, temporal, 8, True)
+        # yardstick, printed only: the same oracle under PyTorch's bf16 autocast
+        sdy = _cuda_state(sd0, grad=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yloss, ylogits, _ = O.mtmm_train_step(sdy, rgb, depth, labels, 8, temporal, 8, True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    e_logits, e_loss = _err(logits, ologits), abs(loss.item() - oloss.item()) / abs(oloss.item())
+    y_logits, y_loss = _err(ylogits, ologits), abs(float(yloss) - oloss.item()) / abs(oloss.item())
+    # per-parameter RMS error relative to that parameter's gradient RMS — floored at 1e-3 of the largest RMS of any
+    # parameter, because some gradients are mathematically zero (a BatchNorm shift feeding only a train-mode
+    # BatchNorm) and hold nothing but rounding noise in every implementation
+    rms = {k: float(v.grad.float().pow(2).mean().sqrt()) for k, v in sd.items() if v.is_floating_point() and v.grad is not None}
+    floor = 1e-3 * max(rms.values())
+    # The shift (beta) of every block's LAST BatchNorm has an exactly-zero gradient in train mode: a per-channel
+    # constant added to a block output passes the identity shortcuts unchanged and is removed by the batch-mean
+    # subtraction of the next expand convolution's BatchNorm.  What any implementation holds there is rounding
+    # noise; it is bounded against the gradient of the same layer's scale (gamma) instead of against itself.
+    zero_grad = {f"base_model.features.{idx}.conv.{4 if t == 1 else 7}.bias" for idx, _i, _o, _s, t in O.mbv2_block_table()}
+    for k in zero_grad:
+        noise = float(dict(model.named_parameters())[k].grad.float().pow(2).mean().sqrt())
+        assert noise <= 1.0 * rms[k.replace(".bias", ".weight")], (k, noise, rms[k.replace(".bias", ".weight")])
+    g_ours, g_auto = {}, {}
+    for k, p in model.named_parameters():
+        if k not in rms or k in zero_grad:
+            continue
+        ref = sd[k].grad.float()
+        g_ours[k] = float((p.grad.float() - ref).pow(2).mean().sqrt()) / max(rms[k], floor)
+        g_auto[k] = float((sdy[k].grad.float() - ref).pow(2).mean().sqrt()) / max(rms[k], floor)
+    wk = max(g_ours, key=g_ours.get)
+    gn_ours = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in model.parameters() if p.grad is not None)).item()
+    gn_ref = torch.sqrt(sum((v.grad.float() ** 2).sum() for v in sd.values() if v.is_floating_point() and v.grad is not None)).item()
+    print(f"[{temporal}] logits {e_logits:.3e} (autocast {y_logits:.3e})  loss {e_loss:.3e} (autocast {y_loss:.3e})  "
+          f"worst grad RMS {g_ours[wk]:.3e} at {wk} (autocast worst {max(g_auto.values()):.3e})  "
+          f"grad-norm {gn_ours:.5f} vs {gn_ref:.5f}")
+    top = sorted(g_ours, key=g_ours.get, reverse=True)[:6]
+    print("   worst gradients:", [(k, round(g_ours[k], 4), round(g_auto[k], 4)) for k in top])
+    keys = [k for k, _ in model.named_parameters() if k in rms]
+    named = dict(model.named_parameters())
+    d_ours = torch.sqrt(sum(((named[k].grad.float() - sd[k].grad.float()) ** 2).sum() for k in keys)).item() / gn_ref
+    d_auto = torch.sqrt(sum(((sdy[k].grad.float() - sd[k].grad.float()) ** 2).sum() for k in keys)).item() / gn_ref
+    print(f"   whole-gradient relative error {d_ours:.4f} (autocast {d_auto:.4f})")
+    assert e_logits < E2E_LOGITS and e_loss < E2E_LOSS
+    assert abs(gn_ours - gn_ref) / gn_ref < E2E_GRAD_NORM
+    # the whole gradient VECTOR of this random-weight, train-mode-BN problem is rounding-dominated at bf16 storage
+    # (relative error ~1.0 for PyTorch's autocast run as well): the claim that can be held is "not worse than PyTorch"
+    assert d_ours <= 1.15 * d_auto + 1e-2, (d_ours, d_auto)
+
+
+# (name, inp, hidden-expansion t, oup, H_in, stride, temporal) — every distinct InvertedResidual shape of MobileNetV2
+BLOCK_SHAPES = [("f1", 32, 1, 16, 112, 1, "none"), ("f2", 16, 6, 24, 112, 2, "none"), ("f3", 24, 6, 24, 56, 1, "tsm"),
+                ("f4", 24, 6, 32, 56, 2, "none"), ("f5", 32, 6, 32, 28, 1, "tsm"), ("f7", 32, 6, 64, 28, 2, "none"),
+                ("f8", 64, 6, 64, 14, 1, "tsm"), ("f11", 64, 6, 96, 14, 1, "none"), ("f12", 96, 6, 96, 14, 1, "tsm"),
+                ("f14", 96, 6, 160, 14, 2, "none"), ("f15", 160, 6, 160, 7, 1, "tsm"), ("f17", 160, 6, 320, 7, 1, "none"),
+                ("f3a", 24, 6, 24, 56, 1, "action"), ("f12a", 96, 6, 96, 14, 1, "action"), ("f15a", 160, 6, 160, 7, 1, "action")]
+BLOCK_TOL = 2e-2
+
+
+@pytest.mark.parametrize("name,inp,t,oup,h,stride,temporal", BLOCK_SHAPES)
+def test_block_forward_backward_at_bench_size_bf16(name, inp, t, oup, h, stride, temporal):
+    """One InvertedResidual at the bench size (256 frames), bf16 storage, forward AND backward, against the fp32
+    oracle on the same bf16-rounded input and output gradient: output, input gradient and every parameter gradient
+    within 2e-2: max-norm relative for the output; RMS-relative for the gradients (a bf16-rounded pre-activation that
+    lands on the other side of a ReLU6 corner flips single mask bits against the fp32 run, which makes the max-norm of a
+    gradient an extreme-value statistic of the rounding, in any implementation).  This is where the multi-wave paths of the GEMM / wgrad / depthwise
+    kernels (dgrad, wgrad, fused BN-backward operands) are checked at full size."""
+    import ehgr_b200 as E
+    torch.manual_seed(0)
+    nt = CLIPS * 8
+    with _quiet():
+        blk = E.InvertedResidual(inp, oup, stride, t)
+        if temporal == "tsm":
+            blk.conv[0] = E.TemporalShift(blk.conv[0], n_segment=8, n_div=8)
+        if temporal == "action":
+            blk.conv[0] = E.Action(blk.conv[0], n_segment=8, shift_div=8)
+            with torch.no_grad():
+                g0 = torch.Generator().manual_seed(9)
+                for k, p in blk.conv[0].named_parameters():
+                    if k.startswith("action_") and "bn" not in k:
+                        p.add_(torch.randn(p.shape, generator=g0) * 0.3)
+    g0 = torch.Generator().manual_seed(3)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.weight.shape, generator=g0) * 0.5 + 0.75
+            m.bias.data = torch.randn(m.bias.shape, generator=g0) * 0.1
+    sd0 = {"f." + k: v.clone() for k, v in blk.state_dict().items()}
+    ho = (h - 1) // stride + 1
+    x = torch.randn(nt, inp, h, h, generator=g0).bfloat16()
+    g = (torch.randn(nt, oup, ho, ho, generator=g0) * 0.1).bfloat16()
+    blk = blk.cuda().train()
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    with E.fused.compute_dtype(torch.bfloat16):
+        y = blk(xd)
+    y.backward(g.cuda().contiguous(memory_format=torch.channels_last))
+    sd = _cuda_state(sd0, grad=True)
+    xo = x.float().cuda().requires_grad_(True)
+    yo = O.inverted_residual(xo, sd, "f", inp, oup, stride, t, temporal, 8, 8, True)
+    yo.backward(g.float().cuda())
+    # yardstick (printed only): the same oracle under PyTorch's bf16 autocast
+    sdy = _cuda_state(sd0, grad=True)
+    xy = x.float().cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yy = O.inverted_residual(xy, sdy, "f", inp, oup, stride, t, temporal, 8, 8, True)
+    yy.backward(g.cuda().to(yy.dtype))
+    errs = {"y": _err(y, yo), "dx": _rms_err(xd.grad, xo.grad)}
+    auto = {"y": _err(yy, yo), "dx": _rms_err(xy.grad, xo.grad)}
+    # parameter gradients: RMS error relative to the RMS of the largest gradient of the same kind in the block (conv
+    # weights / BatchNorm vectors), so that mathematically-zero gradients (the last BatchNorm's shift) do not divide by 0
+    rms = {k: float(v.grad.float().pow(2).mean().sqrt()) for k, v in sd.items() if v.grad is not None}
+    scale_w = max(v for k, v in rms.items() if sd[k].dim() > 1)
+    scale_b = max(v for k, v in rms.items() if sd[k].dim() == 1)
+    for k, p in blk.named_parameters():
+        ref = sd["f." + k].grad.float()
+        sc = max(rms["f." + k], 0.1 * (scale_w if ref.dim() > 1 else scale_b))
+        errs[k] = float((p.grad.float() - ref).pow(2).mean().sqrt()) / sc
+        auto[k] = float((sdy["f." + k].grad.float() - ref).pow(2).mean().sqrt()) / sc
+    print(name, {k: (round(v, 4), round(auto[k], 4)) for k, v in errs.items()})
+    # output: the flat 2e-2 line.  Gradients: 2e-2, or — where bf16 STORAGE itself costs more — no worse than 1.25x what
+    # PyTorch's own bf16 run of the reference ops loses on the same data: about 0.15 % of the bf16-rounded
+    # pre-activations fall on the other side of a ReLU6 corner than their fp32 values, each flips one mask bit, and
+    # that alone is a 4-6 % RMS error in d(x) and the conv-weight gradients (8-30 % in the expand BatchNorm's
+    # scale/shift gradients, which are sums with heavy cancellation), identically in both implementations.
+    bad = {k: (v, auto[k]) for k, v in errs.items()
+           if not (v < BLOCK_TOL or (k != "y" and v <= 1.25 * auto[k] + 5e-3))}
+    assert not bad, bad
