@@ -19,10 +19,6 @@ void ensure_dyn_smem(const void* func, int bytes) {
 }
 }
 
-namespace ehgr { int g_debug_flags = 0; }
-// undocumented bring-up switch (timing experiments only; results are wrong when set)
-extern "C" void ehgr_debug_set(int flags) { ehgr::g_debug_flags = flags; }
-
 namespace ehgr {
 namespace tma {
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -11,7 +11,6 @@
 namespace ehgr {
 
 extern std::atomic<long long> g_launches;
-extern int g_debug_flags;
 
 // Every launch goes through this so that `ehgr_launch_count()` is an honest count.
 inline int launch_status() {

@@ -36,7 +36,6 @@ struct DwSw {
   int nt, h, w, c, ho, wo;
   int tiles_y, tiles_x, n_chunks;
   long long items;          // nt * tiles_y * tiles_x
-  int dbg;                  // bring-up timing switches (api.cu: ehgr_debug_set)
 };
 
 template <int STRIDE, int CVN, int TW, int TH>
@@ -351,7 +350,7 @@ dw_bwd_sw_kernel(RowOp dy, RowOp a, const __grid_constant__ CUtensorMap tm_a, co
     }
     mbar_wait(bar, phase);
     phase ^= 1;
-    if (cv_on && !(g.dbg & 256)) {
+    if (cv_on) {
       if (a.mode != EHGR_ROW_PLAIN) {
         RowOp ac = a;
         ac.mode = EHGR_ROW_AFFINE;      // compile-time constants for the loaders (the host admits only these modes)
@@ -370,8 +369,7 @@ dw_bwd_sw_kernel(RowOp dy, RowOp a, const __grid_constant__ CUtensorMap tm_a, co
     __syncthreads();
     if (col < TW) {
       // ---- weight gradient
-      if (!(g.dbg & 64)) wgrad_sweep<STRIDE, CVN, Cfg::IW, Cfg::IH, TH, DWID, DOFF>(a_tile, g_tile, cv, col, acc9);
-      if (g.dbg & 128) continue;
+      wgrad_sweep<STRIDE, CVN, Cfg::IW, Cfg::IH, TH, DWID, DOFF>(a_tile, g_tile, cv, col, acc9);
       // ---- input gradient
       if constexpr (STRIDE == 1) {
         float2 wf[9][4];
@@ -464,7 +462,6 @@ static void dw_sw_geom(DwSw& g, int nt, int h, int w, int c) {
   g.tiles_x = (g.wo + TW - 1) / TW;
   g.n_chunks = (c + CVN * 8 - 1) / (CVN * 8);
   g.items = static_cast<long long>(nt) * g.tiles_y * g.tiles_x;
-  g.dbg = g_debug_flags;
 }
 
 static unsigned dw_sw_grid(const DwSw& g, int per_sm) {

@@ -21,10 +21,18 @@
 //   warp  8    MMA       : one elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16 per
 //                          instruction) into one of two TMEM accumulator buffers; tcgen05.commit
 //                          releases ring slots / publishes the accumulator through mbarriers.
-//   warps 9-12 EPILOGUE  : tcgen05.ld the accumulator (each warp its 32-lane quarter), fold the
-//                          BatchNorm batch statistics (shuffle transpose-reduction, kept in registers
-//                          across all tiles of the CTA, one flush of double atomics at the end), add the
-//                          optional addend, convert to bf16, store 32-byte row segments.
+//   16 EPILOGUE warps    : four per TMEM lane quarter, each a contiguous quarter of the tile's columns (<= 4 chunks of
+//                          16).  The epilogue is a chain of dependent instructions per warp (ncu: the tile rate
+//                          of the output-heavy expand layers followed the per-warp instruction count, not the
+//                          bytes), so it is spread over many warps and kept short: two tcgen05.ld in flight,
+//                          optional addend (prefetched into the staging rows with cp.async while the warp waits
+//                          for the accumulator), bf16 rows staged in shared memory (odd 16-byte pitch: no bank
+//                          conflicts), the TMEM buffer released as soon as the last chunk has been read, then
+//                          COALESCED 16-byte global stores: a lane owns one 16-byte piece column of the row
+//                          segment and walks down the rows — and accumulates the BatchNorm batch statistics of
+//                          its eight channels from the very words it stores (packed FADD2 / FFMA2, registers kept
+//                          across all tiles of the CTA, one reduction at the end).  The statistics therefore
+//                          describe the STORED bf16 tensor, which is the tensor the consumer normalises.
 // The two TMEM buffers let the epilogue of tile i overlap the loads and MMAs of tile i+1.
 // w_is_kn selects the B operand's major-ness: forward reads the conv weight [N,K] as a K-major B,
 // dgrad reads the same array [K,N] as an MN-major B — no transposed weight copy exists.
@@ -39,13 +47,16 @@ constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int BK = 64;             // reduction elements per ring stage
 constexpr int kProducerWarps = 7;   // 12 warps = 384 threads: up to 168 registers per thread
 constexpr int kMmaWarp = kProducerWarps;
-constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, alternating 16-column chunks
-constexpr int kThreads = (kProducerWarps + 1 + kEpiWarps) * 32;   // 512: up to 128 registers per thread
+// Epilogue warps: a template parameter (kEpi).  16 (four per TMEM lane quarter; 768 threads, <= 80 registers) for the
+// output-heavy shapes (N > K: expand forward, dgrad of the project layers), whose tile rate follows the epilogue's
+// per-warp instruction chain; 8 (two per quarter; 512 threads, <= 128 registers) for the input-heavy shapes
+// (K >= N), whose bound is the producers' load + in-place transform and which want the registers and issue slots.
+constexpr int threads_of(int epi_warps) { return (kProducerWarps + 1 + epi_warps) * 32; }
 constexpr int kMaxStages = 12;
 constexpr int kBatch = 4;                      // vectors a producer lane fetches before it converts any
 constexpr int kMaxBufs = 8;                    // TMEM accumulator buffers (n_bufs * BN <= 512 columns)
 constexpr int kBarBytes = 512;                 // mbarriers + TMEM slot
-constexpr int kTailBytes = kBarBytes + kEpiWarps * 512 * 4;   // + per-epilogue-warp statistics accumulators
+constexpr int kTailBytes = kBarBytes;
 
 struct GemmArgs {
   RowOp a;
@@ -66,7 +77,7 @@ struct GemmArgs {
   int n_stages;    // ring depth
   int a_bytes;     // bytes of the A part of a stage = 128 * min(Kp,64) * 2
   int stage_bytes; // a_bytes (+ BN*128 when B is streamed)
-  int dbg;
+  int epi_pitch;   // bytes between the 32 staging rows of an epilogue warp (odd multiple of 16)
 };
 
 // B tile -> shared memory in core-matrix layout: group stride `gs` bytes, k-group stride 128.
@@ -152,8 +163,10 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
 //                  stage IN PLACE (each lane re-reads exactly the chunks it copied).  SHIFT is a pure gather:
 //                  the copy's source is the neighbouring frame or a zero fill.
 // kAsync = false: register path (batched fetch -> rowop -> store) for the two-tensor BNBWD operand.
-template <int kMode>
-__global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
+template <int kMode, int kEpiWarps>
+__global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(GemmArgs p) {
+  constexpr int kThreads = threads_of(kEpiWarps);
+  constexpr int kParts = kEpiWarps / 4;           // epilogue warps per TMEM lane quarter
   constexpr bool kAsync = kMode != EHGR_ROW_BNBWD;     // the operand mode is a compile-time constant: one kernel per mode
   extern __shared__ __align__(128) uint8_t smem[];
   const int Kp = (p.K + 15) & ~15;
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
             t0 = static_cast<int>(f0 % p.a.n_segment);
           }
 #pragma unroll 1
-          for (int pass = 0; pass * 4 < kv && !(p.dbg & 8); ++pass) {
+          for (int pass = 0; pass * 4 < kv; ++pass) {
             const int k8 = pass * 4 + (slot % kvp);
             const int k = k_base + k8 * 8;
             const bool kin = k8 < kv && k < p.K;
@@ -256,15 +269,13 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
                 int left = left64 > 4096 ? 4096 : static_cast<int>(left64);    // > 0: row exists
                 const uint32_t dst_step = static_cast<uint32_t>(f * a_sbo);
                 const long long src_step = 8LL * f * p.K;
-                if (!(p.dbg & 2)) {
 #pragma unroll 4
-                  for (int rg = rg0; rg < 16; rg += f) {
-                    const bool live = left > 0;
-                    cp_async16(dst, live ? src : in1, live ? 16u : 0u);
-                    dst += dst_step;
-                    src += src_step;
-                    left -= 8 * f;
-                  }
+                for (int rg = rg0; rg < 16; rg += f) {
+                  const bool live = left > 0;
+                  cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+                  dst += dst_step;
+                  src += src_step;
+                  left -= 8 * f;
                 }
               }
               continue;
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
                 live = tt >= 0 && tt < p.a.n_segment;
                 src += cls == 0 ? step : -step;
               }
-              if (!(p.dbg & 2)) cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+              cp_async16(dst, live ? src : in1, live ? 16u : 0u);
             }
           }
           if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
           cp_async_wait_all();
         }
-        if (!(p.dbg & 1)) fence_proxy_async();
+        fence_proxy_async();
         __syncwarp();                                // every lane's writes are fenced before the single arrival
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
@@ -421,88 +432,145 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_tc_kernel(GemmArgs p) {
           const uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(ks) * 64u : a_lo + abytes16;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
-            if (kk < ksteps && !(p.dbg & 4))
+            if (kk < ksteps)
               umma_bf16(d_tmem, desc(a_lo + kk * 16, hi_a), desc(b_lo + kk * 16, hi_b), idesc, (ks | kk) ? 1u : 0u);
-          if (p.dbg & 32) mbar_arrive(bar_empty + 8 * s); else
           umma_commit(bar_empty + 8 * s);          // ring slot free once these MMAs have read it
         }
-        if (p.dbg & 32) mbar_arrive(bar_tfull + 8 * buf); else
         umma_commit(bar_tfull + 8 * buf);          // accumulator complete
       }
     }
   } else {
     // ===================== EPILOGUE =====================
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    const int ew = warp - (kMmaWarp + 1);           // epilogue warp index 0..7
-    const int half = ew >> 2;                       // which of the quarter's two warps: chunks cc = half, half+2, ...
-    const int n_cc = p.BN >> 4;                     // 16-column chunks
-    // per-warp statistics accumulators live in shared memory (column index is dynamic); the chunk loop
-    // is deliberately NOT unrolled: the kernel must stay small enough for the instruction cache
-    float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + ew * 512;
-    float* s_sq = s_sum + 256;
-    const int col = (lane >> 1) & 15;
-    if (p.stats) {
-      for (int i = lane; i < 512; i += 32) s_sum[i] = 0.f;
-      __syncwarp();
-    }
+    const int ew = warp - (kMmaWarp + 1);           // epilogue warp index 0..15
+    const int part = ew >> 2;                       // which of the quarter's kParts warps
+    const int n_cc = p.BN >> 4;                     // 16-column chunks of a tile
+    const int cpp = (n_cc + kParts - 1) / kParts;   // chunks per warp
+    const int c_lo = min(part * cpp, n_cc), c_hi = min(c_lo + cpp, n_cc);   // this warp's chunks: a contiguous column range
+    const int nch = c_hi - c_lo;
+    uint8_t* tail = reinterpret_cast<uint8_t*>(bars) + kBarBytes;
+    const uint32_t pitch = static_cast<uint32_t>(p.epi_pitch);
+    const uint32_t stage32 = smem_u32(tail) + static_cast<uint32_t>(ew) * 32u * pitch;
+    const uint32_t my_row32 = stage32 + static_cast<uint32_t>(lane) * pitch;
+    // store phase: lane = (row group rgp, 16-byte piece pc) of the row segment; ppr valid pieces per row
+    const int n_sub = n0 + c_lo * 16;
+    int nv = p.N - n_sub;                            // valid columns of this warp (multiple of 8)
+    nv = nv < 0 ? 0 : (nv > nch * 16 ? nch * 16 : nv);
+    const int ppr = nv >> 3;
+    int lg = 0;
+    while ((1 << lg) < ppr) ++lg;                    // pieces per row padded to a power of two (1, 2, 4, 8)
+    const int pc = lane & ((1 << lg) - 1), rgp = lane >> lg, rstep = 32 >> lg;
+    const bool pc_on = pc < ppr;
+    float2 st_sum[4], st_sq[4];                      // statistics of this lane's eight channels, all tiles
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st_sum[i] = st_sq[i] = make_float2(0.f, 0.f);
     uint32_t buf = 0, bph = 0;
     const int tile_step = gridDim.x / p.n_chunks;
     int m_tile = blockIdx.x / p.n_chunks;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++buf, m_tile += tile_step) {
       if (buf == static_cast<uint32_t>(p.n_bufs)) { buf = 0; bph ^= 1; }
-      const long long m = static_cast<long long>(m_tile) * BM + q * 32 + lane;
-      mbar_wait(bar_tfull + 8 * buf, bph);
-      tc_fence_after();
+      const long long m_base = static_cast<long long>(m_tile) * BM + q * 32;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * static_cast<uint32_t>(p.BN);
-#pragma unroll 1
-      for (int cc = half; cc < n_cc && !(p.dbg & 16); cc += 2) {
-        {
-          float v[16];
-          tmem_ld16(t_base + cc * 16, v);
-          if (p.stats) {
-            float sq[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-            const float cs = warp_colsum16(v, lane), cq = warp_colsum16(sq, lane);
-            if (!(lane & 1)) {                      // lanes 2c and 2c+1 hold the same column: one writes
-              s_sum[cc * 16 + col] += cs;
-              s_sq[cc * 16 + col] += cq;
-            }
-          }
-          const int n = n0 + cc * 16;
-          if (m < p.M && n < p.N) {
-            const long long off = m * p.N + n;
-            const bool second = n + 8 < p.N;       // N % 8 == 0: a chunk is 1 or 2 valid 8-column halves
-            if (p.addend) {
-              float ad[8];
-              load_vec<__nv_bfloat16, 8>(p.addend + off, ad);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += ad[i];
-              if (second) {
-                load_vec<__nv_bfloat16, 8>(p.addend + off + 8, ad);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[8 + i] += ad[i];
-              }
-            }
-            float lo[8], hi[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
-            *reinterpret_cast<uint4*>(p.out + off) = pack8(lo);
-            if (second) *reinterpret_cast<uint4*>(p.out + off + 8) = pack8(hi);
-          }
+      __syncwarp();                                  // the previous tile's staging reads are complete
+      if (p.addend && pc_on) {                       // coalesced prefetch of the addend rows into the staging rows
+        const __nv_bfloat16* src = p.addend + (m_base + rgp) * p.N + n_sub + pc * 8;
+        uint32_t dst = stage32 + static_cast<uint32_t>(rgp) * pitch + static_cast<uint32_t>(pc) * 16u;
+        long long left = p.M - m_base - rgp;
+        for (int r = rgp; r < 32; r += rstep) {
+          const bool live = left > 0;
+          cp_async16(dst, live ? src : p.addend, live ? 16u : 0u);
+          dst += static_cast<uint32_t>(rstep) * pitch;
+          src += static_cast<long long>(rstep) * p.N;
+          left -= rstep;
         }
       }
-      tc_fence_before();
+      mbar_wait_warp(bar_tfull + 8 * buf, bph);      // lane 0 polls: 16 waiting warps must not flood the barrier
+      tc_fence_after();
+      if (p.addend) {
+        cp_async_wait_all();
+        __syncwarp();
+      }
+      // ---- TMEM -> registers -> (+ addend) -> bf16 staging row of this lane
+#pragma unroll 1
+      for (int j = 0; j < nch; j += 2) {
+        uint32_t r0[16], r1[16];
+        const bool two = j + 1 < nch;
+        tmem_ld16_issue(t_base + (c_lo + j) * 16, r0);
+        if (two) tmem_ld16_issue(t_base + (c_lo + j + 1) * 16, r1);
+        tmem_ld_wait(r0);
+        if (two) tmem_ld_wait(r1);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          if (h2 == 1 && !two) break;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(h2 ? r1[i] : r0[i]);
+          const uint32_t dst = my_row32 + static_cast<uint32_t>(j + h2) * 32u;
+          if (p.addend) {
+            float ad[8];
+            uint4 a4 = lds128(dst);
+            load_vec<__nv_bfloat16, 8>(reinterpret_cast<const __nv_bfloat16*>(&a4), ad);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += ad[i];
+            a4 = lds128(dst + 16);
+            load_vec<__nv_bfloat16, 8>(reinterpret_cast<const __nv_bfloat16*>(&a4), ad);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 + i] += ad[i];
+          }
+          float lo[8], hi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+          sts128(dst, pack8(lo));
+          sts128(dst + 16, pack8(hi));
+        }
+      }
+      tc_fence_before();                             // last chunk read: hand the accumulator buffer back to the MMA warp
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      // ---- staging rows -> global, statistics from the stored words
+      if (pc_on) {
+        __nv_bfloat16* dst = p.out + (m_base + rgp) * p.N + n_sub + pc * 8;
+        uint32_t src = stage32 + static_cast<uint32_t>(rgp) * pitch + static_cast<uint32_t>(pc) * 16u;
+        long long left = p.M - m_base - rgp;
+        for (int r = rgp; r < 32; r += rstep) {
+          if (left > 0) {
+            const uint4 w = lds128(src);
+            stg128(dst, w);
+            if (p.stats) {                           // rows past M are never stored and never counted
+              const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = bf2_to_f2(ww[i]);
+                st_sum[i] = __fadd2_rn(st_sum[i], f);
+                st_sq[i] = __ffma2_rn(f, f, st_sq[i]);
+              }
+            }
+          }
+          src += static_cast<uint32_t>(rstep) * pitch;
+          dst += static_cast<long long>(rstep) * p.N;
+          left -= rstep;
+        }
+      }
     }
     if (p.stats) {
-      __syncwarp();
-      for (int c = lane; c < p.BN; c += 32) {
-        const int n = n0 + c;
-        if (n < p.N && ((c >> 4) & 1) == half) {
-          atomicAdd(&p.stats[n], static_cast<double>(s_sum[c]));
-          atomicAdd(&p.stats[p.N + n], static_cast<double>(s_sq[c]));
+      // reduce over the row-group lanes that share a piece column (fixed order), then one pair of atomics per channel
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        for (int o = 16; o >= (1 << lg) && o > 0; o >>= 1) {
+          st_sum[i].x += __shfl_xor_sync(0xffffffffu, st_sum[i].x, o);
+          st_sum[i].y += __shfl_xor_sync(0xffffffffu, st_sum[i].y, o);
+          st_sq[i].x += __shfl_xor_sync(0xffffffffu, st_sq[i].x, o);
+          st_sq[i].y += __shfl_xor_sync(0xffffffffu, st_sq[i].y, o);
+        }
+      }
+      if (pc_on && rgp == 0) {
+        const int n = n_sub + pc * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          atomicAdd(&p.stats[n + 2 * i], static_cast<double>(st_sum[i].x));
+          atomicAdd(&p.stats[n + 2 * i + 1], static_cast<double>(st_sum[i].y));
+          atomicAdd(&p.stats[p.N + n + 2 * i], static_cast<double>(st_sq[i].x));
+          atomicAdd(&p.stats[p.N + n + 2 * i + 1], static_cast<double>(st_sq[i].y));
         }
       }
     }
@@ -531,24 +599,47 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   tc::GemmArgs p;
   p.a = a; p.w = w; p.w_is_kn = w_is_kn;
   p.w16 = static_cast<const __nv_bfloat16*>(w16);
-  p.dbg = g_debug_flags;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
   p.stats = stats;
   p.M = M; p.K = K; p.N = N;
-  p.BN = tc::pick_bn(N);
-  p.n_chunks = (N + p.BN - 1) / p.BN;
   p.m_tiles = static_cast<int>(cdiv(M, tc::BM));
   p.n_bufs = 2;   // more buffers bought nothing (the hand-shake is not the bound) and a 512-column allocation
                   // makes the next kernel's CTAs wait for TMEM
+  const int Kp = (K + 15) & ~15;
+  constexpr int kBudget = 200 * 1024;
+  p.a_bytes = tc::BM * std::min(Kp, tc::BK) * 2;
+  // Output columns per tile: as few column chunks as possible (A is re-read once per chunk), but the epilogue
+  // staging (the whole bf16 output tile) and the weights share the 200 KB with the operand ring: take the first
+  // chunk count that leaves at least four ring stages, else the one with the deepest ring.  Input-heavy shapes
+  // (K >= N: the project / dgrad-of-expand layers) never take extra chunks: re-reading A costs more than a shallow ring.
+  const int Np = (N + 15) & ~15;
+  const int epi_warps = K >= N ? 8 : 16, parts = epi_warps / 4;
+  int best_chunks = 0, best_stages = -1, bar_bytes = 0, b_res = 0;
+  const int min_chunks = (Np + 255) / 256;
+  for (int chunks = min_chunks; chunks <= min_chunks + (K >= N ? 0 : 3); ++chunks) {
+    int bn = (Np / chunks + 15) & ~15;
+    while (bn * chunks < Np) bn += 16;
+    if (bn > 256 || bn < 16) continue;
+    const int pitch = ((bn >> 4) + parts - 1) / parts * 32 + 16;
+    const int bar = tc::kTailBytes + epi_warps * 32 * pitch;
+    const int bres = bn * Kp * 2;
+    const bool resident = bres + 6 * p.a_bytes + bar <= kBudget;
+    const int stage = p.a_bytes + (resident ? 0 : bn * tc::BK * 2);
+    const int stages = std::min(tc::kMaxStages, (kBudget - bar - (resident ? bres : 0)) / stage);
+    if (stages > best_stages) { best_stages = stages; best_chunks = chunks; }
+    if (stages >= 4) { best_chunks = chunks; break; }
+  }
+  p.n_chunks = best_chunks;
+  p.BN = (Np / p.n_chunks + 15) & ~15;
+  while (p.BN * p.n_chunks < Np) p.BN += 16;
   int cols = 32;
   while (cols < p.n_bufs * p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  const int Kp = (K + 15) & ~15;
-  constexpr int kBudget = 200 * 1024;
-  const int bar_bytes = tc::kTailBytes;
-  p.a_bytes = tc::BM * std::min(Kp, tc::BK) * 2;
-  const int b_res = p.BN * Kp * 2;
+  const int n_cc = p.BN >> 4;
+  p.epi_pitch = (n_cc + parts - 1) / parts * 32 + 16;           // odd multiple of 16 bytes: conflict-free row stores
+  bar_bytes = tc::kTailBytes + epi_warps * 32 * p.epi_pitch;
+  b_res = p.BN * Kp * 2;
   // weights resident when that still leaves >= 6 A stages (the large-M layers all qualify)
   p.b_resident = (b_res + 6 * p.a_bytes + bar_bytes <= kBudget) ? 1 : 0;
   p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : p.BN * tc::BK * 2);
@@ -561,8 +652,13 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes;
   auto go = [&](auto mode_tag) {
     constexpr int kMode = decltype(mode_tag)::value;
-    ensure_smem(tc::pw_gemm_tc_kernel<kMode>, kBudget);
-    tc::pw_gemm_tc_kernel<kMode><<<static_cast<unsigned>(grid), tc::kThreads, smem, s>>>(p);
+    if (epi_warps == 16) {
+      ensure_smem(tc::pw_gemm_tc_kernel<kMode, 16>, kBudget);
+      tc::pw_gemm_tc_kernel<kMode, 16><<<static_cast<unsigned>(grid), tc::threads_of(16), smem, s>>>(p);
+    } else {
+      ensure_smem(tc::pw_gemm_tc_kernel<kMode, 8>, kBudget);
+      tc::pw_gemm_tc_kernel<kMode, 8><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p);
+    }
   };
   switch (a.mode) {
     case EHGR_ROW_PLAIN: go(std::integral_constant<int, EHGR_ROW_PLAIN>{}); break;

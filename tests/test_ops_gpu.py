@@ -158,7 +158,10 @@ def test_pw_gemm_tcgen05_forward(M, K, N):
     aa = torch.clamp(a.double() * scale.double() + shift.double(), 0, 6).to(dtype).double()   # operand is rounded to bf16
     want = aa @ w.to(dtype).double().t()
     assert rel_err(out.cpu(), want) < 1e-2
-    assert rel_err(stats[:N].cpu(), want.sum(0)) < 2e-3 and rel_err(stats[N:].cpu(), (want ** 2).sum(0)) < 2e-3
+    # the batch statistics describe the STORED (bf16-rounded) tensor — the one the consumer normalises
+    stored = out.cpu().double()
+    assert rel_err(stats[:N].cpu(), stored.sum(0)) < 1e-5 and rel_err(stats[N:].cpu(), (stored ** 2).sum(0)) < 1e-5
+    assert rel_err(stats[:N].cpu(), want.sum(0)) < 5e-3 and rel_err(stats[N:].cpu(), (want ** 2).sum(0)) < 5e-3
     # same call on the SIMT engine must agree to bf16 rounding
     out_s = torch.empty_like(out)
     _call("ehgr_pw_gemm", ctypes.byref(f.op_affine(ad, sc_d, sh_d, True)), wd.data_ptr(), 0, out_s.data_ptr(), 0, 0,

@@ -56,10 +56,7 @@ def main():
     ap.add_argument("--blocks", default="")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--engine", type=int, default=0)
-    ap.add_argument("--dbg", type=int, default=0)
     args = ap.parse_args()
-    if args.dbg:
-        _lib.lib().ehgr_debug_set(args.dbg)
     only = set(filter(None, args.only.split(",")))
     blocks = set(filter(None, args.blocks.split(",")))
     nt = args.frames
