@@ -125,7 +125,10 @@ SIGNATURES = {
     "ehgr_bn_bwd_finalize": [_P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
     "ehgr_row_apply": [_R, _P, _P, _L, _I, _I, _P],
     "ehgr_normalize_u8": [_P, _P, _L, _I, _L, _P, _P, _F, _I, _P],
-    "ehgr_sgd_step": [_P, _P, _P, _P, _P, _P, _I, _P, _F, _F, _L, _P],
+    "ehgr_sgd_step": [_P, _P, _P, _P, _P, _P, _I, _P, _F, _F, _L, _P, _D, _P],
+    "ehgr_ema_update": [_P, _P, _L, _D, _I, _P],
+    "ehgr_temporal_pool_fwd": [_P, _P, _L, _I, _L, _I, _P],
+    "ehgr_temporal_pool_bwd": [_P, _P, _P, _L, _I, _L, _I, _P],
     "ehgr_pool_fwd": [_R, _P, _I, _I, _I, _I, _P],
     "ehgr_pool_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "ehgr_fc_consensus_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -4,6 +4,12 @@
 // (dampening 0, no Nesterov — the reference's configuration; a zero-initialised momentum buffer reproduces
 // torch's first-step rule buf = d).  k = group code of the element (one byte per element); the base learning
 // rate is read from DEVICE memory so that a schedule (adjust_learning_rate) never invalidates a captured graph.
+//
+// EMA (the reference's EMAWrapper, train_mtmm.py:110-128, updated after every optimiser step, :245):
+//   ema = decay * ema + (1 - decay) * value   over EVERY state_dict entry.  For the parameters it is folded into the
+// SGD kernel (the freshly updated parameter is still in registers); floating-point buffers (BatchNorm running
+// statistics) and the int64 num_batches_tracked counters have one small kernel each.  The three roundings of the
+// reference expression (two products, one sum, each a separate fp32 op) are reproduced: bit-identical results.
 #include "common.cuh"
 
 namespace ehgr {
@@ -11,7 +17,8 @@ namespace ehgr {
 __global__ void __launch_bounds__(256)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, const uint8_t* __restrict__ code,
                 const float* __restrict__ lr_mult, const float* __restrict__ decay_mult, int n_groups,
-                const float* __restrict__ lr_dev, float momentum, float weight_decay, long long n) {
+                const float* __restrict__ lr_dev, float momentum, float weight_decay, long long n,
+                float* __restrict__ ema, float ema_decay, float ema_rest) {
   __shared__ float s_lr[64], s_wd[64];
   const float lr = *lr_dev;
   for (int i = threadIdx.x; i < n_groups; i += blockDim.x) {
@@ -39,22 +46,68 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     }
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(buf)[i] = bv;
+    if (ema) {                                               // padding elements: 0 stays 0
+      float4 ev = reinterpret_cast<float4*>(ema)[i];
+      float* ep = reinterpret_cast<float*>(&ev);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ep[k] = __fadd_rn(__fmul_rn(ema_decay, ep[k]), __fmul_rn(ema_rest, pp[k]));
+      reinterpret_cast<float4*>(ema)[i] = ev;
+    }
   }
+}
+
+__global__ void __launch_bounds__(256)
+ema_f32_kernel(float* __restrict__ ema, const float* __restrict__ x, float decay, float rest, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    ema[i] = __fadd_rn(__fmul_rn(decay, ema[i]), __fmul_rn(rest, x[i]));
+}
+
+// int64 entries: the reference evaluates python_float * int64_tensor in the default float32 and copy_()s the sum back
+// into the int64 tensor (truncation toward zero)
+__global__ void __launch_bounds__(256)
+ema_i64_kernel(long long* __restrict__ ema, const long long* __restrict__ x, float decay, float rest, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    ema[i] = static_cast<long long>(__fadd_rn(__fmul_rn(decay, static_cast<float>(ema[i])), __fmul_rn(rest, static_cast<float>(x[i]))));
 }
 
 }  // namespace ehgr
 
 using namespace ehgr;
 
+static void ema_coefs(double decay, float* d, float* rest) {
+  *d = static_cast<float>(decay);              // python scalars reach the fp32 kernels as (float)decay and (float)(1. - decay)
+  *rest = static_cast<float>(1.0 - decay);
+}
+
 extern "C" int ehgr_sgd_step(float* p, const float* g, float* buf, const void* code, const float* lr_mult,
                              const float* decay_mult, int n_groups, const float* lr_dev, float momentum, float weight_decay,
-                             long long n, ehgr_stream_t stream) {
+                             long long n, float* ema, double ema_decay, ehgr_stream_t stream) {
   if (!p || !g || !buf || !code || !lr_mult || !decay_mult || !lr_dev) return EHGR_E_NULL;
   if (n < 0 || (n % 4) || n_groups <= 0 || n_groups > 64) return EHGR_E_SHAPE;
-  if (!aligned_to(p, 16) || !aligned_to(g, 16) || !aligned_to(buf, 16) || !aligned_to(code, 4)) return EHGR_E_ALIGN;
+  if (!aligned_to(p, 16) || !aligned_to(g, 16) || !aligned_to(buf, 16) || !aligned_to(code, 4) || (ema && !aligned_to(ema, 16)))
+    return EHGR_E_ALIGN;
+  float ed = 0.f, er = 0.f;
+  ema_coefs(ema_decay, &ed, &er);
   if (n == 0) return EHGR_OK;
   const unsigned blocks = static_cast<unsigned>(std::max(1LL, std::min(cdiv(n / 4, 256), 8LL * kNumSMs)));
   sgd_step_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, buf, static_cast<const uint8_t*>(code), lr_mult, decay_mult,
-                                                          n_groups, lr_dev, momentum, weight_decay, n);
+                                                          n_groups, lr_dev, momentum, weight_decay, n, ema, ed, er);
+  return launch_status();
+}
+
+extern "C" int ehgr_ema_update(void* ema, const void* x, long long n, double decay, int is_int64, ehgr_stream_t stream) {
+  if (!ema || !x) return EHGR_E_NULL;
+  if (n < 0) return EHGR_E_SHAPE;
+  if (!aligned_to(ema, is_int64 ? 8 : 4) || !aligned_to(x, is_int64 ? 8 : 4)) return EHGR_E_ALIGN;
+  if (n == 0) return EHGR_OK;
+  float ed, er;
+  ema_coefs(decay, &ed, &er);
+  const unsigned blocks = static_cast<unsigned>(std::max(1LL, std::min(cdiv(n, 256), 4LL * kNumSMs)));
+  if (is_int64)
+    ema_i64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<long long*>(ema), static_cast<const long long*>(x), ed, er, n);
+  else
+    ema_f32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<float*>(ema), static_cast<const float*>(x), ed, er, n);
   return launch_status();
 }

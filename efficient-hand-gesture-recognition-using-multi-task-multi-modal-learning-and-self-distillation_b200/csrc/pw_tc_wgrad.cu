@@ -23,6 +23,10 @@ constexpr int kWgMmaWarp = 7;
 constexpr int kWgThreads = 256;
 constexpr int kWgMaxStages = 12;
 constexpr int kWgBarBytes = 256;
+constexpr int kWgGroupStride = kMS * 16 + 16;   // bytes between 8-channel groups of a stage: padded by one 16-byte slot so
+                                                // that lanes walking along the groups hit different banks (the
+                                                // unpadded 512-byte stride made every 16-byte access an 8-way conflict)
+constexpr int kWgBudget = 100 * 1024;           // two CTAs per SM: 16 warps instead of 8 hide the copy / transform latency
 
 struct WgradArgs {
   RowOp dy, a;
@@ -31,6 +35,7 @@ struct WgradArgs {
   int K, N;
   int BKc;        // k columns per output tile (multiple of 16, <= 256)
   int k_tiles, n_tiles, splits;
+  int n_tile;     // n rows per output tile (<= 128, multiple of 8): N split EVENLY over the n tiles (144 -> 72 + 72, not 128 + 16)
   long long m_chunks;   // ceil(M / kMS)
   int tmem_cols;
   int n_stages, stage_bytes;
@@ -122,10 +127,10 @@ __device__ __forceinline__ void wg_affine_inplace(const RowOp& op, const WgLane&
 // kAMode: mode of operand a as a compile-time constant (PLAIN / AFFINE / SHIFT: asynchronous path, dy PLAIN);
 // -1: the generic register path.
 template <int kAMode>
-__global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p) {
+__global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p) {
   constexpr bool kAsync = kAMode >= 0;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int gs = kMS * 16;                              // bytes between channel groups inside a stage
+  const int gs = kWgGroupStride;                        // bytes between channel groups inside a stage
   const int dy_bytes = 16 * gs;                         // 128 n = 16 groups
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * p.stage_bytes);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWgMaxStages), bar_done = smem_u32(bars + 2 * kWgMaxStages);
@@ -153,8 +158,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
 
   const int tiles = p.n_tiles * p.k_tiles;
   const int tile = blockIdx.x % tiles, split = blockIdx.x / tiles;
-  const int n0 = (tile / p.k_tiles) * 128, k0 = (tile % p.k_tiles) * p.BKc;
-  const int n_valid = min(128, p.N - n0), k_valid = min(p.BKc, p.K - k0);   // multiples of 8
+  const int n0 = (tile / p.k_tiles) * p.n_tile, k0 = (tile % p.k_tiles) * p.BKc;
+  const int n_valid = min(p.n_tile, p.N - n0), k_valid = min(p.BKc, p.K - k0);   // multiples of 8
   const int ng = n_valid >> 3, kg = k_valid >> 3;
   long long my_chunks = 0;
   if (split < p.m_chunks) my_chunks = (p.m_chunks - split + p.splits - 1) / p.splits;
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_tc_kernel(WgradArgs p)
     for (int cc = 0; cc * 16 < k_valid; ++cc) {
       float v[16];
       tmem_ld16(t_base + cc * 16, v);
-      if (n < p.N) {
+      if (q * 32 + lane < n_valid) {
         float* dst = p.dw + static_cast<size_t>(n) * p.K + k0 + cc * 16;
         // k_valid is a multiple of 8: whole 16-byte groups, one vector reduction each (4x fewer L2 atomics)
 #pragma unroll
@@ -312,14 +317,15 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   p.BKc = tc::pick_bn(K);
   p.k_tiles = (K + p.BKc - 1) / p.BKc;
   p.n_tiles = (N + 127) / 128;
+  p.n_tile = ((N + p.n_tiles - 1) / p.n_tiles + 7) & ~7;
   p.m_chunks = cdiv(M, tc::kMS);
   const int tiles = p.n_tiles * p.k_tiles;
-  p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>(p.m_chunks, kNumSMs / tiles)));
+  p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>(p.m_chunks, 2 * kNumSMs / tiles)));
   int cols = 32;
   while (cols < p.BKc) cols <<= 1;
   p.tmem_cols = cols;
-  constexpr int kBudget = 200 * 1024;
-  p.stage_bytes = (128 + p.BKc) * tc::kMS * 2;
+  constexpr int kBudget = tc::kWgBudget;
+  p.stage_bytes = (16 + p.BKc / 8) * tc::kWgGroupStride;
   p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes) / p.stage_bytes));
   const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes;
   const bool async = dy.mode == EHGR_ROW_PLAIN &&

@@ -116,9 +116,43 @@ class InplaceShift(torch.autograd.Function):
         return g.view(n, t, c, h, w), None
 
 
+class _TemporalPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_segment):
+        _lib.require_cuda(x)
+        nt, c, h, w = x.shape
+        x, _layout = _layout_of(x)                 # frames are contiguous in both layouts: the kernel sees [n, T, c*h*w]
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        n, t_out = nt // n_segment, (n_segment - 1) // 2 + 1
+        out = torch.empty((n * t_out, c, h, w), dtype=x.dtype, device=x.device,
+                          memory_format=torch.channels_last if _layout == _lib.NHWC else torch.contiguous_format)
+        if x.numel():
+            with torch.cuda.device(x.device):
+                _lib.call("ehgr_temporal_pool_fwd", x.data_ptr(), out.data_ptr(), n, n_segment, c * h * w, _lib.dtype_code(x),
+                          _lib.stream_ptr(x.device), algo_bytes=(x.numel() + out.numel()) * x.element_size())
+        ctx.save_for_backward(x)
+        ctx.n_segment = n_segment
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        nt, c, h, w = x.shape
+        g = g.contiguous(memory_format=torch.channels_last) if (x.dim() == 4 and not x.is_contiguous()) else g.contiguous()
+        g = g.to(x.dtype)
+        dx = torch.empty_like(x)
+        if x.numel():
+            with torch.cuda.device(x.device):
+                _lib.call("ehgr_temporal_pool_bwd", x.data_ptr(), g.data_ptr(), dx.data_ptr(), nt // ctx.n_segment, ctx.n_segment,
+                          c * h * w, _lib.dtype_code(x), _lib.stream_ptr(x.device),
+                          algo_bytes=(2 * x.numel() + g.numel()) * x.element_size())
+        return dx, None
+
+
 class TemporalPool(nn.Module):
-    """Temporal max-pool k=3,s=2 between stages (reference models/temporal_shift.py:79-98).
-    Caller-side of the hot path: kept on the library max_pool3d."""
+    """Temporal max-pool k=3,s=2 between stages (reference models/temporal_shift.py:79-98): one kernel over
+    [n, T, c*h*w] (csrc/tpool.cu) instead of view / transpose / max_pool3d / transpose / contiguous."""
 
     def __init__(self, net, n_segment):
         super().__init__()
@@ -132,10 +166,9 @@ class TemporalPool(nn.Module):
     @staticmethod
     def temporal_pool(x, n_segment):
         nt, c, h, w = x.size()
-        n_batch = nt // n_segment
-        x = x.view(n_batch, n_segment, c, h, w).transpose(1, 2)
-        x = F.max_pool3d(x, kernel_size=(3, 1, 1), stride=(2, 1, 1), padding=(1, 0, 0))
-        return x.transpose(1, 2).contiguous().view(nt // 2, c, h, w)
+        if nt % n_segment:
+            raise RuntimeError(f"shape '[{nt // n_segment}, {n_segment}, {c}, {h}, {w}]' is invalid for input of size {x.numel()}")
+        return _TemporalPoolFunction.apply(x, n_segment)
 
 
 def _is_mobilenet_v2(net) -> bool:

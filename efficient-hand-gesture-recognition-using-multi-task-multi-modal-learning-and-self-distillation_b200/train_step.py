@@ -186,15 +186,104 @@ class FlatSGD:
         else:
             self.lr_dev.fill_(float(lr))
 
-    def step(self):
+    def step(self, ema: Optional[torch.Tensor] = None, ema_decay: float = 0.0):
+        """One optimiser step; with ``ema`` (a flat fp32 tensor laid out like ``flat_p``) the EMA of the parameters is
+        updated in the same kernel from the freshly stepped values (FlatEMA)."""
         from . import _lib
         f = self.buckets.flat
         _lib.call("ehgr_sgd_step", self.flat_p.data_ptr(), f.data_ptr(), self.flat_m.data_ptr(), self.code.data_ptr(),
                   self.lr_mult.data_ptr(), self.decay_mult.data_ptr(), len(self.param_groups), self.lr_dev.data_ptr(),
-                  self.momentum, self.weight_decay, f.numel(), _lib.stream_ptr(f.device), algo_bytes=f.numel() * 21)
+                  self.momentum, self.weight_decay, f.numel(), _lib.ptr(ema), float(ema_decay), _lib.stream_ptr(f.device),
+                  algo_bytes=f.numel() * (21 + (8 if ema is not None else 0)))
 
     def zero_grad(self, set_to_none: bool = False):
         self.buckets.zero()
+
+
+class FlatEMA:
+    """The reference's ``EMAWrapper`` (train_mtmm.py:110-140): an exponential moving average of EVERY ``state_dict``
+    entry, updated after each optimiser step (train_mtmm.py:242-245).  Same surface (``update``, ``set``, ``forward``,
+    ``state_dict``, ``load_state_dict``, ``.model``, ``.decay``); instead of one tiny op group per tensor (444 entries
+    for TSM-MobileNetV2 MTMM) the update is three launches:
+      * parameters     — inside ``ehgr_sgd_step`` (``FlatSGD.step(ema=...)``): the EMA copy lives in ``flat`` with the
+                         layout of ``FlatSGD.flat_p`` and the EMA model's parameters are views into it;
+      * float buffers  — BatchNorm running statistics of model and EMA model are moved into two flat tensors (the
+                         modules keep views), one ``ehgr_ema_update`` launch;
+      * int64 counters — ``num_batches_tracked``, likewise (evaluated in fp32 and truncated, as the reference's
+                         ``decay * e + (1. - decay) * m`` followed by ``copy_`` does).
+    Results are bit-identical to the reference expression."""
+
+    def __init__(self, model, opt: "FlatSGD", decay: float = 0.9999):
+        from copy import deepcopy
+        self.decay = float(decay)
+        self.opt = opt
+        self.model = deepcopy(model)
+        for p in self.model.parameters():
+            p.requires_grad_(False)
+        dev = opt.flat_p.device
+        self.flat = opt.flat_p.detach().clone()
+        extra_f = []                                     # (training tensor, ema tensor): float entries outside flat_p
+        for pm, pe in zip(model.parameters(), self.model.parameters()):
+            off = opt.buckets._offset_of.get(id(pm))
+            if off is None:                              # frozen parameter: goes with the buffers
+                extra_f.append((pm, pe))
+            else:
+                pe.data = self.flat[off:off + pm.numel()].view_as(pm)
+        ints = []
+        for bm, be in zip(model.buffers(), self.model.buffers()):
+            (extra_f if bm.is_floating_point() else ints).append((bm, be))
+
+        def flatten(pairs, dtype):
+            n = sum(a.numel() for a, _ in pairs)
+            src, dst = torch.zeros(n, dtype=dtype, device=dev), torch.zeros(n, dtype=dtype, device=dev)
+            off = 0
+            with torch.no_grad():
+                for a, b in pairs:
+                    k = a.numel()
+                    src[off:off + k].copy_(a.detach().reshape(-1).to(dtype))
+                    dst[off:off + k].copy_(b.detach().reshape(-1).to(dtype))
+                    a.data = src[off:off + k].view(a.shape)      # the modules keep views: kernels write running statistics here
+                    b.data = dst[off:off + k].view(b.shape)
+                    off += k
+            return src, dst
+        if any(a.dtype != torch.float32 for a, _ in extra_f) or any(a.dtype != torch.int64 for a, _ in ints):
+            raise TypeError("FlatEMA expects float32 buffers and int64 counters")
+        self.buf_src, self.buf_ema = flatten(extra_f, torch.float32)
+        self.int_src, self.int_ema = flatten(ints, torch.int64)
+
+    # -- the three launches of one update; the parameter part normally rides on the optimiser step ----------
+    def update_buffers(self):
+        from . import _lib
+        sp = _lib.stream_ptr(self.flat.device)
+        if self.buf_src.numel():
+            _lib.call("ehgr_ema_update", self.buf_ema.data_ptr(), self.buf_src.data_ptr(), self.buf_src.numel(), self.decay, 0, sp,
+                      algo_bytes=12 * self.buf_src.numel())
+        if self.int_src.numel():
+            _lib.call("ehgr_ema_update", self.int_ema.data_ptr(), self.int_src.data_ptr(), self.int_src.numel(), self.decay, 1, sp)
+
+    def update(self, model=None):
+        """EMAWrapper.update for callers that step the optimiser themselves (``FlatSGD.step()`` without ``ema``)."""
+        from . import _lib
+        _lib.call("ehgr_ema_update", self.flat.data_ptr(), self.opt.flat_p.data_ptr(), self.flat.numel(), self.decay, 0,
+                  _lib.stream_ptr(self.flat.device), algo_bytes=12 * self.flat.numel())
+        self.update_buffers()
+
+    def set(self, model=None):
+        with torch.no_grad():
+            self.flat.copy_(self.opt.flat_p)
+            self.buf_ema.copy_(self.buf_src)
+            self.int_ema.copy_(self.int_src)
+
+    def forward(self, *args, **kwargs):
+        return self.model(*args, **kwargs)
+
+    __call__ = forward
+
+    def state_dict(self):
+        return self.model.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self.model.load_state_dict(state_dict)       # copy_ into the views: the flat layout is preserved
 
 
 def adjust_learning_rate(learning_rate, optimizer, epoch, lr_steps):
@@ -245,7 +334,7 @@ class MTMMTrainStep:
     """
 
     def __init__(self, model, lr=0.00125, momentum=0.9, weight_decay=5e-4, compute_dtype=torch.bfloat16,
-                 n_buckets=3, process_group=None, use_graph=False, graph_warmup=2):
+                 n_buckets=3, process_group=None, use_graph=False, graph_warmup=2, ema_decay=None):
         from . import fused
         self.model = model
         self.compute_dtype = compute_dtype
@@ -272,6 +361,12 @@ class MTMMTrainStep:
             self._mean_std = (torch.tensor(model.input_mean, dtype=torch.float32, device=self.device),
                               torch.tensor(model.input_std, dtype=torch.float32, device=self.device))
         self.launches_per_step = None      # libehgr_b200 kernel launches of one step (counted while capturing)
+        # model_ema = EMAWrapper(model) of the reference's main() (train_mtmm.py:569), updated after every step (:245)
+        self.ema = None
+        if ema_decay is not None:
+            if not isinstance(self.opt, FlatSGD):
+                raise RuntimeError("the fused EMA needs the CUDA optimiser (FlatSGD)")
+            self.ema = FlatEMA(model, self.opt, ema_decay)
         self.group = process_group
         if self.buckets.world > 1:
             self.sync_initial_state()
@@ -354,8 +449,15 @@ class MTMMTrainStep:
         with self._fused.grad_sink(self.buckets):
             loss.backward()
         self.buckets.finish()
-        self.opt.step()
+        self._optimizer_step()
         return loss.detach()
+
+    def _optimizer_step(self):
+        if self.ema is not None:
+            self.opt.step(self.ema.flat, self.ema.decay)
+            self.ema.update_buffers()
+        else:
+            self.opt.step()
 
     def invalidate_graph(self):
         """Call after anything the captured graph has baked in changes (learning rate, train/eval mode,
@@ -433,7 +535,7 @@ class SDTrainStep(MTMMTrainStep):
         with self._fused.grad_sink(self.buckets):
             total.backward()
         self.buckets.finish()
-        self.opt.step()
+        self._optimizer_step()
         return total.detach()
 
     def __call__(self, rgb_h, labels_h) -> float:

@@ -16,7 +16,9 @@
  *   - dtype: EHGR_F32 / EHGR_BF16 is the STORAGE type of activations; arithmetic is fp32;
  *   - layout: EHGR_NCHW (reference layout) or EHGR_NHWC (channels-last, the layout the fused
  *     block kernels use internally);
- *   - re-entrant and thread-safe: no mutable global state.
+ *   - re-entrant and thread-safe: the only mutable process-wide state is the launch counter (atomic) and two
+ *     mutex-guarded caches (per-kernel dynamic-shared-memory attribute, driver entry point for tensor maps);
+ *     there are no debug switches or other settings that change what a launch computes.
  */
 #ifndef EHGR_B200_H_
 #define EHGR_B200_H_
@@ -193,16 +195,36 @@ int ehgr_normalize_u8(const void* src, void* dst, long long n_planes, int channe
                       const float* mean, const float* stdv, float div, int dst_dtype, ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * N4  TemporalPool.temporal_pool (models/temporal_shift.py:89-98, duplicate models/action.py:165-176): max over the
+ *   frames {2t'-1, 2t', 2t'+1} of a clip, stride 2 (max_pool3d kernel (3,1,1), stride (2,1,1), padding (1,0,0)).
+ *   x: [n, t_in, frame_elems], out: [n, (t_in-1)/2+1, frame_elems]; frame_elems = c*h*w of either layout (16-byte
+ *   vectors when it is a multiple of the vector width, single elements otherwise).  bwd recomputes the first maximum of every window from x (strict '>' scan, as max_pool3d):
+ *   dx[n, t_in, frame_elems] is written in full, no atomics.
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_temporal_pool_fwd(const void* x, void* out, long long n, int t_in, long long frame_elems, int dtype,
+                           ehgr_stream_t stream);
+int ehgr_temporal_pool_bwd(const void* x, const void* g, void* dx, long long n, int t_in, long long frame_elems,
+                           int dtype, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * N1  optimiser step: torch.optim.SGD (momentum, weight decay, dampening 0, no Nesterov) over the policy
  *   groups of get_optim_policies (train_mtmm.py:576-585; lr_mult / decay_mult per group) as one kernel
  *   over flat fp32 buffers:  d = g + wd*decay_mult[k]*p;  buf = momentum*buf + d;  p -= lr*lr_mult[k]*buf.
  *   code: one byte per element = its group k (255 = padding, untouched); n % 4 == 0; buf starts at zero
  *   (reproduces torch's first step).  lr is read from DEVICE memory (float[1]): a learning-rate schedule
  *   (utils.py:39-46) only rewrites that scalar and never invalidates a captured CUDA graph.
+ *   ema (optional, NULL = off): the EMA copy of the parameters, laid out like p; updated in the same pass with the
+ *   freshly stepped parameter, ema = decay*ema + (1-decay)*p — EMAWrapper.update (train_mtmm.py:110-128), which the
+ *   reference calls right after optimizer.step() (train_mtmm.py:242-245).  The expression is evaluated as the reference
+ *   does (two fp32 products and one fp32 sum, scalars rounded to fp32): bit-identical.
+ * ehgr_ema_update: the same update for the other state_dict entries — floating-point buffers (is_int64 = 0: BatchNorm
+ *   running statistics) and the int64 num_batches_tracked counters (is_int64 = 1: evaluated in fp32 and truncated,
+ *   as python_float * int64_tensor followed by copy_() does in the reference).
  * ------------------------------------------------------------------------------------------- */
 int ehgr_sgd_step(float* p, const float* g, float* buf, const void* code, const float* lr_mult,
                   const float* decay_mult, int n_groups, const float* lr_dev, float momentum, float weight_decay,
-                  long long n, ehgr_stream_t stream);
+                  long long n, float* ema, double ema_decay, ehgr_stream_t stream);
+int ehgr_ema_update(void* ema, const void* x, long long n, double decay, int is_int64, ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K10  classifier head: x.mean(3).mean(2) (archs/mobilenet_v2.py:112), new_fc and the segment

@@ -449,3 +449,35 @@ def test_train_step_uint8_batch_equals_normalised_float_batch():
         step = E.train_step.MTMMTrainStep(model, lr=1e-4, compute_dtype=torch.float32)
         losses.append(float(step.run(*(t.cuda() for t in batch)).item()))
     assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[1]), losses
+
+
+def test_flat_ema_follows_the_reference_emawrapper_bit_exact():
+    """MTMMTrainStep(ema_decay=...) keeps `model_ema` the way the reference's train loop does (EMAWrapper.update after
+    every optimizer.step(), train_mtmm.py:242-245) with the parameter part folded into the SGD kernel.  The yardstick is
+    the oracle's ema_update (pinned bit-exact to the reference class in tests/test_oracle_golden.py) applied to the
+    model's state_dict after every step."""
+    import ehgr_b200 as E
+    sd0 = O.build_mtmm_state(83, "tsm", 8, seed=31)
+    with _quiet():
+        model = E.tsn_mtmm.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                               dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                               modal='rgb_depth', temporal_module='tsm')
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    step = E.train_step.MTMMTrainStep(model, lr=1e-2, compute_dtype=torch.float32, ema_decay=0.9)
+    ema_ref = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert set(step.ema.state_dict().keys()) == set(ema_ref.keys())
+    for i in range(3):
+        batch = tuple(t.cuda() for t in O.synthetic_clip_batch(2, 8, 64, 83, seed=50 + i))
+        step.run(*batch)
+        O.ema_update(ema_ref, model.state_dict(), 0.9)
+    got = step.ema.state_dict()
+    moved = 0
+    for k, v in got.items():
+        assert v.dtype == ema_ref[k].dtype and torch.equal(v, ema_ref[k]), k
+        moved += int(not torch.equal(v, sd0[k].to(v.device)))
+    assert moved > 300                                  # parameters, running statistics and counters all moved
+    # the EMA model is a working module: same forward entry as the reference wrapper
+    with torch.no_grad():
+        out = step.ema(batch[0])
+    assert out[0].shape == (2, 83)

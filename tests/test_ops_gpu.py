@@ -562,3 +562,54 @@ def test_normalize_u8_bit_exact(shape):
     assert torch.equal(got.cpu(), want)
     got16 = E.train_step.normalize_u8(x.cuda(), mean, std, out_dtype=torch.bfloat16)
     assert torch.equal(got16.cpu(), want.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: TemporalPool kernel, EMA kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tp_a", "tp_b", "tp_c"])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_temporal_pool_matches_reference_fixture_bit_exact(name, layout):
+    """TemporalPool.temporal_pool (models/temporal_shift.py:89-98) forward and backward against the fixture produced by
+    the live reference (tests/golden/ema_pool.npz); the upstream gradient of the fixture is 0.5 + y."""
+    E = _E()
+    z = np.load(GOLDEN / "ema_pool.npz")
+    nt, c, h, T = (int(v) for v in z[name + "_meta"])
+    x = torch.from_numpy(z[name + "_x"]).cuda()
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y = E.TemporalPool.temporal_pool(x, T)
+    want = torch.from_numpy(z[name + "_y"])
+    assert tuple(y.shape) == tuple(want.shape) and torch.equal(y.cpu(), want)
+    y.backward(0.5 + y.detach())
+    assert torch.equal(x.grad.cpu(), torch.from_numpy(z[name + "_gx"]))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_temporal_pool_vector_path_against_torch(dtype):
+    E = _E()
+    g0 = torch.Generator().manual_seed(5)
+    x = torch.randn(16, 32, 7, 7, generator=g0).to(dtype).cuda().requires_grad_(True)
+    y = E.TemporalPool.temporal_pool(x, 8)
+    xr = x.detach().float().clone().requires_grad_(True)
+    yr = torch.nn.functional.max_pool3d(xr.view(2, 8, 32, 7, 7).transpose(1, 2), (3, 1, 1), (2, 1, 1), (1, 0, 0)).transpose(1, 2).reshape(8, 32, 7, 7)
+    assert torch.equal(y.float(), yr)
+    gup = torch.randn(8, 32, 7, 7, generator=g0).to(dtype).cuda()
+    y.backward(gup)
+    yr.backward(gup.float())
+    assert rel_err(x.grad.float(), xr.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+def test_ema_kernels_replay_the_reference_fixture_bit_exact():
+    """ehgr_ema_update (float buffers and int64 counters) on the states recorded from the reference EMAWrapper
+    (train_mtmm.py:110-128; tests/golden/ema_pool.npz): three updates at decay 0.9, every entry bit-identical."""
+    z = np.load(GOLDEN / "ema_pool.npz")
+    keys = [k[len("ema_init_"):] for k in z.files if k.startswith("ema_init_")]
+    for k in keys:
+        ema = torch.from_numpy(z["ema_init_" + k].copy()).cuda().reshape(-1)
+        is_int = ema.dtype == torch.int64
+        for step in range(3):
+            m = torch.from_numpy(z[f"ema_model{step}_{k}"]).cuda().reshape(-1)
+            _call("ehgr_ema_update", ema.data_ptr(), m.data_ptr(), ema.numel(), 0.9, int(is_int), _sp())
+        assert torch.equal(ema.cpu(), torch.from_numpy(z["ema_final_" + k]).reshape(-1)), k
