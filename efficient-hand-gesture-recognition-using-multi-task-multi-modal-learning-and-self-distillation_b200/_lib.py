@@ -102,8 +102,24 @@ class ActionArgs(ctypes.Structure):
                     "d_p3_expand")])
 
 
+class BnFin(ctypes.Structure):
+    """struct ehgr_bnfin (include/ehgr_b200.h): BatchNorm finalisation run by the last CTA of the producing kernel."""
+    _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p),
+                ("scale", c_void_p), ("shift", c_void_p), ("mean", c_void_p), ("invstd", c_void_p), ("counter", c_void_p),
+                ("count", c_longlong), ("momentum", c_float), ("eps", c_float), ("training", ctypes.c_int32)]
+
+
+class BnBwd(ctypes.Structure):
+    """struct ehgr_bnbwd: BatchNorm-backward coefficients computed by the last CTA of the reduction."""
+    _fields_ = [("gamma", c_void_p), ("mean", c_void_p), ("invstd", c_void_p), ("ca", c_void_p), ("cb", c_void_p),
+                ("cc", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p), ("counter", c_void_p), ("count", c_longlong),
+                ("training", ctypes.c_int32)]
+
+
 _L = c_longlong
 _R = ctypes.POINTER(RowOp)
+_BF = ctypes.POINTER(BnFin)
+_BB = ctypes.POINTER(BnBwd)
 _A = ctypes.POINTER(ActionArgs)
 
 # name -> argtypes for every int-returning symbol of include/ehgr_b200.h
@@ -113,19 +129,23 @@ SIGNATURES = {
     "ehgr_temporal_shift_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_pw_gemm": [_R, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_pw_gemm_w16": [_R, _P, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_pw_gemm_bn": [_R, _P, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _BF, _P],
     "ehgr_pw_wgrad": [_R, _R, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_dw_fwd": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_dw_fwd_bn": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _BF, _P],
     "ehgr_dw_dgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_dw_wgrad": [_R, _R, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_dw_bwd": [_R, _R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_stem_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "ehgr_stem_fwd_bn": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _BF, _P],
     "ehgr_stem_wgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_bn_finalize": [_P, _L, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P],
     "ehgr_bn_bwd_reduce": [_P, _P, _P, _P, _I, _P, _L, _I, _I, _P],
     "ehgr_bn_bwd_finalize": [_P, _L, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P],
+    "ehgr_bn_bwd_reduce_fin": [_P, _P, _P, _P, _I, _P, _L, _I, _I, _BB, _P],
     "ehgr_row_apply": [_R, _P, _P, _L, _I, _I, _P],
     "ehgr_normalize_u8": [_P, _P, _L, _I, _L, _P, _P, _F, _I, _P],
-    "ehgr_sgd_step": [_P, _P, _P, _P, _P, _P, _I, _P, _F, _F, _L, _P, _D, _P],
+    "ehgr_sgd_step": [_P, _P, _P, _P, _P, _P, _I, _P, _F, _F, _L, _P, _D, _P, _P],
     "ehgr_ema_update": [_P, _P, _L, _D, _I, _P],
     "ehgr_temporal_pool_fwd": [_P, _P, _L, _I, _L, _I, _P],
     "ehgr_temporal_pool_bwd": [_P, _P, _P, _L, _I, _L, _I, _P],

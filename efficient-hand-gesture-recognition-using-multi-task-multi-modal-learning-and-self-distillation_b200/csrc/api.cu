@@ -1,5 +1,5 @@
 // api.cu — library-level entry points of libehgr_b200.so (version, status text, launch counter).
-#include "common.cuh"
+#include "bnfin.cuh"
 
 #include <cuda.h>
 
@@ -18,6 +18,13 @@ void ensure_dyn_smem(const void* func, int bytes) {
   if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess) cur = bytes;
 }
 }
+
+namespace ehgr {
+FinSlot& fin_slot() {
+  static thread_local FinSlot slot;
+  return slot;
+}
+}  // namespace ehgr
 
 namespace ehgr {
 namespace tma {

@@ -11,8 +11,19 @@
 #include <type_traits>
 
 #include "rowop.cuh"
+#include "bnfin.cuh"
 
 namespace ehgr {
+
+__global__ void bn_finalize_fin_kernel(BnFin f, const double* __restrict__ stats, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) bn_finalize_channel(f, stats, c, C);
+}
+
+int bn_finalize_standalone(const BnFin& f, const double* stats, int c, cudaStream_t s) {
+  bn_finalize_fin_kernel<<<static_cast<unsigned>(cdiv(c, 128)), 128, 0, s>>>(f, stats, c);
+  return launch_status();
+}
 
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean,
@@ -50,7 +61,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, double coun
 template <typename T, bool relu6>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const float* __restrict__ scale,
-                     const float* __restrict__ shift, double* __restrict__ sums, long long M, int C) {
+                     const float* __restrict__ shift, double* __restrict__ sums, long long M, int C, BnBwd fin, float hi) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ float smem[];  // [2C]
   const int nthreads = blockDim.x * blockDim.y;
@@ -88,8 +99,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const f
             const float2 rr = bf2_to_f2(rw[k]);
             if (relu6) {
               const float2 z = __ffma2_rn(rr, make_float2(s[2 * k], s[2 * k + 1]), make_float2(b[2 * k], b[2 * k + 1]));
-              if (!(z.x > 0.f && z.x < 6.f)) gg.x = 0.f;
-              if (!(z.y > 0.f && z.y < 6.f)) gg.y = 0.f;
+              if (!(z.x > 0.f && z.x < hi)) gg.x = 0.f;
+              if (!(z.y > 0.f && z.y < hi)) gg.y = 0.f;
             }
             const float2 n1 = __fadd2_rn(make_float2(a1[2 * k], a1[2 * k + 1]), gg);
             const float2 n2 = __ffma2_rn(gg, rr, make_float2(a2[2 * k], a2[2 * k + 1]));
@@ -106,7 +117,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const f
           float gg = gv[i];
           if (relu6) {
             const float z = fmaf(rv[i], s[i], b[i]);
-            if (!(z > 0.f && z < 6.f)) gg = 0.f;
+            if (!(z > 0.f && z < hi)) gg = 0.f;
           }
           a1[i] += gg;
           a2[i] = fmaf(gg, rv[i], a2[i]);
@@ -118,6 +129,18 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const f
   }
   __syncthreads();
   for (int i = tid; i < 2 * C; i += nthreads) atomicAdd(&sums[i], static_cast<double>(smem[i]));
+  if (fin.counter) {                                       // 2-D block: the helper's thread 0 / stride are 1-D
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int c = tid; c < C; c += nthreads) bn_bwd_finalize_channel(fin, sums, c, C);
+      if (tid == 0) *fin.counter = 0u;
+    }
+  }
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
@@ -217,7 +240,19 @@ extern "C" int ehgr_bn_finalize(const double* stats, long long count, const floa
 
 extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* scale, const float* shift,
                                   int relu6, double* sums, long long m, int c, int dtype, ehgr_stream_t stream) {
+  return ehgr_bn_bwd_reduce_fin(g, raw, scale, shift, relu6, sums, m, c, dtype, nullptr, stream);
+}
+
+extern "C" int ehgr_bn_bwd_reduce_fin(const void* g, const void* raw, const float* scale, const float* shift,
+                                      int relu6, double* sums, long long m, int c, int dtype, const ehgr_bnbwd* fin,
+                                      ehgr_stream_t stream) {
   const int es = esize_of(dtype);
+  BnBwd f{};
+  if (fin) {
+    f = *fin;
+    if (!f.mean || !f.invstd || !f.ca || !f.cb || !f.cc || !f.counter) return EHGR_E_NULL;
+    if (f.count <= 0) return EHGR_E_SHAPE;
+  }
   if (es == 0) return EHGR_E_DTYPE;
   if (!g || !raw || !sums || (relu6 && (!scale || !shift))) return EHGR_E_NULL;
   const int V = 16 / es;
@@ -236,7 +271,7 @@ extern "C" int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* s
   auto go = [&](auto tag, auto rtag) {
     using T = decltype(tag);
     bn_bwd_reduce_kernel<T, decltype(rtag)::value><<<static_cast<unsigned>(blocks), block, smem, s>>>(
-        static_cast<const T*>(g), static_cast<const T*>(raw), scale, shift, sums, m, c);
+        static_cast<const T*>(g), static_cast<const T*>(raw), scale, shift, sums, m, c, f, relu6 == 2 ? INFINITY : 6.f);
   };
   if (dtype == EHGR_F32) {
     if (relu6) go(float{}, std::true_type{}); else go(float{}, std::false_type{});

@@ -13,6 +13,7 @@
 // pixel instead of nine.  Channels are innermost: every warp access is a run of full 16-byte vectors;
 // the 3x3 re-use is served by L1/L2.
 #include "rowop.cuh"
+#include "bnfin.cuh"
 
 namespace ehgr {
 
@@ -286,6 +287,16 @@ using namespace ehgr;
 
 extern "C" int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, double* stats, int nt, int h, int wd,
                            int c, int stride, int dtype, ehgr_stream_t stream) {
+  return ehgr_dw_fwd_bn(a, w, out, stats, nt, h, wd, c, stride, dtype, nullptr, stream);
+}
+
+extern "C" int ehgr_dw_fwd_bn(const ehgr_rowop* a, const float* w, void* out, double* stats, int nt, int h, int wd,
+                              int c, int stride, int dtype, const ehgr_bnfin* fin, ehgr_stream_t stream) {
+  if (fin) {
+    if (!fin->scale || !fin->shift || !fin->counter) return EHGR_E_NULL;
+    if (fin->training && (!stats || fin->count <= 0)) return EHGR_E_NULL;
+    if (!fin->training && (!fin->running_mean || !fin->running_var)) return EHGR_E_NULL;
+  }
   DwGeom g;
   if (int st = dw_geom(g, nt, h, wd, c, stride, dtype)) return st;
   if (!w || !out) return EHGR_E_NULL;
@@ -293,7 +304,9 @@ extern "C" int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, doubl
   if (!aligned_to(out, 16)) return EHGR_E_ALIGN;
   if (g.n_out == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);
-  return dw_fwd_tiled(*a, w, out, stats, nt, h, wd, c, stride, dtype, s);   // shared-memory-tiled kernel (dw_tiled.cu)
+  fin_slot().fin = fin;            // the bf16 TMA kernel finalises in its last CTA; the fp32 kernels leave it parked
+  const int st = dw_fwd_tiled(*a, w, out, stats, nt, h, wd, c, stride, dtype, s);   // shared-memory-tiled kernel (dw_tiled.cu)
+  return finish_fin(stats, c, s, st);
 }
 
 extern "C" int ehgr_dw_dgrad(const ehgr_rowop* dy, const float* w, void* da, int nt, int h, int wd, int c,

@@ -16,6 +16,7 @@
 //   CVN = 8  (64 channels / chunk), 16 columns of threads, output tile 14 wide   (maps >= 14 wide)
 //   CVN = 16 (128 channels / chunk), 8 columns of threads, output tile  7 wide   (7x7 maps, 14 -> 7)
 #include "tma.cuh"
+#include "bnfin.cuh"
 
 namespace ehgr {
 
@@ -142,7 +143,7 @@ __device__ __forceinline__ void conv_sweep(uint32_t tile, int cv, int ox, const 
 template <int STRIDE, int CVN, int TW, int TH>
 __global__ void __launch_bounds__(128, 3)
 dw_fwd_sw_kernel(RowOp a, const __grid_constant__ CUtensorMap tm_a, const float* __restrict__ wgt,
-                 __nv_bfloat16* __restrict__ out, double* __restrict__ stats, DwSw g) {
+                 __nv_bfloat16* __restrict__ out, double* __restrict__ stats, DwSw g, BnFin fin) {
   using Cfg = DwCfg<STRIDE, CVN, TW, TH>;
   using Ld = RowLoader<__nv_bfloat16, 8, false, false>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -259,6 +260,7 @@ dw_fwd_sw_kernel(RowOp a, const __grid_constant__ CUtensorMap tm_a, const float*
       }
     }
   }
+  bn_finalize_if_last(fin, stats, g.c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -482,7 +484,7 @@ static int dw_fwd_sw_go(const RowOp& a, const float* w, void* out, double* stats
   auto kern = dw_fwd_sw_kernel<STRIDE, CVN, TW, TH>;
   ensure_smem(kern, static_cast<int>(smem));
   const int per_sm = std::max(1, std::min(3, static_cast<int>((220 * 1024) / (smem + 1024))));
-  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(a, tm_a, w, static_cast<__nv_bfloat16*>(out), stats, g);
+  kern<<<dw_sw_grid(g, per_sm), 128, smem, s>>>(a, tm_a, w, static_cast<__nv_bfloat16*>(out), stats, g, take_fin());
   return launch_status();
 }
 

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, const uint8_t* __restrict__ code,
                 const float* __restrict__ lr_mult, const float* __restrict__ decay_mult, int n_groups,
                 const float* __restrict__ lr_dev, float momentum, float weight_decay, long long n,
-                float* __restrict__ ema, float ema_decay, float ema_rest) {
+                float* __restrict__ ema, float ema_decay, float ema_rest, __nv_bfloat16* __restrict__ p16) {
   __shared__ float s_lr[64], s_wd[64];
   const float lr = *lr_dev;
   for (int i = threadIdx.x; i < n_groups; i += blockDim.x) {
@@ -46,6 +46,10 @@ sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     }
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(buf)[i] = bv;
+    if (p16) {                                               // bf16 mirror of the parameters for the tensor-core kernels
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(pp[0], pp[1]), hi = __floats2bfloat162_rn(pp[2], pp[3]);
+      reinterpret_cast<uint2*>(p16)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
     if (ema) {                                               // padding elements: 0 stays 0
       float4 ev = reinterpret_cast<float4*>(ema)[i];
       float* ep = reinterpret_cast<float*>(&ev);
@@ -83,17 +87,19 @@ static void ema_coefs(double decay, float* d, float* rest) {
 
 extern "C" int ehgr_sgd_step(float* p, const float* g, float* buf, const void* code, const float* lr_mult,
                              const float* decay_mult, int n_groups, const float* lr_dev, float momentum, float weight_decay,
-                             long long n, float* ema, double ema_decay, ehgr_stream_t stream) {
+                             long long n, float* ema, double ema_decay, void* p16, ehgr_stream_t stream) {
   if (!p || !g || !buf || !code || !lr_mult || !decay_mult || !lr_dev) return EHGR_E_NULL;
   if (n < 0 || (n % 4) || n_groups <= 0 || n_groups > 64) return EHGR_E_SHAPE;
-  if (!aligned_to(p, 16) || !aligned_to(g, 16) || !aligned_to(buf, 16) || !aligned_to(code, 4) || (ema && !aligned_to(ema, 16)))
+  if (!aligned_to(p, 16) || !aligned_to(g, 16) || !aligned_to(buf, 16) || !aligned_to(code, 4) || (ema && !aligned_to(ema, 16)) ||
+      (p16 && !aligned_to(p16, 8)))
     return EHGR_E_ALIGN;
   float ed = 0.f, er = 0.f;
   ema_coefs(ema_decay, &ed, &er);
   if (n == 0) return EHGR_OK;
   const unsigned blocks = static_cast<unsigned>(std::max(1LL, std::min(cdiv(n / 4, 256), 8LL * kNumSMs)));
   sgd_step_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, buf, static_cast<const uint8_t*>(code), lr_mult, decay_mult,
-                                                          n_groups, lr_dev, momentum, weight_decay, n, ema, ed, er);
+                                                          n_groups, lr_dev, momentum, weight_decay, n, ema, ed, er,
+                                                          static_cast<__nv_bfloat16*>(p16));
   return launch_status();
 }
 

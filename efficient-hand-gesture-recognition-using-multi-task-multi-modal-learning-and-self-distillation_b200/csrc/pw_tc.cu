@@ -39,6 +39,7 @@
 #include <type_traits>
 
 #include "tc_common.cuh"
+#include "bnfin.cuh"
 
 namespace ehgr {
 namespace tc {
@@ -78,6 +79,7 @@ struct GemmArgs {
   int a_bytes;     // bytes of the A part of a stage = 128 * min(Kp,64) * 2
   int stage_bytes; // a_bytes (+ BN*128 when B is streamed)
   int epi_pitch;   // bytes between the 32 staging rows of an epilogue warp (odd multiple of 16)
+  BnFin fin;       // BatchNorm finalisation by the last CTA (fin.counter == NULL: none)
 };
 
 // B tile -> shared memory in core-matrix layout: group stride `gs` bytes, k-group stride 128.
@@ -582,6 +584,7 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
     __syncwarp();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+  bn_finalize_if_last(p.fin, p.stats, p.N);      // every epilogue warp's statistics atomics precede the barrier above
 }
 
 }  // namespace tc
@@ -602,6 +605,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   p.out = static_cast<__nv_bfloat16*>(out);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
   p.stats = stats;
+  p.fin = take_fin();
   p.M = M; p.K = K; p.N = N;
   p.m_tiles = static_cast<int>(cdiv(M, tc::BM));
   p.n_bufs = 2;   // more buffers bought nothing (the hand-shake is not the bound) and a 512-column allocation

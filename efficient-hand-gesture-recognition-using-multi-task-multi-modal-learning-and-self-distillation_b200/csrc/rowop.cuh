@@ -93,6 +93,11 @@ __device__ __forceinline__ uint32_t bf2_min6(uint32_t w) {
   asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(w), "r"(0x40C040C0u));   // 6.0 is exact in bf16
   return d;
 }
+// The `relu6` field of a row operand is an activation code: 0 none, 1 ReLU6 (MobileNetV2), 2 plain ReLU (the SepConv
+// exit heads and the depth decoder, models/models_SD.py:81-101, models/models_MTMM.py:129-155).  Everything that
+// clamps or masks uses the upper bound relu_hi(): 6 or +infinity.
+__device__ __forceinline__ float relu_hi(int act) { return act == 2 ? INFINITY : 6.f; }
+__device__ __forceinline__ uint32_t bf2_min_hi(uint32_t w, int act) { return act == 2 ? w : bf2_min6(w); }
 
 template <>
 __device__ __forceinline__ void store_vec<__nv_bfloat16, 4>(__nv_bfloat16* __restrict__ p, const float (&v)[4]) {
@@ -130,7 +135,7 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float z = fmaf(v[i], s[i], b[i]);
-      if (op.relu6) z = fminf(fmaxf(z, 0.f), 6.f);
+      if (op.relu6) z = fminf(fmaxf(z, 0.f), relu_hi(op.relu6));
       v[i] = z;
     }
   } else if (op.mode == EHGR_ROW_SHIFT) {
@@ -189,7 +194,7 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const float z = fmaf(r[i], s[i], b[i]);
-        if (!(z > 0.f && z < 6.f)) g[i] = 0.f;
+        if (!(z > 0.f && z < relu_hi(op.relu6))) g[i] = 0.f;
       }
     }
 #pragma unroll
@@ -244,7 +249,7 @@ struct RowLoader {
       load_vec<T, NV>(in1 + off, v);
       if (op.relu6) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(fmaf(v[i], s[i], b[i]), 0.f), 6.f);
+        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(fmaf(v[i], s[i], b[i]), 0.f), relu_hi(op.relu6));
       } else {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
@@ -257,7 +262,7 @@ struct RowLoader {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const float z = fmaf(r[i], s[i], b[i]);
-          if (!(z > 0.f && z < 6.f)) g[i] = 0.f;
+          if (!(z > 0.f && z < relu_hi(op.relu6))) g[i] = 0.f;
         }
       }
 #pragma unroll
@@ -323,7 +328,7 @@ struct RowLoader {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float2 z = __ffma2_rn(bf2_to_f2(w[i]), make_float2(s[2 * i], s[2 * i + 1]), make_float2(b[2 * i], b[2 * i + 1]));
-        o[i] = op.relu6 ? bf2_min6(f2_to_bf2_relu(z)) : pack_bf16x2(z.x, z.y);
+        o[i] = op.relu6 ? bf2_min_hi(f2_to_bf2_relu(z), op.relu6) : pack_bf16x2(z.x, z.y);
       }
       return make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -335,8 +340,9 @@ struct RowLoader {
         const float2 raw = bf2_to_f2(rw[i]);
         if (op.relu6) {
           const float2 z = __ffma2_rn(raw, make_float2(s[2 * i], s[2 * i + 1]), make_float2(b[2 * i], b[2 * i + 1]));
-          if (!(z.x > 0.f && z.x < 6.f)) g.x = 0.f;
-          if (!(z.y > 0.f && z.y < 6.f)) g.y = 0.f;
+          const float hi = relu_hi(op.relu6);
+          if (!(z.x > 0.f && z.x < hi)) g.x = 0.f;
+          if (!(z.y > 0.f && z.y < hi)) g.y = 0.f;
         }
         const int j = kTwo ? 2 * i : 0;
         const float2 t = __ffma2_rn(make_float2(cb[j], cb[kTwo ? j + 1 : 0]), raw, make_float2(cc[j], cc[kTwo ? j + 1 : 0]));
@@ -357,7 +363,7 @@ struct RowLoader {
     if (op.mode == EHGR_ROW_AFFINE) {
       if (op.relu6) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(fmaf(v[i], s[i], b[i]), 0.f), 6.f);
+        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(fmaf(v[i], s[i], b[i]), 0.f), relu_hi(op.relu6));
       } else {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = fmaf(v[i], s[i], b[i]);
@@ -378,7 +384,7 @@ struct RowLoader {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const float z = fmaf(raw[i], s[i], b[i]);
-          if (!(z > 0.f && z < 6.f)) v[i] = 0.f;
+          if (!(z > 0.f && z < relu_hi(op.relu6))) v[i] = 0.f;
         }
       }
 #pragma unroll

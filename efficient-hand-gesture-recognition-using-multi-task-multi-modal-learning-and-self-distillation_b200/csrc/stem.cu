@@ -3,6 +3,7 @@
 // activation + batch statistics the fused chain works on; and its weight gradient.
 // Reference: conv_bn(3, 32, 2), archs/mobilenet_v2.py:7-12,90.
 #include "tma.cuh"
+#include "bnfin.cuh"
 
 namespace ehgr {
 
@@ -301,7 +302,7 @@ __device__ __forceinline__ float lds_x<__nv_bfloat16>(const __nv_bfloat16* p) { 
 template <typename X, typename T, int R>
 __global__ void __launch_bounds__(128, 2)
 stem_fwd32_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ wgt, T* __restrict__ out,
-                      double* __restrict__ stats, StemGeom g, int bands, int bw, int tile_bytes) {
+                      double* __restrict__ stats, StemGeom g, int bands, int bw, int tile_bytes, BnFin fin) {
   constexpr int NR = 2 * R + 1;
   constexpr int kPad = 16 / static_cast<int>(sizeof(X));      // elements in 16 bytes
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -405,6 +406,7 @@ stem_fwd32_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
     __syncthreads();
     if (tid < 2 * kStemC) atomicAdd(&stats[tid], static_cast<double>(s_stat[tid]));
   }
+  bn_finalize_if_last(fin, stats, kStemC);
 }
 
 // Weight gradient.  12 warps = 4 channel groups (8 output channels) x 3 input planes; a warp keeps its
@@ -648,7 +650,7 @@ static bool stem_fwd32_tma_go(const void* x, const float* w, void* out, double* 
   ensure_smem(stem_fwd32_tma_kernel<X, T, R>, smem);
   const long long items = static_cast<long long>(g.nt) * bands;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(items, 3LL * kNumSMs));
-  stem_fwd32_tma_kernel<X, T, R><<<grid, 128, smem, s>>>(tm, w, static_cast<T*>(out), stats, g, bands, bw, tile_bytes);
+  stem_fwd32_tma_kernel<X, T, R><<<grid, 128, smem, s>>>(tm, w, static_cast<T*>(out), stats, g, bands, bw, tile_bytes, take_fin());
   return true;
 }
 
@@ -729,6 +731,16 @@ using namespace ehgr;
 
 extern "C" int ehgr_stem_fwd(const void* x, const float* w, void* out, double* stats, int nt, int h, int wd,
                              int cout, int x_dtype, int dtype, ehgr_stream_t stream) {
+  return ehgr_stem_fwd_bn(x, w, out, stats, nt, h, wd, cout, x_dtype, dtype, nullptr, stream);
+}
+
+extern "C" int ehgr_stem_fwd_bn(const void* x, const float* w, void* out, double* stats, int nt, int h, int wd,
+                                int cout, int x_dtype, int dtype, const ehgr_bnfin* fin, ehgr_stream_t stream) {
+  if (fin) {
+    if (!fin->scale || !fin->shift || !fin->counter) return EHGR_E_NULL;
+    if (fin->training && (!stats || fin->count <= 0)) return EHGR_E_NULL;
+    if (!fin->training && (!fin->running_mean || !fin->running_var)) return EHGR_E_NULL;
+  }
   StemGeom g;
   if (esize_of(x_dtype) == 0 || esize_of(dtype) == 0) return EHGR_E_DTYPE;
   if (!x || !w || !out) return EHGR_E_NULL;
@@ -736,8 +748,10 @@ extern "C" int ehgr_stem_fwd(const void* x, const float* w, void* out, double* s
   if (!aligned_to(out, 16) || !aligned_to(x, esize_of(x_dtype))) return EHGR_E_ALIGN;
   if (g.n_out == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);
-  return x_dtype == EHGR_F32 ? stem_fwd_launch<float>(x, w, out, stats, g, dtype, s)
-                             : stem_fwd_launch<__nv_bfloat16>(x, w, out, stats, g, dtype, s);
+  fin_slot().fin = fin;            // the TMA band kernel finalises in its last CTA; the other variants leave it parked
+  const int st = x_dtype == EHGR_F32 ? stem_fwd_launch<float>(x, w, out, stats, g, dtype, s)
+                                     : stem_fwd_launch<__nv_bfloat16>(x, w, out, stats, g, dtype, s);
+  return finish_fin(stats, cout, s, st);
 }
 
 extern "C" int ehgr_stem_wgrad(const ehgr_rowop* dy, const void* x, float* dw, int nt, int h, int wd, int cout,

@@ -12,11 +12,11 @@ namespace ehgr {
 // 16-byte vectors when a frame is a whole number of them, single elements otherwise (V = 1)
 template <typename T, int V>
 __device__ __forceinline__ void ldv(const T* __restrict__ p, float (&v)[V]) {
-  if constexpr (V == 1) v[0] = static_cast<float>(*p); else ldv<T, V>(p, v);
+  if constexpr (V == 1) v[0] = static_cast<float>(*p); else load_vec<T, V>(p, v);
 }
 template <typename T, int V>
 __device__ __forceinline__ void stv(T* __restrict__ p, const float (&v)[V]) {
-  if constexpr (V == 1) *p = static_cast<T>(v[0]); else stv<T, V>(p, v);
+  if constexpr (V == 1) *p = static_cast<T>(v[0]); else store_vec<T, V>(p, v);
 }
 
 template <typename T, int V>

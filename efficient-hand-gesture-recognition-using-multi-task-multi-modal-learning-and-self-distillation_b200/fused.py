@@ -25,9 +25,21 @@ import torch
 import torch.nn as nn
 
 from . import _lib, action_ops
-from ._lib import RowOp
+from ._lib import BnBwd, BnFin, RowOp
 
-_STATE = {"dtype": torch.float32, "engine": 0, "grad_sink": None}
+_STATE = {"dtype": torch.float32, "engine": 0, "grad_sink": None, "mirrors": None}
+
+
+@contextlib.contextmanager
+def weight_mirrors(provider):
+    """While active, ``provider.mirror_for(weight)`` supplies the bf16 mirror of a pointwise-conv weight (or None) —
+    train_step.FlatSGD keeps one flat mirror current inside its SGD kernel, so no per-layer cast runs."""
+    old = _STATE["mirrors"]
+    _STATE["mirrors"] = provider
+    try:
+        yield
+    finally:
+        _STATE["mirrors"] = old
 
 
 @contextlib.contextmanager
@@ -90,7 +102,10 @@ def _bf16_mirror(w, storage_dtype, cache=None):
         return None
     if cache is not None and id(w) in cache:
         return cache[id(w)]
-    m = w.detach().to(torch.bfloat16)
+    prov = _STATE["mirrors"]
+    m = prov.mirror_for(w) if prov is not None else None
+    if m is None:
+        m = w.detach().to(torch.bfloat16)
     if cache is not None:
         cache[id(w)] = m
     return m
@@ -139,14 +154,14 @@ def _as_nhwc(x, dtype):
 class Stage:
     kind: str                      # 'stem' | 'pw' | 'dw'
     conv: nn.Conv2d
-    bn: nn.BatchNorm2d
-    relu6: bool
+    bn: Optional[nn.BatchNorm2d]   # None: a bare convolution (the depthwise halves of SepConv, models/models_SD.py:81-101)
+    relu6: int                     # activation code after the BatchNorm: 0 none, 1 ReLU6, 2 ReLU
     stride: int = 1
     shift: Optional[Tuple[int, int]] = None   # (n_segment, fold) — TemporalShift on the input (pw only)
     action: Optional[nn.Module] = None        # Action module wrapping this conv (pw only, first stage of a unit)
 
     def n_params(self) -> int:
-        return 3 + (10 if self.action is not None else 0)
+        return (3 if self.bn is not None else 1) + (10 if self.action is not None else 0)
 
 
 @dataclass
@@ -158,10 +173,19 @@ class Unit:
 
 def _conv_bn_stage(kind, conv, bn, relu6, shift=None):
     if conv.bias is not None:
-        raise NotImplementedError("fused chain expects bias-free convolutions followed by BatchNorm")
-    if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+        raise NotImplementedError("fused chain expects bias-free convolutions")
+    if bn is not None and (bn.momentum is None or not bn.track_running_stats or not bn.affine):
         raise NotImplementedError("fused chain expects the default nn.BatchNorm2d configuration")
-    return Stage(kind, conv, bn, relu6, conv.stride[0], shift)
+    return Stage(kind, conv, bn, int(relu6), conv.stride[0], shift)
+
+
+def unit_of_sepconv(m) -> "Unit":
+    """SepConv (models/models_SD.py:81-101): dw3x3(stride) -> pw -> BN -> ReLU -> dw3x3 -> pw -> BN -> ReLU as four
+    stages of the fused chain — the depthwise halves are bare convolutions (their raw output is the PLAIN operand of
+    the pointwise GEMM), the activations are plain ReLU (activation code 2)."""
+    op = m.op
+    return Unit([_conv_bn_stage('dw', op[0], None, 0), _conv_bn_stage('pw', op[1], op[2], 2),
+                 _conv_bn_stage('dw', op[4], None, 0), _conv_bn_stage('pw', op[5], op[6], 2)])
 
 
 def unit_of_block(block) -> Unit:
@@ -179,11 +203,11 @@ def unit_of_block(block) -> Unit:
         action = None
         if isinstance(first, Action):
             action, first = first, first.net
-        stages.append(_conv_bn_stage('pw', first, conv[1], True, shift))
+        stages.append(_conv_bn_stage('pw', first, conv[1], 1, shift))
         stages[-1].action = action
         k = 3
-    stages.append(_conv_bn_stage('dw', conv[k], conv[k + 1], True))
-    stages.append(_conv_bn_stage('pw', conv[k + 3], conv[k + 4], False))
+    stages.append(_conv_bn_stage('dw', conv[k], conv[k + 1], 1))
+    stages.append(_conv_bn_stage('pw', conv[k + 3], conv[k + 4], 0))
     return Unit(stages, residual=block.use_res_connect)
 
 
@@ -193,7 +217,7 @@ def units_of_backbone(model, taps: Sequence[int] = ()) -> List[Unit]:
     from .mobilenet_v2 import InvertedResidual
     feats = model.features
     units: List[Unit] = []
-    stem = _conv_bn_stage('stem', feats[0][0], feats[0][1], True)
+    stem = _conv_bn_stage('stem', feats[0][0], feats[0][1], 1)
     first = True
     for i in range(1, len(feats) - 1):
         blk = feats[i]
@@ -209,7 +233,7 @@ def units_of_backbone(model, taps: Sequence[int] = ()) -> List[Unit]:
         u.tap = i in taps
         units.append(u)
     last = feats[len(feats) - 1]
-    units.append(Unit([_conv_bn_stage('pw', last[0], last[1], True)], tap=(len(feats) - 1) in taps))
+    units.append(Unit([_conv_bn_stage('pw', last[0], last[1], 1)], tap=(len(feats) - 1) in taps))
     return units
 
 
@@ -221,27 +245,30 @@ def _has_action(model) -> bool:
 # ------------------------------------------------------------------------------------------------
 # the chain autograd Function
 # ------------------------------------------------------------------------------------------------
-def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None, mirrors=None):
+def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None, mirrors=None, fin=None):
+    """One convolution (+ batch statistics) and, inside the same launch, the BatchNorm finalisation `fin` (the CTA that
+    finishes last writes scale / shift / mean / invstd and updates the running statistics: csrc/bnfin.cuh)."""
     nt, h, wd, cin = a_geom
     cout = st.conv.out_channels
     sp = _lib.stream_ptr(dev)
     stats_p = 0 if stats is None else stats.data_ptr()
     code = _lib.dtype_code(out)
     es = out.element_size()
+    fin_p = ctypes.byref(fin) if fin is not None else None
     if st.kind == 'stem':
-        _lib.call("ehgr_stem_fwd", x_nchw.data_ptr(), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cout,
-                  _lib.dtype_code(x_nchw), code, sp,
+        _lib.call("ehgr_stem_fwd_bn", x_nchw.data_ptr(), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cout,
+                  _lib.dtype_code(x_nchw), code, fin_p, sp,
                   algo_bytes=x_nchw.numel() * x_nchw.element_size() + out.numel() * es,
                   algo_flops=2 * 27 * out.numel())
     elif st.kind == 'pw':
         m = nt * h * wd
         w16 = _bf16_mirror(w, out.dtype, mirrors)
-        _lib.call("ehgr_pw_gemm_w16", ctypes.byref(a_op), w.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
-                  cin, cout, code, _STATE["engine"], sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
+        _lib.call("ehgr_pw_gemm_bn", ctypes.byref(a_op), w.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
+                  cin, cout, code, _STATE["engine"], fin_p, sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
                   algo_flops=2 * m * cin * cout)
     else:
-        _lib.call("ehgr_dw_fwd", ctypes.byref(a_op), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cin,
-                  st.stride, code, sp, algo_bytes=(nt * h * wd * cin + out.numel()) * es + 36 * cin,
+        _lib.call("ehgr_dw_fwd_bn", ctypes.byref(a_op), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cin,
+                  st.stride, code, fin_p, sp, algo_bytes=(nt * h * wd * cin + out.numel()) * es + 36 * cin,
                   algo_flops=18 * out.numel())
 
 
@@ -253,10 +280,11 @@ class _ChainFunction(torch.autograd.Function):
         dev = x.device
         _lib.require_cuda(x)
         stages = [s for u in units for s in u.stages]
-        n_stat = sum(2 * s.conv.out_channels for s in stages if s.bn.training)
+        n_stat = sum(2 * s.conv.out_channels for s in stages if s.bn is not None and s.bn.training)
         stat_arena = torch.zeros(max(n_stat, 1), dtype=torch.float64, device=dev)
-        vec_arena = torch.empty(sum(4 * s.conv.out_channels for s in stages), dtype=torch.float32, device=dev)
-        s_off = v_off = 0
+        vec_arena = torch.empty(sum(4 * s.conv.out_channels for s in stages if s.bn is not None), dtype=torch.float32, device=dev)
+        tickets = torch.zeros(len(stages), dtype=torch.int32, device=dev)    # one "last CTA" counter per layer
+        s_off = v_off = k_i = 0
         sp = _lib.stream_ptr(dev)
 
         mirrors = {}                                     # id(weight) -> bf16 mirror, reused by backward
@@ -281,8 +309,9 @@ class _ChainFunction(torch.autograd.Function):
             lazy = None                                  # (raw, scale, shift, relu6) of the previous stage
             recs = []
             for st in u.stages:
-                w, gamma, beta = params[p_i], params[p_i + 1], params[p_i + 2]
-                act_params = params[p_i + 3:p_i + st.n_params()]
+                w = params[p_i]
+                gamma, beta = (params[p_i + 1], params[p_i + 2]) if st.bn is not None else (None, None)
+                act_params = params[p_i + (3 if st.bn is not None else 1):p_i + st.n_params()]
                 p_i += st.n_params()
                 nt, h, wd, cin = geom
                 cout = st.conv.out_channels
@@ -299,28 +328,38 @@ class _ChainFunction(torch.autograd.Function):
                 else:
                     if st.shift is not None:
                         raise NotImplementedError("temporal shift is defined on a block input")
-                    a_op = op_affine(*lazy)
+                    a_op = op_affine(*lazy) if lazy[1] is not None else op_plain(lazy[0])
                 ho, wo = ((h - 1) // st.stride + 1, (wd - 1) // st.stride + 1) if st.kind != 'pw' else (h, wd)
                 raw = _nhwc_empty(nt, ho, wo, cout, dt, dev)
+                if st.bn is None:                        # bare convolution: no statistics, no finalisation
+                    _launch_conv_fwd(st, a_op, geom, w, raw, None, dev, mirrors=mirrors)
+                    k_i += 1
+                    recs.append((raw, None, geom, False, None))
+                    lazy = (raw, None, None, 0)
+                    geom = (nt, ho, wo, cout)
+                    continue
                 tr = st.bn.training
                 stats = None
                 if tr:
                     stats = stat_arena[s_off:s_off + 2 * cout]
                     s_off += 2 * cout
-                _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None,
-                                 mirrors=mirrors)
                 vec = vec_arena[v_off:v_off + 4 * cout].view(4, cout)   # scale, shift, mean, invstd
                 v_off += 4 * cout
-                _lib.call("ehgr_bn_finalize", 0 if stats is None else stats.data_ptr(), nt * ho * wo, gamma.data_ptr(),
-                          beta.data_ptr(), st.bn.running_mean.data_ptr(), st.bn.running_var.data_ptr(),
-                          float(st.bn.momentum), float(st.bn.eps), int(tr), vec[0].data_ptr(), vec[1].data_ptr(),
-                          vec[2].data_ptr(), vec[3].data_ptr(), cout, sp)
+                fin = BnFin(gamma=gamma.data_ptr(), beta=beta.data_ptr(), running_mean=st.bn.running_mean.data_ptr(),
+                            running_var=st.bn.running_var.data_ptr(), scale=vec[0].data_ptr(), shift=vec[1].data_ptr(),
+                            mean=vec[2].data_ptr(), invstd=vec[3].data_ptr(), counter=tickets[k_i:].data_ptr(),
+                            count=nt * ho * wo, momentum=float(st.bn.momentum), eps=float(st.bn.eps), training=int(tr))
+                k_i += 1
+                _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None,
+                                 mirrors=mirrors, fin=fin)
                 if tr and st.bn.num_batches_tracked is not None:
                     nbt.append(st.bn.num_batches_tracked)
                 recs.append((raw, vec, geom, tr, act_state))
                 lazy = (raw, vec[0], vec[1], st.relu6)
                 geom = (nt, ho, wo, cout)
-            # materialise the unit output: BN(+ReLU6) (+ residual)
+            # materialise the unit output: BN(+activation) (+ residual)
+            if lazy[1] is None:
+                raise NotImplementedError("a unit must end with a BatchNorm stage")
             nt, h, wd, c = geom
             out = _nhwc_empty(nt, h, wd, c, dt, dev)
             _lib.call("ehgr_row_apply", ctypes.byref(op_affine(*lazy)), unit_in.data_ptr() if u.residual else 0,
@@ -359,9 +398,10 @@ class _ChainFunction(torch.autograd.Function):
                 continue
             gviews.append(gflat[off:off + n].view(p.shape))
             off += (n + 7) // 8 * 8
-        sum_arena = torch.zeros(sum(2 * s.conv.out_channels for s in stages), dtype=torch.float64, device=dev)
-        coef_arena = torch.empty(sum(3 * s.conv.out_channels for s in stages), dtype=torch.float32, device=dev)
-        s_off = c_off = 0
+        sum_arena = torch.zeros(sum(2 * s.conv.out_channels for s in stages if s.bn is not None) or 1, dtype=torch.float64, device=dev)
+        coef_arena = torch.empty(sum(3 * s.conv.out_channels for s in stages if s.bn is not None) or 1, dtype=torch.float32, device=dev)
+        tickets = torch.zeros(len(stages), dtype=torch.int32, device=dev)
+        s_off = c_off = k_i = 0
         gout_of = {ui: g for ui, g in zip(ctx.tap_units, gouts) if g is not None}
         need_x_grad = ctx.needs_input_grad[2]
 
@@ -398,18 +438,26 @@ class _ChainFunction(torch.autograd.Function):
                 ho, wo = raw.shape[2], raw.shape[3]
                 m_out = nt * ho * wo
                 pb = p_off[si]
-                w, gamma = params[pb], params[pb + 1]
-                gw, ggam, gbet = gviews[pb], gviews[pb + 1], gviews[pb + 2]
-                sums = sum_arena[s_off:s_off + 2 * cout]
-                s_off += 2 * cout
-                coef = coef_arena[c_off:c_off + 3 * cout].view(3, cout)
-                c_off += 3 * cout
-                _lib.call("ehgr_bn_bwd_reduce", g.data_ptr(), raw.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(),
-                          int(st.relu6), sums.data_ptr(), m_out, cout, code, sp, algo_bytes=2 * m_out * cout * es)
-                _lib.call("ehgr_bn_bwd_finalize", sums.data_ptr(), m_out, gamma.data_ptr(), vec[2].data_ptr(),
-                          vec[3].data_ptr(), int(tr), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
-                          ggam.data_ptr(), gbet.data_ptr(), cout, sp)
-                dy_op = op_bnbwd(g, raw, coef[0], coef[1], coef[2], vec[0], vec[1], st.relu6)
+                w, gw = params[pb], gviews[pb]
+                if st.bn is None:                        # bare convolution: d(raw) is the incoming gradient itself
+                    dy_op = op_plain(g)
+                    k_i += 1
+                else:
+                    gamma = params[pb + 1]
+                    ggam, gbet = gviews[pb + 1], gviews[pb + 2]
+                sums = sum_arena[s_off:s_off + 2 * cout] if st.bn is not None else None
+                if st.bn is not None:
+                  s_off += 2 * cout
+                  coef = coef_arena[c_off:c_off + 3 * cout].view(3, cout)
+                  c_off += 3 * cout
+                  bwd = BnBwd(gamma=gamma.data_ptr(), mean=vec[2].data_ptr(), invstd=vec[3].data_ptr(), ca=coef[0].data_ptr(),
+                            cb=coef[1].data_ptr(), cc=coef[2].data_ptr(), dgamma=ggam.data_ptr(), dbeta=gbet.data_ptr(),
+                            counter=tickets[k_i:].data_ptr(), count=m_out, training=int(tr))
+                  k_i += 1
+                  _lib.call("ehgr_bn_bwd_reduce_fin", g.data_ptr(), raw.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(),
+                            int(st.relu6), sums.data_ptr(), m_out, cout, code, ctypes.byref(bwd), sp,
+                            algo_bytes=2 * m_out * cout * es)
+                  dy_op = op_bnbwd(g, raw, coef[0], coef[1], coef[2], vec[0], vec[1], st.relu6)
                 if st.kind == 'stem':
                     _lib.call("ehgr_stem_wgrad", ctypes.byref(dy_op), ctx.x_in.data_ptr(), gw.data_ptr(), nt, h, wd,
                               cout, _lib.dtype_code(ctx.x_in), code, sp,
@@ -423,12 +471,14 @@ class _ChainFunction(torch.autograd.Function):
                 elif si == 0:
                     a_op = (op_shift(unit_in, st.shift[0], st.shift[1], h * wd, 1) if st.shift is not None
                             else op_plain(unit_in))
+                elif recs[si - 1][1] is None:
+                    a_op = op_plain(recs[si - 1][0])
                 else:
                     a_op = op_affine(recs[si - 1][0], recs[si - 1][1][0], recs[si - 1][1][1], u.stages[si - 1].relu6)
                 m_in = nt * h * wd
                 need_dgrad = not (si == 0 and ui == 0 and not need_x_grad)
                 g_prev = None
-                if st.kind == 'pw' and need_dgrad:
+                if st.kind == 'pw' and need_dgrad and dy_op.mode != 0:
                     # dgrad AND wgrad both consume d(raw): evaluate the BN-backward operand once (one
                     # streaming pass at full occupancy) so the tensor-core producers only copy bf16 rows
                     draw = torch.empty_like(raw)
@@ -492,7 +542,7 @@ def _chain_params(units):
     ps = []
     for u in units:
         for s in u.stages:
-            ps += [s.conv.weight, s.bn.weight, s.bn.bias]
+            ps += [s.conv.weight] + ([s.bn.weight, s.bn.bias] if s.bn is not None else [])
             if s.action is not None:
                 ps += action_ops.action_params(s.action)
     return ps
@@ -509,6 +559,12 @@ def inverted_residual(m, x):
     """InvertedResidual.forward (archs/mobilenet_v2.py:62-66) as a one-unit chain."""
     _lib.require_cuda(x)
     return run_chain([unit_of_block(m)], x)[0]
+
+
+def sepconv_stack(modules, x):
+    """A stack of SepConv blocks (one exit head's ``scala``: models/models_SD.py:214-253) as ONE fused chain."""
+    _lib.require_cuda(x)
+    return run_chain([unit_of_sepconv(m) for m in modules], x)[0]
 
 
 def mobilenet_v2_features(model, x, taps: Sequence[int] = ()):

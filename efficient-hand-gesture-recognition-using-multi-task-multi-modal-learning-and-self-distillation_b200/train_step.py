@@ -175,6 +175,16 @@ class FlatSGD:
         self.lr_mult = torch.tensor([g['lr_mult'] for g in self.param_groups], dtype=torch.float32, device=dev)
         self.decay_mult = torch.tensor([g['decay_mult'] for g in self.param_groups], dtype=torch.float32, device=dev)
         self.lr_dev = torch.tensor([float(lr)], dtype=torch.float32, device=dev)
+        # bf16 mirror of every parameter (same offsets), kept current by the SGD kernel itself: the tensor-core GEMMs
+        # stage their weights from it (fused.weight_mirrors) instead of casting 34 weights per step
+        self.flat_p16 = self.flat_p.to(torch.bfloat16) if dev.type == "cuda" else None
+        self._mirror_of = {}
+        if self.flat_p16 is not None:
+            for g in self.param_groups:
+                for p in g['params']:
+                    off = buckets._offset_of.get(id(p))
+                    if off is not None:
+                        self._mirror_of[id(p)] = self.flat_p16[off:off + p.numel()].view(p.shape)
         self._host_lr = torch.empty(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
 
     def set_base_lr(self, lr: float):
@@ -186,6 +196,15 @@ class FlatSGD:
         else:
             self.lr_dev.fill_(float(lr))
 
+    def refresh_mirror(self):
+        """Re-derive the bf16 mirror from the fp32 parameters (after load_state_dict / a broadcast / any outside write)."""
+        if self.flat_p16 is not None:
+            self.flat_p16.copy_(self.flat_p)
+
+    def mirror_for(self, p):
+        """bf16 view of parameter p inside the mirror, or None (fused.weight_mirrors protocol)."""
+        return self._mirror_of.get(id(p))
+
     def step(self, ema: Optional[torch.Tensor] = None, ema_decay: float = 0.0):
         """One optimiser step; with ``ema`` (a flat fp32 tensor laid out like ``flat_p``) the EMA of the parameters is
         updated in the same kernel from the freshly stepped values (FlatEMA)."""
@@ -193,8 +212,8 @@ class FlatSGD:
         f = self.buckets.flat
         _lib.call("ehgr_sgd_step", self.flat_p.data_ptr(), f.data_ptr(), self.flat_m.data_ptr(), self.code.data_ptr(),
                   self.lr_mult.data_ptr(), self.decay_mult.data_ptr(), len(self.param_groups), self.lr_dev.data_ptr(),
-                  self.momentum, self.weight_decay, f.numel(), _lib.ptr(ema), float(ema_decay), _lib.stream_ptr(f.device),
-                  algo_bytes=f.numel() * (21 + (8 if ema is not None else 0)))
+                  self.momentum, self.weight_decay, f.numel(), _lib.ptr(ema), float(ema_decay), _lib.ptr(self.flat_p16),
+                  _lib.stream_ptr(f.device), algo_bytes=f.numel() * (23 + (8 if ema is not None else 0)))
 
     def zero_grad(self, set_to_none: bool = False):
         self.buckets.zero()
@@ -391,6 +410,10 @@ class MTMMTrainStep:
                 rest = [p.data for p in self.model.parameters()]
             for t in rest + [b.data for b in self.model.buffers()]:
                 dist.broadcast(t, self._src(), group=self.group)
+            if isinstance(self.opt, FlatSGD):
+                self.opt.refresh_mirror()
+            if self.ema is not None:
+                self.ema.set()
 
     def sync_bn_buffers(self):
         """BatchNorm batch statistics are per rank while training (the reference has no SyncBN and is
@@ -443,14 +466,17 @@ class MTMMTrainStep:
         from .losses import mtmm_loss
         rgb, depth = self._prepare(rgb, depth)
         self.buckets.zero()
-        with self._fused.compute_dtype(self.compute_dtype):
+        with self._fused.compute_dtype(self.compute_dtype), self._fused.weight_mirrors(self._mirrors()):
             logits, dpred = self.model(rgb)
             loss, _ = mtmm_loss(logits, labels, dpred, depth)
-        with self._fused.grad_sink(self.buckets):
+        with self._fused.grad_sink(self.buckets), self._fused.weight_mirrors(self._mirrors()):
             loss.backward()
         self.buckets.finish()
         self._optimizer_step()
         return loss.detach()
+
+    def _mirrors(self):
+        return self.opt if isinstance(self.opt, FlatSGD) else None
 
     def _optimizer_step(self):
         if self.ema is not None:
@@ -461,7 +487,9 @@ class MTMMTrainStep:
 
     def invalidate_graph(self):
         """Call after anything the captured graph has baked in changes (learning rate, train/eval mode,
-        frozen parameters, input shapes)."""
+        frozen parameters, input shapes) and after writing parameters from outside (load_state_dict)."""
+        if isinstance(self.opt, FlatSGD):
+            self.opt.refresh_mirror()
         self._graph = None
         self._static_in = None
         self._static_loss = None
@@ -529,10 +557,10 @@ class SDTrainStep(MTMMTrainStep):
         from .losses import sd_loss
         rgb, _ = self._prepare(rgb)
         self.buckets.zero()
-        with self._fused.compute_dtype(self.compute_dtype):
+        with self._fused.compute_dtype(self.compute_dtype), self._fused.weight_mirrors(self._mirrors()):
             outs = self.model(rgb)
             total, _terms = sd_loss(outs[:4], outs[4:], labels, self.alpha, self.beta, self.temperature)
-        with self._fused.grad_sink(self.buckets):
+        with self._fused.grad_sink(self.buckets), self._fused.weight_mirrors(self._mirrors()):
             total.backward()
         self.buckets.finish()
         self._optimizer_step()

@@ -9,8 +9,10 @@ implementation exists: SURVEY §8a A13) the taps are the outputs of ``features[3
 head downsamples with stride-2 ``SepConv`` blocks until it reaches 7x7 with 1280 channels, so the four
 feature vectors compared by the feature loss have equal shape, as in the reference (2048 there).
 
-The backbone (and its taps) runs on the fused sm_100a chain; the exit heads are ``SepConv`` stacks
-(SURVEY §8f N2 — "next": they still use the library convolutions).
+The backbone (and its taps) runs on the fused sm_100a chain, and so do the exit heads: a ``scala`` (a stack of
+``SepConv`` blocks) is ONE fused chain of depthwise / pointwise stages with plain-ReLU row operands
+(``fused.sepconv_stack``: the kernels of K7 / K8, no library convolution, BatchNorm or activation op), followed by
+the pooling and classifier kernels of K10.  ``SepConv.forward`` itself (a stand-alone block) takes the same path.
 """
 from __future__ import annotations
 
@@ -42,7 +44,10 @@ class SepConv(nn.Module):
         )
 
     def forward(self, x):
-        return self.op(x)
+        if x.is_cuda:
+            from . import fused
+            return fused.sepconv_stack([self], x)
+        return self.op(x)               # CPU: plain module arithmetic (shape / policy tests only; no CUDA kernels exist there)
 
 
 class TSN(_BaseTSN):
@@ -92,6 +97,11 @@ class TSN(_BaseTSN):
 
     def _exit(self, x, scala, pool, fc):
         from . import fused
+        if x.is_cuda and all(isinstance(m, SepConv) for m in scala):
+            y = fused.sepconv_stack(list(scala), x)     # one fused chain per exit head
+            pooled = fused.global_avg_pool(y)           # [NT, F] fp32
+            fea = pooled.view(pooled.shape[0], pooled.shape[1], 1, 1)
+            return fused.fc_consensus(pooled, fc, self.num_segments), fea
         y = scala(x)
         fea = pool(y)                                   # [NT, F, 1, 1]
         z = fused.fc_consensus(torch.flatten(fea, 1).float(), fc, self.num_segments)

@@ -81,7 +81,8 @@ enum { EHGR_ROW_PLAIN = 0, EHGR_ROW_AFFINE = 1, EHGR_ROW_SHIFT = 2, EHGR_ROW_BNB
 
 typedef struct ehgr_rowop {
   int32_t mode;        /* EHGR_ROW_* */
-  int32_t relu6;       /* AFFINE: clamp to [0,6];  BNBWD: mask in1 where !(0 < in2*scale+shift < 6) */
+  int32_t relu6;       /* activation code: 0 none, 1 ReLU6, 2 plain ReLU.  AFFINE: clamp to [0,hi];  BNBWD: mask in1 where
+                          !(0 < in2*scale+shift < hi);  hi = 6 (ReLU6) or +inf (ReLU) */
   const void* in1;     /* [M, C] activation (or, for BNBWD, gradient w.r.t. the post-activation) */
   const void* in2;     /* BNBWD: raw forward output of the layer, [M, C] */
   const float* scale;  /* [C] BatchNorm scale  gamma*invstd       (AFFINE; BNBWD when relu6) */
@@ -98,6 +99,45 @@ typedef struct ehgr_rowop {
 } ehgr_rowop;
 
 enum { EHGR_ENGINE_AUTO = 0, EHGR_ENGINE_SIMT = 1, EHGR_ENGINE_TCGEN05 = 2 };
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm bookkeeping folded into the producing kernel (csrc/bnfin.cuh).  The *_bn entry points below take one
+ * of these HOST structs (device pointers inside): the CTA that finishes LAST turns the batch statistics the launch
+ * has just accumulated into what the consumers need, so no separate ehgr_bn_finalize / ehgr_bn_bwd_finalize launch
+ * follows.  `counter` is a device uint32 that is ZERO before the launch (the kernel leaves it zero again).
+ *   ehgr_bnfin (forward, nn.BatchNorm2d semantics as ehgr_bn_finalize): stats[2C] -> scale, shift, mean, invstd;
+ *     training: running statistics updated with `momentum`; eval (training = 0): scale/shift from the running ones.
+ *   ehgr_bnbwd (backward, as ehgr_bn_bwd_finalize): sums[2C] -> ca, cb, cc, d(gamma), d(beta).
+ * A NULL struct pointer means "no finalisation" (the plain entry points).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ehgr_bnfin {
+  const float* gamma;          /* [C] or NULL (= 1) */
+  const float* beta;           /* [C] or NULL (= 0) */
+  float* running_mean;         /* [C]; may be NULL in training mode (no running-statistics update) */
+  float* running_var;
+  float* scale;                /* out [C]: gamma * invstd */
+  float* shift;                /* out [C]: beta - mean * scale */
+  float* mean;                 /* out [C] or NULL */
+  float* invstd;               /* out [C] or NULL */
+  unsigned int* counter;
+  long long count;             /* elements per channel (M) */
+  float momentum, eps;
+  int32_t training;
+} ehgr_bnfin;
+
+typedef struct ehgr_bnbwd {
+  const float* gamma;          /* [C] or NULL (= 1) */
+  const float* mean;           /* [C] saved by the forward finalisation */
+  const float* invstd;
+  float* ca;                   /* out [C]: coefficients of the BNBWD row operand */
+  float* cb;
+  float* cc;
+  float* dgamma;               /* out [C] or NULL (stored, not accumulated) */
+  float* dbeta;
+  unsigned int* counter;
+  long long count;
+  int32_t training;
+} ehgr_bnbwd;
 
 /* ---------------------------------------------------------------------------------------------
  * K8/K11  pointwise (1x1) convolution as a GEMM over NHWC rows — replaces the nn.Conv2d 1x1 layers of
@@ -122,6 +162,11 @@ int ehgr_pw_gemm_w16(const ehgr_rowop* a, const float* w, const void* w16, int w
                      const void* addend, double* stats, long long M, int K, int N, int dtype, int engine,
                      ehgr_stream_t stream);
 
+/* ehgr_pw_gemm_w16 followed, inside the same launch, by the BatchNorm finalisation of `stats` (fin may be NULL). */
+int ehgr_pw_gemm_bn(const ehgr_rowop* a, const float* w, const void* w16, int w_is_kn, void* out,
+                    const void* addend, double* stats, long long M, int K, int N, int dtype, int engine,
+                    const ehgr_bnfin* fin, ehgr_stream_t stream);
+
 /* weight gradient of the same layer: dw[N,K] += sum_m rowop(dy)[m,n] * rowop(a)[m,k]   (fp32, atomics;
  * the caller zeroes dw).  dy is normally a BNBWD operand, a the layer's forward operand. */
 int ehgr_pw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, long long M, int K, int N,
@@ -138,6 +183,9 @@ int ehgr_pw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, long lon
  * ------------------------------------------------------------------------------------------- */
 int ehgr_dw_fwd(const ehgr_rowop* a, const float* w, void* out, double* stats, int nt, int h, int wd, int c,
                 int stride, int dtype, ehgr_stream_t stream);
+/* ehgr_dw_fwd + in-launch BatchNorm finalisation of `stats` (fin may be NULL) */
+int ehgr_dw_fwd_bn(const ehgr_rowop* a, const float* w, void* out, double* stats, int nt, int h, int wd, int c,
+                   int stride, int dtype, const ehgr_bnfin* fin, ehgr_stream_t stream);
 int ehgr_dw_dgrad(const ehgr_rowop* dy, const float* w, void* da, int nt, int h, int wd, int c, int stride,
                   int dtype, ehgr_stream_t stream);
 int ehgr_dw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, int nt, int h, int wd, int c,
@@ -154,6 +202,8 @@ int ehgr_dw_bwd(const ehgr_rowop* dy, const ehgr_rowop* a, const float* w, void*
  * ------------------------------------------------------------------------------------------- */
 int ehgr_stem_fwd(const void* x, const float* w, void* out, double* stats, int nt, int h, int wd, int cout,
                   int x_dtype, int dtype, ehgr_stream_t stream);
+int ehgr_stem_fwd_bn(const void* x, const float* w, void* out, double* stats, int nt, int h, int wd, int cout,
+                     int x_dtype, int dtype, const ehgr_bnfin* fin, ehgr_stream_t stream);
 int ehgr_stem_wgrad(const ehgr_rowop* dy, const void* x, float* dw, int nt, int h, int wd, int cout,
                     int x_dtype, int dtype, ehgr_stream_t stream);
 
@@ -165,7 +215,8 @@ int ehgr_stem_wgrad(const ehgr_rowop* dy, const void* x, float* dw, int nt, int 
  *                  training != 0 also updates running_mean/var in place.  training == 0 ignores
  *                  stats/count and uses running_mean/var.
  *   bwd_reduce   : sums[c] += sum_m mask*g[m,c];  sums[C+c] += sum_m mask*g[m,c]*raw[m,c]
- *                  mask = relu6 ? (0 < raw*scale+shift < 6) : 1          (double[2C], caller zeroes)
+ *                  mask = relu6 ? (0 < raw*scale+shift < hi) : 1, hi = 6 (relu6 = 1) or +inf (relu6 = 2: plain ReLU)
+ *                  (double[2C], caller zeroes)
  *   bwd_finalize : sums -> (ca, cb, cc) of the BNBWD row operand and dgamma, dbeta.
  * ------------------------------------------------------------------------------------------- */
 int ehgr_bn_finalize(const double* stats, long long count, const float* gamma, const float* beta,
@@ -176,6 +227,10 @@ int ehgr_bn_bwd_reduce(const void* g, const void* raw, const float* scale, const
 int ehgr_bn_bwd_finalize(const double* sums, long long count, const float* gamma, const float* mean,
                          const float* invstd, int training, float* ca, float* cb, float* cc, float* dgamma,
                          float* dbeta, int c, ehgr_stream_t stream);
+/* bwd_reduce + bwd_finalize in ONE launch: the last CTA of the reduction turns the sums into the coefficients */
+int ehgr_bn_bwd_reduce_fin(const void* g, const void* raw, const float* scale, const float* shift, int relu6,
+                           double* sums, long long m, int c, int dtype, const ehgr_bnbwd* fin,
+                           ehgr_stream_t stream);
 
 /* out[M,C] = rowop(a) (+ addend): materialises a lazy activation — BatchNorm(+ReLU6)(+residual add,
  * InvertedResidual.forward archs/mobilenet_v2.py:62-66) — or, with a SHIFT operand of shift_dir=-1,
@@ -217,13 +272,15 @@ int ehgr_temporal_pool_bwd(const void* x, const void* g, void* dx, long long n, 
  *   freshly stepped parameter, ema = decay*ema + (1-decay)*p — EMAWrapper.update (train_mtmm.py:110-128), which the
  *   reference calls right after optimizer.step() (train_mtmm.py:242-245).  The expression is evaluated as the reference
  *   does (two fp32 products and one fp32 sum, scalars rounded to fp32): bit-identical.
+ *   p16 (optional, NULL = off): bf16 mirror of p (same element offsets), rewritten in the same pass: the tensor-core
+ *   GEMMs stage their weight operand from it with asynchronous copies (ehgr_pw_gemm_w16) — no per-layer cast kernels.
  * ehgr_ema_update: the same update for the other state_dict entries — floating-point buffers (is_int64 = 0: BatchNorm
  *   running statistics) and the int64 num_batches_tracked counters (is_int64 = 1: evaluated in fp32 and truncated,
  *   as python_float * int64_tensor followed by copy_() does in the reference).
  * ------------------------------------------------------------------------------------------- */
 int ehgr_sgd_step(float* p, const float* g, float* buf, const void* code, const float* lr_mult,
                   const float* decay_mult, int n_groups, const float* lr_dev, float momentum, float weight_decay,
-                  long long n, float* ema, double ema_decay, ehgr_stream_t stream);
+                  long long n, float* ema, double ema_decay, void* p16, ehgr_stream_t stream);
 int ehgr_ema_update(void* ema, const void* x, long long n, double decay, int is_int64, ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

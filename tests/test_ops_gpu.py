@@ -7,7 +7,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_err
+from conftest import GOLDEN, rel_err
 
 pytestmark = pytest.mark.gpu
 
