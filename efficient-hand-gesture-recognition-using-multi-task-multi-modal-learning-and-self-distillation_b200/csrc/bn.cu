@@ -131,7 +131,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, const f
   for (int i = tid; i < 2 * C; i += nthreads) atomicAdd(&sums[i], static_cast<double>(smem[i]));
   if (fin.counter) {                                       // 2-D block: the helper's thread 0 / stride are 1-D
     __shared__ int s_last;
-    __threadfence();
+    if (tid < 2 * C) __threadfence();                      // the threads that issued this CTA's atomics
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1 ? 1 : 0;
     __syncthreads();

@@ -69,10 +69,12 @@ __device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwd& f, const do
 }
 
 // Call from ALL threads of the CTA after the CTA's last statistics atomic.  True (in every thread) in the CTA that
-// arrives last; that CTA may read everything the other CTAs accumulated.
-__device__ __forceinline__ bool cta_arrives_last(unsigned int* counter) {
+// arrives last; that CTA may read everything the other CTAs accumulated.  `did_atomics`: this thread issued some of
+// the CTA's statistics atomics — only those threads need the (expensive: it drains the thread's outstanding stores)
+// device-scope fence before the ticket.
+__device__ __forceinline__ bool cta_arrives_last(unsigned int* counter, bool did_atomics) {
   __shared__ int s_last;
-  __threadfence();
+  if (did_atomics) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
   __syncthreads();
@@ -82,15 +84,15 @@ __device__ __forceinline__ bool cta_arrives_last(unsigned int* counter) {
 }
 
 // the whole epilogue: no-op when fin.counter is NULL
-__device__ __forceinline__ void bn_finalize_if_last(const BnFin& f, const double* stats, int C) {
+__device__ __forceinline__ void bn_finalize_if_last(const BnFin& f, const double* stats, int C, bool did_atomics = true) {
   if (!f.counter) return;
-  if (!cta_arrives_last(f.counter)) return;
+  if (!cta_arrives_last(f.counter, did_atomics)) return;
   for (int c = threadIdx.x; c < C; c += blockDim.x) bn_finalize_channel(f, stats, c, C);
   if (threadIdx.x == 0) *f.counter = 0u;
 }
-__device__ __forceinline__ void bn_bwd_finalize_if_last(const BnBwd& f, const double* sums, int C) {
+__device__ __forceinline__ void bn_bwd_finalize_if_last(const BnBwd& f, const double* sums, int C, bool did_atomics = true) {
   if (!f.counter) return;
-  if (!cta_arrives_last(f.counter)) return;
+  if (!cta_arrives_last(f.counter, did_atomics)) return;
   for (int c = threadIdx.x; c < C; c += blockDim.x) bn_bwd_finalize_channel(f, sums, c, C);
   if (threadIdx.x == 0) *f.counter = 0u;
 }

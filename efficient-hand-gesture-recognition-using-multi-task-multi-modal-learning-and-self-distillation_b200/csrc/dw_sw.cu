@@ -260,7 +260,7 @@ dw_fwd_sw_kernel(RowOp a, const __grid_constant__ CUtensorMap tm_a, const float*
       }
     }
   }
-  bn_finalize_if_last(fin, stats, g.c);
+  bn_finalize_if_last(fin, stats, g.c, stats != nullptr && tid < Cfg::CC);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -584,7 +584,8 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
     __syncwarp();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
-  bn_finalize_if_last(p.fin, p.stats, p.N);      // every epilogue warp's statistics atomics precede the barrier above
+  // every epilogue warp's statistics atomics precede the barrier above; only those warps fence
+  bn_finalize_if_last(p.fin, p.stats, p.N, warp > kMmaWarp && p.stats != nullptr);
 }
 
 }  // namespace tc

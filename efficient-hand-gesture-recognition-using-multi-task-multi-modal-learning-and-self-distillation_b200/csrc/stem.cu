@@ -406,7 +406,7 @@ stem_fwd32_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __r
     __syncthreads();
     if (tid < 2 * kStemC) atomicAdd(&stats[tid], static_cast<double>(s_stat[tid]));
   }
-  bn_finalize_if_last(fin, stats, kStemC);
+  bn_finalize_if_last(fin, stats, kStemC, stats != nullptr && tid < 2 * kStemC);
 }
 
 // Weight gradient.  12 warps = 4 channel groups (8 output channels) x 3 input planes; a warp keeps its

@@ -27,7 +27,15 @@ import torch.nn as nn
 from . import _lib, action_ops
 from ._lib import BnBwd, BnFin, RowOp
 
+import os as _os
+
 _STATE = {"dtype": torch.float32, "engine": 0, "grad_sink": None, "mirrors": None}
+
+# BatchNorm finalisation inside the producing kernel ("last CTA done", csrc/bnfin.cuh): bit 0 forward, bit 1 backward.
+# Measured on B200 inside the captured step (profiles/README.md, round 2): the in-kernel tail (device-scope fence,
+# ticket, one CTA finalising) costs MORE than a dependent one-block launch inside a CUDA graph (17.2 vs 16.9 ms per
+# step with both bits set), so the default keeps the separate ehgr_bn_finalize / ehgr_bn_bwd_finalize launches.
+FUSED_FINALIZE = int(_os.environ.get("EHGR_FUSED_FINALIZE", "0"))
 
 
 @contextlib.contextmanager
@@ -351,7 +359,12 @@ class _ChainFunction(torch.autograd.Function):
                             count=nt * ho * wo, momentum=float(st.bn.momentum), eps=float(st.bn.eps), training=int(tr))
                 k_i += 1
                 _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None,
-                                 mirrors=mirrors, fin=fin)
+                                 mirrors=mirrors, fin=fin if FUSED_FINALIZE & 1 else None)
+                if not FUSED_FINALIZE & 1:
+                    _lib.call("ehgr_bn_finalize", 0 if stats is None else stats.data_ptr(), nt * ho * wo, gamma.data_ptr(),
+                              beta.data_ptr(), st.bn.running_mean.data_ptr(), st.bn.running_var.data_ptr(),
+                              float(st.bn.momentum), float(st.bn.eps), int(tr), vec[0].data_ptr(), vec[1].data_ptr(),
+                              vec[2].data_ptr(), vec[3].data_ptr(), cout, sp)
                 if tr and st.bn.num_batches_tracked is not None:
                     nbt.append(st.bn.num_batches_tracked)
                 recs.append((raw, vec, geom, tr, act_state))
@@ -455,8 +468,12 @@ class _ChainFunction(torch.autograd.Function):
                             counter=tickets[k_i:].data_ptr(), count=m_out, training=int(tr))
                   k_i += 1
                   _lib.call("ehgr_bn_bwd_reduce_fin", g.data_ptr(), raw.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(),
-                            int(st.relu6), sums.data_ptr(), m_out, cout, code, ctypes.byref(bwd), sp,
-                            algo_bytes=2 * m_out * cout * es)
+                            int(st.relu6), sums.data_ptr(), m_out, cout, code, ctypes.byref(bwd) if FUSED_FINALIZE & 2 else None,
+                            sp, algo_bytes=2 * m_out * cout * es)
+                  if not FUSED_FINALIZE & 2:
+                      _lib.call("ehgr_bn_bwd_finalize", sums.data_ptr(), m_out, gamma.data_ptr(), vec[2].data_ptr(),
+                                vec[3].data_ptr(), int(tr), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
+                                ggam.data_ptr(), gbet.data_ptr(), cout, sp)
                   dy_op = op_bnbwd(g, raw, coef[0], coef[1], coef[2], vec[0], vec[1], st.relu6)
                 if st.kind == 'stem':
                     _lib.call("ehgr_stem_wgrad", ctypes.byref(dy_op), ctx.x_in.data_ptr(), gw.data_ptr(), nt, h, wd,
