@@ -19,6 +19,7 @@ losses = _importlib.import_module(__name__ + ".losses")
 train_step = _importlib.import_module(__name__ + ".train_step")
 tsn_mtmm = _importlib.import_module(__name__ + ".tsn_mtmm")
 tsn_sd = _importlib.import_module(__name__ + ".tsn_sd")
+tsn_mtmm_sd = _importlib.import_module(__name__ + ".tsn_mtmm_sd")
 
 from .temporal_shift import (InplaceShift, TemporalPool, TemporalShift, make_temporal_pool,  # noqa: E402,F401
                              make_temporal_shift, temporal_shift)

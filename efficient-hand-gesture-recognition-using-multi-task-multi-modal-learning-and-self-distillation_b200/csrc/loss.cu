@@ -188,8 +188,10 @@ extern "C" int ehgr_mtmm_loss(const float* logits, const long long* labels, cons
                               float depth_weight, float* loss_out, float* dlogits, float* dpred, int n, int k,
                               int frames, int ph, int pw, int dtype, ehgr_stream_t stream) {
   if (esize_of(dtype) == 0) return EHGR_E_DTYPE;
-  if (!logits || !labels || !pred || !depth_gt || !loss_out || !dlogits || !dpred) return EHGR_E_NULL;
-  if (n <= 0 || k <= 0 || frames <= 0 || ph <= 0 || pw <= 0) return EHGR_E_SHAPE;
+  // n == 0: the depth term alone (the MTMM+SD step adds it to the SD loss kernel's terms, train_mtmm_sd.py:240-293)
+  if (!pred || !depth_gt || !loss_out || !dpred) return EHGR_E_NULL;
+  if (n > 0 && (!logits || !labels || !dlogits)) return EHGR_E_NULL;
+  if (n < 0 || (n > 0 && k <= 0) || frames <= 0 || ph <= 0 || pw <= 0) return EHGR_E_SHAPE;
   const long long cells = static_cast<long long>(frames) * ph * pw;
   const long long depth_blocks = std::min(cdiv(cells, 128 * 4), 8LL * kNumSMs);
   const unsigned grid = static_cast<unsigned>(n + depth_blocks);

@@ -99,3 +99,43 @@ def sd_loss(outputs, feats, labels, alpha: float = 0.1, beta: float = 1e-6, temp
         raise ValueError("sd_loss expects four logits and four feature tensors (final first)")
     terms = _SDLossFunction.apply(labels, alpha, beta, temperature, *outputs, *feats)
     return terms[0], terms[1:].detach()
+
+
+class _DepthMSEFunction(torch.autograd.Function):
+    """weight * MSE(pred, bilinear56(depth_gt)) alone (ehgr_mtmm_loss with n = 0)."""
+
+    @staticmethod
+    def forward(ctx, pred, depth_gt, weight):
+        _lib.require_cuda(pred, depth_gt)
+        ph, pw = pred.shape[-2:]
+        frames = pred.numel() // (ph * pw)
+        if depth_gt.shape[-2] != 4 * ph or depth_gt.shape[-1] != 4 * pw or depth_gt.numel() != frames * 16 * ph * pw:
+            raise RuntimeError("depth loss expects depth_gt of 4x the spatial size of depth_pred and the same frame count")
+        pr = pred.contiguous()
+        if pr.dtype not in (torch.float32, torch.bfloat16):
+            pr = pr.float()
+        gt = depth_gt.contiguous().float()
+        out = torch.zeros(3, dtype=torch.float32, device=pred.device)
+        dpred = torch.empty(pr.shape, dtype=torch.float32, device=pr.device)
+        _lib.call("ehgr_mtmm_loss", 0, 0, pr.data_ptr(), gt.data_ptr(), float(weight), out.data_ptr(), 0, dpred.data_ptr(),
+                  0, 0, frames, ph, pw, _lib.dtype_code(pr), _lib.stream_ptr(pred.device),
+                  algo_bytes=gt.numel() * 2 + pr.numel() * (pr.element_size() + 4))
+        ctx.save_for_backward(dpred)
+        ctx.dtype = pred.dtype
+        return out                                  # [weight * MSE, 0, MSE]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (dpred,) = ctx.saved_tensors
+        return (dpred * g_out[0]).to(ctx.dtype), None, None
+
+
+def mtmm_sd_loss(outputs, feats, global_depth_out, depth_gt, labels, alpha: float = 0.1, beta: float = 1e-6,
+                 temperature: float = 3.0, depth_weight: float = 0.01):
+    """The combined stage of train_mtmm_sd.py:240-293: ``loss = CE(output) + 0.01 * MSE(g_depth_out, bilinear56(depth))``
+    and ``total = (1-alpha) * (loss + 3 CE) + alpha * 3 KD + beta * 3 feature`` — the self-distillation kernel's total plus
+    ``(1-alpha) * 0.01 * MSE`` from the depth kernel (two launches; both return their gradients with the forward).
+    Returns (total, terms[10] of sd_loss, depth_mse)."""
+    total_sd, terms = sd_loss(outputs, feats, labels, alpha, beta, temperature)
+    d = _DepthMSEFunction.apply(global_depth_out, depth_gt, (1.0 - alpha) * depth_weight)
+    return total_sd + d[0], terms, d[2].detach()

@@ -568,3 +568,28 @@ class SDTrainStep(MTMMTrainStep):
 
     def __call__(self, rgb_h, labels_h) -> float:
         return float(self.run(*self.stage(rgb_h, labels_h)).item())
+
+
+class MTMMSDTrainStep(MTMMTrainStep):
+    """One step of the combined stage (train_mtmm_sd.py:213-320): forward with the three exit heads and the two depth
+    decoders (tsn_mtmm_sd.TSN, modal='rgb_depth'), total = (1-alpha)(CE + 0.01 MSE_depth + 3 CE) + alpha 3 KD + beta 3
+    feature, backward of ``total`` (the reference script back-propagates ``loss`` alone, :310 — SURVEY section 4 lists it
+    among the script's defects; the quantity it logs and means to minimise is ``total_loss``), all-reduce, SGD."""
+
+    def __init__(self, model, alpha=0.1, beta=1e-6, temperature=3.0, **kw):
+        super().__init__(model, **kw)
+        self.alpha, self.beta, self.temperature = alpha, beta * self.buckets.world, temperature
+
+    def _step(self, rgb, depth, labels):
+        from .losses import mtmm_sd_loss
+        rgb, depth = self._prepare(rgb, depth)
+        self.buckets.zero()
+        with self._fused.compute_dtype(self.compute_dtype), self._fused.weight_mirrors(self._mirrors()):
+            outs = self.model(rgb)
+            total, _terms, _mse = mtmm_sd_loss(outs[:4], outs[4:8], outs[9], depth, labels, self.alpha, self.beta,
+                                               self.temperature)
+        with self._fused.grad_sink(self.buckets), self._fused.weight_mirrors(self._mirrors()):
+            total.backward()
+        self.buckets.finish()
+        self._optimizer_step()
+        return total.detach()

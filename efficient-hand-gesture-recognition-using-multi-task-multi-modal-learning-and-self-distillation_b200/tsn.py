@@ -147,7 +147,8 @@ class TSN(nn.Module):
         groups = {k: [] for k in ("first_conv_weight", "first_conv_bias", "normal_weight", "normal_bias",
                                   "bn", "custom_weight", "custom_bn", "lr5_weight", "lr10_bias")}
         conv_cnt = bn_cnt = 0
-        conv_types = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
+        # ConvTranspose2d: the MTMM+SD decoders (models/models_MTMM_SD.py:361 lists it with the convolutions)
+        conv_types = (nn.Conv1d, nn.Conv2d, nn.Conv3d, nn.ConvTranspose2d)
         bn_types = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)
         for name, m in self.named_modules():
             if 'action' in name:

@@ -307,6 +307,8 @@ int ehgr_fc_consensus_bwd(const float* dlogits, const float* meanfeat, const flo
  *   logits fp32 [n,k]; labels int64 [n]; pred `dtype` [frames,ph,pw]; depth_gt fp32 [frames,gh,gw].
  *   out: loss_out[0] = total, loss_out[1] = CE, loss_out[2] = MSE (fp32, caller zeroes);
  *        dlogits fp32 [n,k]; dpred fp32 [frames,ph,pw]   (gradients of `total`).
+ *   n == 0 (logits / labels / dlogits may then be NULL): the depth term alone — the MTMM+SD step (train_mtmm_sd.py:240-293)
+ *   adds it, weighted (1 - alpha) * 0.01, to the terms of the self-distillation kernel below.
  * K13  self-distillation loss (train_sd.py:178-193,227-265), forward+backward in one launch:
  *   logits: HOST array of 4 device pointers fp32 [n,k] (final, mid1..3); feats: HOST array of 4 device
  *   pointers fp32 [rows,f] (final, mid1..3).

@@ -512,3 +512,77 @@ def test_sepconv_on_the_fused_chain_against_reference_fixture(name):
             assert (got - ref).abs().max().item() <= 3e-5 * max(ref.abs().max().item(), 1e-3 * gmax), pk
         if k.startswith(name + "_buf_") and train_bn:
             assert rel_err(dict(mod.named_buffers())[k[len(name + "_buf_"):]], torch.from_numpy(z[k])) < 1e-5, k
+
+
+def test_mtmm_sd_loss_matches_reference_fixture():
+    """Combined MTMM+SD loss (train_mtmm_sd.py:240-293; fixture = the reference statements with its own kd / feature
+    functions, tests/golden/heads.npz ms_*): total, and the gradient of every input, within 1e-5."""
+    import ehgr_b200 as E
+    z = np.load(GOLDEN / "heads.npz")
+    lg = [torch.from_numpy(z[f"ms_logits{i}"]).cuda().requires_grad_(True) for i in range(4)]
+    ft = [torch.from_numpy(z[f"ms_feat{i}"]).cuda().requires_grad_(True) for i in range(4)]
+    pred = torch.from_numpy(z["ms_gpred_in"]).cuda().requires_grad_(True)
+    depth = torch.from_numpy(z["ms_depth"].astype(np.float32)).cuda()
+    labels = torch.from_numpy(z["ms_labels"]).cuda()
+    total, terms, mse = E.losses.mtmm_sd_loss(lg, ft, pred, depth, labels, 0.1, 1e-6, 3.0)
+    assert abs(total.item() - float(z["ms_total"])) < 1e-5 * abs(float(z["ms_total"]))
+    assert abs((terms[0] + 0.01 * mse).item() - float(z["ms_loss"])) < 1e-5      # `loss` of the reference = CE + 0.01 MSE
+    total.backward()
+    for i in range(4):
+        assert rel_err(lg[i].grad, torch.from_numpy(z[f"ms_glogits{i}"])) < 1e-5
+        if i:
+            assert rel_err(ft[i].grad, torch.from_numpy(z[f"ms_gfeat{i}"])) < 1e-5
+    assert ft[0].grad is None or float(ft[0].grad.abs().max()) == 0.0
+    assert rel_err(pred.grad, torch.from_numpy(z["ms_gpred"])) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_mtmm_sd_step_against_oracle(dtype, tol):
+    """The combined MTMM+SD wrapper on TSM-MobileNetV2 (models/models_MTMM_SD.py:431-532 generalised: ten outputs for
+    modal='rgb_depth') + combined loss, one clip at 224x224, against the oracle (its decoders and loss are pinned to the
+    live reference); yardstick = the oracle at the same precision, as for the MTMM and SD steps."""
+    import ehgr_b200 as E
+    sd0 = O.build_mtmm_sd_state(83, "tsm", 8, seed=8)
+    with _quiet():
+        model = E.tsn_mtmm_sd.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8,
+                                  dropout=0.5, img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                                  modal='rgb_depth', temporal_module='tsm')
+    model.load_state_dict(sd0, strict=True)
+    model = model.cuda().train()
+    for d in model.modules():
+        if isinstance(d, torch.nn.Dropout):
+            d.eval()
+    rgb, depth, labels = O.synthetic_clip_batch(1, 8, 224, 83, seed=9)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False      # the ConvTranspose decoders run on library kernels
+    try:
+        with E.fused.compute_dtype(dtype):
+            outs = model(rgb.cuda())
+            total, terms, mse = E.losses.mtmm_sd_loss(outs[:4], outs[4:8], outs[9], depth.cuda(), labels.cuda())
+        total.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert [tuple(o.shape) for o in outs] == [(1, 83)] * 4 + [(8, 1280, 1, 1)] * 4 + [(8, 1, 224, 224), (8, 1, 56, 56)]
+    sd = O.clone_state(sd0, dtype=torch.float64)
+    ototal, _oloss, _ = O.mtmm_sd_train_step(sd, rgb.double(), depth.double(), labels)
+    if dtype == torch.float32:
+        sdy = O.clone_state(sd0)
+        ytotal, _, _ = O.mtmm_sd_train_step(sdy, rgb, depth, labels)
+    else:
+        sdy = {k: (v.detach().float().cuda().requires_grad_(v.requires_grad) if v.is_floating_point() else v.cuda())
+               for k, v in O.clone_state(sd0).items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ytotal, _, _ = O.mtmm_sd_train_step(sdy, rgb.cuda(), depth.cuda(), labels.cuda())
+    gmax = max(v.grad.abs().max().item() for v in sd.values() if v.grad is not None)
+
+    def grad_err(named):
+        return max(((g.detach().cpu().double() - sd[k].grad).abs().max().item() / gmax) for k, g in named if g is not None and sd[k].grad is not None)
+
+    ours = {"loss": abs(total.item() - ototal.item()) / abs(ototal.item()),
+            "grad": grad_err((k, p.grad) for k, p in model.named_parameters())}
+    ref = {"loss": abs(float(ytotal) - ototal.item()) / abs(ototal.item()),
+           "grad": grad_err((k, v.grad) for k, v in sdy.items() if v.is_floating_point())}
+    for k in ours:
+        assert ours[k] <= max(3.0 * ref[k], tol), (k, ours, ref)
+    # the local decoder feeds no loss term (train_mtmm_sd.py:240-252 uses g_depth_out only): no gradient reaches it
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in model.local_decoder.parameters())

@@ -113,3 +113,28 @@ def test_normalize_u8_refuses_cpu_tensors_and_wrong_dtypes():
     import ehgr_b200
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ehgr_b200.train_step.normalize_u8(torch.zeros((1, 3, 4, 4), dtype=torch.uint8))
+
+
+def test_mtmm_sd_wrapper_structure_and_policies():
+    """models_MTMM_SD.TSN generalised to MobileNetV2: strict state_dict contract with the oracle's key set, ConvTranspose
+    decoders as in models/models_MTMM_SD.py:226-249, policy groups (ConvTranspose2d counts as a convolution, :361)."""
+    import contextlib, io
+    import ehgr_b200 as E
+    from oracle import ref_oracle as O
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = E.tsn_mtmm_sd.TSN(83, 8, 'RGB', is_shift=True, partial_bn=False, base_model='mobilenetv2', shift_div=8, dropout=0.5,
+                              img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True, modal='rgb_depth',
+                              temporal_module='tsm')
+    m.load_state_dict(O.build_mtmm_sd_state(83, 'tsm', 8, 0), strict=True)
+    assert [type(l).__name__ for l in m.global_decoder] == ['ConvTranspose2d', 'BatchNorm2d', 'ConvTranspose2d', 'BatchNorm2d',
+                                                             'ConvTranspose2d', 'Sigmoid']
+    assert [type(l).__name__ for l in m.local_decoder] == ['ConvTranspose2d', 'BatchNorm2d', 'ConvTranspose2d', 'Sigmoid']
+    groups = {g['name']: g for g in m.get_optim_policies()}
+    n_all = sum(len(g['params']) for g in groups.values())
+    assert n_all == len(list(m.parameters()))
+    assert len(groups['normal_bias']['params']) == 5            # the five ConvTranspose2d biases
+    assert len(groups['lr5_weight']['params']) == 4 and len(groups['lr10_bias']['params']) == 4
+    import pytest
+    with pytest.raises(NotImplementedError):
+        with contextlib.redirect_stdout(io.StringIO()):
+            E.tsn_mtmm_sd.TSN(83, 8, 'RGB', base_model='mobilenetv2', pretrain=None, modal='rgb_depth_skeleton')
