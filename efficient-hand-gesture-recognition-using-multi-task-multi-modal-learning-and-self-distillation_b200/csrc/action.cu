@@ -27,7 +27,7 @@ __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + __expf(
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
+action_xs_generic_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ float smem[];
   const int C = a.c, Cr = a.cr, HW = a.h * a.w, CV = C / V, P = blockDim.x / CV;
@@ -106,6 +106,199 @@ action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs) {
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&a.pool[nt * C + i], s_pool[i]);   // spatial SUM (row splits add up)
   for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) atomicAdd(&a.qstats[i], static_cast<double>(s_qs[i]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane-group streaming kernels (round 2).  The first versions above staged every row reduction through
+// shared-memory float atomics with two block barriers per batch of rows (ncu / events: 5 % of the HBM peak on the
+// 56x56 site).  Here the channel vectors of a row sit in G consecutive lanes (G = power of two >= C/V, <= 32), a
+// warp covers 32/G rows, every per-row reduction is an xor-shuffle inside the group, and the row loop has no
+// barrier.  A CTA owns a row range of ONE CLIP and walks the T frames in order: the frame that is read as
+// "t+1" is read again as "t" and "t-1" by the same CTA a few microseconds later (L1/L2 hits: x is fetched from
+// HBM once).  Used when C/V <= 32 (all MobileNetV2 sites); wider inputs take the generic kernels.
+// ------------------------------------------------------------------------------------------------
+struct LaneGroup {
+  int G, lg, cvl, rg, rows_per_warp;
+  __device__ __forceinline__ LaneGroup(int cv_count, int lane) {
+    lg = 0;
+    while ((1 << lg) < cv_count) ++lg;
+    G = 1 << lg;
+    cvl = lane & (G - 1);
+    rg = lane >> lg;
+    rows_per_warp = 32 >> lg;
+  }
+  // sum over the lanes of a group (every lane of the group gets it)
+  __device__ __forceinline__ float group_sum(float v) const {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  // sum over the row groups of the warp, i.e. over lanes with equal cvl
+  __device__ __forceinline__ float rows_sum(float v) const {
+    for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+action_xs_kernel(Act a, const T* __restrict__ x, T* __restrict__ xs, int row_splits) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float smem[];
+  const int C = a.c, Cr = a.cr, HW = a.h * a.w, CV = C / V, Tn = a.t;
+  float* s_sq3 = smem;                         // [Cr][C]
+  float* s_qs = s_sq3 + Cr * C;                // [2*Cr]
+  for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) s_sq3[i] = a.p3_squeeze[i];
+  for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) s_qs[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const LaneGroup lgp(CV, lane);
+  const bool on = lgp.cvl < CV;
+  const int c0 = lgp.cvl * V;
+  const long long clip = blockIdx.x / row_splits;
+  const int split = blockIdx.x % row_splits;
+  const int rows_per_split = (HW + row_splits - 1) / row_splits;
+  const int r_begin = split * rows_per_split, r_end = min(HW, r_begin + rows_per_split);
+  const int rows_per_pass = (blockDim.x >> 5) * lgp.rows_per_warp;
+  float w0[V], w1[V], w2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    w0[i] = on ? a.shift_w[(c0 + i) * 3 + 0] : 0.f;
+    w1[i] = on ? a.shift_w[(c0 + i) * 3 + 1] : 0.f;
+    w2[i] = on ? a.shift_w[(c0 + i) * 3 + 2] : 0.f;
+  }
+  float qsum = 0.f, qsq = 0.f;                 // statistics of q[:, j] for j = cvl (lanes cvl < Cr)
+  const long long frame_elems = static_cast<long long>(HW) * C;
+  for (int t = 0; t < Tn; ++t) {
+    const long long nt = clip * Tn + t;
+    const bool has_prev = t > 0, has_next = t < Tn - 1;
+    float pool_acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) pool_acc[i] = 0.f;
+    // the loop bound is warp-uniform (the group reductions below are full-warp shuffles)
+    constexpr int U = 2;                         // rows per lane and iteration: 3U independent 16-byte loads in flight
+                                                 // (U = 4 at half the resident CTAs measured 20 % slower: the kernel
+                                                 // lives on warps in flight, not on loads per warp)
+    for (int rb = r_begin + warp * lgp.rows_per_warp; rb < r_end; rb += U * rows_per_pass) {
+      const int r0 = rb + lgp.rg;
+      uint4 rc[U], rp[U], rn[U];
+      bool live[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int row = r0 + u * rows_per_pass;
+        live[u] = on && row < r_end;
+        rc[u] = rp[u] = rn[u] = make_uint4(0, 0, 0, 0);
+        if (live[u]) {
+          const T* px = x + (nt * HW + row) * C + c0;
+          rc[u] = *reinterpret_cast<const uint4*>(px);
+          if (has_prev) rp[u] = *reinterpret_cast<const uint4*>(px - frame_elems);
+          if (has_next) rn[u] = *reinterpret_cast<const uint4*>(px + frame_elems);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int row = r0 + u * rows_per_pass;
+        const bool row_ok = row < r_end;           // uniform over the lanes of a group
+        const long long m = nt * HW + row;
+        float cur[V], prv[V], nxt[V], v[V];
+        load_vec<T, V>(reinterpret_cast<const T*>(&rc[u]), cur);
+        load_vec<T, V>(reinterpret_cast<const T*>(&rp[u]), prv);
+        load_vec<T, V>(reinterpret_cast<const T*>(&rn[u]), nxt);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = fmaf(w0[i], prv[i], fmaf(w1[i], cur[i], w2[i] * nxt[i]));
+        float s8 = 0.f;
+        if (live[u]) {
+          store_vec<T, V>(xs + m * C + c0, v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            // the reductions see the value as the consumers will read it back (storage rounding)
+            const float r = round_to<T>(v[i]);
+            v[i] = r;
+            s8 += r;
+            pool_acc[i] += r;
+          }
+        }
+        s8 = lgp.group_sum(s8);
+        if (row_ok && lgp.cvl == 0) a.mrow[m] = s8 / static_cast<float>(C);
+        for (int j = 0; j < Cr; ++j) {
+          float d = 0.f;
+          if (live[u]) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) d = fmaf(s_sq3[j * C + c0 + i], v[i], d);
+          }
+          d = lgp.group_sum(d);
+          if (row_ok && lgp.cvl == j) {            // lane j of the group owns q[:, j]: coalesced 4*Cr-byte rows
+            a.q[m * Cr + j] = d;
+            qsum += d;
+            qsq = fmaf(d, d, qsq);
+          }
+        }
+      }
+    }
+    // spatial sums of this frame: over the row groups of the warp, then one atomic per channel and warp
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float ps = lgp.rows_sum(pool_acc[i]);
+      if (on && lgp.rg == 0) atomicAdd(&a.pool[nt * C + c0 + i], ps);
+    }
+  }
+  qsum = lgp.rows_sum(qsum);
+  qsq = lgp.rows_sum(qsq);
+  if (lgp.rg == 0 && lgp.cvl < Cr) {
+    atomicAdd(&s_qs[lgp.cvl], qsum);
+    atomicAdd(&s_qs[Cr + lgp.cvl], qsq);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * Cr; i += blockDim.x) atomicAdd(&a.qstats[i], static_cast<double>(s_qs[i]));
+}
+
+// backward pass 1 in the same lane-group form: dG = gy * xs reduced over channels (-> dg1[m]) and over pixels
+// (-> dgc[frame][c], accumulated with one atomic per channel and warp: the caller zeroes dgc)
+template <typename T>
+__global__ void __launch_bounds__(256)
+action_bwd_reduce_kernel(Act a, const T* __restrict__ gy, const T* __restrict__ xs, int row_splits) {
+  constexpr int V = VecOf<T>::N;
+  const int C = a.c, HW = a.h * a.w, CV = C / V;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const LaneGroup lgp(CV, lane);
+  const bool on = lgp.cvl < CV;
+  const int c0 = lgp.cvl * V;
+  const long long nt = blockIdx.x / row_splits;
+  const int split = blockIdx.x % row_splits;
+  const int rows_per_split = (HW + row_splits - 1) / row_splits;
+  const int r_begin = split * rows_per_split, r_end = min(HW, r_begin + rows_per_split);
+  const int rows_per_pass = (blockDim.x >> 5) * lgp.rows_per_warp;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  for (int rb = r_begin + warp * lgp.rows_per_warp; rb < r_end; rb += 2 * rows_per_pass) {   // warp-uniform bound
+    const int r0 = rb + lgp.rg;
+    float g[2][V], v[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int row = r0 + u * rows_per_pass;
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[u][i] = v[u][i] = 0.f;
+      if (on && row < r_end) {
+        const long long off = (nt * HW + row) * C + c0;
+        load_vec<T, V>(gy + off, g[u]);
+        load_vec<T, V>(xs + off, v[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int row = r0 + u * rows_per_pass;
+      float s8 = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { const float d = g[u][i] * v[u][i]; s8 += d; acc[i] += d; }
+      s8 = lgp.group_sum(s8);
+      if (row < r_end && lgp.cvl == 0) a.dg1[nt * HW + row] = s8;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float cs = lgp.rows_sum(acc[i]);
+    if (on && lgp.rg == 0) atomicAdd(&a.dgc[nt * C + c0 + i], cs);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,7 +455,7 @@ __global__ void __launch_bounds__(256) action_gates_kernel(Act a) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-action_bwd_reduce_kernel(Act a, const T* __restrict__ gy, const T* __restrict__ xs) {
+action_bwd_reduce_generic_kernel(Act a, const T* __restrict__ gy, const T* __restrict__ xs) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ float smem[];
   const int C = a.c, HW = a.h * a.w, CV = C / V, P = blockDim.x / CV;
@@ -688,17 +881,34 @@ using namespace ehgr;
 extern "C" int ehgr_action_xs(const ehgr_action* a, const void* x, void* xs, int dtype, ehgr_stream_t stream) {
   if (int st = act_check(a, dtype)) return st;
   if (!x || !xs || !a->shift_w || !a->p3_squeeze || !a->mrow || !a->pool || !a->q || !a->qstats) return EHGR_E_NULL;
-  const int V = 16 / esize_of(dtype), CV = a->c / V, P = 256 / CV;
-  const size_t smem = (static_cast<size_t>(a->cr) * a->c + static_cast<size_t>(P) * (a->cr + 1) + a->c + 2 * a->cr) * sizeof(float);
+  const int V = 16 / esize_of(dtype), CV = a->c / V;
   const unsigned frames = static_cast<unsigned>(a->n) * a->t;
   const int hw = a->h * a->w;
+  cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(a->pool, 0, static_cast<size_t>(frames) * a->c * sizeof(float), s);      // pool is accumulated by atomics
+  if (CV <= 32) {
+    // lane-group kernel: a CTA = (clip, row range), ~4 CTAs per SM in total, at least one pass of rows per CTA
+    int lg = 0;
+    while ((1 << lg) < CV) ++lg;
+    const int rows_per_pass = 8 * (32 >> lg);
+    int splits = (4 * kNumSMs) / std::max(1, a->n);        // rounded DOWN: all CTAs resident in one wave (4 per SM)
+    splits = std::max(1, std::min(splits, (hw + 2 * rows_per_pass - 1) / (2 * rows_per_pass)));
+    const size_t smem = (static_cast<size_t>(a->cr) * a->c + 2 * a->cr) * sizeof(float);
+    const unsigned grid = static_cast<unsigned>(a->n) * splits;
+    if (dtype == EHGR_F32)
+      action_xs_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(x), static_cast<float*>(xs), splits);
+    else
+      action_xs_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<__nv_bfloat16*>(xs), splits);
+    return launch_status();
+  }
+  const int P = 256 / CV;
+  const size_t smem = (static_cast<size_t>(a->cr) * a->c + static_cast<size_t>(P) * (a->cr + 1) + a->c + 2 * a->cr) * sizeof(float);
   int splits = static_cast<int>((4 * kNumSMs + frames - 1) / std::max(1u, frames));      // ~4 CTAs per SM in total
   splits = std::max(1, std::min(std::min(splits, 16), (hw + P - 1) / P));
   const dim3 grid(frames, splits);
-  cudaStream_t s = as_stream(stream);
-  cudaMemsetAsync(a->pool, 0, static_cast<size_t>(frames) * a->c * sizeof(float), s);      // pool is accumulated by atomics
-  if (dtype == EHGR_F32) action_xs_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(x), static_cast<float*>(xs));
-  else action_xs_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xs));
+  if (dtype == EHGR_F32) action_xs_generic_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(x), static_cast<float*>(xs));
+  else action_xs_generic_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(xs));
   return launch_status();
 }
 
@@ -720,15 +930,31 @@ extern "C" int ehgr_action_bwd_reduce(const ehgr_action* a, const void* gy, cons
                                       ehgr_stream_t stream) {
   if (int st = act_check(a, dtype)) return st;
   if (!gy || !xs || !a->dg1 || !a->dgc) return EHGR_E_NULL;
-  const int V = 16 / esize_of(dtype), CV = a->c / V, P = 256 / CV;
-  const size_t smem = (static_cast<size_t>(P) + a->c) * sizeof(float);
-  const unsigned grid = static_cast<unsigned>(a->n) * a->t;
+  const int V = 16 / esize_of(dtype), CV = a->c / V;
+  const unsigned frames = static_cast<unsigned>(a->n) * a->t;
   cudaStream_t s = as_stream(stream);
+  if (CV <= 32) {
+    int lg = 0;
+    while ((1 << lg) < CV) ++lg;
+    const int rows_per_pass = 8 * (32 >> lg), hw = a->h * a->w;
+    int splits = static_cast<int>((4 * kNumSMs + frames - 1) / std::max(1u, frames));
+    splits = std::max(1, std::min(splits, (hw + 2 * rows_per_pass - 1) / (2 * rows_per_pass)));
+    cudaMemsetAsync(a->dgc, 0, static_cast<size_t>(frames) * a->c * sizeof(float), s);     // accumulated by atomics
+    if (dtype == EHGR_F32)
+      action_bwd_reduce_kernel<float><<<frames * splits, 256, 0, s>>>(*a, static_cast<const float*>(gy),
+                                                                      static_cast<const float*>(xs), splits);
+    else
+      action_bwd_reduce_kernel<__nv_bfloat16><<<frames * splits, 256, 0, s>>>(*a, static_cast<const __nv_bfloat16*>(gy),
+                                                                              static_cast<const __nv_bfloat16*>(xs), splits);
+    return launch_status();
+  }
+  const int P = 256 / CV;
+  const size_t smem = (static_cast<size_t>(P) + a->c) * sizeof(float);
   if (dtype == EHGR_F32)
-    action_bwd_reduce_kernel<float><<<grid, 256, smem, s>>>(*a, static_cast<const float*>(gy), static_cast<const float*>(xs));
+    action_bwd_reduce_generic_kernel<float><<<frames, 256, smem, s>>>(*a, static_cast<const float*>(gy), static_cast<const float*>(xs));
   else
-    action_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(gy),
-                                                                    static_cast<const __nv_bfloat16*>(xs));
+    action_bwd_reduce_generic_kernel<__nv_bfloat16><<<frames, 256, smem, s>>>(*a, static_cast<const __nv_bfloat16*>(gy),
+                                                                            static_cast<const __nv_bfloat16*>(xs));
   return launch_status();
 }
 
