@@ -32,6 +32,9 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 METRIC = "train clips/sec TSM-MBv2 8x224^2"
+WORKLOAD_NAMES = {"mtmm": "MTMM stage-1 step (fwd+loss+bwd+allreduce+SGD), RGB+pseudo-depth",
+                  "sd": "SD stage-2 step (fwd with 3 exit heads + SD loss + bwd + allreduce + SGD), RGB",
+                  "mtmm_sd": "MTMM+SD combined step (3 exit heads + depth decoders + combined loss), RGB+pseudo-depth"}
 UNIT = "clips/s"
 T_SEG, SIZE, NUM_CLASS = 8, 224, 83
 
@@ -45,9 +48,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--temporal", default="tsm", choices=["tsm", "action", "none"])
-    ap.add_argument("--workload", default="mtmm", choices=["mtmm", "sd"],
-                    help="mtmm: BASELINE configs[1] (the headline); sd: the stage-2 self-distillation step (configs[2]), "
-                         "reported for the record (its reference arm / CPU baseline are not wired)")
+    ap.add_argument("--workload", default="mtmm", choices=["mtmm", "sd", "mtmm_sd"],
+                    help="mtmm: BASELINE configs[1] (the headline); sd: the stage-2 self-distillation step (configs[2]); "
+                         "mtmm_sd: the combined stage of train_mtmm_sd.py")
+    ap.add_argument("--classes", type=int, default=83, help="83 = EgoGesture (configs[0-2]), 25 = NvGesture (configs[3])")
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-input", choices=["uint8", "float32"], default="uint8",
@@ -114,7 +118,10 @@ class ClockSampler(threading.Thread):
 def ncu_traffic():
     """DRAM bytes per launch of each library kernel, from the committed ncu capture of this same workload
     (profiles/r1_traffic.json; produced by the command named inside it) — never measured under the timer."""
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = os.path.join(here, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(here, "profiles", "r1_traffic.json")
     try:
         with open(p) as f:
             return json.load(f)["bytes_per_launch"]
@@ -129,19 +136,25 @@ def quiet():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(temporal: str, clips: int, steps: int, warmup: int):
-    """clips/s of the reference MTMM step (fwd + loss + bwd + SGD) on all host cores, fp32."""
+def cpu_reference_step_rate(temporal: str, clips: int, steps: int, warmup: int, workload: str = "mtmm", classes: int = 83):
+    """clips/s of the reference step (fwd + loss + bwd + SGD) of `workload` on all host cores, fp32."""
     from oracle import ref_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.clone_state(O.build_mtmm_state(NUM_CLASS, temporal, 8, seed=0))
+    build = {"mtmm": O.build_mtmm_state, "sd": O.build_sd_state, "mtmm_sd": O.build_mtmm_sd_state}[workload]
+    sd = O.clone_state(build(classes, temporal, 8, seed=0))
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.SGD(params, lr=0.00125, momentum=0.9, weight_decay=5e-4)
-    rgb, depth, labels = O.synthetic_clip_batch(clips, T_SEG, SIZE, NUM_CLASS, seed=0)
+    rgb, depth, labels = O.synthetic_clip_batch(clips, T_SEG, SIZE, classes, seed=0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.mtmm_train_step(sd, rgb, depth, labels, T_SEG, temporal, 8, True)
+        if workload == "mtmm":
+            O.mtmm_train_step(sd, rgb, depth, labels, T_SEG, temporal, 8, True)
+        elif workload == "sd":
+            O.sd_train_step(sd, rgb, labels, T_SEG, temporal, 8, True)
+        else:
+            O.mtmm_sd_train_step(sd, rgb, depth, labels, T_SEG, temporal, 8, True)
         opt.step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
@@ -155,13 +168,13 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 6))
     warm = max(1, min(args.warmup, 2))
-    v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, steps, warm)
+    v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, steps, warm, args.workload, args.classes)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"MTMM stage-1 step, {args.temporal.upper()}-MobileNetV2 RGB+pseudo-depth, "
-                               f"8x224^2, 83 classes; CPU sample = {args.cpu_clips} clips/step"},
+        "config": {"workload": f"{WORKLOAD_NAMES[args.workload]}, {args.temporal.upper()}-MobileNetV2, "
+                               f"8x224^2, {args.classes} classes; CPU sample = {args.cpu_clips} clips/step"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32, "
                                    f"{cores} threads"},
@@ -189,20 +202,21 @@ def run_ours(args):
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     torch.manual_seed(1)  # train_mtmm.py:43 default seed; identical initial weights on every rank
     sd_mode = args.workload == "sd"
+    NUM_CLASS = args.classes
+    common = dict(is_shift=(args.temporal != "none"), partial_bn=False, base_model='mobilenetv2', shift_div=8, dropout=0.5,
+                  img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
+                  temporal_module=("tsm" if args.temporal == "tsm" else "action"))
     with quiet():
         if sd_mode:
-            model = ehgr_b200.tsn_sd.TSN(NUM_CLASS, T_SEG, 'RGB', is_shift=(args.temporal != "none"), partial_bn=False,
-                                         base_model='mobilenetv2', shift_div=8, dropout=0.5, img_feature_dim=224,
-                                         pretrain=None, consensus_type='avg', fc_lr5=True,
-                                         temporal_module=("tsm" if args.temporal == "tsm" else "action"))
+            model = ehgr_b200.tsn_sd.TSN(NUM_CLASS, T_SEG, 'RGB', **common)
+        elif args.workload == "mtmm_sd":
+            model = ehgr_b200.tsn_mtmm_sd.TSN(NUM_CLASS, T_SEG, 'RGB', modal='rgb_depth', **common)
         else:
-            model = ehgr_b200.tsn_mtmm.TSN(NUM_CLASS, T_SEG, 'RGB', is_shift=(args.temporal != "none"), partial_bn=False,
-                                           base_model='mobilenetv2', shift_div=8, dropout=0.5, img_feature_dim=224,
-                                           pretrain=None, consensus_type='avg', fc_lr5=True, modal='rgb_depth',
-                                           temporal_module=("tsm" if args.temporal == "tsm" else "action"))
+            model = ehgr_b200.tsn_mtmm.TSN(NUM_CLASS, T_SEG, 'RGB', modal='rgb_depth', **common)
     model = model.to(dev)
     model.train()
-    step_cls = ehgr_b200.train_step.SDTrainStep if sd_mode else ehgr_b200.train_step.MTMMTrainStep
+    step_cls = {"sd": ehgr_b200.train_step.SDTrainStep, "mtmm_sd": ehgr_b200.train_step.MTMMSDTrainStep,
+                "mtmm": ehgr_b200.train_step.MTMMTrainStep}[args.workload]
     step = step_cls(model, compute_dtype=dtype, use_graph=not args.no_graph)
 
     def pick(batch):          # the SD step takes (rgb, labels); the MTMM step (rgb, depth, labels)
@@ -297,6 +311,10 @@ def run_ours(args):
     leg_e2e(max(args.warmup, 5))     # new input format: eager warm-up calls + graph capture happen here, untimed
     ms_e2e = timed(leg_e2e, args.steps)
 
+    # replicas must hold identical parameters after all those steps with NCCL inside the captured graph
+    in_sync = step.ranks_in_sync()
+    if not in_sync:
+        raise RuntimeError("data-parallel replicas diverged: parameter checksums differ between ranks")
     loss_value = float(last_loss["v"].item())
     if not (loss_value == loss_value and abs(loss_value) < 1e6):        # NaN / inf: the number would be meaningless
         raise RuntimeError(f"training loss is not finite ({loss_value}); refusing to report a throughput")
@@ -309,10 +327,8 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": (f"SD stage-2 step (fwd with 3 exit heads + SD loss + bwd + allreduce + SGD), "
-                                    f"{args.temporal.upper()}-MobileNetV2 RGB, 8x224^2, 83 classes, train-mode BN" if sd_mode else
-                                    f"MTMM stage-1 step (fwd+loss+bwd+allreduce+SGD), {args.temporal.upper()}-MobileNetV2 "
-                                    f"RGB+pseudo-depth, 8x224^2, 83 classes, train-mode BN"),
+            "config": {"workload": f"{WORKLOAD_NAMES[args.workload]}, {args.temporal.upper()}-MobileNetV2, 8x224^2, "
+                                   f"{NUM_CLASS} classes, train-mode BN",
                        "clips_per_gpu": B, "global_clips": B * world, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if step.use_graph else "eager",
                        "l2": "activations >> 126 MB L2 (inputs larger than L2; no explicit flush)"},
@@ -322,13 +338,17 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG, ncu_traffic()),
+            "roofline_traffic_source": "static: DRAM bytes per launch from the committed ncu capture profiles/r2_traffic.json "
+                                       "(same command, 1 GPU); not measured inside this run",
             "peaks": pk_kind,
             "final_loss": round(loss_value, 5),
             "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
             "ms_per_step_with_kernel_events": round(ms_prof / args.steps, 3),
         }
-        if not args.no_cpu_baseline and world == 1 and not sd_mode:
-            v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1)
+        if world > 1:
+            line["ranks_in_sync"] = bool(in_sync)
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1, args.workload, NUM_CLASS)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"3 steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32 oracle "
                                               f"port of the reference modules, {cores} threads"}
