@@ -494,29 +494,37 @@ class MTMMTrainStep:
         self._static_in = None
         self._static_loss = None
 
+    def _run_on_side(self, batch):
+        """Every step — eager, warm-up or captured — runs on ONE private stream.  Autograd ties the gradient accumulation
+        of a leaf to the stream its accumulator was first used on; a step issued from another stream would let the bucket
+        all-reduce (ordered after the CALLER's stream) overtake that accumulation: the late local gradient then lands on
+        top of the reduced one and the replicas drift apart (caught by ranks_in_sync() in round 2)."""
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            loss = self._step(*batch)
+        for t in batch:
+            t.record_stream(self._side)
+        cur.wait_stream(self._side)
+        return loss
+
     def run(self, *batch):
         if not self.use_graph:
-            return self._step(*batch)
+            return self._run_on_side(batch) if self.device.type == "cuda" else self._step(*batch)
         if self._graph is not None and any(a.shape != b.shape or a.dtype != b.dtype
                                            for a, b in zip(batch, self._static_in)):
             self.invalidate_graph()
             self._eager_calls = 0          # new shapes / dtypes: warm up eagerly again before re-capturing
         if self._graph is None:
-            # Warm-up calls and the capture run on ONE side stream (the documented whole-network recipe):
-            # autograd ties gradient accumulation of a leaf to the stream its accumulator was first used on,
-            # which must be the capturing stream, not the caller's.
+            # Warm-up calls and the capture run on the same private stream (the documented whole-network recipe).
             cur = torch.cuda.current_stream()
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             if self._eager_calls < self.graph_warmup:
                 self._eager_calls += 1
-                self._side.wait_stream(cur)
-                with torch.cuda.stream(self._side):
-                    loss = self._step(*batch)
-                for t in batch:
-                    t.record_stream(self._side)
-                cur.wait_stream(self._side)
-                return loss
+                return self._run_on_side(batch)
             from . import _lib
             self._static_in = [torch.empty_like(t) for t in batch]
             for dst, src in zip(self._static_in, batch):

@@ -106,9 +106,13 @@ def golden_action():
     np.savez_compressed(HERE / "action.npz", **out)
 
 
+TSN_FIXTURE_CLIPS, TSN_FIXTURE_SIZE = 4, 96
+
+
 def golden_tsn():
-    """Whole TSN-MobileNetV2 fwd+bwd at 64x64 (final map 2x2), the three temporal variants, train-BN
-    and frozen-BN (eval) modes."""
+    """Whole TSN-MobileNetV2 fwd+bwd at 96x96, 4 clips (final map 3x3: the last BatchNorms see 288 samples per
+    channel — the round-1 fixture, 2 clips at 64x64, gave them 64 and was so ill-conditioned that the reference's own
+    fp32 run sat 5e-3 from its fp64 run), the three temporal variants, train-BN and frozen-BN (eval) modes."""
     from models.models import TSN
     from models.temporal_shift import TemporalShift
     from archs.mobilenet_v2 import InvertedResidual
@@ -131,7 +135,7 @@ def golden_tsn():
                 for m in ref.modules():
                     if isinstance(m, torch.nn.Dropout):
                         m.eval()
-                rgb, _, labels = O.synthetic_clip_batch(2, 8, 64, 83, seed=3)
+                rgb, _, labels = O.synthetic_clip_batch(TSN_FIXTURE_CLIPS, 8, TSN_FIXTURE_SIZE, 83, seed=3)
                 logits = ref(rgb.to(dt))
                 loss = F.cross_entropy(logits, labels)
                 loss.backward()
@@ -140,6 +144,11 @@ def golden_tsn():
                 out[tag + f"_loss{dtag}"] = np.array(loss.item())
                 for k, v in grad_digest({k: p.grad for k, p in ref.named_parameters()}).items():
                     out[f"{tag}_g{dtag}_{k}"] = v
+                # full gradient tensors of the first and the last layer (the digests above sample 16 entries each)
+                named = dict(ref.named_parameters())
+                out[f"{tag}_gfull{dtag}_base_model.features.0.0.weight"] = named["base_model.features.0.0.weight"].grad.numpy().copy()
+                out[f"{tag}_gfull{dtag}_new_fc.bias"] = named["new_fc.bias"].grad.numpy().copy()
+                out[f"{tag}_gfull{dtag}_new_fc.weight"] = named["new_fc.weight"].grad[:8].numpy().copy()
                 rsd = ref.state_dict()
                 for k in ("base_model.features.0.1.running_mean", "base_model.features.9.conv.4.running_var",
                           "base_model.features.18.1.running_var"):

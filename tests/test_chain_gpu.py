@@ -119,6 +119,9 @@ def _digest(g):
     return np.concatenate([[g.sum().item(), g.abs().sum().item()], g[idx].numpy()])
 
 
+GRAD_NOISE_FACTOR = 4.0
+
+
 def _tsn(temporal):
     import ehgr_b200 as E
     with _quiet():
@@ -127,29 +130,18 @@ def _tsn(temporal):
                      temporal_module=("tsm" if temporal == "tsm" else "action"))
 
 
-def _retry_once(fn):
-    """The whole-network comparisons are bounded by a small multiple of the REFERENCE's own fp32-vs-fp64 error on an
-    ill-conditioned problem, and our reductions use atomics (run-to-run order): about one run in thirty lands just
-    outside the bound.  A systematic error fails both attempts; a noise excursion does not fail the suite."""
-    import functools
-
-    @functools.wraps(fn)
-    def wrapper(*args, **kwargs):
-        try:
-            return fn(*args, **kwargs)
-        except AssertionError:
-            torch.cuda.synchronize()
-            return fn(*args, **kwargs)
-    return wrapper
-
-
 @pytest.mark.parametrize("temporal", ["none", "tsm", "action"])
 @pytest.mark.parametrize("mode", ["train", "eval"])
-@_retry_once
 def test_tsn_against_reference_fixture(temporal, mode):
-    """Whole network, fp32 kernels, against the live-reference fixture.  The arbiter is the reference's
-    fp64 run; the bound is a small multiple of the reference's own fp32-vs-fp64 error on the same case
-    (the problem is ill-conditioned: see DESIGN.md 'Parity')."""
+    """Whole network (4 clips at 96x96), fp32 kernels, against the live-reference fixture; the arbiter is the reference's
+    fp64 run.
+      * logits, loss, running statistics: the flat 1e-5 of north_star, in both BatchNorm modes;
+      * gradients with FROZEN BatchNorm (eval): flat 1e-5 as well;
+      * gradients with batch-statistics BatchNorm (train): the reference's OWN fp32 run is 0.6-1.2e-2 away from its fp64
+        run on this fixture (52 BatchNorm layers back-to-back with random weights: every layer's backward subtracts two
+        nearly equal means) — no fp32 implementation can hold 1e-5 there, PyTorch's included.  The bound is
+        GRAD_NOISE_FACTOR x that measured reference noise; the 1e-5 line for train-mode gradients is held per block
+        (test_inverted_residual_block) where the problem is well conditioned."""
     z = np.load(GOLDEN / "tsn_mbv2.npz")
     tag = f"{temporal}_{mode}"
     m = _tsn(temporal)
@@ -158,11 +150,10 @@ def test_tsn_against_reference_fixture(temporal, mode):
     for d in m.modules():
         if isinstance(d, torch.nn.Dropout):
             d.eval()
-    rgb, _, labels = O.synthetic_clip_batch(2, 8, 64, 83, seed=3)
+    rgb, _, labels = O.synthetic_clip_batch(4, 8, 96, 83, seed=3)
     logits = m(rgb.cuda())
     ref64 = torch.from_numpy(z[tag + "_logits64"])
-    ref32 = torch.from_numpy(z[tag + "_logits"])
-    assert rel_err(logits, ref64) < max(3 * rel_err(ref32, ref64), 1e-5)
+    assert rel_err(logits, ref64) < 1e-5
     loss = F.cross_entropy(logits, labels.cuda())
     assert abs(loss.item() - float(z[tag + "_loss64"])) < 1e-5
     loss.backward()
@@ -174,7 +165,15 @@ def test_tsn_against_reference_fixture(temporal, mode):
         if k.startswith(tag + "_g64_"):
             got = _digest(params[k[len(tag + "_g64_"):]].grad)
             worst = max(worst, np.abs(got[2:] - z[k][2:]).max() / scale)
-    assert worst < max(3 * ref_noise, 1e-5), (worst, ref_noise)
+    # full gradient tensors of the first and the last layer (stem weight, classifier bias, 8 classifier rows)
+    for k in z.files:
+        if k.startswith(tag + "_gfull64_"):
+            name = k[len(tag + "_gfull64_"):]
+            got = params[name].grad.detach().cpu().double()
+            ref = torch.from_numpy(z[k]).double()
+            worst = max(worst, float((got[:ref.shape[0]] - ref).abs().max()) / scale)
+    print(f"[{tag}] gradient error {worst:.3e}, reference fp32-vs-fp64 {ref_noise:.3e}")
+    assert worst < (1e-5 if mode == "eval" else GRAD_NOISE_FACTOR * ref_noise), (worst, ref_noise)
     if mode == "train":
         sd = m.state_dict()
         for k in z.files:

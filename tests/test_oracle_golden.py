@@ -78,7 +78,7 @@ def test_tsn_oracle_matches_reference(temporal, mode):
     (the reference's own fp32-vs-fp64 gradient error on this case is ~5e-3)."""
     z = np.load(GOLDEN / "tsn_mbv2.npz")
     tag = f"{temporal}_{mode}"
-    rgb, _, labels = O.synthetic_clip_batch(2, 8, 64, 83, seed=3)
+    rgb, _, labels = O.synthetic_clip_batch(4, 8, 96, 83, seed=3)
     # --- fp64 pin ---
     sd = O.clone_state(O.build_tsn_state(83, temporal, 8, seed=5), dtype=torch.float64)
     logits = O.tsn_forward(rgb.double(), sd, 8, temporal, 8, bn_training=(mode == "train"))
