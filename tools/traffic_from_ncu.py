@@ -14,7 +14,7 @@ FAMILY = {  # entry point -> substring of the kernel name
     "ehgr_pw_wgrad": "pw_wgrad_tc_kernel", "ehgr_dw_bwd": "dw_bwd_sw_kernel", "ehgr_dw_fwd_bn": "dw_fwd_sw_kernel",
     "ehgr_dw_fwd": "dw_fwd_sw_kernel", "ehgr_bn_bwd_reduce_fin": "bn_bwd_reduce_kernel", "ehgr_bn_bwd_reduce": "bn_bwd_reduce_kernel",
     "ehgr_row_apply": "row_apply_kernel", "ehgr_stem_fwd_bn": "stem_fwd32", "ehgr_stem_wgrad": "stem_wgrad32",
-    "ehgr_conv3_fwd": "conv3", "ehgr_action_xs": "action_xs", "ehgr_action_bwd_dxs": "action_bwd_dxs",
+    "ehgr_action_xs": "action_xs", "ehgr_action_bwd_dxs": "action_bwd_dxs",
 }
 
 
