@@ -17,6 +17,7 @@ _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / "csrc" / "libehgr_b200.so"
 
 F32, BF16 = 0, 1
+ABI_VERSION = 2
 NCHW, NHWC = 0, 1
 
 _lib = None
@@ -35,7 +36,7 @@ def _load() -> ctypes.CDLL:
     lib.ehgr_status_string.restype = c_char_p
     lib.ehgr_status_string.argtypes = [c_int]
     lib.ehgr_launch_count.restype = c_longlong
-    if lib.ehgr_abi_version() != 1:
+    if lib.ehgr_abi_version() != ABI_VERSION:
         raise RuntimeError("libehgr_b200.so ABI version mismatch; rebuild with EHGR_REBUILD=1")
     _declare(lib)
     _lib = lib
@@ -87,7 +88,8 @@ class RowOp(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_int32), ("relu6", ctypes.c_int32), ("in1", c_void_p), ("in2", c_void_p),
                 ("scale", c_void_p), ("shift", c_void_p), ("ca", c_void_p), ("cb", c_void_p), ("cc", c_void_p),
                 ("n_segment", ctypes.c_int32), ("fold", ctypes.c_int32), ("hw", ctypes.c_int32),
-                ("shift_dir", ctypes.c_int32)]
+                ("shift_dir", ctypes.c_int32), ("cv_h", ctypes.c_int32), ("cv_w", ctypes.c_int32),
+                ("cv_cin", ctypes.c_int32), ("cv_up", ctypes.c_int32)]
 
 
 class ActionArgs(ctypes.Structure):
@@ -131,6 +133,11 @@ SIGNATURES = {
     "ehgr_pw_gemm_w16": [_R, _P, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_pw_gemm_bn": [_R, _P, _P, _I, _P, _P, _P, _L, _I, _I, _I, _I, _BF, _P],
     "ehgr_pw_wgrad": [_R, _R, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_conv3_pack": [_P, _P, _P, _I, _I, _I, _P],
+    "ehgr_conv3_unpack_grad": [_P, _P, _I, _I, _P],
+    "ehgr_upsample2_bwd": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_depth_head_fwd": [_R, _P, _P, _P, _L, _I, _I, _P],
+    "ehgr_depth_head_bwd": [_R, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "ehgr_dw_fwd": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_dw_fwd_bn": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _BF, _P],
     "ehgr_dw_dgrad": [_R, _P, _P, _I, _I, _I, _I, _I, _I, _P],

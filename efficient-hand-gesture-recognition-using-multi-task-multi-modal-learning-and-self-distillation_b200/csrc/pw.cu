@@ -44,8 +44,9 @@ extern "C" int ehgr_pw_gemm_bn(const ehgr_rowop* a, const float* w, const void* 
   if (int st = check_bnfin(fin, stats)) return st;
   if (es == 0) return EHGR_E_DTYPE;
   if (!w || !out) return EHGR_E_NULL;
-  if (int st = validate_rowop(a, es)) return st;
+  if (int st = validate_rowop(a, es, true)) return st;
   if (M < 0 || K <= 0 || N <= 0 || (K % 8) || (N % 8)) return EHGR_E_SHAPE;
+  if (a->mode == EHGR_ROW_CONV3 && (K != 9 * a->cv_cin || M % a->hw || M * a->cv_cin > 0x7fffffffLL)) return EHGR_E_SHAPE;   // 32-bit element offsets
   if (!aligned_to(out, 16) || !aligned_to(w, 16) || (w16 && !aligned_to(w16, 16)) || (addend && !aligned_to(addend, 16)) ||
       (stats && !aligned_to(stats, 8)))
     return EHGR_E_ALIGN;
@@ -65,8 +66,9 @@ extern "C" int ehgr_pw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* d
   if (es == 0) return EHGR_E_DTYPE;
   if (!dw) return EHGR_E_NULL;
   if (int st = validate_rowop(dy, es)) return st;
-  if (int st = validate_rowop(a, es)) return st;
+  if (int st = validate_rowop(a, es, true)) return st;
   if (M < 0 || K <= 0 || N <= 0 || (K % 8) || (N % 8)) return EHGR_E_SHAPE;
+  if (a->mode == EHGR_ROW_CONV3 && (K != 9 * a->cv_cin || M % a->hw || M * a->cv_cin > 0x7fffffffLL)) return EHGR_E_SHAPE;   // 32-bit element offsets
   if (!aligned_to(dw, 16)) return EHGR_E_ALIGN;
   if (M == 0) return EHGR_OK;
   cudaStream_t s = as_stream(stream);

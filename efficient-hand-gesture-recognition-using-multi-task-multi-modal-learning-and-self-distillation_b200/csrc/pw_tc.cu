@@ -93,31 +93,45 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
     // Lanes run along the CONTIGUOUS direction of the weight array (k-chunks of one row n for the K-major
     // form, n-chunks of one row k for the MN-major form): coalesced 128-byte reads, no per-chunk division.
     const uint32_t dst32 = smem_u32(dst);
+    // Source / destination / live counts advance by constants: a producer warp streams a slice with every stage, so
+    // the per-copy instruction count is what bounds the stage rate of the weight-streaming (small-M, large-K) layers.
     if (!p.w_is_kn) {
-      const int step = nthreads >> 3;
+      const int step = nthreads >> 3;                   // 4 (one warp) or a multiple of 8 (whole CTA)
+      const int nl0 = tid >> 3;
       for (int kg = tid & 7; kg < kv; kg += 8) {        // kv > 8 only for the resident form (whole K at once)
         const int k = k_base + kg * 8;
         const bool k_ok = k < p.K;
+        const __nv_bfloat16* src = p.w16 + static_cast<size_t>(n0 + nl0) * p.K + k;
+        const size_t sstep = static_cast<size_t>(step) * p.K;
+        int left = k_ok ? p.N - n0 - nl0 : 0;           // > 0: row n exists
+        if (step >= 8) {
+          uint32_t d = dst32 + (nl0 >> 3) * gs + kg * 128 + (nl0 & 7) * 16;
+          const uint32_t dstep = static_cast<uint32_t>((step >> 3) * gs);
 #pragma unroll 4
-        for (int nl = tid >> 3; nl < p.BN; nl += step) {
-          const int n = n0 + nl;
-          const bool ok = k_ok && n < p.N;
-          cp_async16(dst32 + (nl >> 3) * gs + kg * 128 + (nl & 7) * 16, ok ? p.w16 + static_cast<size_t>(n) * p.K + k : p.w16,
-                     ok ? 16u : 0u);
+          for (int nl = nl0; nl < p.BN; nl += step, d += dstep, src += sstep, left -= step)
+            cp_async16(d, left > 0 ? src : p.w16, left > 0 ? 16u : 0u);
+        } else {                                        // step == 4: rows nl0 and nl0 + 4 of every 8-row group
+          uint32_t d = dst32 + kg * 128 + nl0 * 16;
+#pragma unroll 4
+          for (int g = 0; g < (p.BN >> 3); ++g, d += gs, src += 2 * sstep, left -= 8) {
+            cp_async16(d, left > 0 ? src : p.w16, left > 0 ? 16u : 0u);
+            cp_async16(d + 64, left > 4 ? src + sstep : p.w16, left > 4 ? 16u : 0u);
+          }
         }
       }
     } else {
       const int ng = tid & 31, step = nthreads >> 5;
       const int n = n0 + ng * 8;
-      const bool n_ok = n < p.N;
       if (ng < (p.BN >> 3)) {
+        const int kl0 = tid >> 5;
+        // (kl >> 3) * 128 + (kl & 7) * 16 == kl * 16: the k rows of one n group are contiguous in the stage
+        uint32_t d = dst32 + ng * gs + kl0 * 16;
+        const __nv_bfloat16* src = p.w16 + static_cast<size_t>(k_base + kl0) * p.N + n;
+        const size_t sstep = static_cast<size_t>(step) * p.N;
+        int left = n < p.N ? p.K - k_base - kl0 : 0;
 #pragma unroll 4
-        for (int kl = tid >> 5; kl < kvalid; kl += step) {
-          const int k = k_base + kl;
-          const bool ok = n_ok && k < p.K;
-          cp_async16(dst32 + ng * gs + (kl >> 3) * 128 + (kl & 7) * 16, ok ? p.w16 + static_cast<size_t>(k) * p.N + n : p.w16,
-                     ok ? 16u : 0u);
-        }
+        for (int kl = kl0; kl < kvalid; kl += step, d += 16 * step, src += sstep, left -= step)
+          cp_async16(d, left > 0 ? src : p.w16, left > 0 ? 16u : 0u);
       }
     }
     return;
@@ -207,6 +221,10 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
 
   const int total_tiles = p.m_tiles * p.n_chunks;
   const int k_stages = (p.K + BK - 1) / BK;
+  // Streamed weights: every CTA would ask L2 for the SAME 64-wide weight slice at the same moment (hot lines served
+  // one requester at a time).  Each CTA therefore walks the reduction in its own rotation (accumulation order is free),
+  // so that at any instant the CTAs read different slices.
+  const int k_rot = p.b_resident ? 0 : static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(k_stages));
   const int a_sbo = p.a_bytes >> 4;                 // BYTES between 8-row groups of an A stage = min(Kp,64)*16
 
   if (warp < kProducerWarps) {
@@ -219,6 +237,10 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
     uint32_t ph = 0;
     const int tile_step = gridDim.x / p.n_chunks;            // grid is a multiple of n_chunks
     int m_tile = blockIdx.x / p.n_chunks;
+    // CONV3: per-warp row table (1 KB each) behind the epilogue staging rows
+    [[maybe_unused]] const uint32_t conv_tab32 =
+        smem_u32(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + static_cast<uint32_t>(kEpiWarps * 32 * p.epi_pitch);
+    [[maybe_unused]] int tab_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x, m_tile += tile_step) {
       const long long m0 = static_cast<long long>(m_tile) * BM;
       for (int ks = 0; ks < k_stages; ++ks, ++turn, ++s) {
@@ -231,7 +253,8 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
         if (turn != warp) continue;
         const uint32_t parity = ph ^ 1;
         uint8_t* a_dst = ring + s * p.stage_bytes;
-        const int k_base = ks * BK;
+        const int kr = ks + k_rot < k_stages ? ks + k_rot : ks + k_rot - k_stages;
+        const int k_base = kr * BK;
         const int kvalid = min(BK, Kp - k_base);     // multiple of 16
         const int kv = kvalid >> 3;                    // 2, 4, 6 or 8 channel vectors per row
         const int kvp = kv < 4 ? kv : 4;               // channel vectors handled per pass by the 4 lane slots
@@ -241,6 +264,84 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
           constexpr int mode = kMode;
           const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(p.a.in1);
           const uint32_t a_dst32 = smem_u32(a_dst);
+          if constexpr (mode == EHGR_ROW_CONV3) {
+            // Implicit-GEMM gather of a dense 3x3 convolution: column k = (tap, channel), row = output pixel.  The rows of
+            // a tile are decomposed ONCE per tile into a per-warp table (element offset of the pixel in the stored tensor,
+            // ho | wo << 16; rows past M get ho = 0x7fff and are never live); a stage then costs a table read, two
+            // bounds checks and an add per 16-byte copy.  K is a multiple of 32, so a lane always owns the 16 rows
+            // r, r+8, ... of its channel vector (f == 1).
+            const int Wo = p.a.cv_w, Ho = p.a.cv_h, up = p.a.cv_up, cin = p.a.cv_cin;
+            const int Ws = Wo >> up;
+            const uint32_t tab32 = conv_tab32 + static_cast<uint32_t>(warp) * 1024u;
+            if (tab_tile != tile) {
+              const int Hs = Ho >> up, hw = p.a.hw;
+#pragma unroll 1
+              for (int i = lane; i < BM; i += 32) {
+                const long long m = m0 + i;
+                uint32_t off = 0, hwp = 0x7fffu;
+                if (m < p.M) {
+                  const int mi = static_cast<int>(m);
+                  const int fr = mi / hw, rem = mi - fr * hw;
+                  const int ho = rem / Wo, wo = rem - ho * Wo;
+                  off = static_cast<uint32_t>(((fr * Hs + (ho >> up)) * Ws + (wo >> up)) * cin);
+                  hwp = static_cast<uint32_t>(ho) | (static_cast<uint32_t>(wo) << 16);
+                }
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(tab32 + i * 8), "r"(off), "r"(hwp) : "memory");
+              }
+              __syncwarp();
+              tab_tile = tile;
+            }
+            const bool affine = p.a.scale != nullptr;
+#pragma unroll 1
+            for (int round = 0; round < (affine ? 2 : 1); ++round) {
+              // round 0: the copies; round 1 (lazy BatchNorm + activation of the producer layer): the live pixels in place
+              RowOp ac = p.a;
+              ac.mode = EHGR_ROW_AFFINE;
+#pragma unroll 1
+              for (int pass = 0; pass * 4 < kv; ++pass) {
+                const int k8 = pass * 4 + (slot % kvp);
+                const int k = k_base + k8 * 8;
+                if (k8 >= kv) continue;
+                const bool kin = k < p.K;
+                const int rg0 = slot / kvp;
+                const int tap = kin ? k / cin : 0, ty = tap / 3;
+                const int dy = ty - 1, dx = tap - ty * 3 - 1, c = k - tap * cin;
+                const int tapoff = (dy * Ws + dx) * cin + c;       // up == 0: the tap is a constant element offset
+                RowLoader<__nv_bfloat16, 8, false, false> ld;
+                if (round) {
+                  if (!kin) continue;
+                  ld.init(ac, c, cin);
+                }
+                uint32_t dst = a_dst32 + rg0 * a_sbo + k8 * 128 + r * 16;
+                uint32_t tp = tab32 + (rg0 * 8 + r) * 8;
+                const uint32_t dstep = static_cast<uint32_t>(f * a_sbo), tstep = static_cast<uint32_t>(f * 64);
+#pragma unroll 4
+                for (int rg = rg0; rg < 16; rg += f, dst += dstep, tp += tstep) {
+                  uint32_t off, hwp;
+                  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(off), "=r"(hwp) : "r"(tp));
+                  const int ho = static_cast<int>(hwp & 0xffffu), wo = static_cast<int>(hwp >> 16);
+                  const bool live = kin && static_cast<unsigned>(ho + dy) < static_cast<unsigned>(Ho) &&
+                                    static_cast<unsigned>(wo + dx) < static_cast<unsigned>(Wo);
+                  if (round) {
+                    if (live) {
+                      RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
+                      raw.a = lds128(dst);
+                      sts128(dst, ld.finish_packed(ac, raw));
+                    }
+                    continue;
+                  }
+                  // up == 1: (ho + dy) >> 1 = (ho >> 1) + ((dy + (ho & 1)) >> 1), likewise for the column
+                  const int o = up ? (((dy + (ho & 1)) >> 1) * Ws + ((dx + (wo & 1)) >> 1)) * cin + c : tapoff;
+                  const __nv_bfloat16* src = in1 + (static_cast<int>(off) + o);
+                  cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+                }
+              }
+              if (round == 0) {
+                if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+                cp_async_wait_all();
+              }
+            }
+          } else {
           // SHIFT: frame / segment index of the tile's first row (rows advance by < 128 inside a stage)
           int t0 = 0, rem0 = 0;
           if (mode == EHGR_ROW_SHIFT) {
@@ -354,6 +455,7 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
               }
             }
           }
+          }   // mode != CONV3
         } else {
         bool waited = false;
 #pragma unroll 1
@@ -429,7 +531,8 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
           if (s == p.n_stages) { s = 0; ph ^= 1; a_lo = ring_lo; }
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const int ksteps = ks == k_stages - 1 ? last_ksteps : BK / 16;
+          const int kr = ks + k_rot < k_stages ? ks + k_rot : ks + k_rot - k_stages;
+          const int ksteps = kr == k_stages - 1 ? last_ksteps : BK / 16;
           // one K=16 step = two 8-element core matrices along K = 256 bytes = 16 address units
           const uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(ks) * 64u : a_lo + abytes16;
 #pragma unroll
@@ -619,15 +722,18 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   // chunk count that leaves at least four ring stages, else the one with the deepest ring.  Input-heavy shapes
   // (K >= N: the project / dgrad-of-expand layers) never take extra chunks: re-reading A costs more than a shallow ring.
   const int Np = (N + 15) & ~15;
-  const int epi_warps = K >= N ? 8 : 16, parts = epi_warps / 4;
+  const int epi_warps = (K >= N || a.mode == EHGR_ROW_CONV3) ? 8 : 16, parts = epi_warps / 4;
   int best_chunks = 0, best_stages = -1, bar_bytes = 0, b_res = 0;
+  const int conv_tab = a.mode == EHGR_ROW_CONV3 ? tc::kProducerWarps * 1024 : 0;   // per-warp row tables
   const int min_chunks = (Np + 255) / 256;
-  for (int chunks = min_chunks; chunks <= min_chunks + (K >= N ? 0 : 3); ++chunks) {
+  // (CONV3: K = 9*cin is large and the operand comes out of L2 — a deeper ring is worth narrower tiles)
+  const bool extra_chunks = epi_warps != 8 || a.mode == EHGR_ROW_CONV3;
+  for (int chunks = min_chunks; chunks <= min_chunks + (extra_chunks ? 3 : 0); ++chunks) {
     int bn = (Np / chunks + 15) & ~15;
     while (bn * chunks < Np) bn += 16;
     if (bn > 256 || bn < 16) continue;
     const int pitch = ((bn >> 4) + parts - 1) / parts * 32 + 16;
-    const int bar = tc::kTailBytes + epi_warps * 32 * pitch;
+    const int bar = tc::kTailBytes + epi_warps * 32 * pitch + conv_tab;
     const int bres = bn * Kp * 2;
     const bool resident = bres + 6 * p.a_bytes + bar <= kBudget;
     const int stage = p.a_bytes + (resident ? 0 : bn * tc::BK * 2);
@@ -643,7 +749,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   p.tmem_cols = cols;
   const int n_cc = p.BN >> 4;
   p.epi_pitch = (n_cc + parts - 1) / parts * 32 + 16;           // odd multiple of 16 bytes: conflict-free row stores
-  bar_bytes = tc::kTailBytes + epi_warps * 32 * p.epi_pitch;
+  bar_bytes = tc::kTailBytes + epi_warps * 32 * p.epi_pitch + conv_tab;
   b_res = p.BN * Kp * 2;
   // weights resident when that still leaves >= 6 A stages (the large-M layers all qualify)
   p.b_resident = (b_res + 6 * p.a_bytes + bar_bytes <= kBudget) ? 1 : 0;
@@ -670,6 +776,10 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
     case EHGR_ROW_AFFINE: go(std::integral_constant<int, EHGR_ROW_AFFINE>{}); break;
     case EHGR_ROW_SHIFT: go(std::integral_constant<int, EHGR_ROW_SHIFT>{}); break;
     case EHGR_ROW_GATE: go(std::integral_constant<int, EHGR_ROW_GATE>{}); break;
+    case EHGR_ROW_CONV3:   // K = 9*cin >= N for every decoder layer: the 8-epilogue-warp form only
+      ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8>, kBudget);
+      tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p);
+      break;
     default: go(std::integral_constant<int, EHGR_ROW_BNBWD>{}); break;
   }
   return launch_status();

@@ -77,6 +77,29 @@ __device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_
   if (!w.on) return;
   const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(op.in1);
   const int c = c_base + w.g * 8;
+  if constexpr (kMode == EHGR_ROW_CONV3) {
+    // im2col gather (see rowop.cuh): the lane's column c = (tap, channel) is fixed, its rows walk the output grid
+    const Conv3Tap tp = conv3_tap(op, c);
+    const int Wo = op.cv_w, Ho = op.cv_h;
+    const int mfirst = static_cast<int>(m_base) + w.rsub;
+    int fr = mfirst / op.hw;
+    const int rem = mfirst - fr * op.hw;
+    int ho = rem / Wo, wo = rem - ho * Wo, m = mfirst;
+    const int Mi = static_cast<int>(M);
+#pragma unroll 2
+    for (int row = w.rsub; row < kMS; row += w.rstep) {
+      const int hs = ho + tp.dy, ws = wo + tp.dx;
+      const bool live = m < Mi && static_cast<unsigned>(hs) < static_cast<unsigned>(Ho) &&
+                        static_cast<unsigned>(ws) < static_cast<unsigned>(Wo);
+      const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
+      cp_async16(dst, live ? in1 + conv3_src(op, fr, hs, ws) + tp.c : in1, live ? 16u : 0u);
+      m += w.rstep;
+      wo += w.rstep;
+      while (wo >= Wo) { wo -= Wo; ++ho; }
+      while (ho >= Ho) { ho -= Ho; ++fr; }
+    }
+    return;
+  }
   int t0 = 0, rem0 = 0;
   const int dir = op.shift_dir < 0 ? -1 : 1;
   if (kMode == EHGR_ROW_SHIFT && w.cls != 2) {
@@ -123,7 +146,36 @@ __device__ __forceinline__ void wg_affine_inplace(const RowOp& op, const WgLane&
   }
 }
 
-// kAsync: dy is PLAIN and a is PLAIN / AFFINE / SHIFT (what the fused chain issues); otherwise the register path.
+// CONV3 with a lazy BatchNorm+activation: transform the live (in-grid) pixels of the lane's column in place
+__device__ __forceinline__ void wg_conv3_affine_inplace(const RowOp& op, const WgLane& w, int c_base,
+                                                        const RowLoader<__nv_bfloat16, 8, false, false>& ld, uint32_t dst_base,
+                                                        int gs, long long m_base, long long M) {
+  if (!w.on) return;
+  const Conv3Tap tp = conv3_tap(op, c_base + w.g * 8);
+  const int Wo = op.cv_w, Ho = op.cv_h;
+  const int mfirst = static_cast<int>(m_base) + w.rsub;
+  const int rem = mfirst % op.hw;
+  int ho = rem / Wo, wo = rem - ho * Wo, m = mfirst;
+  const int Mi = static_cast<int>(M);
+  RowOp oc = op;
+  oc.mode = EHGR_ROW_AFFINE;
+#pragma unroll 2
+  for (int row = w.rsub; row < kMS; row += w.rstep) {
+    if (m < Mi && static_cast<unsigned>(ho + tp.dy) < static_cast<unsigned>(Ho) &&
+        static_cast<unsigned>(wo + tp.dx) < static_cast<unsigned>(Wo)) {
+      const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
+      RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
+      raw.a = lds128(dst);
+      sts128(dst, ld.finish_packed(oc, raw));
+    }
+    m += w.rstep;
+    wo += w.rstep;
+    while (wo >= Wo) { wo -= Wo; ++ho; }
+    while (ho >= Ho) ho -= Ho;
+  }
+}
+
+// kAsync: dy is PLAIN and a is PLAIN / AFFINE / SHIFT / CONV3 (what the fused chain issues); otherwise the register path.
 // kAMode: mode of operand a as a compile-time constant (PLAIN / AFFINE / SHIFT: asynchronous path, dy PLAIN);
 // -1: the generic register path.
 template <int kAMode>
@@ -174,6 +226,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
         ac.mode = EHGR_ROW_AFFINE;
         ld_a.init(ac, k0 + wl_a.g * 8, p.K);
       }
+      if (kAMode == EHGR_ROW_CONV3 && wl_a.on && p.a.scale) {
+        RowOp ac = p.a;
+        ac.mode = EHGR_ROW_AFFINE;
+        ld_a.init(ac, conv3_tap(p.a, k0 + wl_a.g * 8).c, p.a.cv_cin);
+      }
       int s = 0, turn = 0;
       uint32_t ph = 0;
       for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++s, ++turn) {
@@ -186,6 +243,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
         wg_copy<kAMode>(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M);
         cp_async_wait_all();
         if (kAMode == EHGR_ROW_AFFINE) wg_affine_inplace(p.a, wl_a, ld_a, a_dst, gs, mc * kMS, p.M);
+        if (kAMode == EHGR_ROW_CONV3 && p.a.scale) wg_conv3_affine_inplace(p.a, wl_a, k0, ld_a, a_dst, gs, mc * kMS, p.M);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
@@ -303,10 +361,11 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
 }  // namespace tc
 
 bool pw_wgrad_tc_supported(const RowOp& dy, const RowOp& a, long long M, int K, int N, int dtype) {
-  (void)dy; (void)a;
   if (dtype != EHGR_BF16) return false;
   if (K % 8 || N % 8 || K < 8 || N < 8) return false;
   if (M < 1) return false;
+  if (a.mode == EHGR_ROW_CONV3 && dy.mode != EHGR_ROW_PLAIN) return false;   // the register path has no gather
+  if (dy.mode == EHGR_ROW_CONV3) return false;
   return true;
 }
 
@@ -328,8 +387,8 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   p.stage_bytes = (16 + p.BKc / 8) * tc::kWgGroupStride;
   p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes) / p.stage_bytes));
   const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes;
-  const bool async = dy.mode == EHGR_ROW_PLAIN &&
-                     (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_SHIFT);
+  const bool async = dy.mode == EHGR_ROW_PLAIN && (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE ||
+                                                   a.mode == EHGR_ROW_SHIFT || a.mode == EHGR_ROW_CONV3);
   auto go = [&](auto mode_tag) {
     constexpr int kAMode = decltype(mode_tag)::value;
     ensure_smem(tc::pw_wgrad_tc_kernel<kAMode>, kBudget);
@@ -338,6 +397,7 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   if (!async) go(std::integral_constant<int, -1>{});
   else if (a.mode == EHGR_ROW_PLAIN) go(std::integral_constant<int, EHGR_ROW_PLAIN>{});
   else if (a.mode == EHGR_ROW_AFFINE) go(std::integral_constant<int, EHGR_ROW_AFFINE>{});
+  else if (a.mode == EHGR_ROW_CONV3) go(std::integral_constant<int, EHGR_ROW_CONV3>{});
   else go(std::integral_constant<int, EHGR_ROW_SHIFT>{});
   return launch_status();
 }

@@ -13,6 +13,9 @@
 //            in1 = gradient w.r.t. the post-activation, in2 = raw forward output of that layer:
 //            this is d(loss)/d(raw) of conv->BN(->ReLU6) with batch statistics (cb, cc != 0) or frozen
 //            statistics (cb = cc = 0).
+//   CONV3  : the im2col row of a dense 3x3 convolution (pad 1, stride 1; optionally over the nearest-x2 upsampled
+//            tensor) with the producer's lazy BatchNorm+ReLU applied to the gathered pixels — GEMM family only
+//            (include/ehgr_b200.h; models/models_MTMM.py:129-155).
 #pragma once
 #include "common.cuh"
 
@@ -117,6 +120,20 @@ __device__ __forceinline__ float round_to<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float round_to<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+// ---- CONV3 geometry ---------------------------------------------------------------------------------
+struct Conv3Tap { int dy, dx, c; };
+// column k of the implicit GEMM -> (dy, dx) in {-1,0,1}^2 and the channel offset inside the pixel
+__device__ __forceinline__ Conv3Tap conv3_tap(const RowOp& op, int k) {
+  const int tap = k / op.cv_cin;
+  const int ty = tap / 3;
+  return Conv3Tap{ty - 1, tap - ty * 3 - 1, k - tap * op.cv_cin};
+}
+// element offset of pixel (hs, ws) of frame fr — coordinates on the OUTPUT grid — inside the stored tensor
+__device__ __forceinline__ long long conv3_src(const RowOp& op, int fr, int hs, int ws) {
+  const int Hs = op.cv_h >> op.cv_up, Ws = op.cv_w >> op.cv_up;
+  return ((static_cast<long long>(fr) * Hs + (hs >> op.cv_up)) * Ws + (ws >> op.cv_up)) * op.cv_cin;
+}
+
 // ---- the row operand ------------------------------------------------------------------------------
 // Loads NV consecutive channels [c0, c0+NV) of row m (C channels per row) as fp32 with the operand's
 // transformation applied.  The caller guarantees c0 % NV == 0, C % NV == 0 and 0 <= m < M.
@@ -169,6 +186,29 @@ __device__ __forceinline__ void load_row(const RowOp& op, long long m, int c0, i
       for (int i = 0; i < NV; ++i) {
         const int k = cls_of(c0 + i);
         v[i] = k == 0 ? a[i] : (k == 1 ? b[i] : c[i]);
+      }
+    }
+  } else if (kGate && op.mode == EHGR_ROW_CONV3) {
+    // column c0 of the implicit GEMM = (tap, channel); row m = (frame, ho, wo) of the output grid
+    const Conv3Tap tp = conv3_tap(op, c0);
+    const int fr = static_cast<int>(m / op.hw);
+    const int rem = static_cast<int>(m - static_cast<long long>(fr) * op.hw);
+    const int ho = rem / op.cv_w, wo = rem - ho * op.cv_w;
+    const int hs = ho + tp.dy, ws = wo + tp.dx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.f;
+    if (static_cast<unsigned>(hs) < static_cast<unsigned>(op.cv_h) && static_cast<unsigned>(ws) < static_cast<unsigned>(op.cv_w)) {
+      load_vec<T, NV>(in1 + conv3_src(op, fr, hs, ws) + tp.c, v);
+      if (op.scale) {
+        float s[NV], b[NV];
+        load_vec<float, NV>(op.scale + tp.c, s);
+        load_vec<float, NV>(op.shift + tp.c, b);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float z = fmaf(v[i], s[i], b[i]);
+          if (op.relu6) z = fminf(fmaxf(z, 0.f), relu_hi(op.relu6));
+          v[i] = z;
+        }
       }
     }
   } else if (kGate && op.mode == EHGR_ROW_GATE) {
@@ -393,10 +433,16 @@ struct RowLoader {
   }
 };
 
-inline int validate_rowop(const RowOp* op, int es) {
+inline int validate_rowop(const RowOp* op, int es, bool allow_conv3 = false) {
   if (!op || !op->in1) return EHGR_E_NULL;
   if (!aligned_to(op->in1, 16)) return EHGR_E_ALIGN;
   switch (op->mode) {
+    case EHGR_ROW_CONV3:
+      if (!allow_conv3) return EHGR_E_UNSUPPORTED;            // GEMM family only
+      if (op->cv_h <= 0 || op->cv_w <= 0 || op->cv_cin <= 0 || (op->cv_cin % 8) || op->hw != op->cv_h * op->cv_w) return EHGR_E_SHAPE;
+      if (op->cv_up != 0 && (op->cv_up != 1 || (op->cv_h & 1) || (op->cv_w & 1))) return EHGR_E_SHAPE;
+      if (op->scale && !op->shift) return EHGR_E_NULL;
+      return EHGR_OK;
     case EHGR_ROW_PLAIN: return EHGR_OK;
     case EHGR_ROW_AFFINE: return (op->scale && op->shift) ? EHGR_OK : EHGR_E_NULL;
     case EHGR_ROW_SHIFT:

@@ -136,6 +136,13 @@ def op_bnbwd(g, raw, ca, cb, cc, scale, shift, relu6):
                  shift=shift.data_ptr(), ca=ca.data_ptr(), cb=cb.data_ptr(), cc=cc.data_ptr())
 
 
+def op_conv3(src, scale, shift, act, ho, wo, cin, up):
+    """im2col row of a dense 3x3 convolution over `src` ([frames, ho >> up, wo >> up, cin], NHWC) with the producer's
+    BatchNorm+activation (scale/shift/act; scale None = plain tensor) and a nearest x2 upsample (up) applied on load."""
+    return RowOp(mode=5, relu6=int(act) if scale is not None else 0, in1=src.data_ptr(), scale=_lib.ptr(scale),
+                 shift=_lib.ptr(shift), hw=ho * wo, cv_h=ho, cv_w=wo, cv_cin=cin, cv_up=int(up))
+
+
 def _nhwc_empty(nt, h, w, c, dtype, device):
     """logical [NT,C,H,W] tensor with channels-last strides."""
     return torch.empty((nt, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
@@ -160,13 +167,14 @@ def _as_nhwc(x, dtype):
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class Stage:
-    kind: str                      # 'stem' | 'pw' | 'dw'
+    kind: str                      # 'stem' | 'pw' | 'dw' | 'conv3' (dense 3x3, pad 1, stride 1: the depth decoder)
     conv: nn.Conv2d
     bn: Optional[nn.BatchNorm2d]   # None: a bare convolution (the depthwise halves of SepConv, models/models_SD.py:81-101)
     relu6: int                     # activation code after the BatchNorm: 0 none, 1 ReLU6, 2 ReLU
     stride: int = 1
     shift: Optional[Tuple[int, int]] = None   # (n_segment, fold) — TemporalShift on the input (pw only)
     action: Optional[nn.Module] = None        # Action module wrapping this conv (pw only, first stage of a unit)
+    up: bool = False                          # conv3 only: the input is read through a nearest x2 upsample
 
     def n_params(self) -> int:
         return (3 if self.bn is not None else 1) + (10 if self.action is not None else 0)
@@ -274,10 +282,31 @@ def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None, m
         _lib.call("ehgr_pw_gemm_bn", ctypes.byref(a_op), w.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
                   cin, cout, code, _STATE["engine"], fin_p, sp, algo_bytes=m * (cin + cout) * es + cin * cout * 4,
                   algo_flops=2 * m * cin * cout)
+    elif st.kind == 'conv3':
+        # implicit GEMM over the im2col operand: M = output pixels, K = 9*cin; w = (fp32 packed or the raw weight as a
+        # placeholder, bf16 packed) from _pack_conv3
+        m = out.shape[0] * out.shape[2] * out.shape[3]
+        w32, w16 = w
+        _lib.call("ehgr_pw_gemm_bn", ctypes.byref(a_op), w32.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
+                  9 * cin, cout, code, _STATE["engine"], fin_p, sp,
+                  algo_bytes=(nt * h * wd * cin + m * cout) * es + 9 * cin * cout * es, algo_flops=2 * m * 9 * cin * cout)
     else:
         _lib.call("ehgr_dw_fwd_bn", ctypes.byref(a_op), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cin,
                   st.stride, code, fin_p, sp, algo_bytes=(nt * h * wd * cin + out.numel()) * es + 36 * cin,
                   algo_flops=18 * out.numel())
+
+
+def _pack_conv3(w, dt, dev):
+    """The two GEMM layouts of a dense 3x3 filter (csrc/conv3.cu): forward [cout, 9*cin] and dgrad [cin, 9*cout] (flipped,
+    transposed), in the storage dtype the engine reads — bf16 for the tensor-core engine, fp32 for the SIMT engine.
+    Returns ((w32, w16) forward, (w32, w16) dgrad); the unused member of a pair is the raw weight (placeholder) / None."""
+    cout, cin = w.shape[0], w.shape[1]
+    simt = dt == torch.float32 or _STATE["engine"] == 1
+    pdt = torch.float32 if simt else torch.bfloat16
+    wf = torch.empty(cout * 9 * cin, dtype=pdt, device=dev)
+    wd = torch.empty(cout * 9 * cin, dtype=pdt, device=dev)
+    _lib.call("ehgr_conv3_pack", w.data_ptr(), wf.data_ptr(), wd.data_ptr(), cout, cin, _lib.dtype_code(wf), _lib.stream_ptr(dev))
+    return ((wf, None), (wd, None)) if simt else ((w, wf), (w, wd))
 
 
 class _ChainFunction(torch.autograd.Function):
@@ -324,8 +353,14 @@ class _ChainFunction(torch.autograd.Function):
                 nt, h, wd, cin = geom
                 cout = st.conv.out_channels
                 act_state = None
+                aux = None
                 if st.kind == 'stem':
                     a_op = None
+                elif st.kind == 'conv3':
+                    ho, wo = (h << 1, wd << 1) if st.up else (h, wd)
+                    a_op = (op_conv3(cur_final, None, None, 0, ho, wo, cin, st.up) if lazy is None
+                            else op_conv3(lazy[0], lazy[1], lazy[2], lazy[3], ho, wo, cin, st.up))
+                    aux = _pack_conv3(w, dt, dev)
                 elif st.action is not None:
                     if lazy is not None:
                         raise NotImplementedError("Action is defined on a block input")
@@ -337,12 +372,14 @@ class _ChainFunction(torch.autograd.Function):
                     if st.shift is not None:
                         raise NotImplementedError("temporal shift is defined on a block input")
                     a_op = op_affine(*lazy) if lazy[1] is not None else op_plain(lazy[0])
-                ho, wo = ((h - 1) // st.stride + 1, (wd - 1) // st.stride + 1) if st.kind != 'pw' else (h, wd)
+                if st.kind != 'conv3':
+                    ho, wo = ((h - 1) // st.stride + 1, (wd - 1) // st.stride + 1) if st.kind != 'pw' else (h, wd)
                 raw = _nhwc_empty(nt, ho, wo, cout, dt, dev)
+                w_arg = aux[0] if st.kind == 'conv3' else w
                 if st.bn is None:                        # bare convolution: no statistics, no finalisation
-                    _launch_conv_fwd(st, a_op, geom, w, raw, None, dev, mirrors=mirrors)
+                    _launch_conv_fwd(st, a_op, geom, w_arg, raw, None, dev, mirrors=mirrors)
                     k_i += 1
-                    recs.append((raw, None, geom, False, None))
+                    recs.append((raw, None, geom, False, None, aux))
                     lazy = (raw, None, None, 0)
                     geom = (nt, ho, wo, cout)
                     continue
@@ -358,7 +395,7 @@ class _ChainFunction(torch.autograd.Function):
                             mean=vec[2].data_ptr(), invstd=vec[3].data_ptr(), counter=tickets[k_i:].data_ptr(),
                             count=nt * ho * wo, momentum=float(st.bn.momentum), eps=float(st.bn.eps), training=int(tr))
                 k_i += 1
-                _launch_conv_fwd(st, a_op, geom, w, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None,
+                _launch_conv_fwd(st, a_op, geom, w_arg, raw, stats, dev, x_nchw=x_in if st.kind == 'stem' else None,
                                  mirrors=mirrors, fin=fin if FUSED_FINALIZE & 1 else None)
                 if not FUSED_FINALIZE & 1:
                     _lib.call("ehgr_bn_finalize", 0 if stats is None else stats.data_ptr(), nt * ho * wo, gamma.data_ptr(),
@@ -367,7 +404,7 @@ class _ChainFunction(torch.autograd.Function):
                               vec[2].data_ptr(), vec[3].data_ptr(), cout, sp)
                 if tr and st.bn.num_batches_tracked is not None:
                     nbt.append(st.bn.num_batches_tracked)
-                recs.append((raw, vec, geom, tr, act_state))
+                recs.append((raw, vec, geom, tr, act_state, aux))
                 lazy = (raw, vec[0], vec[1], st.relu6)
                 geom = (nt, ho, wo, cout)
             # materialise the unit output: BN(+activation) (+ residual)
@@ -445,7 +482,7 @@ class _ChainFunction(torch.autograd.Function):
             unit_grad_done = False
             for si in range(len(u.stages) - 1, -1, -1):
                 st = u.stages[si]
-                raw, vec, geom, tr, act_state = recs[si]
+                raw, vec, geom, tr, act_state, aux = recs[si]
                 nt, h, wd, cin = geom
                 cout = st.conv.out_channels
                 ho, wo = raw.shape[2], raw.shape[3]
@@ -483,7 +520,11 @@ class _ChainFunction(torch.autograd.Function):
                     g = None
                     continue
                 # forward operand of this stage, re-derived from what was saved
-                if act_state is not None:
+                if st.kind == 'conv3':
+                    a_op = (op_conv3(unit_in, None, None, 0, ho, wo, cin, st.up) if si == 0 else
+                            op_conv3(recs[si - 1][0], *(recs[si - 1][1][:2] if recs[si - 1][1] is not None else (None, None)),
+                                     u.stages[si - 1].relu6, ho, wo, cin, st.up))
+                elif act_state is not None:
                     a_op = action_ops.gate_op(act_state)
                 elif si == 0:
                     a_op = (op_shift(unit_in, st.shift[0], st.shift[1], h * wd, 1) if st.shift is not None
@@ -495,14 +536,37 @@ class _ChainFunction(torch.autograd.Function):
                 m_in = nt * h * wd
                 need_dgrad = not (si == 0 and ui == 0 and not need_x_grad)
                 g_prev = None
-                if st.kind == 'pw' and need_dgrad and dy_op.mode != 0:
+                dy_src = g                               # tensor holding d(raw) once the BN-backward operand is materialised
+                if (st.kind == 'pw' and need_dgrad and dy_op.mode != 0) or (st.kind == 'conv3' and dy_op.mode != 0):
                     # dgrad AND wgrad both consume d(raw): evaluate the BN-backward operand once (one
                     # streaming pass at full occupancy) so the tensor-core producers only copy bf16 rows
                     draw = torch.empty_like(raw)
                     _lib.call("ehgr_row_apply", ctypes.byref(dy_op), 0, draw.data_ptr(), m_out, cout, code, sp,
                               algo_bytes=3 * m_out * cout * es)
                     dy_op = op_plain(draw)
-                if st.kind == 'pw':
+                    dy_src = draw
+                if st.kind == 'conv3':
+                    # wgrad as a [cout, 9*cin] GEMM over the same im2col operand, then back to [cout, cin, 3, 3]
+                    dwp = torch.zeros(cout * 9 * cin, dtype=torch.float32, device=dev)
+                    _lib.call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), dwp.data_ptr(), m_out, 9 * cin, cout,
+                              code, _STATE["engine"], sp, algo_bytes=(m_out * cout + m_in * cin) * es + 36 * cin * cout,
+                              algo_flops=2 * m_out * 9 * cin * cout)
+                    _lib.call("ehgr_conv3_unpack_grad", dwp.data_ptr(), gw.data_ptr(), cout, cin, sp)
+                    if need_dgrad:
+                        # dgrad = the same convolution of d(raw) with the flipped, transposed filter
+                        wd32, wd16 = aux[1]
+                        g_up = _nhwc_empty(nt, ho, wo, cin, dt, dev)
+                        _lib.call("ehgr_pw_gemm_w16", ctypes.byref(op_conv3(dy_src, None, None, 0, ho, wo, cout, False)),
+                                  wd32.data_ptr(), _lib.ptr(wd16), 0, g_up.data_ptr(), 0, 0, m_out, 9 * cout, cin, code,
+                                  _STATE["engine"], sp, algo_bytes=m_out * (cout + cin) * es + 9 * cin * cout * es,
+                                  algo_flops=2 * m_out * 9 * cin * cout)
+                        if st.up:                        # adjoint of the nearest x2 upsample folded into the forward gather
+                            g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
+                            _lib.call("ehgr_upsample2_bwd", g_up.data_ptr(), g_prev.data_ptr(), nt, h, wd, cin, code, sp,
+                                      algo_bytes=5 * g_prev.numel() * es)
+                        else:
+                            g_prev = g_up
+                elif st.kind == 'pw':
                     _lib.call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), gw.data_ptr(), m_in, cin, cout,
                               code, _STATE["engine"], sp,
                               algo_bytes=((1 if dy_op.mode == 0 else 2) * cout + cin) * m_in * es + cin * cout * 4,
@@ -675,6 +739,83 @@ def classifier_head(tsn, fmap):
         z = tsn.softmax(z)
     z = z.view((-1, tsn.num_segments) + z.size()[1:])
     return tsn.consensus(z).squeeze(1)
+
+
+# ------------------------------------------------------------------------------------------------
+# MTMM depth decoder (models/models_MTMM.py:129-155) on the fused chain
+# ------------------------------------------------------------------------------------------------
+def parse_depth_decoder(seq: nn.Sequential):
+    """[Conv3x3, BN, ReLU, (Upsample x2)]* , Conv1x1(bias), Sigmoid  ->  (conv3 stages, head conv) or None when the module
+    does not have that shape (then the caller runs it as the nn.Sequential it is)."""
+    mods = list(seq)
+    stages, i, up = [], 0, False
+    while i + 2 < len(mods):
+        conv, bn, act = mods[i], mods[i + 1], mods[i + 2]
+        if not (isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
+                and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and isinstance(bn, nn.BatchNorm2d)
+                and isinstance(act, nn.ReLU) and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0):
+            break
+        st = _conv_bn_stage('conv3', conv, bn, 2)
+        st.up = up
+        stages.append(st)
+        i += 3
+        up = False
+        if i < len(mods) and isinstance(mods[i], nn.Upsample):
+            if mods[i].mode != 'nearest' or float(mods[i].scale_factor) != 2.0:
+                return None
+            up = True
+            i += 1
+    if up or not stages or len(mods) != i + 2:
+        return None
+    head, sig = mods[i], mods[i + 1]
+    if not (isinstance(head, nn.Conv2d) and head.kernel_size == (1, 1) and head.out_channels == 1 and head.groups == 1
+            and isinstance(sig, nn.Sigmoid) and head.in_channels % 8 == 0 and head.in_channels <= 256):
+        return None
+    return stages, head
+
+
+class _DepthHeadFunction(torch.autograd.Function):
+    """sigmoid(Conv2d(C, 1, 1, bias)(x)) — csrc/conv3.cu depth_head_kernel; x NHWC in the compute dtype, out fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        nt, c, h, w = x.shape
+        out = torch.empty((nt, 1, h, w), dtype=torch.float32, device=x.device)
+        wv = weight.detach().reshape(-1).float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        _lib.call("ehgr_depth_head_fwd", ctypes.byref(op_plain(x)), wv.data_ptr(), _lib.ptr(b), out.data_ptr(), nt * h * w, c,
+                  _lib.dtype_code(x), _lib.stream_ptr(x.device), algo_bytes=x.numel() * x.element_size() + out.numel() * 4)
+        ctx.save_for_backward(x, wv, out)
+        ctx.has_bias, ctx.wshape = bias is not None, weight.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wv, out = ctx.saved_tensors
+        nt, c, h, w = x.shape
+        g = g.contiguous().float()
+        gx = torch.empty_like(x)
+        dw = torch.zeros(c, dtype=torch.float32, device=x.device)
+        db = torch.zeros(1, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        _lib.call("ehgr_depth_head_bwd", ctypes.byref(op_plain(x)), wv.data_ptr(), out.data_ptr(), g.data_ptr(), gx.data_ptr(),
+                  dw.data_ptr(), _lib.ptr(db), nt * h * w, c, _lib.dtype_code(x), _lib.stream_ptr(x.device),
+                  algo_bytes=2 * x.numel() * x.element_size() + 2 * out.numel() * 4)
+        return gx, dw.view(ctx.wshape), db
+
+
+def depth_decoder(seq: nn.Sequential, fmap):
+    """``global_decoder(fmap)`` of models/models_MTMM.py:129-155 -> [NT, 1, 8H, 8W] fp32: the four 3x3 convolutions are ONE
+    fused chain of implicit-GEMM stages (BatchNorm+ReLU and the three nearest x2 upsamples live in the operand loads), the
+    1x1 convolution + sigmoid is one more kernel.  No library convolution / BatchNorm / activation / upsample op."""
+    _lib.require_cuda(fmap)
+    parsed = parse_depth_decoder(seq)
+    if parsed is None:
+        return seq(fmap)                                 # another decoder architecture (e.g. ConvTranspose2d): library modules
+    stages, head = parsed
+    # one unit per convolution: a unit materialises BatchNorm+ReLU once (a few MB), so the nine taps of the next
+    # convolution gather finished activations instead of re-evaluating the affine map nine times per pixel
+    y = run_chain([Unit([st]) for st in stages], fmap)[0]
+    return _DepthHeadFunction.apply(y, head.weight, head.bias)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -68,5 +68,7 @@ class TSN(_BaseTSN):
         if self.modal == 'rgb':
             return output
         if self.modal == 'rgb_depth':
-            return output, self.global_decoder(fmap)
+            if fmap.is_cuda:                                   # four implicit-GEMM conv stages + the depth head (fused.py)
+                return output, fused.depth_decoder(self.global_decoder, fmap)
+            return output, self.global_decoder(fmap)           # CPU: shape / policy tests only
         raise ValueError(self.modal)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define EHGR_ABI_VERSION 1
+#define EHGR_ABI_VERSION 2
 
 enum { EHGR_F32 = 0, EHGR_BF16 = 1 };
 enum { EHGR_NCHW = 0, EHGR_NHWC = 1 };
@@ -77,7 +77,8 @@ int ehgr_temporal_shift_bwd(const void* grad_out, void* grad_in, int n_batch, in
  * and the BatchNorm-backward combination are applied while loading (csrc/rowop.cuh).  HOST struct,
  * copied into the kernel's parameters; all pointers inside are device pointers.
  * ------------------------------------------------------------------------------------------- */
-enum { EHGR_ROW_PLAIN = 0, EHGR_ROW_AFFINE = 1, EHGR_ROW_SHIFT = 2, EHGR_ROW_BNBWD = 3, EHGR_ROW_GATE = 4 };
+enum { EHGR_ROW_PLAIN = 0, EHGR_ROW_AFFINE = 1, EHGR_ROW_SHIFT = 2, EHGR_ROW_BNBWD = 3, EHGR_ROW_GATE = 4,
+       EHGR_ROW_CONV3 = 5 };
 
 typedef struct ehgr_rowop {
   int32_t mode;        /* EHGR_ROW_* */
@@ -96,6 +97,17 @@ typedef struct ehgr_rowop {
   int32_t shift_dir;   /* SHIFT: +1 forward shift, -1 its adjoint */
   /* GATE (ACTION, models/action.py:83,96,113,115): v = in1 * (3 + g1[m] + g2[m/hw, c] + g3[m/hw, c]) with
    * in2 = g1 (fp32 [M]), scale = g2, shift = g3 (fp32 [frames, C]) and hw = rows per frame. */
+  /* CONV3 (pointwise-GEMM family only): the im2col row of a dense 3x3 convolution, pad 1, stride 1 — the operand that
+   * turns ehgr_pw_gemm* / ehgr_pw_wgrad into the implicit GEMM of nn.Conv2d(cin, cout, 3, padding=1)
+   * (models/models_MTMM.py:131-149).  Row m = (frame, ho, wo) of the OUTPUT grid [cv_h, cv_w] (hw = cv_h*cv_w), the
+   * GEMM's K = 9*cv_cin and column k = tap*cv_cin + c with tap = 3*(dy+1) + (dx+1):
+   *     v[m, k] = act(in1[frame, (ho+dy) >> cv_up, (wo+dx) >> cv_up, c] * scale[c] + shift[c]),  0 outside the grid
+   * in1 is the stored NHWC tensor [frames, cv_h >> cv_up, cv_w >> cv_up, cv_cin]; cv_up = 1 folds the nearest-neighbour
+   * nn.Upsample(scale_factor=2) that precedes the convolution into the gather (the upsampled tensor never exists);
+   * scale == NULL: no affine / activation (plain tensor).  `relu6` is the activation code as for AFFINE. */
+  int32_t cv_h, cv_w;  /* CONV3: output grid */
+  int32_t cv_cin;      /* CONV3: channels of in1 (multiple of 8) */
+  int32_t cv_up;       /* CONV3: 0 | 1 */
 } ehgr_rowop;
 
 enum { EHGR_ENGINE_AUTO = 0, EHGR_ENGINE_SIMT = 1, EHGR_ENGINE_TCGEN05 = 2 };
@@ -171,6 +183,32 @@ int ehgr_pw_gemm_bn(const ehgr_rowop* a, const float* w, const void* w16, int w_
  * the caller zeroes dw).  dy is normally a BNBWD operand, a the layer's forward operand. */
 int ehgr_pw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, long long M, int K, int N,
                   int dtype, int engine, ehgr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * N2  dense 3x3 convolution (depth decoder, models/models_MTMM.py:129-155) on the pointwise-GEMM kernels.
+ *   forward : ehgr_pw_gemm_bn(a = CONV3 operand, w = wf, w16 = wf16, w_is_kn = 0, M = frames*H*W, K = 9*cin, N = cout)
+ *   dgrad   : the same call on d(raw) with a CONV3 operand of cout channels and the flipped weights wd
+ *             (K = 9*cout, N = cin); with an upsampled input the result is the gradient w.r.t. the UPSAMPLED tensor and
+ *             ehgr_upsample2_bwd folds it back;
+ *   wgrad   : ehgr_pw_wgrad(dy, a = the forward CONV3 operand, dwp[cout, 9*cin]) then ehgr_conv3_unpack_grad.
+ * ehgr_conv3_pack lays the nn.Conv2d weight w[cout, cin, 3, 3] (fp32) out for those GEMMs, in `dtype`:
+ *   wf[n, tap*cin + c] = w[n, c, tap]            (forward:  B[k][n] = wf[n*K + k])
+ *   wd[c, tap*cout + n] = w[n, c, 8 - tap]       (dgrad: the spatially flipped, transposed filter)
+ * Either output may be NULL.  ehgr_conv3_unpack_grad: dw[n, c, tap] += dwp[n, tap*cin + c].
+ * ehgr_upsample2_bwd: g[f, h, w, c] = sum of the 2x2 block of g_up[f, 2h.., 2w.., c] (adjoint of nearest x2), NHWC.
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_conv3_pack(const float* w, void* wf, void* wd, int cout, int cin, int dtype, ehgr_stream_t stream);
+int ehgr_conv3_unpack_grad(const float* dwp, float* dw, int cout, int cin, ehgr_stream_t stream);
+int ehgr_upsample2_bwd(const void* g_up, void* g, long long frames, int h, int w, int c, int dtype, ehgr_stream_t stream);
+
+/* Depth head: Conv2d(C, 1, 1, bias) + Sigmoid (models/models_MTMM.py:151-154) as one pass over the rows.
+ *   fwd: out[m] = sigmoid(sum_c rowop(a)[m, c] * w[c] + bias[0])                       (out fp32 [M])
+ *   bwd: dz = dout[m] * out[m] * (1 - out[m]);  g_a[m, c] = dz * w[c] (dtype);  dw[c] += sum_m dz * rowop(a)[m, c];
+ *        dbias[0] += sum_m dz.  C % 8 == 0, C <= 256. */
+int ehgr_depth_head_fwd(const ehgr_rowop* a, const float* w, const float* bias, float* out, long long m, int c, int dtype,
+                        ehgr_stream_t stream);
+int ehgr_depth_head_bwd(const ehgr_rowop* a, const float* w, const float* out, const float* dout, void* g_a, float* dw,
+                        float* dbias, long long m, int c, int dtype, ehgr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K7  depthwise 3x3 convolution, pad 1, stride 1|2 (archs/mobilenet_v2.py:40,54), NHWC.

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = ehgr_b200._lib.lib()
     for s in _declared_symbols():
         assert hasattr(lib, s), f"libehgr_b200.so does not export {s}"
-    assert lib.ehgr_abi_version() == 1
+    assert lib.ehgr_abi_version() == ehgr_b200._lib.ABI_VERSION == 2
     assert ehgr_b200._lib.lib().ehgr_status_string(-4).decode().startswith("invalid")
 
 
