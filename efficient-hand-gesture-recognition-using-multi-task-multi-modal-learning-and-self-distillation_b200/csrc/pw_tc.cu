@@ -241,6 +241,8 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
     [[maybe_unused]] const uint32_t conv_tab32 =
         smem_u32(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + static_cast<uint32_t>(kEpiWarps * 32 * p.epi_pitch);
     [[maybe_unused]] int tab_tile = -1;
+    // SHIFT with an odd fold: one scratch word per tile row and producer warp (same place as the CONV3 tables)
+    [[maybe_unused]] const uint32_t shift_scr32 = conv_tab32 + static_cast<uint32_t>(warp) * 512u;
     for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x, m_tile += tile_step) {
       const long long m0 = static_cast<long long>(m_tile) * BM;
       for (int ks = 0; ks < k_stages; ++ks, ++turn, ++s) {
@@ -395,12 +397,30 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
               const uint32_t dst = a_dst32 + rg * a_sbo + k8 * 128 + r * 16;
               const __nv_bfloat16* src = in1 + m * p.K + k;
               if (mode == EHGR_ROW_SHIFT && cls != 2 && live) {
-                if (cls == 3) {
-                  sts128(dst, shift_straddle_raw<__nv_bfloat16, 8>(p.a, m, k, p.K));
-                  continue;
-                }
                 int rem = rem0 + d, t = t0;
                 while (rem >= p.a.hw) { rem -= p.a.hw; t = t + 1 == p.a.n_segment ? 0 : t + 1; }
+                if (cls == 3) {
+                  // The vector straddles a fold boundary: four asynchronous 4-byte copies, one per channel pair, each
+                  // from the frame its class reads (zero fill at the clip ends).  A pair is split only by an ODD fold
+                  // (channels fold-1 | fold): its upper channel travels to a per-warp scratch word and is patched in
+                  // after the wait — no synchronous global load anywhere on this path.
+                  const int fold = p.a.fold;
+                  const bool ok0 = t + dir >= 0 && t + dir < p.a.n_segment, ok1 = t - dir >= 0 && t - dir < p.a.n_segment;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const int c = k + 2 * q;
+                    const int c_lo = c < fold ? 0 : (c < 2 * fold ? 1 : 2), c_hi = c + 1 < fold ? 0 : (c + 1 < 2 * fold ? 1 : 2);
+                    const __nv_bfloat16* sq = src + 2 * q;
+                    const bool lv = c_lo == 2 || (c_lo == 0 ? ok0 : ok1);
+                    cp_async4(dst + 4 * q, lv ? sq + (c_lo == 0 ? step : c_lo == 1 ? -step : 0) : in1, lv ? 4u : 0u);
+                    if (c_hi != c_lo) {
+                      const bool lh = c_hi == 2 || (c_hi == 0 ? ok0 : ok1);
+                      cp_async4(shift_scr32 + static_cast<uint32_t>(d) * 4u, lh ? sq + (c_hi == 0 ? step : c_hi == 1 ? -step : 0) : in1,
+                                lh ? 4u : 0u);
+                    }
+                  }
+                  continue;
+                }
                 const int tt = cls == 0 ? t + dir : t - dir;       // frame the data comes from
                 live = tt >= 0 && tt < p.a.n_segment;
                 src += cls == 0 ? step : -step;
@@ -410,6 +430,24 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
           }
           if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
           cp_async_wait_all();
+          if (mode == EHGR_ROW_SHIFT && (p.a.fold & 1)) {
+            // odd fold: the pair (fold-1, fold) was copied from the frame of its lower channel; patch the upper one
+            const int fold = p.a.fold;
+            const int k8 = (fold - 1 - k_base) >> 3;                   // vector holding channels fold-1 and fold (one pair)
+            if (fold - 1 >= k_base && k8 < kv && (slot % kvp) == (k8 & 3)) {
+              const uint32_t e = static_cast<uint32_t>(fold - (k_base + k8 * 8)) * 2u;   // byte offset of channel `fold`
+#pragma unroll 4
+              for (int j = 0; j * f < 16; ++j) {
+                const int rg = j * f + slot / kvp;
+                const int d = rg * 8 + r;
+                if (rg < 16 && m0 + d < p.M) {
+                  uint16_t v;
+                  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(shift_scr32 + static_cast<uint32_t>(d) * 4u + 2u));
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_dst32 + rg * a_sbo + k8 * 128 + r * 16 + e), "h"(v) : "memory");
+                }
+              }
+            }
+          }
           if (mode == EHGR_ROW_AFFINE) {            // the hot one: constant mode, no GATE code in the loop
             RowOp ac = p.a;
             ac.mode = EHGR_ROW_AFFINE;
@@ -724,7 +762,8 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   const int Np = (N + 15) & ~15;
   const int epi_warps = (K >= N || a.mode == EHGR_ROW_CONV3) ? 8 : 16, parts = epi_warps / 4;
   int best_chunks = 0, best_stages = -1, bar_bytes = 0, b_res = 0;
-  const int conv_tab = a.mode == EHGR_ROW_CONV3 ? tc::kProducerWarps * 1024 : 0;   // per-warp row tables
+  const int conv_tab = a.mode == EHGR_ROW_CONV3 ? tc::kProducerWarps * 1024          // per-warp row tables
+                       : (a.mode == EHGR_ROW_SHIFT && (a.fold & 1)) ? tc::kProducerWarps * 512 : 0;   // odd-fold scratch words
   const int min_chunks = (Np + 255) / 256;
   // (CONV3: K = 9*cin is large and the operand comes out of L2 — a deeper ring is worth narrower tiles)
   const bool extra_chunks = epi_warps != 8 || a.mode == EHGR_ROW_CONV3;

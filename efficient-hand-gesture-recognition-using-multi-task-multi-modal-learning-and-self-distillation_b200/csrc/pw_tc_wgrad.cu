@@ -22,7 +22,8 @@ constexpr int kWgProducers = 7;
 constexpr int kWgMmaWarp = 7;
 constexpr int kWgThreads = 256;
 constexpr int kWgMaxStages = 12;
-constexpr int kWgBarBytes = 256;
+constexpr int kWgBarBytes = 256 + 7 * 128;        // mbarriers + TMEM slot, then one scratch word per stage row and producer warp
+                                                  // (SHIFT operand with an odd fold, see wg_copy)
 constexpr int kWgGroupStride = kMS * 16 + 16;   // bytes between 8-channel groups of a stage: padded by one 16-byte slot so
                                                 // that lanes walking along the groups hit different banks (the
                                                 // unpadded 512-byte stride made every 16-byte access an 8-way conflict)
@@ -73,7 +74,7 @@ __device__ __forceinline__ WgLane wg_lane(const RowOp& op, int c_base, int group
 
 template <int kMode>
 __device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_base, int C, uint32_t dst_base, int gs,
-                                        long long m_base, long long M) {
+                                        long long m_base, long long M, uint32_t scr32 = 0) {
   if (!w.on) return;
   const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(op.in1);
   const int c = c_base + w.g * 8;
@@ -115,17 +116,51 @@ __device__ __forceinline__ void wg_copy(const RowOp& op, const WgLane& w, int c_
     const uint32_t dst = dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16;
     const __nv_bfloat16* src = in1 + m * C + c;
     if (kMode == EHGR_ROW_SHIFT && w.cls != 2 && live) {
-      if (w.cls == 3) {
-        sts128(dst, shift_straddle_raw<__nv_bfloat16, 8>(op, m, c, C));
-        continue;
-      }
       int rem = rem0 + row, t = t0;
       while (rem >= op.hw) { rem -= op.hw; t = t + 1 == op.n_segment ? 0 : t + 1; }
+      if (w.cls == 3) {
+        // straddles a fold boundary: one asynchronous 4-byte copy per channel pair from the frame its class reads; a
+        // pair split by an odd fold sends its upper channel to the scratch word (patched in by wg_shift_patch)
+        const int fold = op.fold;
+        const bool ok0 = t + dir >= 0 && t + dir < op.n_segment, ok1 = t - dir >= 0 && t - dir < op.n_segment;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cq = c + 2 * q;
+          const int c_lo = cq < fold ? 0 : (cq < 2 * fold ? 1 : 2), c_hi = cq + 1 < fold ? 0 : (cq + 1 < 2 * fold ? 1 : 2);
+          const __nv_bfloat16* sq = src + 2 * q;
+          const bool lv = c_lo == 2 || (c_lo == 0 ? ok0 : ok1);
+          cp_async4(dst + 4 * q, lv ? sq + (c_lo == 0 ? step : c_lo == 1 ? -step : 0) : in1, lv ? 4u : 0u);
+          if (c_hi != c_lo) {
+            const bool lh = c_hi == 2 || (c_hi == 0 ? ok0 : ok1);
+            cp_async4(scr32 + static_cast<uint32_t>(row) * 4u, lh ? sq + (c_hi == 0 ? step : c_hi == 1 ? -step : 0) : in1,
+                      lh ? 4u : 0u);
+          }
+        }
+        continue;
+      }
       const int tt = w.cls == 0 ? t + dir : t - dir;
       live = tt >= 0 && tt < op.n_segment;
       src += w.cls == 0 ? step : -step;
     }
     cp_async16(dst, live ? src : in1, live ? 16u : 0u);
+  }
+}
+
+// SHIFT, odd fold: channel `fold` of the pair (fold-1, fold) comes from the scratch word of its row
+__device__ __forceinline__ void wg_shift_patch(const RowOp& op, const WgLane& w, int c_base, uint32_t dst_base, int gs,
+                                               long long m_base, long long M, uint32_t scr32) {
+  const int fold = op.fold;
+  if (!w.on || !(fold & 1) || w.cls != 3) return;
+  const int c = c_base + w.g * 8;
+  if (!(c <= fold - 1 && fold < c + 8)) return;           // this lane's vector does not hold the split pair
+  const uint32_t e = static_cast<uint32_t>(fold - c) * 2u;
+#pragma unroll 4
+  for (int row = w.rsub; row < kMS; row += w.rstep) {
+    if (m_base + row < M) {
+      uint16_t v;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(scr32 + static_cast<uint32_t>(row) * 4u + 2u));
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst_base + w.g * gs + (row >> 3) * 128 + (row & 7) * 16 + e), "h"(v) : "memory");
+    }
   }
 }
 
@@ -233,6 +268,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
       }
       int s = 0, turn = 0;
       uint32_t ph = 0;
+      const uint32_t scr32 = smem_u32(reinterpret_cast<uint8_t*>(bars) + 256) + static_cast<uint32_t>(warp) * 128u;
       for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++s, ++turn) {
         if (turn == pw) turn = 0;
         if (s == p.n_stages) { s = 0; ph ^= 1; }
@@ -240,8 +276,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
         const uint32_t dy_dst = smem_base + s * p.stage_bytes, a_dst = dy_dst + dy_bytes;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         wg_copy<EHGR_ROW_PLAIN>(p.dy, wl_dy, n0, p.N, dy_dst, gs, mc * kMS, p.M);
-        wg_copy<kAMode>(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M);
+        wg_copy<kAMode>(p.a, wl_a, k0, p.K, a_dst, gs, mc * kMS, p.M, scr32);
         cp_async_wait_all();
+        if (kAMode == EHGR_ROW_SHIFT) wg_shift_patch(p.a, wl_a, k0, a_dst, gs, mc * kMS, p.M, scr32);
         if (kAMode == EHGR_ROW_AFFINE) wg_affine_inplace(p.a, wl_a, ld_a, a_dst, gs, mc * kMS, p.M);
         if (kAMode == EHGR_ROW_CONV3 && p.a.scale) wg_conv3_affine_inplace(p.a, wl_a, k0, ld_a, a_dst, gs, mc * kMS, p.M);
         fence_proxy_async();

@@ -55,6 +55,10 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// 4-byte variant (cp.async.cg only exists for 16 bytes): a channel pair of a vector that straddles a shift-fold boundary
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
