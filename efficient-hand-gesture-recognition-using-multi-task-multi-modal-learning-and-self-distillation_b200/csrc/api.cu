@@ -70,6 +70,18 @@ int make_map_4d(CUtensorMap* out, int elem_bytes, const void* base, const unsign
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EHGR_OK : EHGR_E_UNSUPPORTED;
 }
+int make_map_2d_sw128(CUtensorMap* out, const void* base, unsigned long long cols, unsigned long long rows, unsigned box_rows) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return EHGR_E_UNSUPPORTED;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? EHGR_OK : EHGR_E_UNSUPPORTED;
+}
 }  // namespace tma
 }  // namespace ehgr
 

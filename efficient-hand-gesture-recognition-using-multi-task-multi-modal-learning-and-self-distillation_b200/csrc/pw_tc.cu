@@ -36,9 +36,10 @@
 // The two TMEM buffers let the epilogue of tile i overlap the loads and MMAs of tile i+1.
 // w_is_kn selects the B operand's major-ness: forward reads the conv weight [N,K] as a K-major B,
 // dgrad reads the same array [K,N] as an MN-major B — no transposed weight copy exists.
+#include <cstring>
 #include <type_traits>
 
-#include "tc_common.cuh"
+#include "tma.cuh"
 #include "bnfin.cuh"
 
 namespace ehgr {
@@ -179,20 +180,30 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
 //                  stage IN PLACE (each lane re-reads exactly the chunks it copied).  SHIFT is a pure gather:
 //                  the copy's source is the neighbouring frame or a zero fill.
 // kAsync = false: register path (batched fetch -> rowop -> store) for the two-tensor BNBWD operand.
-template <int kMode, int kEpiWarps>
-__global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(GemmArgs p) {
+// kTma (operand modes PLAIN / AFFINE / GATE): the A stage — 128 rows x 64 channels, 128-byte rows — arrives as ONE
+//                  cp.async.bulk.tensor box written in the SWIZZLE_128B layout (zero fill past M and past K); AFFINE /
+//                  GATE then transform the 16-byte chunks in place (chunk c of row r sits at r*128 + ((c ^ (r & 7)) << 4)).
+//                  The producers issue one instruction per stage instead of 32 copies per lane, which is what bounded
+//                  the stage rate of the register / cp.async forms (ncu: ~20 dependent instructions per 16-byte copy).
+template <int kMode, int kEpiWarps, bool kTma>
+__global__ void __launch_bounds__(threads_of(kEpiWarps), 1)
+pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CUtensorMap tm_a) {
   constexpr int kThreads = threads_of(kEpiWarps);
   constexpr int kParts = kEpiWarps / 4;           // epilogue warps per TMEM lane quarter
   constexpr bool kAsync = kMode != EHGR_ROW_BNBWD;     // the operand mode is a compile-time constant: one kernel per mode
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // SWIZZLE_128B stages must start on 1024-byte boundaries: the dynamic window follows the static variables, so the
+  // base is rounded up here (the launch asks for 1 KB more) and the resident weights are padded to 1 KB
+  uint8_t* smem = kTma ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
   const int Kp = (p.K + 15) & ~15;
-  const int b_res_bytes = p.b_resident ? p.BN * Kp * 2 : 0;
+  const int b_res_bytes = p.b_resident ? (kTma ? (p.BN * Kp * 2 + 1023) & ~1023 : p.BN * Kp * 2) : 0;
   uint8_t* ring = smem + b_res_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
   // bars: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2]
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
   const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + kMaxBufs);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxBufs);
+  [[maybe_unused]] const uint32_t bar_landed = smem_u32(bars + 2 * kMaxStages + 2 * kMaxBufs + 1);   // kTma: box has landed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % p.n_chunks;
@@ -201,7 +212,9 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);          // one arrival per producer warp (lane 0, after __syncwarp)
       mbar_init(bar_empty + 8 * s, 1);
+      if (kTma) mbar_init(bar_landed + 8 * s, 1);
     }
+    if (kTma) tma::prefetch_map(&tm_a);
     for (int b = 0; b < p.n_bufs; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, kEpiWarps);   // one arrival per epilogue warp
@@ -221,15 +234,17 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
 
   const int total_tiles = p.m_tiles * p.n_chunks;
   const int k_stages = (p.K + BK - 1) / BK;
-  // Streamed weights: every CTA would ask L2 for the SAME 64-wide weight slice at the same moment (hot lines served
-  // one requester at a time).  Each CTA therefore walks the reduction in its own rotation (accumulation order is free),
-  // so that at any instant the CTAs read different slices.
-  const int k_rot = p.b_resident ? 0 : static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(k_stages));
   const int a_sbo = p.a_bytes >> 4;                 // BYTES between 8-row groups of an A stage = min(Kp,64)*16
 
   if (warp < kProducerWarps) {
     // ===================== PRODUCERS (one warp per ring stage) =====================
-    const int r = lane & 7, slot = lane >> 3;
+    // Lane -> (row r of an 8-row group, channel-vector slot).  16-byte accesses are served per QUARTER warp (8 lanes),
+    // and the copies bypass L1: a 32-byte sector is fetched once only if both of its halves are asked for by the same
+    // quarter.  Lane bit 0 therefore selects the half (slot bit 0), bits 1-3 the row and bit 4 the second slot bit: a
+    // quarter reads four whole sectors (4 rows x 32 bytes).  (With r = lane & 7 every sector travelled twice from L2 —
+    // ncu: 29.6 sectors per LDGSTS instead of 16.)  The price is a 2-way bank conflict on the shared-memory side of the
+    // copy (slots k and k+1 are 128 bytes apart).
+    const int r = (lane >> 1) & 7, slot = (lane & 1) | ((lane >> 3) & 2);
     const int pw = p.n_stages < kProducerWarps ? p.n_stages : kProducerWarps;   // active producer warps
     // ring position kept with counters (no integer division in the per-stage path): s = it % n_stages,
     // ph = (it / n_stages) & 1, turn = it % pw
@@ -255,13 +270,62 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
         if (turn != warp) continue;
         const uint32_t parity = ph ^ 1;
         uint8_t* a_dst = ring + s * p.stage_bytes;
-        const int kr = ks + k_rot < k_stages ? ks + k_rot : ks + k_rot - k_stages;
-        const int k_base = kr * BK;
+        const int k_base = ks * BK;
         const int kvalid = min(BK, Kp - k_base);     // multiple of 16
         const int kv = kvalid >> 3;                    // 2, 4, 6 or 8 channel vectors per row
         const int kvp = kv < 4 ? kv : 4;               // channel vectors handled per pass by the 4 lane slots
         const int f = 4 / kvp;                         // spare slots interleave row groups (kv == 2)
-        if constexpr (kAsync) {
+        if constexpr (kTma) {
+          mbar_wait(bar_empty + 8 * s, parity);
+          const uint32_t a_dst32 = smem_u32(a_dst);
+          constexpr uint32_t kBoxBytes = BM * BK * 2;
+          if constexpr (kMode == EHGR_ROW_PLAIN) {
+            // the box completes its bytes on the FULL barrier itself; the warp's arrival follows the weight slice
+            if (lane == 0) {
+              tma::expect_tx_only(bar_full + 8 * s, kBoxBytes);
+              tma::load_2d(a_dst32, &tm_a, bar_full + 8 * s, k_base, static_cast<int>(m0));
+            }
+          } else {
+            if (lane == 0) {
+              tma::expect_tx(bar_landed + 8 * s, kBoxBytes);
+              tma::load_2d(a_dst32, &tm_a, bar_landed + 8 * s, k_base, static_cast<int>(m0));
+            }
+          }
+          if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+          if constexpr (kMode != EHGR_ROW_PLAIN) {
+            mbar_wait(bar_landed + 8 * s, ph);
+            // in-place row operand; lanes of a quarter warp take the 8 rows of a group at one chunk: the XOR swizzle
+            // spreads them over all banks
+            const int tr = lane & 7, ts = lane >> 3;
+            using Ld = RowLoader<__nv_bfloat16, 8, false, kMode == EHGR_ROW_GATE>;
+            RowOp ac = p.a;
+            ac.mode = kMode;
+#pragma unroll 1
+            for (int pass = 0; pass * 4 < kv; ++pass) {
+              const int k8 = pass * 4 + ts;
+              const int k = k_base + k8 * 8;
+              if (!(k8 < kv && k < p.K)) continue;
+              Ld ld;
+              ld.init(ac, k, p.K);
+              const uint32_t base = a_dst32 + tr * 128 + ((k8 ^ tr) << 4);
+#pragma unroll 4
+              for (int rg = 0; rg < 16; ++rg) {
+                const long long m = m0 + rg * 8 + tr;
+                if (m < p.M) {
+                  const uint32_t dst = base + rg * 1024;
+                  typename Ld::Raw raw;
+                  raw.a = lds128(dst);
+                  if (kMode == EHGR_ROW_GATE) {
+                    raw.b[0].x = static_cast<uint32_t>(m & 0xffffffffLL);
+                    raw.b[0].y = static_cast<uint32_t>(m >> 32);
+                  }
+                  sts128(dst, ld.finish_packed(ac, raw));
+                }
+              }
+            }
+          }
+          if (!p.b_resident && p.w16) cp_async_wait_all();
+        } else if constexpr (kAsync) {
           mbar_wait(bar_empty + 8 * s, parity);
           constexpr int mode = kMode;
           const __nv_bfloat16* in1 = static_cast<const __nv_bfloat16*>(p.a.in1);
@@ -551,7 +615,11 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
       // count bounds the stage rate), so everything that does not change is hoisted: descriptor high words,
       // the ring's start-address field per stage (incremental), K-steps of the last stage.
       const uint32_t idesc = make_idesc(BM, p.BN, 0, p.w_is_kn ? 1 : 0);
-      const uint32_t hi_a = ((static_cast<uint32_t>(a_sbo) >> 4) & 0x3FFF) | (1u << 14);      // SBO | version
+      // A: no-swizzle core matrices (SBO = bytes between 8-row groups), or — kTma — SWIZZLE_128B rows (SBO = 1024 bytes,
+      // layout type 2 in descriptor bits 61-63; a K=16 step advances the start address by 32 bytes inside the atom)
+      const uint32_t hi_a = kTma ? (64u | (1u << 14) | (2u << 29))
+                                 : (((static_cast<uint32_t>(a_sbo) >> 4) & 0x3FFF) | (1u << 14));      // SBO | version
+      constexpr uint32_t a_kstep = kTma ? 2u : 16u;
       const uint32_t hi_b = ((p.b_resident ? static_cast<uint32_t>(Kp) : 64u) & 0x3FFF) | (1u << 14);   // SBO = Kp*16 or 1024 bytes
       const uint32_t lbo = (128u >> 4) << 16;
       const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFF) >> 4) | lbo, bres_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | lbo;
@@ -569,14 +637,13 @@ __global__ void __launch_bounds__(threads_of(kEpiWarps), 1) pw_gemm_tc_kernel(Ge
           if (s == p.n_stages) { s = 0; ph ^= 1; a_lo = ring_lo; }
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
-          const int kr = ks + k_rot < k_stages ? ks + k_rot : ks + k_rot - k_stages;
-          const int ksteps = kr == k_stages - 1 ? last_ksteps : BK / 16;
+          const int ksteps = ks == k_stages - 1 ? last_ksteps : BK / 16;
           // one K=16 step = two 8-element core matrices along K = 256 bytes = 16 address units
           const uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(ks) * 64u : a_lo + abytes16;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
             if (kk < ksteps)
-              umma_bf16(d_tmem, desc(a_lo + kk * 16, hi_a), desc(b_lo + kk * 16, hi_b), idesc, (ks | kk) ? 1u : 0u);
+              umma_bf16(d_tmem, desc(a_lo + kk * a_kstep, hi_a), desc(b_lo + kk * 16, hi_b), idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);          // ring slot free once these MMAs have read it
         }
         umma_commit(bar_tfull + 8 * buf);          // accumulator complete
@@ -754,7 +821,10 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
                   // makes the next kernel's CTAs wait for TMEM
   const int Kp = (K + 15) & ~15;
   constexpr int kBudget = 200 * 1024;
-  p.a_bytes = tc::BM * std::min(Kp, tc::BK) * 2;
+  // TMA + SWIZZLE_128B operand path: the modes that read ONE tensor row by row (the in1 rows are the GEMM rows)
+  const bool use_tma = (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_GATE) && M < 0x7fffffffLL;
+  p.a_bytes = use_tma ? tc::BM * tc::BK * 2 : tc::BM * std::min(Kp, tc::BK) * 2;   // a box is always 128 x 128 bytes
+  const int pad = use_tma ? 1023 : 0;               // resident weights padded to the 1 KB stage alignment
   // Output columns per tile: as few column chunks as possible (A is re-read once per chunk), but the epilogue
   // staging (the whole bf16 output tile) and the weights share the 200 KB with the operand ring: take the first
   // chunk count that leaves at least four ring stages, else the one with the deepest ring.  Input-heavy shapes
@@ -773,7 +843,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
     if (bn > 256 || bn < 16) continue;
     const int pitch = ((bn >> 4) + parts - 1) / parts * 32 + 16;
     const int bar = tc::kTailBytes + epi_warps * 32 * pitch + conv_tab;
-    const int bres = bn * Kp * 2;
+    const int bres = (bn * Kp * 2 + pad) & ~pad;
     const bool resident = bres + 6 * p.a_bytes + bar <= kBudget;
     const int stage = p.a_bytes + (resident ? 0 : bn * tc::BK * 2);
     const int stages = std::min(tc::kMaxStages, (kBudget - bar - (resident ? bres : 0)) / stage);
@@ -789,7 +859,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   const int n_cc = p.BN >> 4;
   p.epi_pitch = (n_cc + parts - 1) / parts * 32 + 16;           // odd multiple of 16 bytes: conflict-free row stores
   bar_bytes = tc::kTailBytes + epi_warps * 32 * p.epi_pitch + conv_tab;
-  b_res = p.BN * Kp * 2;
+  b_res = (p.BN * Kp * 2 + pad) & ~pad;
   // weights resident when that still leaves >= 6 A stages (the large-M layers all qualify)
   p.b_resident = (b_res + 6 * p.a_bytes + bar_bytes <= kBudget) ? 1 : 0;
   p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : p.BN * tc::BK * 2);
@@ -799,27 +869,46 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   // persistent grid: a multiple of n_chunks (a CTA keeps one column chunk -> statistics stay in registers)
   long long grid = std::min<long long>(tiles, kNumSMs);
   grid = std::max<long long>(p.n_chunks, grid / p.n_chunks * p.n_chunks);
-  const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes;
-  auto go = [&](auto mode_tag) {
+  const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes +
+                      (use_tma ? 1024 : 0);          // + room to round the base up to 1 KB
+  CUtensorMap tm_a;
+  memset(&tm_a, 0, sizeof(tm_a));
+  if (use_tma)
+    if (int st = tma::make_map_2d_sw128(&tm_a, a.in1, static_cast<unsigned long long>(K), static_cast<unsigned long long>(M), tc::BM))
+      return st;
+  constexpr int kSmemMax = kBudget + 1024;
+  auto go = [&](auto mode_tag, auto tma_tag) {
     constexpr int kMode = decltype(mode_tag)::value;
+    constexpr bool kTma = decltype(tma_tag)::value;
     if (epi_warps == 16) {
-      ensure_smem(tc::pw_gemm_tc_kernel<kMode, 16>, kBudget);
-      tc::pw_gemm_tc_kernel<kMode, 16><<<static_cast<unsigned>(grid), tc::threads_of(16), smem, s>>>(p);
+      ensure_smem(tc::pw_gemm_tc_kernel<kMode, 16, kTma>, kSmemMax);
+      tc::pw_gemm_tc_kernel<kMode, 16, kTma><<<static_cast<unsigned>(grid), tc::threads_of(16), smem, s>>>(p, tm_a);
     } else {
-      ensure_smem(tc::pw_gemm_tc_kernel<kMode, 8>, kBudget);
-      tc::pw_gemm_tc_kernel<kMode, 8><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p);
+      ensure_smem(tc::pw_gemm_tc_kernel<kMode, 8, kTma>, kSmemMax);
+      tc::pw_gemm_tc_kernel<kMode, 8, kTma><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a);
     }
   };
+  using T = std::true_type;
+  using F = std::false_type;
   switch (a.mode) {
-    case EHGR_ROW_PLAIN: go(std::integral_constant<int, EHGR_ROW_PLAIN>{}); break;
-    case EHGR_ROW_AFFINE: go(std::integral_constant<int, EHGR_ROW_AFFINE>{}); break;
-    case EHGR_ROW_SHIFT: go(std::integral_constant<int, EHGR_ROW_SHIFT>{}); break;
-    case EHGR_ROW_GATE: go(std::integral_constant<int, EHGR_ROW_GATE>{}); break;
-    case EHGR_ROW_CONV3:   // K = 9*cin >= N for every decoder layer: the 8-epilogue-warp form only
-      ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8>, kBudget);
-      tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p);
+    case EHGR_ROW_PLAIN:
+      if (use_tma) go(std::integral_constant<int, EHGR_ROW_PLAIN>{}, T{});
+      else go(std::integral_constant<int, EHGR_ROW_PLAIN>{}, F{});
       break;
-    default: go(std::integral_constant<int, EHGR_ROW_BNBWD>{}); break;
+    case EHGR_ROW_AFFINE:
+      if (use_tma) go(std::integral_constant<int, EHGR_ROW_AFFINE>{}, T{});
+      else go(std::integral_constant<int, EHGR_ROW_AFFINE>{}, F{});
+      break;
+    case EHGR_ROW_GATE:
+      if (use_tma) go(std::integral_constant<int, EHGR_ROW_GATE>{}, T{});
+      else go(std::integral_constant<int, EHGR_ROW_GATE>{}, F{});
+      break;
+    case EHGR_ROW_SHIFT: go(std::integral_constant<int, EHGR_ROW_SHIFT>{}, F{}); break;
+    case EHGR_ROW_CONV3:   // K = 9*cin >= N for every decoder layer: the 8-epilogue-warp form only
+      ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false>, kSmemMax);
+      tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a);
+      break;
+    default: go(std::integral_constant<int, EHGR_ROW_BNBWD>{}, F{}); break;
   }
   return launch_status();
 }

@@ -18,6 +18,9 @@ int make_nhwc_bf16_map(CUtensorMap* out, const void* base, int nt, int h, int w,
 int make_map_4d(CUtensorMap* out, int elem_bytes, const void* base, const unsigned long long (&dims)[4],
                 const unsigned long long (&strides_bytes)[3], const unsigned (&box)[4]);
 
+// row-major bf16 matrix [rows, cols] -> boxes of box_rows x 64 columns in the SWIZZLE_128B shared-memory layout
+int make_map_2d_sw128(CUtensorMap* out, const void* base, unsigned long long cols, unsigned long long rows, unsigned box_rows);
+
 __device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -27,6 +30,16 @@ __device__ __forceinline__ void load_4d(uint32_t dst, const CUtensorMap* map, ui
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(x), "r"(y), "r"(n)
       : "memory");
+}
+// transaction bytes only (no arrival): the same thread arrives later, once its other copies are complete
+__device__ __forceinline__ void expect_tx_only(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 2-D box (coordinates innermost first: channel, row)
+__device__ __forceinline__ void load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(row)
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
