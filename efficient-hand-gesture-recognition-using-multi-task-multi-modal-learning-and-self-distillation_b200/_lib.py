@@ -202,8 +202,10 @@ class KernelTimer:
         return out
 
 
-def call(name: str, *args, algo_bytes: int = 0, algo_flops: int = 0) -> None:
-    """Invoke C-ABI entry point `name` (args already raw pointers / ints) and raise on failure."""
+def call(name: str, *args, algo_bytes: int = 0, algo_flops: int = 0, tag: str = "") -> None:
+    """Invoke C-ABI entry point `name` (args already raw pointers / ints) and raise on failure.  `tag` only labels the
+    launch in the per-kernel timing table (e.g. the implicit-GEMM convolutions that share ehgr_pw_gemm_bn with the
+    pointwise layers but are tensor-bound, not HBM-bound)."""
     fn = getattr(_load(), name)
     rec = KernelTimer.active
     if rec is None:
@@ -214,7 +216,7 @@ def call(name: str, *args, algo_bytes: int = 0, algo_flops: int = 0) -> None:
     st = fn(*args)
     e1.record()
     check(st, name)
-    r = rec.setdefault(name, {"events": [], "bytes": 0, "flops": 0})
+    r = rec.setdefault(name + tag, {"events": [], "bytes": 0, "flops": 0})
     r["events"].append((e0, e1))
     r["bytes"] += int(algo_bytes)
     r["flops"] += int(algo_flops)

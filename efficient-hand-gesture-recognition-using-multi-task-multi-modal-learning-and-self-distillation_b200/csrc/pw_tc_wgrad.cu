@@ -12,7 +12,9 @@
 //   0-3 double as the epilogue at the end.
 #include <type_traits>
 
-#include "tc_common.cuh"
+#include <cstring>
+
+#include "tma.cuh"
 
 namespace ehgr {
 namespace tc {
@@ -22,7 +24,8 @@ constexpr int kWgProducers = 7;
 constexpr int kWgMmaWarp = 7;
 constexpr int kWgThreads = 256;
 constexpr int kWgMaxStages = 12;
-constexpr int kWgBarBytes = 256 + 7 * 128;        // mbarriers + TMEM slot, then one scratch word per stage row and producer warp
+constexpr int kWgBarBytes = 256 + 7 * 128 + 128;  // (+ the kTma "box has landed" barriers)
+//constexpr int kWgBarBytesOld = 256 + 7 * 128;        // mbarriers + TMEM slot, then one scratch word per stage row and producer warp
                                                   // (SHIFT operand with an odd fold, see wg_copy)
 constexpr int kWgGroupStride = kMS * 16 + 16;   // bytes between 8-channel groups of a stage: padded by one 16-byte slot so
                                                 // that lanes walking along the groups hit different banks (the
@@ -40,6 +43,7 @@ struct WgradArgs {
   long long m_chunks;   // ceil(M / kMS)
   int tmem_cols;
   int n_stages, stage_bytes;
+  int dy_blocks;  // kTma: 64-channel blocks of the dy part of a stage
 };
 
 // Asynchronous staging of one operand of a ring stage (32 rows x `groups` 8-channel groups): lane owns a
@@ -213,15 +217,24 @@ __device__ __forceinline__ void wg_conv3_affine_inplace(const RowOp& op, const W
 // kAsync: dy is PLAIN and a is PLAIN / AFFINE / SHIFT / CONV3 (what the fused chain issues); otherwise the register path.
 // kAMode: mode of operand a as a compile-time constant (PLAIN / AFFINE / SHIFT: asynchronous path, dy PLAIN);
 // -1: the generic register path.
-template <int kAMode>
-__global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p) {
+// kTma (dy PLAIN, a PLAIN / AFFINE): both operands arrive as TMA boxes of 32 rows x 64 channels in the SWIZZLE_128B
+//       layout — MN-major canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: a 64-channel block is 32 rows x
+//       128 bytes (4 KB, LBO = 4096 to the next block), 8-row groups are 1 KB apart (SBO = 1024), a K=16 step = 2 KB.
+//       One thread issues <= 6 boxes per stage; AFFINE transforms a's chunks in place (lane = one 8-channel column of
+//       the tile for the whole kernel, coefficients in registers).
+template <int kAMode, bool kTma>
+__global__ void __launch_bounds__(kWgThreads, 2)
+pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ CUtensorMap tm_dy,
+                   const __grid_constant__ CUtensorMap tm_a) {
   constexpr bool kAsync = kAMode >= 0;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int gs = kWgGroupStride;                        // bytes between channel groups inside a stage
-  const int dy_bytes = 16 * gs;                         // 128 n = 16 groups
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = kTma ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
+  const int gs = kTma ? 4096 : kWgGroupStride;          // bytes between channel groups (kTma: 64-channel blocks) of a stage
+  const int dy_bytes = kTma ? p.dy_blocks * 4096 : 16 * gs;   // 128 n = 16 groups
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * p.stage_bytes);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWgMaxStages), bar_done = smem_u32(bars + 2 * kWgMaxStages);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
+  [[maybe_unused]] const uint32_t bar_landed = smem_u32(reinterpret_cast<uint8_t*>(bars) + 256 + 7 * 128);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -229,7 +242,9 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);          // one arrival per producer warp (lane 0, after __syncwarp)
       mbar_init(bar_empty + 8 * s, 1);
+      if (kTma) mbar_init(bar_landed + 8 * s, 1);
     }
+    if (kTma) { tma::prefetch_map(&tm_dy); tma::prefetch_map(&tm_a); }
     mbar_init(bar_done, 1);
     fence_mbar_init();
   }
@@ -253,7 +268,56 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
   const int pw = p.n_stages < kWgProducers ? p.n_stages : kWgProducers;   // see pw_tc.cu: parity aliasing
 
   if (warp < pw) {
-    if constexpr (kAsync) {
+    if constexpr (kTma) {
+      const int a_blocks = (k_valid + 63) >> 6, dy_blocks = (n_valid + 63) >> 6;
+      const uint32_t bytes_dy = static_cast<uint32_t>(dy_blocks) * 4096u, bytes_a = static_cast<uint32_t>(a_blocks) * 4096u;
+      // AFFINE: lane = 8-channel column `lane` of the tile (block lane >> 3, chunk lane & 7), all 32 rows of a stage
+      RowLoader<__nv_bfloat16, 8, false, false> ld_a;
+      RowOp ac = p.a;
+      ac.mode = EHGR_ROW_AFFINE;
+      const bool col_on = kAMode == EHGR_ROW_AFFINE && lane * 8 < k_valid;
+      if (col_on) ld_a.init(ac, k0 + lane * 8, p.K);
+      int s = 0, turn = 0;
+      uint32_t ph = 0;
+      for (long long mc = split; mc < p.m_chunks; mc += p.splits, ++s, ++turn) {
+        if (turn == pw) turn = 0;
+        if (s == p.n_stages) { s = 0; ph ^= 1; }
+        if (turn != warp) continue;
+        const uint32_t dy_dst = smem_base + s * p.stage_bytes, a_dst = dy_dst + dy_bytes;
+        const int row0 = static_cast<int>(mc * kMS);
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (lane == 0) {
+          if (kAMode == EHGR_ROW_PLAIN) {
+            tma::expect_tx(bar_full + 8 * s, bytes_dy + bytes_a);      // the one arrival; every box completes its bytes here
+          } else {
+            tma::expect_tx_only(bar_full + 8 * s, bytes_dy);
+            tma::expect_tx(bar_landed + 8 * s, bytes_a);
+          }
+          for (int b = 0; b < dy_blocks; ++b) tma::load_2d(dy_dst + b * 4096, &tm_dy, bar_full + 8 * s, n0 + b * 64, row0);
+          const uint32_t bar_a = kAMode == EHGR_ROW_PLAIN ? bar_full + 8 * s : bar_landed + 8 * s;
+          for (int b = 0; b < a_blocks; ++b) tma::load_2d(a_dst + b * 4096, &tm_a, bar_a, k0 + b * 64, row0);
+        }
+        if (kAMode != EHGR_ROW_PLAIN) {
+          mbar_wait(bar_landed + 8 * s, ph);
+          if (col_on) {
+            const uint32_t base = a_dst + (lane >> 3) * 4096;
+            const int c16 = lane & 7;
+#pragma unroll 4
+            for (int row = 0; row < kMS; ++row) {
+              if (row0 + row < p.M) {
+                const uint32_t dst = base + row * 128 + ((c16 ^ (row & 7)) << 4);
+                RowLoader<__nv_bfloat16, 8, false, false>::Raw raw;
+                raw.a = lds128(dst);
+                sts128(dst, ld_a.finish_packed(ac, raw));
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
+      }
+    } else if constexpr (kAsync) {
       const WgLane wl_dy = wg_lane<EHGR_ROW_PLAIN>(p.dy, n0, ng, lane), wl_a = wg_lane<kAMode>(p.a, k0, kg, lane);
       RowLoader<__nv_bfloat16, 8, false, false> ld_a;
       if (kAMode == EHGR_ROW_AFFINE && wl_a.on) {
@@ -354,8 +418,10 @@ __global__ void __launch_bounds__(kWgThreads, 2) pw_wgrad_tc_kernel(WgradArgs p)
 #pragma unroll
       for (int kk = 0; kk < kMS / 16; ++kk) {
         // 16 rows of m = two 8-row core matrices = 256 bytes; LBO (m groups) = 128, SBO (channel groups) = gs
-        const uint64_t da = make_desc(dy_addr + kk * 256, 128, gs);
-        const uint64_t db = make_desc(a_addr + kk * 256, 128, gs);
+        // no swizzle: 16 rows of m = two 8-row core matrices = 256 bytes, LBO (m groups) = 128, SBO (channel groups) = gs;
+        // kTma: SWIZZLE_128B, a K=16 step = two 1 KB row groups, LBO = 4096 (64-channel blocks), SBO = 1024
+        const uint64_t da = kTma ? (make_desc(dy_addr + kk * 2048, 4096, 1024) | (2ull << 61)) : make_desc(dy_addr + kk * 256, 128, gs);
+        const uint64_t db = kTma ? (make_desc(a_addr + kk * 2048, 4096, 1024) | (2ull << 61)) : make_desc(a_addr + kk * 256, 128, gs);
         umma_bf16(tmem_base, da, db, idesc, (it | kk) ? 1u : 0u);
       }
       umma_commit(bar_empty + 8 * s);
@@ -421,21 +487,34 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   while (cols < p.BKc) cols <<= 1;
   p.tmem_cols = cols;
   constexpr int kBudget = tc::kWgBudget;
-  p.stage_bytes = (16 + p.BKc / 8) * tc::kWgGroupStride;
-  p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes) / p.stage_bytes));
-  const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes;
+  // TMA + SWIZZLE_128B operand path: both operands read one tensor row by row
+  const bool use_tma = dy.mode == EHGR_ROW_PLAIN && (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE) && M < 0x7fffffffLL;
+  p.dy_blocks = (p.n_tile + 63) / 64;
+  p.stage_bytes = use_tma ? (p.dy_blocks + (p.BKc + 63) / 64) * 4096 : (16 + p.BKc / 8) * tc::kWgGroupStride;
+  p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes - (use_tma ? 1024 : 0)) / p.stage_bytes));
+  const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes + (use_tma ? 1024 : 0);
+  CUtensorMap tm_dy, tm_a;
+  memset(&tm_dy, 0, sizeof(tm_dy));
+  memset(&tm_a, 0, sizeof(tm_a));
+  if (use_tma) {
+    if (int st = tma::make_map_2d_sw128(&tm_dy, dy.in1, static_cast<unsigned long long>(N), static_cast<unsigned long long>(M), tc::kMS)) return st;
+    if (int st = tma::make_map_2d_sw128(&tm_a, a.in1, static_cast<unsigned long long>(K), static_cast<unsigned long long>(M), tc::kMS)) return st;
+  }
   const bool async = dy.mode == EHGR_ROW_PLAIN && (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE ||
                                                    a.mode == EHGR_ROW_SHIFT || a.mode == EHGR_ROW_CONV3);
-  auto go = [&](auto mode_tag) {
+  auto go = [&](auto mode_tag, auto tma_tag) {
     constexpr int kAMode = decltype(mode_tag)::value;
-    ensure_smem(tc::pw_wgrad_tc_kernel<kAMode>, kBudget);
-    tc::pw_wgrad_tc_kernel<kAMode><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p);
+    constexpr bool kTma = decltype(tma_tag)::value;
+    ensure_smem(tc::pw_wgrad_tc_kernel<kAMode, kTma>, kBudget);
+    tc::pw_wgrad_tc_kernel<kAMode, kTma><<<static_cast<unsigned>(tiles * p.splits), tc::kWgThreads, smem, s>>>(p, tm_dy, tm_a);
   };
-  if (!async) go(std::integral_constant<int, -1>{});
-  else if (a.mode == EHGR_ROW_PLAIN) go(std::integral_constant<int, EHGR_ROW_PLAIN>{});
-  else if (a.mode == EHGR_ROW_AFFINE) go(std::integral_constant<int, EHGR_ROW_AFFINE>{});
-  else if (a.mode == EHGR_ROW_CONV3) go(std::integral_constant<int, EHGR_ROW_CONV3>{});
-  else go(std::integral_constant<int, EHGR_ROW_SHIFT>{});
+  using T = std::true_type;
+  using F = std::false_type;
+  if (!async) go(std::integral_constant<int, -1>{}, F{});
+  else if (a.mode == EHGR_ROW_PLAIN) { if (use_tma) go(std::integral_constant<int, EHGR_ROW_PLAIN>{}, T{}); else go(std::integral_constant<int, EHGR_ROW_PLAIN>{}, F{}); }
+  else if (a.mode == EHGR_ROW_AFFINE) { if (use_tma) go(std::integral_constant<int, EHGR_ROW_AFFINE>{}, T{}); else go(std::integral_constant<int, EHGR_ROW_AFFINE>{}, F{}); }
+  else if (a.mode == EHGR_ROW_CONV3) go(std::integral_constant<int, EHGR_ROW_CONV3>{}, F{});
+  else go(std::integral_constant<int, EHGR_ROW_SHIFT>{}, F{});
   return launch_status();
 }
 

@@ -288,7 +288,7 @@ def _launch_conv_fwd(st: Stage, a_op, a_geom, w, out, stats, dev, x_nchw=None, m
         m = out.shape[0] * out.shape[2] * out.shape[3]
         w32, w16 = w
         _lib.call("ehgr_pw_gemm_bn", ctypes.byref(a_op), w32.data_ptr(), _lib.ptr(w16), 0, out.data_ptr(), 0, stats_p, m,
-                  9 * cin, cout, code, _STATE["engine"], fin_p, sp,
+                  9 * cin, cout, code, _STATE["engine"], fin_p, sp, tag="[conv3x3]",
                   algo_bytes=(nt * h * wd * cin + m * cout) * es + 9 * cin * cout * es, algo_flops=2 * m * 9 * cin * cout)
     else:
         _lib.call("ehgr_dw_fwd_bn", ctypes.byref(a_op), w.data_ptr(), out.data_ptr(), stats_p, nt, h, wd, cin,
@@ -549,8 +549,8 @@ class _ChainFunction(torch.autograd.Function):
                     # wgrad as a [cout, 9*cin] GEMM over the same im2col operand, then back to [cout, cin, 3, 3]
                     dwp = torch.zeros(cout * 9 * cin, dtype=torch.float32, device=dev)
                     _lib.call("ehgr_pw_wgrad", ctypes.byref(dy_op), ctypes.byref(a_op), dwp.data_ptr(), m_out, 9 * cin, cout,
-                              code, _STATE["engine"], sp, algo_bytes=(m_out * cout + m_in * cin) * es + 36 * cin * cout,
-                              algo_flops=2 * m_out * 9 * cin * cout)
+                              code, _STATE["engine"], sp, tag="[conv3x3]",
+                              algo_bytes=(m_out * cout + m_in * cin) * es + 36 * cin * cout, algo_flops=2 * m_out * 9 * cin * cout)
                     _lib.call("ehgr_conv3_unpack_grad", dwp.data_ptr(), gw.data_ptr(), cout, cin, sp)
                     if need_dgrad:
                         # dgrad = the same convolution of d(raw) with the flipped, transposed filter
@@ -558,8 +558,8 @@ class _ChainFunction(torch.autograd.Function):
                         g_up = _nhwc_empty(nt, ho, wo, cin, dt, dev)
                         _lib.call("ehgr_pw_gemm_w16", ctypes.byref(op_conv3(dy_src, None, None, 0, ho, wo, cout, False)),
                                   wd32.data_ptr(), _lib.ptr(wd16), 0, g_up.data_ptr(), 0, 0, m_out, 9 * cout, cin, code,
-                                  _STATE["engine"], sp, algo_bytes=m_out * (cout + cin) * es + 9 * cin * cout * es,
-                                  algo_flops=2 * m_out * 9 * cin * cout)
+                                  _STATE["engine"], sp, tag="[conv3x3]",
+                                  algo_bytes=m_out * (cout + cin) * es + 9 * cin * cout * es, algo_flops=2 * m_out * 9 * cin * cout)
                         if st.up:                        # adjoint of the nearest x2 upsample folded into the forward gather
                             g_prev = _nhwc_empty(nt, h, wd, cin, dt, dev)
                             _lib.call("ehgr_upsample2_bwd", g_up.data_ptr(), g_prev.data_ptr(), nt, h, wd, cin, code, sp,
