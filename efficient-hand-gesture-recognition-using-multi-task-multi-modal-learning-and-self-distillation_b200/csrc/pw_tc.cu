@@ -76,6 +76,8 @@ struct GemmArgs {
   int tmem_cols;   // power of two >= n_bufs*BN
   int n_bufs;      // accumulator buffers in TMEM: the tile hand-shake latency is spread over n_bufs tiles
   int b_resident;  // 1: whole [BN x Kp] B staged once; 0: a [BN x 64] slice per stage
+  int b_tma;       // streamed slice arrives as TMA box(es) in the SWIZZLE_128B layout (else 16-byte cp.async, no swizzle)
+  int b_bytes;     // bytes of the B part of a stage
   int n_stages;    // ring depth
   int a_bytes;     // bytes of the A part of a stage = 128 * min(Kp,64) * 2
   int stage_bytes; // a_bytes (+ BN*128 when B is streamed)
@@ -187,14 +189,15 @@ __device__ __forceinline__ void stage_b(const GemmArgs& p, uint8_t* dst, int gs,
 //                  the stage rate of the register / cp.async forms (ncu: ~20 dependent instructions per 16-byte copy).
 template <int kMode, int kEpiWarps, bool kTma>
 __global__ void __launch_bounds__(threads_of(kEpiWarps), 1)
-pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CUtensorMap tm_a) {
+pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CUtensorMap tm_a,
+                  const __grid_constant__ CUtensorMap tm_b) {
   constexpr int kThreads = threads_of(kEpiWarps);
   constexpr int kParts = kEpiWarps / 4;           // epilogue warps per TMEM lane quarter
   constexpr bool kAsync = kMode != EHGR_ROW_BNBWD;     // the operand mode is a compile-time constant: one kernel per mode
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // SWIZZLE_128B stages must start on 1024-byte boundaries: the dynamic window follows the static variables, so the
   // base is rounded up here (the launch asks for 1 KB more) and the resident weights are padded to 1 KB
-  uint8_t* smem = kTma ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int Kp = (p.K + 15) & ~15;
   const int b_res_bytes = p.b_resident ? (kTma ? (p.BN * Kp * 2 + 1023) & ~1023 : p.BN * Kp * 2) : 0;
   uint8_t* ring = smem + b_res_bytes;
@@ -215,6 +218,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
       if (kTma) mbar_init(bar_landed + 8 * s, 1);
     }
     if (kTma) tma::prefetch_map(&tm_a);
+    if (p.b_tma) tma::prefetch_map(&tm_b);
     for (int b = 0; b < p.n_bufs; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, kEpiWarps);   // one arrival per epilogue warp
@@ -256,6 +260,24 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
     [[maybe_unused]] const uint32_t conv_tab32 =
         smem_u32(reinterpret_cast<uint8_t*>(bars) + kBarBytes) + static_cast<uint32_t>(kEpiWarps * 32 * p.epi_pitch);
     [[maybe_unused]] int tab_tile = -1;
+    // Streamed weight slice of a stage.  TMA form: lane 0 adds the slice's bytes to the stage's FULL barrier and issues
+    // one box (K-major: [BN rows x 64 k]) or one box per 64-column block (MN-major: [64 k x 64 n], 8 KB apart); the
+    // warp's arrival on that barrier comes later in program order.  Otherwise 16-byte cp.async copies (stage_b).
+    auto stream_b = [&](uint8_t* b_dst, int s_, int k_base_, int kvalid_) {
+      if (p.b_tma) {
+        if (lane == 0) {
+          const uint32_t bar = bar_full + 8 * s_, d32 = smem_u32(b_dst);
+          tma::expect_tx_only(bar, static_cast<uint32_t>(p.b_bytes));
+          if (!p.w_is_kn) {
+            tma::load_2d(d32, &tm_b, bar, k_base_, n0);
+          } else {
+            for (int b = 0; b * 64 < p.BN; ++b) tma::load_2d(d32 + b * 8192, &tm_b, bar, n0 + b * 64, k_base_);
+          }
+        }
+      } else {
+        stage_b(p, b_dst, 1024, n0, k_base_, kvalid_, lane, 32);
+      }
+    };
     // SHIFT with an odd fold: one scratch word per tile row and producer warp (same place as the CONV3 tables)
     [[maybe_unused]] const uint32_t shift_scr32 = conv_tab32 + static_cast<uint32_t>(warp) * 512u;
     for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x, m_tile += tile_step) {
@@ -291,7 +313,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
               tma::load_2d(a_dst32, &tm_a, bar_landed + 8 * s, k_base, static_cast<int>(m0));
             }
           }
-          if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+          if (!p.b_resident && p.w16) stream_b(a_dst + p.a_bytes, s, k_base, kvalid);
           if constexpr (kMode != EHGR_ROW_PLAIN) {
             mbar_wait(bar_landed + 8 * s, ph);
             // in-place row operand; lanes of a quarter warp take the 8 rows of a group at one chunk: the XOR swizzle
@@ -403,7 +425,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
                 }
               }
               if (round == 0) {
-                if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+                if (!p.b_resident && p.w16) stream_b(a_dst + p.a_bytes, s, k_base, kvalid);
                 cp_async_wait_all();
               }
             }
@@ -492,7 +514,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
               cp_async16(dst, live ? src : in1, live ? 16u : 0u);
             }
           }
-          if (!p.b_resident && p.w16) stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+          if (!p.b_resident && p.w16) stream_b(a_dst + p.a_bytes, s, k_base, kvalid);
           cp_async_wait_all();
           if (mode == EHGR_ROW_SHIFT && (p.a.fold & 1)) {
             // odd fold: the pair (fold-1, fold) was copied from the frame of its lower channel; patch the upper one
@@ -599,8 +621,8 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
           }
         }
         }
-        if (!p.b_resident && !(kAsync && p.w16)) {
-          stage_b(p, a_dst + p.a_bytes, 1024, n0, k_base, kvalid, lane, 32);
+        if (!p.b_resident && !(kAsync && p.w16)) {       // register-path operand (BNBWD) or fp32 weights without a mirror
+          stream_b(a_dst + p.a_bytes, s, k_base, kvalid);
           cp_async_wait_all();
         }
         fence_proxy_async();
@@ -620,8 +642,13 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
       const uint32_t hi_a = kTma ? (64u | (1u << 14) | (2u << 29))
                                  : (((static_cast<uint32_t>(a_sbo) >> 4) & 0x3FFF) | (1u << 14));      // SBO | version
       constexpr uint32_t a_kstep = kTma ? 2u : 16u;
-      const uint32_t hi_b = ((p.b_resident ? static_cast<uint32_t>(Kp) : 64u) & 0x3FFF) | (1u << 14);   // SBO = Kp*16 or 1024 bytes
+      // B: resident / cp.async slices = no-swizzle core matrices (SBO = Kp*16 or 1024 bytes, K step 256 bytes); TMA slices =
+      // SWIZZLE_128B, K-major (SBO 1024, K step 32 bytes) or MN-major (LBO 8192 between 64-column blocks, SBO 1024, K step 2 KB)
+      const uint32_t hi_b = p.b_tma ? (64u | (1u << 14) | (2u << 29))
+                                    : (((p.b_resident ? static_cast<uint32_t>(Kp) : 64u) & 0x3FFF) | (1u << 14));
+      const uint32_t b_kstep = p.b_tma ? (p.w_is_kn ? 128u : 2u) : 16u;
       const uint32_t lbo = (128u >> 4) << 16;
+      const uint32_t lbo_b = (p.b_tma && p.w_is_kn) ? (8192u >> 4) << 16 : lbo;
       const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFF) >> 4) | lbo, bres_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | lbo;
       const uint32_t stage16 = static_cast<uint32_t>(p.stage_bytes) >> 4, abytes16 = static_cast<uint32_t>(p.a_bytes) >> 4;
       const int last_ksteps = (Kp - (k_stages - 1) * BK) >> 4;
@@ -639,11 +666,11 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
           tc_fence_after();
           const int ksteps = ks == k_stages - 1 ? last_ksteps : BK / 16;
           // one K=16 step = two 8-element core matrices along K = 256 bytes = 16 address units
-          const uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(ks) * 64u : a_lo + abytes16;
+          const uint32_t b_lo = p.b_resident ? bres_lo + static_cast<uint32_t>(ks) * 64u : (((a_lo & 0xFFFFu) + abytes16) | lbo_b);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
             if (kk < ksteps)
-              umma_bf16(d_tmem, desc(a_lo + kk * a_kstep, hi_a), desc(b_lo + kk * 16, hi_b), idesc, (ks | kk) ? 1u : 0u);
+              umma_bf16(d_tmem, desc(a_lo + kk * a_kstep, hi_a), desc(b_lo + kk * b_kstep, hi_b), idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);          // ring slot free once these MMAs have read it
         }
         umma_commit(bar_tfull + 8 * buf);          // accumulator complete
@@ -824,7 +851,10 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   // TMA + SWIZZLE_128B operand path: the modes that read ONE tensor row by row (the in1 rows are the GEMM rows)
   const bool use_tma = (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_GATE) && M < 0x7fffffffLL;
   p.a_bytes = use_tma ? tc::BM * tc::BK * 2 : tc::BM * std::min(Kp, tc::BK) * 2;   // a box is always 128 x 128 bytes
-  const int pad = use_tma ? 1023 : 0;               // resident weights padded to the 1 KB stage alignment
+  const int pad = 1023;                             // resident weights padded to the 1 KB stage alignment
+  // streamed weight slices by TMA (needs the bf16 mirror and whole 64-wide K stages on the operand side)
+  const bool b_tma_ok = w16 != nullptr && Kp >= tc::BK;
+  auto slice_bytes = [&](int bn) { return (b_tma_ok && w_is_kn) ? (bn + 63) / 64 * 8192 : bn * tc::BK * 2; };
   // Output columns per tile: as few column chunks as possible (A is re-read once per chunk), but the epilogue
   // staging (the whole bf16 output tile) and the weights share the 200 KB with the operand ring: take the first
   // chunk count that leaves at least four ring stages, else the one with the deepest ring.  Input-heavy shapes
@@ -845,7 +875,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
     const int bar = tc::kTailBytes + epi_warps * 32 * pitch + conv_tab;
     const int bres = (bn * Kp * 2 + pad) & ~pad;
     const bool resident = bres + 6 * p.a_bytes + bar <= kBudget;
-    const int stage = p.a_bytes + (resident ? 0 : bn * tc::BK * 2);
+    const int stage = p.a_bytes + (resident ? 0 : slice_bytes(bn));
     const int stages = std::min(tc::kMaxStages, (kBudget - bar - (resident ? bres : 0)) / stage);
     if (stages > best_stages) { best_stages = stages; best_chunks = chunks; }
     if (stages >= 4) { best_chunks = chunks; break; }
@@ -862,7 +892,9 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   b_res = (p.BN * Kp * 2 + pad) & ~pad;
   // weights resident when that still leaves >= 6 A stages (the large-M layers all qualify)
   p.b_resident = (b_res + 6 * p.a_bytes + bar_bytes <= kBudget) ? 1 : 0;
-  p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : p.BN * tc::BK * 2);
+  p.b_tma = (!p.b_resident && b_tma_ok) ? 1 : 0;
+  p.b_bytes = p.b_resident ? 0 : slice_bytes(p.BN);
+  p.stage_bytes = p.a_bytes + p.b_bytes;
   const int avail = kBudget - bar_bytes - (p.b_resident ? b_res : 0);
   p.n_stages = std::max(2, std::min(tc::kMaxStages, avail / p.stage_bytes));
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_chunks;
@@ -870,22 +902,30 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   long long grid = std::min<long long>(tiles, kNumSMs);
   grid = std::max<long long>(p.n_chunks, grid / p.n_chunks * p.n_chunks);
   const size_t smem = static_cast<size_t>(p.b_resident ? b_res : 0) + static_cast<size_t>(p.n_stages) * p.stage_bytes + bar_bytes +
-                      (use_tma ? 1024 : 0);          // + room to round the base up to 1 KB
+                      1024;                          // + room to round the base up to 1 KB
   CUtensorMap tm_a;
   memset(&tm_a, 0, sizeof(tm_a));
   if (use_tma)
     if (int st = tma::make_map_2d_sw128(&tm_a, a.in1, static_cast<unsigned long long>(K), static_cast<unsigned long long>(M), tc::BM))
       return st;
+  CUtensorMap tm_b;
+  memset(&tm_b, 0, sizeof(tm_b));
+  if (p.b_tma) {
+    const int st = w_is_kn ? tma::make_map_2d_sw128(&tm_b, w16, static_cast<unsigned long long>(N), static_cast<unsigned long long>(K), 64)
+                           : tma::make_map_2d_sw128(&tm_b, w16, static_cast<unsigned long long>(K), static_cast<unsigned long long>(N),
+                                                    static_cast<unsigned>(p.BN));
+    if (st) return st;
+  }
   constexpr int kSmemMax = kBudget + 1024;
   auto go = [&](auto mode_tag, auto tma_tag) {
     constexpr int kMode = decltype(mode_tag)::value;
     constexpr bool kTma = decltype(tma_tag)::value;
     if (epi_warps == 16) {
       ensure_smem(tc::pw_gemm_tc_kernel<kMode, 16, kTma>, kSmemMax);
-      tc::pw_gemm_tc_kernel<kMode, 16, kTma><<<static_cast<unsigned>(grid), tc::threads_of(16), smem, s>>>(p, tm_a);
+      tc::pw_gemm_tc_kernel<kMode, 16, kTma><<<static_cast<unsigned>(grid), tc::threads_of(16), smem, s>>>(p, tm_a, tm_b);
     } else {
       ensure_smem(tc::pw_gemm_tc_kernel<kMode, 8, kTma>, kSmemMax);
-      tc::pw_gemm_tc_kernel<kMode, 8, kTma><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a);
+      tc::pw_gemm_tc_kernel<kMode, 8, kTma><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a, tm_b);
     }
   };
   using T = std::true_type;
@@ -906,7 +946,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
     case EHGR_ROW_SHIFT: go(std::integral_constant<int, EHGR_ROW_SHIFT>{}, F{}); break;
     case EHGR_ROW_CONV3:   // K = 9*cin >= N for every decoder layer: the 8-epilogue-warp form only
       ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false>, kSmemMax);
-      tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a);
+      tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a, tm_b);
       break;
     default: go(std::integral_constant<int, EHGR_ROW_BNBWD>{}, F{}); break;
   }
