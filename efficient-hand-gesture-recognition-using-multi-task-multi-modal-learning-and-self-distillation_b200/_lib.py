@@ -136,6 +136,7 @@ SIGNATURES = {
     "ehgr_conv3_pack": [_P, _P, _P, _I, _I, _I, _P],
     "ehgr_conv3_unpack_grad": [_P, _P, _I, _I, _P],
     "ehgr_upsample2_bwd": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_upsample2_fwd": [_P, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_depth_head_fwd": [_R, _P, _P, _P, _L, _I, _I, _P],
     "ehgr_depth_head_bwd": [_R, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
     "ehgr_dw_fwd": [_R, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

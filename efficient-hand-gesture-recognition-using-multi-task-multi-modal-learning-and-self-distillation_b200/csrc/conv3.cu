@@ -71,6 +71,25 @@ upsample2_bwd_kernel(const T* __restrict__ gu, T* __restrict__ g, long long fram
   }
 }
 
+// out[f, 2h+a, 2w+b, c] = in[f, h, w, c]; thread = one 16-byte channel vector of one OUTPUT pixel (coalesced stores)
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long frames, int h, int w, int c) {
+  constexpr int V = VecOf<T>::N;
+  const int cv = c / V;
+  const long long total = frames * 4 * h * w * cv;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+    const int v = static_cast<int>(i % cv);
+    long long pix = i / cv;
+    const int xo = static_cast<int>(pix % (2 * w));
+    pix /= 2 * w;
+    const int yo = static_cast<int>(pix % (2 * h));
+    const long long f = pix / (2 * h);
+    const uint4 val = *reinterpret_cast<const uint4*>(x + ((f * h + (yo >> 1)) * w + (xo >> 1)) * c + v * V);
+    *reinterpret_cast<uint4*>(y + i * V) = val;
+  }
+}
+
 // Depth head.  A group of C/V lanes owns a row (C = 32, bf16: 4 lanes; fp32: 8 lanes): each lane loads one 16-byte
 // vector through the row operand (the last decoder BatchNorm+ReLU is applied here), partial dot products are
 // combined with shuffles inside the group.
@@ -187,6 +206,25 @@ extern "C" int ehgr_upsample2_bwd(const void* g_up, void* g, long long frames, i
   else
     upsample2_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(g_up),
                                                              static_cast<__nv_bfloat16*>(g), frames, h, w, c);
+  return launch_status();
+}
+
+extern "C" int ehgr_upsample2_fwd(const void* x, void* y, long long frames, int h, int w, int c, int dtype,
+                                  ehgr_stream_t stream) {
+  const int es = esize_of(dtype);
+  if (es == 0) return EHGR_E_DTYPE;
+  if (!x || !y) return EHGR_E_NULL;
+  if (frames < 0 || h <= 0 || w <= 0 || c <= 0 || (c % (16 / es))) return EHGR_E_SHAPE;
+  if (!aligned_to(x, 16) || !aligned_to(y, 16)) return EHGR_E_ALIGN;
+  if (frames == 0) return EHGR_OK;
+  const long long total = frames * 4 * h * w * (c / (16 / es));
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(cdiv(total, 256), 16LL * kNumSMs));
+  cudaStream_t s = as_stream(stream);
+  if (dtype == EHGR_F32)
+    upsample2_fwd_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y), frames, h, w, c);
+  else
+    upsample2_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
+                                                             frames, h, w, c);
   return launch_status();
 }
 

@@ -76,6 +76,8 @@ struct GemmArgs {
   int tmem_cols;   // power of two >= n_bufs*BN
   int n_bufs;      // accumulator buffers in TMEM: the tile hand-shake latency is spread over n_bufs tiles
   int b_resident;  // 1: whole [BN x Kp] B staged once; 0: a [BN x 64] slice per stage
+  int bm_rows;     // rows of a tile that exist (128; CONV3 by TMA: the pixels of one box, 98 or 112) — tile t starts at row t*bm_rows
+  int cv_hbox, cv_nbox, cv_tiles_per_frame;   // CONV3 by TMA: a tile = cv_nbox frames x cv_hbox rows x the full width
   int b_tma;       // streamed slice arrives as TMA box(es) in the SWIZZLE_128B layout (else 16-byte cp.async, no swizzle)
   int b_bytes;     // bytes of the B part of a stage
   int n_stages;    // ring depth
@@ -281,7 +283,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
     // SHIFT with an odd fold: one scratch word per tile row and producer warp (same place as the CONV3 tables)
     [[maybe_unused]] const uint32_t shift_scr32 = conv_tab32 + static_cast<uint32_t>(warp) * 512u;
     for (int tile = blockIdx.x; tile < total_tiles && warp < pw; tile += gridDim.x, m_tile += tile_step) {
-      const long long m0 = static_cast<long long>(m_tile) * BM;
+      const long long m0 = static_cast<long long>(m_tile) * p.bm_rows;
       for (int ks = 0; ks < k_stages; ++ks, ++turn, ++s) {
         if (turn == pw) turn = 0;
         if (s == p.n_stages) { s = 0; ph ^= 1; }
@@ -301,7 +303,20 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
           mbar_wait(bar_empty + 8 * s, parity);
           const uint32_t a_dst32 = smem_u32(a_dst);
           constexpr uint32_t kBoxBytes = BM * BK * 2;
-          if constexpr (kMode == EHGR_ROW_PLAIN) {
+          if constexpr (kMode == EHGR_ROW_CONV3) {
+            // im2col by TMA: the stage's 64 channels of ONE tap for the tile's pixels are a 4-D box of the NHWC tensor
+            // (channels, full width, cv_hbox rows, cv_nbox frames) shifted by the tap; the zero padding of the
+            // convolution is the hardware's out-of-bounds fill.  Box rows land in pixel order = the tile's row order.
+            if (lane == 0) {
+              const int cin = p.a.cv_cin;
+              const int tap = k_base / cin, ty = tap / 3;
+              const int frame_tile = m_tile / p.cv_tiles_per_frame;
+              const int h0 = (m_tile - frame_tile * p.cv_tiles_per_frame) * p.cv_hbox;
+              tma::expect_tx_only(bar_full + 8 * s, static_cast<uint32_t>(p.bm_rows) * 128u);
+              tma::load_4d(a_dst32, &tm_a, bar_full + 8 * s, k_base - tap * cin, tap - ty * 3 - 1, h0 + ty - 1,
+                           frame_tile * p.cv_nbox);
+            }
+          } else if constexpr (kMode == EHGR_ROW_PLAIN) {
             // the box completes its bytes on the FULL barrier itself; the warp's arrival follows the weight slice
             if (lane == 0) {
               tma::expect_tx_only(bar_full + 8 * s, kBoxBytes);
@@ -314,7 +329,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
             }
           }
           if (!p.b_resident && p.w16) stream_b(a_dst + p.a_bytes, s, k_base, kvalid);
-          if constexpr (kMode != EHGR_ROW_PLAIN) {
+          if constexpr (kMode != EHGR_ROW_PLAIN && kMode != EHGR_ROW_CONV3) {
             mbar_wait(bar_landed + 8 * s, ph);
             // in-place row operand; lanes of a quarter warp take the 8 rows of a group at one chunk: the XOR swizzle
             // spreads them over all banks
@@ -706,13 +721,15 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
     int m_tile = blockIdx.x / p.n_chunks;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++buf, m_tile += tile_step) {
       if (buf == static_cast<uint32_t>(p.n_bufs)) { buf = 0; bph ^= 1; }
-      const long long m_base = static_cast<long long>(m_tile) * BM + q * 32;
+      const long long m_base = static_cast<long long>(m_tile) * p.bm_rows + q * 32;
+      // rows this tile owns end at the next tile's first row (bm_rows < 128: a CONV3 box) or at M
+      const long long m_end = min(p.M, static_cast<long long>(m_tile + 1) * p.bm_rows);
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * static_cast<uint32_t>(p.BN);
       __syncwarp();                                  // the previous tile's staging reads are complete
       if (p.addend && pc_on) {                       // coalesced prefetch of the addend rows into the staging rows
         const __nv_bfloat16* src = p.addend + (m_base + rgp) * p.N + n_sub + pc * 8;
         uint32_t dst = stage32 + static_cast<uint32_t>(rgp) * pitch + static_cast<uint32_t>(pc) * 16u;
-        long long left = p.M - m_base - rgp;
+        long long left = m_end - m_base - rgp;
         for (int r = rgp; r < 32; r += rstep) {
           const bool live = left > 0;
           cp_async16(dst, live ? src : p.addend, live ? 16u : 0u);
@@ -768,7 +785,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
       if (pc_on) {
         __nv_bfloat16* dst = p.out + (m_base + rgp) * p.N + n_sub + pc * 8;
         uint32_t src = stage32 + static_cast<uint32_t>(rgp) * pitch + static_cast<uint32_t>(pc) * 16u;
-        long long left = p.M - m_base - rgp;
+        long long left = m_end - m_base - rgp;
         for (int r = rgp; r < 32; r += rstep) {
           if (left > 0) {
             const uint4 w = lds128(src);
@@ -844,13 +861,38 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   p.fin = take_fin();
   p.M = M; p.K = K; p.N = N;
   p.m_tiles = static_cast<int>(cdiv(M, tc::BM));
+  p.bm_rows = tc::BM;
+  p.cv_hbox = p.cv_nbox = p.cv_tiles_per_frame = 1;
+  // CONV3 im2col by TMA: plain operand at the output resolution, whole 64-channel stages, and a tile geometry of whole
+  // image rows (cv_hbox divides the height) or whole frames that fits the 128 rows of a UMMA tile
+  bool conv_tma = false;
+  if (a.mode == EHGR_ROW_CONV3 && !a.scale && !a.cv_up && a.cv_cin % 64 == 0 && a.cv_w <= 128 && w16) {
+    const int hw = a.cv_h * a.cv_w;
+    if (hw <= tc::BM) {
+      p.cv_hbox = a.cv_h;
+      p.cv_nbox = tc::BM / hw;
+      p.cv_tiles_per_frame = 1;
+      conv_tma = true;
+    } else {
+      for (int hb = tc::BM / a.cv_w; hb >= 1; --hb)
+        if (a.cv_h % hb == 0) { p.cv_hbox = hb; break; }
+      p.cv_nbox = 1;
+      p.cv_tiles_per_frame = a.cv_h / p.cv_hbox;
+      conv_tma = p.cv_hbox * a.cv_w >= 64;            // at least half a tile of real rows
+    }
+    if (conv_tma) {
+      p.bm_rows = p.cv_nbox * p.cv_hbox * a.cv_w;
+      const long long frames = M / hw;
+      p.m_tiles = static_cast<int>(cdiv(frames, p.cv_nbox) * p.cv_tiles_per_frame);
+    }
+  }
   p.n_bufs = 2;   // more buffers bought nothing (the hand-shake is not the bound) and a 512-column allocation
                   // makes the next kernel's CTAs wait for TMEM
   const int Kp = (K + 15) & ~15;
   constexpr int kBudget = 200 * 1024;
   // TMA + SWIZZLE_128B operand path: the modes that read ONE tensor row by row (the in1 rows are the GEMM rows)
   const bool use_tma = (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE || a.mode == EHGR_ROW_GATE) && M < 0x7fffffffLL;
-  p.a_bytes = use_tma ? tc::BM * tc::BK * 2 : tc::BM * std::min(Kp, tc::BK) * 2;   // a box is always 128 x 128 bytes
+  p.a_bytes = (use_tma || conv_tma) ? tc::BM * tc::BK * 2 : tc::BM * std::min(Kp, tc::BK) * 2;   // a box is always 128 x 128 bytes
   const int pad = 1023;                             // resident weights padded to the 1 KB stage alignment
   // streamed weight slices by TMA (needs the bf16 mirror and whole 64-wide K stages on the operand side)
   const bool b_tma_ok = w16 != nullptr && Kp >= tc::BK;
@@ -862,7 +904,7 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   const int Np = (N + 15) & ~15;
   const int epi_warps = (K >= N || a.mode == EHGR_ROW_CONV3) ? 8 : 16, parts = epi_warps / 4;
   int best_chunks = 0, best_stages = -1, bar_bytes = 0, b_res = 0;
-  const int conv_tab = a.mode == EHGR_ROW_CONV3 ? tc::kProducerWarps * 1024          // per-warp row tables
+  const int conv_tab = conv_tma ? 0 : a.mode == EHGR_ROW_CONV3 ? tc::kProducerWarps * 1024          // per-warp row tables
                        : (a.mode == EHGR_ROW_SHIFT && (a.fold & 1)) ? tc::kProducerWarps * 512 : 0;   // odd-fold scratch words
   const int min_chunks = (Np + 255) / 256;
   // (CONV3: K = 9*cin is large and the operand comes out of L2 — a deeper ring is worth narrower tiles)
@@ -908,6 +950,13 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   if (use_tma)
     if (int st = tma::make_map_2d_sw128(&tm_a, a.in1, static_cast<unsigned long long>(K), static_cast<unsigned long long>(M), tc::BM))
       return st;
+  if (conv_tma) {
+    const unsigned long long cin = a.cv_cin, wo = a.cv_w, ho = a.cv_h, frames = M / a.hw;
+    const unsigned long long dims[4] = {cin, wo, ho, frames};
+    const unsigned long long strides[3] = {cin * 2, wo * cin * 2, ho * wo * cin * 2};
+    const unsigned box[4] = {64, static_cast<unsigned>(wo), static_cast<unsigned>(p.cv_hbox), static_cast<unsigned>(p.cv_nbox)};
+    if (int st = tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box, /*swizzle128=*/true)) return st;
+  }
   CUtensorMap tm_b;
   memset(&tm_b, 0, sizeof(tm_b));
   if (p.b_tma) {
@@ -945,8 +994,13 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
       break;
     case EHGR_ROW_SHIFT: go(std::integral_constant<int, EHGR_ROW_SHIFT>{}, F{}); break;
     case EHGR_ROW_CONV3:   // K = 9*cin >= N for every decoder layer: the 8-epilogue-warp form only
-      ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false>, kSmemMax);
-      tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a, tm_b);
+      if (conv_tma) {
+        ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, true>, kSmemMax);
+        tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, true><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a, tm_b);
+      } else {
+        ensure_smem(tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false>, kSmemMax);
+        tc::pw_gemm_tc_kernel<EHGR_ROW_CONV3, 8, false><<<static_cast<unsigned>(grid), tc::threads_of(8), smem, s>>>(p, tm_a, tm_b);
+      }
       break;
     default: go(std::integral_constant<int, EHGR_ROW_BNBWD>{}, F{}); break;
   }

@@ -358,9 +358,20 @@ class _ChainFunction(torch.autograd.Function):
                     a_op = None
                 elif st.kind == 'conv3':
                     ho, wo = (h << 1, wd << 1) if st.up else (h, wd)
-                    a_op = (op_conv3(cur_final, None, None, 0, ho, wo, cin, st.up) if lazy is None
-                            else op_conv3(lazy[0], lazy[1], lazy[2], lazy[3], ho, wo, cin, st.up))
-                    aux = _pack_conv3(w, dt, dev)
+                    xu = None
+                    if lazy is None and st.up:
+                        # the nearest x2 upsample of a finished activation is materialised (a few MB): the convolution
+                        # then gathers its operand with TMA boxes, which cannot fold the x2 index map (a lazy
+                        # BatchNorm+ReLU producer keeps the fused gather instead)
+                        xu = _nhwc_empty(nt, ho, wo, cin, dt, dev)
+                        _lib.call("ehgr_upsample2_fwd", cur_final.data_ptr(), xu.data_ptr(), nt, h, wd, cin, _lib.dtype_code(xu), sp,
+                                  algo_bytes=5 * cur_final.numel() * cur_final.element_size())
+                        a_op = op_conv3(xu, None, None, 0, ho, wo, cin, False)
+                    elif lazy is None:
+                        a_op = op_conv3(cur_final, None, None, 0, ho, wo, cin, False)
+                    else:
+                        a_op = op_conv3(lazy[0], lazy[1], lazy[2], lazy[3], ho, wo, cin, st.up)
+                    aux = _pack_conv3(w, dt, dev) + (xu,)
                 elif st.action is not None:
                     if lazy is not None:
                         raise NotImplementedError("Action is defined on a block input")
@@ -520,7 +531,9 @@ class _ChainFunction(torch.autograd.Function):
                     g = None
                     continue
                 # forward operand of this stage, re-derived from what was saved
-                if st.kind == 'conv3':
+                if st.kind == 'conv3' and aux[2] is not None:        # the materialised upsampled input
+                    a_op = op_conv3(aux[2], None, None, 0, ho, wo, cin, False)
+                elif st.kind == 'conv3':
                     a_op = (op_conv3(unit_in, None, None, 0, ho, wo, cin, st.up) if si == 0 else
                             op_conv3(recs[si - 1][0], *(recs[si - 1][1][:2] if recs[si - 1][1] is not None else (None, None)),
                                      u.stages[si - 1].relu6, ho, wo, cin, st.up))

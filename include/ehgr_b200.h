@@ -199,6 +199,9 @@ int ehgr_pw_wgrad(const ehgr_rowop* dy, const ehgr_rowop* a, float* dw, long lon
  * ------------------------------------------------------------------------------------------- */
 int ehgr_conv3_pack(const float* w, void* wf, void* wd, int cout, int cin, int dtype, ehgr_stream_t stream);
 int ehgr_conv3_unpack_grad(const float* dwp, float* dw, int cout, int cin, ehgr_stream_t stream);
+/* y[f, 2h+a, 2w+b, c] = x[f, h, w, c]: nn.Upsample(scale_factor=2, mode='nearest') materialised (NHWC) — used when the
+ * following convolution gathers its operand with TMA boxes, which cannot fold the x2 index map. */
+int ehgr_upsample2_fwd(const void* x, void* y, long long frames, int h, int w, int c, int dtype, ehgr_stream_t stream);
 int ehgr_upsample2_bwd(const void* g_up, void* g, long long frames, int h, int w, int c, int dtype, ehgr_stream_t stream);
 
 /* Depth head: Conv2d(C, 1, 1, bias) + Sigmoid (models/models_MTMM.py:151-154) as one pass over the rows.

@@ -31,7 +31,11 @@ def _nhwc(x, dtype):
 
 CASES = [  # nt, hs, ws (stored grid), cin, cout, up, affine
     (2, 7, 7, 64, 32, 0, False), (3, 3, 5, 32, 16, 1, True), (2, 14, 14, 64, 64, 1, True), (1, 28, 28, 32, 32, 0, True),
-    (2, 7, 7, 256, 40, 0, False), (5, 4, 4, 8, 8, 1, False)]
+    (2, 7, 7, 256, 40, 0, False), (5, 4, 4, 8, 8, 1, False),
+    # plain operands with 64-channel stages: the tcgen05 engine gathers them with TMA boxes (whole frames per tile when the
+    # map is small, else cv_hbox image rows): ragged frame counts, 2 / 7 / 5-row boxes, several column chunks
+    (3, 14, 14, 64, 32, 0, False), (2, 28, 28, 64, 16, 0, False), (5, 5, 3, 64, 16, 0, False), (1, 20, 24, 128, 24, 0, False),
+    (3, 7, 7, 128, 320, 0, False), (2, 56, 56, 64, 8, 0, False)]
 
 
 @pytest.mark.parametrize("nt,hs,ws,cin,cout,up,affine", CASES)
