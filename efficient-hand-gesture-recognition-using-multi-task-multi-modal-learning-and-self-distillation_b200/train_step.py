@@ -61,6 +61,7 @@ class GradBuckets:
         for p in order:
             self._need[self._bucket_of[id(p)]] += 1
         self._left = list(self._need)
+        self._done = set()                   # parameters already counted in this step (a parameter reports once)
         self._works = []
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] \
@@ -70,6 +71,7 @@ class GradBuckets:
     def zero(self):
         self.flat.zero_()
         self._left = list(self._need)
+        self._done = set()
         self._works = []
         # a caller's ``optimizer.zero_grad(set_to_none=True)`` or a replaced ``.grad`` would silently detach a
         # parameter from the flat buffer (the fused optimiser and the all-reduce only see the buffer): re-attach
@@ -95,6 +97,14 @@ class GradBuckets:
             self._works.append(dist.all_reduce(chunk, group=self.group, async_op=True))
 
     def _on_grad(self, p):
+        # A parameter whose gradient the fused chain wrote into the flat buffer reports through mark_done(); autograd
+        # still runs its AccumulateGrad node afterwards (with an undefined gradient) and fires the post-accumulate hook a
+        # second time.  Counting it twice let a bucket that mixes several autograd Functions (the SD exit heads + the
+        # end of the backbone) start its all-reduce before its last gradients were written: replicas diverged
+        # (found by ranks_in_sync() on the 2-GPU SD run of round 2).
+        if id(p) in self._done:
+            return
+        self._done.add(id(p))
         b = self._bucket_of[id(p)]
         self._left[b] -= 1
         if self._left[b] == 0 and self.world > 1:

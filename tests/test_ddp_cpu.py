@@ -124,6 +124,29 @@ def test_bucket_assignment_with_one_dominant_parameter():
                 assert lo <= gb._offset_of[id(p)] and gb._offset_of[id(p)] + p.numel() <= hi
 
 
+def test_a_parameter_reports_done_once_per_step():
+    """A sunk parameter reports through mark_done() AND (autograd runs its AccumulateGrad node afterwards) through the
+    post-accumulate hook: the second report must not count, or a bucket mixing several autograd Functions launches
+    its all-reduce before its last gradients exist (the 2-GPU SD divergence of round 2)."""
+    import ehgr_b200
+    params = [torch.nn.Parameter(torch.zeros(8)) for _ in range(6)]
+    gb = ehgr_b200.train_step.GradBuckets(params, n_buckets=2)
+    gb.world = 2                                   # pretend to be data-parallel; record launches instead of reducing
+    launched = []
+    gb._launch = lambda b: launched.append((b, sorted(id(p) for p in params if id(p) in gb._done)))
+    order = list(reversed(params))                 # backward order
+    b0 = [p for p in order if gb._bucket_of[id(p)] == 0]
+    gb.zero()
+    gb.mark_done(b0[:-1])                          # all but the last parameter of bucket 0
+    for p in b0[:-1]:
+        gb._on_grad(p)                             # ... whose hooks fire afterwards
+    assert launched == []                          # bucket 0 still waits for its last parameter
+    gb.mark_done(b0[-1:])
+    assert [b for b, _ in launched] == [0]
+    gb.zero()
+    assert gb._done == set() and gb._left == gb._need
+
+
 def test_sgd_groups_follow_reference_multipliers():
     import contextlib, io
     import ehgr_b200
