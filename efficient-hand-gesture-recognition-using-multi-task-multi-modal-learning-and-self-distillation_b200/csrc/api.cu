@@ -58,7 +58,7 @@ int make_nhwc_bf16_map(CUtensorMap* out, const void* base, int nt, int h, int w,
   return r == CUDA_SUCCESS ? EHGR_OK : EHGR_E_UNSUPPORTED;
 }
 int make_map_4d(CUtensorMap* out, int elem_bytes, const void* base, const unsigned long long (&dims)[4],
-                const unsigned long long (&strides_bytes)[3], const unsigned (&box)[4], bool swizzle128) {
+                const unsigned long long (&strides_bytes)[3], const unsigned (&box)[4], int swizzle_bytes) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return EHGR_E_UNSUPPORTED;
   cuuint64_t d[4], st[3];
@@ -67,7 +67,7 @@ int make_map_4d(CUtensorMap* out, int elem_bytes, const void* base, const unsign
   for (int i = 0; i < 3; ++i) st[i] = strides_bytes[i];
   const CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                         const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? EHGR_OK : EHGR_E_UNSUPPORTED;
 }

@@ -78,6 +78,7 @@ struct GemmArgs {
   int b_resident;  // 1: whole [BN x Kp] B staged once; 0: a [BN x 64] slice per stage
   int bm_rows;     // rows of a tile that exist (128; CONV3 by TMA: the pixels of one box, 98 or 112) — tile t starts at row t*bm_rows
   int cv_hbox, cv_nbox, cv_tiles_per_frame;   // CONV3 by TMA: a tile = cv_nbox frames x cv_hbox rows x the full width
+  int cv_sw64;     // CONV3 by TMA with 32-channel pixels: a stage = two taps, each a box of 64-byte rows (SWIZZLE_64B), 8 KB apart
   int b_tma;       // streamed slice arrives as TMA box(es) in the SWIZZLE_128B layout (else 16-byte cp.async, no swizzle)
   int b_bytes;     // bytes of the B part of a stage
   int n_stages;    // ring depth
@@ -309,12 +310,21 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
             // convolution is the hardware's out-of-bounds fill.  Box rows land in pixel order = the tile's row order.
             if (lane == 0) {
               const int cin = p.a.cv_cin;
-              const int tap = k_base / cin, ty = tap / 3;
               const int frame_tile = m_tile / p.cv_tiles_per_frame;
               const int h0 = (m_tile - frame_tile * p.cv_tiles_per_frame) * p.cv_hbox;
-              tma::expect_tx_only(bar_full + 8 * s, static_cast<uint32_t>(p.bm_rows) * 128u);
-              tma::load_4d(a_dst32, &tm_a, bar_full + 8 * s, k_base - tap * cin, tap - ty * 3 - 1, h0 + ty - 1,
-                           frame_tile * p.cv_nbox);
+              if (!p.cv_sw64) {
+                const int tap = k_base / cin, ty = tap / 3;
+                tma::expect_tx_only(bar_full + 8 * s, static_cast<uint32_t>(p.bm_rows) * 128u);
+                tma::load_4d(a_dst32, &tm_a, bar_full + 8 * s, k_base - tap * cin, tap - ty * 3 - 1, h0 + ty - 1,
+                             frame_tile * p.cv_nbox);
+              } else {                                 // cin == 32: the stage's 64 columns are two whole taps
+                const int n_box = kvalid >> 5;
+                tma::expect_tx_only(bar_full + 8 * s, static_cast<uint32_t>(n_box * p.bm_rows) * 64u);
+                for (int b = 0; b < n_box; ++b) {
+                  const int tap = (k_base >> 5) + b, ty = tap / 3;
+                  tma::load_4d(a_dst32 + b * 8192, &tm_a, bar_full + 8 * s, 0, tap - ty * 3 - 1, h0 + ty - 1, frame_tile * p.cv_nbox);
+                }
+              }
             }
           } else if constexpr (kMode == EHGR_ROW_PLAIN) {
             // the box completes its bytes on the FULL barrier itself; the warp's arrival follows the weight slice
@@ -654,7 +664,8 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
       const uint32_t idesc = make_idesc(BM, p.BN, 0, p.w_is_kn ? 1 : 0);
       // A: no-swizzle core matrices (SBO = bytes between 8-row groups), or — kTma — SWIZZLE_128B rows (SBO = 1024 bytes,
       // layout type 2 in descriptor bits 61-63; a K=16 step advances the start address by 32 bytes inside the atom)
-      const uint32_t hi_a = kTma ? (64u | (1u << 14) | (2u << 29))
+      // (CONV3 with 32-channel pixels: SWIZZLE_64B — layout type 4, SBO 512 bytes; K steps 0,1 in the first tap's box, 2,3 in the second)
+      const uint32_t hi_a = kTma ? (p.cv_sw64 ? (32u | (1u << 14) | (4u << 29)) : (64u | (1u << 14) | (2u << 29)))
                                  : (((static_cast<uint32_t>(a_sbo) >> 4) & 0x3FFF) | (1u << 14));      // SBO | version
       constexpr uint32_t a_kstep = kTma ? 2u : 16u;
       // B: resident / cp.async slices = no-swizzle core matrices (SBO = Kp*16 or 1024 bytes, K step 256 bytes); TMA slices =
@@ -685,7 +696,7 @@ pw_gemm_tc_kernel(const __grid_constant__ GemmArgs p, const __grid_constant__ CU
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk)
             if (kk < ksteps)
-              umma_bf16(d_tmem, desc(a_lo + kk * a_kstep, hi_a), desc(b_lo + kk * b_kstep, hi_b), idesc, (ks | kk) ? 1u : 0u);
+              umma_bf16(d_tmem, desc(a_lo + ((kTma && p.cv_sw64) ? (kk >> 1) * 512u + (kk & 1) * 2u : kk * a_kstep), hi_a), desc(b_lo + kk * b_kstep, hi_b), idesc, (ks | kk) ? 1u : 0u);
           umma_commit(bar_empty + 8 * s);          // ring slot free once these MMAs have read it
         }
         umma_commit(bar_tfull + 8 * buf);          // accumulator complete
@@ -863,10 +874,12 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
   p.m_tiles = static_cast<int>(cdiv(M, tc::BM));
   p.bm_rows = tc::BM;
   p.cv_hbox = p.cv_nbox = p.cv_tiles_per_frame = 1;
+  p.cv_sw64 = 0;
   // CONV3 im2col by TMA: plain operand at the output resolution, whole 64-channel stages, and a tile geometry of whole
   // image rows (cv_hbox divides the height) or whole frames that fits the 128 rows of a UMMA tile
   bool conv_tma = false;
-  if (a.mode == EHGR_ROW_CONV3 && !a.scale && !a.cv_up && a.cv_cin % 64 == 0 && a.cv_w <= 128 && w16) {
+  if (a.mode == EHGR_ROW_CONV3 && !a.scale && !a.cv_up && (a.cv_cin % 64 == 0 || a.cv_cin == 32) && a.cv_w <= 128 && w16) {
+    p.cv_sw64 = a.cv_cin == 32 ? 1 : 0;
     const int hw = a.cv_h * a.cv_w;
     if (hw <= tc::BM) {
       p.cv_hbox = a.cv_h;
@@ -954,8 +967,9 @@ int pw_gemm_tc(const RowOp& a, const float* w, const void* w16, int w_is_kn, voi
     const unsigned long long cin = a.cv_cin, wo = a.cv_w, ho = a.cv_h, frames = M / a.hw;
     const unsigned long long dims[4] = {cin, wo, ho, frames};
     const unsigned long long strides[3] = {cin * 2, wo * cin * 2, ho * wo * cin * 2};
-    const unsigned box[4] = {64, static_cast<unsigned>(wo), static_cast<unsigned>(p.cv_hbox), static_cast<unsigned>(p.cv_nbox)};
-    if (int st = tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box, /*swizzle128=*/true)) return st;
+    const unsigned box[4] = {p.cv_sw64 ? 32u : 64u, static_cast<unsigned>(wo), static_cast<unsigned>(p.cv_hbox),
+                             static_cast<unsigned>(p.cv_nbox)};
+    if (int st = tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box, p.cv_sw64 ? 64 : 128)) return st;
   }
   CUtensorMap tm_b;
   memset(&tm_b, 0, sizeof(tm_b));

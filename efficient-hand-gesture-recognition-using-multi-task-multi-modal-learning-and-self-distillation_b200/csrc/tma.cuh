@@ -16,7 +16,7 @@ int make_nhwc_bf16_map(CUtensorMap* out, const void* base, int nt, int h, int w,
 
 // generic 4-D map (dims / box innermost first, strides of dims 1..3 in bytes), bf16 (elem_bytes 2) or fp32 (4)
 int make_map_4d(CUtensorMap* out, int elem_bytes, const void* base, const unsigned long long (&dims)[4],
-                const unsigned long long (&strides_bytes)[3], const unsigned (&box)[4], bool swizzle128 = false);
+                const unsigned long long (&strides_bytes)[3], const unsigned (&box)[4], int swizzle_bytes = 0);   // 0 | 64 | 128
 
 // row-major bf16 matrix [rows, cols] -> boxes of box_rows x 64 columns in the SWIZZLE_128B shared-memory layout
 int make_map_2d_sw128(CUtensorMap* out, const void* base, unsigned long long cols, unsigned long long rows, unsigned box_rows);

@@ -35,7 +35,9 @@ CASES = [  # nt, hs, ws (stored grid), cin, cout, up, affine
     # plain operands with 64-channel stages: the tcgen05 engine gathers them with TMA boxes (whole frames per tile when the
     # map is small, else cv_hbox image rows): ragged frame counts, 2 / 7 / 5-row boxes, several column chunks
     (3, 14, 14, 64, 32, 0, False), (2, 28, 28, 64, 16, 0, False), (5, 5, 3, 64, 16, 0, False), (1, 20, 24, 128, 24, 0, False),
-    (3, 7, 7, 128, 320, 0, False), (2, 56, 56, 64, 8, 0, False)]
+    (3, 7, 7, 128, 320, 0, False), (2, 56, 56, 64, 8, 0, False),
+    # 32-channel pixels: two taps per stage as SWIZZLE_64B boxes, half-filled last stage (K = 288)
+    (2, 56, 56, 32, 32, 0, False), (3, 28, 28, 32, 64, 0, False), (5, 7, 7, 32, 16, 0, False)]
 
 
 @pytest.mark.parametrize("nt,hs,ws,cin,cout,up,affine", CASES)

@@ -58,7 +58,11 @@ def main():
         dwp = torch.zeros(cout * 9 * cin, dtype=torch.float32, device="cuda")
         stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
         flops = 2.0 * M * 9 * cin * cout
-        for tag, op in (("plain", f.op_conv3(x, None, None, 0, ho, ho, cin, up)), ("affine", f.op_conv3(x, sc, sh, 2, ho, ho, cin, up))):
+        xu = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1).contiguous().to(torch.bfloat16) if up else x
+        variants = [("gather", f.op_conv3(x, None, None, 0, ho, ho, cin, up)), ("affine", f.op_conv3(x, sc, sh, 2, ho, ho, cin, up))]
+        if up:       # what the fused chain runs: the upsample materialised, the operand gathered with TMA boxes
+            variants.insert(0, ("tma", f.op_conv3(xu, None, None, 0, ho, ho, cin, 0)))
+        for tag, op in variants:
             t = timeit(lambda: _lib.call("ehgr_pw_gemm_w16", ctypes.byref(op), w.data_ptr(), wf.data_ptr(), 0, out.data_ptr(), 0,
                                          stats.data_ptr(), M, 9 * cin, cout, 1, 2, sp), a.reps)
             print(f"fwd   {cin:5d}->{cout:4d} @{ho:3d} up={up} {tag:6s} {t * 1e6:9.1f} us  {flops / t / 1e12:7.1f} TFLOP/s")
