@@ -197,7 +197,7 @@ def test_mtmm_step_against_oracle(dtype, tol):
             d.eval()
     rgb, depth, labels = O.synthetic_clip_batch(1, 8, 224, 83, seed=4)
     old = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False      # the depth decoder still runs on library convolutions
+    torch.backends.cudnn.allow_tf32 = False      # (the oracle side, when it runs on the GPU; our step has no library convolution)
     try:
         with E.fused.compute_dtype(dtype):
             logits, dpred = model(rgb.cuda())
