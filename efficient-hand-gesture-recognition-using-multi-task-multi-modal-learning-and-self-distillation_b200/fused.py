@@ -430,6 +430,9 @@ class _ChainFunction(torch.autograd.Function):
             cur_final = out
             if u.tap:
                 outputs.append(out)
+                # the next unit saves its input for backward: keep a detached alias there, not the Function output itself
+                # (output -> grad_fn -> ctx -> saved input would be a reference cycle that only the cycle GC frees)
+                cur_final = out.detach()
         tap_units = [i for i, u in enumerate(units) if u.tap]
         if not units[-1].tap:
             outputs.append(cur_final)
