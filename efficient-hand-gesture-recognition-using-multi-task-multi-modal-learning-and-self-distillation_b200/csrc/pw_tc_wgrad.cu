@@ -44,6 +44,8 @@ struct WgradArgs {
   int tmem_cols;
   int n_stages, stage_bytes;
   int dy_blocks;  // kTma: 64-channel blocks of the dy part of a stage
+  int stage_rows; // kTma: reduction rows of a stage (32; CONV3 by TMA: the box's pixels rounded up to 16 — the rest stays zero)
+  int box_px, cv_hb, cv_nb, cv_tpf;   // CONV3 by TMA: a stage = one box of cv_nb frames x cv_hb image rows x the full width
 };
 
 // Asynchronous staging of one operand of a ring stage (32 rows x `groups` 8-channel groups): lane owns a
@@ -229,8 +231,8 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
   constexpr bool kAsync = kAMode >= 0;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = kTma ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
-  const int gs = kTma ? 4096 : kWgGroupStride;          // bytes between channel groups (kTma: 64-channel blocks) of a stage
-  const int dy_bytes = kTma ? p.dy_blocks * 4096 : 16 * gs;   // 128 n = 16 groups
+  const int gs = kTma ? p.stage_rows * 128 : kWgGroupStride;   // bytes between channel groups (kTma: 64-channel blocks) of a stage
+  const int dy_bytes = kTma ? p.dy_blocks * gs : 16 * gs;      // 128 n = 16 groups
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * p.stage_bytes);
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kWgMaxStages), bar_done = smem_u32(bars + 2 * kWgMaxStages);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
@@ -270,7 +272,8 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
   if (warp < pw) {
     if constexpr (kTma) {
       const int a_blocks = (k_valid + 63) >> 6, dy_blocks = (n_valid + 63) >> 6;
-      const uint32_t bytes_dy = static_cast<uint32_t>(dy_blocks) * 4096u, bytes_a = static_cast<uint32_t>(a_blocks) * 4096u;
+      const uint32_t box_bytes = static_cast<uint32_t>(kAMode == EHGR_ROW_CONV3 ? p.box_px : kMS) * 128u;
+      const uint32_t bytes_dy = static_cast<uint32_t>(dy_blocks) * box_bytes, bytes_a = static_cast<uint32_t>(a_blocks) * box_bytes;
       // AFFINE: lane = 8-channel column `lane` of the tile (block lane >> 3, chunk lane & 7), all 32 rows of a stage
       RowLoader<__nv_bfloat16, 8, false, false> ld_a;
       RowOp ac = p.a;
@@ -286,6 +289,23 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
         const uint32_t dy_dst = smem_base + s * p.stage_bytes, a_dst = dy_dst + dy_bytes;
         const int row0 = static_cast<int>(mc * kMS);
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if constexpr (kAMode == EHGR_ROW_CONV3) {
+          // im2col by TMA: the stage's pixels are one box (cv_nb frames x cv_hb image rows x the full width): dy's rows
+          // are that contiguous pixel range, a's 64-channel blocks are the same box shifted by each block's tap (the zero
+          // padding is the out-of-bounds fill); rows past the box stay zero from the ring's initialisation
+          if (lane == 0) {
+            const int ft = static_cast<int>(mc / p.cv_tpf), h0 = static_cast<int>(mc - static_cast<long long>(ft) * p.cv_tpf) * p.cv_hb;
+            const int nfr = ft * p.cv_nb;
+            const int px0 = (nfr * p.a.cv_h + h0) * p.a.cv_w;
+            tma::expect_tx(bar_full + 8 * s, bytes_dy + bytes_a);
+            for (int b = 0; b < dy_blocks; ++b) tma::load_2d(dy_dst + b * gs, &tm_dy, bar_full + 8 * s, n0 + b * 64, px0);
+            for (int b = 0; b < a_blocks; ++b) {
+              const int k = k0 + b * 64, tap = k / p.a.cv_cin, ty = tap / 3;
+              tma::load_4d(a_dst + b * gs, &tm_a, bar_full + 8 * s, k - tap * p.a.cv_cin, tap - ty * 3 - 1, h0 + ty - 1, nfr);
+            }
+          }
+          continue;
+        }
         if (lane == 0) {
           if (kAMode == EHGR_ROW_PLAIN) {
             tma::expect_tx(bar_full + 8 * s, bytes_dy + bytes_a);      // the one arrival; every box completes its bytes here
@@ -415,13 +435,15 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
       tc_fence_after();
       const uint32_t dy_addr = smem_base + s * p.stage_bytes;
       const uint32_t a_addr = dy_addr + dy_bytes;
-#pragma unroll
-      for (int kk = 0; kk < kMS / 16; ++kk) {
+      const int ksteps = kTma ? p.stage_rows >> 4 : kMS / 16;
+      const uint32_t blk = static_cast<uint32_t>(gs);
+#pragma unroll 4
+      for (int kk = 0; kk < ksteps; ++kk) {
         // 16 rows of m = two 8-row core matrices = 256 bytes; LBO (m groups) = 128, SBO (channel groups) = gs
         // no swizzle: 16 rows of m = two 8-row core matrices = 256 bytes, LBO (m groups) = 128, SBO (channel groups) = gs;
         // kTma: SWIZZLE_128B, a K=16 step = two 1 KB row groups, LBO = 4096 (64-channel blocks), SBO = 1024
-        const uint64_t da = kTma ? (make_desc(dy_addr + kk * 2048, 4096, 1024) | (2ull << 61)) : make_desc(dy_addr + kk * 256, 128, gs);
-        const uint64_t db = kTma ? (make_desc(a_addr + kk * 2048, 4096, 1024) | (2ull << 61)) : make_desc(a_addr + kk * 256, 128, gs);
+        const uint64_t da = kTma ? (make_desc(dy_addr + kk * 2048, blk, 1024) | (2ull << 61)) : make_desc(dy_addr + kk * 256, 128, gs);
+        const uint64_t db = kTma ? (make_desc(a_addr + kk * 2048, blk, 1024) | (2ull << 61)) : make_desc(a_addr + kk * 256, 128, gs);
         umma_bf16(tmem_base, da, db, idesc, (it | kk) ? 1u : 0u);
       }
       umma_commit(bar_empty + 8 * s);
@@ -481,22 +503,60 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   p.n_tiles = (N + 127) / 128;
   p.n_tile = ((N + p.n_tiles - 1) / p.n_tiles + 7) & ~7;
   p.m_chunks = cdiv(M, tc::kMS);
-  const int tiles = p.n_tiles * p.k_tiles;
+  int tiles = p.n_tiles * p.k_tiles;
   p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>(p.m_chunks, 2 * kNumSMs / tiles)));
+  constexpr int kBudget = tc::kWgBudget;
+  // TMA + SWIZZLE_128B operand path: both operands read one tensor row by row
+  bool use_tma = dy.mode == EHGR_ROW_PLAIN && (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE) && M < 0x7fffffffLL;
+  p.stage_rows = tc::kMS;
+  p.box_px = tc::kMS;
+  p.cv_hb = p.cv_nb = p.cv_tpf = 1;
+  // CONV3 im2col by TMA: plain operand at the output resolution with 64-channel pixels; a stage = one box of <= 64 pixels
+  bool conv_tma = false;
+  if (dy.mode == EHGR_ROW_PLAIN && a.mode == EHGR_ROW_CONV3 && !a.scale && !a.cv_up && a.cv_cin % 64 == 0 && a.cv_w <= 64) {
+    const int hw = a.cv_h * a.cv_w;
+    if (hw <= 64) {
+      p.cv_hb = a.cv_h;
+      p.cv_nb = 64 / hw;
+      p.cv_tpf = 1;
+      conv_tma = true;
+    } else {
+      for (int hb = 64 / a.cv_w; hb >= 1; --hb)
+        if (a.cv_h % hb == 0) { p.cv_hb = hb; conv_tma = true; break; }
+      p.cv_nb = 1;
+      p.cv_tpf = a.cv_h / p.cv_hb;
+    }
+    if (conv_tma) {
+      p.BKc = std::min(256, K);                       // whole 64-channel blocks: a block never straddles a tap
+      p.k_tiles = (K + p.BKc - 1) / p.BKc;
+      tiles = p.n_tiles * p.k_tiles;
+      p.box_px = p.cv_nb * p.cv_hb * a.cv_w;
+      p.stage_rows = (p.box_px + 15) & ~15;
+      p.m_chunks = cdiv(M / hw, p.cv_nb) * p.cv_tpf;
+      p.splits = static_cast<int>(std::max<long long>(1, std::min<long long>(p.m_chunks, 2 * kNumSMs / tiles)));
+      use_tma = true;
+    }
+  }
   int cols = 32;
   while (cols < p.BKc) cols <<= 1;
   p.tmem_cols = cols;
-  constexpr int kBudget = tc::kWgBudget;
-  // TMA + SWIZZLE_128B operand path: both operands read one tensor row by row
-  const bool use_tma = dy.mode == EHGR_ROW_PLAIN && (a.mode == EHGR_ROW_PLAIN || a.mode == EHGR_ROW_AFFINE) && M < 0x7fffffffLL;
   p.dy_blocks = (p.n_tile + 63) / 64;
-  p.stage_bytes = use_tma ? (p.dy_blocks + (p.BKc + 63) / 64) * 4096 : (16 + p.BKc / 8) * tc::kWgGroupStride;
+  p.stage_bytes = use_tma ? (p.dy_blocks + (p.BKc + 63) / 64) * p.stage_rows * 128 : (16 + p.BKc / 8) * tc::kWgGroupStride;
   p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes - (use_tma ? 1024 : 0)) / p.stage_bytes));
   const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes + (use_tma ? 1024 : 0);
   CUtensorMap tm_dy, tm_a;
   memset(&tm_dy, 0, sizeof(tm_dy));
   memset(&tm_a, 0, sizeof(tm_a));
-  if (use_tma) {
+  if (conv_tma) {
+    if (int st = tma::make_map_2d_sw128(&tm_dy, dy.in1, static_cast<unsigned long long>(N), static_cast<unsigned long long>(M),
+                                        static_cast<unsigned>(p.box_px)))
+      return st;
+    const unsigned long long cin = a.cv_cin, wo = a.cv_w, ho = a.cv_h, frames = M / a.hw;
+    const unsigned long long dims[4] = {cin, wo, ho, frames};
+    const unsigned long long strides[3] = {cin * 2, wo * cin * 2, ho * wo * cin * 2};
+    const unsigned box[4] = {64, static_cast<unsigned>(wo), static_cast<unsigned>(p.cv_hb), static_cast<unsigned>(p.cv_nb)};
+    if (int st = tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box, 128)) return st;
+  } else if (use_tma) {
     if (int st = tma::make_map_2d_sw128(&tm_dy, dy.in1, static_cast<unsigned long long>(N), static_cast<unsigned long long>(M), tc::kMS)) return st;
     if (int st = tma::make_map_2d_sw128(&tm_a, a.in1, static_cast<unsigned long long>(K), static_cast<unsigned long long>(M), tc::kMS)) return st;
   }
@@ -513,7 +573,7 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   if (!async) go(std::integral_constant<int, -1>{}, F{});
   else if (a.mode == EHGR_ROW_PLAIN) { if (use_tma) go(std::integral_constant<int, EHGR_ROW_PLAIN>{}, T{}); else go(std::integral_constant<int, EHGR_ROW_PLAIN>{}, F{}); }
   else if (a.mode == EHGR_ROW_AFFINE) { if (use_tma) go(std::integral_constant<int, EHGR_ROW_AFFINE>{}, T{}); else go(std::integral_constant<int, EHGR_ROW_AFFINE>{}, F{}); }
-  else if (a.mode == EHGR_ROW_CONV3) go(std::integral_constant<int, EHGR_ROW_CONV3>{}, F{});
+  else if (a.mode == EHGR_ROW_CONV3) { if (conv_tma) go(std::integral_constant<int, EHGR_ROW_CONV3>{}, T{}); else go(std::integral_constant<int, EHGR_ROW_CONV3>{}, F{}); }
   else go(std::integral_constant<int, EHGR_ROW_SHIFT>{}, F{});
   return launch_status();
 }
