@@ -46,6 +46,7 @@ struct WgradArgs {
   int dy_blocks;  // kTma: 64-channel blocks of the dy part of a stage
   int stage_rows; // kTma: reduction rows of a stage (32; CONV3 by TMA: the box's pixels rounded up to 16 — the rest stays zero)
   int box_px, cv_hb, cv_nb, cv_tpf;   // CONV3 by TMA: a stage = one box of cv_nb frames x cv_hb image rows x the full width
+  int a_sw64;     // CONV3 by TMA with 32-channel pixels: operand a in 32-channel blocks of 64-byte rows (SWIZZLE_64B)
 };
 
 // Asynchronous staging of one operand of a ring stage (32 rows x `groups` 8-channel groups): lane owns a
@@ -273,7 +274,10 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
     if constexpr (kTma) {
       const int a_blocks = (k_valid + 63) >> 6, dy_blocks = (n_valid + 63) >> 6;
       const uint32_t box_bytes = static_cast<uint32_t>(kAMode == EHGR_ROW_CONV3 ? p.box_px : kMS) * 128u;
-      const uint32_t bytes_dy = static_cast<uint32_t>(dy_blocks) * box_bytes, bytes_a = static_cast<uint32_t>(a_blocks) * box_bytes;
+      const int a_blk = p.a_sw64 ? p.stage_rows * 64 : gs;          // bytes between operand a's channel blocks
+      const int a_nblk = p.a_sw64 ? (k_valid + 31) >> 5 : a_blocks;
+      const uint32_t bytes_dy = static_cast<uint32_t>(dy_blocks) * box_bytes;
+      const uint32_t bytes_a = p.a_sw64 ? static_cast<uint32_t>(a_nblk * p.box_px) * 64u : static_cast<uint32_t>(a_blocks) * box_bytes;
       // AFFINE: lane = 8-channel column `lane` of the tile (block lane >> 3, chunk lane & 7), all 32 rows of a stage
       RowLoader<__nv_bfloat16, 8, false, false> ld_a;
       RowOp ac = p.a;
@@ -299,9 +303,9 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
             const int px0 = (nfr * p.a.cv_h + h0) * p.a.cv_w;
             tma::expect_tx(bar_full + 8 * s, bytes_dy + bytes_a);
             for (int b = 0; b < dy_blocks; ++b) tma::load_2d(dy_dst + b * gs, &tm_dy, bar_full + 8 * s, n0 + b * 64, px0);
-            for (int b = 0; b < a_blocks; ++b) {
-              const int k = k0 + b * 64, tap = k / p.a.cv_cin, ty = tap / 3;
-              tma::load_4d(a_dst + b * gs, &tm_a, bar_full + 8 * s, k - tap * p.a.cv_cin, tap - ty * 3 - 1, h0 + ty - 1, nfr);
+            for (int b = 0; b < a_nblk; ++b) {
+              const int k = k0 + b * (p.a_sw64 ? 32 : 64), tap = k / p.a.cv_cin, ty = tap / 3;
+              tma::load_4d(a_dst + b * a_blk, &tm_a, bar_full + 8 * s, k - tap * p.a.cv_cin, tap - ty * 3 - 1, h0 + ty - 1, nfr);
             }
           }
           continue;
@@ -443,7 +447,10 @@ pw_wgrad_tc_kernel(const __grid_constant__ WgradArgs p, const __grid_constant__ 
         // no swizzle: 16 rows of m = two 8-row core matrices = 256 bytes, LBO (m groups) = 128, SBO (channel groups) = gs;
         // kTma: SWIZZLE_128B, a K=16 step = two 1 KB row groups, LBO = 4096 (64-channel blocks), SBO = 1024
         const uint64_t da = kTma ? (make_desc(dy_addr + kk * 2048, blk, 1024) | (2ull << 61)) : make_desc(dy_addr + kk * 256, 128, gs);
-        const uint64_t db = kTma ? (make_desc(a_addr + kk * 2048, blk, 1024) | (2ull << 61)) : make_desc(a_addr + kk * 256, 128, gs);
+        // (operand a with 32-channel pixels: SWIZZLE_64B — 64-byte rows, 8-row groups 512 bytes apart, a K=16 step = 1 KB)
+        const uint64_t db = !kTma ? make_desc(a_addr + kk * 256, 128, gs)
+                            : p.a_sw64 ? (make_desc(a_addr + kk * 1024, static_cast<uint32_t>(p.stage_rows) * 64u, 512) | (4ull << 61))
+                                       : (make_desc(a_addr + kk * 2048, blk, 1024) | (2ull << 61));
         umma_bf16(tmem_base, da, db, idesc, (it | kk) ? 1u : 0u);
       }
       umma_commit(bar_empty + 8 * s);
@@ -511,9 +518,12 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   p.stage_rows = tc::kMS;
   p.box_px = tc::kMS;
   p.cv_hb = p.cv_nb = p.cv_tpf = 1;
+  p.a_sw64 = 0;
   // CONV3 im2col by TMA: plain operand at the output resolution with 64-channel pixels; a stage = one box of <= 64 pixels
   bool conv_tma = false;
-  if (dy.mode == EHGR_ROW_PLAIN && a.mode == EHGR_ROW_CONV3 && !a.scale && !a.cv_up && a.cv_cin % 64 == 0 && a.cv_w <= 64) {
+  if (dy.mode == EHGR_ROW_PLAIN && a.mode == EHGR_ROW_CONV3 && !a.scale && !a.cv_up && (a.cv_cin % 64 == 0 || a.cv_cin == 32) &&
+      a.cv_w <= 64) {
+    p.a_sw64 = a.cv_cin == 32 ? 1 : 0;
     const int hw = a.cv_h * a.cv_w;
     if (hw <= 64) {
       p.cv_hb = a.cv_h;
@@ -527,7 +537,7 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
       p.cv_tpf = a.cv_h / p.cv_hb;
     }
     if (conv_tma) {
-      p.BKc = std::min(256, K);                       // whole 64-channel blocks: a block never straddles a tap
+      p.BKc = std::min(256, K);                       // whole 64- (32-) channel blocks: a block never straddles a tap
       p.k_tiles = (K + p.BKc - 1) / p.BKc;
       tiles = p.n_tiles * p.k_tiles;
       p.box_px = p.cv_nb * p.cv_hb * a.cv_w;
@@ -541,7 +551,9 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
   while (cols < p.BKc) cols <<= 1;
   p.tmem_cols = cols;
   p.dy_blocks = (p.n_tile + 63) / 64;
-  p.stage_bytes = use_tma ? (p.dy_blocks + (p.BKc + 63) / 64) * p.stage_rows * 128 : (16 + p.BKc / 8) * tc::kWgGroupStride;
+  p.stage_bytes = !use_tma ? (16 + p.BKc / 8) * tc::kWgGroupStride
+                  : (conv_tma && p.a_sw64) ? (p.dy_blocks * 128 + (p.BKc + 31) / 32 * 64) * p.stage_rows
+                                           : (p.dy_blocks + (p.BKc + 63) / 64) * p.stage_rows * 128;
   p.n_stages = std::max(2, std::min(tc::kWgMaxStages, (kBudget - tc::kWgBarBytes - (use_tma ? 1024 : 0)) / p.stage_bytes));
   const size_t smem = static_cast<size_t>(p.n_stages) * p.stage_bytes + tc::kWgBarBytes + (use_tma ? 1024 : 0);
   CUtensorMap tm_dy, tm_a;
@@ -554,8 +566,8 @@ int pw_wgrad_tc(const RowOp& dy, const RowOp& a, float* dw, long long M, int K, 
     const unsigned long long cin = a.cv_cin, wo = a.cv_w, ho = a.cv_h, frames = M / a.hw;
     const unsigned long long dims[4] = {cin, wo, ho, frames};
     const unsigned long long strides[3] = {cin * 2, wo * cin * 2, ho * wo * cin * 2};
-    const unsigned box[4] = {64, static_cast<unsigned>(wo), static_cast<unsigned>(p.cv_hb), static_cast<unsigned>(p.cv_nb)};
-    if (int st = tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box, 128)) return st;
+    const unsigned box[4] = {p.a_sw64 ? 32u : 64u, static_cast<unsigned>(wo), static_cast<unsigned>(p.cv_hb), static_cast<unsigned>(p.cv_nb)};
+    if (int st = tma::make_map_4d(&tm_a, 2, a.in1, dims, strides, box, p.a_sw64 ? 64 : 128)) return st;
   } else if (use_tma) {
     if (int st = tma::make_map_2d_sw128(&tm_dy, dy.in1, static_cast<unsigned long long>(N), static_cast<unsigned long long>(M), tc::kMS)) return st;
     if (int st = tma::make_map_2d_sw128(&tm_a, a.in1, static_cast<unsigned long long>(K), static_cast<unsigned long long>(M), tc::kMS)) return st;
