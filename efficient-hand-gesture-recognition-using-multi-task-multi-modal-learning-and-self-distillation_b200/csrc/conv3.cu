@@ -1,9 +1,10 @@
 // conv3.cu — N2: the pieces of the MTMM depth decoder (models/models_MTMM.py:129-155) around the implicit-GEMM
 // convolution.  The dense 3x3 convolutions themselves run on the pointwise-GEMM kernels through the CONV3 row
-// operand (rowop.cuh, pw_tc.cu, pw_tc_wgrad.cu: im2col gather with the producer's BatchNorm+ReLU and the nearest x2
-// upsample folded into the load); this file holds
+// operand (rowop.cuh, pw_tc.cu, pw_tc_wgrad.cu: im2col by TMA boxes for a finished activation, or a cp.async gather
+// with the producer's BatchNorm+ReLU and the nearest x2 upsample folded into the load); this file holds
 //   * the weight layouts those GEMMs read (conv3_pack) and the inverse for the weight gradient (conv3_unpack_grad),
-//   * the adjoint of nn.Upsample(scale_factor=2, mode='nearest') (upsample2_bwd: 2x2 block sums),
+//   * nn.Upsample(scale_factor=2, mode='nearest') materialised (upsample2_fwd: the TMA gather cannot fold the x2 index
+//     map) and its adjoint (upsample2_bwd: 2x2 block sums),
 //   * the depth head Conv2d(32, 1, 1, bias) + Sigmoid, forward and backward, as one streaming pass each.
 #include "rowop.cuh"
 

@@ -821,8 +821,9 @@ class _DepthHeadFunction(torch.autograd.Function):
 
 def depth_decoder(seq: nn.Sequential, fmap):
     """``global_decoder(fmap)`` of models/models_MTMM.py:129-155 -> [NT, 1, 8H, 8W] fp32: the four 3x3 convolutions are ONE
-    fused chain of implicit-GEMM stages (BatchNorm+ReLU and the three nearest x2 upsamples live in the operand loads), the
-    1x1 convolution + sigmoid is one more kernel.  No library convolution / BatchNorm / activation / upsample op."""
+    fused chain of implicit-GEMM units (tcgen05, im2col by TMA boxes; BatchNorm statistics in the GEMM epilogue,
+    BatchNorm+ReLU applied once per unit, the three nearest x2 upsamples as one small copy each), the 1x1 convolution +
+    sigmoid is one more kernel.  No library convolution / BatchNorm / activation / upsample op."""
     _lib.require_cuda(fmap)
     parsed = parse_depth_decoder(seq)
     if parsed is None:
