@@ -186,6 +186,13 @@ class TSN(nn.Module):
     def forward(self, input, no_reshape=False):
         assert input.size()[1] > 3, \
             'channel and temporal dimension mismatch, tensor size should be: n_batch, n_segment, nc, h, w'
+        if (input.is_cuda and not no_reshape and self.reshape and self.base_model_name == 'mobilenetv2'
+                and not (self.is_shift and self.temporal_pool)):
+            # backbone -> global average pool -> Dropout -> new_fc -> segment consensus, all on the library's kernels
+            # (csrc/head.cu folds the 'avg' consensus in front of the classifier GEMV: fused.classifier_head)
+            from . import fused
+            fmap = fused.mobilenet_v2_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))
+            return fused.classifier_head(self, fmap)
         if not no_reshape:
             sample_len = 3 * self.new_length
             base_out = self.base_model(input.view((-1, sample_len) + input.size()[-2:]))
