@@ -47,8 +47,9 @@ def test_argument_errors_do_not_need_a_gpu():
 
 
 def test_built_objects_contain_the_blackwell_instructions():
-    """SASS evidence (no GPU needed): the GEMMs issue tcgen05 MMAs (UTCHMMA) fed by cp.async (LDGSTS), the depthwise
-    and stem kernels load their tiles with TMA (UTMALDG), and the FP32 inner loops use packed FFMA2."""
+    """SASS evidence (no GPU needed): the GEMMs issue tcgen05 MMAs (UTCHMMA) fed by TMA boxes (UTMALDG: plain / affine /
+    gated operands, weight slices, 3x3 im2col) and cp.async gathers (LDGSTS: temporal shift), the depthwise and stem
+    kernels load their tiles with TMA, and the FP32 inner loops use packed FFMA2."""
     import shutil
     import subprocess
     from pathlib import Path
@@ -59,7 +60,7 @@ def test_built_objects_contain_the_blackwell_instructions():
     build = Path(ehgr_b200._lib.LIB_PATH).parent / "build"
     if not (build / "pw_tc.o").exists():
         ehgr_b200.build.build()
-    want = {"pw_tc.o": ("UTCHMMA", "LDGSTS", "UTCBAR"), "pw_tc_wgrad.o": ("UTCHMMA", "LDGSTS"),
+    want = {"pw_tc.o": ("UTCHMMA", "LDGSTS", "UTCBAR", "UTMALDG"), "pw_tc_wgrad.o": ("UTCHMMA", "LDGSTS", "UTMALDG"),
             "dw_sw.o": ("UTMALDG", "FFMA2"), "stem.o": ("UTMALDG", "FFMA2"), "bn.o": ("FFMA2",)}
     for obj, mnemonics in want.items():
         sass = subprocess.run(["cuobjdump", "-sass", str(build / obj)], capture_output=True, text=True, timeout=300).stdout
