@@ -166,8 +166,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
-    warm = max(1, min(args.warmup, 2))
+    # the same K timed steps and W warm-up steps as the GPU arm (a CPU step of `--cpu-clips` clips takes ~0.2 s:
+    # K = 20, W = 5 is a few seconds); only absurd requests are bounded so that the arm always ends within minutes
+    steps = max(1, min(args.steps, 200))
+    warm = max(0, min(args.warmup, 50))
     v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, steps, warm, args.workload, args.classes)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
