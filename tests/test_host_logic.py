@@ -138,3 +138,22 @@ def test_mtmm_sd_wrapper_structure_and_policies():
     with pytest.raises(NotImplementedError):
         with contextlib.redirect_stdout(io.StringIO()):
             E.tsn_mtmm_sd.TSN(83, 8, 'RGB', base_model='mobilenetv2', pretrain=None, modal='rgb_depth_skeleton')
+
+
+def test_depth_decoder_parser_recognises_the_reference_architecture_only():
+    """fused.parse_depth_decoder maps models/models_MTMM.py:129-155 onto four conv3 stages (upsample flags on stages 2-4)
+    and the 1x1 head; any other decoder (the ConvTranspose ones of models_MTMM_SD.py:226-249) is left to its modules."""
+    import ehgr_b200 as E
+    dec = E.tsn_mtmm.make_global_decoder(1280)
+    stages, head = E.fused.parse_depth_decoder(dec)
+    assert [(s.kind, s.conv.in_channels, s.conv.out_channels, s.up, s.relu6) for s in stages] == [
+        ("conv3", 1280, 256, False, 2), ("conv3", 256, 64, True, 2), ("conv3", 64, 32, True, 2), ("conv3", 32, 32, True, 2)]
+    assert head.in_channels == 32 and head.out_channels == 1 and head.bias is not None
+    assert sorted(dec.state_dict()) == sorted(
+        [f"{i}.weight" for i in (0, 4, 8, 12, 15)] + ["15.bias"] +
+        [f"{i}.{k}" for i in (1, 5, 9, 13) for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")])
+    assert E.fused.parse_depth_decoder(E.tsn_mtmm_sd.make_convt_decoder((1280, 256, 32, 1))) is None
+    import torch.nn as nn
+    assert E.fused.parse_depth_decoder(nn.Sequential(nn.Conv2d(8, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8), nn.ReLU(),
+                                                     nn.Upsample(scale_factor=2, mode="bilinear"), nn.Conv2d(8, 1, 1),
+                                                     nn.Sigmoid())) is None
