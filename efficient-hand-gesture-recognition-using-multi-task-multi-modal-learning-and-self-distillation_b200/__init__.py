@@ -14,6 +14,7 @@ mobilenet_v2_module = _importlib.import_module(__name__ + ".mobilenet_v2")
 action = _importlib.import_module(__name__ + ".action")
 basic_ops = _importlib.import_module(__name__ + ".basic_ops")
 fused = _importlib.import_module(__name__ + ".fused")
+resnet_ops = _importlib.import_module(__name__ + ".resnet_ops")
 tsn = _importlib.import_module(__name__ + ".tsn")
 losses = _importlib.import_module(__name__ + ".losses")
 train_step = _importlib.import_module(__name__ + ".train_step")

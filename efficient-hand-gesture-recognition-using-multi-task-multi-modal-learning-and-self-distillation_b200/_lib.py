@@ -169,6 +169,15 @@ SIGNATURES = {
     "ehgr_action_fir_bwd": [_A, _P, _P, _P, _P, _I, _P],
     "ehgr_mtmm_loss": [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "ehgr_sd_loss": [_P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _L, _I, _P],
+    # N3: torchvision ResNet bottleneck path (csrc/resnet.cu)
+    "ehgr_stem7_fwd": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "ehgr_stem7_wgrad": [_R, _P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "ehgr_maxpool3_fwd": [_R, _P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_maxpool3_bwd": [_P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_subsample2_fwd": [_P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_subsample2_bwd": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "ehgr_bn_add_relu": [_P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "ehgr_relu_bwd": [_P, _P, _P, _L, _I, _P],
 }
 
 

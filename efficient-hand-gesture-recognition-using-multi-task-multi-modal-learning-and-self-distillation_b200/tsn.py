@@ -193,6 +193,11 @@ class TSN(nn.Module):
             from . import fused
             fmap = fused.mobilenet_v2_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))
             return fused.classifier_head(self, fmap)
+        if input.is_cuda and not no_reshape and self.reshape and self._fused_resnet():
+            # N3: torchvision Bottleneck ResNet (+ TemporalShift on conv1) on the library's kernels (resnet_ops.py)
+            from . import fused, resnet_ops
+            fmap = resnet_ops.resnet_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))
+            return fused.classifier_head(self, fmap)
         if not no_reshape:
             sample_len = 3 * self.new_length
             base_out = self.base_model(input.view((-1, sample_len) + input.size()[-2:]))
@@ -207,6 +212,19 @@ class TSN(nn.Module):
             base_out = base_out.view((-1, segs) + base_out.size()[1:])
             output = self.consensus(base_out)
             return output.squeeze(1)
+
+    def _fused_resnet(self) -> bool:
+        """True when the backbone is a torchvision ResNet the sm_100a path covers (resnet_ops.plan_of).  Anything else
+        (BasicBlock nets, Action on wide stages, temporal_pool ...) runs the torchvision modules, and says so once."""
+        if 'resnet' not in self.base_model_name:
+            return False
+        from . import resnet_ops
+        ok, why = resnet_ops.supported(self.base_model)
+        if not ok and not getattr(self, '_warned_library_resnet', False):
+            import warnings
+            warnings.warn("ResNet backbone runs on torchvision / library kernels, not on libehgr_b200: " + why)
+            self._warned_library_resnet = True
+        return ok
 
     @property
     def crop_size(self):

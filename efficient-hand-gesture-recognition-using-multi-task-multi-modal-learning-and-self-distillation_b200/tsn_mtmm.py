@@ -57,6 +57,9 @@ class TSN(_BaseTSN):
         bm = self.base_model
         if self.base_model_name == 'mobilenetv2':
             return fused.mobilenet_v2_features(bm, x)
+        if x.is_cuda and self._fused_resnet():                 # N3: Bottleneck ResNet on the library's kernels
+            from . import resnet_ops
+            return resnet_ops.resnet_features(bm, x)
         x = bm.maxpool(bm.relu(bm.bn1(bm.conv1(x))))
         return bm.layer4(bm.layer3(bm.layer2(bm.layer1(x))))
 

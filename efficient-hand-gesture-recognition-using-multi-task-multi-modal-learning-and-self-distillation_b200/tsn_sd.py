@@ -89,6 +89,9 @@ class TSN(_BaseTSN):
         bm = self.base_model
         if self.base_model_name == 'mobilenetv2':
             return fused.mobilenet_v2_features(bm, x, taps=MBV2_TAPS)          # (f3, f6, f13, final)
+        if x.is_cuda and self._fused_resnet():                 # N3: Bottleneck ResNet on the library's kernels
+            from . import resnet_ops
+            return resnet_ops.resnet_features(bm, x, taps=(1, 2, 3))          # (layer1, layer2, layer3, layer4)
         x = bm.maxpool(bm.relu(bm.bn1(bm.conv1(x))))
         t1 = bm.layer1(x)
         t2 = bm.layer2(t1)

@@ -429,6 +429,42 @@ int ehgr_action_bwd_dxs(const ehgr_action* a, const void* gy, const void* xs, vo
 int ehgr_action_fir_bwd(const ehgr_action* a, const void* dxs, const void* x, const void* addend, void* dx, int dtype,
                         ehgr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * N3  torchvision ResNet bottleneck path (csrc/resnet.cu) — the reference builds torchvision.models.resnet50 for
+ *     base_model='resnet50' (models/models.py:108-117) and wraps conv1 of every bottleneck with a temporal module
+ *     (models/temporal_shift.py:101-146).  The 1x1 / 3x3 convolutions of a bottleneck run on ehgr_pw_gemm* /
+ *     ehgr_pw_wgrad (PLAIN / AFFINE / SHIFT / CONV3 operands); these entry points are the rest.  All activations NHWC.
+ *
+ *   ehgr_stem7_fwd   : replaces ResNet.conv1 = Conv2d(3, 64, 7, stride=2, padding=3, bias=False).  x [frames,3,h,w] NCHW
+ *                      (x_dtype), w [64,3,7,7] fp32, out [frames, ho, wo, 64] raw (before BatchNorm), ho = (h-1)/2+1;
+ *                      stats (optional, += ) [2*64] doubles: per-channel sum and sum of squares of the stored values.
+ *   ehgr_stem7_wgrad : dw [64,3,7,7] += rowop(dy)^T * patches(x); dy is usually a BNBWD operand over (g, raw).
+ *   ehgr_maxpool3_fwd: replaces ReLU + MaxPool2d(3, stride=2, padding=1) after bn1: y [frames,ho,wo,c] = window max of
+ *                      rowop(a) (an AFFINE operand = lazy BatchNorm+ReLU of the stem output); idx (uint8, same shape
+ *                      as y) = winning tap 3*ky+kx, first maximum in scan order as at::max_pool2d.
+ *   ehgr_maxpool3_bwd: gx [frames,h,w,c] = gradient w.r.t. the pooled tensor's input (gather over <= 4 windows, no atomics).
+ *   ehgr_subsample2_fwd: y = x[:, ::2, ::2, :] (+ statistics of y when stats != NULL).  conv(k, stride 2, padding (k-1)/2)
+ *                      == subsample2(conv(k, stride 1)), so layer{2,3,4}.0.conv2 and the downsample 1x1 (torchvision
+ *                      Bottleneck / ResNet._make_layer) reuse the stride-1 GEMMs.
+ *   ehgr_subsample2_bwd: the adjoint: gx [frames,h,w,c] = g at even (h, w), zero elsewhere.
+ *   ehgr_bn_add_relu : out = relu(raw*scale + shift + addend)  — `out = relu(bn3(conv3(.)) + identity)` (Bottleneck.forward).
+ *   ehgr_relu_bwd    : gz = g where out > 0 else 0, n elements (a multiple of the 16-byte vector).
+ * ------------------------------------------------------------------------------------------- */
+int ehgr_stem7_fwd(const void* x, const float* w, void* out, double* stats, long long frames, int h, int w_in, int cout,
+                   int x_dtype, int out_dtype, ehgr_stream_t stream);
+int ehgr_stem7_wgrad(const ehgr_rowop* dy, const void* x, float* dw, long long frames, int h, int w_in, int cout,
+                     int x_dtype, int dtype, ehgr_stream_t stream);
+int ehgr_maxpool3_fwd(const ehgr_rowop* a, void* y, void* idx, long long frames, int h, int w, int c, int dtype,
+                      ehgr_stream_t stream);
+int ehgr_maxpool3_bwd(const void* g, const void* idx, void* gx, long long frames, int h, int w, int c, int dtype,
+                      ehgr_stream_t stream);
+int ehgr_subsample2_fwd(const void* x, void* y, double* stats, long long frames, int h, int w, int c, int dtype,
+                        ehgr_stream_t stream);
+int ehgr_subsample2_bwd(const void* g, void* gx, long long frames, int h, int w, int c, int dtype, ehgr_stream_t stream);
+int ehgr_bn_add_relu(const void* raw, const float* scale, const float* shift, const void* addend, void* out, long long m,
+                     int c, int dtype, ehgr_stream_t stream);
+int ehgr_relu_bwd(const void* g, const void* out, void* gz, long long n, int dtype, ehgr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,276 @@
+"""TEST INFRASTRUCTURE — a numpy restatement of the C-ABI contracts in include/ehgr_b200.h, fp32 only, on HOST pointers.
+
+Purpose: the host-side orchestration of the fused autograd Functions (which kernels are called, with which operands,
+shapes and saved tensors, and where every gradient lands) can be exercised on a machine without a GPU: the CPU tests
+monkeypatch ``_lib.call`` with ``call`` below and compare the result with PyTorch autograd on the same modules.  Nothing
+in the product imports this file; the product path still refuses CPU tensors (``_lib.require_cuda``).  Each function
+states the header contract it restates; the CUDA kernels themselves are checked against PyTorch in the ``-m gpu`` tests.
+"""
+import ctypes
+
+import numpy as np
+
+F32 = np.float32
+
+
+def arr(ptr, shape, dtype=F32):
+    """numpy view of host memory at `ptr` (an int address, or None / 0)."""
+    if hasattr(ptr, "value"):
+        ptr = ptr.value
+    if not ptr:
+        return None
+    n = int(np.prod(shape))
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(int(ptr))
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _struct(ref):
+    return ref._obj if hasattr(ref, "_obj") else ref
+
+
+def _act(z, code):
+    if code == 1:
+        return np.clip(z, 0.0, 6.0)
+    if code == 2:
+        return np.maximum(z, 0.0)
+    return z
+
+
+def _mask(z, code):
+    if code == 1:
+        return (z > 0) & (z < 6)
+    if code == 2:
+        return z > 0
+    return np.ones_like(z, dtype=bool)
+
+
+def rowop(ref, M, C):
+    """struct ehgr_rowop evaluated for all rows: [M, C] float32 (C = K of the GEMM for CONV3)."""
+    op = _struct(ref)
+    mode = op.mode
+    if mode == 0:
+        return arr(op.in1, (M, C)).copy()
+    if mode == 1:
+        return _act(arr(op.in1, (M, C)) * arr(op.scale, (C,)) + arr(op.shift, (C,)), op.relu6).astype(F32)
+    if mode == 2:
+        T, hw, fold = op.n_segment, op.hw, op.fold
+        x = arr(op.in1, (M // (T * hw), T, hw, C))
+        out = np.zeros_like(x)
+        if op.shift_dir >= 0:
+            out[:, :-1, :, :fold] = x[:, 1:, :, :fold]
+            out[:, 1:, :, fold:2 * fold] = x[:, :-1, :, fold:2 * fold]
+        else:
+            out[:, 1:, :, :fold] = x[:, :-1, :, :fold]
+            out[:, :-1, :, fold:2 * fold] = x[:, 1:, :, fold:2 * fold]
+        out[:, :, :, 2 * fold:] = x[:, :, :, 2 * fold:]
+        return out.reshape(M, C)
+    if mode == 3:
+        g, r = arr(op.in1, (M, C)), arr(op.in2, (M, C))
+        if op.relu6:
+            g = g * _mask(r * arr(op.scale, (C,)) + arr(op.shift, (C,)), op.relu6)
+        return (arr(op.ca, (C,)) * g + arr(op.cb, (C,)) * r + arr(op.cc, (C,))).astype(F32)
+    if mode == 5:
+        H, W, cin, up = op.cv_h, op.cv_w, op.cv_cin, op.cv_up
+        assert C == 9 * cin and op.hw == H * W
+        frames = M // (H * W)
+        src = arr(op.in1, (frames, H >> up, W >> up, cin))
+        if op.scale:
+            src = _act(src * arr(op.scale, (cin,)) + arr(op.shift, (cin,)), op.relu6)
+        if up:
+            src = src.repeat(2, axis=1).repeat(2, axis=2)
+        pad = np.zeros((frames, H + 2, W + 2, cin), F32)
+        pad[:, 1:-1, 1:-1] = src
+        cols = [pad[:, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)]     # tap = 3*ky + kx
+        return np.concatenate(cols, axis=-1).reshape(M, 9 * cin).astype(F32)
+    raise NotImplementedError(f"row operand mode {mode}")
+
+
+def _add_stats(stats, y, C):
+    if stats:
+        s = arr(stats, (2 * C,), np.float64)
+        s[:C] += y.astype(np.float64).sum(0)
+        s[C:] += (y.astype(np.float64) ** 2).sum(0)
+
+
+def _half(v):
+    return (v - 1) // 2 + 1
+
+
+# ---- GEMM family -----------------------------------------------------------------------------------------------------
+def ehgr_pw_gemm_bn(a, w, w16, w_is_kn, out, addend, stats, M, K, N, dtype, engine, fin, stream):
+    assert dtype == 0 and fin is None
+    A = rowop(a, M, K)
+    Wm = arr(w, (K, N)) if w_is_kn else arr(w, (N, K)).T
+    y = A @ Wm
+    if addend:
+        y = y + arr(addend, (M, N))
+    arr(out, (M, N))[...] = y
+    _add_stats(stats, y, N)
+
+
+def ehgr_pw_gemm_w16(a, w, w16, w_is_kn, out, addend, stats, M, K, N, dtype, engine, stream):
+    ehgr_pw_gemm_bn(a, w, w16, w_is_kn, out, addend, stats, M, K, N, dtype, engine, None, stream)
+
+
+def ehgr_pw_wgrad(dy, a, dw, M, K, N, dtype, engine, stream):
+    assert dtype == 0
+    arr(dw, (N, K))[...] += rowop(dy, M, N).T @ rowop(a, M, K)
+
+
+def ehgr_conv3_pack(w, wf, wd, cout, cin, dtype, stream):
+    assert dtype == 0
+    W = arr(w, (cout, cin, 9))
+    if wf:
+        arr(wf, (cout, 9, cin))[...] = W.transpose(0, 2, 1)
+    if wd:
+        arr(wd, (cin, 9, cout))[...] = W[:, :, ::-1].transpose(1, 2, 0)
+
+
+def ehgr_conv3_unpack_grad(dwp, dw, cout, cin, stream):
+    arr(dw, (cout, cin, 9))[...] += arr(dwp, (cout, 9, cin)).transpose(0, 2, 1)
+
+
+# ---- BatchNorm -------------------------------------------------------------------------------------------------------
+def ehgr_bn_finalize(stats, count, gamma, beta, rm, rv, momentum, eps, training, scale, shift, mean, invstd, c, stream):
+    g = arr(gamma, (c,)) if gamma else np.ones(c, F32)
+    b = arr(beta, (c,)) if beta else np.zeros(c, F32)
+    if training:
+        s = arr(stats, (2 * c,), np.float64)
+        mu = s[:c] / count
+        var = np.maximum(s[c:] / count - mu * mu, 0.0)
+        if rm:
+            arr(rm, (c,))[...] = (1 - momentum) * arr(rm, (c,)) + momentum * mu
+            arr(rv, (c,))[...] = (1 - momentum) * arr(rv, (c,)) + momentum * var * (count / max(count - 1, 1))
+    else:
+        mu, var = arr(rm, (c,)).astype(np.float64), arr(rv, (c,)).astype(np.float64)
+    istd = 1.0 / np.sqrt(var + eps)
+    sc = g * istd
+    arr(scale, (c,))[...] = sc
+    arr(shift, (c,))[...] = b - mu * sc
+    if mean:
+        arr(mean, (c,))[...] = mu
+    if invstd:
+        arr(invstd, (c,))[...] = istd
+
+
+def ehgr_bn_bwd_reduce_fin(g, raw, scale, shift, relu6, sums, m, c, dtype, fin, stream):
+    assert dtype == 0 and fin is None
+    G, R = arr(g, (m, c)).astype(np.float64), arr(raw, (m, c)).astype(np.float64)
+    if relu6:
+        G = G * _mask(R * arr(scale, (c,)) + arr(shift, (c,)), relu6)
+    s = arr(sums, (2 * c,), np.float64)
+    s[:c] += G.sum(0)
+    s[c:] += (G * R).sum(0)
+
+
+def ehgr_bn_bwd_finalize(sums, count, gamma, mean, invstd, training, ca, cb, cc, dgamma, dbeta, c, stream):
+    s = arr(sums, (2 * c,), np.float64)
+    sdz, sdzr = s[:c], s[c:]
+    mu, istd = arr(mean, (c,)).astype(np.float64), arr(invstd, (c,)).astype(np.float64)
+    g = arr(gamma, (c,)).astype(np.float64) if gamma else np.ones(c)
+    sdzx = (sdzr - mu * sdz) * istd
+    if dgamma:
+        arr(dgamma, (c,))[...] = sdzx
+    if dbeta:
+        arr(dbeta, (c,))[...] = sdz
+    sc = g * istd
+    arr(ca, (c,))[...] = sc
+    if training:
+        k1, k2 = sdz / count, sdzx / count
+        arr(cb, (c,))[...] = -sc * k2 * istd
+        arr(cc, (c,))[...] = -sc * (k1 - mu * istd * k2)
+    else:
+        arr(cb, (c,))[...] = 0
+        arr(cc, (c,))[...] = 0
+
+
+def ehgr_row_apply(a, addend, out, m, c, dtype, stream):
+    assert dtype == 0
+    y = rowop(a, m, c)
+    if addend:
+        y = y + arr(addend, (m, c))
+    arr(out, (m, c))[...] = y
+
+
+# ---- N3: ResNet pieces (csrc/resnet.cu) ----------------------------------------------------------------------------------
+def _patches(xp, k, stride, ho, wo):
+    """xp [F, C, Hp, Wp] padded -> [F, C, k*k, ho, wo], tap = k*ky + kx."""
+    return np.stack([xp[:, :, ky:ky + stride * (ho - 1) + 1:stride, kx:kx + stride * (wo - 1) + 1:stride]
+                     for ky in range(k) for kx in range(k)], axis=2)
+
+
+def ehgr_stem7_fwd(x, w, out, stats, frames, h, w_in, cout, x_dtype, out_dtype, stream):
+    assert x_dtype == 0 and out_dtype == 0 and cout == 64
+    ho, wo = _half(h), _half(w_in)
+    xp = np.zeros((frames, 3, h + 6, w_in + 6), F32)
+    xp[:, :, 3:-3, 3:-3] = arr(x, (frames, 3, h, w_in))
+    P = _patches(xp, 7, 2, ho, wo)                                     # [F, 3, 49, ho, wo]
+    y = np.einsum("fcthw,oct->fhwo", P, arr(w, (cout, 3, 49)), optimize=True).astype(F32)
+    arr(out, (frames, ho, wo, cout))[...] = y
+    _add_stats(stats, y.reshape(-1, cout), cout)
+
+
+def ehgr_stem7_wgrad(dy, x, dw, frames, h, w_in, cout, x_dtype, dtype, stream):
+    assert x_dtype == 0 and dtype == 0 and cout == 64
+    ho, wo = _half(h), _half(w_in)
+    D = rowop(dy, frames * ho * wo, cout).reshape(frames, ho, wo, cout)
+    xp = np.zeros((frames, 3, h + 6, w_in + 6), F32)
+    xp[:, :, 3:-3, 3:-3] = arr(x, (frames, 3, h, w_in))
+    P = _patches(xp, 7, 2, ho, wo)
+    arr(dw, (cout, 3, 49))[...] += np.einsum("fhwo,fcthw->oct", D, P, optimize=True)
+
+
+def ehgr_maxpool3_fwd(a, y, idx, frames, h, w, c, dtype, stream):
+    assert dtype == 0
+    ho, wo = _half(h), _half(w)
+    X = rowop(a, frames * h * w, c).reshape(frames, h, w, c).transpose(0, 3, 1, 2)
+    xp = np.full((frames, c, h + 2, w + 2), -np.inf, F32)
+    xp[:, :, 1:-1, 1:-1] = X
+    P = _patches(xp, 3, 2, ho, wo)                                     # [F, C, 9, ho, wo]
+    arr(y, (frames, ho, wo, c))[...] = P.max(2).transpose(0, 2, 3, 1)
+    arr(idx, (frames, ho, wo, c), np.uint8)[...] = P.argmax(2).transpose(0, 2, 3, 1)   # first maximum in scan order
+
+
+def ehgr_maxpool3_bwd(g, idx, gx, frames, h, w, c, dtype, stream):
+    assert dtype == 0
+    ho, wo = _half(h), _half(w)
+    G, I = arr(g, (frames, ho, wo, c)), arr(idx, (frames, ho, wo, c), np.uint8)
+    out = np.zeros((frames, h + 2, w + 2, c), F32)
+    for tap in range(9):
+        ky, kx = divmod(tap, 3)
+        out[:, ky:ky + 2 * (ho - 1) + 1:2, kx:kx + 2 * (wo - 1) + 1:2] += G * (I == tap)
+    arr(gx, (frames, h, w, c))[...] = out[:, 1:-1, 1:-1]
+
+
+def ehgr_subsample2_fwd(x, y, stats, frames, h, w, c, dtype, stream):
+    assert dtype == 0
+    Y = arr(x, (frames, h, w, c))[:, ::2, ::2]
+    arr(y, Y.shape)[...] = Y
+    _add_stats(stats, Y.reshape(-1, c), c)
+
+
+def ehgr_subsample2_bwd(g, gx, frames, h, w, c, dtype, stream):
+    assert dtype == 0
+    out = arr(gx, (frames, h, w, c))
+    out[...] = 0
+    out[:, ::2, ::2] = arr(g, (frames, _half(h), _half(w), c))
+
+
+def ehgr_bn_add_relu(raw, scale, shift, addend, out, m, c, dtype, stream):
+    assert dtype == 0
+    arr(out, (m, c))[...] = np.maximum(arr(raw, (m, c)) * arr(scale, (c,)) + arr(shift, (c,)) + arr(addend, (m, c)), 0)
+
+
+def ehgr_relu_bwd(g, out, gz, n, dtype, stream):
+    assert dtype == 0
+    arr(gz, (n,))[...] = arr(g, (n,)) * (arr(out, (n,)) > 0)
+
+
+_TABLE = {k: v for k, v in globals().items() if k.startswith("ehgr_")}
+
+
+def call(name, *args, algo_bytes=0, algo_flops=0, tag=""):
+    """Drop-in for ehgr_b200._lib.call on host tensors."""
+    if name not in _TABLE:
+        raise NotImplementedError(f"the ABI emulator has no restatement of {name}")
+    _TABLE[name](*args)

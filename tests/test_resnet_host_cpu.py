@@ -1,0 +1,130 @@
+"""N3 host logic on CPU: the orchestration of resnet_ops._ResNetFunction (which C-ABI entry point is called with which
+operands, shapes and saved tensors; where every gradient lands) against PyTorch autograd over the same torchvision
+modules.  The kernels are replaced by the numpy restatement of their header contracts (tests/abi_emulator.py) — the CUDA
+kernels themselves are checked on the GPU (tests/test_resnet_gpu.py).  The reference path being mirrored:
+torchvision.models.resnet50 built by models/models.py:108-117 with TemporalShift on every Bottleneck.conv1
+(models/temporal_shift.py:101-146)."""
+import contextlib
+import io
+
+import pytest
+import torch
+import torch.nn as nn
+
+import abi_emulator
+from conftest import rel_err
+from oracle import ref_oracle as O
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    import ehgr_b200
+    monkeypatch.setattr(ehgr_b200._lib, "call", abi_emulator.call)
+    monkeypatch.setattr(ehgr_b200._lib, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(ehgr_b200._lib, "stream_ptr", lambda device=None: 0)
+    # the oracle's differentiable shift stands in for the shift kernel in the eager (reference-side) run
+    monkeypatch.setattr(ehgr_b200.TemporalShift, "shift",
+                        staticmethod(lambda x, n_segment, fold_div=3, inplace=False: O.temporal_shift(x, n_segment, fold_div)))
+    return ehgr_b200
+
+
+def _net(E, layers, shift, n_segment, seed=0):
+    from torchvision.models.resnet import Bottleneck, ResNet
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = ResNet(Bottleneck, layers)
+        if shift:
+            E.make_temporal_shift(net, n_segment, n_div=8, place='blockres')
+    g = torch.Generator().manual_seed(seed + 1)
+    for m in net.modules():                               # non-trivial BatchNorm parameters and running statistics
+        if isinstance(m, nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.num_features, generator=g) + 0.5
+            m.bias.data = torch.randn(m.num_features, generator=g) * 0.2
+            m.running_mean.data = torch.randn(m.num_features, generator=g) * 0.1
+            m.running_var.data = torch.rand(m.num_features, generator=g) + 0.5
+    return net
+
+
+def _eager(net, x):
+    y = net.maxpool(net.relu(net.bn1(net.conv1(x))))
+    t1 = net.layer1(y)
+    t2 = net.layer2(t1)
+    t3 = net.layer3(t2)
+    return t1, t2, t3, net.layer4(t3)
+
+
+@pytest.mark.parametrize("shift,train_bn", [(True, True), (False, True), (True, False)])
+def test_resnet_function_matches_autograd(emulated, shift, train_bn):
+    E = emulated
+    R = E.resnet_ops
+    T, size = 2, 48
+    net = _net(E, [2, 1, 1, 1], shift, T)
+    net.train(train_bn)
+    ok, why = R.supported(net)
+    assert ok, why
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2 * T, 3, size, size, generator=g)
+    gouts = None
+
+    # ---- reference: PyTorch autograd over the same modules, float64
+    ref = _net(E, [2, 1, 1, 1], shift, T).double()
+    ref.train(train_bn)
+    outs_ref = _eager(ref, x.double())
+    gouts = [torch.randn(o.shape, generator=g, dtype=torch.float64) / o.numel() ** 0.5 for o in outs_ref]
+    torch.autograd.backward(outs_ref, gouts)
+
+    # ---- ours: one autograd Function over the emulated C ABI, float32
+    with E.fused.compute_dtype(torch.float32):
+        outs = R.resnet_features(net, x, taps=(1, 2, 3))
+    assert len(outs) == 4
+    for o, r in zip(outs, outs_ref):
+        assert o.shape == r.shape
+        assert rel_err(o, r) < 2e-4
+    torch.autograd.backward(outs, [q.float() for q in gouts])
+    # a ReLU whose pre-activation is at rounding level (|z| ~ 1e-7) may take the other branch in fp32 than in the fp64 run
+    # and moves one channel's gradient by a few per cent of the maximum: the bound is norm-wise (2-norm) and the max-norm
+    # only has to stay far below the O(1) error of a wrong operand / shape / saved tensor
+    for (name, p), (_, pr) in zip(net.named_parameters(), ref.named_parameters()):
+        if name.startswith("fc."):
+            continue
+        assert p.grad is not None, name
+        e2 = ((p.grad.double() - pr.grad).norm() / pr.grad.norm().clamp_min(1e-30)).item()
+        assert e2 < 3e-2 and rel_err(p.grad, pr.grad) < 8e-2, (name, e2, rel_err(p.grad, pr.grad))
+    # BatchNorm buffers follow nn.BatchNorm2d
+    for (name, b), (_, br) in zip(net.named_buffers(), ref.named_buffers()):
+        if b.dtype.is_floating_point:
+            assert rel_err(b, br) < 1e-4, name
+        else:
+            assert int(b) == int(br), name
+
+
+def test_single_output_and_tap_selection(emulated):
+    E = emulated
+    R = E.resnet_ops
+    net = _net(E, [1, 1, 1, 1], True, 2)
+    x = torch.randn(2, 3, 32, 32)
+    with E.fused.compute_dtype(torch.float32):
+        f = R.resnet_features(net, x)
+        assert isinstance(f, torch.Tensor) and f.shape == (2, 2048, 1, 1)
+        t2, f2 = R.resnet_features(net, x, taps=(2,))
+    assert t2.shape == (2, 512, 4, 4) and f2.shape == (2, 2048, 1, 1)
+    # only the final map gets a gradient: the tapped stage still back-propagates through the trunk
+    f2.float().sum().backward()
+    assert net.conv1.weight.grad is not None and net.conv1.weight.grad.abs().sum() > 0
+    with pytest.raises(ValueError):
+        R.resnet_features(net, x, taps=(4,))
+
+
+def test_unsupported_trees_are_named(emulated):
+    import torchvision
+    E = emulated
+    R = E.resnet_ops
+    ok, why = R.supported(torchvision.models.resnet18())
+    assert not ok and "BasicBlock" in why
+    ok, why = R.supported(torchvision.models.resnext50_32x4d())
+    assert not ok and "grouped" in why
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = torchvision.models.resnet50()
+        E.action.make_temporal_shift(net, 4, n_div=8)
+    ok, why = R.supported(net)
+    assert not ok and "Action" in why
