@@ -593,3 +593,86 @@ def temporal_pool_np(x: np.ndarray, n_segment: int) -> np.ndarray:
         lo, hi = max(2 * t - 1, 0), min(2 * t + 1, n_segment - 1)
         out[:, t] = v[:, lo:hi + 1].max(axis=1)
     return out.reshape(-1, c, h, w)
+
+
+# --------------------------------------------------------------------------------------------
+# N3 — ResNet-50 bottleneck backbone.  The reference has no ResNet source of its own: models/models.py:108-117 builds
+# `torchvision.models.resnet50` (third-party dependency, not vendored; torchvision 0.26.0 in this image, the v1.5
+# Bottleneck with the stride on the 3x3 convolution: torchvision/models/resnet.py Bottleneck.forward / ResNet._forward_impl)
+# and models/temporal_shift.py:101-146 (place='blockres') wraps `conv1` of every bottleneck with TemporalShift, which
+# renames that weight to `...conv1.net.weight`.  Restated below over a state_dict with those key names; pinned against
+# the live torchvision module + the reference's make_temporal_shift by tests/golden/make_golden.py -> resnet.npz.
+# --------------------------------------------------------------------------------------------
+RESNET50_LAYERS = (3, 4, 6, 3)
+
+
+def resnet_bottleneck(x, sd: SD, prefix: str, stride: int, temporal: str, n_segment: int, shift_div: int, bn_training: bool):
+    """torchvision Bottleneck.forward: relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(x)))))))) + identity); conv1's input goes
+    through the temporal shift when `temporal == 'tsm'` (TemporalShift.forward, models/temporal_shift.py:22-25)."""
+    if temporal == "tsm":
+        out = F.conv2d(temporal_shift(x, n_segment, shift_div), sd[prefix + ".conv1.net.weight"])
+    else:
+        out = F.conv2d(x, sd[prefix + ".conv1.weight"])
+    out = F.relu(_bn(out, sd, prefix + ".bn1", bn_training))
+    out = F.relu(_bn(F.conv2d(out, sd[prefix + ".conv2.weight"], stride=stride, padding=1), sd, prefix + ".bn2", bn_training))
+    out = _bn(F.conv2d(out, sd[prefix + ".conv3.weight"]), sd, prefix + ".bn3", bn_training)
+    identity = x
+    if prefix + ".downsample.0.weight" in sd:
+        identity = _bn(F.conv2d(x, sd[prefix + ".downsample.0.weight"], stride=stride), sd, prefix + ".downsample.1", bn_training)
+    return F.relu(out + identity)
+
+
+def resnet_features(x, sd: SD, layers=RESNET50_LAYERS, temporal: str = "tsm", n_segment: int = 8, shift_div: int = 8,
+                    bn_training: bool = True, prefix: str = "base_model"):
+    """ResNet._forward_impl up to layer4: conv1 7x7/2 -> bn1 -> relu -> maxpool 3x3/2 -> layer1..4.  Returns the four stage
+    outputs (the taps of models/models_SD.py:364-431; layer4 is the map models/models_MTMM.py:70-77 decodes)."""
+    y = F.relu(_bn(F.conv2d(x, sd[prefix + ".conv1.weight"], stride=2, padding=3), sd, prefix + ".bn1", bn_training))
+    y = F.max_pool2d(y, kernel_size=3, stride=2, padding=1)
+    outs = []
+    for si, n_blocks in enumerate(layers, 1):
+        for bi in range(n_blocks):
+            stride = 2 if (bi == 0 and si > 1) else 1
+            y = resnet_bottleneck(y, sd, f"{prefix}.layer{si}.{bi}", stride, temporal, n_segment, shift_div, bn_training)
+        outs.append(y)
+    return tuple(outs)
+
+
+def resnet_tsn_forward(x5, sd: SD, num_segments: int, layers=RESNET50_LAYERS, temporal: str = "tsm", shift_div: int = 8,
+                       bn_training: bool = True):
+    """models/models.py:323-356 with a ResNet base: fold T into the batch, backbone, AdaptiveAvgPool2d(1) + flatten, Dropout
+    as identity, new_fc, mean over the segments."""
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    f = resnet_features(x, sd, layers, temporal, num_segments, shift_div, bn_training)[-1]
+    z = F.linear(f.mean((2, 3)), sd["new_fc.weight"], sd["new_fc.bias"])
+    return z.view((-1, num_segments) + tuple(z.shape[1:])).mean(dim=1)
+
+
+def build_resnet_state(layers=RESNET50_LAYERS, num_class: int = 83, temporal: str = "tsm", seed: int = 0) -> SD:
+    """state_dict of TSN(base_model='resnet50', dropout>0) with torchvision's key names (conv1 of every bottleneck under
+    `.net` when a temporal module wraps it), loadable with strict=True.  Values from numpy RandomState(seed); the last
+    BatchNorm of a block gets a small scale (as zero_init_residual would, but not zero) so that deep stacks stay O(1)."""
+    rs = np.random.RandomState(seed)
+    sd: SD = {}
+    b = "base_model"
+    _conv_entry(sd, f"{b}.conv1.weight", (64, 3, 7, 7), rs)
+    _bn_entries(sd, f"{b}.bn1", 64, rs)
+    inplanes = 64
+    for si, n_blocks in enumerate(layers, 1):
+        planes = 64 << (si - 1)
+        for bi in range(n_blocks):
+            p = f"{b}.layer{si}.{bi}"
+            stride = 2 if (bi == 0 and si > 1) else 1
+            _conv_entry(sd, p + (".conv1.net.weight" if temporal == "tsm" else ".conv1.weight"), (planes, inplanes, 1, 1), rs)
+            _bn_entries(sd, p + ".bn1", planes, rs)
+            _conv_entry(sd, p + ".conv2.weight", (planes, planes, 3, 3), rs)
+            _bn_entries(sd, p + ".bn2", planes, rs)
+            _conv_entry(sd, p + ".conv3.weight", (4 * planes, planes, 1, 1), rs)
+            _bn_entries(sd, p + ".bn3", 4 * planes, rs)
+            sd[p + ".bn3.weight"] *= 0.5
+            if stride != 1 or inplanes != 4 * planes:
+                _conv_entry(sd, p + ".downsample.0.weight", (4 * planes, inplanes, 1, 1), rs)
+                _bn_entries(sd, p + ".downsample.1", 4 * planes, rs)
+            inplanes = 4 * planes
+    sd["new_fc.weight"] = torch.from_numpy((rs.standard_normal((num_class, inplanes)) * 0.02).astype(np.float32))
+    sd["new_fc.bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
+    return sd

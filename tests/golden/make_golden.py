@@ -376,6 +376,89 @@ def golden_heads():
     np.savez_compressed(HERE / "heads.npz", **out)
 
 
+RESNET_FIXTURE = dict(clips=2, T=4, size=64, num_class=10, seed=11, in_seed=12)
+
+
+def golden_resnet():
+    """N3: ResNet-50.  The reference has no ResNet source: models/models.py:108-117 instantiates torchvision.models.resnet50 and
+    models/temporal_shift.py:101-146 wraps conv1 of every bottleneck.  Pinned here: (a) live torchvision resnet50 + the
+    REFERENCE's make_temporal_shift (the TSM variant of config #5) — the four stage outputs and every gradient, fp64;
+    (b) the live reference TSN(base_model='resnet50', is_shift=False) — logits and gradients, fp64."""
+    import torchvision
+    from models.models import TSN
+    from models.temporal_shift import make_temporal_shift
+    cfg = RESNET_FIXTURE
+    rgb, _, labels = O.synthetic_clip_batch(cfg["clips"], cfg["T"], cfg["size"], cfg["num_class"], seed=cfg["in_seed"])
+    x = rgb.view((-1, 3) + tuple(rgb.shape[-2:])).double()
+    out = {}
+    rs = np.random.RandomState(5)
+    # (a) TSM backbone
+    for bn_train in (True, False):
+        tag = "tsm_" + ("train" if bn_train else "eval")
+        sd = O.build_resnet_state(O.RESNET50_LAYERS, cfg["num_class"], "tsm", seed=cfg["seed"])
+        with _quiet():
+            net = torchvision.models.resnet50()
+            make_temporal_shift(net, cfg["T"], n_div=8, place='blockres')
+        bsd = {k[len("base_model."):]: v for k, v in sd.items() if k.startswith("base_model.")}
+        missing = net.load_state_dict(bsd, strict=False)
+        assert not missing.unexpected_keys and set(missing.missing_keys) == {"fc.weight", "fc.bias"}, missing
+        net = net.double()
+        net.train(bn_train)
+        y = net.maxpool(net.relu(net.bn1(net.conv1(x))))
+        t1 = net.layer1(y); t2 = net.layer2(t1); t3 = net.layer3(t2); t4 = net.layer4(t3)
+        live = (t1, t2, t3, t4)
+        if bn_train:
+            out["gout_seed"] = np.array(5)
+        gouts = [torch.from_numpy(np.random.RandomState(100 + i).standard_normal(tuple(t.shape))) / t.numel() ** 0.5
+                 for i, t in enumerate(live)]
+        torch.autograd.backward(live, gouts)
+        osd = O.clone_state(sd, dtype=torch.float64)
+        mine = O.resnet_features(x, osd, O.RESNET50_LAYERS, "tsm", cfg["T"], 8, bn_train)
+        torch.autograd.backward(mine, gouts)
+        for i, (a, b) in enumerate(zip(mine, live)):
+            assert (a - b).abs().max().item() <= 1e-9 * b.abs().max().item(), (tag, i)
+            out[f"{tag}_tap{i + 1}_chansum"] = b.detach().sum((0, 2, 3)).numpy()
+            out[f"{tag}_tap{i + 1}_abs"] = np.array(b.detach().abs().sum().item())
+        out[tag + "_layer4"] = live[3].detach().numpy()
+        named = {"base_model." + k: p for k, p in net.named_parameters() if not k.startswith("fc.")}
+        gmax = max(p.grad.abs().max().item() for p in named.values())
+        for k, p in named.items():
+            assert (osd[k].grad - p.grad).abs().max().item() <= 1e-9 * gmax, (tag, k)
+        for k, v in grad_digest({k: p.grad for k, p in named.items()}).items():
+            out[f"{tag}_g_{k}"] = v
+        out[f"{tag}_gfull_base_model.conv1.weight"] = named["base_model.conv1.weight"].grad.numpy().copy()
+        rsd = net.state_dict()
+        for k in ("bn1.running_mean", "layer2.0.downsample.1.running_var", "layer4.2.bn3.running_var"):
+            assert (osd["base_model." + k] - rsd[k]).abs().max().item() <= 1e-12 * rsd[k].abs().max().item()
+            out[f"{tag}_rs_base_model.{k}"] = rsd[k].numpy()
+    # (b) the reference's own TSN wrapper on resnet50, no temporal module
+    sd = O.build_resnet_state(O.RESNET50_LAYERS, cfg["num_class"], "none", seed=cfg["seed"])
+    with _quiet():
+        ref = TSN(cfg["num_class"], cfg["T"], 'RGB', base_model='resnet50', pretrain=None, dropout=0.5, partial_bn=False,
+                  is_shift=False, consensus_type='avg', fc_lr5=True, img_feature_dim=224)
+    ref.load_state_dict(sd, strict=True)
+    ref = ref.double()
+    ref.train()                                   # the reference's TSN.train() returns None
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.eval()
+    logits = ref(rgb.double())
+    loss = F.cross_entropy(logits, labels)
+    loss.backward()
+    osd = O.clone_state(sd, dtype=torch.float64)
+    ologits = O.resnet_tsn_forward(rgb.double(), osd, cfg["T"], O.RESNET50_LAYERS, "none", 8, True)
+    assert (ologits - logits).abs().max().item() <= 1e-10 * logits.abs().max().item()
+    F.cross_entropy(ologits, labels).backward()
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters())
+    for k, p in ref.named_parameters():
+        assert (osd[k].grad - p.grad).abs().max().item() <= 1e-9 * gmax, k
+    out["tsn_none_logits"] = logits.detach().numpy()
+    out["tsn_none_loss"] = np.array(loss.item())
+    for k, v in grad_digest({k: p.grad for k, p in ref.named_parameters()}).items():
+        out[f"tsn_none_g_{k}"] = v
+    np.savez_compressed(HERE / "resnet.npz", **out)
+
+
 def golden_ema_and_pool():
     """Separate small file: EMAWrapper replay (initial state stored explicitly) and TemporalPool."""
     from models.temporal_shift import TemporalPool
@@ -418,7 +501,8 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     only = set(sys.argv[1:])
     for name, fn in (("shift", golden_shift), ("action", golden_action), ("losses", golden_losses), ("tsn", golden_tsn),
-                     ("heads", golden_heads), ("ema_pool", golden_ema_and_pool)):
+                     ("heads", golden_heads), ("ema_pool", golden_ema_and_pool),
+                     ("resnet", golden_resnet)):
         if not only or name in only:
             fn()
     for p in sorted(HERE.glob("*.npz")):

@@ -235,3 +235,50 @@ def test_temporal_pool_oracle_matches_reference_bit_exact(name):
     z = np.load(GOLDEN / "ema_pool.npz")
     nt, c, h, T = (int(v) for v in z[name + "_meta"])
     assert np.array_equal(O.temporal_pool_np(z[name + "_x"], T), z[name + "_y"])
+
+
+RESNET_FIXTURE = dict(clips=2, T=4, size=64, num_class=10, seed=11, in_seed=12)     # tests/golden/make_golden.py
+
+
+def resnet_fixture_gouts(shapes):
+    """The output gradients make_golden.golden_resnet used for the four stage outputs."""
+    return [torch.from_numpy(np.random.RandomState(100 + i).standard_normal(tuple(s))) / float(np.prod(s)) ** 0.5
+            for i, s in enumerate(shapes)]
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_resnet50_tsm_oracle_matches_live_torchvision_plus_reference_shift(mode):
+    """N3: the reference instantiates torchvision.models.resnet50 (models/models.py:108-117) and wraps conv1 of every
+    bottleneck (models/temporal_shift.py:101-146).  Fixture = that live pair in fp64; the oracle restatement must agree."""
+    z = np.load(GOLDEN / "resnet.npz")
+    cfg = RESNET_FIXTURE
+    tag = "tsm_" + mode
+    rgb, _, _ = O.synthetic_clip_batch(cfg["clips"], cfg["T"], cfg["size"], cfg["num_class"], seed=cfg["in_seed"])
+    x = rgb.view((-1, 3) + tuple(rgb.shape[-2:])).double()
+    sd = O.clone_state(O.build_resnet_state(O.RESNET50_LAYERS, cfg["num_class"], "tsm", seed=cfg["seed"]), dtype=torch.float64)
+    taps = O.resnet_features(x, sd, O.RESNET50_LAYERS, "tsm", cfg["T"], 8, mode == "train")
+    assert [tuple(t.shape[1:]) for t in taps] == [(256, 16, 16), (512, 8, 8), (1024, 4, 4), (2048, 2, 2)]
+    for i, t in enumerate(taps):
+        assert rel_err(t.sum((0, 2, 3)), torch.from_numpy(z[f"{tag}_tap{i + 1}_chansum"])) < 1e-9
+        assert abs(t.abs().sum().item() - float(z[f"{tag}_tap{i + 1}_abs"])) < 1e-9 * float(z[f"{tag}_tap{i + 1}_abs"])
+    assert rel_err(taps[3], torch.from_numpy(z[tag + "_layer4"])) < 1e-9
+    torch.autograd.backward(taps, resnet_fixture_gouts([t.shape for t in taps]))
+    assert _digest_err(sd, z, tag + "_g_") < 1e-9
+    assert rel_err(sd["base_model.conv1.weight"].grad, torch.from_numpy(z[tag + "_gfull_base_model.conv1.weight"])) < 1e-9
+    for k in z.files:
+        if k.startswith(tag + "_rs_"):
+            assert rel_err(sd[k[len(tag + "_rs_"):]], torch.from_numpy(z[k])) < 1e-12
+
+
+def test_resnet50_tsn_oracle_matches_reference_wrapper():
+    """The live reference TSN(base_model='resnet50', is_shift=False): logits, loss, gradient digests (fp64)."""
+    z = np.load(GOLDEN / "resnet.npz")
+    cfg = RESNET_FIXTURE
+    rgb, _, labels = O.synthetic_clip_batch(cfg["clips"], cfg["T"], cfg["size"], cfg["num_class"], seed=cfg["in_seed"])
+    sd = O.clone_state(O.build_resnet_state(O.RESNET50_LAYERS, cfg["num_class"], "none", seed=cfg["seed"]), dtype=torch.float64)
+    logits = O.resnet_tsn_forward(rgb.double(), sd, cfg["T"], O.RESNET50_LAYERS, "none", 8, True)
+    assert rel_err(logits, torch.from_numpy(z["tsn_none_logits"])) < 1e-10
+    loss = F.cross_entropy(logits, labels)
+    assert abs(loss.item() - float(z["tsn_none_loss"])) < 1e-10
+    loss.backward()
+    assert _digest_err(sd, z, "tsn_none_g_") < 1e-9
