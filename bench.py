@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--e2e-input", choices=["uint8", "float32"], default="uint8",
                     help="host batch format of the end-to-end leg: uint8 frames normalised on the device, or fp32")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph per step")
+    ap.add_argument("--backbone", default="mobilenetv2", choices=["mobilenetv2", "resnet50"],
+                    help="resnet50 (+ --temporal tsm|none, --segments 16): BASELINE configs[4], the N3 row — not the headline")
+    ap.add_argument("--segments", type=int, default=T_SEG, help="frames per clip (8 for the headline configs, 16 for configs[4])")
     return ap.parse_args()
 
 
@@ -205,7 +208,11 @@ def run_ours(args):
     torch.manual_seed(1)  # train_mtmm.py:43 default seed; identical initial weights on every rank
     sd_mode = args.workload == "sd"
     NUM_CLASS = args.classes
-    common = dict(is_shift=(args.temporal != "none"), partial_bn=False, base_model='mobilenetv2', shift_div=8, dropout=0.5,
+    T_SEG = args.segments
+    resnet = args.backbone == "resnet50"
+    if resnet and (args.temporal == "action" or args.workload == "mtmm_sd"):
+        raise SystemExit("--backbone resnet50 runs --temporal tsm|none with --workload mtmm|sd (ACTION covers widths <= 256 channels)")
+    common = dict(is_shift=(args.temporal != "none"), partial_bn=False, base_model=args.backbone, shift_div=8, dropout=0.5,
                   img_feature_dim=224, pretrain=None, consensus_type='avg', fc_lr5=True,
                   temporal_module=("tsm" if args.temporal == "tsm" else "action"))
     with quiet():
@@ -326,10 +333,12 @@ def run_ours(args):
         value = clips / (ms / 1e3)
         e2e = clips / (ms_e2e / 1e3)
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": (METRIC if not resnet else f"train clips/sec TSM-ResNet50 {T_SEG}x224^2"), "value": round(value, 2),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD_NAMES[args.workload]}, {args.temporal.upper()}-MobileNetV2, 8x224^2, "
+            "config": {"workload": f"{WORKLOAD_NAMES[args.workload]}, {args.temporal.upper()}-"
+                                   f"{'ResNet50' if resnet else 'MobileNetV2'}, {T_SEG}x224^2, "
                                    f"{NUM_CLASS} classes, train-mode BN",
                        "clips_per_gpu": B, "global_clips": B * world, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if step.use_graph else "eager",
@@ -339,9 +348,10 @@ def run_ours(args):
                                    else "normalised fp32 tensors")},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG, ncu_traffic()),
-            "roofline_traffic_source": "static: DRAM bytes per launch from the committed ncu capture profiles/r2_traffic.json "
-                                       "(same command, 1 GPU); not measured inside this run",
+            "roofline": _lib.roofline_entry(kernel_times, pk, pk_kind, B * T_SEG, ncu_traffic() if not resnet else None),
+            "roofline_traffic_source": ("static: DRAM bytes per launch from the committed ncu capture profiles/r2_traffic.json "
+                                        "(same command, 1 GPU); not measured inside this run" if not resnet else
+                                        "none: no ncu capture of the ResNet-50 shapes exists"),
             "peaks": pk_kind,
             "final_loss": round(loss_value, 5),
             "host_enqueue_ms_per_step": round(host_ms.get("resident", 0.0), 3),
@@ -349,7 +359,7 @@ def run_ours(args):
         }
         if world > 1:
             line["ranks_in_sync"] = bool(in_sync)
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not resnet:
             v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1, args.workload, NUM_CLASS)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"3 steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32 oracle "
