@@ -172,6 +172,9 @@ SIGNATURES = {
     # N3: torchvision ResNet bottleneck path (csrc/resnet.cu)
     "ehgr_stem7_fwd": [_P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
     "ehgr_stem7_wgrad": [_R, _P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "ehgr_stem7_im2col": [_P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "ehgr_stem7_pack": [_P, _P, _I, _I, _I, _P],
+    "ehgr_stem7_unpack_grad": [_P, _P, _I, _I, _P],
     "ehgr_maxpool3_fwd": [_R, _P, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_maxpool3_bwd": [_P, _P, _P, _L, _I, _I, _I, _I, _P],
     "ehgr_subsample2_fwd": [_P, _P, _P, _L, _I, _I, _I, _I, _P],

@@ -150,6 +150,59 @@ stem7_wgrad_kernel(RowOp dy, const TX* __restrict__ x, float* __restrict__ dw, l
   }
 }
 
+// im2col of the 7x7/2 stem for the tensor-core GEMM: a[pix][t] = x[f, ci, 2oh-3+ky, 2ow-3+kx] with t = (ci*7 + ky)*7 + kx,
+// zero outside the image and for the pad columns t >= 147.  thread = 8 consecutive columns of one output pixel.
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256)
+stem7_im2col_kernel(const TX* __restrict__ x, T* __restrict__ a, long long frames, int H, int W, int Ho, int Wo, int KP) {
+  const int kvn = KP / 8;
+  const long long total = frames * Ho * Wo * kvn;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+    const int kv = static_cast<int>(i % kvn);
+    long long pix = i / kvn;
+    const int ow = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int oh = static_cast<int>(pix % Ho);
+    const long long f = pix / Ho;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = kv * 8 + k;
+      float xv = 0.f;
+      if (t < kStem7Taps) {
+        const int ci = t / 49, rem = t - ci * 49, ky = rem / 7, kx = rem - ky * 7;
+        const int ih = 2 * oh - 3 + ky, iw = 2 * ow - 3 + kx;
+        if (static_cast<unsigned>(ih) < static_cast<unsigned>(H) && static_cast<unsigned>(iw) < static_cast<unsigned>(W))
+          xv = ld_in<TX>(x + ((f * 3 + ci) * static_cast<long long>(H) + ih) * W + iw);
+      }
+      v[k] = xv;
+    }
+    store_vec<T, 8>(a + i * 8, v);
+  }
+}
+
+// wp[co][t] = w[co][t] for t < 147, 0 for the pad columns (fp32 or bf16)
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem7_pack_kernel(const float* __restrict__ w, T* __restrict__ wp, int cout, int KP) {
+  const int total = cout * KP;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += 256 * gridDim.x) {
+    const int co = i / KP, t = i - co * KP;
+    const float v = t < kStem7Taps ? w[co * kStem7Taps + t] : 0.f;
+    if constexpr (sizeof(T) == 4) wp[i] = v; else wp[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dw[co][t] += dwp[co][t], t < 147
+__global__ void __launch_bounds__(256)
+stem7_unpack_grad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int cout, int KP) {
+  const int total = cout * kStem7Taps;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += 256 * gridDim.x) {
+    const int co = i / kStem7Taps, t = i - co * kStem7Taps;
+    dw[i] += dwp[co * KP + t];
+  }
+}
+
 // y[f,oh,ow,c] = max over the 3x3 window (stride 2, padding 1; padding never wins) of rowop(a); idx = winning tap 3*ky+kx
 // (the first maximum in scan order, as at::max_pool2d).  thread = one 16-byte channel vector of one output pixel.
 template <typename T>
@@ -377,6 +430,40 @@ extern "C" int ehgr_stem7_wgrad(const ehgr_rowop* dy, const void* x, float* dw, 
   if (x_dtype == EHGR_F32) { if (dtype == EHGR_F32) EHGR_S7W(float, float); else EHGR_S7W(float, __nv_bfloat16); }
   else { if (dtype == EHGR_F32) EHGR_S7W(__nv_bfloat16, float); else EHGR_S7W(__nv_bfloat16, __nv_bfloat16); }
 #undef EHGR_S7W
+  return launch_status();
+}
+
+extern "C" int ehgr_stem7_im2col(const void* x, void* a, long long frames, int h, int w_in, int kp, int x_dtype, int dtype,
+                                 ehgr_stream_t stream) {
+  if (esize_of(x_dtype) == 0 || esize_of(dtype) == 0) return EHGR_E_DTYPE;
+  if (!x || !a) return EHGR_E_NULL;
+  if (frames < 0 || h <= 0 || w_in <= 0 || kp < kStem7Taps || (kp % 8)) return EHGR_E_SHAPE;
+  if (!aligned_to(a, 16) || !aligned_to(x, esize_of(x_dtype))) return EHGR_E_ALIGN;
+  if (frames == 0) return EHGR_OK;
+  const int ho = half_up(h), wo = half_up(w_in);
+  const unsigned grid = stream_grid(frames * ho * wo * (kp / 8));
+  cudaStream_t s = as_stream(stream);
+#define EHGR_S7I(TX, T) stem7_im2col_kernel<TX, T><<<grid, 256, 0, s>>>(static_cast<const TX*>(x), static_cast<T*>(a), frames, h, w_in, ho, wo, kp)
+  if (x_dtype == EHGR_F32) { if (dtype == EHGR_F32) EHGR_S7I(float, float); else EHGR_S7I(float, __nv_bfloat16); }
+  else { if (dtype == EHGR_F32) EHGR_S7I(__nv_bfloat16, float); else EHGR_S7I(__nv_bfloat16, __nv_bfloat16); }
+#undef EHGR_S7I
+  return launch_status();
+}
+
+extern "C" int ehgr_stem7_pack(const float* w, void* wp, int cout, int kp, int dtype, ehgr_stream_t stream) {
+  if (esize_of(dtype) == 0) return EHGR_E_DTYPE;
+  if (!w || !wp) return EHGR_E_NULL;
+  if (cout <= 0 || kp < kStem7Taps || (kp % 8)) return EHGR_E_SHAPE;
+  const unsigned grid = stream_grid(static_cast<long long>(cout) * kp);
+  if (dtype == EHGR_F32) stem7_pack_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(w, static_cast<float*>(wp), cout, kp);
+  else stem7_pack_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16*>(wp), cout, kp);
+  return launch_status();
+}
+
+extern "C" int ehgr_stem7_unpack_grad(const float* dwp, float* dw, int cout, int kp, ehgr_stream_t stream) {
+  if (!dwp || !dw) return EHGR_E_NULL;
+  if (cout <= 0 || kp < kStem7Taps || (kp % 8)) return EHGR_E_SHAPE;
+  stem7_unpack_grad_kernel<<<stream_grid(static_cast<long long>(cout) * kStem7Taps), 256, 0, as_stream(stream)>>>(dwp, dw, cout, kp);
   return launch_status();
 }
 

@@ -5,7 +5,7 @@ The reference builds ``torchvision.models.resnet50`` for ``base_model='resnet50'
 The torchvision module tree stays the parameter container (names = checkpoint contract); one
 ``torch.autograd.Function`` runs stem -> max-pool -> layer1..4, forward and backward, through the C ABI:
 
-  * ``conv1`` 7x7/2 + bn1 statistics            ehgr_stem7_fwd            (csrc/resnet.cu)
+  * ``conv1`` 7x7/2 + bn1 statistics            bf16: ehgr_stem7_im2col + ehgr_pw_gemm_bn (tcgen05); fp32: ehgr_stem7_fwd
   * ReLU + MaxPool2d(3, 2, 1)                   ehgr_maxpool3_fwd/bwd     (lazy BatchNorm+ReLU applied on load)
   * Bottleneck.conv1 (1x1, TemporalShift)       ehgr_pw_gemm_bn, SHIFT / PLAIN row operand (tcgen05 for bf16)
   * Bottleneck.conv2 (3x3)                      ehgr_pw_gemm_bn, CONV3 row operand (implicit GEMM, im2col by TMA boxes);
@@ -31,6 +31,17 @@ import torch.nn as nn
 
 from . import _lib, fused
 from .fused import (_bf16_mirror, _nhwc_empty, _pack_conv3, op_affine, op_bnbwd, op_conv3, op_plain, op_shift)
+
+
+# The 7x7 stem as a tensor-core GEMM over a materialised patch matrix (ehgr_stem7_im2col, K = 147 padded to 160) instead of
+# the exact-fp32 CUDA-core kernel.  None = by storage dtype (bf16 -> GEMM, fp32 -> CUDA cores: the parity mode).  Measured
+# on B200 at 1024 frames of 224^2: the CUDA-core pair cost 28 + 25 ms of a 168 ms step (profiles/README.md, round 2 N3).
+STEM_GEMM = None
+STEM_KP = 160
+
+
+def _stem_as_gemm(dt) -> bool:
+    return (dt == torch.bfloat16 and fused._STATE["engine"] != 1) if STEM_GEMM is None else bool(STEM_GEMM)
 
 
 @dataclass
@@ -196,10 +207,27 @@ class _ResNetFunction(torch.autograd.Function):
         w0, g0, b0 = params[0:3]
         ho, wo = _half(H), _half(W)
         raw0 = _nhwc_empty(nt, ho, wo, 64, dt, dev)
-        vec0, tr0 = bn_forward(lambda st: _lib.call(
-            "ehgr_stem7_fwd", x_in.data_ptr(), w0.data_ptr(), raw0.data_ptr(), st, nt, H, W, 64, _lib.dtype_code(x_in), code, sp,
-            algo_bytes=x_in.numel() * x_in.element_size() + raw0.numel() * es, algo_flops=2 * 147 * raw0.numel()),
-            plan.bn1, g0, b0, nt * ho * wo)
+        if _stem_as_gemm(dt):
+            # patch matrix [M, 160] (147 taps + zero pad) -> one plain GEMM on the tensor cores; the matrix is rebuilt in
+            # backward instead of being kept (M * 320 bytes)
+            m0 = nt * ho * wo
+            patches = torch.empty((m0, STEM_KP), dtype=dt, device=dev)
+            _lib.call("ehgr_stem7_im2col", x_in.data_ptr(), patches.data_ptr(), nt, H, W, STEM_KP, _lib.dtype_code(x_in), code, sp,
+                      algo_bytes=x_in.numel() * x_in.element_size() + patches.numel() * es)
+            wp32 = torch.empty((64, STEM_KP), dtype=torch.float32, device=dev)
+            _lib.call("ehgr_stem7_pack", w0.data_ptr(), wp32.data_ptr(), 64, STEM_KP, _lib.F32, sp)
+            wp16 = None
+            if dt == torch.bfloat16 and eng != 1:
+                wp16 = torch.empty((64, STEM_KP), dtype=torch.bfloat16, device=dev)
+                _lib.call("ehgr_stem7_pack", w0.data_ptr(), wp16.data_ptr(), 64, STEM_KP, _lib.BF16, sp)
+            vec0, tr0 = bn_forward(lambda st: gemm(op_plain(patches), wp32, wp16, raw0, st, m0, STEM_KP, 64, "[stem7x7]",
+                                                   m0 * STEM_KP), plan.bn1, g0, b0, m0)
+            del patches
+        else:
+            vec0, tr0 = bn_forward(lambda st: _lib.call(
+                "ehgr_stem7_fwd", x_in.data_ptr(), w0.data_ptr(), raw0.data_ptr(), st, nt, H, W, 64, _lib.dtype_code(x_in), code, sp,
+                algo_bytes=x_in.numel() * x_in.element_size() + raw0.numel() * es, algo_flops=2 * 147 * raw0.numel()),
+                plan.bn1, g0, b0, nt * ho * wo)
         h, w = _half(ho), _half(wo)
         cur = _nhwc_empty(nt, h, w, 64, dt, dev)
         pool_idx = torch.empty((nt, h, w, 64), dtype=torch.uint8, device=dev)
@@ -431,9 +459,21 @@ class _ResNetFunction(torch.autograd.Function):
         g_act = torch.empty_like(raw0)
         _lib.call("ehgr_maxpool3_bwd", g.data_ptr(), pool_idx.data_ptr(), g_act.data_ptr(), nt, ho, wo, 64, code, sp,
                   algo_bytes=g.numel() * (es + 1) + g_act.numel() * es)
-        dy_op = bn_backward(g_act, raw0, vec0, tr0, 2, params[1], gviews[1], gviews[2], nt * ho * wo, materialise=False)
-        _lib.call("ehgr_stem7_wgrad", ctypes.byref(dy_op), x_in.data_ptr(), gviews[0].data_ptr(), nt, H, W, 64, _lib.dtype_code(x_in),
-                  code, sp, algo_bytes=2 * raw0.numel() * es + x_in.numel() * x_in.element_size(), algo_flops=2 * 147 * raw0.numel())
+        if _stem_as_gemm(dt):
+            m0 = nt * ho * wo
+            draw0 = bn_backward(g_act, raw0, vec0, tr0, 2, params[1], gviews[1], gviews[2], m0)
+            del g_act
+            patches = torch.empty((m0, STEM_KP), dtype=dt, device=dev)
+            _lib.call("ehgr_stem7_im2col", x_in.data_ptr(), patches.data_ptr(), nt, H, W, STEM_KP, _lib.dtype_code(x_in), code, sp,
+                      algo_bytes=x_in.numel() * x_in.element_size() + patches.numel() * es)
+            dwp = torch.zeros(64 * STEM_KP, dtype=torch.float32, device=dev)
+            wgrad(draw0, op_plain(patches), dwp, m0, STEM_KP, 64, "[stem7x7]")
+            _lib.call("ehgr_stem7_unpack_grad", dwp.data_ptr(), gviews[0].data_ptr(), 64, STEM_KP, sp)
+        else:
+            dy_op = bn_backward(g_act, raw0, vec0, tr0, 2, params[1], gviews[1], gviews[2], nt * ho * wo, materialise=False)
+            _lib.call("ehgr_stem7_wgrad", ctypes.byref(dy_op), x_in.data_ptr(), gviews[0].data_ptr(), nt, H, W, 64,
+                      _lib.dtype_code(x_in), code, sp, algo_bytes=2 * raw0.numel() * es + x_in.numel() * x_in.element_size(),
+                      algo_flops=2 * 147 * raw0.numel())
         if sink is not None:
             sink.mark_done([q for q, sv in zip(params[0:3], sunk[0:3]) if sv is not None])
         pg = [gv if (q.requires_grad and sv is None) else None for gv, q, sv in zip(gviews, params, sunk)]

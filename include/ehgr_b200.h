@@ -439,6 +439,10 @@ int ehgr_action_fir_bwd(const ehgr_action* a, const void* dxs, const void* x, co
  *                      (x_dtype), w [64,3,7,7] fp32, out [frames, ho, wo, 64] raw (before BatchNorm), ho = (h-1)/2+1;
  *                      stats (optional, += ) [2*64] doubles: per-channel sum and sum of squares of the stored values.
  *   ehgr_stem7_wgrad : dw [64,3,7,7] += rowop(dy)^T * patches(x); dy is usually a BNBWD operand over (g, raw).
+ *   ehgr_stem7_im2col / ehgr_stem7_pack / ehgr_stem7_unpack_grad : the same convolution as a tensor-core GEMM (bf16 path):
+ *                      a [frames*ho*wo, kp] = the 147-column patch matrix (column t = (ci*7+ky)*7+kx, zero padded to kp, a
+ *                      multiple of 8), wp [cout, kp] = the filter in that column order (fp32 or bf16), and
+ *                      dw [cout,3,7,7] += dwp [cout, kp][:, :147]; the GEMM itself is ehgr_pw_gemm_bn / ehgr_pw_wgrad.
  *   ehgr_maxpool3_fwd: replaces ReLU + MaxPool2d(3, stride=2, padding=1) after bn1: y [frames,ho,wo,c] = window max of
  *                      rowop(a) (an AFFINE operand = lazy BatchNorm+ReLU of the stem output); idx (uint8, same shape
  *                      as y) = winning tap 3*ky+kx, first maximum in scan order as at::max_pool2d.
@@ -454,6 +458,10 @@ int ehgr_stem7_fwd(const void* x, const float* w, void* out, double* stats, long
                    int x_dtype, int out_dtype, ehgr_stream_t stream);
 int ehgr_stem7_wgrad(const ehgr_rowop* dy, const void* x, float* dw, long long frames, int h, int w_in, int cout,
                      int x_dtype, int dtype, ehgr_stream_t stream);
+int ehgr_stem7_im2col(const void* x, void* a, long long frames, int h, int w_in, int kp, int x_dtype, int dtype,
+                      ehgr_stream_t stream);
+int ehgr_stem7_pack(const float* w, void* wp, int cout, int kp, int dtype, ehgr_stream_t stream);
+int ehgr_stem7_unpack_grad(const float* dwp, float* dw, int cout, int kp, ehgr_stream_t stream);
 int ehgr_maxpool3_fwd(const ehgr_rowop* a, void* y, void* idx, long long frames, int h, int w, int c, int dtype,
                       ehgr_stream_t stream);
 int ehgr_maxpool3_bwd(const void* g, const void* idx, void* gx, long long frames, int h, int w, int c, int dtype,

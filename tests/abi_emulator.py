@@ -220,6 +220,28 @@ def ehgr_stem7_wgrad(dy, x, dw, frames, h, w_in, cout, x_dtype, dtype, stream):
     arr(dw, (cout, 3, 49))[...] += np.einsum("fhwo,fcthw->oct", D, P, optimize=True)
 
 
+def ehgr_stem7_im2col(x, a, frames, h, w_in, kp, x_dtype, dtype, stream):
+    assert x_dtype == 0 and dtype == 0
+    ho, wo = _half(h), _half(w_in)
+    xp = np.zeros((frames, 3, h + 6, w_in + 6), F32)
+    xp[:, :, 3:-3, 3:-3] = arr(x, (frames, 3, h, w_in))
+    P = _patches(xp, 7, 2, ho, wo)                                     # [F, 3, 49, ho, wo]
+    A = arr(a, (frames * ho * wo, kp))
+    A[...] = 0
+    A[:, :147] = P.transpose(0, 3, 4, 1, 2).reshape(frames * ho * wo, 147)
+
+
+def ehgr_stem7_pack(w, wp, cout, kp, dtype, stream):
+    assert dtype == 0
+    Wp = arr(wp, (cout, kp))
+    Wp[...] = 0
+    Wp[:, :147] = arr(w, (cout, 147))
+
+
+def ehgr_stem7_unpack_grad(dwp, dw, cout, kp, stream):
+    arr(dw, (cout, 147))[...] += arr(dwp, (cout, kp))[:, :147]
+
+
 def ehgr_maxpool3_fwd(a, y, idx, frames, h, w, c, dtype, stream):
     assert dtype == 0
     ho, wo = _half(h), _half(w)

@@ -77,6 +77,50 @@ def test_stem7_forward_statistics_wgrad(frames, h, w, dtype, tol):
     assert rel_err(dw.cpu(), wr.grad) < 1e-5          # fp32 accumulation of the operands as stored
 
 
+@pytest.mark.parametrize("frames,h,w", [(3, 38, 38), (2, 64, 48), (1, 7, 9)])
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_stem7_as_gemm(frames, h, w, dtype, tol):
+    """The bf16 path of the stem: patch matrix (ehgr_stem7_im2col) x packed filter on the pointwise GEMM kernels, forward with
+    statistics and weight gradient, against F.conv2d in fp64; the patch matrix itself against F.unfold (bit-exact copy)."""
+    E = _E()
+    KP = E.resnet_ops.STEM_KP
+    g = torch.Generator().manual_seed(h + 1)
+    x = torch.randn(frames, 3, h, w, generator=g)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5).cuda()
+    xd = x.to(dtype).cuda()
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    M = frames * ho * wo
+    A = torch.full((M, KP), float("nan"), dtype=dtype, device="cuda")
+    E._lib.call("ehgr_stem7_im2col", xd.data_ptr(), A.data_ptr(), frames, h, w, KP, _code(dtype), _code(dtype), _sp())
+    want = F.unfold(xd.cpu().double(), 7, padding=3, stride=2).transpose(1, 2).reshape(M, 147)
+    assert torch.equal(A[:, :147].cpu().double(), want) and bool((A[:, 147:] == 0).all())
+    wp32 = torch.full((64, KP), float("nan"), dtype=torch.float32, device="cuda")
+    wp16 = torch.full((64, KP), float("nan"), dtype=torch.bfloat16, device="cuda")
+    E._lib.call("ehgr_stem7_pack", wt.data_ptr(), wp32.data_ptr(), 64, KP, 0, _sp())
+    E._lib.call("ehgr_stem7_pack", wt.data_ptr(), wp16.data_ptr(), 64, KP, 1, _sp())
+    assert torch.equal(wp32[:, :147], wt.view(64, 147)) and bool((wp32[:, 147:] == 0).all())
+    assert torch.equal(wp16, wp32.to(torch.bfloat16))
+    engine = 1 if dtype == torch.float32 else 2
+    out = torch.full((M, 64), float("nan"), dtype=dtype, device="cuda")
+    stats = torch.zeros(128, dtype=torch.float64, device="cuda")
+    E._lib.call("ehgr_pw_gemm_bn", ctypes.byref(E.fused.op_plain(A)), wp32.data_ptr(), wp16.data_ptr() if engine == 2 else 0, 0,
+                out.data_ptr(), 0, stats.data_ptr(), M, KP, 64, _code(dtype), engine, None, _sp())
+    wr = (wt.cpu().to(dtype).double() if engine == 2 else wt.cpu().double()).requires_grad_(True)
+    y = F.conv2d(xd.cpu().double(), wr, stride=2, padding=3)
+    got = out.view(frames, ho, wo, 64).cpu().double().permute(0, 3, 1, 2)
+    assert rel_err(got, y) < tol
+    assert rel_err(stats[:64].cpu(), got.sum((0, 2, 3))) < 1e-4
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    gyd = _nhwc(gy.float(), dtype)
+    y.backward(_back(gyd))
+    dwp = torch.zeros(64 * KP, dtype=torch.float32, device="cuda")
+    E._lib.call("ehgr_pw_wgrad", ctypes.byref(E.fused.op_plain(gyd)), ctypes.byref(E.fused.op_plain(A)), dwp.data_ptr(), M, KP, 64,
+                _code(dtype), engine, _sp())
+    dw = torch.zeros(64, 3, 7, 7, dtype=torch.float32, device="cuda")
+    E._lib.call("ehgr_stem7_unpack_grad", dwp.data_ptr(), dw.data_ptr(), 64, KP, _sp())
+    assert rel_err(dw.cpu(), wr.grad) < tol
+
+
 @pytest.mark.parametrize("frames,h,w,c", [(3, 16, 16, 64), (2, 7, 9, 64), (2, 12, 6, 24), (1, 1, 1, 8)])
 @pytest.mark.parametrize("dtype,tol", DTYPES)
 def test_maxpool3_forward_backward(frames, h, w, c, dtype, tol):

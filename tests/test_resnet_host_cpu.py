@@ -53,10 +53,11 @@ def _eager(net, x):
     return t1, t2, t3, net.layer4(t3)
 
 
-@pytest.mark.parametrize("shift,train_bn", [(True, True), (False, True), (True, False)])
-def test_resnet_function_matches_autograd(emulated, shift, train_bn):
+@pytest.mark.parametrize("shift,train_bn,stem_gemm", [(True, True, False), (False, True, True), (True, False, True)])
+def test_resnet_function_matches_autograd(emulated, monkeypatch, shift, train_bn, stem_gemm):
     E = emulated
     R = E.resnet_ops
+    monkeypatch.setattr(R, "STEM_GEMM", stem_gemm)        # the 7x7 stem as a patch-matrix GEMM (the bf16 path) or the CUDA-core kernel
     T, size = 2, 48
     net = _net(E, [2, 1, 1, 1], shift, T)
     net.train(train_bn)
