@@ -208,8 +208,8 @@ class _ResNetFunction(torch.autograd.Function):
         ho, wo = _half(H), _half(W)
         raw0 = _nhwc_empty(nt, ho, wo, 64, dt, dev)
         if _stem_as_gemm(dt):
-            # patch matrix [M, 160] (147 taps + zero pad) -> one plain GEMM on the tensor cores; the matrix is rebuilt in
-            # backward instead of being kept (M * 320 bytes)
+            # patch matrix [M, 160] (147 taps + zero pad) -> one plain GEMM on the tensor cores; backward's weight-gradient
+            # GEMM reads the same matrix, so it is kept (M * 320 bytes = 4 MB per 224^2 frame, ~10 % of what the step saves)
             m0 = nt * ho * wo
             patches = torch.empty((m0, STEM_KP), dtype=dt, device=dev)
             _lib.call("ehgr_stem7_im2col", x_in.data_ptr(), patches.data_ptr(), nt, H, W, STEM_KP, _lib.dtype_code(x_in), code, sp,
@@ -222,8 +222,8 @@ class _ResNetFunction(torch.autograd.Function):
                 _lib.call("ehgr_stem7_pack", w0.data_ptr(), wp16.data_ptr(), 64, STEM_KP, _lib.BF16, sp)
             vec0, tr0 = bn_forward(lambda st: gemm(op_plain(patches), wp32, wp16, raw0, st, m0, STEM_KP, 64, "[stem7x7]",
                                                    m0 * STEM_KP), plan.bn1, g0, b0, m0)
-            del patches
         else:
+            patches = None
             vec0, tr0 = bn_forward(lambda st: _lib.call(
                 "ehgr_stem7_fwd", x_in.data_ptr(), w0.data_ptr(), raw0.data_ptr(), st, nt, H, W, 64, _lib.dtype_code(x_in), code, sp,
                 algo_bytes=x_in.numel() * x_in.element_size() + raw0.numel() * es, algo_flops=2 * 147 * raw0.numel()),
@@ -233,7 +233,7 @@ class _ResNetFunction(torch.autograd.Function):
         pool_idx = torch.empty((nt, h, w, 64), dtype=torch.uint8, device=dev)
         _lib.call("ehgr_maxpool3_fwd", ctypes.byref(op_affine(raw0, vec0[0], vec0[1], 2)), cur.data_ptr(), pool_idx.data_ptr(), nt,
                   ho, wo, 64, code, sp, algo_bytes=raw0.numel() * es + cur.numel() * (es + 1))
-        stem_saved = (raw0, vec0, tr0, pool_idx, (ho, wo))
+        stem_saved = (raw0, vec0, tr0, pool_idx, (ho, wo), patches)
 
         saved, outputs, tap_blocks = [], [], []
         p_i = 3
@@ -455,17 +455,14 @@ class _ResNetFunction(torch.autograd.Function):
                 n_p = 9 + (3 if b.down is not None else 0)
                 sink.mark_done([q for q, sv in zip(params[pb:pb + n_p], sunk[pb:pb + n_p]) if sv is not None])
         # ---- stem: max-pool adjoint -> bn1 + ReLU backward (BNBWD operand) -> 7x7 weight gradient
-        raw0, vec0, tr0, pool_idx, (ho, wo) = ctx.stem_saved
+        raw0, vec0, tr0, pool_idx, (ho, wo), patches = ctx.stem_saved
         g_act = torch.empty_like(raw0)
         _lib.call("ehgr_maxpool3_bwd", g.data_ptr(), pool_idx.data_ptr(), g_act.data_ptr(), nt, ho, wo, 64, code, sp,
                   algo_bytes=g.numel() * (es + 1) + g_act.numel() * es)
-        if _stem_as_gemm(dt):
+        if patches is not None:
             m0 = nt * ho * wo
             draw0 = bn_backward(g_act, raw0, vec0, tr0, 2, params[1], gviews[1], gviews[2], m0)
             del g_act
-            patches = torch.empty((m0, STEM_KP), dtype=dt, device=dev)
-            _lib.call("ehgr_stem7_im2col", x_in.data_ptr(), patches.data_ptr(), nt, H, W, STEM_KP, _lib.dtype_code(x_in), code, sp,
-                      algo_bytes=x_in.numel() * x_in.element_size() + patches.numel() * es)
             dwp = torch.zeros(64 * STEM_KP, dtype=torch.float32, device=dev)
             wgrad(draw0, op_plain(patches), dwp, m0, STEM_KP, 64, "[stem7x7]")
             _lib.call("ehgr_stem7_unpack_grad", dwp.data_ptr(), gviews[0].data_ptr(), 64, STEM_KP, sp)
