@@ -139,20 +139,27 @@ def quiet():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(temporal: str, clips: int, steps: int, warmup: int, workload: str = "mtmm", classes: int = 83):
+def cpu_reference_step_rate(temporal: str, clips: int, steps: int, warmup: int, workload: str = "mtmm", classes: int = 83,
+                            backbone: str = "mobilenetv2", segments: int = T_SEG):
     """clips/s of the reference step (fwd + loss + bwd + SGD) of `workload` on all host cores, fp32."""
     from oracle import ref_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    resnet = backbone == "resnet50"
+    if resnet and workload != "mtmm":
+        raise SystemExit("the CPU arm of --backbone resnet50 restates the MTMM step only")
     build = {"mtmm": O.build_mtmm_state, "sd": O.build_sd_state, "mtmm_sd": O.build_mtmm_sd_state}[workload]
-    sd = O.clone_state(build(classes, temporal, 8, seed=0))
+    sd = O.clone_state(O.build_resnet_mtmm_state(classes, temporal, seed=0) if resnet else build(classes, temporal, 8, seed=0))
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.SGD(params, lr=0.00125, momentum=0.9, weight_decay=5e-4)
+    T_SEG = segments
     rgb, depth, labels = O.synthetic_clip_batch(clips, T_SEG, SIZE, classes, seed=0)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        if workload == "mtmm":
+        if resnet:
+            O.resnet_mtmm_train_step(sd, rgb, depth, labels, T_SEG, temporal, 8, True)
+        elif workload == "mtmm":
             O.mtmm_train_step(sd, rgb, depth, labels, T_SEG, temporal, 8, True)
         elif workload == "sd":
             O.sd_train_step(sd, rgb, labels, T_SEG, temporal, 8, True)
@@ -173,13 +180,17 @@ def run_reference(args):
     # K = 20, W = 5 is a few seconds); only absurd requests are bounded so that the arm always ends within minutes
     steps = max(1, min(args.steps, 200))
     warm = max(0, min(args.warmup, 50))
-    v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, steps, warm, args.workload, args.classes)
+    resnet = args.backbone == "resnet50"
+    v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, steps, warm, args.workload, args.classes,
+                                           args.backbone, args.segments)
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": (METRIC if not resnet else f"train clips/sec TSM-ResNet50 {args.segments}x224^2"),
+        "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD_NAMES[args.workload]}, {args.temporal.upper()}-MobileNetV2, "
-                               f"8x224^2, {args.classes} classes; CPU sample = {args.cpu_clips} clips/step"},
+        "config": {"workload": f"{WORKLOAD_NAMES[args.workload]}, {args.temporal.upper()}-"
+                               f"{'ResNet50' if resnet else 'MobileNetV2'}, "
+                               f"{args.segments}x224^2, {args.classes} classes; CPU sample = {args.cpu_clips} clips/step"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32, "
                                    f"{cores} threads"},
@@ -359,8 +370,9 @@ def run_ours(args):
         }
         if world > 1:
             line["ranks_in_sync"] = bool(in_sync)
-        if not args.no_cpu_baseline and world == 1 and not resnet:
-            v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1, args.workload, NUM_CLASS)
+        if not args.no_cpu_baseline and world == 1 and not (resnet and args.workload != "mtmm"):
+            v, dt, cores = cpu_reference_step_rate(args.temporal, args.cpu_clips, 3, 1, args.workload, NUM_CLASS,
+                                                   args.backbone, T_SEG)
             line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"3 steps of {args.cpu_clips} clips (fwd+loss+bwd+SGD), torch fp32 oracle "
                                               f"port of the reference modules, {cores} threads"}

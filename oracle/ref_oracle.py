@@ -676,3 +676,28 @@ def build_resnet_state(layers=RESNET50_LAYERS, num_class: int = 83, temporal: st
     sd["new_fc.weight"] = torch.from_numpy((rs.standard_normal((num_class, inplanes)) * 0.02).astype(np.float32))
     sd["new_fc.bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
     return sd
+
+
+def build_resnet_mtmm_state(num_class: int = 83, temporal: str = "tsm", seed: int = 0, layers=RESNET50_LAYERS) -> SD:
+    """models_MTMM.TSN(base_model='resnet50'): the backbone + new_fc + global_decoder over 2048 channels
+    (models/models_MTMM.py:129-155 — the reference's own configuration of the decoder)."""
+    sd = build_resnet_state(layers, num_class, temporal, seed)
+    decoder_state(sd, np.random.RandomState(seed + 77), 512 * 4)
+    return sd
+
+
+def resnet_mtmm_train_step(sd: SD, rgb, depth, labels, num_segments=16, temporal="tsm", shift_div=8, bn_training=True,
+                           layers=RESNET50_LAYERS):
+    """One MTMM step (train_mtmm.py:205-245) on the ResNet-50 wrapper (models/models_MTMM.py:268-292): logits from the pooled
+    layer4 map, depth from global_decoder(layer4), loss train_mtmm.py:223-231, backward.  Gradients are left in sd[*].grad."""
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    x = rgb.view((-1, 3) + tuple(rgb.shape[-2:]))
+    f = resnet_features(x, sd, layers, temporal, num_segments, shift_div, bn_training)[-1]
+    z = F.linear(f.mean((2, 3)), sd["new_fc.weight"], sd["new_fc.bias"])
+    logits = z.view((-1, num_segments) + tuple(z.shape[1:])).mean(dim=1)
+    dpred = global_decoder(f, sd, bn_training)
+    loss, _ = mtmm_loss(logits, labels, dpred, depth)
+    loss.backward()
+    return loss.detach(), logits.detach(), dpred.detach()
