@@ -288,6 +288,110 @@ def ehgr_relu_bwd(g, out, gz, n, dtype, stream):
     arr(gz, (n,))[...] = arr(g, (n,)) * (arr(out, (n,)) > 0)
 
 
+# ---- MobileNetV2 chain: depthwise (K7), stem (K9), head (K10), decoder pieces (N2) — restated with torch ops ------------------
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def ehgr_dw_fwd_bn(a, w, out, stats, nt, h, wd, c, stride, dtype, fin, stream):
+    import torch.nn.functional as TF
+    assert dtype == 0 and fin is None
+    X = _t(rowop(a, nt * h * wd, c).reshape(nt, h, wd, c)).permute(0, 3, 1, 2)
+    y = TF.conv2d(X, _t(arr(w, (c, 1, 3, 3))), stride=stride, padding=1, groups=c).permute(0, 2, 3, 1).numpy()
+    arr(out, y.shape)[...] = y
+    _add_stats(stats, y.reshape(-1, c), c)
+
+
+def ehgr_dw_fwd(a, w, out, stats, nt, h, wd, c, stride, dtype, stream):
+    ehgr_dw_fwd_bn(a, w, out, stats, nt, h, wd, c, stride, dtype, None, stream)
+
+
+def ehgr_dw_bwd(dy, a, w, da, dw, nt, h, wd, c, stride, dtype, stream):
+    import torch
+    import torch.nn.functional as TF
+    assert dtype == 0
+    ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    X = _t(rowop(a, nt * h * wd, c).reshape(nt, h, wd, c)).permute(0, 3, 1, 2).requires_grad_(True)
+    Wt = _t(arr(w, (c, 1, 3, 3)).copy()).requires_grad_(True)
+    DY = _t(rowop(dy, nt * ho * wo, c).reshape(nt, ho, wo, c)).permute(0, 3, 1, 2)
+    with torch.enable_grad():          # called from inside an autograd.Function.backward, where grad mode is off
+        gx, gw = torch.autograd.grad(TF.conv2d(X, Wt, stride=stride, padding=1, groups=c), (X, Wt), DY)
+    arr(da, (nt, h, wd, c))[...] = gx.permute(0, 2, 3, 1).numpy()
+    arr(dw, (c, 1, 3, 3))[...] += gw.numpy()
+
+
+def ehgr_stem_fwd_bn(x, w, out, stats, nt, h, wd, cout, x_dtype, dtype, fin, stream):
+    import torch.nn.functional as TF
+    assert x_dtype == 0 and dtype == 0 and fin is None
+    y = TF.conv2d(_t(arr(x, (nt, 3, h, wd))), _t(arr(w, (cout, 3, 3, 3))), stride=2, padding=1).permute(0, 2, 3, 1).numpy()
+    arr(out, y.shape)[...] = y
+    _add_stats(stats, y.reshape(-1, cout), cout)
+
+
+def ehgr_stem_wgrad(dy, x, dw, nt, h, wd, cout, x_dtype, dtype, stream):
+    import torch
+    import torch.nn.functional as TF
+    assert x_dtype == 0 and dtype == 0
+    ho, wo = (h - 1) // 2 + 1, (wd - 1) // 2 + 1
+    Wt = torch.zeros(cout, 3, 3, 3, requires_grad=True)
+    DY = _t(rowop(dy, nt * ho * wo, cout).reshape(nt, ho, wo, cout)).permute(0, 3, 1, 2)
+    with torch.enable_grad():
+        (gw,) = torch.autograd.grad(TF.conv2d(_t(arr(x, (nt, 3, h, wd))), Wt, stride=2, padding=1), (Wt,), DY)
+    arr(dw, (cout, 3, 3, 3))[...] += gw.numpy()
+
+
+def ehgr_pool_fwd(a, pooled, nt, hw, c, dtype, stream):
+    assert dtype == 0
+    arr(pooled, (nt, c))[...] = rowop(a, nt * hw, c).reshape(nt, hw, c).mean(1)
+
+
+def ehgr_pool_bwd(dpooled, da, nt, hw, c, dtype, stream):
+    assert dtype == 0
+    arr(da, (nt, hw, c))[...] = arr(dpooled, (nt, 1, c)) / hw
+
+
+def ehgr_fc_consensus_fwd(feat, w, bias, meanfeat, logits, n, T, f, k, stream):
+    mf = arr(feat, (n, T, f)).mean(1)
+    arr(meanfeat, (n, f))[...] = mf
+    z = mf @ arr(w, (k, f)).T
+    arr(logits, (n, k))[...] = z + (arr(bias, (k,)) if bias else 0)
+
+
+def ehgr_fc_consensus_bwd(dlogits, meanfeat, w, dfeat, dw, dbias, n, T, f, k, stream):
+    G = arr(dlogits, (n, k))
+    arr(dfeat, (n, T, f))[...] = ((G @ arr(w, (k, f))) / T)[:, None, :]
+    arr(dw, (k, f))[...] += G.T @ arr(meanfeat, (n, f))
+    if dbias:
+        arr(dbias, (k,))[...] += G.sum(0)
+
+
+def ehgr_upsample2_fwd(x, y, frames, h, w, c, dtype, stream):
+    assert dtype == 0
+    arr(y, (frames, 2 * h, 2 * w, c))[...] = arr(x, (frames, h, w, c)).repeat(2, axis=1).repeat(2, axis=2)
+
+
+def ehgr_upsample2_bwd(g_up, g, frames, h, w, c, dtype, stream):
+    assert dtype == 0
+    arr(g, (frames, h, w, c))[...] = arr(g_up, (frames, h, 2, w, 2, c)).sum((2, 4))
+
+
+def ehgr_depth_head_fwd(a, w, bias, out, m, c, dtype, stream):
+    assert dtype == 0
+    z = rowop(a, m, c) @ arr(w, (c,)) + (arr(bias, (1,))[0] if bias else 0.0)
+    arr(out, (m,))[...] = 1.0 / (1.0 + np.exp(-z))
+
+
+def ehgr_depth_head_bwd(a, w, out, dout, g_a, dw, dbias, m, c, dtype, stream):
+    assert dtype == 0
+    o = arr(out, (m,))
+    dz = arr(dout, (m,)) * o * (1 - o)
+    arr(g_a, (m, c))[...] = dz[:, None] * arr(w, (c,))[None, :]
+    arr(dw, (c,))[...] += dz @ rowop(a, m, c)
+    if dbias:
+        arr(dbias, (1,))[...] += dz.sum()
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("ehgr_")}
 
 
