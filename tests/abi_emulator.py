@@ -392,6 +392,32 @@ def ehgr_depth_head_bwd(a, w, out, dout, g_a, dw, dbias, m, c, dtype, stream):
         arr(dbias, (1,))[...] += dz.sum()
 
 
+def ehgr_mtmm_loss(logits, labels, pred, depth_gt, depth_weight, loss_out, dlogits, dpred, n, k, frames, ph, pw, dtype, stream):
+    """K12: total = CE + depth_weight * MSE(pred, mean of the 2x2 centre pixels of every 4x4 cell of depth_gt)."""
+    import torch
+    import torch.nn.functional as TF
+    assert dtype == 0
+    P = _t(arr(pred, (frames, ph, pw)).copy()).requires_grad_(True)
+    gt = _t(arr(depth_gt, (frames, ph, 4, pw, 4)))[:, :, 1:3, :, 1:3].mean((2, 4))
+    with torch.enable_grad():
+        mse = ((P - gt) ** 2).mean()
+        total = depth_weight * mse
+        ce = torch.zeros(())
+        if n > 0:
+            L = _t(arr(logits, (n, k)).copy()).requires_grad_(True)
+            ce = TF.cross_entropy(L, _t(arr(labels, (n,), np.int64)))
+            total = total + ce
+            gP, gL = torch.autograd.grad(total, (P, L))
+            arr(dlogits, (n, k))[...] = gL.numpy()
+        else:
+            (gP,) = torch.autograd.grad(total, (P,))
+    arr(dpred, (frames, ph, pw))[...] = gP.numpy()
+    out = arr(loss_out, (3,))
+    out[0] += float(total)
+    out[1] += float(ce)
+    out[2] += float(mse)
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("ehgr_")}
 
 
