@@ -77,6 +77,12 @@ def require_cuda(*tensors) -> None:
                 f"(got a tensor on {t.device})")
 
 
+def on_gpu(t) -> bool:
+    """Whether `t` lives on a CUDA device — the one place the module wrappers ask before taking the library's path
+    (CPU tensors run the plain modules: shape / policy tests only; the CPU test-suite points this at its C-ABI emulator)."""
+    return bool(t.is_cuda)
+
+
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
 

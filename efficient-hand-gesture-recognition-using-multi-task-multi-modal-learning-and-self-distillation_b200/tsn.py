@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+
+from . import _lib
 from torch.nn.init import constant_, normal_
 
 from .basic_ops import ConsensusModule
@@ -186,14 +188,14 @@ class TSN(nn.Module):
     def forward(self, input, no_reshape=False):
         assert input.size()[1] > 3, \
             'channel and temporal dimension mismatch, tensor size should be: n_batch, n_segment, nc, h, w'
-        if (input.is_cuda and not no_reshape and self.reshape and self.base_model_name == 'mobilenetv2'
+        if (_lib.on_gpu(input) and not no_reshape and self.reshape and self.base_model_name == 'mobilenetv2'
                 and not (self.is_shift and self.temporal_pool)):
             # backbone -> global average pool -> Dropout -> new_fc -> segment consensus, all on the library's kernels
             # (csrc/head.cu folds the 'avg' consensus in front of the classifier GEMV: fused.classifier_head)
             from . import fused
             fmap = fused.mobilenet_v2_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))
             return fused.classifier_head(self, fmap)
-        if input.is_cuda and not no_reshape and self.reshape and self._fused_resnet():
+        if _lib.on_gpu(input) and not no_reshape and self.reshape and self._fused_resnet():
             # N3: torchvision Bottleneck ResNet (+ TemporalShift on conv1) on the library's kernels (resnet_ops.py)
             from . import fused, resnet_ops
             fmap = resnet_ops.resnet_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))

@@ -15,6 +15,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import _lib
+
 from .tsn import TSN as _BaseTSN
 
 
@@ -57,7 +59,7 @@ class TSN(_BaseTSN):
         bm = self.base_model
         if self.base_model_name == 'mobilenetv2':
             return fused.mobilenet_v2_features(bm, x)
-        if x.is_cuda and self._fused_resnet():                 # N3: Bottleneck ResNet on the library's kernels
+        if _lib.on_gpu(x) and self._fused_resnet():                 # N3: Bottleneck ResNet on the library's kernels
             from . import resnet_ops
             return resnet_ops.resnet_features(bm, x)
         x = bm.maxpool(bm.relu(bm.bn1(bm.conv1(x))))
@@ -71,7 +73,7 @@ class TSN(_BaseTSN):
         if self.modal == 'rgb':
             return output
         if self.modal == 'rgb_depth':
-            if fmap.is_cuda:                                   # four implicit-GEMM conv stages + the depth head (fused.py)
+            if _lib.on_gpu(fmap):                                   # four implicit-GEMM conv stages + the depth head (fused.py)
                 return output, fused.depth_decoder(self.global_decoder, fmap)
             return output, self.global_decoder(fmap)           # CPU: shape / policy tests only
         raise ValueError(self.modal)

@@ -19,6 +19,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import _lib
+
 from .tsn import TSN as _BaseTSN
 
 MBV2_TAPS = (3, 6, 13)            # features indices
@@ -44,7 +46,7 @@ class SepConv(nn.Module):
         )
 
     def forward(self, x):
-        if x.is_cuda:
+        if _lib.on_gpu(x):
             from . import fused
             return fused.sepconv_stack([self], x)
         return self.op(x)               # CPU: plain module arithmetic (shape / policy tests only; no CUDA kernels exist there)
@@ -89,7 +91,7 @@ class TSN(_BaseTSN):
         bm = self.base_model
         if self.base_model_name == 'mobilenetv2':
             return fused.mobilenet_v2_features(bm, x, taps=MBV2_TAPS)          # (f3, f6, f13, final)
-        if x.is_cuda and self._fused_resnet():                 # N3: Bottleneck ResNet on the library's kernels
+        if _lib.on_gpu(x) and self._fused_resnet():                 # N3: Bottleneck ResNet on the library's kernels
             from . import resnet_ops
             return resnet_ops.resnet_features(bm, x, taps=(1, 2, 3))          # (layer1, layer2, layer3, layer4)
         x = bm.maxpool(bm.relu(bm.bn1(bm.conv1(x))))
@@ -100,7 +102,7 @@ class TSN(_BaseTSN):
 
     def _exit(self, x, scala, pool, fc):
         from . import fused
-        if x.is_cuda and all(isinstance(m, SepConv) for m in scala):
+        if _lib.on_gpu(x) and all(isinstance(m, SepConv) for m in scala):
             y = fused.sepconv_stack(list(scala), x)     # one fused chain per exit head
             pooled = fused.global_avg_pool(y)           # [NT, F] fp32
             fea = pooled.view(pooled.shape[0], pooled.shape[1], 1, 1)

@@ -701,3 +701,48 @@ def resnet_mtmm_train_step(sd: SD, rgb, depth, labels, num_segments=16, temporal
     loss, _ = mtmm_loss(logits, labels, dpred, depth)
     loss.backward()
     return loss.detach(), logits.detach(), dpred.detach()
+
+
+# N3: the reference's OWN MTMM / SD wrappers are written for ResNet bases (models/models_MTMM.py:112-157, 268-292;
+# models/models_SD.py:214-253, 364-431).  Restated over the ResNet functions above; pinned against the live, unmodified
+# wrappers (is_shift=False: the reference's ResNet temporal module is Action) by make_golden.golden_resnet_wrappers.
+RESNET_SD_HEADS = (("scala1", (256, 512, 1024, 2048)), ("scala2", (512, 1024, 2048)), ("scala3", (1024, 2048)))
+
+
+def resnet_mtmm_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8, bn_training: bool = True,
+                        layers=RESNET50_LAYERS):
+    """models_MTMM.TSN.forward: -> (logits [N,cls], depth [NT,1,8h,8w]) with h x w the layer4 map."""
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    f = resnet_features(x, sd, layers, temporal, num_segments, shift_div, bn_training)[-1]
+    z = F.linear(f.mean((2, 3)), sd["new_fc.weight"], sd["new_fc.bias"])
+    return z.view((-1, num_segments) + tuple(z.shape[1:])).mean(dim=1), global_decoder(f, sd, bn_training)
+
+
+def resnet_sd_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8, bn_training: bool = True,
+                      layers=RESNET50_LAYERS):
+    """models_SD.TSN.forward: -> (output, mid1, mid2, mid3, final_fea, fea1, fea2, fea3), taps after layer1 / 2 / 3."""
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    t1, t2, t3, t4 = resnet_features(x, sd, layers, temporal, num_segments, shift_div, bn_training)
+    mids, feas = [], []
+    for (name, chans), y, fc in zip(RESNET_SD_HEADS, (t1, t2, t3), ("middle_fc1", "middle_fc2", "middle_fc3")):
+        for j in range(len(chans) - 1):
+            y = sepconv(y, sd, f"{name}.{j}", bn_training)
+        fea = F.adaptive_avg_pool2d(y, 1)
+        z = F.linear(torch.flatten(fea, 1), sd[fc + ".weight"], sd[fc + ".bias"])
+        mids.append(z.view((-1, num_segments) + tuple(z.shape[1:])).mean(1))
+        feas.append(fea)
+    final_fea = F.adaptive_avg_pool2d(t4, 1)
+    z = F.linear(torch.flatten(final_fea, 1), sd["new_fc.weight"], sd["new_fc.bias"])
+    return (z.view((-1, num_segments) + tuple(z.shape[1:])).mean(1), *mids, final_fea, *feas)
+
+
+def build_resnet_sd_state(num_class: int = 83, temporal: str = "tsm", seed: int = 0, layers=RESNET50_LAYERS) -> SD:
+    sd = build_resnet_state(layers, num_class, temporal, seed)
+    rs = np.random.RandomState(seed + 991)
+    for name, chans in RESNET_SD_HEADS:
+        for j, (ci, co) in enumerate(zip(chans[:-1], chans[1:])):
+            sepconv_state(sd, f"{name}.{j}", ci, co, rs)
+    for fc in ("middle_fc1", "middle_fc2", "middle_fc3"):
+        sd[fc + ".weight"] = torch.from_numpy((rs.standard_normal((num_class, 2048)) * 0.02).astype(np.float32))
+        sd[fc + ".bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
+    return sd

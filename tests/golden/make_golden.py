@@ -459,6 +459,84 @@ def golden_resnet():
     np.savez_compressed(HERE / "resnet.npz", **out)
 
 
+def golden_resnet_wrappers():
+    """N3: the UNMODIFIED reference wrappers on their own backbone — models_MTMM.TSN and models_SD.TSN with
+    base_model='resnet50' (is_shift=False) — against the oracle's resnet_mtmm_forward / resnet_sd_forward in fp64: outputs and
+    every gradient.  Written into resnet_wrappers.npz (outputs + gradient digests)."""
+    import models.models_MTMM as MT
+    import models.models_SD as SDM
+    cfg = RESNET_FIXTURE
+    rgb, depth, labels = O.synthetic_clip_batch(cfg["clips"], cfg["T"], cfg["size"], cfg["num_class"], seed=cfg["in_seed"])
+    out = {}
+    common = dict(base_model='resnet50', pretrain=None, dropout=0.5, partial_bn=False, is_shift=False, consensus_type='avg',
+                  fc_lr5=True, img_feature_dim=224)
+
+    def load(ref, sd):
+        res = ref.load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        # models_MTMM keeps a torch.fx feature extractor over the SAME parameters (models/models_MTMM.py:70-77)
+        assert all(k.startswith("feature_extractor.") for k in res.missing_keys), res.missing_keys
+        ref.double()
+        ref.train()
+        for m in ref.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.eval()
+
+    # ---- MTMM
+    sd = O.build_resnet_mtmm_state(cfg["num_class"], "none", seed=cfg["seed"])
+    with _quiet():
+        ref = MT.TSN(cfg["num_class"], cfg["T"], 'RGB', modal='rgb_depth', **common)
+    load(ref, sd)
+    logits, dpred = ref(rgb.double())
+    gt = F.interpolate(depth.double().view(-1, 1, cfg["size"], cfg["size"]), tuple(dpred.shape[-2:]), mode='bilinear')
+    (F.cross_entropy(logits, labels) + 0.01 * F.mse_loss(dpred, gt)).backward()
+    osd = O.clone_state(sd, dtype=torch.float64)
+    ol, od = O.resnet_mtmm_forward(rgb.double(), osd, cfg["T"], "none", 8, True)
+    (F.cross_entropy(ol, labels) + 0.01 * F.mse_loss(od, gt)).backward()
+    assert (ol - logits).abs().max().item() <= 1e-10 * logits.abs().max().item()
+    assert (od - dpred).abs().max().item() <= 1e-10
+    named = {k: p for k, p in ref.named_parameters() if not k.startswith("feature_extractor.")}
+    gmax = max(p.grad.abs().max().item() for p in named.values())
+    for k, p in named.items():
+        assert (osd[k].grad - p.grad).abs().max().item() <= 1e-9 * gmax, k
+    out["mtmm_logits"], out["mtmm_depth"] = logits.detach().numpy(), dpred.detach().numpy()
+    for k, v in grad_digest({k: p.grad for k, p in named.items()}).items():
+        out[f"mtmm_g_{k}"] = v
+    # ---- SD
+    sd = O.build_resnet_sd_state(cfg["num_class"], "none", seed=cfg["seed"])
+    with _quiet():
+        ref = SDM.TSN(cfg["num_class"], cfg["T"], 'RGB', **common)
+    res = ref.load_state_dict(sd, strict=True)
+    ref.double()
+    ref.train()
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.eval()
+    outs = ref(rgb.double())
+    (kd_loss_function, feature_loss_function) = ref_functions(REF / "train_sd.py", ["kd_loss_function", "feature_loss_function"])
+    class _A: temperature = 3.0
+    def total_of(o):
+        ce = sum(F.cross_entropy(z, labels) for z in o[:4])
+        temp4 = torch.softmax(o[0] / _A.temperature, dim=1)                # train_sd.py:236-237
+        kd = sum(kd_loss_function(z, temp4.detach(), _A) * 9.0 for z in o[1:4])
+        fe = sum(feature_loss_function(f, o[4].detach()) for f in o[5:8])
+        return 0.9 * ce + 0.1 * kd + 1e-6 * fe
+    total_of(outs).backward()
+    osd = O.clone_state(sd, dtype=torch.float64)
+    oouts = O.resnet_sd_forward(rgb.double(), osd, cfg["T"], "none", 8, True)
+    ototal, _ = O.sd_loss(oouts[:4], oouts[4:], labels, 0.1, 1e-6, 3.0)
+    ototal.backward()
+    for i, (a, b) in enumerate(zip(oouts, outs)):
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 1e-10 * max(b.abs().max().item(), 1e-30), i
+        out[f"sd_out{i}"] = b.detach().numpy()
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters())
+    for k, p in ref.named_parameters():
+        assert (osd[k].grad - p.grad).abs().max().item() <= 1e-9 * gmax, k
+    for k, v in grad_digest({k: p.grad for k, p in ref.named_parameters()}).items():
+        out[f"sd_g_{k}"] = v
+    np.savez_compressed(HERE / "resnet_wrappers.npz", **out)
+
+
 def golden_ema_and_pool():
     """Separate small file: EMAWrapper replay (initial state stored explicitly) and TemporalPool."""
     from models.temporal_shift import TemporalPool
@@ -502,7 +580,7 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, fn in (("shift", golden_shift), ("action", golden_action), ("losses", golden_losses), ("tsn", golden_tsn),
                      ("heads", golden_heads), ("ema_pool", golden_ema_and_pool),
-                     ("resnet", golden_resnet)):
+                     ("resnet", golden_resnet), ("resnet_wrappers", golden_resnet_wrappers)):
         if not only or name in only:
             fn()
     for p in sorted(HERE.glob("*.npz")):

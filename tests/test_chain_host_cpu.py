@@ -21,6 +21,7 @@ def emulated(monkeypatch):
     monkeypatch.setattr(ehgr_b200._lib, "call", abi_emulator.call)
     monkeypatch.setattr(ehgr_b200._lib, "require_cuda", lambda *t: None)
     monkeypatch.setattr(ehgr_b200._lib, "stream_ptr", lambda device=None: 0)
+    monkeypatch.setattr(ehgr_b200._lib, "on_gpu", lambda t: True)      # the wrappers take the library's path for host tensors
     return ehgr_b200
 
 

@@ -40,6 +40,7 @@ def _worker(rank, world, port, backbone, out):
         E._lib.call = abi_emulator.call
         E._lib.require_cuda = lambda *t: None
         E._lib.stream_ptr = lambda device=None: 0
+        E._lib.on_gpu = lambda t: True         # the wrappers take the library's path for host tensors
         T, cls, size, lr = 2, 5, 64, 0.01
         resnet = backbone == "resnet50"
         sd0 = (O.build_resnet_mtmm_state(cls, "tsm", seed=4) if resnet else O.build_mtmm_state(cls, "tsm", 8, seed=4))
@@ -52,19 +53,6 @@ def _worker(rank, world, port, backbone, out):
         for d in model.modules():
             if isinstance(d, torch.nn.Dropout):
                 d.eval()
-        # the ResNet route is taken for CUDA inputs only: on this CPU run the test takes it explicitly
-        if resnet:
-            from types import MethodType
-            model._last_feature_map = MethodType(lambda self, x: E.resnet_ops.resnet_features(self.base_model, x), model)
-        else:
-            model._last_feature_map = lambda x: E.fused.mobilenet_v2_features(model.base_model, x)
-        orig_forward = model.forward
-
-        def forward(inp):                      # as tsn_mtmm.TSN.forward, with the decoder on the fused path (it checks is_cuda)
-            x = inp.view((-1, 3) + inp.size()[-2:])
-            fmap = model._last_feature_map(x)
-            return E.fused.classifier_head(model, fmap), E.fused.depth_decoder(model.global_decoder, fmap)
-        model.forward = forward
         step = E.train_step.MTMMTrainStep(model, lr=lr, momentum=0.9, weight_decay=0.0, compute_dtype=torch.float32, n_buckets=3)
         assert step.buckets.world == world
         before = {k: p.detach().clone() for k, p in model.named_parameters()}

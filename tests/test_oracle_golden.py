@@ -282,3 +282,27 @@ def test_resnet50_tsn_oracle_matches_reference_wrapper():
     assert abs(loss.item() - float(z["tsn_none_loss"])) < 1e-10
     loss.backward()
     assert _digest_err(sd, z, "tsn_none_g_") < 1e-9
+
+
+def test_resnet50_mtmm_and_sd_oracles_match_the_unmodified_reference_wrappers():
+    """N3's purpose: the reference's OWN models_MTMM.TSN / models_SD.TSN run on ResNet bases.  Fixture = those
+    live wrappers (base_model='resnet50', is_shift=False) in fp64: outputs and gradient digests of every parameter."""
+    z = np.load(GOLDEN / "resnet_wrappers.npz")
+    cfg = RESNET_FIXTURE
+    rgb, depth, labels = O.synthetic_clip_batch(cfg["clips"], cfg["T"], cfg["size"], cfg["num_class"], seed=cfg["in_seed"])
+    # MTMM: logits + depth map, loss of train_mtmm.py:223-231 at this resolution
+    sd = O.clone_state(O.build_resnet_mtmm_state(cfg["num_class"], "none", seed=cfg["seed"]), dtype=torch.float64)
+    ol, od = O.resnet_mtmm_forward(rgb.double(), sd, cfg["T"], "none", 8, True)
+    assert rel_err(ol, torch.from_numpy(z["mtmm_logits"])) < 1e-10 and rel_err(od, torch.from_numpy(z["mtmm_depth"])) < 1e-10
+    gt = F.interpolate(depth.double().view(-1, 1, cfg["size"], cfg["size"]), tuple(od.shape[-2:]), mode='bilinear')
+    (F.cross_entropy(ol, labels) + 0.01 * F.mse_loss(od, gt)).backward()
+    assert _digest_err(sd, z, "mtmm_g_") < 1e-9
+    # SD: eight outputs, loss of train_sd.py:227-265
+    sd = O.clone_state(O.build_resnet_sd_state(cfg["num_class"], "none", seed=cfg["seed"]), dtype=torch.float64)
+    outs = O.resnet_sd_forward(rgb.double(), sd, cfg["T"], "none", 8, True)
+    assert [tuple(o.shape) for o in outs] == [(2, 10)] * 4 + [(8, 2048, 1, 1)] * 4
+    for i, o in enumerate(outs):
+        assert rel_err(o, torch.from_numpy(z[f"sd_out{i}"])) < 1e-10, i
+    total, _ = O.sd_loss(outs[:4], outs[4:], labels, 0.1, 1e-6, 3.0)
+    total.backward()
+    assert _digest_err(sd, z, "sd_g_") < 1e-9

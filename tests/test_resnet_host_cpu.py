@@ -22,6 +22,7 @@ def emulated(monkeypatch):
     monkeypatch.setattr(ehgr_b200._lib, "call", abi_emulator.call)
     monkeypatch.setattr(ehgr_b200._lib, "require_cuda", lambda *t: None)
     monkeypatch.setattr(ehgr_b200._lib, "stream_ptr", lambda device=None: 0)
+    monkeypatch.setattr(ehgr_b200._lib, "on_gpu", lambda t: True)      # the wrappers take the library's path for host tensors
     # the oracle's differentiable shift stands in for the shift kernel in the eager (reference-side) run
     monkeypatch.setattr(ehgr_b200.TemporalShift, "shift",
                         staticmethod(lambda x, n_segment, fold_div=3, inplace=False: O.temporal_shift(x, n_segment, fold_div)))
@@ -122,3 +123,68 @@ def test_unsupported_trees_are_named(emulated):
         E.action.make_temporal_shift(net, 4, n_div=8)
     ok, why = R.supported(net)
     assert not ok and "Action" in why
+
+
+def _wrapper(E, cls_mod, T, num_class, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return cls_mod.TSN(num_class, T, 'RGB', base_model='resnet50', pretrain=None, dropout=0.5, partial_bn=False, is_shift=True,
+                           shift_div=8, consensus_type='avg', fc_lr5=True, img_feature_dim=224, temporal_module='tsm',
+                           print_spec=False, **kw)
+
+
+def _no_dropout(model):
+    model.train()
+    for d in model.modules():
+        if isinstance(d, nn.Dropout):
+            d.eval()
+    return model
+
+
+def test_mtmm_wrapper_on_resnet50_matches_the_oracle(emulated):
+    """tsn_mtmm.TSN.forward on TSM-ResNet-50 (backbone through resnet_ops, classifier head, depth decoder over 2048 channels)
+    against oracle.resnet_mtmm_forward — the restatement pinned to the UNMODIFIED reference wrapper models_MTMM.TSN
+    (tests/golden/resnet_wrappers.npz): outputs and every parameter gradient."""
+    import torch.nn.functional as F
+    E = emulated
+    T, cls, size = 2, 6, 64
+    sd0 = O.build_resnet_mtmm_state(cls, "tsm", seed=8)
+    model = _wrapper(E, E.tsn_mtmm, T, cls, modal='rgb_depth')
+    model.load_state_dict(sd0, strict=True)
+    _no_dropout(model)
+    rgb, depth, labels = O.synthetic_clip_batch(2, T, size, cls, seed=9)
+    with E.fused.compute_dtype(torch.float32):
+        logits, dpred = model(rgb)
+    gt = F.interpolate(depth.view(-1, 1, size, size), tuple(dpred.shape[-2:]), mode='bilinear')
+    (F.cross_entropy(logits, labels) + 0.01 * F.mse_loss(dpred, gt)).backward()
+    sd64 = O.clone_state(sd0, dtype=torch.float64)
+    ol, od = O.resnet_mtmm_forward(rgb.double(), sd64, T, "tsm", 8, True)
+    (F.cross_entropy(ol, labels) + 0.01 * F.mse_loss(od, gt.double())).backward()
+    assert tuple(dpred.shape) == tuple(od.shape) == (2 * T, 1, 16, 16)
+    assert rel_err(logits, ol) < 1e-4 and rel_err(dpred, od) < 1e-4
+    check_grads_up_to_relu_flips(model.named_parameters(), {k: v.grad for k, v in sd64.items() if v.is_floating_point()})
+
+
+def test_sd_wrapper_on_resnet50_matches_the_oracle(emulated):
+    """tsn_sd.TSN.forward on TSM-ResNet-50: layer1-3 taps of ONE resnet_ops pass feed the SepConv exit heads (fused chains
+    of depthwise / pointwise stages), eight outputs as models/models_SD.py:431 — against oracle.resnet_sd_forward (pinned to
+    the unmodified models_SD.TSN) with the SD loss of train_sd.py:227-265."""
+    E = emulated
+    T, cls, size = 2, 6, 64
+    sd0 = O.build_resnet_sd_state(cls, "tsm", seed=8)
+    model = _wrapper(E, E.tsn_sd, T, cls)
+    model.load_state_dict(sd0, strict=True)
+    _no_dropout(model)
+    rgb, _, labels = O.synthetic_clip_batch(2, T, size, cls, seed=9)
+    with E.fused.compute_dtype(torch.float32):
+        outs = model(rgb)
+    total, _ = O.sd_loss(outs[:4], outs[4:], labels, 0.1, 1e-6, 3.0)      # the loss as torch ops on OUR outputs
+    total.backward()
+    sd64 = O.clone_state(sd0, dtype=torch.float64)
+    oouts = O.resnet_sd_forward(rgb.double(), sd64, T, "tsm", 8, True)
+    ototal, _ = O.sd_loss(oouts[:4], oouts[4:], labels, 0.1, 1e-6, 3.0)
+    ototal.backward()
+    assert [tuple(o.shape) for o in outs] == [tuple(o.shape) for o in oouts] == [(2, cls)] * 4 + [(2 * T, 2048, 1, 1)] * 4
+    for i, (a, b) in enumerate(zip(outs, oouts)):
+        assert rel_err(a, b) < 2e-4, i
+    assert abs(total.item() - ototal.item()) < 1e-4 * abs(ototal.item())
+    check_grads_up_to_relu_flips(model.named_parameters(), {k: v.grad for k, v in sd64.items() if v.is_floating_point()})
