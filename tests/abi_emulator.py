@@ -418,6 +418,29 @@ def ehgr_mtmm_loss(logits, labels, pred, depth_gt, depth_weight, loss_out, dlogi
     out[2] += float(mse)
 
 
+def ehgr_sd_loss(logits, feats, labels, alpha, beta, temperature, terms_out, dlogits, dfeats, n, k, rows, f, stream):
+    """K13 (train_sd.py:178-193,227-265): total = (1-a) * sum_4 CE(z_i, y) + a * T^2 * sum_3 KD(z_i, softmax(z_0 / T).detach())
+    + b * sum_3 sum((f_i - f_0.detach())^2 * [(f_i > 0) | (f_0 > 0)]);  terms = total, 4 CE, 3 KD (x T^2), 3 feature sums."""
+    import torch
+    import torch.nn.functional as TF
+    y = _t(arr(labels, (n,), np.int64))
+    Z = [_t(arr(p, (n, k)).copy()).requires_grad_(True) for p in logits]
+    Fs = [_t(arr(p, (rows, f)).copy()).requires_grad_(True) for p in feats]
+    with torch.enable_grad():
+        ce = [TF.cross_entropy(z, y) for z in Z]
+        soft = torch.softmax(Z[0] / temperature, dim=1).detach()
+        kd = [-(torch.log_softmax(z / temperature, dim=1) * soft).sum(1).mean() * temperature ** 2 for z in Z[1:]]
+        f0 = Fs[0].detach()
+        fe = [(((fi - f0) ** 2) * ((fi > 0) | (f0 > 0)).float()).sum() for fi in Fs[1:]]
+        total = (1 - alpha) * sum(ce) + alpha * sum(kd) + beta * sum(fe)
+        grads = torch.autograd.grad(total, Z + Fs[1:])
+    for p, g in zip(dlogits, grads[:4]):
+        arr(p, (n, k))[...] = g.numpy()
+    for p, g in zip(dfeats, grads[4:]):
+        arr(p, (rows, f))[...] = g.numpy()
+    arr(terms_out, (11,))[...] += np.array([float(total)] + [float(v) for v in ce + kd + fe], F32)
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("ehgr_")}
 
 

@@ -98,3 +98,67 @@ def test_mtmm_wrapper_decoder_and_taps(emulated):
     assert [tuple(t.shape[1:]) for t in taps] == [(24, 16, 16), (32, 8, 8), (96, 4, 4), (1280, 2, 2)]
     sum((t.float() ** 2).mean() for t in taps).backward()
     assert model.base_model.features[0][0].weight.grad.abs().sum() > 0
+
+
+def _model(E, mod, T, cls, **kw):
+    with _quiet():
+        m = mod.TSN(cls, T, 'RGB', base_model='mobilenetv2', pretrain=None, dropout=0.5, partial_bn=False, is_shift=True,
+                    shift_div=8, consensus_type='avg', fc_lr5=True, img_feature_dim=224, temporal_module='tsm',
+                    print_spec=False, **kw)
+    m.train()
+    for d in m.modules():
+        if isinstance(d, torch.nn.Dropout):
+            d.eval()
+    return m
+
+
+def test_sd_wrapper_and_fused_sd_loss_match_the_oracle(emulated):
+    """tsn_sd.TSN.forward (one chain pass with three taps, SepConv exit heads as fused chains, K10 heads) and
+    losses.sd_loss (K13: forward + gradients from one launch) against oracle.sd_forward / sd_loss (train_sd.py:227-265)."""
+    E = emulated
+    T, cls = 2, 6
+    sd0 = O.build_sd_state(cls, "tsm", 8, seed=5)
+    model = _model(E, E.tsn_sd, T, cls)
+    model.load_state_dict(sd0, strict=True)
+    rgb, _, labels = O.synthetic_clip_batch(2, T, 64, cls, seed=6)
+    with E.fused.compute_dtype(torch.float32):
+        outs = model(rgb)
+        total, terms = E.losses.sd_loss(outs[:4], outs[4:], labels, 0.1, 1e-6, 3.0)
+    total.backward()
+    sd64 = O.clone_state(sd0, dtype=torch.float64)
+    oouts = O.sd_forward(rgb.double(), sd64, T, "tsm", 8, True)
+    ototal, oterms = O.sd_loss(oouts[:4], oouts[4:], labels, 0.1, 1e-6, 3.0)
+    ototal.backward()
+    for i, (a, b) in enumerate(zip(outs, oouts)):
+        assert a.shape == b.shape and rel_err(a, b) < 2e-4, i
+    assert abs(total.item() - ototal.item()) < 1e-4 * abs(ototal.item())
+    assert rel_err(terms, torch.as_tensor([float(v) for v in oterms["ce"] + oterms["kd"] + oterms["feat"]])) < 1e-3
+    check_grads_up_to_relu_flips(model.named_parameters(), {k: v.grad for k, v in sd64.items() if v.is_floating_point()})
+
+
+def test_mtmm_sd_wrapper_and_combined_loss_match_the_oracle(emulated):
+    """tsn_mtmm_sd.TSN.forward (ten outputs, models/models_MTMM_SD.py:431-532) and losses.mtmm_sd_loss
+    (train_mtmm_sd.py:240-293) against the oracle's mtmm_sd_forward / mtmm_sd_loss."""
+    E = emulated
+    T, cls = 2, 6
+    sd0 = O.build_mtmm_sd_state(cls, "tsm", 8, seed=5)
+    model = _model(E, E.tsn_mtmm_sd, T, cls, modal='rgb_depth')
+    model.load_state_dict(sd0, strict=True)
+    rgb, depth, labels = O.synthetic_clip_batch(2, T, 64, cls, seed=6)
+    with E.fused.compute_dtype(torch.float32):
+        outs = model(rgb)
+        total, terms, mse = E.losses.mtmm_sd_loss(outs[:4], outs[4:8], outs[9], depth, labels, 0.1, 1e-6, 3.0)
+    total.backward()
+    sd64 = O.clone_state(sd0, dtype=torch.float64)
+    oouts = O.mtmm_sd_forward(rgb.double(), sd64, T, "tsm", 8, True)
+    assert len(outs) == len(oouts) == 10
+    for i, (a, b) in enumerate(zip(outs, oouts)):
+        assert a.shape == b.shape and rel_err(a, b) < 2e-4, i
+    # train_mtmm_sd.py:240-293 at this resolution (the oracle's mtmm_sd_loss resizes 224 -> 56)
+    gt = F.interpolate(depth.double().view(-1, 1, 64, 64), (16, 16), mode='bilinear')
+    osd_total, _ = O.sd_loss(oouts[:4], oouts[4:8], labels, 0.1, 1e-6, 3.0)
+    ototal = osd_total + 0.9 * 0.01 * F.mse_loss(oouts[9], gt)
+    ototal.backward()
+    assert abs(total.item() - ototal.item()) < 1e-4 * abs(ototal.item())
+    named = [(k, p) for k, p in model.named_parameters() if not k.startswith("local_decoder.")]   # outs[8] is not in the loss
+    check_grads_up_to_relu_flips(named, {k: v.grad for k, v in sd64.items() if v.is_floating_point()})

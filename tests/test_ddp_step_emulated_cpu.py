@@ -3,7 +3,9 @@
 ResNet function write parameter gradients straight into GradBuckets' flat buffer and report finished parameters, buckets
 are all-reduced while backward continues), SGD.  Checked per rank: the averaged gradients equal the mean of the oracle's
 gradients on the two ranks' shards, replicas stay in sync, and the parameters move by exactly -lr * (that gradient) on
-the first step.  Both backbones: TSM-MobileNetV2 (headline path) and TSM-ResNet-50 (N3)."""
+the first step.  Cases: the MTMM step on TSM-MobileNetV2 (headline path) and on TSM-ResNet-50 (N3), and the SD step on
+TSM-MobileNetV2 (its first bucket mixes several autograd Functions — the exit heads and the end of the backbone — which is
+where a double-counted parameter let replicas diverge on 2 GPUs in round 2)."""
 import contextlib
 import io
 import os
@@ -23,7 +25,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, backbone, out):
+def _worker(rank, world, port, case, out):
     try:
         here = os.path.dirname(os.path.abspath(__file__))
         for p in (here, os.path.dirname(here)):
@@ -42,29 +44,43 @@ def _worker(rank, world, port, backbone, out):
         E._lib.stream_ptr = lambda device=None: 0
         E._lib.on_gpu = lambda t: True         # the wrappers take the library's path for host tensors
         T, cls, size, lr = 2, 5, 64, 0.01
+        workload, backbone = case.split("-")
         resnet = backbone == "resnet50"
-        sd0 = (O.build_resnet_mtmm_state(cls, "tsm", seed=4) if resnet else O.build_mtmm_state(cls, "tsm", 8, seed=4))
+        sd_mode = workload == "sd"
+        if sd_mode:
+            sd0 = O.build_sd_state(cls, "tsm", 8, seed=4)
+        else:
+            sd0 = (O.build_resnet_mtmm_state(cls, "tsm", seed=4) if resnet else O.build_mtmm_state(cls, "tsm", 8, seed=4))
+        common = dict(base_model=backbone, pretrain=None, dropout=0.5, partial_bn=False, is_shift=True, shift_div=8,
+                      consensus_type='avg', fc_lr5=True, img_feature_dim=224, temporal_module='tsm', print_spec=False)
         with contextlib.redirect_stdout(io.StringIO()):
-            model = E.tsn_mtmm.TSN(cls, T, 'RGB', base_model=backbone, pretrain=None, dropout=0.5, partial_bn=False,
-                                   is_shift=True, shift_div=8, consensus_type='avg', fc_lr5=True, img_feature_dim=224,
-                                   modal='rgb_depth', temporal_module='tsm', print_spec=False)
+            model = (E.tsn_sd.TSN(cls, T, 'RGB', **common) if sd_mode else
+                     E.tsn_mtmm.TSN(cls, T, 'RGB', modal='rgb_depth', **common))
         model.load_state_dict(sd0, strict=True)
         model.train()
         for d in model.modules():
             if isinstance(d, torch.nn.Dropout):
                 d.eval()
-        step = E.train_step.MTMMTrainStep(model, lr=lr, momentum=0.9, weight_decay=0.0, compute_dtype=torch.float32, n_buckets=3)
+        step_cls = E.train_step.SDTrainStep if sd_mode else E.train_step.MTMMTrainStep
+        step = step_cls(model, lr=lr, momentum=0.9, weight_decay=0.0, compute_dtype=torch.float32, n_buckets=3)
         assert step.buckets.world == world
         before = {k: p.detach().clone() for k, p in model.named_parameters()}
         shards = [O.synthetic_clip_batch(2, T, size, cls, seed=20 + r) for r in range(world)]
         rgb, depth, labels = shards[rank]
-        loss = step.run(rgb, depth, labels)
+        loss = step.run(rgb, labels) if sd_mode else step.run(rgb, depth, labels)
         assert torch.isfinite(loss)
         # reference: the mean over the ranks of the oracle's gradients on each shard (fp64)
         mean_grad = None
         for r in range(world):
             sd64 = O.clone_state(sd0, dtype=torch.float64)
             x5, dep, lab = shards[r][0].double(), shards[r][1].double(), shards[r][2]
+            if sd_mode:
+                # SDTrainStep scales beta by the world size: the feature term is a SUM over the local batch (train_sd.py:191-193)
+                oo = O.sd_forward(x5, sd64, T, "tsm", 8, True)
+                O.sd_loss(oo[:4], oo[4:], lab, 0.1, 1e-6 * world, 3.0)[0].backward()
+                g = {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.grad is not None}
+                mean_grad = g if mean_grad is None else {k: mean_grad[k] + g[k] for k in g}
+                continue
             if resnet:
                 f = O.resnet_features(x5.view((-1, 3, size, size)), sd64, O.RESNET50_LAYERS, "tsm", T, 8, True)[-1]
                 z = F.linear(f.mean((2, 3)), sd64["new_fc.weight"], sd64["new_fc.bias"])
@@ -93,12 +109,12 @@ def _worker(rank, world, port, backbone, out):
         raise
 
 
-@pytest.mark.parametrize("backbone", ["mobilenetv2", "resnet50"])
-def test_data_parallel_step_world2_gloo(backbone):
+@pytest.mark.parametrize("case", ["mtmm-mobilenetv2", "mtmm-resnet50", "sd-mobilenetv2"])
+def test_data_parallel_step_world2_gloo(case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, backbone, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
