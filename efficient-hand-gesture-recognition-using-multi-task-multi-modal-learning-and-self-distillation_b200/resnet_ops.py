@@ -236,6 +236,10 @@ class _ResNetFunction(torch.autograd.Function):
         stem_saved = (raw0, vec0, tr0, pool_idx, (ho, wo), patches)
 
         saved, outputs, tap_blocks = [], [], []
+        if 0 in taps:                     # the max-pool output (models/models_MTMM_SD.py:431-476 feeds it to local_decoder)
+            outputs.append(cur)
+            tap_blocks.append(-1)
+            cur = cur.detach()            # layer1.0 saves an alias, not the Function output
         p_i = 3
         for bi, b in enumerate(plan.blocks):
             w1, g1, b1, w2, g2, b2, w3, g3, b3 = params[p_i:p_i + 9]
@@ -456,6 +460,13 @@ class _ResNetFunction(torch.autograd.Function):
                 sink.mark_done([q for q, sv in zip(params[pb:pb + n_p], sunk[pb:pb + n_p]) if sv is not None])
         # ---- stem: max-pool adjoint -> bn1 + ReLU backward (BNBWD operand) -> 7x7 weight gradient
         raw0, vec0, tr0, pool_idx, (ho, wo), patches = ctx.stem_saved
+        gt = gout_of.get(-1)              # gradient of the tapped max-pool output
+        if gt is not None:
+            gt = fused._as_nhwc(gt, dt)
+            tmp = torch.empty_like(g)
+            _lib.call("ehgr_row_apply", ctypes.byref(op_plain(g)), gt.data_ptr(), tmp.data_ptr(), g.numel() // 64, 64, code, sp,
+                      algo_bytes=3 * g.numel() * es)
+            g = tmp
         g_act = torch.empty_like(raw0)
         _lib.call("ehgr_maxpool3_bwd", g.data_ptr(), pool_idx.data_ptr(), g_act.data_ptr(), nt, ho, wo, 64, code, sp,
                   algo_bytes=g.numel() * (es + 1) + g_act.numel() * es)
@@ -479,11 +490,12 @@ class _ResNetFunction(torch.autograd.Function):
 
 def resnet_features(model, x, taps: Sequence[int] = ()):
     """conv1 .. layer4 of a torchvision Bottleneck ResNet -> [NT, 2048, H/32, W/32] (NHWC strides, compute dtype).  With
-    ``taps`` (stage numbers among 1, 2, 3) returns a tuple: those stage outputs (ascending) followed by the layer4 output."""
+    ``taps`` (stage numbers among 1, 2, 3; 0 = the max-pool output) returns a tuple: those outputs (ascending) followed by
+    the layer4 output."""
     _lib.require_cuda(x)
     plan = plan_of(model)
     taps = tuple(sorted(set(int(t) for t in taps)))
-    if any(t not in (1, 2, 3) for t in taps):
-        raise ValueError("taps are stage numbers among 1, 2, 3")
+    if any(t not in (0, 1, 2, 3) for t in taps):
+        raise ValueError("taps are stage numbers among 1, 2, 3 (0 = the max-pool output)")
     outs = _ResNetFunction.apply(plan, fused._STATE["dtype"], taps, x, *_plan_params(plan))
     return outs[0] if not taps else outs

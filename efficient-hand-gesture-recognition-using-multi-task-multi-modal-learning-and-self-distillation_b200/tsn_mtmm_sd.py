@@ -17,6 +17,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .tsn_sd import MBV2_TAP_CHANNELS, TSN as _SDTSN
 
 
@@ -61,6 +62,9 @@ class TSN(_SDTSN):
         if self.base_model_name == 'mobilenetv2':
             t1, t2, t3, fmap = self._taps(x)
             local_in = t1
+        elif _lib.on_gpu(x) and self._fused_resnet():      # N3: one pass of resnet_ops with the max-pool output tapped too
+            from . import resnet_ops
+            local_in, t1, t2, t3, fmap = resnet_ops.resnet_features(self.base_model, x, taps=(0, 1, 2, 3))
         else:
             bm = self.base_model
             local_in = bm.maxpool(bm.relu(bm.bn1(bm.conv1(x))))

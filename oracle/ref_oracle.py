@@ -623,12 +623,13 @@ def resnet_bottleneck(x, sd: SD, prefix: str, stride: int, temporal: str, n_segm
 
 
 def resnet_features(x, sd: SD, layers=RESNET50_LAYERS, temporal: str = "tsm", n_segment: int = 8, shift_div: int = 8,
-                    bn_training: bool = True, prefix: str = "base_model"):
+                    bn_training: bool = True, prefix: str = "base_model", with_stem: bool = False):
     """ResNet._forward_impl up to layer4: conv1 7x7/2 -> bn1 -> relu -> maxpool 3x3/2 -> layer1..4.  Returns the four stage
-    outputs (the taps of models/models_SD.py:364-431; layer4 is the map models/models_MTMM.py:70-77 decodes)."""
+    outputs (the taps of models/models_SD.py:364-431; layer4 is the map models/models_MTMM.py:70-77 decodes), preceded by
+    the max-pool output when `with_stem` (the tensor models/models_MTMM_SD.py:431-476 hands to local_decoder)."""
     y = F.relu(_bn(F.conv2d(x, sd[prefix + ".conv1.weight"], stride=2, padding=3), sd, prefix + ".bn1", bn_training))
     y = F.max_pool2d(y, kernel_size=3, stride=2, padding=1)
-    outs = []
+    outs = [y] if with_stem else []
     for si, n_blocks in enumerate(layers, 1):
         for bi in range(n_blocks):
             stride = 2 if (bi == 0 and si > 1) else 1
@@ -719,10 +720,12 @@ def resnet_mtmm_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", sh
 
 
 def resnet_sd_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8, bn_training: bool = True,
-                      layers=RESNET50_LAYERS):
+                      layers=RESNET50_LAYERS, taps=None):
     """models_SD.TSN.forward: -> (output, mid1, mid2, mid3, final_fea, fea1, fea2, fea3), taps after layer1 / 2 / 3."""
-    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
-    t1, t2, t3, t4 = resnet_features(x, sd, layers, temporal, num_segments, shift_div, bn_training)
+    if taps is None:
+        x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+        taps = resnet_features(x, sd, layers, temporal, num_segments, shift_div, bn_training)
+    t1, t2, t3, t4 = taps
     mids, feas = [], []
     for (name, chans), y, fc in zip(RESNET_SD_HEADS, (t1, t2, t3), ("middle_fc1", "middle_fc2", "middle_fc3")):
         for j in range(len(chans) - 1):
@@ -746,3 +749,24 @@ def build_resnet_sd_state(num_class: int = 83, temporal: str = "tsm", seed: int 
         sd[fc + ".weight"] = torch.from_numpy((rs.standard_normal((num_class, 2048)) * 0.02).astype(np.float32))
         sd[fc + ".bias"] = torch.from_numpy((rs.standard_normal(num_class) * 0.02).astype(np.float32))
     return sd
+
+
+def build_resnet_mtmm_sd_state(num_class: int = 83, temporal: str = "tsm", seed: int = 0) -> SD:
+    """models_MTMM_SD.TSN(base_model='resnet50', modal='rgb_depth'): the SD network + local_decoder (64, 32, 1) on the
+    max-pool output + global_decoder (2048, 256, 32, 1) on layer4 (models/models_MTMM_SD.py:226-249)."""
+    sd = build_resnet_sd_state(num_class, temporal, seed)
+    rs = np.random.RandomState(seed + 313)
+    convt_decoder_state(sd, "local_decoder", (64, 32, 1), rs)
+    convt_decoder_state(sd, "global_decoder", (2048, 256, 32, 1), rs)
+    return sd
+
+
+def resnet_mtmm_sd_forward(x5, sd: SD, num_segments: int, temporal: str = "tsm", shift_div: int = 8, bn_training: bool = True):
+    """The ten tensors of models_MTMM_SD.TSN.forward (:522-523) from ONE backbone pass (the reference runs the backbone
+    twice, by hand :431-476 and through a torch.fx extractor :492; both passes compute the same activations, only the
+    BatchNorm running statistics are updated twice there)."""
+    x = x5.view((-1, 3) + tuple(x5.shape[-2:]))
+    pooled, t1, t2, t3, t4 = resnet_features(x, sd, RESNET50_LAYERS, temporal, num_segments, shift_div, bn_training, with_stem=True)
+    outs = resnet_sd_forward(x5, sd, num_segments, temporal, shift_div, bn_training, taps=(t1, t2, t3, t4))
+    return (*outs, convt_decoder(pooled, sd, "local_decoder", 2, bn_training),
+            convt_decoder(t4, sd, "global_decoder", 3, bn_training))

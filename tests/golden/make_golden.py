@@ -534,6 +534,37 @@ def golden_resnet_wrappers():
         assert (osd[k].grad - p.grad).abs().max().item() <= 1e-9 * gmax, k
     for k, v in grad_digest({k: p.grad for k, p in ref.named_parameters()}).items():
         out[f"sd_g_{k}"] = v
+    # ---- MTMM+SD (models/models_MTMM_SD.py: ResNet only; two backbone passes there, one in the oracle)
+    import models.models_MTMM_SD as MS
+    sd = O.build_resnet_mtmm_sd_state(cfg["num_class"], "none", seed=cfg["seed"])
+    with _quiet():
+        ref = MS.TSN(cfg["num_class"], cfg["T"], 'RGB', modal='rgb_depth', **common)
+    load(ref, sd)
+    outs = ref(rgb.double())
+    gt = F.interpolate(depth.double().view(-1, 1, cfg["size"], cfg["size"]), tuple(outs[9].shape[-2:]), mode='bilinear')
+
+    def combined(o):            # train_mtmm_sd.py:240-293 (+ a term on local_depth_out so that local_decoder gets a gradient)
+        loss = F.cross_entropy(o[0], labels) + 0.01 * F.mse_loss(o[9], gt)
+        ce = sum(F.cross_entropy(z, labels) for z in o[1:4])
+        temp4 = torch.softmax(o[0] / _A.temperature, dim=1)
+        kd = sum(kd_loss_function(z, temp4.detach(), _A) * 9.0 for z in o[1:4])
+        fe = sum(feature_loss_function(f, o[4].detach()) for f in o[5:8])
+        return 0.9 * (loss + ce) + 0.1 * kd + 1e-6 * fe + 0.01 * (o[8] ** 2).mean()
+    combined(outs).backward()
+    osd = O.clone_state(sd, dtype=torch.float64)
+    oouts = O.resnet_mtmm_sd_forward(rgb.double(), osd, cfg["T"], "none", 8, True)
+    combined(oouts).backward()
+    assert len(outs) == len(oouts) == 10
+    for i, (a, b) in enumerate(zip(oouts, outs)):
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 1e-10 * max(b.abs().max().item(), 1e-30), i
+        if i not in (5, 6, 7):
+            out[f"mtmmsd_out{i}"] = b.detach().numpy()
+    named = {k: p for k, p in ref.named_parameters() if not k.startswith("feature_extractor.") and p.grad is not None}
+    gmax = max(p.grad.abs().max().item() for p in named.values())
+    for k, p in named.items():
+        assert (osd[k].grad - p.grad).abs().max().item() <= 1e-9 * gmax, k
+    for k, v in grad_digest({k: p.grad for k, p in named.items()}).items():
+        out[f"mtmmsd_g_{k}"] = v
     np.savez_compressed(HERE / "resnet_wrappers.npz", **out)
 
 

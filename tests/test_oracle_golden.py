@@ -306,3 +306,20 @@ def test_resnet50_mtmm_and_sd_oracles_match_the_unmodified_reference_wrappers():
     total, _ = O.sd_loss(outs[:4], outs[4:], labels, 0.1, 1e-6, 3.0)
     total.backward()
     assert _digest_err(sd, z, "sd_g_") < 1e-9
+
+
+def test_resnet50_mtmm_sd_oracle_matches_the_unmodified_reference_wrapper():
+    """models_MTMM_SD.TSN (ResNet only in the reference, two backbone passes there): the oracle's single-pass restatement
+    gives the same ten tensors and the same gradients of the combined loss (train_mtmm_sd.py:240-293), fp64."""
+    z = np.load(GOLDEN / "resnet_wrappers.npz")
+    cfg = RESNET_FIXTURE
+    rgb, depth, labels = O.synthetic_clip_batch(cfg["clips"], cfg["T"], cfg["size"], cfg["num_class"], seed=cfg["in_seed"])
+    sd = O.clone_state(O.build_resnet_mtmm_sd_state(cfg["num_class"], "none", seed=cfg["seed"]), dtype=torch.float64)
+    o = O.resnet_mtmm_sd_forward(rgb.double(), sd, cfg["T"], "none", 8, True)
+    assert len(o) == 10
+    for i in (0, 1, 2, 3, 4, 8, 9):
+        assert rel_err(o[i], torch.from_numpy(z[f"mtmmsd_out{i}"])) < 1e-10, i
+    gt = F.interpolate(depth.double().view(-1, 1, cfg["size"], cfg["size"]), tuple(o[9].shape[-2:]), mode='bilinear')
+    sd_total, _ = O.sd_loss(o[:4], o[4:8], labels, 0.1, 1e-6, 3.0)
+    (sd_total + 0.9 * 0.01 * F.mse_loss(o[9], gt) + 0.01 * (o[8] ** 2).mean()).backward()
+    assert _digest_err(sd, z, "mtmmsd_g_") < 1e-9

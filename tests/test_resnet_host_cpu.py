@@ -188,3 +188,32 @@ def test_sd_wrapper_on_resnet50_matches_the_oracle(emulated):
         assert rel_err(a, b) < 2e-4, i
     assert abs(total.item() - ototal.item()) < 1e-4 * abs(ototal.item())
     check_grads_up_to_relu_flips(model.named_parameters(), {k: v.grad for k, v in sd64.items() if v.is_floating_point()})
+
+
+def test_mtmm_sd_wrapper_on_resnet50_matches_the_oracle(emulated):
+    """tsn_mtmm_sd.TSN.forward on TSM-ResNet-50 (the only backbone the reference's models_MTMM_SD.py supports): ONE
+    resnet_ops pass with the max-pool output and layer1-3 tapped, exit heads, ConvTranspose decoders (library modules);
+    ten outputs and the gradients of the combined loss (train_mtmm_sd.py:240-293) against the oracle."""
+    import torch.nn.functional as F
+    E = emulated
+    T, cls, size = 2, 6, 64
+    sd0 = O.build_resnet_mtmm_sd_state(cls, "tsm", seed=8)
+    model = _wrapper(E, E.tsn_mtmm_sd, T, cls, modal='rgb_depth')
+    model.load_state_dict(sd0, strict=True)
+    _no_dropout(model)
+    rgb, depth, labels = O.synthetic_clip_batch(2, T, size, cls, seed=9)
+    with E.fused.compute_dtype(torch.float32):
+        outs = model(rgb)
+    assert len(outs) == 10 and tuple(outs[8].shape) == (2 * T, 1, size, size) and tuple(outs[9].shape) == (2 * T, 1, size // 4, size // 4)
+    gt = F.interpolate(depth.view(-1, 1, size, size), (size // 4, size // 4), mode='bilinear')
+
+    def total_of(o, gt_):       # combined loss + a term on the local decoder so that the tapped max-pool output gets a gradient
+        t, _ = O.sd_loss(o[:4], o[4:8], labels, 0.1, 1e-6, 3.0)
+        return t + 0.9 * 0.01 * F.mse_loss(o[9], gt_) + 0.01 * (o[8] ** 2).mean()
+    total_of(outs, gt).backward()
+    sd64 = O.clone_state(sd0, dtype=torch.float64)
+    oouts = O.resnet_mtmm_sd_forward(rgb.double(), sd64, T, "tsm", 8, True)
+    total_of(oouts, gt.double()).backward()
+    for i, (a, b) in enumerate(zip(outs, oouts)):
+        assert a.shape == b.shape and rel_err(a, b) < 2e-4, i
+    check_grads_up_to_relu_flips(model.named_parameters(), {k: v.grad for k, v in sd64.items() if v.is_floating_point()})
