@@ -69,6 +69,11 @@ def rowop(ref, M, C):
         if op.relu6:
             g = g * _mask(r * arr(op.scale, (C,)) + arr(op.shift, (C,)), op.relu6)
         return (arr(op.ca, (C,)) * g + arr(op.cb, (C,)) * r + arr(op.cc, (C,))).astype(F32)
+    if mode == 4:                       # GATE: in1 * (3 + g1[m] + g2[m / hw, c] + g3[m / hw, c])
+        fr = M // op.hw
+        x = arr(op.in1, (fr, op.hw, C))
+        g = 3.0 + arr(op.in2, (fr, op.hw, 1)) + arr(op.scale, (fr, 1, C)) + arr(op.shift, (fr, 1, C))
+        return (x * g).reshape(M, C).astype(F32)
     if mode == 5:
         H, W, cin, up = op.cv_h, op.cv_w, op.cv_cin, op.cv_up
         assert C == 9 * cin and op.hw == H * W
@@ -439,6 +444,150 @@ def ehgr_sd_loss(logits, feats, labels, alpha, beta, temperature, terms_out, dlo
     for p, g in zip(dfeats, grads[4:]):
         arr(p, (rows, f))[...] = g.numpy()
     arr(terms_out, (11,))[...] += np.array([float(total)] + [float(v) for v in ce + kd + fe], F32)
+
+
+# ---- K2-K6: ACTION (models/action.py:61-116).  The host (action_ops.py) owns every buffer and only interprets qstats
+# (-> ehgr_bn_finalize), bn3_sums (-> ehgr_bn_bwd_finalize), the three gates (GATE operand) and the gradients; the other
+# workspaces are private to the kernels, so this restatement keeps its own (consistent) meaning for them: `dpool` is the
+# gradient w.r.t. the spatial SUM `pool`, `dg1` stays sum_c gy*xs.
+def _act_dims(a):
+    return a.n, a.t, a.h, a.w, a.c, a.cr
+
+
+def _act_params(a):
+    c, cr = a.c, a.cr
+    shapes = {"shift_w": (c, 1, 3), "p1_w": (1, 1, 3, 3, 3), "p2_squeeze": (cr, c), "p2_conv1": (cr, cr, 3), "p2_expand": (c, cr),
+              "p3_squeeze": (cr, c), "p3_conv1": (cr, 1, 3, 3), "p3_expand": (c, cr)}
+    return {k: _t(arr(getattr(a, k), shp).copy()) for k, shp in shapes.items()}
+
+
+def _act_gates(a, mrow, pool, x3, P):
+    """(g1 [M], g2 [nt, c], g3 [nt, c], s, u, pi) as differentiable torch functions of mrow [M], pool [nt, c] (spatial SUM),
+    x3 [M, cr] (the BatchNorm output of the motion squeeze) and the parameters."""
+    import torch
+    import torch.nn.functional as TF
+    n, t, h, w, c, cr = _act_dims(a)
+    # spatio-temporal excitation (:76-83): sigmoid(conv3d over (t, h, w) of the channel mean)
+    g1 = torch.sigmoid(TF.conv3d(mrow.view(n, 1, t, h, w), P["p1_w"], padding=1)).reshape(-1)
+    # channel excitation (:86-96): spatial mean -> squeeze -> conv1d over t -> ReLU -> expand -> sigmoid
+    sq = (pool / (h * w)).view(n, t, c) @ P["p2_squeeze"].t()                       # [n, t, cr]
+    u = TF.conv1d(sq.transpose(1, 2), P["p2_conv1"], padding=1).transpose(1, 2)      # [n, t, cr]
+    g2 = torch.sigmoid(torch.relu(u) @ P["p2_expand"].t()).reshape(n * t, c)
+    # motion excitation (:99-113): depthwise 3x3 of frame t+1 minus frame t, zero for the last frame
+    x3f = x3.view(n, t, h, w, cr).permute(0, 1, 4, 2, 3)                             # [n, t, cr, h, w]
+    c3 = TF.conv2d(x3f.reshape(n * t, cr, h, w), P["p3_conv1"], padding=1, groups=cr).view(n, t, cr, h, w)
+    d = torch.cat([c3[:, 1:] - x3f[:, :-1], torch.zeros_like(x3f[:, :1])], 1)
+    pi = d.mean((3, 4))                                                              # [n, t, cr]
+    g3 = torch.sigmoid(pi @ P["p3_expand"].t()).reshape(n * t, c)
+    return g1, g2, g3, sq.reshape(n * t, cr), u.reshape(n * t, cr), pi.reshape(n * t, cr)
+
+
+def ehgr_action_xs(a, x, xs, dtype, stream):
+    assert dtype == 0
+    a = _struct(a)
+    n, t, h, w, c, cr = _act_dims(a)
+    X = arr(x, (n, t, h * w, c))
+    wk = arr(a.shift_w, (c, 3))
+    pad = np.zeros((n, t + 2, h * w, c), F32)
+    pad[:, 1:-1] = X
+    Y = pad[:, :-2] * wk[:, 0] + pad[:, 1:-1] * wk[:, 1] + pad[:, 2:] * wk[:, 2]      # conv1d(k=3, padding=1) over t, per channel
+    arr(xs, (n, t, h * w, c))[...] = Y
+    arr(a.mrow, (n * t * h * w,))[...] = Y.mean(-1).reshape(-1)
+    arr(a.pool, (n * t, c))[...] = Y.sum(2).reshape(n * t, c)
+    q = Y.reshape(-1, c) @ arr(a.p3_squeeze, (cr, c)).T
+    arr(a.q, (n * t * h * w, cr))[...] = q
+    _add_stats(a.qstats, q, cr)
+
+
+def ehgr_action_gates(a, stream):
+    import torch
+    a = _struct(a)
+    n, t, h, w, c, cr = _act_dims(a)
+    M = n * t * h * w
+    x3 = _t(arr(a.q, (M, cr)) * arr(a.bn3_scale, (cr,)) + arr(a.bn3_shift, (cr,)))
+    with torch.no_grad():
+        g1, g2, g3, sq, u, pi = _act_gates(a, _t(arr(a.mrow, (M,)).copy()), _t(arr(a.pool, (n * t, c)).copy()), x3, _act_params(a))
+    for name, v, shp in (("g1", g1, (M,)), ("g2", g2, (n * t, c)), ("g3", g3, (n * t, c)), ("s", sq, (n * t, cr)),
+                         ("u", u, (n * t, cr)), ("pi", pi, (n * t, cr))):
+        arr(getattr(a, name), shp)[...] = v.numpy()
+
+
+def ehgr_action_bwd_reduce(a, gy, xs, dtype, stream):
+    assert dtype == 0
+    a = _struct(a)
+    n, t, h, w, c, cr = _act_dims(a)
+    prod = arr(gy, (n * t, h * w, c)) * arr(xs, (n * t, h * w, c))
+    arr(a.dg1, (n * t * h * w,))[...] = prod.sum(-1).reshape(-1)
+    arr(a.dgc, (n * t, c))[...] = prod.sum(1)
+
+
+def _act_small_backward(a):
+    """Gradients of sum(dg1*g1) + sum(dgc*(g2 + g3)) w.r.t. mrow, pool, x3 and the gate parameters."""
+    import torch
+    n, t, h, w, c, cr = _act_dims(a)
+    M = n * t * h * w
+    P = {k: v.requires_grad_(True) for k, v in _act_params(a).items()}
+    mrow = _t(arr(a.mrow, (M,)).copy()).requires_grad_(True)
+    pool = _t(arr(a.pool, (n * t, c)).copy()).requires_grad_(True)
+    x3 = _t(arr(a.q, (M, cr)) * arr(a.bn3_scale, (cr,)) + arr(a.bn3_shift, (cr,))).requires_grad_(True)
+    names = ("p1_w", "p2_squeeze", "p2_conv1", "p2_expand", "p3_conv1", "p3_expand")
+    with torch.enable_grad():
+        g1, g2, g3, _, _, _ = _act_gates(a, mrow, pool, x3, P)
+        obj = (g1 * _t(arr(a.dg1, (M,)))).sum() + ((g2 + g3) * _t(arr(a.dgc, (n * t, c)))).sum()
+        grads = torch.autograd.grad(obj, [mrow, pool, x3] + [P[k] for k in names])
+    return grads[0], grads[1], grads[2], dict(zip(names, grads[3:]))
+
+
+def ehgr_action_bwd_small(a, stream):
+    a = _struct(a)
+    n, t, h, w, c, cr = _act_dims(a)
+    M = n * t * h * w
+    dm, dpool, dx3, pg = _act_small_backward(a)
+    arr(a.dm, (M,))[...] = dm.numpy()
+    arr(a.dpool, (n * t, c))[...] = dpool.numpy()
+    arr(a.dd, (n * t, cr))[...] = 0
+    q = arr(a.q, (M, cr)).astype(np.float64)
+    sums = arr(a.bn3_sums, (2 * cr,), np.float64)
+    sums[:cr] += dx3.numpy().astype(np.float64).sum(0)
+    sums[cr:] += (dx3.numpy().astype(np.float64) * q).sum(0)
+    for k, g in pg.items():
+        arr(getattr(a, "d_" + k), tuple(g.shape))[...] += g.numpy()
+
+
+def ehgr_action_bwd_dxs(a, gy, xs, dxs, dtype, stream):
+    assert dtype == 0
+    a = _struct(a)
+    n, t, h, w, c, cr = _act_dims(a)
+    nt, hw = n * t, h * w
+    M = nt * hw
+    _, _, dx3, _ = _act_small_backward(a)
+    q = arr(a.q, (M, cr))
+    dq = arr(a.bn3_ca, (cr,)) * dx3.numpy() + arr(a.bn3_cb, (cr,)) * q + arr(a.bn3_cc, (cr,))       # BatchNorm backward
+    XS = arr(xs, (M, c))
+    G = 3.0 + arr(a.g1, (nt, hw, 1)) + arr(a.g2, (nt, 1, c)) + arr(a.g3, (nt, 1, c))
+    out = arr(gy, (nt, hw, c)) * G + arr(a.dm, (nt, hw, 1)) / c + arr(a.dpool, (nt, 1, c))
+    arr(dxs, (M, c))[...] = out.reshape(M, c) + dq @ arr(a.p3_squeeze, (cr, c))
+    arr(a.d_p3_squeeze, (cr, c))[...] += dq.T @ XS
+
+
+def ehgr_action_fir_bwd(a, dxs, x, addend, dx, dtype, stream):
+    assert dtype == 0
+    a = _struct(a)
+    n, t, h, w, c, cr = _act_dims(a)
+    D = arr(dxs, (n, t, h * w, c))
+    X = arr(x, (n, t, h * w, c))
+    wk = arr(a.shift_w, (c, 3))
+    dp = np.zeros((n, t + 2, h * w, c), F32)
+    dp[:, 1:-1] = D
+    out = dp[:, 2:] * wk[:, 0] + dp[:, 1:-1] * wk[:, 1] + dp[:, :-2] * wk[:, 2]       # the adjoint of the temporal FIR
+    if addend:
+        out = out + arr(addend, (n, t, h * w, c))
+    arr(dx, (n, t, h * w, c))[...] = out
+    xp = np.zeros((n, t + 2, h * w, c), F32)
+    xp[:, 1:-1] = X
+    gw = arr(a.d_shift_w, (c, 3))
+    for k in range(3):
+        gw[:, k] += (D * xp[:, k:k + t]).sum((0, 1, 2))
 
 
 _TABLE = {k: v for k, v in globals().items() if k.startswith("ehgr_")}

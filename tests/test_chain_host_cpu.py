@@ -29,7 +29,7 @@ def _quiet():
     return contextlib.redirect_stdout(io.StringIO())
 
 
-@pytest.mark.parametrize("temporal,train_bn", [("tsm", True), ("none", True), ("tsm", False)])
+@pytest.mark.parametrize("temporal,train_bn", [("tsm", True), ("none", True), ("tsm", False), ("action", True), ("action", False)])
 def test_mobilenet_chain_and_head_match_the_oracle(emulated, temporal, train_bn):
     E = emulated
     T, cls = 4, 11
@@ -37,7 +37,7 @@ def test_mobilenet_chain_and_head_match_the_oracle(emulated, temporal, train_bn)
     with _quiet():
         model = E.TSN(cls, T, 'RGB', base_model='mobilenetv2', pretrain=None, dropout=0.5, partial_bn=False,
                       is_shift=(temporal != "none"), shift_div=8, consensus_type='avg', fc_lr5=True, img_feature_dim=224,
-                      temporal_module='tsm', print_spec=False)
+                      temporal_module=('action' if temporal == "action" else 'tsm'), print_spec=False)
     model.load_state_dict(sd0, strict=True)
     model.train(train_bn)
     for d in model.modules():
@@ -162,3 +162,36 @@ def test_mtmm_sd_wrapper_and_combined_loss_match_the_oracle(emulated):
     assert abs(total.item() - ototal.item()) < 1e-4 * abs(ototal.item())
     named = [(k, p) for k, p in model.named_parameters() if not k.startswith("local_decoder.")]   # outs[8] is not in the loss
     check_grads_up_to_relu_flips(named, {k: v.grad for k, v in sd64.items() if v.is_floating_point()})
+
+
+@pytest.mark.parametrize("c,train_bn", [(32, True), (96, False)])
+def test_standalone_action_module_matches_the_oracle(emulated, c, train_bn):
+    """Action wrapping a 1x1 convolution, used outside a chain (models/action.py:61-116): the gated tensor is materialised
+    (action_ops._ActionGateFunction) and handed to the wrapped module; against oracle.action_forward."""
+    E = emulated
+    T, h = 4, 6
+    rs = __import__("numpy").random.RandomState(3 + c)
+    sd0 = {}
+    O.action_state(sd0, "m", c, 8, rs)
+    O._conv_entry(sd0, "m.net.weight", (2 * c, c, 1, 1), rs)
+    with _quiet():
+        m = E.Action(torch.nn.Conv2d(c, 2 * c, 1, bias=False), n_segment=T, shift_div=8)
+    m.load_state_dict({k[2:]: v for k, v in sd0.items()}, strict=True)
+    m.train(train_bn)
+    g = torch.Generator().manual_seed(c)
+    x = torch.randn(2 * T, c, h, h, generator=g, requires_grad=True)
+    gy = torch.randn(2 * T, 2 * c, h, h, generator=g)
+    with E.fused.compute_dtype(torch.float32):
+        y = m(x)
+    y.backward(gy)
+    sd64 = O.clone_state(sd0, dtype=torch.float64)
+    x64 = x.detach().double().requires_grad_(True)
+    y64 = O.action_forward(x64, sd64, "m", T, train_bn)
+    y64.backward(gy.double())
+    assert rel_err(y, y64) < 1e-5 and rel_err(x.grad, x64.grad) < 1e-4
+    for k, p in m.named_parameters():
+        ref = sd64["m." + k].grad
+        if ref.abs().max() < 1e-12:
+            assert p.grad.abs().max() < 1e-6, k
+        else:
+            assert rel_err(p.grad, ref) < 2e-4, k
