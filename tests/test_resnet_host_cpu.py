@@ -54,14 +54,27 @@ def _eager(net, x):
     return t1, t2, t3, net.layer4(t3)
 
 
-@pytest.mark.parametrize("shift,train_bn,stem_gemm", [(True, True, False), (False, True, True), (True, False, True)])
+def _set_mode(net, train_bn):
+    """True / False: every BatchNorm in train / eval mode; "partial": TSN.train() with partial_bn (models/models.py:214-230) —
+    every BatchNorm but the first frozen (eval mode, no gradient for its affine parameters)."""
+    net.train(train_bn is not False)
+    if train_bn == "partial":
+        bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]
+        for m in bns[1:]:
+            m.eval()
+            m.weight.requires_grad = False
+            m.bias.requires_grad = False
+
+
+@pytest.mark.parametrize("shift,train_bn,stem_gemm", [(True, True, False), (False, True, True), (True, False, True),
+                                                      (True, "partial", False)])
 def test_resnet_function_matches_autograd(emulated, monkeypatch, shift, train_bn, stem_gemm):
     E = emulated
     R = E.resnet_ops
     monkeypatch.setattr(R, "STEM_GEMM", stem_gemm)        # the 7x7 stem as a patch-matrix GEMM (the bf16 path) or the CUDA-core kernel
     T, size = 2, 48
     net = _net(E, [2, 1, 1, 1], shift, T)
-    net.train(train_bn)
+    _set_mode(net, train_bn)
     ok, why = R.supported(net)
     assert ok, why
     g = torch.Generator().manual_seed(5)
@@ -70,7 +83,7 @@ def test_resnet_function_matches_autograd(emulated, monkeypatch, shift, train_bn
 
     # ---- reference: PyTorch autograd over the same modules, float64
     ref = _net(E, [2, 1, 1, 1], shift, T).double()
-    ref.train(train_bn)
+    _set_mode(ref, train_bn)
     outs_ref = _eager(ref, x.double())
     gouts = [torch.randn(o.shape, generator=g, dtype=torch.float64) / o.numel() ** 0.5 for o in outs_ref]
     torch.autograd.backward(outs_ref, gouts)
@@ -83,8 +96,11 @@ def test_resnet_function_matches_autograd(emulated, monkeypatch, shift, train_bn
         assert o.shape == r.shape
         assert rel_err(o, r) < 2e-4
     torch.autograd.backward(outs, [q.float() for q in gouts])
-    check_grads_up_to_relu_flips(((k, p) for k, p in net.named_parameters() if not k.startswith("fc.")),
-                                 {k: p.grad for k, p in ref.named_parameters() if not k.startswith("fc.")})
+    frozen = [k for k, p in net.named_parameters() if not p.requires_grad]
+    assert (len(frozen) == 2 * (len([m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]) - 1)) == (train_bn == "partial")
+    assert all(dict(net.named_parameters())[k].grad is None for k in frozen)
+    check_grads_up_to_relu_flips(((k, p) for k, p in net.named_parameters() if not k.startswith("fc.") and p.requires_grad),
+                                 {k: p.grad for k, p in ref.named_parameters() if not k.startswith("fc.") and p.requires_grad})
     # BatchNorm buffers follow nn.BatchNorm2d
     for (name, b), (_, br) in zip(net.named_buffers(), ref.named_buffers()):
         if b.dtype.is_floating_point:
