@@ -590,6 +590,135 @@ def ehgr_action_fir_bwd(a, dxs, x, addend, dx, dtype, stream):
         gw[:, k] += (D * xp[:, k:k + t]).sum((0, 1, 2))
 
 
+# ---- the remaining entry points of include/ehgr_b200.h ------------------------------------------------------------------
+def _shift(x, out, n_batch, T, c, hw, fold, dtype, layout, direction):
+    assert dtype == 0
+    if n_batch * T * c * hw == 0:
+        return
+    shape = (n_batch, T, c, hw) if layout == 0 else (n_batch, T, hw, c)
+    X, Y = arr(x, shape), arr(out, shape)
+    if layout == 1:
+        X, Y = X.transpose(0, 1, 3, 2), Y.transpose(0, 1, 3, 2)          # views with the channel axis third
+    Y[...] = 0
+    a, b = (slice(None, -1), slice(1, None)) if direction > 0 else (slice(1, None), slice(None, -1))
+    Y[:, a, :fold] = X[:, b, :fold]
+    Y[:, b, fold:2 * fold] = X[:, a, fold:2 * fold]
+    Y[:, :, 2 * fold:] = X[:, :, 2 * fold:]
+
+
+def ehgr_temporal_shift_fwd(x, out, n_batch, n_segment, c, hw, fold, dtype, layout, stream):
+    """K1: out[:, t, :fold] = x[:, t+1, :fold]; out[:, t, fold:2fold] = x[:, t-1, fold:2fold]; rest copied; zero at the ends."""
+    _shift(x, out, n_batch, n_segment, c, hw, fold, dtype, layout, +1)
+
+
+def ehgr_temporal_shift_bwd(g, gx, n_batch, n_segment, c, hw, fold, dtype, layout, stream):
+    _shift(g, gx, n_batch, n_segment, c, hw, fold, dtype, layout, -1)
+
+
+def ehgr_pw_gemm(a, w, w_is_kn, out, addend, stats, M, K, N, dtype, engine, stream):
+    ehgr_pw_gemm_bn(a, w, None, w_is_kn, out, addend, stats, M, K, N, dtype, engine, None, stream)
+
+
+def ehgr_stem_fwd(x, w, out, stats, nt, h, wd, cout, x_dtype, dtype, stream):
+    ehgr_stem_fwd_bn(x, w, out, stats, nt, h, wd, cout, x_dtype, dtype, None, stream)
+
+
+def ehgr_bn_bwd_reduce(g, raw, scale, shift, relu6, sums, m, c, dtype, stream):
+    ehgr_bn_bwd_reduce_fin(g, raw, scale, shift, relu6, sums, m, c, dtype, None, stream)
+
+
+def ehgr_dw_dgrad(dy, w, da, nt, h, wd, c, stride, dtype, stream):
+    import torch
+    import torch.nn.functional as TF
+    assert dtype == 0
+    ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    X = torch.zeros(nt, c, h, wd, requires_grad=True)
+    DY = _t(rowop(dy, nt * ho * wo, c).reshape(nt, ho, wo, c)).permute(0, 3, 1, 2)
+    with torch.enable_grad():
+        (gx,) = torch.autograd.grad(TF.conv2d(X, _t(arr(w, (c, 1, 3, 3))), stride=stride, padding=1, groups=c), (X,), DY)
+    arr(da, (nt, h, wd, c))[...] = gx.permute(0, 2, 3, 1).numpy()
+
+
+def ehgr_dw_wgrad(dy, a, dw, nt, h, wd, c, stride, dtype, stream):
+    import torch
+    import torch.nn.functional as TF
+    assert dtype == 0
+    ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+    X = _t(rowop(a, nt * h * wd, c).reshape(nt, h, wd, c)).permute(0, 3, 1, 2)
+    Wt = torch.zeros(c, 1, 3, 3, requires_grad=True)
+    DY = _t(rowop(dy, nt * ho * wo, c).reshape(nt, ho, wo, c)).permute(0, 3, 1, 2)
+    with torch.enable_grad():
+        (gw,) = torch.autograd.grad(TF.conv2d(X, Wt, stride=stride, padding=1, groups=c), (Wt,), DY)
+    arr(dw, (c, 1, 3, 3))[...] += gw.numpy()
+
+
+def ehgr_normalize_u8(src, dst, n_planes, channels, plane, mean, stdv, div, dst_dtype, stream):
+    """N4: dst[p][i] = (float(src[p][i]) / div - mean[p % channels]) / std[p % channels], every step in fp32."""
+    assert dst_dtype == 0
+    v = arr(src, (n_planes, plane), np.uint8).astype(F32) / F32(div)
+    ch = np.arange(n_planes) % channels
+    if mean:
+        v = v - arr(mean, (channels,))[ch][:, None]
+    if stdv:
+        v = v / arr(stdv, (channels,))[ch][:, None]
+    arr(dst, (n_planes, plane))[...] = v.astype(F32)
+
+
+def ehgr_temporal_pool_fwd(x, out, n, t_in, frame_elems, dtype, stream):
+    """N4: max over the frames {2t'-1, 2t', 2t'+1} of a clip (max_pool3d (3,1,1) / (2,1,1) / (1,0,0))."""
+    assert dtype == 0
+    t_out = (t_in - 1) // 2 + 1
+    X = arr(x, (n, t_in, frame_elems))
+    pad = np.full((n, t_in + 2, frame_elems), -np.inf, F32)
+    pad[:, 1:-1] = X
+    arr(out, (n, t_out, frame_elems))[...] = np.stack([pad[:, 2 * k:2 * k + 3].max(1) for k in range(t_out)], 1)
+
+
+def ehgr_temporal_pool_bwd(x, g, dx, n, t_in, frame_elems, dtype, stream):
+    assert dtype == 0
+    t_out = (t_in - 1) // 2 + 1
+    X, G = arr(x, (n, t_in, frame_elems)), arr(g, (n, t_out, frame_elems))
+    pad = np.full((n, t_in + 2, frame_elems), -np.inf, F32)
+    pad[:, 1:-1] = X
+    acc = np.zeros((n, t_in + 2, frame_elems), F32)
+    for k in range(t_out):
+        win = pad[:, 2 * k:2 * k + 3]
+        first = win.argmax(1)                       # first maximum of the window (strict '>' scan)
+        for j in range(3):
+            acc[:, 2 * k + j] += G[:, k] * (first == j)
+    arr(dx, (n, t_in, frame_elems))[...] = acc[:, 1:-1]
+
+
+def ehgr_sgd_step(p, g, buf, code, lr_mult, decay_mult, n_groups, lr_dev, momentum, weight_decay, n, ema, ema_decay, p16, stream):
+    """N1: d = g + wd * decay_mult[k] * p; buf = momentum * buf + d; p -= lr * lr_mult[k] * buf (fp32, torch.optim.SGD's
+    order of operations); optional EMA of the stepped parameter (two fp32 products, one fp32 sum)."""
+    assert not p16, "the bf16 mirror only exists on the GPU"
+    P, G, B = arr(p, (n,)), arr(g, (n,)), arr(buf, (n,))
+    k = arr(code, (n,), np.uint8)
+    live = k != 255
+    kk = np.where(live, k, 0).astype(np.int64)
+    lr = arr(lr_dev, (1,))[0]
+    d = (G + (F32(weight_decay) * arr(decay_mult, (n_groups,))[kk]) * P).astype(F32)
+    nb = (F32(momentum) * B + d).astype(F32)
+    npar = (P - (lr * arr(lr_mult, (n_groups,))[kk]).astype(F32) * nb).astype(F32)
+    B[live] = nb[live]
+    P[live] = npar[live]
+    if ema:
+        E = arr(ema, (n,))
+        dec, rest = F32(ema_decay), F32(1.0 - float(ema_decay))      # python scalars reach fp32 as (float)decay, (float)(1. - decay)
+        E[live] = (dec * E + rest * P).astype(F32)[live]
+
+
+def ehgr_ema_update(ema, x, n, decay, is_int64, stream):
+    dec, rest = F32(decay), F32(1.0 - float(decay))
+    if is_int64:
+        E, X = arr(ema, (n,), np.int64), arr(x, (n,), np.int64)
+        E[...] = (dec * E.astype(F32) + rest * X.astype(F32)).astype(F32).astype(np.int64)
+    else:
+        E, X = arr(ema, (n,)), arr(x, (n,))
+        E[...] = (dec * E + rest * X).astype(F32)
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("ehgr_")}
 
 
