@@ -47,21 +47,25 @@ def _worker(rank, world, port, case, out):
         workload, backbone = case.split("-")
         resnet = backbone == "resnet50"
         sd_mode = workload == "sd"
-        if sd_mode:
+        comb = workload == "mtmmsd"
+        if comb:
+            sd0 = O.build_mtmm_sd_state(cls, "tsm", 8, seed=4)
+        elif sd_mode:
             sd0 = O.build_sd_state(cls, "tsm", 8, seed=4)
         else:
             sd0 = (O.build_resnet_mtmm_state(cls, "tsm", seed=4) if resnet else O.build_mtmm_state(cls, "tsm", 8, seed=4))
         common = dict(base_model=backbone, pretrain=None, dropout=0.5, partial_bn=False, is_shift=True, shift_div=8,
                       consensus_type='avg', fc_lr5=True, img_feature_dim=224, temporal_module='tsm', print_spec=False)
         with contextlib.redirect_stdout(io.StringIO()):
-            model = (E.tsn_sd.TSN(cls, T, 'RGB', **common) if sd_mode else
+            model = (E.tsn_mtmm_sd.TSN(cls, T, 'RGB', modal='rgb_depth', **common) if comb else
+                     E.tsn_sd.TSN(cls, T, 'RGB', **common) if sd_mode else
                      E.tsn_mtmm.TSN(cls, T, 'RGB', modal='rgb_depth', **common))
         model.load_state_dict(sd0, strict=True)
         model.train()
         for d in model.modules():
             if isinstance(d, torch.nn.Dropout):
                 d.eval()
-        step_cls = E.train_step.SDTrainStep if sd_mode else E.train_step.MTMMTrainStep
+        step_cls = (E.train_step.MTMMSDTrainStep if comb else E.train_step.SDTrainStep if sd_mode else E.train_step.MTMMTrainStep)
         step = step_cls(model, lr=lr, momentum=0.9, weight_decay=0.0, compute_dtype=torch.float32, n_buckets=3)
         assert step.buckets.world == world
         before = {k: p.detach().clone() for k, p in model.named_parameters()}
@@ -74,6 +78,14 @@ def _worker(rank, world, port, case, out):
         for r in range(world):
             sd64 = O.clone_state(sd0, dtype=torch.float64)
             x5, dep, lab = shards[r][0].double(), shards[r][1].double(), shards[r][2]
+            if comb:
+                # train_mtmm_sd.py:240-293 at this resolution; beta scaled by the world size as in the SD step
+                oo = O.mtmm_sd_forward(x5, sd64, T, "tsm", 8, True)
+                gt = F.interpolate(dep.view(-1, 1, size, size), (size // 4, size // 4), mode='bilinear')
+                (O.sd_loss(oo[:4], oo[4:8], lab, 0.1, 1e-6 * world, 3.0)[0] + 0.9 * 0.01 * F.mse_loss(oo[9], gt)).backward()
+                g = {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.grad is not None}
+                mean_grad = g if mean_grad is None else {k: mean_grad[k] + g[k] for k in g}
+                continue
             if sd_mode:
                 # SDTrainStep scales beta by the world size: the feature term is a SUM over the local batch (train_sd.py:191-193)
                 oo = O.sd_forward(x5, sd64, T, "tsm", 8, True)
@@ -93,7 +105,11 @@ def _worker(rank, world, port, case, out):
             g = {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.grad is not None}
             mean_grad = g if mean_grad is None else {k: mean_grad[k] + g[k] for k in g}
         mean_grad = {k: v / world for k, v in mean_grad.items()}
-        check_grads_up_to_relu_flips(model.named_parameters(), mean_grad)
+        # parameters outside the loss (local_decoder of the combined stage: its output is returned, not trained on) keep a
+        # zero gradient and are left where they are
+        used = [(k, p) for k, p in model.named_parameters() if k in mean_grad]
+        assert all(float(p.grad.abs().sum()) == 0.0 for k, p in model.named_parameters() if k not in mean_grad)
+        check_grads_up_to_relu_flips(used, mean_grad)
         # first SGD step (zero momentum buffer, no weight decay): p' = p - lr * lr_mult * averaged gradient
         mult = {id(p): g['lr_mult'] for g in model.get_optim_policies() for p in g['params']}
         for k, p in model.named_parameters():
@@ -109,7 +125,7 @@ def _worker(rank, world, port, case, out):
         raise
 
 
-@pytest.mark.parametrize("case", ["mtmm-mobilenetv2", "mtmm-resnet50", "sd-mobilenetv2"])
+@pytest.mark.parametrize("case", ["mtmm-mobilenetv2", "mtmm-resnet50", "sd-mobilenetv2", "mtmmsd-mobilenetv2"])
 def test_data_parallel_step_world2_gloo(case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
