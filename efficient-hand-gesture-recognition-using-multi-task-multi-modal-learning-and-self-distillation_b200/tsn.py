@@ -195,7 +195,8 @@ class TSN(nn.Module):
             from . import fused
             fmap = fused.mobilenet_v2_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))
             return fused.classifier_head(self, fmap)
-        if _lib.on_gpu(input) and not no_reshape and self.reshape and self._fused_resnet():
+        if (_lib.on_gpu(input) and not no_reshape and self.reshape and not (self.is_shift and self.temporal_pool)
+                and self._fused_resnet()):
             # N3: torchvision Bottleneck ResNet (+ TemporalShift on conv1) on the library's kernels (resnet_ops.py)
             from . import fused, resnet_ops
             fmap = resnet_ops.resnet_features(self.base_model, input.view((-1, 3 * self.new_length) + input.size()[-2:]))
