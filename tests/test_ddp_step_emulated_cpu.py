@@ -25,7 +25,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, case, out):
+CASES = ("mtmm-mobilenetv2", "mtmm-resnet50", "sd-mobilenetv2", "mtmmsd-mobilenetv2")
+
+
+def _worker(rank, world, port, out):
     try:
         here = os.path.dirname(os.path.abspath(__file__))
         for p in (here, os.path.dirname(here)):
@@ -44,6 +47,22 @@ def _worker(rank, world, port, case, out):
         E._lib.stream_ptr = lambda device=None: 0
         E._lib.on_gpu = lambda t: True         # the wrappers take the library's path for host tensors
         T, cls, size, lr = 2, 5, 64, 0.01
+        for case in CASES:                     # one pair of processes runs every case (spawn + import cost paid once)
+            try:
+                _run_case(E, O, check_grads_up_to_relu_flips, case, rank, world, T, cls, size, lr)
+            except Exception as e:
+                raise RuntimeError(f"case {case}: {e!r}") from e
+        if rank == 0:
+            out.put("ok")
+        dist.destroy_process_group()
+    except Exception as e:      # surface the failure in the parent
+        import traceback
+        out.put("rank %d: %s\n%s" % (rank, e, traceback.format_exc()))
+        raise
+
+
+def _run_case(E, O, check_grads_up_to_relu_flips, case, rank, world, T, cls, size, lr):
+    if True:                                   # (indentation kept from the single-case form)
         workload, backbone = case.split("-")
         resnet = backbone == "resnet50"
         sd_mode = workload == "sd"
@@ -115,22 +134,14 @@ def _worker(rank, world, port, case, out):
         for k, p in model.named_parameters():
             want = before[k] - lr * mult[id(p)] * p.grad
             assert torch.allclose(p.detach(), want, rtol=1e-5, atol=1e-7), k
-        assert step.ranks_in_sync()
-        if rank == 0:
-            out.put("ok")
-        dist.destroy_process_group()
-    except Exception as e:      # surface the failure in the parent
-        import traceback
-        out.put("rank %d: %s\n%s" % (rank, e, traceback.format_exc()))
-        raise
+        assert step.ranks_in_sync(), case
 
 
-@pytest.mark.parametrize("case", ["mtmm-mobilenetv2", "mtmm-resnet50", "sd-mobilenetv2", "mtmmsd-mobilenetv2"])
-def test_data_parallel_step_world2_gloo(case):
+def test_data_parallel_steps_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
